@@ -1,0 +1,120 @@
+/* saeb200 -- C ABI of the B200-native SAE encode / TopK / sparse-decode / activation-cache engine.
+ *
+ * Drop-in boundary for the hot path of EvolvingLMMs-Lab/multimodal-sae.  The reference has no FFI: its seam is the
+ * Python function pointer `decoder_impl(top_indices, top_acts, W_dec_T)` (sae_auto_interp/sae/utils.py:107-129) and
+ * the methods of `sae_auto_interp.sae.Sae` (sae/sae.py:172-247).  Each entry point below names the reference code it
+ * replaces; `INTEGRATION.md` shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - the caller owns every buffer including workspaces (query the size first);
+ *   - functions only enqueue work on `stream` (a cudaStream_t passed as void*); no allocation, no host sync;
+ *   - return 0 on success, negative on error (-1 bad argument, -2 CUDA error); `saeb_last_error()` returns a
+ *     thread-local message; nothing throws across the boundary;
+ *   - dtype codes: SAEB_F32 = 0, SAEB_BF16 = 1, SAEB_F16 = 2;
+ *   - TopK indices are int64 like `EncoderOutput.top_indices` (sae/sae.py:17-22).
+ * There is no CPU fallback: without an sm_100a device the compute entry points fail with -2.
+ */
+#ifndef SAEB200_H
+#define SAEB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAEB_F32 0
+#define SAEB_BF16 1
+#define SAEB_F16 2
+
+/* Library version (major*10000 + minor*100 + patch). */
+int saeb_version(void);
+/* Thread-local description of the last error returned on this thread ("" if none). */
+const char* saeb_last_error(void);
+/* Number of kernel launches enqueued by this library in this process (bench.py's `gpu_launches` claim). */
+long long saeb_launch_count(void);
+/* Tuning knobs.  "cta_pair": 2 (default) = CTA pairs with tcgen05 cta_group::2 (256-row MMA tiles), 1 = single-CTA
+ * tiles.  Results are identical; only throughput differs. */
+int saeb_set_option(const char* name, int value);
+
+/* ---- one-time weight repack -------------------------------------------------------------------------------
+ * Reference parameters: `encoder.weight [N,d]`, `encoder.bias [N]`, `b_dec [d]` fp32 (sae/sae.py:59-66, loaded by
+ * Sae.load_from_disk sae/sae.py:126-148).  Produces `planes` bf16 planes of W_enc (1: bf16(W); 2: hi + lo, the
+ * parity-grade mode) followed by the folded bias b_enc - W_enc b_dec (sae/sae.py:174-175 rewritten as
+ * W x + (b_enc - W b_dec)).  Layout of `packed`: [planes][N][d] bf16, then [N] fp32 at
+ * saeb_packed_bias_offset(). */
+size_t saeb_packed_weights_bytes(int64_t N, int64_t d, int planes);
+size_t saeb_packed_bias_offset(int64_t N, int64_t d, int planes);
+int saeb_pack_weights(const float* W_enc, const float* b_enc, const float* b_dec, int64_t N, int64_t d, int planes,
+                      void* packed, void* stream);
+
+/* ---- fused encode + TopK ------------------------------------------------------------------------------------
+ * Replaces Sae.encode = select_topk(pre_acts(x)) (sae/sae.py:172-185) and the cache path's
+ * `pre_acts -> torch.topk` (features/cache.py:210-213, :407-412) without materialising the dense [T,N] latents.
+ *   x            [T, ld_x] activations (bf16 consumed in place; f16 / f32 are split into two bf16 planes in the
+ *                workspace); d % 8 == 0, ld_x % 8 == 0, 16-byte aligned
+ *   clamp_feature / clamp_value: steering (features/steering.py:113-114): that latent is forced to clamp_value
+ *                before TopK; pass -1 to disable
+ *   out_vals     [T,k] f32, out_idx [T,k] i64, each row ordered by (value desc, index asc); rows with fewer than k
+ *                positive pre-activations are padded with value 0 on distinct unused indices
+ *   dense_out    optional [T, ld_dense] f32: relu(pre-activations) for callers that need Sae.pre_acts
+ *                (sae/sae.py:172-177); out_vals/out_idx may be NULL when only dense_out is wanted. */
+size_t saeb_encode_topk_workspace_bytes(int64_t T, int64_t d, int64_t N, int k, int x_dtype);
+int saeb_encode_topk(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed, int planes, int64_t d,
+                     int64_t N, int k, int64_t clamp_feature, float clamp_value, float* out_vals, int64_t* out_idx,
+                     float* dense_out, int64_t ld_dense, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- sparse decode ------------------------------------------------------------------------------------------
+ * Replaces decoder_impl (sae/utils.py:107-129: triton_sparse_dense_matmul sae/kernels.py:178-284, or eager_decode
+ * sae/utils.py:108-111) + `+ b_dec` (sae/sae.py:191) + the steering hook's output cast (features/steering.py:116-118).
+ *   out[t,:] = sum_j vals[t,j] * W_dec[idx[t,j],:] + b_dec        (fp32 accumulate in j order, zeros skipped)
+ *   W_dec [N,d] contiguous (the reference passes the transposed view W_dec.mT; pass the parameter itself),
+ *   w_dtype SAEB_F32 (parity grade) or SAEB_BF16; b_dec may be NULL; out_dtype any of the three codes.
+ *   If sq_err != NULL, x (same shape as out) is read and sum((out - x)^2) is ADDED to *sq_err (double) -- the
+ *   numerator of the FVU (sae/sae.py:201,229).  err_flag (int, may be NULL) is set to 1 if an index is out of
+ *   range (tl.device_assert at sae/kernels.py:276). */
+int saeb_decode(const int64_t* idx, const float* vals, int64_t T, int k, const void* W_dec, int w_dtype, int64_t d,
+                int64_t N, const float* b_dec, void* out, int out_dtype, int64_t ld_out, const void* x, int x_dtype,
+                int64_t ld_x, double* sq_err, int* err_flag, void* stream);
+
+/* FVU denominator  sum((x - x.mean(0))^2)  (sae/sae.py:204); scratch = 2*d doubles. */
+int saeb_total_variance(const void* x, int x_dtype, int64_t T, int64_t d, int64_t ld_x, double* scratch, double* out,
+                        void* stream);
+
+/* ---- activation-cache extraction ----------------------------------------------------------------------------
+ * Replaces `zeros_like + scatter_` (features/cache.py:215-217) + Cache.get_nonzeros (features/cache.py:73-92).
+ * Input is TopK output of T = batch*seq_len tokens; output is the reference's `locations [nnz,3]` int64
+ * (row_offset + t / seq_len, t % seq_len, feature) in torch.nonzero order and `activations [nnz]` f32, keeping
+ * entries with |v| > threshold (1e-5 in the reference) whose feature bit is set in `filter_bitmap` (N bits packed in
+ * uint32 words, NULL = keep all; replaces torch.isin at features/cache.py:89-92).  locations/activations must hold
+ * T*k entries; *nnz_out (device int64) receives the count. */
+size_t saeb_coo_workspace_bytes(int64_t T);
+int saeb_coo_extract(const float* vals, const int64_t* idx, int64_t T, int k, float threshold,
+                     const uint32_t* filter_bitmap, int64_t seq_len, int64_t row_offset, int64_t* locations,
+                     float* activations, int64_t* nnz_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- per-feature top-activation scan ------------------------------------------------------------------------
+ * Replaces, for all features at once, TensorBuffer.__getitem__ (features/loader.py:74-90) +
+ * pool_max_activation_windows (features/constructors.py:11-85): max-pool of the TopK-masked activations over
+ * windows of ctx_len tokens and the n_top best windows per feature, ordered (score desc, window asc).
+ * saeb_scan_pool processes one chunk of tokens (at most bucket_cap windows): only features in [feat_lo, feat_hi)
+ * (this GPU's shard) are kept, local index f - feat_lo.  tok_thr (NULL or [T]) is the per-token global k-th value
+ * used under feature sharding.  saeb_scan_merge folds the buckets into the sorted per-feature lists
+ * top_vals [F,n_top] f32 / top_win [F,n_top] i64 (-1 = empty), refreshes feat_thr and clears the bucket counters.
+ * Initialise feat_thr to the activation threshold (1e-5), top_win to -1, bucket_cnt to 0. */
+int saeb_scan_pool(const float* vals, const int64_t* idx, int64_t T, int k, int ctx_len, float threshold,
+                   int64_t feat_lo, int64_t feat_hi, int64_t window_base, const float* tok_thr,
+                   const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap, int* overflow_flag,
+                   void* stream);
+int saeb_scan_merge(void* bucket, int* bucket_cnt, int bucket_cap, int64_t F, int n_top, float base_threshold,
+                    float* top_vals, int64_t* top_win, float* feat_thr, void* stream);
+/* Per-token k-th largest of R gathered per-shard top-k value lists, gathered [R][T][k] f32 (after the NCCL
+ * all-gather of local top-k values). */
+int saeb_kth_of_gathered(const float* gathered, int R, int64_t T, int k, float* tok_thr, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAEB200_H */

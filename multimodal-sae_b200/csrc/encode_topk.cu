@@ -1,0 +1,682 @@
+// Fused SAE encoder:  pre = relu(x @ W_enc^T + bias_folded)  ->  per-row TopK, dense latents never written.
+//
+// Replaces the reference chain  Sae.pre_acts (sae/sae.py:172-177, nn.Linear -> fp32 GEMM, dense [T,N] output)
+// + Sae.select_topk / torch.topk (sae/sae.py:179-181, features/cache.py:211-213).
+//
+// Structure (one persistent CTA, or CTA pair with cta_group::2, per SM):
+//   warp 0     : TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles of x and W_enc planes)
+//   warp 1     : MMA issuer     (tcgen05.mma kind::f16, fp32 accumulator 128 x 256 per CTA in TMEM, double buffered)
+//   warp 2     : TMEM allocator
+//   warps 4..7 : epilogue       (tcgen05.ld -> + folded bias -> running per-row threshold filter -> candidate list;
+//                                warp-cooperative radix-select compaction when a list fills up)
+// A work unit is (m_tile, n_split): a tile of 128*PAIR token rows swept over a contiguous range of 256-wide feature
+// tiles.  Each (row, split) produces a candidate list that is a superset of the split's top-k; `topk_merge_kernel`
+// selects the exact top-k per row with the canonical order (value desc, index asc).
+//
+// Precision: W_enc is stored as BP bf16 planes (hi, lo) whose sum reproduces fp32 W_enc to ~2^-17; x as AP planes
+// (1 for bf16 activations, which are exact; 2 for fp16/fp32 activations).  All plane products accumulate into the
+// same fp32 TMEM accumulator.  The decoder bias is folded: W(x - b_dec) + b_enc = Wx + (b_enc - W b_dec).
+#include <cuda.h>
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace saeb {
+
+constexpr int BM = 128;   // token rows per CTA
+constexpr int BN = 256;   // feature columns per MMA tile (UMMA N)
+constexpr int BK = 64;    // K elements per pipeline stage (128 bytes of bf16 = one swizzle row)
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 256;
+constexpr int SMEM_BUDGET = 232448;   // 227 KB
+constexpr int SMEM_MISC = 8192;       // barriers + tmem ptr + bias staging
+
+template <int AP, int BP, int PAIR>
+struct EncCfg {
+  static constexpr int B_ROWS = BN / PAIR;
+  static constexpr int A_PLANE = BM * BK * 2;
+  static constexpr int B_PLANE = B_ROWS * BK * 2;
+  static constexpr int STAGE = AP * A_PLANE + BP * B_PLANE;
+  static constexpr int STAGES_RAW = (SMEM_BUDGET - SMEM_MISC - 1024) / STAGE;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM = STAGES * STAGE + SMEM_MISC + 1024;
+  static_assert(STAGES >= 2, "need at least two pipeline stages");
+};
+
+struct EncodeArgs {
+  int T, d, N, k;
+  int num_m_tiles;    // ceil(T / (BM*PAIR))
+  int num_n_tiles;    // ceil(N / BN)
+  int S;              // feature-range splits per m tile
+  int num_k_blocks;   // ceil(d / BK)
+  int pass_mask;      // bit (a*BP+b) set -> issue MMA for (A plane a, B plane b)
+  int clamp_col;      // steering: column forced to clamp_val before TopK (-1 = none)
+  float clamp_val;
+  const float* bias;  // folded bias [N]
+  uint2* cand;        // [T][S][CAP] (value bits, column)
+  int* cand_cnt;      // [T][S]
+  float* dense_out;   // optional dense relu(pre) [T][ld_dense]
+  long long ld_dense;
+};
+
+// ---------------------------------------------------------------------------------------------
+// warp-cooperative compaction of one row's candidate list: keep every entry >= the k-th largest value
+// ---------------------------------------------------------------------------------------------
+template <int SLOTS>
+__device__ __forceinline__ void compact_row(uint2* buf, int cnt_in, int k, uint32_t lane, float& thr_out,
+                                            int& cnt_out) {
+  uint32_t key[SLOTS], col[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    int i = s * 32 + lane;
+    if (i < cnt_in) {
+      uint2 e = buf[i];
+      key[s] = e.x;
+      col[s] = e.y;
+    } else {
+      key[s] = 0;
+      col[s] = 0;
+    }
+  }
+  // values are strictly positive floats, so their bit patterns order like unsigned integers.
+  uint32_t prefix = 0;
+  for (int bit = 30; bit >= 0; --bit) {
+    uint32_t trial = prefix | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) c += (key[s] >= trial) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= k) prefix = trial;
+  }
+  int base = 0;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    bool keep = key[s] >= prefix && key[s] != 0;
+    uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (keep) buf[base + __popc(m & lt_mask)] = make_uint2(key[s], col[s]);
+    base += __popc(m);
+  }
+  __syncwarp();
+  thr_out = __uint_as_float(prefix);
+  cnt_out = base;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused kernel
+// ---------------------------------------------------------------------------------------------
+template <int AP, int BP, int PAIR, int SLOTS>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                   const EncodeArgs args) {
+  using Cfg = EncCfg<AP, BP, PAIR>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int CAP = 32 * SLOTS;
+  constexpr uint32_t TMEM_COLS = 512;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* misc = smem + STAGES * Cfg::STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc);   // [STAGES]
+  uint64_t* empty_bar = full_bar + STAGES;                  // [STAGES]
+  uint64_t* tfull_bar = empty_bar + STAGES;                 // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                     // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* bias_s = reinterpret_cast<float*>(misc + 1024);    // [4 warps][BN]
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const uint32_t cta_rank = (PAIR == 2) ? cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], PAIR);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], PAIR * 4);
+    }
+    fence_mbar_init();
+  }
+  if constexpr (PAIR == 2) cluster_sync_all();
+  if (warp == 2) tmem_alloc<PAIR>(tmem_ptr, TMEM_COLS);
+  tc_fence_before();
+  if constexpr (PAIR == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int cluster_id = blockIdx.x / PAIR;
+  const int num_clusters = gridDim.x / PAIR;
+  const int num_units = args.num_m_tiles * args.S;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = cluster_id; u < num_units; u += num_clusters) {
+        const int split = u % args.S, m_tile = u / args.S;
+        const int nt0 = (int)((long long)split * args.num_n_tiles / args.S);
+        const int nt1 = (int)((long long)(split + 1) * args.num_n_tiles / args.S);
+        const int m0 = (m_tile * PAIR + (int)cta_rank) * BM;
+        for (int nt = nt0; nt < nt1; ++nt) {
+          const int n0 = nt * BN + (int)cta_rank * Cfg::B_ROWS;
+          for (int kb = 0; kb < args.num_k_blocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::STAGE;
+            uint8_t* sb = sa + AP * Cfg::A_PLANE;
+            if constexpr (PAIR == 1) {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE);
+#pragma unroll
+              for (int a = 0; a < AP; ++a) tma_load_3d(sa + a * Cfg::A_PLANE, &tm_a, &full_bar[stage], kb * BK, m0, a);
+#pragma unroll
+              for (int b = 0; b < BP; ++b) tma_load_3d(sb + b * Cfg::B_PLANE, &tm_b, &full_bar[stage], kb * BK, n0, b);
+            } else {
+              if (leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE * 2);
+              else mbar_arrive_cluster(&full_bar[stage], 0);
+#pragma unroll
+              for (int a = 0; a < AP; ++a)
+                tma_load_3d_pair(sa + a * Cfg::A_PLANE, &tm_a, &full_bar[stage], kb * BK, m0, a);
+#pragma unroll
+              for (int b = 0; b < BP; ++b)
+                tma_load_3d_pair(sb + b * Cfg::B_PLANE, &tm_b, &full_bar[stage], kb * BK, n0, b);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM * PAIR, BN, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t tile_iter = 0;
+      for (int u = cluster_id; u < num_units; u += num_clusters) {
+        const int split = u % args.S;
+        const int nt0 = (int)((long long)split * args.num_n_tiles / args.S);
+        const int nt1 = (int)((long long)(split + 1) * args.num_n_tiles / args.S);
+        for (int nt = nt0; nt < nt1; ++nt, ++tile_iter) {
+          const uint32_t acc_stage = tile_iter & 1, acc_phase = (tile_iter >> 1) & 1;
+          mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc_stage * BN;
+          for (int kb = 0; kb < args.num_k_blocks; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
+            const uint32_t sb = sa + AP * Cfg::A_PLANE;
+            uint32_t first = (kb == 0) ? 1u : 0u;
+#pragma unroll
+            for (int a = 0; a < AP; ++a) {
+#pragma unroll
+              for (int b = 0; b < BP; ++b) {
+                if (!((args.pass_mask >> (a * BP + b)) & 1)) continue;
+                const uint64_t da = make_smem_desc_sw128(sa + a * Cfg::A_PLANE);
+                const uint64_t db = make_smem_desc_sw128(sb + b * Cfg::B_PLANE);
+#pragma unroll
+                for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                  // advance 32 bytes (16 bf16) along K inside the 128B swizzle row: +2 in 16-byte units
+                  umma_f16<PAIR>(tmem_d, da + 2 * ks, db + 2 * ks, idesc, first ? 0u : 1u);
+                  first = 0;
+                }
+              }
+            }
+            umma_commit<PAIR>(&empty_bar[stage]);
+            if (kb == args.num_k_blocks - 1) umma_commit<PAIR>(&tfull_bar[acc_stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: bias + ReLU + running TopK filter =====================
+    const uint32_t q = warp & 3;                 // TMEM lane quarter owned by this warp
+    float* bias_w = bias_s + q * BN;
+    const uint32_t full = 0xffffffffu;
+    uint32_t tile_iter = 0;
+    for (int u = cluster_id; u < num_units; u += num_clusters) {
+      const int split = u % args.S, m_tile = u / args.S;
+      const int nt0 = (int)((long long)split * args.num_n_tiles / args.S);
+      const int nt1 = (int)((long long)(split + 1) * args.num_n_tiles / args.S);
+      const int row = (m_tile * PAIR + (int)cta_rank) * BM + (int)(q * 32 + lane);
+      const bool valid = row < args.T;
+      const bool do_topk = args.cand != nullptr;
+      uint2* cand = do_topk && valid ? args.cand + ((size_t)row * args.S + split) * CAP : nullptr;
+      float thr = (valid && do_topk) ? 0.0f : __int_as_float(0x7f800000);   // +inf: never append
+      int cnt = 0;
+      for (int nt = nt0; nt < nt1; ++nt, ++tile_iter) {
+        const uint32_t acc_stage = tile_iter & 1, acc_phase = (tile_iter >> 1) & 1;
+        const int n_base = nt * BN;
+        // stage this tile's folded bias (columns >= N get -inf so they can never be selected)
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i) {
+          int c = n_base + i * 32 + lane;
+          bias_w[i * 32 + lane] = (c < args.N) ? __ldg(args.bias + c) : __int_as_float(0xff800000);
+        }
+        __syncwarp();
+        mbar_wait(&tfull_bar[acc_stage], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc_stage * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (c == BN / 32 - 1) {
+            // accumulator fully read: hand the TMEM stage back to the MMA issuer (leader CTA's barrier)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (PAIR == 1) mbar_arrive(&tempty_bar[acc_stage]);
+              else mbar_arrive_cluster(&tempty_bar[acc_stage], 0);
+            }
+          }
+          const int col0 = n_base + c * 32;
+          const int cj = args.clamp_col - col0;   // in [0,32) iff the clamped column is in this chunk
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 b4 = *reinterpret_cast<const float4*>(bias_w + c * 32 + j);
+            v[j + 0] = __uint_as_float(r[j + 0]) + b4.x;
+            v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+            v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
+            v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+          }
+          if (cj >= 0 && cj < 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j == cj) v[j] = args.clamp_val;
+          }
+          if (args.dense_out != nullptr && valid) {
+            float* o = args.dense_out + (size_t)row * args.ld_dense + col0;
+            if (col0 + 32 <= args.N) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) =
+                    make_float4(fmaxf(v[j], 0.f), fmaxf(v[j + 1], 0.f), fmaxf(v[j + 2], 0.f), fmaxf(v[j + 3], 0.f));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < args.N) o[j] = fmaxf(v[j], 0.f);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (v[j] > thr) {
+              cand[cnt] = make_uint2(__float_as_uint(v[j]), (uint32_t)(col0 + j));
+              ++cnt;
+            }
+          }
+          // compaction when a list could overflow during the next chunk
+          uint32_t need = __ballot_sync(full, cnt > CAP - 32);
+          while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const int src_cnt = __shfl_sync(full, cnt, src);
+            const unsigned long long p = __shfl_sync(full, (unsigned long long)(uintptr_t)cand, src);
+            float nthr;
+            int ncnt;
+            __syncwarp();
+            compact_row<SLOTS>(reinterpret_cast<uint2*>((uintptr_t)p), src_cnt, args.k, lane, nthr, ncnt);
+            if ((int)lane == src) {
+              thr = nthr;
+              cnt = ncnt;
+            }
+          }
+        }
+      }
+      if (do_topk && valid) args.cand_cnt[(size_t)row * args.S + split] = cnt;
+    }
+  }
+
+  // ===================== teardown =====================
+  tc_fence_before();
+  if constexpr (PAIR == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<PAIR>(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// merge: exact top-k per row over the S candidate lists; canonical order (value desc, index asc)
+// ---------------------------------------------------------------------------------------------
+__global__ void topk_merge_kernel(const uint2* __restrict__ cand, const int* __restrict__ cand_cnt, int T, int S,
+                                  int CAP, int k, int kp2, int N, int max_entries, float* __restrict__ out_vals,
+                                  long long* __restrict__ out_idx) {
+  extern __shared__ uint2 msm[];
+  const int warps_per_block = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t full = 0xffffffffu;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint2* ent = msm + (size_t)warp * (max_entries + kp2);
+  uint2* sel = ent + max_entries;
+  const int row = blockIdx.x * warps_per_block + warp;
+  if (row >= T) return;
+
+  // 1. stage valid candidates
+  int M = 0;
+  for (int s = 0; s < S; ++s) {
+    const int c = cand_cnt[(size_t)row * S + s];
+    const uint2* src = cand + ((size_t)row * S + s) * CAP;
+    for (int i = lane; i < c; i += 32) ent[M + i] = src[i];
+    M += c;
+  }
+  __syncwarp();
+
+  int nsel = 0;
+  if (M <= k) {
+    for (int i = lane; i < M; i += 32) sel[i] = ent[i];
+    nsel = M;
+  } else {
+    // 2. k-th largest value
+    uint32_t prefix = 0;
+    for (int bit = 30; bit >= 0; --bit) {
+      const uint32_t trial = prefix | (1u << bit);
+      int c = 0;
+      for (int i = lane; i < M; i += 32) c += (ent[i].x >= trial) ? 1 : 0;
+      c = __reduce_add_sync(full, c);
+      if (c >= k) prefix = trial;
+    }
+    int c_gt = 0, c_eq = 0;
+    for (int i = lane; i < M; i += 32) {
+      c_gt += (ent[i].x > prefix) ? 1 : 0;
+      c_eq += (ent[i].x == prefix) ? 1 : 0;
+    }
+    c_gt = __reduce_add_sync(full, c_gt);
+    c_eq = __reduce_add_sync(full, c_eq);
+    const int need_eq = k - c_gt;   // >= 1
+    // 3. among ties at the k-th value keep the `need_eq` smallest indices
+    uint32_t idx_cut = 0xffffffffu;
+    if (c_eq > need_eq) {
+      uint32_t p2 = 0;   // largest t such that #(idx < t) < need_eq  ->  cut = the need_eq-th smallest index
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t trial = p2 | (1u << bit);
+        int c = 0;
+        for (int i = lane; i < M; i += 32) c += (ent[i].x == prefix && ent[i].y < trial) ? 1 : 0;
+        c = __reduce_add_sync(full, c);
+        if (c < need_eq) p2 = trial;
+      }
+      idx_cut = p2;
+    }
+    // 4. compact the selection
+    for (int i0 = 0; i0 < M; i0 += 32) {
+      const int i = i0 + lane;
+      bool keep = false;
+      uint2 e = make_uint2(0, 0);
+      if (i < M) {
+        e = ent[i];
+        keep = e.x > prefix || (e.x == prefix && e.y <= idx_cut);
+      }
+      const uint32_t m = __ballot_sync(full, keep);
+      if (keep) sel[nsel + __popc(m & lt_mask)] = e;
+      nsel += __popc(m);
+    }
+  }
+  for (int i = nsel + lane; i < kp2; i += 32) sel[i] = make_uint2(0u, 0xffffffffu);   // sorts last
+  __syncwarp();
+
+  // 5. bitonic sort, descending by (value bits, then ascending index)
+  for (int size = 2; size <= kp2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = lane; t < (kp2 >> 1); t += 32) {
+        const int lo = ((t / stride) * stride * 2) + (t % stride);
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const uint2 a = sel[lo], b = sel[hi];
+        // "a before b" in canonical order
+        const bool a_first = (a.x > b.x) || (a.x == b.x && a.y < b.y);
+        if (a_first != desc) {
+          sel[lo] = b;
+          sel[hi] = a;
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  // 6. rows with fewer than k positive pre-activations: pad with zeros on distinct unused indices
+  //    (torch.topk would return arbitrary zero-valued entries there; they are dropped by the cache's >1e-5 test
+  //    and contribute nothing to the decode).
+  if (nsel < k) {
+    int filled = nsel;
+    for (int base = 0; base < N && filled < k; base += 32) {
+      const uint32_t j = base + lane;
+      bool free_idx = j < (uint32_t)N;
+      for (int i = 0; i < nsel && free_idx; ++i) free_idx = sel[i].y != j;
+      const uint32_t m = __ballot_sync(full, free_idx);
+      const int pos = filled + __popc(m & lt_mask);
+      if (free_idx && pos < k) sel[pos] = make_uint2(0u, j);
+      filled += __popc(m);
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < k; i += 32) {
+    out_vals[(size_t)row * k + i] = __uint_as_float(sel[i].x);
+    out_idx[(size_t)row * k + i] = (long long)sel[i].y;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// 3-D map over [planes][rows][cols] of 16-bit elements, box = (64 cols, box_rows rows, 1 plane), 128B swizzle.
+static int make_map(CUtensorMap* map, const void* base, long long cols, long long rows, long long planes,
+                    long long row_stride_bytes, long long plane_stride_bytes, int box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  SAEB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)planes};
+  cuuint64_t gstr[2] = {(cuuint64_t)row_stride_bytes, (cuuint64_t)plane_stride_bytes};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SAEB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_num_sms;
+}
+
+int cap_for_k(int k) { return k <= 128 ? 256 : (k <= 256 ? 512 : 1024); }
+
+// how the feature range is split so that (m tiles x splits) fills the machine
+static int choose_splits(int num_m_tiles, int num_n_tiles, int num_clusters, int cap) {
+  int S;
+  if (num_m_tiles >= num_clusters) S = 2;
+  else S = (num_clusters + num_m_tiles - 1) / num_m_tiles;
+  if (S > num_n_tiles) S = num_n_tiles;
+  const int s_max = (200 * 1024) / (cap * 8);   // merge kernel stages all candidates of a row in shared memory
+  if (S > s_max) S = s_max;
+  if (S < 1) S = 1;
+  return S;
+}
+
+struct EncodePlan {
+  int pair, S, cap, num_m_tiles, num_n_tiles, grid;
+  size_t cand_bytes, cnt_bytes;
+};
+
+static EncodePlan make_plan(long long T, long long N, int k, int pair) {
+  EncodePlan p;
+  p.pair = pair;
+  p.cap = cap_for_k(k);
+  p.num_m_tiles = (int)((T + BM * pair - 1) / (BM * pair));
+  p.num_n_tiles = (int)((N + BN - 1) / BN);
+  const int sms = num_sms() > 0 ? num_sms() : 148;
+  const int clusters = sms / pair;
+  p.S = choose_splits(p.num_m_tiles, p.num_n_tiles, clusters, p.cap);
+  int units = p.num_m_tiles * p.S;
+  int use = units < clusters ? units : clusters;
+  p.grid = use * pair;
+  p.cand_bytes = (size_t)T * p.S * p.cap * sizeof(uint2);
+  p.cnt_bytes = (((size_t)T * p.S * sizeof(int)) + 255) & ~(size_t)255;
+  return p;
+}
+
+static int g_cta_pair = 0;   // 0 = not initialised (env SAEB_CTA_PAIR or default 2)
+static int default_pair() {
+  if (g_cta_pair == 0) {
+    const char* e = getenv("SAEB_CTA_PAIR");
+    g_cta_pair = (e && e[0] == '1') ? 1 : 2;
+  }
+  return g_cta_pair;
+}
+int set_cta_pair(int v) {
+  if (v != 1 && v != 2) {
+    set_error("cta_pair must be 1 or 2");
+    return -1;
+  }
+  g_cta_pair = v;
+  return 0;
+}
+
+size_t encode_workspace_bytes(long long T, long long d, long long N, int k) {
+  // worst case over both pair modes so that a caller-sized workspace is always enough
+  EncodePlan p1 = make_plan(T, N, k, 1), p2 = make_plan(T, N, k, 2);
+  size_t a = p1.cand_bytes + p1.cnt_bytes, b = p2.cand_bytes + p2.cnt_bytes;
+  return (a > b ? a : b) + 1024;
+}
+
+template <int AP, int BP, int PAIR, int SLOTS>
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const EncodeArgs& args, int grid,
+                      cudaStream_t stream) {
+  using Cfg = EncCfg<AP, BP, PAIR>;
+  auto kern = encode_topk_kernel<AP, BP, PAIR, SLOTS>;
+  SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SAEB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, args));
+  return 0;
+}
+
+template <int AP, int BP, int PAIR>
+static int launch_slots(const CUtensorMap& ta, const CUtensorMap& tb, const EncodeArgs& args, int grid, int cap,
+                        cudaStream_t stream) {
+  switch (cap) {
+    case 256: return launch_cfg<AP, BP, PAIR, 8>(ta, tb, args, grid, stream);
+    case 512: return launch_cfg<AP, BP, PAIR, 16>(ta, tb, args, grid, stream);
+    case 1024: return launch_cfg<AP, BP, PAIR, 32>(ta, tb, args, grid, stream);
+  }
+  set_error("unsupported candidate capacity %d", cap);
+  return -1;
+}
+
+template <int PAIR>
+static int launch_planes(int ap, int bp, const CUtensorMap& ta, const CUtensorMap& tb, const EncodeArgs& args,
+                         int grid, int cap, cudaStream_t stream) {
+  if (ap == 1 && bp == 1) return launch_slots<1, 1, PAIR>(ta, tb, args, grid, cap, stream);
+  if (ap == 1 && bp == 2) return launch_slots<1, 2, PAIR>(ta, tb, args, grid, cap, stream);
+  if (ap == 2 && bp == 1) return launch_slots<2, 1, PAIR>(ta, tb, args, grid, cap, stream);
+  if (ap == 2 && bp == 2) return launch_slots<2, 2, PAIR>(ta, tb, args, grid, cap, stream);
+  set_error("unsupported plane counts AP=%d BP=%d", ap, bp);
+  return -1;
+}
+
+// x_planes: [ap][T][ld_x] bf16 (ap==1: the caller's bf16 activations in place)
+// w_planes: [bp][N][d] bf16; bias: folded bias [N]
+int encode_topk_launch(const void* x_planes, int ap, long long T, long long ld_x, long long x_plane_stride,
+                       const void* w_planes, int bp, const float* bias, long long d, long long N, int k,
+                       long long clamp_feature, float clamp_value, float* out_vals, long long* out_idx,
+                       float* dense_out, long long ld_dense, void* workspace, size_t workspace_bytes, int pass_mask,
+                       cudaStream_t stream) {
+  SAEB_REQUIRE(T > 0 && d > 0 && N > 0, "empty problem T=%lld d=%lld N=%lld", T, d, N);
+  SAEB_REQUIRE(d % 8 == 0 && ld_x % 8 == 0, "d and ld_x must be multiples of 8 (16-byte TMA strides)");
+  SAEB_REQUIRE(k >= 1 && k <= 512 && k <= N, "k=%d out of range (1..min(512,N))", k);
+  SAEB_REQUIRE(T < (1ll << 31) && N < (1ll << 31), "T/N too large");
+  SAEB_REQUIRE((reinterpret_cast<uintptr_t>(x_planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_planes) & 15) == 0,
+               "x / packed weights must be 16-byte aligned");
+  const int pair = default_pair();
+  EncodePlan plan = make_plan(T, N, k, pair);
+  const bool do_topk = out_vals != nullptr;
+  if (do_topk)
+    SAEB_REQUIRE(workspace != nullptr && workspace_bytes >= plan.cand_bytes + plan.cnt_bytes,
+                 "workspace too small: have %zu need %zu", workspace_bytes, plan.cand_bytes + plan.cnt_bytes);
+
+  CUtensorMap ta, tb;
+  int rc = make_map(&ta, x_planes, d, T, ap, ld_x * 2, x_plane_stride * 2, BM);
+  if (rc) return rc;
+  rc = make_map(&tb, w_planes, d, N, bp, d * 2, N * d * 2, BN / pair);
+  if (rc) return rc;
+
+  EncodeArgs args;
+  args.T = (int)T; args.d = (int)d; args.N = (int)N; args.k = k;
+  args.num_m_tiles = plan.num_m_tiles;
+  args.num_n_tiles = plan.num_n_tiles;
+  args.S = plan.S;
+  args.num_k_blocks = (int)((d + BK - 1) / BK);
+  args.pass_mask = pass_mask;
+  args.clamp_col = (int)clamp_feature;
+  args.clamp_val = clamp_value;
+  args.bias = bias;
+  args.cand_cnt = do_topk ? reinterpret_cast<int*>(workspace) : nullptr;
+  args.cand = do_topk ? reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(workspace) + plan.cnt_bytes) : nullptr;
+  args.dense_out = dense_out;
+  args.ld_dense = ld_dense;
+
+  rc = (pair == 2) ? launch_planes<2>(ap, bp, ta, tb, args, plan.grid, plan.cap, stream)
+                   : launch_planes<1>(ap, bp, ta, tb, args, plan.grid, plan.cap, stream);
+  if (rc) return rc;
+
+  if (do_topk) {
+    int kp2 = 1;
+    while (kp2 < k) kp2 <<= 1;
+    if (kp2 < 2) kp2 = 2;
+    const int max_entries = plan.S * plan.cap;
+    const size_t per_warp = (size_t)(max_entries + kp2) * sizeof(uint2);
+    int wpb = (int)((200 * 1024) / per_warp);
+    if (wpb > 8) wpb = 8;
+    SAEB_REQUIRE(wpb >= 1, "merge: candidate set too large for shared memory");
+    const size_t smem = per_warp * wpb;
+    SAEB_CHECK_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = (int)((T + wpb - 1) / wpb);
+    topk_merge_kernel<<<blocks, wpb * 32, smem, stream>>>(args.cand, args.cand_cnt, (int)T, plan.S, plan.cap, k, kp2,
+                                                         (int)N, max_entries, out_vals, out_idx);
+    SAEB_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace saeb

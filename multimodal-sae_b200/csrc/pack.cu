@@ -1,0 +1,89 @@
+// One-time weight repack and activation plane split.
+//
+// reference parameters (sae/sae.py:59-66): encoder.weight [N,d] fp32, encoder.bias [N], W_dec [N,d], b_dec [d].
+//   W planes : W = bf16(W) + bf16(W - bf16(W)) + O(2^-17 |W|)          -> [BP][N][d] bf16
+//   bias     : W (x - b_dec) + b_enc = W x + (b_enc - W b_dec)         -> [N] fp32 (dot product in fp64)
+// fp16 / fp32 activations are split into two bf16 planes the same way (fp16 splits exactly: 11 = 8 + 3 bits);
+// bf16 activations (the cache path, launch/cache/cache_image.py:36-39) are consumed in place.
+#include "common.cuh"
+
+namespace saeb {
+
+__global__ void pack_w_kernel(const float* __restrict__ W, long long n_elems, int planes,
+                              __nv_bfloat16* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n_elems; i += stride) {
+    const float4 w = *reinterpret_cast<const float4*>(W + i);
+    const float f[4] = {w.x, w.y, w.z, w.w};
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hi[j] = __float2bfloat16_rn(f[j]);
+      lo[j] = __float2bfloat16_rn(f[j] - __bfloat162float(hi[j]));
+    }
+    *reinterpret_cast<uint2*>(out + i) = *reinterpret_cast<uint2*>(hi);
+    if (planes > 1) *reinterpret_cast<uint2*>(out + n_elems + i) = *reinterpret_cast<uint2*>(lo);
+  }
+}
+
+// one warp per feature row: bias_f[n] = b_enc[n] - sum_i W[n,i] * b_dec[i]  (fp64 accumulate)
+__global__ void fold_bias_kernel(const float* __restrict__ W, const float* __restrict__ b_enc,
+                                 const float* __restrict__ b_dec, long long N, long long d,
+                                 float* __restrict__ out) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  double acc = 0.0;
+  for (long long i = lane; i < d; i += 32) acc += (double)W[row * d + i] * (double)b_dec[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[row] = (float)((double)b_enc[row] - acc);
+}
+
+template <typename Tin>
+__global__ void split_x_kernel(const Tin* __restrict__ x, long long T, long long d, long long ld_x,
+                               __nv_bfloat16* __restrict__ out, long long plane_stride) {
+  const long long total = T * d;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / d, c = i - r * d;
+    const float f = (float)x[r * ld_x + c];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(f);
+    out[i] = hi;
+    out[plane_stride + i] = __float2bfloat16_rn(f - __bfloat162float(hi));
+  }
+}
+
+int pack_weights_launch(const float* W_enc, const float* b_enc, const float* b_dec, long long N, long long d,
+                        int planes, void* w_planes, float* bias, cudaStream_t stream) {
+  SAEB_REQUIRE(N > 0 && d > 0 && d % 8 == 0, "pack: need N>0 and d a positive multiple of 8 (got N=%lld d=%lld)", N, d);
+  SAEB_REQUIRE(planes == 1 || planes == 2, "pack: planes must be 1 or 2");
+  const long long n = N * d;
+  int blocks = (int)((n / 4 + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_w_kernel<<<blocks, 256, 0, stream>>>(W_enc, n, planes, reinterpret_cast<__nv_bfloat16*>(w_planes));
+  SAEB_CHECK_CUDA(cudaGetLastError());
+  fold_bias_kernel<<<(int)((N + 7) / 8), 256, 0, stream>>>(W_enc, b_enc, b_dec, N, d, bias);
+  SAEB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int split_x_launch(const void* x, int x_dtype, long long T, long long d, long long ld_x, void* out,
+                   cudaStream_t stream) {
+  const long long total = T * d;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (x_dtype == DT_F32)
+    split_x_kernel<float><<<blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(x), T, d, ld_x, o, total);
+  else if (x_dtype == DT_F16)
+    split_x_kernel<__half><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __half*>(x), T, d, ld_x, o, total);
+  else {
+    set_error("split_x: unsupported dtype %d", x_dtype);
+    return -1;
+  }
+  SAEB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace saeb

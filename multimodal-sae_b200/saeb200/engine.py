@@ -1,0 +1,303 @@
+"""Torch-facing wrappers over the C ABI: PyTorch owns device memory and streams, the library does the math.
+
+Every function requires CUDA tensors and raises otherwise -- there is deliberately no CPU / eager fallback.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _capi
+from ._capi import SaebError, check
+
+_DT = {torch.float32: _capi.F32, torch.bfloat16: _capi.BF16, torch.float16: _capi.F16}
+ACT_THRESHOLD = 1e-5  # reference features/cache.py:80-81
+
+
+def _code(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise SaebError(f"unsupported dtype {t.dtype}") from None
+
+
+def _need_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise SaebError("saeb200 engine needs CUDA tensors: there is no CPU fallback "
+                            f"(got a tensor on {t.device})")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+_ws_cache = {}
+
+
+def _workspace(device: torch.device, nbytes: int, tag: str = "enc") -> torch.Tensor:
+    key = (device.index, tag)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = None
+        _ws_cache.pop(key, None)
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def release_workspaces() -> None:
+    _ws_cache.clear()
+
+
+@dataclass
+class PackedEncoder:
+    """Device-resident repack of (encoder.weight, encoder.bias, b_dec): bf16 planes + folded bias."""
+
+    blob: torch.Tensor  # uint8
+    num_latents: int
+    d_in: int
+    planes: int
+
+    @staticmethod
+    def pack(W_enc: torch.Tensor, b_enc: torch.Tensor, b_dec: torch.Tensor, planes: int = 2) -> "PackedEncoder":
+        _need_cuda(W_enc, b_enc, b_dec)
+        L = _capi.lib()
+        W = W_enc.detach().to(torch.float32).contiguous()
+        be = b_enc.detach().to(torch.float32).contiguous()
+        bd = b_dec.detach().to(torch.float32).contiguous()
+        N, d = W.shape
+        nbytes = L.saeb_packed_weights_bytes(N, d, planes)
+        blob = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
+        with torch.cuda.device(W.device):
+            check(L.saeb_pack_weights(W.data_ptr(), be.data_ptr(), bd.data_ptr(), N, d, planes, blob.data_ptr(),
+                                      _stream()), "saeb_pack_weights")
+        return PackedEncoder(blob, N, d, planes)
+
+    def folded_bias(self) -> torch.Tensor:
+        off = _capi.lib().saeb_packed_bias_offset(self.num_latents, self.d_in, self.planes)
+        return self.blob[off:off + 4 * self.num_latents].view(torch.float32)
+
+    def plane(self, i: int) -> torch.Tensor:
+        n = self.num_latents * self.d_in * 2
+        return self.blob[i * n:(i + 1) * n].view(torch.bfloat16).view(self.num_latents, self.d_in)
+
+
+def _as_2d(x: torch.Tensor, d: int) -> torch.Tensor:
+    if x.shape[-1] != d:
+        raise SaebError(f"last dimension {x.shape[-1]} != d_in {d}")
+    x2 = x.reshape(-1, d)
+    if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 8 != 0) or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    return x2
+
+
+def encode_topk(x: torch.Tensor, enc: PackedEncoder, k: int, *, clamp_feature: int = -1, clamp_value: float = 0.0,
+                want_dense: bool = False, want_topk: bool = True
+                ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """x [..., d] (bf16 / fp16 / fp32) -> (top_acts [..., k] f32, top_indices [..., k] i64, dense [..., N] f32 | None).
+    Rows are ordered by (value desc, index asc)."""
+    _need_cuda(x, enc.blob)
+    L = _capi.lib()
+    lead = x.shape[:-1]
+    x2 = _as_2d(x, enc.d_in)
+    if x2.dtype not in _DT:
+        x2 = x2.to(torch.float32)
+    T = x2.shape[0]
+    dev = x2.device
+    vals = torch.empty((T, k), dtype=torch.float32, device=dev) if want_topk else None
+    idx = torch.empty((T, k), dtype=torch.int64, device=dev) if want_topk else None
+    dense = torch.empty((T, enc.num_latents), dtype=torch.float32, device=dev) if want_dense else None
+    if T > 0:
+        with torch.cuda.device(dev):
+            nbytes = L.saeb_encode_topk_workspace_bytes(T, enc.d_in, enc.num_latents, k, _code(x2))
+            ws = _workspace(dev, nbytes)
+            check(L.saeb_encode_topk(x2.data_ptr(), _code(x2), T, x2.stride(0) if T > 1 else enc.d_in,
+                                     enc.blob.data_ptr(), enc.planes, enc.d_in, enc.num_latents, k,
+                                     clamp_feature, float(clamp_value),
+                                     vals.data_ptr() if want_topk else None, idx.data_ptr() if want_topk else None,
+                                     dense.data_ptr() if want_dense else None, enc.num_latents,
+                                     ws.data_ptr(), ws.numel(), _stream()), "saeb_encode_topk")
+    if want_topk:
+        vals = vals.view(*lead, k)
+        idx = idx.view(*lead, k)
+    if want_dense:
+        dense = dense.view(*lead, enc.num_latents)
+    return vals, idx, dense
+
+
+def decode(top_indices: torch.Tensor, top_acts: torch.Tensor, W_dec: torch.Tensor, b_dec: Optional[torch.Tensor],
+           *, out_dtype: torch.dtype = torch.float32, x: Optional[torch.Tensor] = None,
+           sq_err: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[..., :] = sum_j acts[..., j] * W_dec[idx[..., j], :] + b_dec.  W_dec is the [N, d] parameter
+    (fp32 parity grade, or a bf16 copy).  If `x` and `sq_err` (0-dim float64) are given, sum((out-x)^2) is added
+    to sq_err."""
+    _need_cuda(top_indices, top_acts, W_dec, b_dec, x, sq_err)
+    L = _capi.lib()
+    N, d = W_dec.shape
+    if not W_dec.is_contiguous():
+        raise SaebError("W_dec must be the contiguous [N, d] parameter (not the transposed view)")
+    lead = top_indices.shape[:-1]
+    k = top_indices.shape[-1]
+    idx = top_indices.reshape(-1, k).to(torch.int64).contiguous()
+    vals = top_acts.reshape(-1, k).to(torch.float32).contiguous()
+    T = idx.shape[0]
+    out = torch.empty((T, d), dtype=out_dtype, device=idx.device)
+    if T == 0:
+        return out.view(*lead, d)
+    bd = None if b_dec is None else b_dec.detach().to(torch.float32).contiguous()
+    x2 = None
+    if x is not None and sq_err is not None:
+        x2 = _as_2d(x, d)
+        if x2.dtype not in _DT:
+            x2 = x2.to(torch.float32)
+        if x2.stride(0) % 4 != 0 and T > 1:
+            x2 = x2.contiguous()
+    err_flag = torch.zeros(1, dtype=torch.int32, device=idx.device)
+    with torch.cuda.device(idx.device):
+        check(L.saeb_decode(idx.data_ptr(), vals.data_ptr(), T, k, W_dec.data_ptr(), _code(W_dec), d, N,
+                            None if bd is None else bd.data_ptr(), out.data_ptr(), _DT[out_dtype], d,
+                            None if x2 is None else x2.data_ptr(), 0 if x2 is None else _code(x2),
+                            0 if x2 is None else (x2.stride(0) if T > 1 else d),
+                            None if (sq_err is None or x2 is None) else sq_err.data_ptr(), err_flag.data_ptr(),
+                            _stream()), "saeb_decode")
+    decode.last_err_flag = err_flag
+    return out.view(*lead, d)
+
+
+decode.last_err_flag = None
+
+
+def total_variance(x: torch.Tensor) -> torch.Tensor:
+    """sum((x - x.mean(0))**2) as a 0-dim float64 tensor (reference sae/sae.py:204)."""
+    _need_cuda(x)
+    L = _capi.lib()
+    d = x.shape[-1]
+    x2 = _as_2d(x, d)
+    if x2.dtype not in _DT:
+        x2 = x2.to(torch.float32)
+    T = x2.shape[0]
+    scratch = torch.empty(2 * d, dtype=torch.float64, device=x2.device)
+    out = torch.zeros((), dtype=torch.float64, device=x2.device)
+    with torch.cuda.device(x2.device):
+        check(L.saeb_total_variance(x2.data_ptr(), _code(x2), T, d, x2.stride(0) if T > 1 else d,
+                                    scratch.data_ptr(), out.data_ptr(), _stream()), "saeb_total_variance")
+    return out
+
+
+def make_filter_bitmap(features: torch.Tensor, num_latents: int) -> torch.Tensor:
+    """Feature-id filter (reference `torch.isin(feature, filters[module])`, features/cache.py:89-92) as N bits."""
+    words = (num_latents + 31) // 32
+    f = features.to(torch.int64).flatten()
+    bits = torch.zeros(words * 32, dtype=torch.int64, device=f.device)
+    bits[f] = 1
+    w = (bits.view(words, 32) << torch.arange(32, device=f.device, dtype=torch.int64)).sum(1)
+    return _pack_words(w)
+
+
+def _pack_words(w64: torch.Tensor) -> torch.Tensor:
+    # values in [0, 2^32): store as int32 with wraparound (bit pattern is what the kernel reads)
+    w = w64.clone()
+    w[w >= 2 ** 31] -= 2 ** 32
+    return w.to(torch.int32).contiguous()
+
+
+def coo_extract(top_acts: torch.Tensor, top_indices: torch.Tensor, seq_len: int, *, row_offset: int = 0,
+                threshold: float = ACT_THRESHOLD, filter_bitmap: Optional[torch.Tensor] = None
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """TopK output of batch*seq_len tokens -> (locations [nnz,3] i64, activations [nnz] f32) in the reference's
+    `torch.nonzero` order (features/cache.py:73-92)."""
+    _need_cuda(top_acts, top_indices, filter_bitmap)
+    L = _capi.lib()
+    k = top_acts.shape[-1]
+    vals = top_acts.reshape(-1, k).to(torch.float32).contiguous()
+    idx = top_indices.reshape(-1, k).to(torch.int64).contiguous()
+    T = vals.shape[0]
+    dev = vals.device
+    loc = torch.empty((T * k, 3), dtype=torch.int64, device=dev)
+    act = torch.empty((T * k,), dtype=torch.float32, device=dev)
+    if T == 0:
+        return loc, act
+    nnz = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, L.saeb_coo_workspace_bytes(T), "coo")
+        check(L.saeb_coo_extract(vals.data_ptr(), idx.data_ptr(), T, k, float(threshold),
+                                 None if filter_bitmap is None else filter_bitmap.data_ptr(), seq_len, row_offset,
+                                 loc.data_ptr(), act.data_ptr(), nnz.data_ptr(), ws.data_ptr(), ws.numel(),
+                                 _stream()), "saeb_coo_extract")
+    n = int(nnz.item())  # the reference synchronises here too (.cpu(), features/cache.py:52-53)
+    return loc[:n], act[:n]
+
+
+class TopActivationScan:
+    """Per-feature `n_top` best windows by max TopK-masked activation, for the features [feat_lo, feat_hi) owned by
+    this GPU.  Lists live on the device (F * n_top * 12 bytes); tokens are fed in chunks with `update`."""
+
+    def __init__(self, feat_lo: int, feat_hi: int, n_top: int, ctx_len: int, device, *, bucket_cap: int = 256,
+                 threshold: float = ACT_THRESHOLD):
+        self.feat_lo, self.feat_hi = int(feat_lo), int(feat_hi)
+        self.F = self.feat_hi - self.feat_lo
+        self.n_top, self.ctx_len, self.bucket_cap, self.threshold = n_top, ctx_len, bucket_cap, float(threshold)
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise SaebError("TopActivationScan needs a CUDA device: there is no CPU fallback")
+        self.device = dev
+        self.top_vals = torch.zeros((self.F, n_top), dtype=torch.float32, device=dev)
+        self.top_win = torch.full((self.F, n_top), -1, dtype=torch.int64, device=dev)
+        self.feat_thr = torch.full((self.F,), self.threshold, dtype=torch.float32, device=dev)
+        self.bucket = torch.empty((self.F, bucket_cap, 2), dtype=torch.int32, device=dev)
+        self.bucket_cnt = torch.zeros((self.F,), dtype=torch.int32, device=dev)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._pending = 0
+
+    def update(self, top_acts: torch.Tensor, top_indices: torch.Tensor, window_base: int,
+               tok_thr: Optional[torch.Tensor] = None) -> None:
+        """Feed TopK output of T tokens (T a multiple of ctx_len except for the very last chunk) whose first window
+        has global id `window_base`."""
+        L = _capi.lib()
+        k = top_acts.shape[-1]
+        vals = top_acts.reshape(-1, k)
+        idx = top_indices.reshape(-1, k)
+        T = vals.shape[0]
+        max_tok = self.bucket_cap * self.ctx_len
+        with torch.cuda.device(self.device):
+            for t0 in range(0, T, max_tok):
+                t1 = min(T, t0 + max_tok)
+                n_win = (t1 - t0 + self.ctx_len - 1) // self.ctx_len
+                if self._pending + n_win > self.bucket_cap:
+                    self.flush()
+                v, i = vals[t0:t1], idx[t0:t1]
+                check(L.saeb_scan_pool(v.data_ptr(), i.data_ptr(), t1 - t0, k, self.ctx_len, self.threshold,
+                                       self.feat_lo, self.feat_hi, window_base + t0 // self.ctx_len,
+                                       None if tok_thr is None else tok_thr[t0:t1].data_ptr(),
+                                       self.feat_thr.data_ptr(), self.bucket.data_ptr(), self.bucket_cnt.data_ptr(),
+                                       self.bucket_cap, self.overflow.data_ptr(), _stream()), "saeb_scan_pool")
+                self._pending += n_win
+
+    def flush(self) -> None:
+        if self._pending == 0:
+            return
+        L = _capi.lib()
+        with torch.cuda.device(self.device):
+            check(L.saeb_scan_merge(self.bucket.data_ptr(), self.bucket_cnt.data_ptr(), self.bucket_cap, self.F,
+                                    self.n_top, self.threshold, self.top_vals.data_ptr(), self.top_win.data_ptr(),
+                                    self.feat_thr.data_ptr(), _stream()), "saeb_scan_merge")
+        self._pending = 0
+
+    def finalize(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        self.flush()
+        return self.top_vals, self.top_win
+
+
+def kth_of_gathered(gathered: torch.Tensor) -> torch.Tensor:
+    """gathered [R, T, k] f32 (all-gathered per-shard top-k values) -> per-token global k-th value [T]."""
+    _need_cuda(gathered)
+    L = _capi.lib()
+    R, T, k = gathered.shape
+    g = gathered.contiguous()
+    out = torch.empty((T,), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        check(L.saeb_kth_of_gathered(g.data_ptr(), R, T, k, out.data_ptr(), _stream()), "saeb_kth_of_gathered")
+    return out

@@ -1,0 +1,128 @@
+"""CPU: host-side mirror of the reference interface (checkpoint format, split files, loader, constructors) against
+the golden fixtures produced by the unmodified reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+
+def test_sae_checkpoint_roundtrip_and_attribute_names(tmp_path):
+    """cfg.json + sae.safetensors with keys encoder.weight / encoder.bias / W_dec / b_dec (reference sae/sae.py:126-162)."""
+    from safetensors.torch import load_file
+    from sae_auto_interp.sae import Sae, SaeConfig
+
+    sae = Sae(16, SaeConfig(num_latents=48, k=4))
+    with torch.no_grad():
+        sae.encoder.bias.normal_()
+        sae.b_dec.normal_()
+    sae.save_to_disk(tmp_path / "layers.0")
+    keys = sorted(load_file(str(tmp_path / "layers.0" / "sae.safetensors")).keys())
+    assert keys == ["W_dec", "b_dec", "encoder.bias", "encoder.weight"]
+    cfg = json.load(open(tmp_path / "layers.0" / "cfg.json"))
+    assert cfg["d_in"] == 16 and cfg["k"] == 4 and cfg["num_latents"] == 48 and "expansion_factor" in cfg
+    back = Sae.load_from_disk(tmp_path / "layers.0")
+    for a, b in zip(sae.state_dict().values(), back.state_dict().values()):
+        assert torch.equal(a, b)
+    many = Sae.load_many(str(tmp_path), local=True)
+    assert list(many) == ["layers.0"]
+    # decoder rows are unit norm at construction (sae/sae.py:62-64)
+    np.testing.assert_allclose(torch.norm(Sae(16, SaeConfig(num_latents=48)).W_dec, dim=1).detach().numpy(), 1.0,
+                               rtol=1e-5)
+
+
+class _FakeSae:
+    class cfg:
+        num_latents = 64
+        expansion_factor = 32
+    d_in = 32
+    num_latents = 64
+
+
+class _FakeModel(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.layers = torch.nn.ModuleList([torch.nn.Identity()])
+
+
+def _cache_with_golden():
+    from sae_auto_interp.features import FeatureCache
+
+    g = np.load(os.path.join(GOLDEN, "cache_chain.npz"))
+    fc = FeatureCache(_FakeModel(), None, {"layers.0": _FakeSae()}, batch_size=2, shard_size=100)
+    fc.cache.feature_locations["layers.0"] = torch.from_numpy(g["nofilter_locations"])
+    fc.cache.feature_activations["layers.0"] = torch.from_numpy(g["nofilter_activations"])
+    return fc, g
+
+
+def test_save_splits_and_concat_match_reference_files(tmp_path):
+    """Split files are byte-for-byte the reference's tensors, including the dropped last feature id per split."""
+    from safetensors.torch import load_file
+
+    fc, g = _cache_with_golden()
+    fc.save_splits(4, str(tmp_path), rank=0)
+    fc.concate_safetensors(4, str(tmp_path))
+    files = sorted(os.listdir(tmp_path / "layers.0"))
+    assert files == sorted(g["split_files"].tolist())
+    for f in files:
+        data = load_file(str(tmp_path / "layers.0" / f))
+        assert np.array_equal(data["locations"].numpy(), g[f"split_{f}_locations"])
+        assert np.array_equal(data["activations"].numpy(), g[f"split_{f}_activations"])
+
+
+def test_fix_split_bounds_keeps_every_feature(tmp_path):
+    from safetensors.torch import load_file
+
+    fc, g = _cache_with_golden()
+    fc.fix_split_bounds = True
+    fc.save_splits(4, str(tmp_path), rank=3)
+    n = sum(load_file(str(tmp_path / "layers.0" / f))["activations"].numel()
+            for f in os.listdir(tmp_path / "layers.0"))
+    assert n == g["nofilter_activations"].shape[0]
+
+
+def test_loader_and_constructor_match_reference(tmp_path):
+    from sae_auto_interp.config import FeatureConfig
+    from sae_auto_interp.features import FeatureDataset, pool_max_activation_windows
+    from sae_auto_interp.features.features import FeatureRecord
+
+    fc, g = _cache_with_golden()
+    fc.save_splits(4, str(tmp_path), rank=0)
+    fc.concate_safetensors(4, str(tmp_path))
+    cfg = FeatureConfig(width=64, example_ctx_len=4, min_examples=0, max_examples=5, n_splits=4)
+    sel = torch.tensor([1, 5, 14, 16, 33, 40, 62])
+    ds = FeatureDataset(str(tmp_path), cfg, modules=["layers.0"], features={"layers.0": sel})
+    tokens = torch.from_numpy(g["tokens"])
+    big = torch.zeros(100 + tokens.shape[0], tokens.shape[1], dtype=torch.long)
+    big[100:] = tokens
+    seen = []
+    for buf in ds.buffers:
+        buf._load()
+        for i in range(len(buf)):
+            bo = buf[i]["buffer"]
+            f = bo.feature.feature_index
+            seen.append(f)
+            assert np.array_equal(bo.locations.numpy(), g[f"feat{f}_locations"])
+            assert np.array_equal(bo.activations.numpy(), g[f"feat{f}_activations"])
+            if bo.activations.numel() == 0:
+                continue
+            rec = FeatureRecord(bo.feature)
+            pool_max_activation_windows(rec, bo, big, cfg)
+            np.testing.assert_allclose(torch.stack([e.activations for e in rec.examples]).numpy(),
+                                       g[f"feat{f}_ex_acts"], rtol=1e-6)
+            assert np.array_equal(torch.stack([e.tokens for e in rec.examples]).numpy(), g[f"feat{f}_ex_tokens"])
+    assert seen == g["loader_features"].tolist()
+    # the callback protocol of FeatureDataset.load
+    recs = ds.load(collate=True, constructor=lambda record, buffer_output: setattr(record, "examples", []))
+    assert [r.feature.feature_index for r in recs] == seen and repr(recs[0].feature) == "layers.0_feature1"
+
+
+def test_filter_bitmap_bits():
+    from saeb200.engine import make_filter_bitmap
+
+    bm = make_filter_bitmap(torch.tensor([0, 31, 32, 63, 95]), 96)
+    words = bm.to(torch.int64) & 0xFFFFFFFF
+    assert words.tolist() == [(1 << 0) | (1 << 31), (1 << 0) | (1 << 31), 1 << 31]

@@ -1,0 +1,162 @@
+"""Bring-up probe for the GPU box: each experiment runs in its own process with a timeout so that a hung or trapped
+kernel cannot take the whole call down.  Usage: python tools/gpu_probe.py [exp ...] ; results -> gpurun_out/probe.log"""
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "multimodal-sae_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def _setup(pair):
+    import torch
+    from saeb200 import _capi, engine
+    L = _capi.lib()
+    _capi.check(L.saeb_set_option(b"cta_pair", pair), "set_option")
+    return torch, engine
+
+
+def exp_gemm(pair, planes, T, d, N, xdt="bf16"):
+    torch, engine = _setup(pair)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    W = (torch.rand(N, d, device="cuda", generator=g) * 2 - 1) / d ** 0.5
+    be = torch.randn(N, device="cuda", generator=g) * 0.01
+    bd = torch.randn(d, device="cuda", generator=g) * 0.1
+    x = torch.randn(T, d, device="cuda", generator=g)
+    x = {"bf16": x.to(torch.bfloat16), "f16": x.to(torch.float16), "f32": x}[xdt]
+    enc = engine.PackedEncoder.pack(W, be, bd, planes)
+    torch.cuda.synchronize()
+    _, _, dense = engine.encode_topk(x, enc, 16, want_dense=True, want_topk=False)
+    torch.cuda.synchronize()
+    ref = torch.relu((x.double() - bd.double()) @ W.double().T + be.double())
+    err = (dense.double() - ref).abs().max().item()
+    rel = err / ref.abs().max().item()
+    # error of a plain bf16-weight product for scale
+    Wb = W.to(torch.bfloat16).double()
+    ref1 = torch.relu(x.double() @ Wb.T + (be.double() - W.double() @ bd.double()))
+    err1 = (dense.double() - ref1).abs().max().item()
+    bad = (dense.double() - ref).abs() > 1e-2
+    return dict(max_abs_err_vs_f64=err, rel=rel, max_abs_err_vs_bf16W=err1, n_bad=int(bad.sum()),
+                first_bad=[int(v) for v in torch.nonzero(bad)[0].tolist()] if bad.any() else None,
+                dense_absmax=dense.abs().max().item(), ref_absmax=ref.abs().max().item())
+
+
+def exp_topk(pair, planes, T, d, N, k, xdt="bf16"):
+    torch, engine = _setup(pair)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    W = (torch.rand(N, d, device="cuda", generator=g) * 2 - 1) / d ** 0.5
+    be = torch.randn(N, device="cuda", generator=g) * 0.01
+    bd = torch.randn(d, device="cuda", generator=g) * 0.1
+    x = torch.randn(T, d, device="cuda", generator=g)
+    x = {"bf16": x.to(torch.bfloat16), "f16": x.to(torch.float16), "f32": x}[xdt]
+    enc = engine.PackedEncoder.pack(W, be, bd, planes)
+    vals, idx, _ = engine.encode_topk(x, enc, k)
+    torch.cuda.synchronize()
+    chunks = []
+    bad_rows = 0
+    maxrel = 0.0
+    for t0 in range(0, T, 1024):
+        xs = x[t0:t0 + 1024]
+        ref = torch.relu((xs.double() - bd.double()) @ W.double().T + be.double())
+        rv, ri = ref.topk(k, dim=-1)
+        a = torch.sort(idx[t0:t0 + 1024], dim=-1).values
+        b = torch.sort(ri, dim=-1).values
+        bad_rows += int((a != b).any(-1).sum())
+        maxrel = max(maxrel, ((vals[t0:t0 + 1024].double() - rv).abs() / rv.abs().clamp_min(1e-6)).max().item())
+    sorted_ok = bool((vals[:, :-1] >= vals[:, 1:]).all())
+    return dict(rows=T, rows_with_set_mismatch=bad_rows, max_rel_val_err=maxrel, sorted_desc=sorted_ok)
+
+
+def exp_time(pair, planes, T, d, N, k, iters=3):
+    torch, engine = _setup(pair)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    W = (torch.rand(N, d, device="cuda", generator=g) * 2 - 1) / d ** 0.5
+    be = torch.randn(N, device="cuda", generator=g) * 0.01
+    bd = torch.randn(d, device="cuda", generator=g) * 0.1
+    enc = engine.PackedEncoder.pack(W, be, bd, planes)
+    Wd = W / W.norm(dim=1, keepdim=True)
+    del W
+    x = torch.randn(T, d, device="cuda", generator=g).to(torch.bfloat16)
+    out = {}
+    for _ in range(2):
+        vals, idx, _ = engine.encode_topk(x, enc, k)
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    te, td = [], []
+    for _ in range(iters):
+        e0.record()
+        vals, idx, _ = engine.encode_topk(x, enc, k)
+        e1.record()
+        y = engine.decode(idx, vals, Wd, bd)
+        e2.record()
+        torch.cuda.synchronize()
+        te.append(e0.elapsed_time(e1))
+        td.append(e1.elapsed_time(e2))
+    flops = 2.0 * T * d * N
+    out["encode_ms"] = te
+    out["decode_ms"] = td
+    out["encode_tflops_alg"] = flops / (min(te) * 1e-3) / 1e12
+    out["decode_GBs"] = (T * k * d * 4 + T * d * 4 + T * k * 12) / (min(td) * 1e-3) / 1e9
+    out["tokens_per_s_fwd"] = T / ((min(te) + min(td)) * 1e-3)
+    return out
+
+
+def exp_decode(T, d, N, k):
+    torch, engine = _setup(2)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    Wd = torch.randn(N, d, device="cuda", generator=g)
+    bd = torch.randn(d, device="cuda", generator=g)
+    lat = torch.rand(T, N, device="cuda", generator=g)
+    vals, idx = lat.topk(k)
+    y = engine.decode(idx, vals, Wd, bd)
+    buf = torch.zeros(T, N, device="cuda", dtype=torch.float64)
+    buf.scatter_(-1, idx, vals.double())
+    ref = buf @ Wd.double() + bd.double()
+    return dict(max_abs_err=(y.double() - ref).abs().max().item(), ref_absmax=ref.abs().max().item())
+
+
+EXPS = {
+    "gemm_p1_small": lambda: exp_gemm(1, 1, 256, 128, 512),
+    "gemm_p2_small": lambda: exp_gemm(2, 1, 256, 128, 512),
+    "gemm_p1_mid": lambda: exp_gemm(1, 1, 300, 4096, 2048 + 64),
+    "gemm_p2_mid": lambda: exp_gemm(2, 1, 300, 4096, 2048 + 64),
+    "gemm_p1_hilo": lambda: exp_gemm(1, 2, 512, 4096, 4096),
+    "gemm_p2_hilo": lambda: exp_gemm(2, 2, 512, 4096, 4096),
+    "gemm_p2_f32x": lambda: exp_gemm(2, 2, 512, 1024, 4096, "f32"),
+    "gemm_p2_f16x": lambda: exp_gemm(2, 2, 512, 1024, 4096, "f16"),
+    "topk_p1": lambda: exp_topk(1, 2, 2048, 1024, 16384, 64),
+    "topk_p2": lambda: exp_topk(2, 2, 2048, 1024, 16384, 64),
+    "topk_p2_k256": lambda: exp_topk(2, 2, 1024, 1024, 16384, 256),
+    "topk_p2_full": lambda: exp_topk(2, 2, 2048, 4096, 131072, 64),
+    "decode": lambda: exp_decode(64, 512, 4096, 32),
+    "time_p2_2pl": lambda: exp_time(2, 2, 16384, 4096, 131072, 64),
+    "time_p2_1pl": lambda: exp_time(2, 1, 16384, 4096, 131072, 64),
+    "time_p1_2pl": lambda: exp_time(1, 2, 16384, 4096, 131072, 64),
+    "time_p1_1pl": lambda: exp_time(1, 1, 16384, 4096, 131072, 64),
+    "time_p2_2pl_64k": lambda: exp_time(2, 2, 65536, 4096, 131072, 64, iters=2),
+}
+
+if __name__ == "__main__":
+    if len(sys.argv) >= 3 and sys.argv[1] == "--child":
+        name = sys.argv[2]
+        t = time.time()
+        res = EXPS[name]()
+        res["wall_s"] = round(time.time() - t, 2)
+        print("RESULT " + json.dumps({name: res}))
+        sys.exit(0)
+    names = sys.argv[1:] or list(EXPS)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    log = open(os.path.join(ROOT, "gpurun_out", "probe.log"), "a")
+    for n in names:
+        try:
+            r = subprocess.run([sys.executable, __file__, "--child", n], capture_output=True, text=True, timeout=240)
+            lines = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+            msg = lines[-1] if lines else f"FAIL {n} rc={r.returncode}\n--stdout--\n{r.stdout[-1500:]}\n--stderr--\n{r.stderr[-2500:]}"
+        except subprocess.TimeoutExpired as e:
+            msg = f"TIMEOUT {n}\n{(e.stdout or b'')[-1000:]}\n{(e.stderr or b'')[-1000:]}"
+        print(msg, flush=True)
+        log.write(msg + "\n")
+        log.flush()
