@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Benchmark of the SAE hot path (BASELINE.json metric: SAE tokens/sec at d=4096, width=131k).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step is one pass of the hot path -- fused encode + TopK, sparse decode, FVU (reference Sae.forward,
+sae/sae.py:193-247) -- over one batch of 65 536 synthetic bf16 tokens (BASELINE.json configs[1]).  With N GPUs every
+rank runs the same step on its own 65 536 tokens with the SAE replicated (tokens are independent: no data-path
+collective, weak scaling); `value` is the whole-job tokens/s, timed on the device with CUDA events, barrier +
+synchronize on both sides, max over ranks.  The JSON line also carries
+  e2e          the same metric through the reference-facing `Sae` objects with HOST buffers (pinned x in, TopK + FVU
+               back), copies inside the timed region;
+  roofline     the fused encode kernel against the measured bf16 tensor peak (MEASURED_PEAKS.json);
+  cpu_baseline the oracle's CPU forward (the reference's PyTorch ops) on a bounded sample, rank 0, N=1 only;
+  scan         feature-sharded top-activation scan (north star: features split across ranks, one all-gather of
+               per-shard top lists at the end) on a bounded token count.
+`--impl reference` times the reference's own CPU implementation of the path (the oracle port of its PyTorch ops; a
+Python reference cannot be pre-built into oracle/_ref) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "multimodal-sae_b200"))
+
+D_IN, WIDTH, K = 4096, 131072, 64
+TOKENS = 65536
+FLOPS_PER_TOKEN = 2.0 * D_IN * WIDTH + 2.0 * K * D_IN  # algorithmic, independent of MMA passes
+ENC_FLOPS_PER_TOKEN = 2.0 * D_IN * WIDTH
+METRIC = "SAE tokens/sec (d=4096, width=131k, k=64, encode+TopK+decode)"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], tflops_burst=p["bf16_tflops"],
+                    tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], None, set(), []
+        for ts, line in self.lines:
+            if ts < t0 or ts > t1 + 0.1:
+                continue
+            f = [s.strip() for s in line.split(",")]
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+                power.append(float(f[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference's PyTorch forward on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_forward_tokens_per_s(sample_tokens: int, batch: int, repeats: int, seed: int = 1234):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import sae_oracle as O
+
+    threads = torch.get_num_threads()
+    p = O.init_params(D_IN, WIDTH, K, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(sample_tokens, D_IN, generator=g).to(torch.bfloat16)
+    best = None
+    with torch.no_grad():
+        O.forward(p, x[:batch])  # warm-up
+        for _ in range(repeats):
+            t = time.perf_counter()
+            for b0 in range(0, sample_tokens, batch):
+                O.forward(p, x[b0:b0 + batch])
+            dt = time.perf_counter() - t
+            best = dt if best is None else min(best, dt)
+    return sample_tokens / best, threads, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample, batch = 1024, 512
+    warm = max(args.warmup, 0)
+    tok_s, threads, _ = cpu_forward_tokens_per_s(sample, batch, repeats=max(1, min(args.steps, 3)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 * sample / tok_s, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: d_model=4096 width=131072 k=64 SAE forward (bounded sample)",
+                   "global_batch_tokens": sample, "parallelism": "cpu"},
+        "cpu_baseline": {"value": tok_s, "unit": "tokens/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} tokens in {batch}-token batches per step, best of {max(1, min(args.steps, 3))}"},
+        "e2e": {"value": tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from saeb200 import _capi, dist as sdist, engine, pipeline, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _capi.lib()
+    _capi.check(L.saeb_set_option(b"profile", 1), "set_option")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sae = synth.make_sae(D_IN, WIDTH, K, dev, seed=1234)
+    enc = sae.packed_encoder()
+    x = synth.make_activations(TOKENS, D_IN, dev, seed=1 + rank)
+    acts = torch.empty((TOKENS, K), dtype=torch.float32, device=dev)
+    idx = torch.empty((TOKENS, K), dtype=torch.int64, device=dev)
+    sae_out = torch.empty((TOKENS, D_IN), dtype=torch.float32, device=dev)
+    sq_err = torch.zeros((), dtype=torch.float64, device=dev)
+
+    def step():
+        sq_err.zero_()
+        engine.encode_topk(x, enc, K, out_vals=acts, out_idx=idx)
+        engine.decode(idx, acts, sae.W_dec.data, sae.b_dec.data, x=x, sq_err=sq_err, out=sae_out)
+        return (sq_err / engine.total_variance(x)).to(torch.float32)
+
+    # ---- device-resident throughput (`value`)
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = _capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        fvu = step()
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = _capi.launch_count() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = world * TOKENS * args.steps / (ms_total * 1e-3)
+    fvu_val = float(fvu.item())
+
+    # ---- dominant kernel, live CUDA events on the launching stream (library-side bracket of the main kernel)
+    k_ms = []
+    for _ in range(max(3, min(args.steps, 5))):
+        engine.encode_topk(x, enc, K, out_vals=acts, out_idx=idx)
+        k_ms.append(float(L.saeb_profile_last_encode_ms()))
+    k_avg = sum(k_ms) / len(k_ms)
+    peaks = load_peaks()
+    achieved = ENC_FLOPS_PER_TOKEN * TOKENS / (k_avg * 1e-3) / 1e12
+    traffic = None
+    summ = os.path.join(ROOT, "profiles", "encode_kernel_traffic.json")
+    if os.path.exists(summ):
+        try:
+            traffic = json.load(open(summ)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "kernel": "encode_topk_kernel (tcgen05 GEMM + fused TopK)", "achieved": achieved,
+                "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
+                "traffic": traffic, "peak_source": f"{peaks['source']} bf16 sustained (cuBLAS, MEASURED_PEAKS.json)",
+                "kernel_ms": k_avg, "mma_passes": enc.planes,
+                "path_frac": (value / world) * FLOPS_PER_TOKEN / 1e12 / peaks["tflops_sustained"],
+                "hbm_frac": (value / world) * (2 * D_IN + K * 12 + K * 4 * D_IN + 4 * D_IN + 2.0 * D_IN * WIDTH * enc.planes / TOKENS)
+                / 1e9 / peaks["hbm_gbs"]}
+
+    # ---- end to end through the reference-facing objects with host buffers (`e2e`)
+    x_host = synth.make_activations(TOKENS, D_IN, dev, seed=1 + rank, pinned_host=True)
+    acts_host = torch.empty((TOKENS, K), dtype=torch.float32, pin_memory=True)
+    idx_host = torch.empty((TOKENS, K), dtype=torch.int64, pin_memory=True)
+    hf = pipeline.HostForward(sae, TOKENS, chunk=8192)
+    for _ in range(max(1, min(args.warmup, 2))):
+        hf.run(x_host, acts_host, idx_host)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        fvu_host = hf.run(x_host, acts_host, idx_host)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e = {"value": world * TOKENS * args.steps / (e2e_ms * 1e-3), "unit": "tokens/s",
+           "h2d_bytes_per_step": hf.h2d_bytes * world, "d2h_bytes_per_step": hf.d2h_bytes * world,
+           "api": "sae_auto_interp.sae.Sae + saeb200.pipeline.HostForward (pinned x in; TopK acts/indices + FVU out)",
+           "fvu": float(fvu_host.item())}
+
+    # ---- feature-sharded top-activation scan (bounded token count; one all-gather of top lists at the end)
+    scan = None
+    if args.scan_tokens > 0:
+        ctx_len, n_top, chunk = 64, 20, 16384
+        lo, hi = sdist.shard_range(WIDTH, world, rank)
+        ops = sdist.EngineOps(sae.encoder.weight.data[lo:hi], sae.encoder.bias.data[lo:hi], sae.b_dec.data, lo, hi,
+                              n_top, ctx_len, dev)
+        xs = synth.make_activations(args.scan_tokens, D_IN, dev, seed=99)  # same tokens on every rank
+
+        def chunks():
+            for t0 in range(0, args.scan_tokens, chunk):
+                yield xs[t0:t0 + chunk]
+
+        sdist.sharded_scan(chunks(), ops, K, ctx_len, WIDTH)  # warm-up
+        ops.scan = engine.TopActivationScan(lo, hi, n_top, ctx_len, dev)
+        barrier()
+        e0.record()
+        res = sdist.sharded_scan(chunks(), ops, K, ctx_len, WIDTH)
+        e1.record()
+        barrier()
+        sms = max_over_ranks(e0.elapsed_time(e1))
+        scan = {"tokens": args.scan_tokens, "features": WIDTH, "n_top": n_top, "ctx_len": ctx_len, "ms": sms,
+                "tokens_per_s": args.scan_tokens / (sms * 1e-3), "sharding": f"features/{world}", "exact_topk_mask": True,
+                "filled_features": int((res.top_win[:, 0] >= 0).sum().item())}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        tok_s, threads, secs = cpu_forward_tokens_per_s(2048, 512, repeats=2)
+        cpu = {"value": tok_s, "unit": "tokens/s", "cores": threads, "kind": "port",
+               "sample": f"oracle port of reference Sae.forward (PyTorch CPU fp32), 2048 tokens in 512-token batches, "
+                         f"best of 2 ({secs:.1f} s)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "C2: d_model=4096 width=131072 k=64 SAE forward over 65536 bf16 tokens per GPU "
+                                   "(encode+TopK+decode+FVU), inputs resident in HBM",
+                       "global_batch_tokens": world * TOKENS, "parallelism": f"token-parallel x{world}, SAE replicated",
+                       "precision": "bf16 activations (exact) x bf16 hi+lo W_enc planes, fp32 accumulate; fp32 W_dec",
+                       "l2": "inputs (x 512 MiB, weights 6 GiB) larger than the 126 MB L2"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "scan": scan, "fvu": fvu_val,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scan-tokens", type=int, default=262144)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

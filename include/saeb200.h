@@ -36,15 +36,18 @@ const char* saeb_last_error(void);
 /* Number of kernel launches enqueued by this library in this process (bench.py's `gpu_launches` claim). */
 long long saeb_launch_count(void);
 /* Tuning knobs.  "cta_pair": 2 (default) = CTA pairs with tcgen05 cta_group::2 (256-row MMA tiles), 1 = single-CTA
- * tiles.  Results are identical; only throughput differs. */
+ * tiles.  Results are identical; only throughput differs.  "profile": see saeb_profile_last_encode_ms. */
 int saeb_set_option(const char* name, int value);
+/* With option "profile" = 1 the library brackets the fused encode kernel (main kernel only) with CUDA events on the
+ * launching stream; this returns the duration in ms of the most recent one (synchronises on it), < 0 if none. */
+float saeb_profile_last_encode_ms(void);
 
 /* ---- one-time weight repack -------------------------------------------------------------------------------
  * Reference parameters: `encoder.weight [N,d]`, `encoder.bias [N]`, `b_dec [d]` fp32 (sae/sae.py:59-66, loaded by
  * Sae.load_from_disk sae/sae.py:126-148).  Produces `planes` bf16 planes of W_enc (1: bf16(W); 2: hi + lo, the
  * parity-grade mode) followed by the folded bias b_enc - W_enc b_dec (sae/sae.py:174-175 rewritten as
- * W x + (b_enc - W b_dec)).  Layout of `packed`: [planes][N][d] bf16, then [N] fp32 at
- * saeb_packed_bias_offset(). */
+ * W x + (b_enc - W b_dec)).  Layout of `packed`: [planes][N][d_pad] bf16 with d_pad = d rounded up to 8 (16-byte
+ * rows for TMA, zero padded), then [N] fp32 at saeb_packed_bias_offset().  Any d >= 1 is accepted. */
 size_t saeb_packed_weights_bytes(int64_t N, int64_t d, int planes);
 size_t saeb_packed_bias_offset(int64_t N, int64_t d, int planes);
 int saeb_pack_weights(const float* W_enc, const float* b_enc, const float* b_dec, int64_t N, int64_t d, int planes,
@@ -53,8 +56,9 @@ int saeb_pack_weights(const float* W_enc, const float* b_enc, const float* b_dec
 /* ---- fused encode + TopK ------------------------------------------------------------------------------------
  * Replaces Sae.encode = select_topk(pre_acts(x)) (sae/sae.py:172-185) and the cache path's
  * `pre_acts -> torch.topk` (features/cache.py:210-213, :407-412) without materialising the dense [T,N] latents.
- *   x            [T, ld_x] activations (bf16 consumed in place; f16 / f32 are split into two bf16 planes in the
- *                workspace); d % 8 == 0, ld_x % 8 == 0, 16-byte aligned
+ *   x            [T, ld_x] activations.  bf16 with d % 8 == 0 is consumed in place (needs a 16-byte aligned base and
+ *                ld_x % 8 == 0); f16 / f32 are split into two bf16 planes, bf16 with d % 8 != 0 is copied to a padded
+ *                plane (both in the workspace)
  *   clamp_feature / clamp_value: steering (features/steering.py:113-114): that latent is forced to clamp_value
  *                before TopK; pass -1 to disable
  *   out_vals     [T,k] f32, out_idx [T,k] i64, each row ordered by (value desc, index asc); rows with fewer than k

@@ -22,14 +22,14 @@ void set_error(const char* fmt, ...) {
 // implemented in the kernel translation units
 size_t encode_workspace_bytes(long long T, long long d, long long N, int k);
 int encode_topk_launch(const void* x_planes, int ap, long long T, long long ld_x, long long x_plane_stride,
-                       const void* w_planes, int bp, const float* bias, long long d, long long N, int k,
+                       const void* w_planes, int bp, long long ld_w, const float* bias, long long d, long long N, int k,
                        long long clamp_feature, float clamp_value, float* out_vals, long long* out_idx,
                        float* dense_out, long long ld_dense, void* workspace, size_t workspace_bytes, int pass_mask,
                        cudaStream_t stream);
 int pack_weights_launch(const float* W_enc, const float* b_enc, const float* b_dec, long long N, long long d,
-                        int planes, void* w_planes, float* bias, cudaStream_t stream);
-int split_x_launch(const void* x, int x_dtype, long long T, long long d, long long ld_x, void* out,
-                   cudaStream_t stream);
+                        long long d_pad, int planes, void* w_planes, float* bias, cudaStream_t stream);
+int split_x_launch(const void* x, int x_dtype, long long T, long long d, long long ld_x, long long d_pad, int planes,
+                   void* out, cudaStream_t stream);
 int decode_launch(const long long* idx, const float* vals, long long T, int k, const void* W_dec, int w_dtype,
                   long long d, long long N, const float* b_dec, void* out, int out_dtype, long long ld_out,
                   const void* x, int x_dtype, long long ld_x, double* sq_err, int* err_flag, cudaStream_t stream);
@@ -48,13 +48,19 @@ int scan_merge_launch(void* bucket, int* bucket_cnt, int bucket_cap, long long F
                       float* top_vals, long long* top_win, float* feat_thr, cudaStream_t stream);
 
 int set_cta_pair(int v);
+int set_profile(int v);
+float last_encode_ms();
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline long long pad8(long long d) { return (d + 7) / 8 * 8; }   // 16-byte row strides for TMA
 static inline size_t planes_bytes(long long N, long long d, int planes) {
-  return align_up((size_t)planes * (size_t)N * (size_t)d * 2, 256);
+  return align_up((size_t)planes * (size_t)N * (size_t)pad8(d) * 2, 256);
 }
+// workspace for bf16 activation planes: none for bf16 input consumed in place (d % 8 == 0), one padded plane for
+// bf16 with d % 8 != 0, two planes for fp16 / fp32 input
 static inline size_t x_split_bytes(long long T, long long d, int x_dtype) {
-  return x_dtype == DT_BF16 ? 0 : align_up((size_t)2 * (size_t)T * (size_t)d * 2, 1024);
+  if (x_dtype == DT_BF16 && d % 8 == 0) return 0;
+  return align_up((size_t)(x_dtype == DT_BF16 ? 1 : 2) * (size_t)T * (size_t)pad8(d) * 2, 1024);
 }
 
 }  // namespace saeb
@@ -70,9 +76,12 @@ int saeb_set_option(const char* name, int value) {
   g_err[0] = 0;
   SAEB_REQUIRE(name != nullptr, "set_option: null name");
   if (strcmp(name, "cta_pair") == 0) return set_cta_pair(value);
+  if (strcmp(name, "profile") == 0) return set_profile(value);
   set_error("set_option: unknown option '%s'", name);
   return -1;
 }
+
+float saeb_profile_last_encode_ms(void) { return last_encode_ms(); }
 
 size_t saeb_packed_bias_offset(int64_t N, int64_t d, int planes) { return planes_bytes(N, d, planes); }
 size_t saeb_packed_weights_bytes(int64_t N, int64_t d, int planes) {
@@ -84,7 +93,7 @@ int saeb_pack_weights(const float* W_enc, const float* b_enc, const float* b_dec
   g_err[0] = 0;
   SAEB_REQUIRE(W_enc && b_enc && b_dec && packed, "pack_weights: null pointer");
   float* bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + planes_bytes(N, d, planes));
-  int rc = pack_weights_launch(W_enc, b_enc, b_dec, N, d, planes, packed, bias, (cudaStream_t)stream);
+  int rc = pack_weights_launch(W_enc, b_enc, b_dec, N, d, pad8(d), planes, packed, bias, (cudaStream_t)stream);
   if (rc == 0) g_launches += 2;
   return rc;
 }
@@ -112,16 +121,20 @@ int saeb_encode_topk(const void* x, int x_dtype, int64_t T, int64_t ld_x, const 
   long long ldx = ld_x, xps = (long long)T * ld_x;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   size_t ws_left = workspace_bytes;
-  if (x_dtype != DT_BF16) {
+  const bool in_place = x_dtype == DT_BF16 && ld_x % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  if (!in_place) {
+    SAEB_REQUIRE(!(x_dtype == DT_BF16 && d % 8 == 0),
+                 "encode_topk: bf16 activations need a 16-byte aligned base and ld_x %% 8 == 0 (got ld_x=%lld)",
+                 (long long)ld_x);
     const size_t need = x_split_bytes(T, d, x_dtype);
     SAEB_REQUIRE(workspace != nullptr && workspace_bytes >= need, "encode_topk: workspace too small for x planes");
-    int rc = split_x_launch(x, x_dtype, T, d, ld_x, ws, st);
+    ap = (x_dtype == DT_BF16) ? 1 : 2;
+    int rc = split_x_launch(x, x_dtype, T, d, ld_x, pad8(d), ap, ws, st);
     if (rc) return rc;
     g_launches += 1;
     xp = ws;
-    ap = 2;
-    ldx = d;
-    xps = (long long)T * d;
+    ldx = pad8(d);
+    xps = (long long)T * pad8(d);
     ws += need;
     ws_left -= need;
   }
@@ -130,7 +143,7 @@ int saeb_encode_topk(const void* x, int x_dtype, int64_t T, int64_t ld_x, const 
   for (int a = 0; a < ap; ++a)
     for (int b = 0; b < planes; ++b)
       if (!(a == 1 && b == 1)) pass_mask |= 1 << (a * planes + b);
-  int rc = encode_topk_launch(xp, ap, T, ldx, xps, packed, planes, bias, d, N, k, clamp_feature, clamp_value, out_vals,
+  int rc = encode_topk_launch(xp, ap, T, ldx, xps, packed, planes, pad8(d), bias, d, N, k, clamp_feature, clamp_value, out_vals,
                               reinterpret_cast<long long*>(out_idx), dense_out, ld_dense, ws, ws_left, pass_mask, st);
   if (rc == 0) g_launches += out_vals ? 2 : 1;
   return rc;

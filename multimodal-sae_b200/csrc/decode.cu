@@ -169,6 +169,49 @@ decode_kernel(const long long* __restrict__ idx, const float* __restrict__ vals,
   }
 }
 
+// generic fallback for shapes the vector kernel cannot take (d, ld_out or ld_x not a multiple of 4): one column per
+// thread, scalar loads.  Same arithmetic (fp32 fma in j order, zeros skipped).
+template <typename WT, typename OT, typename XT>
+__global__ void __launch_bounds__(DEC_THREADS)
+decode_scalar_kernel(const long long* __restrict__ idx, const float* __restrict__ vals, int k,
+                     const WT* __restrict__ W, long long d, long long N, const float* __restrict__ b_dec,
+                     OT* __restrict__ out, long long ld_out, const XT* __restrict__ x, long long ld_x,
+                     double* __restrict__ sq_err, int* __restrict__ err_flag) {
+  __shared__ float s_red[DEC_THREADS / 32];
+  const long long t = blockIdx.x;
+  const int tid = threadIdx.x;
+  float local_sq = 0.f;
+  for (long long c = tid; c < d; c += DEC_THREADS) {
+    float acc = 0.f;
+    for (int j = 0; j < k; ++j) {
+      const float v = vals[t * k + j];
+      const long long r = idx[t * k + j];
+      if (r < 0 || r >= N) {
+        if (err_flag) atomicExch(err_flag, 1);
+        continue;
+      }
+      if (v != 0.f) acc = fmaf(v, (float)W[r * d + c], acc);
+    }
+    if (b_dec != nullptr) acc += b_dec[c];
+    out[t * ld_out + c] = (OT)acc;
+    if (sq_err != nullptr) {
+      const float e = acc - (float)x[t * ld_x + c];
+      local_sq += e * e;
+    }
+  }
+  if (sq_err != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local_sq += __shfl_xor_sync(0xffffffffu, local_sq, o);
+    if ((tid & 31) == 0) s_red[tid >> 5] = local_sq;
+    __syncthreads();
+    if (tid == 0) {
+      double s2 = 0.0;
+      for (int w = 0; w < DEC_THREADS / 32; ++w) s2 += (double)s_red[w];
+      atomicAdd(sq_err, s2);
+    }
+  }
+}
+
 // column statistics for the FVU denominator  sum((x - mean_0(x))^2)  (sae/sae.py:204), fp64 accumulation
 template <typename XT>
 __global__ void colstats_kernel(const XT* __restrict__ x, long long T, long long d, long long ld_x, int rows_per_block,
@@ -205,18 +248,28 @@ static int decode_dispatch_x(const long long* idx, const float* vals, long long 
                              long long N, const float* b_dec, OT* out, long long ld_out, const void* x, int x_dtype,
                              long long ld_x, double* sq_err, int* err_flag, cudaStream_t stream) {
   dim3 grid((unsigned)T), block(DEC_THREADS);
-  if (sq_err == nullptr || x == nullptr)
-    decode_kernel<WT, OT, float><<<grid, block, 0, stream>>>(idx, vals, k, W, d, N, b_dec, out, ld_out, nullptr, 0,
-                                                             nullptr, err_flag);
+  const bool with_x = sq_err != nullptr && x != nullptr;
+  const bool vec = d % 4 == 0 && ld_out % 4 == 0 && (!with_x || ld_x % 4 == 0) &&
+                   (reinterpret_cast<uintptr_t>(W) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                   (!with_x || (reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                   (b_dec == nullptr || (reinterpret_cast<uintptr_t>(b_dec) & 15) == 0);
+#define SAEB_DEC_LAUNCH(XT, XP, LDX, SQ)                                                                            \
+  do {                                                                                                              \
+    if (vec)                                                                                                        \
+      decode_kernel<WT, OT, XT><<<grid, block, 0, stream>>>(idx, vals, k, W, d, N, b_dec, out, ld_out, XP, LDX, SQ,  \
+                                                            err_flag);                                              \
+    else                                                                                                            \
+      decode_scalar_kernel<WT, OT, XT><<<grid, block, 0, stream>>>(idx, vals, k, W, d, N, b_dec, out, ld_out, XP,    \
+                                                                   LDX, SQ, err_flag);                              \
+  } while (0)
+  if (!with_x)
+    SAEB_DEC_LAUNCH(float, (const float*)nullptr, 0, (double*)nullptr);
   else if (x_dtype == DT_F32)
-    decode_kernel<WT, OT, float><<<grid, block, 0, stream>>>(idx, vals, k, W, d, N, b_dec, out, ld_out,
-                                                             reinterpret_cast<const float*>(x), ld_x, sq_err, err_flag);
+    SAEB_DEC_LAUNCH(float, reinterpret_cast<const float*>(x), ld_x, sq_err);
   else if (x_dtype == DT_BF16)
-    decode_kernel<WT, OT, __nv_bfloat16><<<grid, block, 0, stream>>>(
-        idx, vals, k, W, d, N, b_dec, out, ld_out, reinterpret_cast<const __nv_bfloat16*>(x), ld_x, sq_err, err_flag);
+    SAEB_DEC_LAUNCH(__nv_bfloat16, reinterpret_cast<const __nv_bfloat16*>(x), ld_x, sq_err);
   else if (x_dtype == DT_F16)
-    decode_kernel<WT, OT, __half><<<grid, block, 0, stream>>>(idx, vals, k, W, d, N, b_dec, out, ld_out,
-                                                              reinterpret_cast<const __half*>(x), ld_x, sq_err, err_flag);
+    SAEB_DEC_LAUNCH(__half, reinterpret_cast<const __half*>(x), ld_x, sq_err);
   else {
     set_error("decode: unsupported x dtype %d", x_dtype);
     return -1;
@@ -248,8 +301,7 @@ int decode_launch(const long long* idx, const float* vals, long long T, int k, c
                   const void* x, int x_dtype, long long ld_x, double* sq_err, int* err_flag, cudaStream_t stream) {
   if (T == 0) return 0;
   SAEB_REQUIRE(k >= 1 && k <= DEC_KMAX, "decode: k=%d out of range (1..%d)", k, DEC_KMAX);
-  SAEB_REQUIRE(d % 4 == 0 && ld_out % 4 == 0, "decode: d and ld_out must be multiples of 4");
-  SAEB_REQUIRE(x == nullptr || ld_x % 4 == 0, "decode: ld_x must be a multiple of 4");
+  SAEB_REQUIRE(d >= 1 && ld_out >= d, "decode: bad d / ld_out");
   if (w_dtype == DT_F32)
     return decode_dispatch_o<float>(idx, vals, T, k, reinterpret_cast<const float*>(W_dec), d, N, b_dec, out,
                                     out_dtype, ld_out, x, x_dtype, ld_x, sq_err, err_flag, stream);

@@ -546,6 +546,27 @@ static EncodePlan make_plan(long long T, long long N, int k, int pair) {
   return p;
 }
 
+static int g_profile = 0;
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+static bool g_ev_valid = false;
+int set_profile(int v) {
+  g_profile = v ? 1 : 0;
+  if (g_profile && g_ev0 == nullptr) {
+    if (cudaEventCreate(&g_ev0) != cudaSuccess || cudaEventCreate(&g_ev1) != cudaSuccess) {
+      set_error("profile: cudaEventCreate failed");
+      return -2;
+    }
+  }
+  return 0;
+}
+// elapsed milliseconds of the most recent fused encode kernel (main kernel only, merge excluded); < 0 if none
+float last_encode_ms() {
+  if (!g_ev_valid) return -1.f;
+  float ms = -1.f;
+  if (cudaEventSynchronize(g_ev1) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, g_ev0, g_ev1) != cudaSuccess) return -1.f;
+  return ms;
+}
 static int g_cta_pair = 0;   // 0 = not initialised (env SAEB_CTA_PAIR or default 2)
 static int default_pair() {
   if (g_cta_pair == 0) {
@@ -618,12 +639,12 @@ static int launch_planes(int ap, int bp, const CUtensorMap& ta, const CUtensorMa
 // x_planes: [ap][T][ld_x] bf16 (ap==1: the caller's bf16 activations in place)
 // w_planes: [bp][N][d] bf16; bias: folded bias [N]
 int encode_topk_launch(const void* x_planes, int ap, long long T, long long ld_x, long long x_plane_stride,
-                       const void* w_planes, int bp, const float* bias, long long d, long long N, int k,
+                       const void* w_planes, int bp, long long ld_w, const float* bias, long long d, long long N, int k,
                        long long clamp_feature, float clamp_value, float* out_vals, long long* out_idx,
                        float* dense_out, long long ld_dense, void* workspace, size_t workspace_bytes, int pass_mask,
                        cudaStream_t stream) {
   SAEB_REQUIRE(T > 0 && d > 0 && N > 0, "empty problem T=%lld d=%lld N=%lld", T, d, N);
-  SAEB_REQUIRE(d % 8 == 0 && ld_x % 8 == 0, "d and ld_x must be multiples of 8 (16-byte TMA strides)");
+  SAEB_REQUIRE(ld_w % 8 == 0 && ld_x % 8 == 0, "ld_w and ld_x must be multiples of 8 (16-byte TMA strides)");
   SAEB_REQUIRE(k >= 1 && k <= 512 && k <= N, "k=%d out of range (1..min(512,N))", k);
   SAEB_REQUIRE(T < (1ll << 31) && N < (1ll << 31), "T/N too large");
   SAEB_REQUIRE((reinterpret_cast<uintptr_t>(x_planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_planes) & 15) == 0,
@@ -638,7 +659,7 @@ int encode_topk_launch(const void* x_planes, int ap, long long T, long long ld_x
   CUtensorMap ta, tb;
   int rc = make_map(&ta, x_planes, d, T, ap, ld_x * 2, x_plane_stride * 2, BM);
   if (rc) return rc;
-  rc = make_map(&tb, w_planes, d, N, bp, d * 2, N * d * 2, BN / pair);
+  rc = make_map(&tb, w_planes, d, N, bp, ld_w * 2, N * ld_w * 2, BN / pair);
   if (rc) return rc;
 
   EncodeArgs args;
@@ -656,9 +677,14 @@ int encode_topk_launch(const void* x_planes, int ap, long long T, long long ld_x
   args.dense_out = dense_out;
   args.ld_dense = ld_dense;
 
+  if (g_profile) cudaEventRecord(g_ev0, stream);
   rc = (pair == 2) ? launch_planes<2>(ap, bp, ta, tb, args, plan.grid, plan.cap, stream)
                    : launch_planes<1>(ap, bp, ta, tb, args, plan.grid, plan.cap, stream);
   if (rc) return rc;
+  if (g_profile) {
+    cudaEventRecord(g_ev1, stream);
+    g_ev_valid = true;
+  }
 
   if (do_topk) {
     int kp2 = 1;

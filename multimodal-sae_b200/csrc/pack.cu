@@ -9,20 +9,16 @@
 
 namespace saeb {
 
-__global__ void pack_w_kernel(const float* __restrict__ W, long long n_elems, int planes,
+__global__ void pack_w_kernel(const float* __restrict__ W, long long N, long long d, long long d_pad, int planes,
                               __nv_bfloat16* __restrict__ out) {
-  const long long stride = (long long)gridDim.x * blockDim.x * 4;
-  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n_elems; i += stride) {
-    const float4 w = *reinterpret_cast<const float4*>(W + i);
-    const float f[4] = {w.x, w.y, w.z, w.w};
-    __nv_bfloat16 hi[4], lo[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      hi[j] = __float2bfloat16_rn(f[j]);
-      lo[j] = __float2bfloat16_rn(f[j] - __bfloat162float(hi[j]));
-    }
-    *reinterpret_cast<uint2*>(out + i) = *reinterpret_cast<uint2*>(hi);
-    if (planes > 1) *reinterpret_cast<uint2*>(out + n_elems + i) = *reinterpret_cast<uint2*>(lo);
+  const long long total = N * d_pad;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / d_pad, c = i - r * d_pad;
+    const float f = (c < d) ? W[r * d + c] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(f);
+    out[i] = hi;
+    if (planes > 1) out[total + i] = __float2bfloat16_rn(f - __bfloat162float(hi));
   }
 }
 
@@ -40,44 +36,48 @@ __global__ void fold_bias_kernel(const float* __restrict__ W, const float* __res
   if (lane == 0) out[row] = (float)((double)b_enc[row] - acc);
 }
 
+// activations -> `planes` bf16 planes [planes][T][d_pad] (zero padded columns); planes == 1 is a padded copy
 template <typename Tin>
-__global__ void split_x_kernel(const Tin* __restrict__ x, long long T, long long d, long long ld_x,
-                               __nv_bfloat16* __restrict__ out, long long plane_stride) {
-  const long long total = T * d;
+__global__ void split_x_kernel(const Tin* __restrict__ x, long long T, long long d, long long ld_x, long long d_pad,
+                               int planes, __nv_bfloat16* __restrict__ out) {
+  const long long total = T * d_pad;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const long long r = i / d, c = i - r * d;
-    const float f = (float)x[r * ld_x + c];
+    const long long r = i / d_pad, c = i - r * d_pad;
+    const float f = (c < d) ? (float)x[r * ld_x + c] : 0.f;
     const __nv_bfloat16 hi = __float2bfloat16_rn(f);
     out[i] = hi;
-    out[plane_stride + i] = __float2bfloat16_rn(f - __bfloat162float(hi));
+    if (planes > 1) out[total + i] = __float2bfloat16_rn(f - __bfloat162float(hi));
   }
 }
 
 int pack_weights_launch(const float* W_enc, const float* b_enc, const float* b_dec, long long N, long long d,
-                        int planes, void* w_planes, float* bias, cudaStream_t stream) {
-  SAEB_REQUIRE(N > 0 && d > 0 && d % 8 == 0, "pack: need N>0 and d a positive multiple of 8 (got N=%lld d=%lld)", N, d);
+                        long long d_pad, int planes, void* w_planes, float* bias, cudaStream_t stream) {
+  SAEB_REQUIRE(N > 0 && d > 0, "pack: need N>0 and d>0 (got N=%lld d=%lld)", N, d);
   SAEB_REQUIRE(planes == 1 || planes == 2, "pack: planes must be 1 or 2");
-  const long long n = N * d;
-  int blocks = (int)((n / 4 + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_w_kernel<<<blocks, 256, 0, stream>>>(W_enc, n, planes, reinterpret_cast<__nv_bfloat16*>(w_planes));
+  const long long n = N * d_pad;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  pack_w_kernel<<<blocks, 256, 0, stream>>>(W_enc, N, d, d_pad, planes, reinterpret_cast<__nv_bfloat16*>(w_planes));
   SAEB_CHECK_CUDA(cudaGetLastError());
   fold_bias_kernel<<<(int)((N + 7) / 8), 256, 0, stream>>>(W_enc, b_enc, b_dec, N, d, bias);
   SAEB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-int split_x_launch(const void* x, int x_dtype, long long T, long long d, long long ld_x, void* out,
-                   cudaStream_t stream) {
-  const long long total = T * d;
+int split_x_launch(const void* x, int x_dtype, long long T, long long d, long long ld_x, long long d_pad, int planes,
+                   void* out, cudaStream_t stream) {
+  const long long total = T * d_pad;
   int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > 148 * 32) blocks = 148 * 32;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   if (x_dtype == DT_F32)
-    split_x_kernel<float><<<blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(x), T, d, ld_x, o, total);
+    split_x_kernel<float><<<blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(x), T, d, ld_x, d_pad, planes, o);
   else if (x_dtype == DT_F16)
-    split_x_kernel<__half><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __half*>(x), T, d, ld_x, o, total);
+    split_x_kernel<__half><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __half*>(x), T, d, ld_x, d_pad, planes, o);
+  else if (x_dtype == DT_BF16)
+    split_x_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), T, d, ld_x,
+                                                              d_pad, planes, o);
   else {
     set_error("split_x: unsupported dtype %d", x_dtype);
     return -1;

@@ -81,8 +81,9 @@ class PackedEncoder:
         return self.blob[off:off + 4 * self.num_latents].view(torch.float32)
 
     def plane(self, i: int) -> torch.Tensor:
-        n = self.num_latents * self.d_in * 2
-        return self.blob[i * n:(i + 1) * n].view(torch.bfloat16).view(self.num_latents, self.d_in)
+        d_pad = (self.d_in + 7) // 8 * 8  # rows are padded to 16-byte multiples for TMA
+        n = self.num_latents * d_pad * 2
+        return self.blob[i * n:(i + 1) * n].view(torch.bfloat16).view(self.num_latents, d_pad)[:, :self.d_in]
 
 
 def _as_2d(x: torch.Tensor, d: int) -> torch.Tensor:
@@ -91,11 +92,14 @@ def _as_2d(x: torch.Tensor, d: int) -> torch.Tensor:
     x2 = x.reshape(-1, d)
     if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 8 != 0) or x2.data_ptr() % 16 != 0:
         x2 = x2.contiguous()
+        if x2.data_ptr() % 16 != 0:  # contiguous() can return a view of an odd-offset storage
+            x2 = x2.clone()
     return x2
 
 
 def encode_topk(x: torch.Tensor, enc: PackedEncoder, k: int, *, clamp_feature: int = -1, clamp_value: float = 0.0,
-                want_dense: bool = False, want_topk: bool = True
+                want_dense: bool = False, want_topk: bool = True, out_vals: Optional[torch.Tensor] = None,
+                out_idx: Optional[torch.Tensor] = None
                 ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
     """x [..., d] (bf16 / fp16 / fp32) -> (top_acts [..., k] f32, top_indices [..., k] i64, dense [..., N] f32 | None).
     Rows are ordered by (value desc, index asc)."""
@@ -107,8 +111,13 @@ def encode_topk(x: torch.Tensor, enc: PackedEncoder, k: int, *, clamp_feature: i
         x2 = x2.to(torch.float32)
     T = x2.shape[0]
     dev = x2.device
-    vals = torch.empty((T, k), dtype=torch.float32, device=dev) if want_topk else None
-    idx = torch.empty((T, k), dtype=torch.int64, device=dev) if want_topk else None
+    vals = idx = None
+    if want_topk:
+        vals = out_vals if out_vals is not None else torch.empty((T, k), dtype=torch.float32, device=dev)
+        idx = out_idx if out_idx is not None else torch.empty((T, k), dtype=torch.int64, device=dev)
+        if (vals.shape != (T, k) or idx.shape != (T, k) or vals.dtype != torch.float32 or idx.dtype != torch.int64
+                or not vals.is_contiguous() or not idx.is_contiguous()):
+            raise SaebError("out_vals / out_idx must be contiguous [T, k] float32 / int64 tensors")
     dense = torch.empty((T, enc.num_latents), dtype=torch.float32, device=dev) if want_dense else None
     if T > 0:
         with torch.cuda.device(dev):
@@ -130,7 +139,7 @@ def encode_topk(x: torch.Tensor, enc: PackedEncoder, k: int, *, clamp_feature: i
 
 def decode(top_indices: torch.Tensor, top_acts: torch.Tensor, W_dec: torch.Tensor, b_dec: Optional[torch.Tensor],
            *, out_dtype: torch.dtype = torch.float32, x: Optional[torch.Tensor] = None,
-           sq_err: Optional[torch.Tensor] = None) -> torch.Tensor:
+           sq_err: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[..., :] = sum_j acts[..., j] * W_dec[idx[..., j], :] + b_dec.  W_dec is the [N, d] parameter
     (fp32 parity grade, or a bf16 copy).  If `x` and `sq_err` (0-dim float64) are given, sum((out-x)^2) is added
     to sq_err."""
@@ -144,7 +153,12 @@ def decode(top_indices: torch.Tensor, top_acts: torch.Tensor, W_dec: torch.Tenso
     idx = top_indices.reshape(-1, k).to(torch.int64).contiguous()
     vals = top_acts.reshape(-1, k).to(torch.float32).contiguous()
     T = idx.shape[0]
-    out = torch.empty((T, d), dtype=out_dtype, device=idx.device)
+    if out is None:
+        out = torch.empty((T, d), dtype=out_dtype, device=idx.device)
+    elif out.shape != (T, d) or not out.is_contiguous() or out.dtype not in _DT:
+        raise SaebError("decode: `out` must be a contiguous [T, d] tensor")
+    else:
+        out_dtype = out.dtype
     if T == 0:
         return out.view(*lead, d)
     bd = None if b_dec is None else b_dec.detach().to(torch.float32).contiguous()

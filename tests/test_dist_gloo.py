@@ -1,0 +1,104 @@
+"""CPU, world_size 2 over gloo: the multi-GPU choreography of saeb200.dist (feature-sharded scan with the per-token
+threshold exchange and the single final all-gather; token-parallel slicing).  The per-rank compute steps are injected
+oracle-backed ops -- the CUDA ops are exercised by the -m gpu tests; here the collectives, offsets and merge are."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import sae_oracle as O
+
+
+class OracleOps:
+    """Same interface as saeb200.dist.EngineOps, computed with the oracle on CPU."""
+
+    def __init__(self, p, lo, hi, n_top, ctx_len):
+        self.p, self.feat_lo, self.feat_hi, self.n_top, self.ctx_len = p, lo, hi, n_top, ctx_len
+        self.sub = O.SaeParams(p.W_enc[lo:hi], p.b_enc[lo:hi], p.W_dec[lo:hi], p.b_dec, p.k)
+        self.acts, self.idx, self.thr = [], [], []
+
+    def encode_topk(self, x, k):
+        pa = O.pre_acts(self.sub, x.float())
+        v, i = pa.topk(k, sorted=True)
+        return v, i + self.feat_lo
+
+    def kth_of_gathered(self, gathered):
+        R, T, k = gathered.shape
+        return gathered.permute(1, 0, 2).reshape(T, R * k).topk(k).values[:, -1].contiguous()
+
+    def scan_update(self, vals, idx, window_base, tok_thr):
+        if tok_thr is not None:
+            vals = torch.where(vals >= tok_thr[:, None], vals, torch.zeros_like(vals))
+        self.acts.append(vals)
+        self.idx.append(idx)
+
+    def scan_finalize(self):
+        acts, idx = torch.cat(self.acts), torch.cat(self.idx)
+        s, w = O.scan_top_windows(acts, idx - self.feat_lo, self.feat_hi - self.feat_lo, self.ctx_len, self.n_top)
+        return torch.from_numpy(s), torch.from_numpy(w)
+
+
+def _worker(rank, world, port, exact, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "multimodal-sae_b200"))
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    from saeb200 import dist as sdist
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        N, d, k, ctx, n_top = 96, 32, 6, 8, 3
+        p = O.init_params(d, N, k, seed=77)
+        x = torch.randn(ctx * 12, d, generator=torch.Generator().manual_seed(78)).to(torch.bfloat16)
+        lo, hi = sdist.shard_range(N, world, rank)
+        ops = OracleOps(p, lo, hi, n_top, ctx)
+        chunks = [x[i:i + ctx * 4] for i in range(0, x.shape[0], ctx * 4)]
+        res = sdist.sharded_scan(chunks, ops, k, ctx, N, exact=exact)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), vals=res.top_vals.numpy(), win=res.top_win.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_feature_sharded_scan_two_ranks(tmp_path, exact):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), exact, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = (np.load(tmp_path / f"rank{r}.npz") for r in range(world))
+    assert np.array_equal(r0["vals"], r1["vals"]) and np.array_equal(r0["win"], r1["win"])  # all ranks agree
+    assert r0["vals"].shape == (96, 3)
+    # single-process ground truth
+    N, d, k, ctx, n_top = 96, 32, 6, 8, 3
+    p = O.init_params(d, N, k, seed=77)
+    x = torch.randn(ctx * 12, d, generator=torch.Generator().manual_seed(78)).to(torch.bfloat16)
+    enc = O.encode(p, x.float())
+    ref_s, ref_w = O.scan_top_windows(enc.top_acts, enc.top_indices, N, ctx, n_top)
+    if exact:  # the threshold exchange reproduces the global TopK mask exactly
+        np.testing.assert_array_equal(r0["vals"], ref_s)
+        np.testing.assert_array_equal(r0["win"], ref_w)
+    else:  # shard-local TopK keeps a superset of each token's latents: scores can only grow
+        assert (r0["vals"] >= ref_s - 1e-7).all() and not np.array_equal(r0["vals"], ref_s)
+
+
+def test_shard_and_token_ranges():
+    from saeb200.dist import shard_range, token_slice
+
+    for n, w in ((131072, 8), (100, 3), (7, 8)):
+        ranges = [shard_range(n, w, r) for r in range(w)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        sizes = [hi - lo for lo, hi in ranges]
+        assert max(sizes) - min(sizes) <= 1
+        assert [token_slice(n, w, r) for r in range(w)] == ranges
