@@ -37,6 +37,14 @@ ENC_FLOPS_PER_TOKEN = 2.0 * D_IN * WIDTH
 METRIC = "SAE tokens/sec (d=4096, width=131k, k=64, encode+TopK+decode)"
 
 
+PRECISION = {
+    3: "one fp16 tensor-core pass (activations exact after a power-of-two row scale, W_enc rounded to fp16, fp32 "
+       "accumulate) + exact fp32 re-evaluation of every candidate inside the rigorous rounding bound; fp32 W_dec",
+    2: "bf16 activations (exact) x bf16 hi+lo W_enc planes (two tensor-core passes), fp32 accumulate; fp32 W_dec",
+    1: "single bf16 pass (NOT parity grade; diagnostic only)",
+}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -172,6 +180,7 @@ def run_gpu(args):
         return float(t.item())
 
     sae = synth.make_sae(D_IN, WIDTH, K, dev, seed=1234)
+    sae.encoder_planes = args.planes
     enc = sae.packed_encoder()
     x = synth.make_activations(TOKENS, D_IN, dev, seed=1 + rank)
     acts = torch.empty((TOKENS, K), dtype=torch.float32, device=dev)
@@ -228,9 +237,10 @@ def run_gpu(args):
     roofline = {"bound": "tensor", "kernel": "encode_topk_kernel (tcgen05 GEMM + fused TopK)", "achieved": achieved,
                 "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
                 "traffic": traffic, "peak_source": f"{peaks['source']} bf16 sustained (cuBLAS, MEASURED_PEAKS.json)",
-                "kernel_ms": k_avg, "mma_passes": enc.planes,
+                "kernel_ms": k_avg, "mma_passes": 1 if enc.planes == 3 else enc.planes,
                 "path_frac": (value / world) * FLOPS_PER_TOKEN / 1e12 / peaks["tflops_sustained"],
-                "hbm_frac": (value / world) * (2 * D_IN + K * 12 + K * 4 * D_IN + 4 * D_IN + 2.0 * D_IN * WIDTH * enc.planes / TOKENS)
+                "hbm_frac": (value / world) * (2 * D_IN + K * 12 + K * 4 * D_IN + 4 * D_IN
+                                               + 2.0 * D_IN * WIDTH * (1 if enc.planes == 3 else enc.planes) / TOKENS)
                 / 1e9 / peaks["hbm_gbs"]}
 
     # ---- end to end through the reference-facing objects with host buffers (`e2e`)
@@ -258,7 +268,7 @@ def run_gpu(args):
         ctx_len, n_top, chunk = 64, 20, 16384
         lo, hi = sdist.shard_range(WIDTH, world, rank)
         ops = sdist.EngineOps(sae.encoder.weight.data[lo:hi], sae.encoder.bias.data[lo:hi], sae.b_dec.data, lo, hi,
-                              n_top, ctx_len, dev)
+                              n_top, ctx_len, dev, planes=args.planes)
         xs = synth.make_activations(args.scan_tokens, D_IN, dev, seed=99)  # same tokens on every rank
 
         def chunks():
@@ -292,7 +302,7 @@ def run_gpu(args):
             "config": {"workload": "C2: d_model=4096 width=131072 k=64 SAE forward over 65536 bf16 tokens per GPU "
                                    "(encode+TopK+decode+FVU), inputs resident in HBM",
                        "global_batch_tokens": world * TOKENS, "parallelism": f"token-parallel x{world}, SAE replicated",
-                       "precision": "bf16 activations (exact) x bf16 hi+lo W_enc planes, fp32 accumulate; fp32 W_dec",
+                       "precision": PRECISION[args.planes],
                        "l2": "inputs (x 512 MiB, weights 6 GiB) larger than the 126 MB L2"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "scan": scan, "fvu": fvu_val,
@@ -310,6 +320,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scan-tokens", type=int, default=262144)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--planes", type=int, default=3, choices=[1, 2, 3],
+                    help="encoder mode: 3 = fp16 pass + exact refinement (default), 2 = bf16 hi+lo, 1 = bf16 (diagnostic)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

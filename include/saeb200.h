@@ -36,7 +36,8 @@ const char* saeb_last_error(void);
 /* Number of kernel launches enqueued by this library in this process (bench.py's `gpu_launches` claim). */
 long long saeb_launch_count(void);
 /* Tuning knobs.  "cta_pair": 2 (default) = CTA pairs with tcgen05 cta_group::2 (256-row MMA tiles), 1 = single-CTA
- * tiles.  Results are identical; only throughput differs.  "profile": see saeb_profile_last_encode_ms. */
+ * tiles.  Results are identical; only throughput differs.  "profile": see saeb_profile_last_encode_ms.  "splits": feature-range splits per token tile
+ * (0 = automatic). */
 int saeb_set_option(const char* name, int value);
 /* With option "profile" = 1 the library brackets the fused encode kernel (main kernel only) with CUDA events on the
  * launching stream; this returns the duration in ms of the most recent one (synchronises on it), < 0 if none. */
@@ -45,7 +46,7 @@ float saeb_profile_last_encode_ms(void);
 /* ---- one-time weight repack -------------------------------------------------------------------------------
  * Reference parameters: `encoder.weight [N,d]`, `encoder.bias [N]`, `b_dec [d]` fp32 (sae/sae.py:59-66, loaded by
  * Sae.load_from_disk sae/sae.py:126-148).  Produces `planes` bf16 planes of W_enc (1: bf16(W); 2: hi + lo, the
- * parity-grade mode) followed by the folded bias b_enc - W_enc b_dec (sae/sae.py:174-175 rewritten as
+ * parity-grade mode; 3: the "fp16 + refine" layout used by saeb_encode_topk_refine) followed by the folded bias b_enc - W_enc b_dec (sae/sae.py:174-175 rewritten as
  * W x + (b_enc - W b_dec)).  Layout of `packed`: [planes][N][d_pad] bf16 with d_pad = d rounded up to 8 (16-byte
  * rows for TMA, zero padded), then [N] fp32 at saeb_packed_bias_offset().  Any d >= 1 is accepted. */
 size_t saeb_packed_weights_bytes(int64_t N, int64_t d, int planes);
@@ -69,6 +70,27 @@ size_t saeb_encode_topk_workspace_bytes(int64_t T, int64_t d, int64_t N, int k, 
 int saeb_encode_topk(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed, int planes, int64_t d,
                      int64_t N, int k, int64_t clamp_feature, float clamp_value, float* out_vals, int64_t* out_idx,
                      float* dense_out, int64_t ld_dense, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- fused encode + TopK, single tensor-core pass with exact refinement ("fp16 + refine") -------------------------
+ * Same result contract as saeb_encode_topk (parity grade) at half the tensor-core work.  `packed` must have been
+ * produced by saeb_pack_weights(..., planes = 3): one fp16 plane of W_enc (power-of-two scaled), folded bias,
+ * per-feature norms.  The GEMM ranks by approximate values; every candidate that can still belong to the TopK under the
+ * rigorous rounding bound  (2^-11 [+2^-11 for fp32 x] + 2^-12) * ||x||_2 * ||w_j||_2  is re-evaluated exactly in fp32
+ * against `W_enc` (the [N,d] fp32 parameter itself), so the returned values are fp32-exact and the index set is the
+ * fp32 reference's.  `margin` = extra candidates kept per row (0 = 64).  Rows whose candidate list could be too short
+ * for the bound (never observed) are recomputed by an exact dense fp32 kernel, up to 64 per call; *status_out (device
+ * int, may be NULL) receives the number of such rows -- more than 64 means the call must be repeated with a larger
+ * margin. */
+size_t saeb_encode_topk_refine_workspace_bytes(int64_t T, int64_t d, int64_t N, int k, int margin);
+int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed,
+                            const float* W_enc, int64_t d, int64_t N, int k, int margin, int64_t clamp_feature,
+                            float clamp_value, float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* TopK of dense non-negative rows, (value desc, index asc): Sae.select_topk (sae/sae.py:179-181) for callers that hold
+ * a dense [T, ld] latent tensor. */
+int saeb_dense_topk(const float* dense, int64_t T, int64_t ld, int64_t N, int k, float* out_vals, int64_t* out_idx,
+                    void* stream);
 
 /* ---- sparse decode ------------------------------------------------------------------------------------------
  * Replaces decoder_impl (sae/utils.py:107-129: triton_sparse_dense_matmul sae/kernels.py:178-284, or eager_decode

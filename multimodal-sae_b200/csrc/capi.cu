@@ -25,7 +25,21 @@ int encode_topk_launch(const void* x_planes, int ap, long long T, long long ld_x
                        const void* w_planes, int bp, long long ld_w, const float* bias, long long d, long long N, int k,
                        long long clamp_feature, float clamp_value, float* out_vals, long long* out_idx,
                        float* dense_out, long long ld_dense, void* workspace, size_t workspace_bytes, int pass_mask,
-                       cudaStream_t stream);
+                       int operand_fmt, const float* row_scale, const float* w_unscale, cudaStream_t stream);
+int pack_weights_f16_launch(const float* W_enc, const float* b_enc, const float* b_dec, long long N, long long d,
+                            long long d_pad, void* w_plane, float* bias, float* wnorm, float* trailer,
+                            cudaStream_t stream);
+int prep_x_f16_launch(const void* x, int x_dtype, long long T, long long d, long long ld_x, long long d_pad, void* out,
+                      float* row_scale, float* xnorm, cudaStream_t stream);
+size_t refine_fallback_bytes(long long N);
+int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const float* W, long long d, long long N,
+                  const float* bias, const float* wnorm, const float* trailer, const float* xnorm, float c_eps,
+                  const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
+                  float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
+                  float* dense_scratch, cudaStream_t stream);
+int dense_topk_launch(const float* dense, long long T, long long ld, long long N, int k, float* out_vals,
+                      long long* out_idx, cudaStream_t stream);
+int set_splits(int v);
 int pack_weights_launch(const float* W_enc, const float* b_enc, const float* b_dec, long long N, long long d,
                         long long d_pad, int planes, void* w_planes, float* bias, cudaStream_t stream);
 int split_x_launch(const void* x, int x_dtype, long long T, long long d, long long ld_x, long long d_pad, int planes,
@@ -53,9 +67,12 @@ float last_encode_ms();
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline long long pad8(long long d) { return (d + 7) / 8 * 8; }   // 16-byte row strides for TMA
+// planes: 1 / 2 = bf16 planes; 3 = "fp16 + refine" mode (one scaled fp16 plane + per-feature norms + trailer)
+static inline int n_planes(int planes) { return planes == 3 ? 1 : planes; }
 static inline size_t planes_bytes(long long N, long long d, int planes) {
-  return align_up((size_t)planes * (size_t)N * (size_t)pad8(d) * 2, 256);
+  return align_up((size_t)n_planes(planes) * (size_t)N * (size_t)pad8(d) * 2, 256);
 }
+static inline size_t bias_bytes(long long N) { return align_up((size_t)N * sizeof(float), 256); }
 // workspace for bf16 activation planes: none for bf16 input consumed in place (d % 8 == 0), one padded plane for
 // bf16 with d % 8 != 0, two planes for fp16 / fp32 input
 static inline size_t x_split_bytes(long long T, long long d, int x_dtype) {
@@ -77,6 +94,7 @@ int saeb_set_option(const char* name, int value) {
   SAEB_REQUIRE(name != nullptr, "set_option: null name");
   if (strcmp(name, "cta_pair") == 0) return set_cta_pair(value);
   if (strcmp(name, "profile") == 0) return set_profile(value);
+  if (strcmp(name, "splits") == 0) return set_splits(value);
   set_error("set_option: unknown option '%s'", name);
   return -1;
 }
@@ -85,14 +103,24 @@ float saeb_profile_last_encode_ms(void) { return last_encode_ms(); }
 
 size_t saeb_packed_bias_offset(int64_t N, int64_t d, int planes) { return planes_bytes(N, d, planes); }
 size_t saeb_packed_weights_bytes(int64_t N, int64_t d, int planes) {
-  return planes_bytes(N, d, planes) + align_up((size_t)N * sizeof(float), 256);
+  // bias [N]; mode 3 appends wnorm [N] and a 256-byte trailer {w_unscale, wnorm_max, scratch}
+  return planes_bytes(N, d, planes) + bias_bytes(N) + (planes == 3 ? bias_bytes(N) + 256 : 0);
 }
 
 int saeb_pack_weights(const float* W_enc, const float* b_enc, const float* b_dec, int64_t N, int64_t d, int planes,
                       void* packed, void* stream) {
   g_err[0] = 0;
   SAEB_REQUIRE(W_enc && b_enc && b_dec && packed, "pack_weights: null pointer");
+  SAEB_REQUIRE(planes >= 1 && planes <= 3, "pack_weights: planes must be 1, 2 or 3");
   float* bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + planes_bytes(N, d, planes));
+  if (planes == 3) {
+    float* wnorm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bias) + bias_bytes(N));
+    float* trailer = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(wnorm) + bias_bytes(N));
+    int rc3 = pack_weights_f16_launch(W_enc, b_enc, b_dec, N, d, pad8(d), packed, bias, wnorm, trailer,
+                                      (cudaStream_t)stream);
+    if (rc3 == 0) g_launches += 2;
+    return rc3;
+  }
   int rc = pack_weights_launch(W_enc, b_enc, b_dec, N, d, pad8(d), planes, packed, bias, (cudaStream_t)stream);
   if (rc == 0) g_launches += 2;
   return rc;
@@ -109,7 +137,7 @@ int saeb_encode_topk(const void* x, int x_dtype, int64_t T, int64_t ld_x, const 
   SAEB_REQUIRE(x && packed, "encode_topk: null pointer");
   SAEB_REQUIRE((out_vals != nullptr) == (out_idx != nullptr), "encode_topk: out_vals and out_idx go together");
   SAEB_REQUIRE(out_vals != nullptr || dense_out != nullptr, "encode_topk: nothing to compute");
-  SAEB_REQUIRE(planes == 1 || planes == 2, "encode_topk: planes must be 1 or 2");
+  SAEB_REQUIRE(planes == 1 || planes == 2, "encode_topk: planes must be 1 or 2 (mode 3 goes through saeb_encode_topk_refine)");
   SAEB_REQUIRE(x_dtype == DT_BF16 || x_dtype == DT_F16 || x_dtype == DT_F32, "encode_topk: bad x dtype %d", x_dtype);
   SAEB_REQUIRE(clamp_feature < N, "encode_topk: clamp_feature out of range");
   if (T == 0) return 0;
@@ -144,8 +172,102 @@ int saeb_encode_topk(const void* x, int x_dtype, int64_t T, int64_t ld_x, const 
     for (int b = 0; b < planes; ++b)
       if (!(a == 1 && b == 1)) pass_mask |= 1 << (a * planes + b);
   int rc = encode_topk_launch(xp, ap, T, ldx, xps, packed, planes, pad8(d), bias, d, N, k, clamp_feature, clamp_value, out_vals,
-                              reinterpret_cast<long long*>(out_idx), dense_out, ld_dense, ws, ws_left, pass_mask, st);
+                              reinterpret_cast<long long*>(out_idx), dense_out, ld_dense, ws, ws_left, pass_mask,
+                              /*operand_fmt=bf16*/ 1, nullptr, nullptr, st);
   if (rc == 0) g_launches += out_vals ? 2 : 1;
+  return rc;
+}
+
+// ---- "fp16 + refine": one tensor-core pass + exact fp32 re-evaluation of the candidates near the k-th value
+static inline int refine_k2(int k, int margin) {
+  int m = margin > 0 ? margin : 64;
+  int K2 = k + m;
+  if (K2 > 512) K2 = 512;
+  return K2;
+}
+struct RefineWs {
+  size_t x16, row_scale, xnorm, status, flag_rows, mvals, midx, dense, enc, total;
+};
+static RefineWs refine_ws(long long T, long long d, long long N, int k, int margin) {
+  RefineWs w;
+  const int K2 = refine_k2(k, margin);
+  size_t off = 0;
+  auto take = [&](size_t bytes, size_t al) {
+    off = align_up(off, al);
+    size_t at = off;
+    off += bytes;
+    return at;
+  };
+  w.x16 = take((size_t)T * pad8(d) * 2, 1024);
+  w.row_scale = take((size_t)T * 4, 256);
+  w.xnorm = take((size_t)T * 4, 256);
+  w.status = take(256, 256);
+  w.flag_rows = take(256, 256);
+  w.mvals = take((size_t)T * K2 * 4, 256);
+  w.midx = take((size_t)T * K2 * 8, 256);
+  w.dense = take(refine_fallback_bytes(N), 256);
+  w.enc = take(encode_workspace_bytes(T, d, N, K2), 1024);
+  w.total = align_up(off, 1024);
+  return w;
+}
+
+size_t saeb_encode_topk_refine_workspace_bytes(int64_t T, int64_t d, int64_t N, int k, int margin) {
+  return refine_ws(T, d, N, k, margin).total;
+}
+
+int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed,
+                            const float* W_enc, int64_t d, int64_t N, int k, int margin, int64_t clamp_feature,
+                            float clamp_value, float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  g_err[0] = 0;
+  SAEB_REQUIRE(x && packed && W_enc && out_vals && out_idx && workspace, "encode_topk_refine: null pointer");
+  SAEB_REQUIRE(x_dtype == DT_BF16 || x_dtype == DT_F16 || x_dtype == DT_F32, "encode_topk_refine: bad x dtype %d",
+               x_dtype);
+  SAEB_REQUIRE(clamp_feature < N, "encode_topk_refine: clamp_feature out of range");
+  SAEB_REQUIRE(k >= 1 && k <= N && k <= 448, "encode_topk_refine: k=%d out of range", k);
+  if (T == 0) return 0;
+  const int K2raw = refine_k2(k, margin);
+  const int K2 = K2raw < N ? K2raw : (int)N;
+  const RefineWs w = refine_ws(T, d, N, k, margin);
+  SAEB_REQUIRE(workspace_bytes >= w.total, "encode_topk_refine: workspace too small: have %zu need %zu",
+               workspace_bytes, w.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
+  const float* bias = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3));
+  const float* wnorm = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + bias_bytes(N));
+  const float* trailer = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + 2 * bias_bytes(N));
+  float* row_scale = reinterpret_cast<float*>(ws + w.row_scale);
+  float* xnorm = reinterpret_cast<float*>(ws + w.xnorm);
+  int* status = reinterpret_cast<int*>(ws + w.status);
+  int* flag_rows = reinterpret_cast<int*>(ws + w.flag_rows);
+  float* mvals = reinterpret_cast<float*>(ws + w.mvals);
+  long long* midx = reinterpret_cast<long long*>(ws + w.midx);
+  SAEB_CHECK_CUDA(cudaMemsetAsync(status, 0, 256, st));
+  int rc = prep_x_f16_launch(x, x_dtype, T, d, ld_x, pad8(d), ws + w.x16, row_scale, xnorm, st);
+  if (rc) return rc;
+  rc = encode_topk_launch(ws + w.x16, 1, T, pad8(d), (long long)T * pad8(d), packed, 1, pad8(d), bias, d, N, K2,
+                          clamp_feature, clamp_value, mvals, midx, nullptr, 0, ws + w.enc, w.total - w.enc, 1,
+                          /*operand_fmt=fp16*/ 0, row_scale, trailer, st);
+  if (rc) return rc;
+  // error-bound constant: fp16 rounding of W (2^-11), of x when it is fp32 (2^-11), and 2^-12 for the fp32 accumulation
+  const float c_eps = ldexpf(1.0f, -11) + (x_dtype == DT_F32 ? ldexpf(1.0f, -11) : 0.f) + ldexpf(1.0f, -12);
+  rc = refine_launch(x, x_dtype, T, ld_x, W_enc, d, N, bias, wnorm, trailer, xnorm, c_eps, mvals, midx, K2,
+                     k < K2 ? k : K2, clamp_feature, clamp_value, out_vals, reinterpret_cast<long long*>(out_idx),
+                     status, flag_rows, reinterpret_cast<float*>(ws + w.dense), st);
+  if (rc) return rc;
+  if (status_out != nullptr)
+    SAEB_CHECK_CUDA(cudaMemcpyAsync(status_out, status, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  g_launches += 7;
+  return 0;
+}
+
+int saeb_dense_topk(const float* dense, int64_t T, int64_t ld, int64_t N, int k, float* out_vals, int64_t* out_idx,
+                    void* stream) {
+  g_err[0] = 0;
+  SAEB_REQUIRE(dense && out_vals && out_idx, "dense_topk: null pointer");
+  int rc = dense_topk_launch(dense, T, ld, N, k, out_vals, reinterpret_cast<long long*>(out_idx), (cudaStream_t)stream);
+  if (rc == 0 && T > 0) g_launches += 1;
   return rc;
 }
 

@@ -52,6 +52,9 @@ struct EncodeArgs {
   int pass_mask;      // bit (a*BP+b) set -> issue MMA for (A plane a, B plane b)
   int clamp_col;      // steering: column forced to clamp_val before TopK (-1 = none)
   float clamp_val;
+  unsigned int idesc;       // tcgen05 instruction descriptor (operand formats are a run-time choice: bf16 or fp16)
+  const float* row_scale;   // optional [T]: per-row power-of-two factor undoing the activation pre-scale
+  const float* w_unscale;   // optional device scalar undoing the weight pre-scale
   const float* bias;  // folded bias [N]
   uint2* cand;        // [T][S][CAP] (value bits, column)
   int* cand_cnt;      // [T][S]
@@ -195,7 +198,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BM * PAIR, BN, 1, 1);
+      const uint32_t idesc = args.idesc;
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tile_iter = 0;
@@ -252,6 +255,8 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       uint2* cand = do_topk && valid ? args.cand + ((size_t)row * args.S + split) * CAP : nullptr;
       float thr = (valid && do_topk) ? 0.0f : __int_as_float(0x7f800000);   // +inf: never append
       int cnt = 0;
+      float sc = 1.0f;   // acc * sc + bias; exact powers of two when the operands were pre-scaled
+      if (args.row_scale != nullptr && valid) sc = __ldg(args.row_scale + row) * __ldg(args.w_unscale);
       for (int nt = nt0; nt < nt1; ++nt, ++tile_iter) {
         const uint32_t acc_stage = tile_iter & 1, acc_phase = (tile_iter >> 1) & 1;
         const int n_base = nt * BN;
@@ -286,10 +291,10 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 b4 = *reinterpret_cast<const float4*>(bias_w + c * 32 + j);
-            v[j + 0] = __uint_as_float(r[j + 0]) + b4.x;
-            v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-            v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
-            v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+            v[j + 0] = fmaf(__uint_as_float(r[j + 0]), sc, b4.x);
+            v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc, b4.y);
+            v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc, b4.z);
+            v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc, b4.w);
           }
           if (cj >= 0 && cj < 32) {
 #pragma unroll
@@ -512,14 +517,47 @@ static int num_sms() {
 
 int cap_for_k(int k) { return k <= 128 ? 256 : (k <= 256 ? 512 : 1024); }
 
-// how the feature range is split so that (m tiles x splits) fills the machine
-static int choose_splits(int num_m_tiles, int num_n_tiles, int num_clusters, int cap) {
+static int g_splits = 0;     // 0 = automatic
+int set_splits(int v) {
+  if (v < 0 || v > 64) {
+    set_error("splits must be in 0..64 (0 = automatic)");
+    return -1;
+  }
+  g_splits = v;
+  return 0;
+}
+
+// How the feature range is split.  Concurrently running clusters work on (clusters / S) different token tiles; each
+// live token tile keeps `a_tile_bytes` of activations hot in L2 and is re-read once per feature tile, so S is chosen
+// large enough that the live activation tiles stay L2-resident (ncu showed 130x DRAM over-fetch with 37 live 2 MB
+// tiles), and among the admissible values the one with the best wave balance wins.  Few token tiles (small T) raise S
+// so that every SM has work.
+static int choose_splits(int num_m_tiles, int num_n_tiles, int num_clusters, int cap, long long a_tile_bytes) {
+  const int s_max_smem = (200 * 1024) / (cap * 8);   // the merge kernel stages a row's candidates in shared memory
+  int s_cap = num_n_tiles < s_max_smem ? num_n_tiles : s_max_smem;
+  if (s_cap < 1) s_cap = 1;
   int S;
-  if (num_m_tiles >= num_clusters) S = 2;
-  else S = (num_clusters + num_m_tiles - 1) / num_m_tiles;
-  if (S > num_n_tiles) S = num_n_tiles;
-  const int s_max = (200 * 1024) / (cap * 8);   // merge kernel stages all candidates of a row in shared memory
-  if (S > s_max) S = s_max;
+  if (g_splits > 0) {
+    S = g_splits;
+  } else if (num_m_tiles * 2 <= num_clusters) {
+    S = (num_clusters + num_m_tiles - 1) / num_m_tiles;
+  } else {
+    const long long l2_budget = 36ll << 20;
+    int s_min = (int)((num_clusters * a_tile_bytes + l2_budget - 1) / l2_budget);
+    if (s_min < 2) s_min = 2;
+    S = s_min;
+    double best = -1.0;
+    for (int c = s_min; c <= s_min + 2; ++c) {
+      const long long units = (long long)num_m_tiles * c;
+      const long long waves = (units + num_clusters - 1) / num_clusters;
+      const double eff = (double)units / (double)(waves * num_clusters);
+      if (eff > best + 1e-9) {
+        best = eff;
+        S = c;
+      }
+    }
+  }
+  if (S > s_cap) S = s_cap;
   if (S < 1) S = 1;
   return S;
 }
@@ -529,7 +567,7 @@ struct EncodePlan {
   size_t cand_bytes, cnt_bytes;
 };
 
-static EncodePlan make_plan(long long T, long long N, int k, int pair) {
+static EncodePlan make_plan(long long T, long long N, int k, int pair, long long d = 4096, int ap = 1) {
   EncodePlan p;
   p.pair = pair;
   p.cap = cap_for_k(k);
@@ -537,7 +575,7 @@ static EncodePlan make_plan(long long T, long long N, int k, int pair) {
   p.num_n_tiles = (int)((N + BN - 1) / BN);
   const int sms = num_sms() > 0 ? num_sms() : 148;
   const int clusters = sms / pair;
-  p.S = choose_splits(p.num_m_tiles, p.num_n_tiles, clusters, p.cap);
+  p.S = choose_splits(p.num_m_tiles, p.num_n_tiles, clusters, p.cap, (long long)BM * pair * d * 2 * ap);
   int units = p.num_m_tiles * p.S;
   int use = units < clusters ? units : clusters;
   p.grid = use * pair;
@@ -586,9 +624,19 @@ int set_cta_pair(int v) {
 
 size_t encode_workspace_bytes(long long T, long long d, long long N, int k) {
   // worst case over both pair modes so that a caller-sized workspace is always enough
-  EncodePlan p1 = make_plan(T, N, k, 1), p2 = make_plan(T, N, k, 2);
-  size_t a = p1.cand_bytes + p1.cnt_bytes, b = p2.cand_bytes + p2.cnt_bytes;
-  return (a > b ? a : b) + 1024;
+  // upper bound over pair modes, plane counts and split overrides: S never exceeds the merge kernel's limit
+  const int cap = cap_for_k(k);
+  long long s_max = (200 * 1024) / (cap * 8);
+  const long long n_tiles = (N + BN - 1) / BN;
+  if (s_max > n_tiles) s_max = n_tiles;
+  EncodePlan p1 = make_plan(T, N, k, 1, d, 2), p2 = make_plan(T, N, k, 2, d, 2);
+  long long S = p1.S > p2.S ? p1.S : p2.S;
+  if (g_splits > S) S = g_splits;
+  if (S > s_max) S = s_max;
+  if (T > 4096 && S < 8) S = 8 < s_max ? 8 : s_max;   // room for later tuning without re-querying
+  const size_t cand = (size_t)T * S * cap * sizeof(uint2);
+  const size_t cnt = (((size_t)T * S * sizeof(int)) + 255) & ~(size_t)255;
+  return cand + cnt + 1024;
 }
 
 template <int AP, int BP, int PAIR, int SLOTS>
@@ -642,7 +690,7 @@ int encode_topk_launch(const void* x_planes, int ap, long long T, long long ld_x
                        const void* w_planes, int bp, long long ld_w, const float* bias, long long d, long long N, int k,
                        long long clamp_feature, float clamp_value, float* out_vals, long long* out_idx,
                        float* dense_out, long long ld_dense, void* workspace, size_t workspace_bytes, int pass_mask,
-                       cudaStream_t stream) {
+                       int operand_fmt, const float* row_scale, const float* w_unscale, cudaStream_t stream) {
   SAEB_REQUIRE(T > 0 && d > 0 && N > 0, "empty problem T=%lld d=%lld N=%lld", T, d, N);
   SAEB_REQUIRE(ld_w % 8 == 0 && ld_x % 8 == 0, "ld_w and ld_x must be multiples of 8 (16-byte TMA strides)");
   SAEB_REQUIRE(k >= 1 && k <= 512 && k <= N, "k=%d out of range (1..min(512,N))", k);
@@ -650,7 +698,7 @@ int encode_topk_launch(const void* x_planes, int ap, long long T, long long ld_x
   SAEB_REQUIRE((reinterpret_cast<uintptr_t>(x_planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_planes) & 15) == 0,
                "x / packed weights must be 16-byte aligned");
   const int pair = default_pair();
-  EncodePlan plan = make_plan(T, N, k, pair);
+  EncodePlan plan = make_plan(T, N, k, pair, d, ap);
   const bool do_topk = out_vals != nullptr;
   if (do_topk)
     SAEB_REQUIRE(workspace != nullptr && workspace_bytes >= plan.cand_bytes + plan.cnt_bytes,
@@ -671,6 +719,9 @@ int encode_topk_launch(const void* x_planes, int ap, long long T, long long ld_x
   args.pass_mask = pass_mask;
   args.clamp_col = (int)clamp_feature;
   args.clamp_val = clamp_value;
+  args.idesc = make_idesc_f16(BM * pair, BN, operand_fmt, operand_fmt);   // 0 = fp16 operands, 1 = bf16
+  args.row_scale = row_scale;
+  args.w_unscale = w_unscale;
   args.bias = bias;
   args.cand_cnt = do_topk ? reinterpret_cast<int*>(workspace) : nullptr;
   args.cand = do_topk ? reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(workspace) + plan.cnt_bytes) : nullptr;

@@ -86,4 +86,127 @@ int split_x_launch(const void* x, int x_dtype, long long T, long long d, long lo
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// mode 3 ("fp16 + refine"): one fp16 plane of W scaled by a power of two, per-feature norms, folded bias.
+// trailer = { w_unscale = 2^-s, wnorm_max }.  No host synchronisation: the scale lives in device memory.
+// ---------------------------------------------------------------------------------------------
+__global__ void w_stats_kernel(const float* __restrict__ W, const float* __restrict__ b_enc,
+                               const float* __restrict__ b_dec, long long N, long long d, float* __restrict__ bias,
+                               float* __restrict__ wnorm, unsigned int* __restrict__ absmax_bits,
+                               unsigned int* __restrict__ wnorm_max_bits) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  double dot = 0.0, sq = 0.0;
+  float amax = 0.f;
+  for (long long i = lane; i < d; i += 32) {
+    const float w = W[row * d + i];
+    dot += (double)w * (double)b_dec[i];
+    sq += (double)w * (double)w;
+    amax = fmaxf(amax, fabsf(w));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  }
+  if (lane == 0) {
+    bias[row] = (float)((double)b_enc[row] - dot);
+    const float nrm = (float)sqrt(sq) * (1.0f + 1e-6f);   // rounded up: it is used in an upper bound
+    wnorm[row] = nrm;
+    atomicMax(absmax_bits, __float_as_uint(amax));        // non-negative floats order like unsigned ints
+    atomicMax(wnorm_max_bits, __float_as_uint(nrm));
+  }
+}
+
+__global__ void pack_w_f16_kernel(const float* __restrict__ W, long long N, long long d, long long d_pad,
+                                  const unsigned int* __restrict__ absmax_bits, __half* __restrict__ out,
+                                  float* __restrict__ trailer) {
+  const float amax = __uint_as_float(*absmax_bits);
+  int e = 0;
+  if (amax > 0.f) frexpf(amax, &e);            // amax = m * 2^e, m in [0.5, 1)
+  const float scale = ldexpf(1.0f, 14 - e);    // largest |W| lands in [2^13, 2^14): far from fp16 overflow/underflow
+  if (blockIdx.x == 0 && threadIdx.x == 0) trailer[0] = ldexpf(1.0f, e - 14);
+  const long long total = N * d_pad;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / d_pad, c = i - r * d_pad;
+    out[i] = __float2half_rn((c < d) ? W[r * d + c] * scale : 0.f);
+  }
+}
+
+int pack_weights_f16_launch(const float* W_enc, const float* b_enc, const float* b_dec, long long N, long long d,
+                            long long d_pad, void* w_plane, float* bias, float* wnorm, float* trailer,
+                            cudaStream_t stream) {
+  SAEB_REQUIRE(N > 0 && d > 0, "pack: need N>0 and d>0 (got N=%lld d=%lld)", N, d);
+  // trailer[0] = w_unscale, trailer[1] = wnorm_max, trailer[2] = |W|max (scratch bits)
+  SAEB_CHECK_CUDA(cudaMemsetAsync(trailer, 0, 16, stream));
+  w_stats_kernel<<<(int)((N + 7) / 8), 256, 0, stream>>>(W_enc, b_enc, b_dec, N, d, bias, wnorm,
+                                                         reinterpret_cast<unsigned int*>(trailer + 2),
+                                                         reinterpret_cast<unsigned int*>(trailer + 1));
+  SAEB_CHECK_CUDA(cudaGetLastError());
+  const long long n = N * d_pad;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  pack_w_f16_kernel<<<blocks, 256, 0, stream>>>(W_enc, N, d, d_pad, reinterpret_cast<unsigned int*>(trailer + 2),
+                                                reinterpret_cast<__half*>(w_plane), trailer);
+  SAEB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// activations -> one fp16 plane [T][d_pad], each row scaled by a power of two so that its largest element lands in
+// [2^13, 2^14); row_scale[t] undoes it; xnorm[t] >= ||x_t||_2 (of the original activations).  bf16 / fp16 inputs are
+// represented exactly (up to fp16 underflow 2^-28 below the row maximum); fp32 inputs are rounded to 11 bits.
+template <typename Tin>
+__global__ void prep_x_f16_kernel(const Tin* __restrict__ x, long long T, long long d, long long ld_x, long long d_pad,
+                                  __half* __restrict__ out, float* __restrict__ row_scale, float* __restrict__ xnorm) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= T) return;
+  const Tin* xr = x + row * ld_x;
+  float amax = 0.f, sq = 0.f;
+  for (long long i = lane; i < d; i += 32) {
+    const float v = (float)xr[i];
+    amax = fmaxf(amax, fabsf(v));
+    sq = fmaf(v, v, sq);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  int e = 0;
+  if (amax > 0.f && amax < 3.0e38f) frexpf(amax, &e);
+  const float scale = ldexpf(1.0f, 14 - e);
+  if (lane == 0) {
+    row_scale[row] = ldexpf(1.0f, e - 14);
+    xnorm[row] = sqrtf(sq) * (1.0f + 1e-5f);
+  }
+  __half* o = out + row * d_pad;
+  for (long long i = lane; i < d_pad; i += 32) o[i] = __float2half_rn((i < d) ? (float)xr[i] * scale : 0.f);
+}
+
+int prep_x_f16_launch(const void* x, int x_dtype, long long T, long long d, long long ld_x, long long d_pad, void* out,
+                      float* row_scale, float* xnorm, cudaStream_t stream) {
+  const int wpb = 8;
+  const unsigned blocks = (unsigned)((T + wpb - 1) / wpb);
+  __half* o = reinterpret_cast<__half*>(out);
+  if (x_dtype == DT_F32)
+    prep_x_f16_kernel<float><<<blocks, wpb * 32, 0, stream>>>(reinterpret_cast<const float*>(x), T, d, ld_x, d_pad, o,
+                                                             row_scale, xnorm);
+  else if (x_dtype == DT_F16)
+    prep_x_f16_kernel<__half><<<blocks, wpb * 32, 0, stream>>>(reinterpret_cast<const __half*>(x), T, d, ld_x, d_pad, o,
+                                                              row_scale, xnorm);
+  else if (x_dtype == DT_BF16)
+    prep_x_f16_kernel<__nv_bfloat16><<<blocks, wpb * 32, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), T, d,
+                                                                     ld_x, d_pad, o, row_scale, xnorm);
+  else {
+    set_error("prep_x: unsupported dtype %d", x_dtype);
+    return -1;
+  }
+  SAEB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace saeb

@@ -1,0 +1,356 @@
+// Exact refinement of an approximate TopK ("fp16 + refine" mode) and the exact dense fallback.
+//
+// The fused GEMM runs ONE tensor-core pass with W_enc rounded to fp16 (11-bit significand) and returns, per row, the
+// K2 = k + margin best candidates by APPROXIMATE value a_j.  With u = 2^-11 the rounding error of candidate j is
+// bounded by  eps_j = c_eps * ||x||_2 * ||w_j||_2  (Cauchy-Schwarz; c_eps = u_w + u_x + accumulation slack).  Hence
+//   * the true k-th value is at least L = k-th largest of (a_j - eps_j);
+//   * only candidates with a_j + eps_j >= L can belong to the true TopK; they are re-evaluated EXACTLY here
+//     (fp32 dot product with the fp32 W_enc row + folded bias), and the final TopK is taken over the exact values;
+//   * a non-candidate has a <= a_last (the smallest kept approximation); if a_last + c_eps*||x||*max_j||w_j|| >= L
+//     the candidate list might be too short: the row is FLAGGED and recomputed by the exact dense kernels below.
+// Output values are fp32-exact like the reference's (sae/sae.py:172-181), the index set is the reference's up to
+// fp32 summation noise; the gather is HBM-bound (about (k + 20) fp32 rows per token).
+#include "common.cuh"
+
+namespace saeb {
+
+constexpr int RF_THREADS = 256;
+constexpr int RF_MAX_FLAG = 64;   // rows the dense fallback can absorb per call
+
+template <typename XT>
+__global__ void __launch_bounds__(RF_THREADS)
+refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict__ W, long long d, long long N,
+              const float* __restrict__ bias, const float* __restrict__ wnorm, const float* __restrict__ trailer,
+              const float* __restrict__ xnorm, float c_eps, const float* __restrict__ cand_vals,
+              const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
+              float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
+              int* __restrict__ flag_rows) {
+  extern __shared__ float rsm[];
+  float* xs = rsm;                                   // [d4] activations of this row as fp32
+  const int d4 = (int)((d + 3) & ~3ll);
+  float* a = xs + d4;                                // [K2] approximate values
+  float* lb = a + K2;                                // [K2]
+  float* ub = lb + K2;                               // [K2]
+  float* ex = ub + K2;                               // [K2] exact values (or -1)
+  int* f = reinterpret_cast<int*>(ex + K2);          // [K2] feature ids
+  __shared__ float s_L;
+  __shared__ int s_cnt[2];
+  const long long t = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int i = tid; i < d4; i += RF_THREADS) xs[i] = (i < d) ? (float)x[t * ld_x + i] : 0.f;
+  const float xn = xnorm[t];
+  const float wmax = trailer[1];
+  for (int j = tid; j < K2; j += RF_THREADS) {
+    const float av = cand_vals[t * K2 + j];
+    const int fj = (int)cand_idx[t * K2 + j];
+    const bool valid = av > 0.f;
+    const float eps = (fj == clamp_feature) ? 0.f : c_eps * xn * wnorm[fj];
+    a[j] = av;
+    f[j] = fj;
+    lb[j] = valid ? av - eps : -INFINITY;
+    ub[j] = valid ? av + eps : -INFINITY;
+    ex[j] = -1.f;
+  }
+  if (tid == 0) {
+    s_L = 0.f;
+    s_cnt[0] = 0;
+    s_cnt[1] = 0;
+  }
+  __syncthreads();
+  // L = k-th largest lower bound (0 if fewer than k positive candidates exist)
+  int my_valid = 0;
+  for (int j = tid; j < K2; j += RF_THREADS) {
+    if (a[j] > 0.f) {
+      ++my_valid;
+      int rank = 0;
+      const float l = lb[j];
+      for (int i = 0; i < K2; ++i) rank += (lb[i] > l || (lb[i] == l && i < j)) ? 1 : 0;
+      if (rank == k - 1) s_L = fmaxf(l, 0.f);
+    }
+  }
+  if (my_valid) atomicAdd(&s_cnt[0], my_valid);
+  __syncthreads();
+  const int nv = s_cnt[0];
+  const float L = (nv >= k) ? s_L : 0.f;
+  // list possibly too short?  (only when the list is full: otherwise every positive latent is already in it)
+  if (tid == 0 && nv == K2) {
+    const float a_last = a[K2 - 1];
+    if (a_last + c_eps * xn * wmax >= L) {
+      const int slot = atomicAdd(&status[0], 1);
+      if (slot < RF_MAX_FLAG) flag_rows[slot] = (int)t;
+    }
+  }
+  // exact re-evaluation of every candidate that can still be in the TopK
+  const bool vec = (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  for (int j = warp; j < K2; j += RF_THREADS / 32) {
+    if (!(ub[j] >= L) || !(a[j] > 0.f)) continue;
+    const int fj = f[j];
+    float val;
+    if (fj == clamp_feature) {
+      val = clamp_value;
+    } else {
+      const float* wr = W + (long long)fj * d;
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      if (vec) {
+        const float4* w4 = reinterpret_cast<const float4*>(wr);
+        const float4* x4 = reinterpret_cast<const float4*>(xs);
+        const int n4 = (int)(d >> 2);
+        int c = lane;
+        for (; c + 7 * 32 < n4; c += 8 * 32) {
+          float4 wv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) wv[u] = ldg_nc_f4(w4 + c + u * 32);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 xv = x4[c + u * 32];
+            acc0 = fmaf(wv[u].x, xv.x, acc0);
+            acc1 = fmaf(wv[u].y, xv.y, acc1);
+            acc2 = fmaf(wv[u].z, xv.z, acc2);
+            acc3 = fmaf(wv[u].w, xv.w, acc3);
+          }
+        }
+        for (; c < n4; c += 32) {
+          const float4 wv = ldg_nc_f4(w4 + c);
+          const float4 xv = x4[c];
+          acc0 = fmaf(wv.x, xv.x, acc0);
+          acc1 = fmaf(wv.y, xv.y, acc1);
+          acc2 = fmaf(wv.z, xv.z, acc2);
+          acc3 = fmaf(wv.w, xv.w, acc3);
+        }
+      } else {
+        for (long long i = lane; i < d; i += 32) acc0 = fmaf(wr[i], xs[i], acc0);
+      }
+      float acc = (acc0 + acc1) + (acc2 + acc3);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      val = acc + bias[fj];
+    }
+    if (lane == 0) ex[j] = (val > 0.f) ? val : -1.f;
+  }
+  __syncthreads();
+  // final TopK over the exact values: rank by (value desc, feature id asc)
+  int my_pos = 0;
+  for (int j = tid; j < K2; j += RF_THREADS) {
+    const float v = ex[j];
+    if (v > 0.f) {
+      ++my_pos;
+      int rank = 0;
+      const int fj = f[j];
+      for (int i = 0; i < K2; ++i) rank += (ex[i] > v || (ex[i] == v && f[i] < fj)) ? 1 : 0;
+      if (rank < k) {
+        out_vals[t * k + rank] = v;
+        out_idx[t * k + rank] = fj;
+      }
+    }
+  }
+  if (my_pos) atomicAdd(&s_cnt[1], my_pos);
+  __syncthreads();
+  const int npos = s_cnt[1];
+  if (npos < k && warp == 0) {
+    // fewer than k positive latents: pad with zeros on the smallest unused feature ids (as topk_merge_kernel does)
+    int filled = npos;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (long long base = 0; base < N && filled < k; base += 32) {
+      const long long jf = base + lane;
+      bool free_idx = jf < N;
+      for (int i = 0; i < K2 && free_idx; ++i) free_idx = !(ex[i] > 0.f && f[i] == (int)jf);
+      const uint32_t m = __ballot_sync(0xffffffffu, free_idx);
+      const int pos = filled + __popc(m & lt_mask);
+      if (free_idx && pos < k) {
+        out_vals[t * k + pos] = 0.f;
+        out_idx[t * k + pos] = jf;
+      }
+      filled += __popc(m);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact dense fallback for flagged rows: dense[slot][n] = relu(x_row . W[n] + bias[n]) in fp32, then a dense TopK
+// ---------------------------------------------------------------------------------------------
+template <typename XT>
+__global__ void __launch_bounds__(256)
+exact_rows_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict__ W, long long d, long long N,
+                  const float* __restrict__ bias, const int* __restrict__ status, const int* __restrict__ flag_rows,
+                  long long clamp_feature, float clamp_value, float* __restrict__ dense) {
+  extern __shared__ float esm[];
+  const int slot = blockIdx.y;
+  const int nflag = min(status[0], RF_MAX_FLAG);
+  if (slot >= nflag) return;
+  const long long t = flag_rows[slot];
+  for (long long i = threadIdx.x; i < d; i += blockDim.x) esm[i] = (float)x[t * ld_x + i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long per_block = (N + gridDim.x - 1) / gridDim.x;
+  const long long n0 = (long long)blockIdx.x * per_block;
+  const long long n1 = (n0 + per_block < N) ? n0 + per_block : N;
+  for (long long n = n0 + warp; n < n1; n += nw) {
+    const float* wr = W + n * d;
+    float acc = 0.f;
+    for (long long i = lane; i < d; i += 32) acc = fmaf(wr[i], esm[i], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      float v = acc + bias[n];
+      if (n == clamp_feature) v = clamp_value;
+      dense[(long long)slot * N + n] = fmaxf(v, 0.f);
+    }
+  }
+}
+
+// TopK of dense non-negative rows (value desc, index asc).  `row_map` (optional) redirects output rows; rows beyond
+// `*n_rows_dev` (optional device count) exit.  One block per row.  Also serves Sae.select_topk on dense tensors.
+__global__ void __launch_bounds__(1024)
+dense_topk_kernel(const float* __restrict__ dense, long long ld, long long N, int k, const int* __restrict__ n_rows_dev,
+                  int max_rows, const int* __restrict__ row_map, float* __restrict__ out_vals,
+                  long long* __restrict__ out_idx) {
+  extern __shared__ uint2 dsm[];   // [kp2] selected (value bits, index)
+  __shared__ int s_red[32];
+  __shared__ int s_count;
+  __shared__ uint32_t s_idx_cut;
+  const int slot = blockIdx.x;
+  if (n_rows_dev != nullptr && slot >= min(*n_rows_dev, max_rows)) return;
+  const long long orow = row_map ? row_map[slot] : slot;
+  const float* row = dense + (long long)slot * ld;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  auto block_sum = [&](int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    int s = 0;
+    for (int w = 0; w < nw; ++w) s += s_red[w];
+    return s;
+  };
+  auto keyof = [&](long long i) { return __float_as_uint(fmaxf(row[i], 0.f)); };
+  int kp2 = 2;
+  while (kp2 < k) kp2 <<= 1;
+  // k-th largest key
+  uint32_t prefix = 0;
+  for (int bit = 30; bit >= 0; --bit) {
+    const uint32_t trial = prefix | (1u << bit);
+    int c = 0;
+    for (long long i = tid; i < N; i += blockDim.x) c += (keyof(i) >= trial) ? 1 : 0;
+    if (block_sum(c) >= k) prefix = trial;
+  }
+  int c_gt = 0, c_eq = 0;
+  for (long long i = tid; i < N; i += blockDim.x) {
+    const uint32_t key = keyof(i);
+    c_gt += key > prefix;
+    c_eq += key == prefix;
+  }
+  c_gt = block_sum(c_gt);
+  c_eq = block_sum(c_eq);
+  const int need_eq = k - c_gt;
+  uint32_t idx_cut = 0xffffffffu;
+  if (c_eq > need_eq) {
+    uint32_t p2 = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t trial = p2 | (1u << bit);
+      int c = 0;
+      for (long long i = tid; i < N; i += blockDim.x) c += (keyof(i) == prefix && (uint32_t)i < trial) ? 1 : 0;
+      if (block_sum(c) < need_eq) p2 = trial;
+    }
+    idx_cut = p2;
+  }
+  if (tid == 0) s_count = 0;
+  for (int i = tid; i < kp2; i += blockDim.x) dsm[i] = make_uint2(0u, 0xffffffffu);
+  __syncthreads();
+  for (long long i = tid; i < N; i += blockDim.x) {
+    const uint32_t key = keyof(i);
+    if (key > prefix || (key == prefix && (uint32_t)i <= idx_cut)) {
+      const int p = atomicAdd(&s_count, 1);
+      if (p < kp2) dsm[p] = make_uint2(key, (uint32_t)i);
+    }
+  }
+  __syncthreads();
+  for (int size = 2; size <= kp2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int p = tid; p < (kp2 >> 1); p += blockDim.x) {
+        const int lo = ((p / stride) * stride * 2) + (p % stride);
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const uint2 a = dsm[lo], b = dsm[hi];
+        const bool a_first = (a.x > b.x) || (a.x == b.x && a.y < b.y);
+        if (a_first != desc) {
+          dsm[lo] = b;
+          dsm[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < k; i += blockDim.x) {
+    out_vals[orow * k + i] = __uint_as_float(dsm[i].x);
+    out_idx[orow * k + i] = (long long)dsm[i].y;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+size_t refine_fallback_bytes(long long N) { return (size_t)RF_MAX_FLAG * (size_t)N * sizeof(float) + 1024; }
+
+template <typename XT>
+static int refine_launch_t(const XT* x, long long T, long long ld_x, const float* W, long long d, long long N,
+                           const float* bias, const float* wnorm, const float* trailer, const float* xnorm, float c_eps,
+                           const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
+                           float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
+                           float* dense_scratch, cudaStream_t stream) {
+  const int d4 = (int)((d + 3) & ~3ll);
+  const size_t smem = (size_t)(d4 + 5 * K2) * sizeof(float);
+  SAEB_REQUIRE(smem <= 200 * 1024, "refine: d=%lld too large for the shared-memory row buffer", d);
+  auto kern = refine_kernel<XT>;
+  SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)T, RF_THREADS, smem, stream>>>(x, ld_x, W, d, N, bias, wnorm, trailer, xnorm, c_eps, cand_vals,
+                                                 cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx,
+                                                 status, flag_rows);
+  SAEB_CHECK_CUDA(cudaGetLastError());
+  // exact dense fallback for the (normally zero) flagged rows; the grids exit at once when nothing is flagged
+  auto ek = exact_rows_kernel<XT>;
+  const size_t esmem = (size_t)d * sizeof(float);
+  SAEB_CHECK_CUDA(cudaFuncSetAttribute(ek, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+  dim3 eg(128, RF_MAX_FLAG);
+  ek<<<eg, 256, esmem, stream>>>(x, ld_x, W, d, N, bias, status, flag_rows, clamp_feature, clamp_value,
+                                 dense_scratch);
+  SAEB_CHECK_CUDA(cudaGetLastError());
+  int kp2 = 2;
+  while (kp2 < k) kp2 <<= 1;
+  dense_topk_kernel<<<RF_MAX_FLAG, 1024, (size_t)kp2 * sizeof(uint2), stream>>>(
+      dense_scratch, N, N, k, status, RF_MAX_FLAG, flag_rows, out_vals, out_idx);
+  SAEB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const float* W, long long d, long long N,
+                  const float* bias, const float* wnorm, const float* trailer, const float* xnorm, float c_eps,
+                  const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
+                  float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
+                  float* dense_scratch, cudaStream_t stream) {
+#define SAEB_RF(XT)                                                                                                  \
+  return refine_launch_t<XT>(reinterpret_cast<const XT*>(x), T, ld_x, W, d, N, bias, wnorm, trailer, xnorm, c_eps,   \
+                             cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx, status,      \
+                             flag_rows, dense_scratch, stream)
+  if (x_dtype == DT_F32) SAEB_RF(float);
+  if (x_dtype == DT_BF16) SAEB_RF(__nv_bfloat16);
+  if (x_dtype == DT_F16) SAEB_RF(__half);
+#undef SAEB_RF
+  set_error("refine: unsupported x dtype %d", x_dtype);
+  return -1;
+}
+
+int dense_topk_launch(const float* dense, long long T, long long ld, long long N, int k, float* out_vals,
+                      long long* out_idx, cudaStream_t stream) {
+  SAEB_REQUIRE(T >= 0 && N >= 1 && k >= 1 && k <= N && k <= 4096, "dense_topk: bad arguments");
+  if (T == 0) return 0;
+  int kp2 = 2;
+  while (kp2 < k) kp2 <<= 1;
+  dense_topk_kernel<<<(unsigned)T, 1024, (size_t)kp2 * sizeof(uint2), stream>>>(dense, ld, N, k, nullptr, 0, nullptr,
+                                                                               out_vals, out_idx);
+  SAEB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace saeb

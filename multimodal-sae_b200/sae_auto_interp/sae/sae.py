@@ -57,10 +57,10 @@ class Sae(nn.Module):
         if decoder and cfg.normalize_decoder:
             self.set_decoder_norm_to_unit_norm()
         self.b_dec = nn.Parameter(torch.zeros(d_in, dtype=dtype, device=device))
-        # device-side repack of the encoder (bf16 hi/lo planes + folded bias); rebuilt when parameters change
-        self.encoder_planes = 2
-        self._packed: Optional[engine.PackedEncoder] = None
-        self._packed_key = None
+        # device-side repack of the encoder, rebuilt when parameters change.  encoder_planes selects the parity-grade
+        # mode of `encode`: 3 = one fp16 tensor-core pass + exact fp32 refinement (default), 2 = bf16 hi+lo (two passes)
+        self.encoder_planes = 3
+        self._packed = {}
 
     # ------------------------------------------------------------------ loading / saving
     @staticmethod
@@ -122,29 +122,28 @@ class Sae(nn.Module):
         return self.encoder.weight.dtype
 
     # ------------------------------------------------------------------ engine plumbing
-    def packed_encoder(self) -> engine.PackedEncoder:
+    def packed_encoder(self, planes: Optional[int] = None) -> engine.PackedEncoder:
+        planes = self.encoder_planes if planes is None else planes
         w, b, bd = self.encoder.weight, self.encoder.bias, self.b_dec
-        key = (w.data_ptr(), w._version, b.data_ptr(), b._version, bd.data_ptr(), bd._version, self.encoder_planes)
-        if self._packed is None or key != self._packed_key:
+        key = (w.data_ptr(), w._version, b.data_ptr(), b._version, bd.data_ptr(), bd._version)
+        hit = self._packed.get(planes)
+        if hit is None or hit[0] != key:
             if not w.is_cuda:
                 raise SaebError("Sae lives on the CPU: the B200 engine has no CPU path, move it to a CUDA device")
-            self._packed = engine.PackedEncoder.pack(w.data, b.data, bd.data, self.encoder_planes)
-            self._packed_key = key
-        return self._packed
+            self._packed[planes] = (key, engine.PackedEncoder.pack(w.data, b.data, bd.data, planes))
+        return self._packed[planes][1]
 
     # ------------------------------------------------------------------ reference API
     def pre_acts(self, x: Tensor) -> Tensor:
         """Dense relu(W_enc (x - b_dec) + b_enc), shape [..., num_latents] fp32 (reference sae/sae.py:172-177).
         Kept for callers that need the dense tensor; `encode` / `forward` never materialise it."""
-        _, _, dense = engine.encode_topk(x, self.packed_encoder(), self.cfg.k, want_dense=True, want_topk=False)
+        _, _, dense = engine.encode_topk(x, self.packed_encoder(2), self.cfg.k, want_dense=True, want_topk=False)
         return dense
 
     def select_topk(self, latents: Tensor) -> EncoderOutput:
         """Top-k of an already dense latent tensor (reference sae/sae.py:179-181).  Only reached by callers that
         built the dense tensor themselves (e.g. after editing it); the fused path is `encode`."""
-        if not latents.is_cuda:
-            raise SaebError("select_topk needs a CUDA tensor: there is no CPU path")
-        return EncoderOutput(*latents.topk(self.cfg.k, sorted=False))
+        return EncoderOutput(*engine.dense_topk(latents, self.cfg.k))
 
     def encode(self, x: Tensor, *, clamp_feature: int = -1, clamp_value: float = 0.0) -> EncoderOutput:
         """Fused encoder GEMM + TopK (reference sae/sae.py:183-185).  Rows come back ordered by

@@ -59,7 +59,8 @@ class PackedEncoder:
     blob: torch.Tensor  # uint8
     num_latents: int
     d_in: int
-    planes: int
+    planes: int  # 1 / 2: bf16 planes (2 = hi+lo, parity grade); 3: one fp16 plane + exact refinement (parity grade)
+    W_enc: Optional[torch.Tensor] = None  # mode 3 re-evaluates candidates against the fp32 parameter itself
 
     @staticmethod
     def pack(W_enc: torch.Tensor, b_enc: torch.Tensor, b_dec: torch.Tensor, planes: int = 2) -> "PackedEncoder":
@@ -74,7 +75,7 @@ class PackedEncoder:
         with torch.cuda.device(W.device):
             check(L.saeb_pack_weights(W.data_ptr(), be.data_ptr(), bd.data_ptr(), N, d, planes, blob.data_ptr(),
                                       _stream()), "saeb_pack_weights")
-        return PackedEncoder(blob, N, d, planes)
+        return PackedEncoder(blob, N, d, planes, W if planes == 3 else None)
 
     def folded_bias(self) -> torch.Tensor:
         off = _capi.lib().saeb_packed_bias_offset(self.num_latents, self.d_in, self.planes)
@@ -99,7 +100,7 @@ def _as_2d(x: torch.Tensor, d: int) -> torch.Tensor:
 
 def encode_topk(x: torch.Tensor, enc: PackedEncoder, k: int, *, clamp_feature: int = -1, clamp_value: float = 0.0,
                 want_dense: bool = False, want_topk: bool = True, out_vals: Optional[torch.Tensor] = None,
-                out_idx: Optional[torch.Tensor] = None
+                out_idx: Optional[torch.Tensor] = None, refine_margin: int = 0
                 ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
     """x [..., d] (bf16 / fp16 / fp32) -> (top_acts [..., k] f32, top_indices [..., k] i64, dense [..., N] f32 | None).
     Rows are ordered by (value desc, index asc)."""
@@ -111,6 +112,8 @@ def encode_topk(x: torch.Tensor, enc: PackedEncoder, k: int, *, clamp_feature: i
         x2 = x2.to(torch.float32)
     T = x2.shape[0]
     dev = x2.device
+    if enc.planes == 3 and want_dense:
+        raise SaebError("dense pre-activations need a bf16 hi+lo packed encoder (planes=2), not the refine mode")
     vals = idx = None
     if want_topk:
         vals = out_vals if out_vals is not None else torch.empty((T, k), dtype=torch.float32, device=dev)
@@ -119,7 +122,19 @@ def encode_topk(x: torch.Tensor, enc: PackedEncoder, k: int, *, clamp_feature: i
                 or not vals.is_contiguous() or not idx.is_contiguous()):
             raise SaebError("out_vals / out_idx must be contiguous [T, k] float32 / int64 tensors")
     dense = torch.empty((T, enc.num_latents), dtype=torch.float32, device=dev) if want_dense else None
-    if T > 0:
+    if T > 0 and enc.planes == 3:
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            nbytes = L.saeb_encode_topk_refine_workspace_bytes(T, enc.d_in, enc.num_latents, k, refine_margin)
+            ws = _workspace(dev, nbytes)
+            check(L.saeb_encode_topk_refine(x2.data_ptr(), _code(x2), T, x2.stride(0) if T > 1 else enc.d_in,
+                                            enc.blob.data_ptr(), enc.W_enc.data_ptr(), enc.d_in, enc.num_latents, k,
+                                            refine_margin,
+                                            clamp_feature, float(clamp_value), vals.data_ptr(), idx.data_ptr(),
+                                            status.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                  "saeb_encode_topk_refine")
+        encode_topk.last_status = status
+    elif T > 0:
         with torch.cuda.device(dev):
             nbytes = L.saeb_encode_topk_workspace_bytes(T, enc.d_in, enc.num_latents, k, _code(x2))
             ws = _workspace(dev, nbytes)
@@ -135,6 +150,27 @@ def encode_topk(x: torch.Tensor, enc: PackedEncoder, k: int, *, clamp_feature: i
     if want_dense:
         dense = dense.view(*lead, enc.num_latents)
     return vals, idx, dense
+
+
+encode_topk.last_status = None  # device int: rows that went through the exact dense fallback in the last refine call
+
+
+def dense_topk(latents: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """TopK of a dense non-negative latent tensor [..., N] -> (values, int64 indices), (value desc, index asc)."""
+    _need_cuda(latents)
+    L = _capi.lib()
+    N = latents.shape[-1]
+    lead = latents.shape[:-1]
+    x2 = latents.reshape(-1, N).to(torch.float32)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    T = x2.shape[0]
+    vals = torch.empty((T, k), dtype=torch.float32, device=x2.device)
+    idx = torch.empty((T, k), dtype=torch.int64, device=x2.device)
+    with torch.cuda.device(x2.device):
+        check(L.saeb_dense_topk(x2.data_ptr(), T, x2.stride(0) if T > 1 else N, N, k, vals.data_ptr(), idx.data_ptr(),
+                                _stream()), "saeb_dense_topk")
+    return vals.view(*lead, k), idx.view(*lead, k)
 
 
 def decode(top_indices: torch.Tensor, top_acts: torch.Tensor, W_dec: torch.Tensor, b_dec: Optional[torch.Tensor],

@@ -26,9 +26,8 @@ def make_sae(d_in: int, num_latents: int, k: int, device, seed: int = 1234):
     Wd /= torch.norm(Wd, dim=1, keepdim=True) + torch.finfo(torch.float32).eps
     sae.W_dec = torch.nn.Parameter(Wd)
     sae.b_dec = torch.nn.Parameter(torch.randn(d_in, device=device, generator=g) * 0.1)
-    sae.encoder_planes = 2
-    sae._packed = None
-    sae._packed_key = None
+    sae.encoder_planes = 3
+    sae._packed = {}
     sae.requires_grad_(False)
     return sae
 

@@ -19,7 +19,7 @@ REL = 1e-3  # tolerance stated by the north star for floating-point outputs
 TIE_REL = 2e-5  # rows whose fp64 k/(k+1) gap is below this (x value) may pick either boundary element
 
 
-def _sae_from_params(p: O.SaeParams, planes: int = 2):
+def _sae_from_params(p: O.SaeParams, planes: int = 3):
     from sae_auto_interp.sae import Sae, SaeConfig
 
     sae = Sae(p.d_in, SaeConfig(num_latents=p.num_latents, k=p.k), device=DEV)
@@ -58,12 +58,13 @@ def _assert_topk_parity(p, x_cpu, acts, idx, *, audit=True):
 # ---------------------------------------------------------------------------------------------
 # golden vectors produced by the reference itself
 # ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("planes", [3, 2])
 @pytest.mark.parametrize("name", ["forward_c1.npz", "forward_c1_bf16.npz", "forward_wide.npz"])
-def test_forward_matches_reference_golden(name):
+def test_forward_matches_reference_golden(name, planes):
     """reference Sae.forward (sae/sae.py:193-247) on BASELINE config 1 and two more small shapes."""
     g = np.load(os.path.join(GOLDEN, name))
     p = _params(g)
-    sae = _sae_from_params(p)
+    sae = _sae_from_params(p, planes)
     x = torch.from_numpy(g["x"])
     xin = x.to(DEV).to(torch.bfloat16) if "bf16" in name or "wide" in name else x.to(DEV)
     out = sae(xin)
@@ -119,21 +120,25 @@ def test_decode_property_random_shapes():
 # ---------------------------------------------------------------------------------------------
 # oracle at sizes it finishes in seconds
 # ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("planes", [3, 2])
 @pytest.mark.parametrize("T,d,N,k,cta_pair", [
     (1024, 1024, 16384, 64, 2), (1024, 1024, 16384, 64, 1), (300, 520, 2048 + 40, 32, 2), (257, 128, 512, 16, 2), (100, 50, 100, 10, 2), (40, 100, 333, 7, 1),
     (64, 4096, 8192, 256, 2), (5, 64, 256, 1, 2), (1, 4096, 4096, 64, 2)])
-def test_encode_topk_vs_oracle(T, d, N, k, cta_pair):
+def test_encode_topk_vs_oracle(T, d, N, k, cta_pair, planes):
     """Fused encode+TopK vs reference pre_acts + topk (sae/sae.py:172-185): ragged T / N / d, k from 1 to 256,
-    single CTA and CTA-pair tiles."""
+    single CTA and CTA-pair tiles, both parity-grade modes (3: fp16 pass + exact refinement, 2: bf16 hi+lo)."""
     from saeb200 import _capi
 
     _capi.check(_capi.lib().saeb_set_option(b"cta_pair", cta_pair), "set_option")
     try:
         p = O.init_params(d, N, k, seed=100 + T)
         x = torch.randn(T, d, generator=torch.Generator().manual_seed(T)).to(torch.bfloat16)
-        sae = _sae_from_params(p)
+        sae = _sae_from_params(p, planes)
         enc = sae.encode(x.to(DEV))
         _assert_topk_parity(p, x.float(), enc.top_acts, enc.top_indices)
+        if planes == 3:
+            from saeb200 import engine
+            assert int(engine.encode_topk.last_status.item()) == 0, "rows needed the dense fallback"
     finally:
         _capi.lib().saeb_set_option(b"cta_pair", 2)
 
@@ -171,6 +176,35 @@ def test_full_width_with_tie_audit():
     rel = (out.sae_out.cpu() - ref.sae_out).norm(dim=1) / ref.sae_out.norm(dim=1)
     assert float(rel.max()) < REL
     np.testing.assert_allclose(float(out.fvu), float(ref.fvu), rtol=REL)
+
+
+def test_refine_dense_fallback_rows():
+    """A margin of one extra candidate cannot certify most rows: they must come out right through the exact dense
+    fallback (at most 64 rows per call), and the status word must report them."""
+    from saeb200 import engine
+
+    p = O.init_params(256, 4096, 16, seed=41)
+    x = torch.randn(48, 256, generator=torch.Generator().manual_seed(42)).to(torch.bfloat16)
+    sae = _sae_from_params(p, 3)
+    acts, idx, _ = engine.encode_topk(x.to(DEV), sae.packed_encoder(), 16, refine_margin=1)
+    n_flag = int(engine.encode_topk.last_status.item())
+    assert 0 < n_flag <= 48
+    _assert_topk_parity(p, x.float(), acts, idx)
+
+
+def test_refine_values_are_fp32_exact():
+    """In refine mode the returned activations are fp32 dot products against the fp32 weights: they agree with the
+    oracle to fp32 summation noise (1e-5 relative), far inside the 1e-3 bar."""
+    p = O.init_params(1024, 8192, 32, seed=43)
+    x = torch.randn(256, 1024, generator=torch.Generator().manual_seed(44)).to(torch.bfloat16)
+    sae = _sae_from_params(p, 3)
+    enc = sae.encode(x.to(DEV))
+    ref = O.encode(p, x.float())
+    ri, rv = O.canonical_topk(ref.top_acts, ref.top_indices)
+    gi, gv = O.canonical_topk(enc.top_acts.cpu(), enc.top_indices.cpu())
+    same = (gi == ri).all(-1)
+    assert same.mean() > 0.99
+    np.testing.assert_allclose(gv[same], rv[same], rtol=1e-5, atol=1e-6)
 
 
 def test_exact_arithmetic_tier():
@@ -227,10 +261,20 @@ def test_pre_acts_dense_and_select_topk():
     ref = O.pre_acts(p, x.float())
     assert dense.shape == ref.shape
     torch.testing.assert_close(dense.cpu(), ref, rtol=REL, atol=2e-5)
-    enc = sae.select_topk(dense)
-    gi, _ = O.canonical_topk(enc.top_acts.cpu(), enc.top_indices.cpu())
-    ri, _ = O.canonical_topk(*ref.topk(8))
+    enc = sae.select_topk(dense)  # native dense TopK kernel
+    gi, gv = O.canonical_topk(enc.top_acts.cpu(), enc.top_indices.cpu())
+    ri, rv = O.canonical_topk(*ref.topk(8))
     assert np.array_equal(gi, ri)
+    dv, di = dense.topk(8)
+    assert torch.equal(enc.top_acts, dv) and bool((enc.top_acts[:, :-1] >= enc.top_acts[:, 1:]).all())
+    # ties and rows with fewer than k positives: lowest index first, zeros padded on distinct ids
+    z = torch.zeros(3, 40, device=DEV)
+    z[0, [5, 9, 30]] = torch.tensor([2.0, 2.0, 1.0], device=DEV)
+    from saeb200 import engine
+
+    zv, zi = engine.dense_topk(z, 4)
+    assert zi[0].tolist() == [5, 9, 30, 0] and zv[0].tolist() == [2.0, 2.0, 1.0, 0.0]
+    assert zi[1].tolist() == [0, 1, 2, 3]
 
 
 def test_empty_input():

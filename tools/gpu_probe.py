@@ -70,8 +70,11 @@ def exp_topk(pair, planes, T, d, N, k, xdt="bf16"):
     return dict(rows=T, rows_with_set_mismatch=bad_rows, max_rel_val_err=maxrel, sorted_desc=sorted_ok)
 
 
-def exp_time(pair, planes, T, d, N, k, iters=3):
+def exp_time(pair, planes, T, d, N, k, iters=3, splits=0):
     torch, engine = _setup(pair)
+    from saeb200 import _capi
+    _capi.check(_capi.lib().saeb_set_option(b"splits", splits), "set_option")
+    _capi.check(_capi.lib().saeb_set_option(b"profile", 1), "set_option")
     g = torch.Generator(device="cuda").manual_seed(3)
     W = (torch.rand(N, d, device="cuda", generator=g) * 2 - 1) / d ** 0.5
     be = torch.randn(N, device="cuda", generator=g) * 0.01
@@ -85,11 +88,12 @@ def exp_time(pair, planes, T, d, N, k, iters=3):
         vals, idx, _ = engine.encode_topk(x, enc, k)
     torch.cuda.synchronize()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    te, td = [], []
+    te, td, tk = [], [], []
     for _ in range(iters):
         e0.record()
         vals, idx, _ = engine.encode_topk(x, enc, k)
         e1.record()
+        tk.append(float(_capi.lib().saeb_profile_last_encode_ms()))
         y = engine.decode(idx, vals, Wd, bd)
         e2.record()
         torch.cuda.synchronize()
@@ -97,6 +101,9 @@ def exp_time(pair, planes, T, d, N, k, iters=3):
         td.append(e1.elapsed_time(e2))
     flops = 2.0 * T * d * N
     out["encode_ms"] = te
+    out["gemm_kernel_ms"] = tk
+    if planes == 3:
+        out["flagged_rows"] = int(engine.encode_topk.last_status.item())
     out["decode_ms"] = td
     out["encode_tflops_alg"] = flops / (min(te) * 1e-3) / 1e12
     out["decode_GBs"] = (T * k * d * 4 + T * d * 4 + T * k * 12) / (min(td) * 1e-3) / 1e9
@@ -137,6 +144,18 @@ EXPS = {
     "time_p1_2pl": lambda: exp_time(1, 2, 16384, 4096, 131072, 64),
     "time_p1_1pl": lambda: exp_time(1, 1, 16384, 4096, 131072, 64),
     "time_p2_2pl_64k": lambda: exp_time(2, 2, 65536, 4096, 131072, 64, iters=2),
+    "topk_refine": lambda: exp_topk(2, 3, 2048, 1024, 16384, 64),
+    "topk_refine_full": lambda: exp_topk(2, 3, 2048, 4096, 131072, 64),
+    "topk_refine_f32x": lambda: exp_topk(2, 3, 1024, 1024, 16384, 64, "f32"),
+    "time_refine_16k": lambda: exp_time(2, 3, 16384, 4096, 131072, 64),
+    "time_refine_64k": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2),
+    "time_refine_64k_s2": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=2),
+    "time_refine_64k_s4": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=4),
+    "time_refine_64k_s6": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=6),
+    "time_refine_64k_s8": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=8),
+    "time_hilo_64k_s2": lambda: exp_time(2, 2, 65536, 4096, 131072, 64, iters=2, splits=2),
+    "time_hilo_64k_s4": lambda: exp_time(2, 2, 65536, 4096, 131072, 64, iters=2, splits=4),
+    "time_hilo_64k_s8": lambda: exp_time(2, 2, 65536, 4096, 131072, 64, iters=2, splits=8),
 }
 
 if __name__ == "__main__":
