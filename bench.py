@@ -188,10 +188,19 @@ def run_gpu(args):
     sae_out = torch.empty((TOKENS, D_IN), dtype=torch.float32, device=dev)
     sq_err = torch.zeros((), dtype=torch.float64, device=dev)
 
+    ov = None
+    if args.planes == 3 and not args.no_overlap:
+        from saeb200.overlap import OverlappedForward
+
+        ov = OverlappedForward(enc, sae.W_dec.data, sae.b_dec.data, K, chunk=args.chunk)
+
     def step():
         sq_err.zero_()
-        engine.encode_topk(x, enc, K, out_vals=acts, out_idx=idx)
-        engine.decode(idx, acts, sae.W_dec.data, sae.b_dec.data, x=x, sq_err=sq_err, out=sae_out)
+        if ov is not None:   # GEMM of chunk c+1 on one stream, refinement + decode of chunk c on another
+            ov.run(x, acts, idx, sae_out, sq_err)
+        else:
+            engine.encode_topk(x, enc, K, out_vals=acts, out_idx=idx)
+            engine.decode(idx, acts, sae.W_dec.data, sae.b_dec.data, x=x, sq_err=sq_err, out=sae_out)
         return (sq_err / engine.total_variance(x)).to(torch.float32)
 
     # ---- device-resident throughput (`value`)
@@ -247,7 +256,7 @@ def run_gpu(args):
     x_host = synth.make_activations(TOKENS, D_IN, dev, seed=1 + rank, pinned_host=True)
     acts_host = torch.empty((TOKENS, K), dtype=torch.float32, pin_memory=True)
     idx_host = torch.empty((TOKENS, K), dtype=torch.int64, pin_memory=True)
-    hf = pipeline.HostForward(sae, TOKENS, chunk=8192)
+    hf = pipeline.HostForward(sae, TOKENS, chunk=args.chunk)
     for _ in range(max(1, min(args.warmup, 2))):
         hf.run(x_host, acts_host, idx_host)
     barrier()
@@ -320,6 +329,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scan-tokens", type=int, default=262144)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run the phases of a step back to back on one stream")
+    ap.add_argument("--chunk", type=int, default=8192, help="tokens per pipeline chunk")
     ap.add_argument("--planes", type=int, default=3, choices=[1, 2, 3],
                     help="encoder mode: 3 = fp16 pass + exact refinement (default), 2 = bf16 hi+lo, 1 = bf16 (diagnostic)")
     args = ap.parse_args()

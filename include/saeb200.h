@@ -87,6 +87,17 @@ int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x,
                             float clamp_value, float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
                             size_t workspace_bytes, void* stream);
 
+/* The two phases of saeb_encode_topk_refine as separate calls over the same workspace, so that a caller can run the
+ * tensor-core-bound phase A of the next token chunk concurrently (other stream) with the HBM-bound phase B and decode
+ * of the previous one: A = activation prep + GEMM + candidate merge, B = exact refinement (+ dense fallback). */
+int saeb_encode_candidates(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed, int64_t d,
+                           int64_t N, int k, int margin, int64_t clamp_feature, float clamp_value, void* workspace,
+                           size_t workspace_bytes, void* stream);
+int saeb_refine_candidates(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed,
+                           const float* W_enc, int64_t d, int64_t N, int k, int margin, int64_t clamp_feature,
+                           float clamp_value, float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* TopK of dense non-negative rows, (value desc, index asc): Sae.select_topk (sae/sae.py:179-181) for callers that hold
  * a dense [T, ld] latent tensor. */
 int saeb_dense_topk(const float* dense, int64_t T, int64_t ld, int64_t N, int k, float* out_vals, int64_t* out_idx,

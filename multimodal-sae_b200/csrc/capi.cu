@@ -40,6 +40,7 @@ int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const
 int dense_topk_launch(const float* dense, long long T, long long ld, long long N, int k, float* out_vals,
                       long long* out_idx, cudaStream_t stream);
 int set_splits(int v);
+int set_l2_hints(int v);
 int pack_weights_launch(const float* W_enc, const float* b_enc, const float* b_dec, long long N, long long d,
                         long long d_pad, int planes, void* w_planes, float* bias, cudaStream_t stream);
 int split_x_launch(const void* x, int x_dtype, long long T, long long d, long long ld_x, long long d_pad, int planes,
@@ -95,6 +96,7 @@ int saeb_set_option(const char* name, int value) {
   if (strcmp(name, "cta_pair") == 0) return set_cta_pair(value);
   if (strcmp(name, "profile") == 0) return set_profile(value);
   if (strcmp(name, "splits") == 0) return set_splits(value);
+  if (strcmp(name, "l2_hints") == 0) return set_l2_hints(value);
   set_error("set_option: unknown option '%s'", name);
   return -1;
 }
@@ -215,51 +217,85 @@ size_t saeb_encode_topk_refine_workspace_bytes(int64_t T, int64_t d, int64_t N, 
   return refine_ws(T, d, N, k, margin).total;
 }
 
-int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed,
-                            const float* W_enc, int64_t d, int64_t N, int k, int margin, int64_t clamp_feature,
-                            float clamp_value, float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
-                            size_t workspace_bytes, void* stream) {
+// phase A: activation prep + single-pass GEMM with fused candidate selection + merge -> K2 candidates per row in the
+// workspace (tensor-core bound)
+int saeb_encode_candidates(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed, int64_t d,
+                           int64_t N, int k, int margin, int64_t clamp_feature, float clamp_value, void* workspace,
+                           size_t workspace_bytes, void* stream) {
   g_err[0] = 0;
-  SAEB_REQUIRE(x && packed && W_enc && out_vals && out_idx && workspace, "encode_topk_refine: null pointer");
-  SAEB_REQUIRE(x_dtype == DT_BF16 || x_dtype == DT_F16 || x_dtype == DT_F32, "encode_topk_refine: bad x dtype %d",
+  SAEB_REQUIRE(x && packed && workspace, "encode_candidates: null pointer");
+  SAEB_REQUIRE(x_dtype == DT_BF16 || x_dtype == DT_F16 || x_dtype == DT_F32, "encode_candidates: bad x dtype %d",
                x_dtype);
-  SAEB_REQUIRE(clamp_feature < N, "encode_topk_refine: clamp_feature out of range");
-  SAEB_REQUIRE(k >= 1 && k <= N && k <= 448, "encode_topk_refine: k=%d out of range", k);
+  SAEB_REQUIRE(clamp_feature < N, "encode_candidates: clamp_feature out of range");
+  SAEB_REQUIRE(k >= 1 && k <= N && k <= 448, "encode_candidates: k=%d out of range", k);
   if (T == 0) return 0;
   const int K2raw = refine_k2(k, margin);
   const int K2 = K2raw < N ? K2raw : (int)N;
   const RefineWs w = refine_ws(T, d, N, k, margin);
-  SAEB_REQUIRE(workspace_bytes >= w.total, "encode_topk_refine: workspace too small: have %zu need %zu",
+  SAEB_REQUIRE(workspace_bytes >= w.total, "encode_candidates: workspace too small: have %zu need %zu",
                workspace_bytes, w.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
+  const float* bias = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3));
+  const float* trailer = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + 2 * bias_bytes(N));
+  float* row_scale = reinterpret_cast<float*>(ws + w.row_scale);
+  float* xnorm = reinterpret_cast<float*>(ws + w.xnorm);
+  int rc = prep_x_f16_launch(x, x_dtype, T, d, ld_x, pad8(d), ws + w.x16, row_scale, xnorm, st);
+  if (rc) return rc;
+  rc = encode_topk_launch(ws + w.x16, 1, T, pad8(d), (long long)T * pad8(d), packed, 1, pad8(d), bias, d, N, K2,
+                          clamp_feature, clamp_value, reinterpret_cast<float*>(ws + w.mvals),
+                          reinterpret_cast<long long*>(ws + w.midx), nullptr, 0, ws + w.enc, w.total - w.enc, 1,
+                          /*operand_fmt=fp16*/ 0, row_scale, trailer, st);
+  if (rc) return rc;
+  g_launches += 3;
+  return 0;
+}
+
+// phase B: exact fp32 re-evaluation of the candidates left in the workspace by phase A (HBM bound)
+int saeb_refine_candidates(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed,
+                           const float* W_enc, int64_t d, int64_t N, int k, int margin, int64_t clamp_feature,
+                           float clamp_value, float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  g_err[0] = 0;
+  SAEB_REQUIRE(x && packed && W_enc && out_vals && out_idx && workspace, "refine_candidates: null pointer");
+  if (T == 0) return 0;
+  const int K2raw = refine_k2(k, margin);
+  const int K2 = K2raw < N ? K2raw : (int)N;
+  const RefineWs w = refine_ws(T, d, N, k, margin);
+  SAEB_REQUIRE(workspace_bytes >= w.total, "refine_candidates: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
   const float* bias = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3));
   const float* wnorm = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + bias_bytes(N));
   const float* trailer = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + 2 * bias_bytes(N));
-  float* row_scale = reinterpret_cast<float*>(ws + w.row_scale);
-  float* xnorm = reinterpret_cast<float*>(ws + w.xnorm);
   int* status = reinterpret_cast<int*>(ws + w.status);
-  int* flag_rows = reinterpret_cast<int*>(ws + w.flag_rows);
-  float* mvals = reinterpret_cast<float*>(ws + w.mvals);
-  long long* midx = reinterpret_cast<long long*>(ws + w.midx);
   SAEB_CHECK_CUDA(cudaMemsetAsync(status, 0, 256, st));
-  int rc = prep_x_f16_launch(x, x_dtype, T, d, ld_x, pad8(d), ws + w.x16, row_scale, xnorm, st);
-  if (rc) return rc;
-  rc = encode_topk_launch(ws + w.x16, 1, T, pad8(d), (long long)T * pad8(d), packed, 1, pad8(d), bias, d, N, K2,
-                          clamp_feature, clamp_value, mvals, midx, nullptr, 0, ws + w.enc, w.total - w.enc, 1,
-                          /*operand_fmt=fp16*/ 0, row_scale, trailer, st);
-  if (rc) return rc;
   // error-bound constant: fp16 rounding of W (2^-11), of x when it is fp32 (2^-11), and 2^-12 for the fp32 accumulation
   const float c_eps = ldexpf(1.0f, -11) + (x_dtype == DT_F32 ? ldexpf(1.0f, -11) : 0.f) + ldexpf(1.0f, -12);
-  rc = refine_launch(x, x_dtype, T, ld_x, W_enc, d, N, bias, wnorm, trailer, xnorm, c_eps, mvals, midx, K2,
-                     k < K2 ? k : K2, clamp_feature, clamp_value, out_vals, reinterpret_cast<long long*>(out_idx),
-                     status, flag_rows, reinterpret_cast<float*>(ws + w.dense), st);
+  int rc = refine_launch(x, x_dtype, T, ld_x, W_enc, d, N, bias, wnorm, trailer,
+                         reinterpret_cast<const float*>(ws + w.xnorm), c_eps,
+                         reinterpret_cast<const float*>(ws + w.mvals), reinterpret_cast<const long long*>(ws + w.midx),
+                         K2, k < K2 ? k : K2, clamp_feature, clamp_value, out_vals,
+                         reinterpret_cast<long long*>(out_idx), status, reinterpret_cast<int*>(ws + w.flag_rows),
+                         reinterpret_cast<float*>(ws + w.dense), st);
   if (rc) return rc;
   if (status_out != nullptr)
     SAEB_CHECK_CUDA(cudaMemcpyAsync(status_out, status, sizeof(int), cudaMemcpyDeviceToDevice, st));
-  g_launches += 7;
+  g_launches += 4;
   return 0;
+}
+
+int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed,
+                            const float* W_enc, int64_t d, int64_t N, int k, int margin, int64_t clamp_feature,
+                            float clamp_value, float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  int rc = saeb_encode_candidates(x, x_dtype, T, ld_x, packed, d, N, k, margin, clamp_feature, clamp_value, workspace,
+                                  workspace_bytes, stream);
+  if (rc) return rc;
+  return saeb_refine_candidates(x, x_dtype, T, ld_x, packed, W_enc, d, N, k, margin, clamp_feature, clamp_value,
+                                out_vals, out_idx, status_out, workspace, workspace_bytes, stream);
 }
 
 int saeb_dense_topk(const float* dense, int64_t T, int64_t ld, int64_t N, int k, float* out_vals, int64_t* out_idx,

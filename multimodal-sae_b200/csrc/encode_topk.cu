@@ -52,6 +52,7 @@ struct EncodeArgs {
   int pass_mask;      // bit (a*BP+b) set -> issue MMA for (A plane a, B plane b)
   int clamp_col;      // steering: column forced to clamp_val before TopK (-1 = none)
   float clamp_val;
+  unsigned long long hint_a, hint_b;   // L2 eviction policies of the activation / weight TMA loads
   unsigned int idesc;       // tcgen05 instruction descriptor (operand formats are a run-time choice: bf16 or fp16)
   const float* row_scale;   // optional [T]: per-row power-of-two factor undoing the activation pre-scale
   const float* w_unscale;   // optional device scalar undoing the weight pre-scale
@@ -177,18 +178,20 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             if constexpr (PAIR == 1) {
               mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE);
 #pragma unroll
-              for (int a = 0; a < AP; ++a) tma_load_3d(sa + a * Cfg::A_PLANE, &tm_a, &full_bar[stage], kb * BK, m0, a);
+              for (int a = 0; a < AP; ++a)
+                tma_load_3d(sa + a * Cfg::A_PLANE, &tm_a, &full_bar[stage], kb * BK, m0, a, args.hint_a);
 #pragma unroll
-              for (int b = 0; b < BP; ++b) tma_load_3d(sb + b * Cfg::B_PLANE, &tm_b, &full_bar[stage], kb * BK, n0, b);
+              for (int b = 0; b < BP; ++b)
+                tma_load_3d(sb + b * Cfg::B_PLANE, &tm_b, &full_bar[stage], kb * BK, n0, b, args.hint_b);
             } else {
               if (leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE * 2);
               else mbar_arrive_cluster(&full_bar[stage], 0);
 #pragma unroll
               for (int a = 0; a < AP; ++a)
-                tma_load_3d_pair(sa + a * Cfg::A_PLANE, &tm_a, &full_bar[stage], kb * BK, m0, a);
+                tma_load_3d_pair(sa + a * Cfg::A_PLANE, &tm_a, &full_bar[stage], kb * BK, m0, a, args.hint_a);
 #pragma unroll
               for (int b = 0; b < BP; ++b)
-                tma_load_3d_pair(sb + b * Cfg::B_PLANE, &tm_b, &full_bar[stage], kb * BK, n0, b);
+                tma_load_3d_pair(sb + b * Cfg::B_PLANE, &tm_b, &full_bar[stage], kb * BK, n0, b, args.hint_b);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -517,6 +520,11 @@ static int num_sms() {
 
 int cap_for_k(int k) { return k <= 128 ? 256 : (k <= 256 ? 512 : 1024); }
 
+static int g_l2_hints = 1;   // 1: activation tiles evict_last (they are re-read once per feature tile), weights normal
+int set_l2_hints(int v) {
+  g_l2_hints = v;
+  return 0;
+}
 static int g_splits = 0;     // 0 = automatic
 int set_splits(int v) {
   if (v < 0 || v > 64) {
@@ -527,13 +535,16 @@ int set_splits(int v) {
   return 0;
 }
 
-// How the feature range is split.  Concurrently running clusters work on (clusters / S) different token tiles; each
-// live token tile keeps `a_tile_bytes` of activations hot in L2 and is re-read once per feature tile, so S is chosen
-// large enough that the live activation tiles stay L2-resident (ncu showed 130x DRAM over-fetch with 37 live 2 MB
-// tiles), and among the admissible values the one with the best wave balance wins.  Few token tiles (small T) raise S
-// so that every SM has work.
-static int choose_splits(int num_m_tiles, int num_n_tiles, int num_clusters, int cap, long long a_tile_bytes) {
-  const int s_max_smem = (200 * 1024) / (cap * 8);   // the merge kernel stages a row's candidates in shared memory
+// How the feature range is split: (token tiles x splits) must fill the machine.  Few token tiles (small T) raise S so
+// that every SM has work; `saeb_set_option("splits", n)` overrides.
+static int merge_max_splits(int cap, int k) {
+  int kp2 = 2;
+  while (kp2 < k) kp2 <<= 1;
+  const int s = (200 * 1024 - kp2 * 8) / (cap * 8);   // the merge kernel stages a row's candidates in shared memory
+  return s < 1 ? 1 : s;
+}
+static int choose_splits(int num_m_tiles, int num_n_tiles, int num_clusters, int cap, int k) {
+  const int s_max_smem = merge_max_splits(cap, k);
   int s_cap = num_n_tiles < s_max_smem ? num_n_tiles : s_max_smem;
   if (s_cap < 1) s_cap = 1;
   int S;
@@ -542,20 +553,9 @@ static int choose_splits(int num_m_tiles, int num_n_tiles, int num_clusters, int
   } else if (num_m_tiles * 2 <= num_clusters) {
     S = (num_clusters + num_m_tiles - 1) / num_m_tiles;
   } else {
-    const long long l2_budget = 36ll << 20;
-    int s_min = (int)((num_clusters * a_tile_bytes + l2_budget - 1) / l2_budget);
-    if (s_min < 2) s_min = 2;
-    S = s_min;
-    double best = -1.0;
-    for (int c = s_min; c <= s_min + 2; ++c) {
-      const long long units = (long long)num_m_tiles * c;
-      const long long waves = (units + num_clusters - 1) / num_clusters;
-      const double eff = (double)units / (double)(waves * num_clusters);
-      if (eff > best + 1e-9) {
-        best = eff;
-        S = c;
-      }
-    }
+    // measured (profiles/r01_probe_splits.log): S = 2 is fastest at large T -- every split restarts its running
+    // threshold from zero, and that early compaction-heavy phase costs more than the L2 over-fetch it would save
+    S = 2;
   }
   if (S > s_cap) S = s_cap;
   if (S < 1) S = 1;
@@ -575,7 +575,7 @@ static EncodePlan make_plan(long long T, long long N, int k, int pair, long long
   p.num_n_tiles = (int)((N + BN - 1) / BN);
   const int sms = num_sms() > 0 ? num_sms() : 148;
   const int clusters = sms / pair;
-  p.S = choose_splits(p.num_m_tiles, p.num_n_tiles, clusters, p.cap, (long long)BM * pair * d * 2 * ap);
+  p.S = choose_splits(p.num_m_tiles, p.num_n_tiles, clusters, p.cap, k);
   int units = p.num_m_tiles * p.S;
   int use = units < clusters ? units : clusters;
   p.grid = use * pair;
@@ -626,7 +626,7 @@ size_t encode_workspace_bytes(long long T, long long d, long long N, int k) {
   // worst case over both pair modes so that a caller-sized workspace is always enough
   // upper bound over pair modes, plane counts and split overrides: S never exceeds the merge kernel's limit
   const int cap = cap_for_k(k);
-  long long s_max = (200 * 1024) / (cap * 8);
+  long long s_max = merge_max_splits(cap, k);
   const long long n_tiles = (N + BN - 1) / BN;
   if (s_max > n_tiles) s_max = n_tiles;
   EncodePlan p1 = make_plan(T, N, k, 1, d, 2), p2 = make_plan(T, N, k, 2, d, 2);
@@ -719,6 +719,8 @@ int encode_topk_launch(const void* x_planes, int ap, long long T, long long ld_x
   args.pass_mask = pass_mask;
   args.clamp_col = (int)clamp_feature;
   args.clamp_val = clamp_value;
+  args.hint_a = (g_l2_hints & 1) ? L2_EVICT_LAST : L2_EVICT_NORMAL;
+  args.hint_b = (g_l2_hints & 2) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
   args.idesc = make_idesc_f16(BM * pair, BN, operand_fmt, operand_fmt);   // 0 = fp16 operands, 1 = bf16
   args.row_scale = row_scale;
   args.w_unscale = w_unscale;

@@ -61,6 +61,8 @@ class Sae(nn.Module):
         # mode of `encode`: 3 = one fp16 tensor-core pass + exact fp32 refinement (default), 2 = bf16 hi+lo (two passes)
         self.encoder_planes = 3
         self._packed = {}
+        self._overlap = None
+        self.overlap_chunk = 8192
 
     # ------------------------------------------------------------------ loading / saving
     @staticmethod
@@ -164,10 +166,29 @@ class Sae(nn.Module):
         if dead_mask is not None or self.cfg.multi_topk:
             raise NotImplementedError("AuxK / Multi-TopK losses are training-only and outside the inference engine")
         assert self.W_dec is not None, "Decoder weight was not initialized."
-        top_acts, top_indices = self.encode(x)
-        sq_err = torch.zeros((), dtype=torch.float64, device=top_acts.device)
-        sae_out = engine.decode(top_indices, top_acts, self.W_dec.data, self.b_dec.data, out_dtype=torch.float32,
-                                x=x, sq_err=sq_err)
+        x2 = x.reshape(-1, self.d_in)
+        T = x2.shape[0]
+        if self.encoder_planes == 3 and T >= 2 * self.overlap_chunk and x2.is_cuda:
+            # large batches: GEMM of chunk c+1 overlaps the HBM-bound refinement + decode of chunk c (two streams)
+            from saeb200.overlap import OverlappedForward
+
+            enc = self.packed_encoder()
+            if self._overlap is None or self._overlap.enc is not enc:
+                self._overlap = OverlappedForward(enc, self.W_dec.data, self.b_dec.data, self.cfg.k, self.overlap_chunk)
+            xin = engine._as_2d(x2, self.d_in)
+            top_acts = torch.empty((T, self.cfg.k), dtype=torch.float32, device=x.device)
+            top_indices = torch.empty((T, self.cfg.k), dtype=torch.int64, device=x.device)
+            sae_out = torch.empty((T, self.d_in), dtype=torch.float32, device=x.device)
+            sq_err = torch.zeros((), dtype=torch.float64, device=x.device)
+            self._overlap.run(xin, top_acts, top_indices, sae_out, sq_err)
+            top_acts = top_acts.view(*x.shape[:-1], self.cfg.k)
+            top_indices = top_indices.view(*x.shape[:-1], self.cfg.k)
+            sae_out = sae_out.view(*x.shape)
+        else:
+            top_acts, top_indices = self.encode(x)
+            sq_err = torch.zeros((), dtype=torch.float64, device=top_acts.device)
+            sae_out = engine.decode(top_indices, top_acts, self.W_dec.data, self.b_dec.data, out_dtype=torch.float32,
+                                    x=x, sq_err=sq_err)
         total_variance = engine.total_variance(x)
         fvu = (sq_err / total_variance).to(torch.float32)
         zero = sae_out.new_tensor(0.0)

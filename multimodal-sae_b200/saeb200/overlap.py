@@ -1,0 +1,80 @@
+"""Chunked forward with the tensor-core-bound and the HBM-bound halves on different streams.
+
+Per token chunk the "fp16 + refine" path has two phases with opposite bottlenecks:
+  A  activation prep + single-pass tcgen05 GEMM with fused candidate selection + merge   (tensor pipe)
+  B  exact fp32 refinement of the candidates + sparse decode (+ residual sum of squares)  (HBM row gathers)
+Phase A of chunk c+1 is issued on the GEMM stream while phase B of chunk c runs on the memory stream; the persistent
+GEMM kernel leaves enough shared memory / registers per SM for the gather kernels' CTAs to co-reside, so the gathers
+ride in the HBM bandwidth the GEMM does not use.  Two workspaces alternate between consecutive chunks.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _capi, engine
+from ._capi import check
+
+
+class OverlappedForward:
+    def __init__(self, enc: engine.PackedEncoder, W_dec: torch.Tensor, b_dec: torch.Tensor, k: int, chunk: int = 8192):
+        if enc.planes != 3:
+            raise _capi.SaebError("OverlappedForward needs the refine-mode packed encoder (planes=3)")
+        self.enc, self.W_dec, self.b_dec, self.k, self.chunk = enc, W_dec, b_dec, k, chunk
+        dev = enc.blob.device
+        self.dev = dev
+        L = _capi.lib()
+        self.ws_bytes = L.saeb_encode_topk_refine_workspace_bytes(chunk, enc.d_in, enc.num_latents, k, 0)
+        self.ws = [torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.status = torch.zeros(2, dtype=torch.int32, device=dev)
+        lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
+        self.s_gemm = torch.cuda.Stream(dev, priority=0)
+        self.s_mem = torch.cuda.Stream(dev, priority=-1)   # gathers first: their CTAs slot in beside the GEMM's
+
+    def run(self, x: torch.Tensor, acts: torch.Tensor, idx: torch.Tensor, sae_out: Optional[torch.Tensor] = None,
+            sq_err: Optional[torch.Tensor] = None, ready_events=None, done_events=None) -> None:
+        """x [T, d] (bf16 / fp16 / fp32, 2-D, row stride a multiple of 8 elements); acts [T,k] f32, idx [T,k] i64,
+        sae_out [T,d] (optional) are filled; sq_err (0-dim f64, optional) accumulates sum((sae_out - x)^2).
+        `ready_events[c]` (optional) gates chunk c's input (H2D copies); `done_events[c]` is recorded when chunk c's
+        outputs are complete.  Returns after ENQUEUEING; the caller's current stream waits for completion."""
+        L = _capi.lib()
+        enc, k = self.enc, self.k
+        T = x.shape[0]
+        n_chunks = (T + self.chunk - 1) // self.chunk
+        main = torch.cuda.current_stream()
+        self.s_gemm.wait_stream(main)
+        self.s_mem.wait_stream(main)
+        code = engine._code(x)
+        ev_a = [torch.cuda.Event() for _ in range(n_chunks)]
+        ev_b = [torch.cuda.Event() for _ in range(n_chunks)]
+        ldx = x.stride(0) if T > 1 else enc.d_in
+        with torch.cuda.device(self.dev):
+            for c in range(n_chunks):
+                a, b = c * self.chunk, min(T, (c + 1) * self.chunk)
+                xc = x[a:b]
+                ws = self.ws[c & 1]
+                with torch.cuda.stream(self.s_gemm):
+                    if c >= 2:
+                        self.s_gemm.wait_event(ev_b[c - 2])   # workspace reuse
+                    if ready_events is not None:
+                        self.s_gemm.wait_event(ready_events[c])
+                    check(L.saeb_encode_candidates(xc.data_ptr(), code, b - a, ldx, enc.blob.data_ptr(), enc.d_in,
+                                                   enc.num_latents, k, 0, -1, 0.0, ws.data_ptr(), ws.numel(),
+                                                   self.s_gemm.cuda_stream), "saeb_encode_candidates")
+                    ev_a[c].record(self.s_gemm)
+                with torch.cuda.stream(self.s_mem):
+                    self.s_mem.wait_event(ev_a[c])
+                    check(L.saeb_refine_candidates(xc.data_ptr(), code, b - a, ldx, enc.blob.data_ptr(),
+                                                   enc.W_enc.data_ptr(), enc.d_in, enc.num_latents, k, 0, -1, 0.0,
+                                                   acts[a:b].data_ptr(), idx[a:b].data_ptr(),
+                                                   self.status[c & 1:].data_ptr(), ws.data_ptr(), ws.numel(),
+                                                   self.s_mem.cuda_stream), "saeb_refine_candidates")
+                    if sae_out is not None:
+                        engine.decode(idx[a:b], acts[a:b], self.W_dec, self.b_dec, x=xc if sq_err is not None else None,
+                                      sq_err=sq_err, out=sae_out[a:b])
+                    ev_b[c].record(self.s_mem)
+                    if done_events is not None:
+                        done_events[c].record(self.s_mem)
+        main.wait_stream(self.s_mem)
+        main.wait_stream(self.s_gemm)

@@ -23,6 +23,11 @@ class HostForward:
         self.n_chunks = (num_tokens + self.chunk - 1) // self.chunk
         self.h2d_bytes = num_tokens * d * self.x_dev.element_size()
         self.d2h_bytes = num_tokens * k * 12 + 4
+        self.overlap = None
+        if sae.encoder_planes == 3:
+            from .overlap import OverlappedForward
+
+            self.overlap = OverlappedForward(sae.packed_encoder(), sae.W_dec.data, sae.b_dec.data, k, self.chunk)
 
     def run(self, x_host: torch.Tensor, acts_host: torch.Tensor, idx_host: torch.Tensor) -> torch.Tensor:
         """x_host [T, d] pinned; acts_host [T, k] f32 / idx_host [T, k] i64 pinned outputs.  Returns the pinned
@@ -37,16 +42,22 @@ class HostForward:
                 a, b = c * self.chunk, min(self.T, (c + 1) * self.chunk)
                 self.x_dev[a:b].copy_(x_host[a:b], non_blocking=True)
                 ev_in[c].record(self.s_in)
-        for c in range(self.n_chunks):
-            a, b = c * self.chunk, min(self.T, (c + 1) * self.chunk)
-            main.wait_event(ev_in[c])
-            acts, idx, _ = engine.encode_topk(self.x_dev[a:b], sae.packed_encoder(), sae.cfg.k,
-                                              out_vals=self.acts[a:b], out_idx=self.idx[a:b])
-            engine.decode(idx, acts, sae.W_dec.data, sae.b_dec.data, x=self.x_dev[a:b], sq_err=self.sq_err,
-                          out=self.sae_out[a:b])
-            ev_done[c].record(main)
-            self.s_out.wait_event(ev_done[c])
-            with torch.cuda.stream(self.s_out):
+        if self.overlap is not None:
+            self.overlap.run(self.x_dev, self.acts, self.idx, self.sae_out, self.sq_err, ready_events=ev_in,
+                             done_events=ev_done)
+        else:
+            for c in range(self.n_chunks):
+                a, b = c * self.chunk, min(self.T, (c + 1) * self.chunk)
+                main.wait_event(ev_in[c])
+                acts, idx, _ = engine.encode_topk(self.x_dev[a:b], sae.packed_encoder(), sae.cfg.k,
+                                                  out_vals=self.acts[a:b], out_idx=self.idx[a:b])
+                engine.decode(idx, acts, sae.W_dec.data, sae.b_dec.data, x=self.x_dev[a:b], sq_err=self.sq_err,
+                              out=self.sae_out[a:b])
+                ev_done[c].record(main)
+        with torch.cuda.stream(self.s_out):
+            for c in range(self.n_chunks):
+                a, b = c * self.chunk, min(self.T, (c + 1) * self.chunk)
+                self.s_out.wait_event(ev_done[c])
                 acts_host[a:b].copy_(self.acts[a:b], non_blocking=True)
                 idx_host[a:b].copy_(self.idx[a:b], non_blocking=True)
         tv = engine.total_variance(self.x_dev)

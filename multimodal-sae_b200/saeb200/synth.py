@@ -28,6 +28,8 @@ def make_sae(d_in: int, num_latents: int, k: int, device, seed: int = 1234):
     sae.b_dec = torch.nn.Parameter(torch.randn(d_in, device=device, generator=g) * 0.1)
     sae.encoder_planes = 3
     sae._packed = {}
+    sae._overlap = None
+    sae.overlap_chunk = 8192
     sae.requires_grad_(False)
     return sae
 

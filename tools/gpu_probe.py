@@ -125,6 +125,48 @@ def exp_decode(T, d, N, k):
     return dict(max_abs_err=(y.double() - ref).abs().max().item(), ref_absmax=ref.abs().max().item())
 
 
+def exp_overlap(T, chunk, planes=3, overlap=True, l2_hints=1, splits=0, iters=3):
+    torch, engine = _setup(2)
+    from saeb200 import _capi, synth
+    from saeb200.overlap import OverlappedForward
+    L = _capi.lib()
+    _capi.check(L.saeb_set_option(b"l2_hints", l2_hints), "set_option")
+    _capi.check(L.saeb_set_option(b"splits", splits), "set_option")
+    sae = synth.make_sae(4096, 131072, 64, "cuda", seed=1234)
+    sae.encoder_planes = planes
+    enc = sae.packed_encoder()
+    x = synth.make_activations(T, 4096, "cuda", seed=3)
+    acts = torch.empty((T, 64), dtype=torch.float32, device="cuda")
+    idx = torch.empty((T, 64), dtype=torch.int64, device="cuda")
+    out = torch.empty((T, 4096), dtype=torch.float32, device="cuda")
+    sq = torch.zeros((), dtype=torch.float64, device="cuda")
+    ov = OverlappedForward(enc, sae.W_dec.data, sae.b_dec.data, 64, chunk=chunk) if (overlap and planes == 3) else None
+
+    def step():
+        sq.zero_()
+        if ov is not None:
+            ov.run(x, acts, idx, out, sq)
+        else:
+            engine.encode_topk(x, enc, 64, out_vals=acts, out_idx=idx)
+            engine.decode(idx, acts, sae.W_dec.data, sae.b_dec.data, x=x, sq_err=sq, out=out)
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms = []
+    for _ in range(iters):
+        e0.record(); step(); e1.record(); torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    res = dict(ms=ms, tokens_per_s=T / (min(ms) * 1e-3), flops_frac_of_1418=T / (min(ms) * 1e-3) * 1.0743e9 / 1.4181e15)
+    if planes == 3:
+        res["flagged"] = int(ov.status.sum().item()) if ov is not None else int(engine.encode_topk.last_status.item())
+    # consistency of the overlapped result with the sequential one
+    if ov is not None:
+        a2, i2, _ = engine.encode_topk(x[:4096], enc, 64)
+        res["overlap_equals_sequential"] = bool(torch.equal(a2, acts[:4096]) and torch.equal(i2, idx[:4096]))
+    return res
+
+
 EXPS = {
     "gemm_p1_small": lambda: exp_gemm(1, 1, 256, 128, 512),
     "gemm_p2_small": lambda: exp_gemm(2, 1, 256, 128, 512),
@@ -153,6 +195,16 @@ EXPS = {
     "time_refine_64k_s4": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=4),
     "time_refine_64k_s6": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=6),
     "time_refine_64k_s8": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=8),
+    "ov_64k_c8k": lambda: exp_overlap(65536, 8192),
+    "ov_64k_c16k": lambda: exp_overlap(65536, 16384),
+    "ov_64k_c4k": lambda: exp_overlap(65536, 4096),
+    "ov_64k_c8k_nohint": lambda: exp_overlap(65536, 8192, l2_hints=0),
+    "ov_64k_c8k_hint3": lambda: exp_overlap(65536, 8192, l2_hints=3),
+    "seq_64k_refine": lambda: exp_overlap(65536, 8192, overlap=False),
+    "seq_64k_refine_nohint": lambda: exp_overlap(65536, 8192, overlap=False, l2_hints=0),
+    "seq_64k_hilo": lambda: exp_overlap(65536, 8192, planes=2, overlap=False),
+    "seq_64k_hilo_nohint": lambda: exp_overlap(65536, 8192, planes=2, overlap=False, l2_hints=0),
+    "time_bf16x1_64k": lambda: exp_time(2, 1, 65536, 4096, 131072, 64, iters=2),
     "time_hilo_64k_s2": lambda: exp_time(2, 2, 65536, 4096, 131072, 64, iters=2, splits=2),
     "time_hilo_64k_s4": lambda: exp_time(2, 2, 65536, 4096, 131072, 64, iters=2, splits=4),
     "time_hilo_64k_s8": lambda: exp_time(2, 2, 65536, 4096, 131072, 64, iters=2, splits=8),
