@@ -330,7 +330,7 @@ def main():
     ap.add_argument("--scan-tokens", type=int, default=262144)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run the phases of a step back to back on one stream")
-    ap.add_argument("--chunk", type=int, default=8192, help="tokens per pipeline chunk")
+    ap.add_argument("--chunk", type=int, default=18944, help="tokens per pipeline chunk (multiple of 9472 = one wave)")
     ap.add_argument("--planes", type=int, default=3, choices=[1, 2, 3],
                     help="encoder mode: 3 = fp16 pass + exact refinement (default), 2 = bf16 hi+lo, 1 = bf16 (diagnostic)")
     args = ap.parse_args()

@@ -37,7 +37,9 @@ const char* saeb_last_error(void);
 long long saeb_launch_count(void);
 /* Tuning knobs.  "cta_pair": 2 (default) = CTA pairs with tcgen05 cta_group::2 (256-row MMA tiles), 1 = single-CTA
  * tiles.  Results are identical; only throughput differs.  "profile": see saeb_profile_last_encode_ms.  "splits": feature-range splits per token tile
- * (0 = automatic). */
+ * (0 = automatic).  "chunking": 1 (default) = long calls run as one launch per wave of token tiles (keeps the live
+ * activation tiles L2-resident).  "persist_a": 1 (default) = pin each launch's activation rows in the persisting part
+ * of L2.  "l2_hints", "debug_tiles": diagnostics. */
 int saeb_set_option(const char* name, int value);
 /* With option "profile" = 1 the library brackets the fused encode kernel (main kernel only) with CUDA events on the
  * launching stream; this returns the duration in ms of the most recent one (synchronises on it), < 0 if none. */
@@ -77,7 +79,7 @@ int saeb_encode_topk(const void* x, int x_dtype, int64_t T, int64_t ld_x, const 
  * per-feature norms.  The GEMM ranks by approximate values; every candidate that can still belong to the TopK under the
  * rigorous rounding bound  (2^-11 [+2^-11 for fp32 x] + 2^-12) * ||x||_2 * ||w_j||_2  is re-evaluated exactly in fp32
  * against `W_enc` (the [N,d] fp32 parameter itself), so the returned values are fp32-exact and the index set is the
- * fp32 reference's.  `margin` = extra candidates kept per row (0 = 64).  Rows whose candidate list could be too short
+ * fp32 reference's.  `margin` = extra candidates kept per row (0 = max(64, k/2)).  Rows whose candidate list could be too short
  * for the bound (never observed) are recomputed by an exact dense fp32 kernel, up to 64 per call; *status_out (device
  * int, may be NULL) receives the number of such rows -- more than 64 means the call must be repeated with a larger
  * margin. */
@@ -87,16 +89,24 @@ int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x,
                             float clamp_value, float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
                             size_t workspace_bytes, void* stream);
 
-/* The two phases of saeb_encode_topk_refine as separate calls over the same workspace, so that a caller can run the
- * tensor-core-bound phase A of the next token chunk concurrently (other stream) with the HBM-bound phase B and decode
- * of the previous one: A = activation prep + GEMM + candidate merge, B = exact refinement (+ dense fallback). */
-int saeb_encode_candidates(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed, int64_t d,
+/* The stages of saeb_encode_topk_refine as separate calls, so that a caller can run the tensor-core-bound GEMM of the
+ * next token chunk concurrently (on another stream) with the HBM-bound refinement and decode of the previous one:
+ *   saeb_prep_activations   whole batch: activations -> power-of-two scaled fp16 plane + per-row scale + norms
+ *                           (`prep`, saeb_prep_bytes(T, d) bytes);
+ *   saeb_encode_candidates  rows [t0, t0+Tc): single-pass GEMM with fused candidate selection (tensor bound);
+ *   saeb_refine_candidates  same rows: candidate merge + exact fp32 re-evaluation + dense fallback (HBM bound); `x`
+ *                           points at row t0 of the original activations.
+ * Both row-range calls share a scratch buffer of saeb_candidates_workspace_bytes(Tc, ...) bytes. */
+size_t saeb_prep_bytes(int64_t T, int64_t d);
+int saeb_prep_activations(const void* x, int x_dtype, int64_t T, int64_t ld_x, int64_t d, void* prep, void* stream);
+size_t saeb_candidates_workspace_bytes(int64_t T, int64_t d, int64_t N, int k, int margin);
+int saeb_encode_candidates(const void* prep, int64_t T_total, int64_t t0, int64_t Tc, const void* packed, int64_t d,
                            int64_t N, int k, int margin, int64_t clamp_feature, float clamp_value, void* workspace,
                            size_t workspace_bytes, void* stream);
-int saeb_refine_candidates(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed,
-                           const float* W_enc, int64_t d, int64_t N, int k, int margin, int64_t clamp_feature,
-                           float clamp_value, float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
-                           size_t workspace_bytes, void* stream);
+int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total, int64_t t0,
+                           int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N, int k, int margin,
+                           int64_t clamp_feature, float clamp_value, float* out_vals, int64_t* out_idx,
+                           int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* TopK of dense non-negative rows, (value desc, index asc): Sae.select_topk (sae/sae.py:179-181) for callers that hold
  * a dense [T, ld] latent tensor. */

@@ -26,6 +26,14 @@ int encode_topk_launch(const void* x_planes, int ap, long long T, long long ld_x
                        long long clamp_feature, float clamp_value, float* out_vals, long long* out_idx,
                        float* dense_out, long long ld_dense, void* workspace, size_t workspace_bytes, int pass_mask,
                        int operand_fmt, const float* row_scale, const float* w_unscale, cudaStream_t stream);
+int encode_gemm_launch(const void* x_planes, int ap, long long T, long long ld_x, long long x_plane_stride,
+                       const void* w_planes, int bp, long long ld_w, const float* bias, long long d, long long N, int k,
+                       long long clamp_feature, float clamp_value, bool do_topk, float* dense_out, long long ld_dense,
+                       void* workspace, size_t workspace_bytes, int pass_mask, int operand_fmt, const float* row_scale,
+                       const float* w_unscale, cudaStream_t stream);
+int encode_merge_launch(long long T, long long N, int k, float* out_vals, long long* out_idx, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream);
+int set_chunking(int v);
 int pack_weights_f16_launch(const float* W_enc, const float* b_enc, const float* b_dec, long long N, long long d,
                             long long d_pad, void* w_plane, float* bias, float* wnorm, float* trailer,
                             cudaStream_t stream);
@@ -41,6 +49,9 @@ int dense_topk_launch(const float* dense, long long T, long long ld, long long N
                       long long* out_idx, cudaStream_t stream);
 int set_splits(int v);
 int set_l2_hints(int v);
+int set_dbg(int v);
+int set_persist_a(int v);
+long long persist_bytes();
 int pack_weights_launch(const float* W_enc, const float* b_enc, const float* b_dec, long long N, long long d,
                         long long d_pad, int planes, void* w_planes, float* bias, cudaStream_t stream);
 int split_x_launch(const void* x, int x_dtype, long long T, long long d, long long ld_x, long long d_pad, int planes,
@@ -97,6 +108,9 @@ int saeb_set_option(const char* name, int value) {
   if (strcmp(name, "profile") == 0) return set_profile(value);
   if (strcmp(name, "splits") == 0) return set_splits(value);
   if (strcmp(name, "l2_hints") == 0) return set_l2_hints(value);
+  if (strcmp(name, "debug_tiles") == 0) return set_dbg(value);
+  if (strcmp(name, "persist_a") == 0) return set_persist_a(value);
+  if (strcmp(name, "chunking") == 0) return set_chunking(value);
   set_error("set_option: unknown option '%s'", name);
   return -1;
 }
@@ -182,13 +196,26 @@ int saeb_encode_topk(const void* x, int x_dtype, int64_t T, int64_t ld_x, const 
 
 // ---- "fp16 + refine": one tensor-core pass + exact fp32 re-evaluation of the candidates near the k-th value
 static inline int refine_k2(int k, int margin) {
-  int m = margin > 0 ? margin : 64;
+  int m = margin > 0 ? margin : (k / 2 > 64 ? k / 2 : 64);   // denser spectra (large k / N) need more room below the k-th value
   int K2 = k + m;
   if (K2 > 512) K2 = 512;
   return K2;
 }
+// prepared activations of a whole batch: x16 [T][d_pad] fp16 | row_scale [T] f32 | xnorm [T] f32
+struct PrepLayout {
+  size_t x16, row_scale, xnorm, total;
+};
+static PrepLayout prep_layout(long long T, long long d) {
+  PrepLayout p;
+  p.x16 = 0;
+  p.row_scale = align_up((size_t)T * pad8(d) * 2, 1024);
+  p.xnorm = p.row_scale + align_up((size_t)T * 4, 256);
+  p.total = p.xnorm + align_up((size_t)T * 4, 256);
+  return p;
+}
+// per-call (or per-chunk) scratch of the candidate pipeline
 struct RefineWs {
-  size_t x16, row_scale, xnorm, status, flag_rows, mvals, midx, dense, enc, total;
+  size_t status, flag_rows, mvals, midx, dense, enc, total;
 };
 static RefineWs refine_ws(long long T, long long d, long long N, int k, int margin) {
   RefineWs w;
@@ -200,9 +227,6 @@ static RefineWs refine_ws(long long T, long long d, long long N, int k, int marg
     off += bytes;
     return at;
   };
-  w.x16 = take((size_t)T * pad8(d) * 2, 1024);
-  w.row_scale = take((size_t)T * 4, 256);
-  w.xnorm = take((size_t)T * 4, 256);
   w.status = take(256, 256);
   w.flag_rows = take(256, 256);
   w.mvals = take((size_t)T * K2 * 4, 256);
@@ -213,89 +237,118 @@ static RefineWs refine_ws(long long T, long long d, long long N, int k, int marg
   return w;
 }
 
-size_t saeb_encode_topk_refine_workspace_bytes(int64_t T, int64_t d, int64_t N, int k, int margin) {
+size_t saeb_prep_bytes(int64_t T, int64_t d) { return prep_layout(T, d).total; }
+
+int saeb_prep_activations(const void* x, int x_dtype, int64_t T, int64_t ld_x, int64_t d, void* prep, void* stream) {
+  g_err[0] = 0;
+  SAEB_REQUIRE(x && prep, "prep_activations: null pointer");
+  SAEB_REQUIRE(x_dtype == DT_BF16 || x_dtype == DT_F16 || x_dtype == DT_F32, "prep_activations: bad x dtype %d", x_dtype);
+  if (T == 0) return 0;
+  const PrepLayout p = prep_layout(T, d);
+  uint8_t* b = reinterpret_cast<uint8_t*>(prep);
+  int rc = prep_x_f16_launch(x, x_dtype, T, d, ld_x, pad8(d), b + p.x16, reinterpret_cast<float*>(b + p.row_scale),
+                             reinterpret_cast<float*>(b + p.xnorm), (cudaStream_t)stream);
+  if (rc == 0) g_launches += 1;
+  return rc;
+}
+
+size_t saeb_candidates_workspace_bytes(int64_t T, int64_t d, int64_t N, int k, int margin) {
   return refine_ws(T, d, N, k, margin).total;
 }
 
-// phase A: activation prep + single-pass GEMM with fused candidate selection + merge -> K2 candidates per row in the
-// workspace (tensor-core bound)
-int saeb_encode_candidates(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed, int64_t d,
+// phase A: single-pass GEMM with fused candidate selection over rows [t0, t0+Tc) of a prepared batch (tensor bound)
+int saeb_encode_candidates(const void* prep, int64_t T_total, int64_t t0, int64_t Tc, const void* packed, int64_t d,
                            int64_t N, int k, int margin, int64_t clamp_feature, float clamp_value, void* workspace,
                            size_t workspace_bytes, void* stream) {
   g_err[0] = 0;
-  SAEB_REQUIRE(x && packed && workspace, "encode_candidates: null pointer");
-  SAEB_REQUIRE(x_dtype == DT_BF16 || x_dtype == DT_F16 || x_dtype == DT_F32, "encode_candidates: bad x dtype %d",
-               x_dtype);
+  SAEB_REQUIRE(prep && packed && workspace, "encode_candidates: null pointer");
+  SAEB_REQUIRE(t0 >= 0 && Tc >= 0 && t0 + Tc <= T_total, "encode_candidates: bad row range");
   SAEB_REQUIRE(clamp_feature < N, "encode_candidates: clamp_feature out of range");
   SAEB_REQUIRE(k >= 1 && k <= N && k <= 448, "encode_candidates: k=%d out of range", k);
-  if (T == 0) return 0;
+  if (Tc == 0) return 0;
   const int K2raw = refine_k2(k, margin);
   const int K2 = K2raw < N ? K2raw : (int)N;
-  const RefineWs w = refine_ws(T, d, N, k, margin);
+  const RefineWs w = refine_ws(Tc, d, N, k, margin);
   SAEB_REQUIRE(workspace_bytes >= w.total, "encode_candidates: workspace too small: have %zu need %zu",
                workspace_bytes, w.total);
-  cudaStream_t st = (cudaStream_t)stream;
+  const PrepLayout p = prep_layout(T_total, d);
+  const uint8_t* pb = reinterpret_cast<const uint8_t*>(prep);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
   const float* bias = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3));
   const float* trailer = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + 2 * bias_bytes(N));
-  float* row_scale = reinterpret_cast<float*>(ws + w.row_scale);
-  float* xnorm = reinterpret_cast<float*>(ws + w.xnorm);
-  int rc = prep_x_f16_launch(x, x_dtype, T, d, ld_x, pad8(d), ws + w.x16, row_scale, xnorm, st);
-  if (rc) return rc;
-  rc = encode_topk_launch(ws + w.x16, 1, T, pad8(d), (long long)T * pad8(d), packed, 1, pad8(d), bias, d, N, K2,
-                          clamp_feature, clamp_value, reinterpret_cast<float*>(ws + w.mvals),
-                          reinterpret_cast<long long*>(ws + w.midx), nullptr, 0, ws + w.enc, w.total - w.enc, 1,
-                          /*operand_fmt=fp16*/ 0, row_scale, trailer, st);
-  if (rc) return rc;
-  g_launches += 3;
-  return 0;
+  int rc = encode_gemm_launch(pb + p.x16 + (size_t)t0 * pad8(d) * 2, 1, Tc, pad8(d), (long long)Tc * pad8(d), packed, 1,
+                              pad8(d), bias, d, N, K2, clamp_feature, clamp_value, true, nullptr, 0, ws + w.enc,
+                              w.total - w.enc, 1, /*operand_fmt=fp16*/ 0,
+                              reinterpret_cast<const float*>(pb + p.row_scale) + t0, trailer, (cudaStream_t)stream);
+  if (rc == 0) g_launches += 1;
+  return rc;
 }
 
-// phase B: exact fp32 re-evaluation of the candidates left in the workspace by phase A (HBM bound)
-int saeb_refine_candidates(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed,
-                           const float* W_enc, int64_t d, int64_t N, int k, int margin, int64_t clamp_feature,
-                           float clamp_value, float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
-                           size_t workspace_bytes, void* stream) {
+// phase B: candidate merge + exact fp32 re-evaluation (+ dense fallback) for the same rows (HBM bound).
+// x points at row t0 of the ORIGINAL activations.
+int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total, int64_t t0,
+                           int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N, int k, int margin,
+                           int64_t clamp_feature, float clamp_value, float* out_vals, int64_t* out_idx,
+                           int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream) {
   g_err[0] = 0;
-  SAEB_REQUIRE(x && packed && W_enc && out_vals && out_idx && workspace, "refine_candidates: null pointer");
-  if (T == 0) return 0;
+  SAEB_REQUIRE(x && prep && packed && W_enc && out_vals && out_idx && workspace, "refine_candidates: null pointer");
+  SAEB_REQUIRE(t0 >= 0 && Tc >= 0 && t0 + Tc <= T_total, "refine_candidates: bad row range");
+  if (Tc == 0) return 0;
   const int K2raw = refine_k2(k, margin);
   const int K2 = K2raw < N ? K2raw : (int)N;
-  const RefineWs w = refine_ws(T, d, N, k, margin);
+  const RefineWs w = refine_ws(Tc, d, N, k, margin);
   SAEB_REQUIRE(workspace_bytes >= w.total, "refine_candidates: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  const PrepLayout p = prep_layout(T_total, d);
+  const uint8_t* pb = reinterpret_cast<const uint8_t*>(prep);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
   const float* bias = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3));
   const float* wnorm = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + bias_bytes(N));
   const float* trailer = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + 2 * bias_bytes(N));
   int* status = reinterpret_cast<int*>(ws + w.status);
+  float* mvals = reinterpret_cast<float*>(ws + w.mvals);
+  long long* midx = reinterpret_cast<long long*>(ws + w.midx);
   SAEB_CHECK_CUDA(cudaMemsetAsync(status, 0, 256, st));
+  int rc = encode_merge_launch(Tc, N, K2, mvals, midx, ws + w.enc, w.total - w.enc, st);
+  if (rc) return rc;
   // error-bound constant: fp16 rounding of W (2^-11), of x when it is fp32 (2^-11), and 2^-12 for the fp32 accumulation
   const float c_eps = ldexpf(1.0f, -11) + (x_dtype == DT_F32 ? ldexpf(1.0f, -11) : 0.f) + ldexpf(1.0f, -12);
-  int rc = refine_launch(x, x_dtype, T, ld_x, W_enc, d, N, bias, wnorm, trailer,
-                         reinterpret_cast<const float*>(ws + w.xnorm), c_eps,
-                         reinterpret_cast<const float*>(ws + w.mvals), reinterpret_cast<const long long*>(ws + w.midx),
-                         K2, k < K2 ? k : K2, clamp_feature, clamp_value, out_vals,
-                         reinterpret_cast<long long*>(out_idx), status, reinterpret_cast<int*>(ws + w.flag_rows),
-                         reinterpret_cast<float*>(ws + w.dense), st);
+  rc = refine_launch(x, x_dtype, Tc, ld_x, W_enc, d, N, bias, wnorm, trailer,
+                     reinterpret_cast<const float*>(pb + p.xnorm) + t0, c_eps, mvals, midx, K2, k < K2 ? k : K2,
+                     clamp_feature, clamp_value, out_vals, reinterpret_cast<long long*>(out_idx), status,
+                     reinterpret_cast<int*>(ws + w.flag_rows), reinterpret_cast<float*>(ws + w.dense), st);
   if (rc) return rc;
   if (status_out != nullptr)
     SAEB_CHECK_CUDA(cudaMemcpyAsync(status_out, status, sizeof(int), cudaMemcpyDeviceToDevice, st));
-  g_launches += 4;
+  g_launches += 5;
   return 0;
+}
+
+size_t saeb_encode_topk_refine_workspace_bytes(int64_t T, int64_t d, int64_t N, int k, int margin) {
+  return align_up(prep_layout(T, d).total, 1024) + refine_ws(T, d, N, k, margin).total;
 }
 
 int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed,
                             const float* W_enc, int64_t d, int64_t N, int k, int margin, int64_t clamp_feature,
                             float clamp_value, float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
                             size_t workspace_bytes, void* stream) {
-  int rc = saeb_encode_candidates(x, x_dtype, T, ld_x, packed, d, N, k, margin, clamp_feature, clamp_value, workspace,
-                                  workspace_bytes, stream);
+  g_err[0] = 0;
+  SAEB_REQUIRE(workspace != nullptr, "encode_topk_refine: null workspace");
+  if (T == 0) return 0;
+  const size_t prep_bytes = align_up(prep_layout(T, d).total, 1024);
+  SAEB_REQUIRE(workspace_bytes >= prep_bytes + refine_ws(T, d, N, k, margin).total,
+               "encode_topk_refine: workspace too small");
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  int rc = saeb_prep_activations(x, x_dtype, T, ld_x, d, ws, stream);
   if (rc) return rc;
-  return saeb_refine_candidates(x, x_dtype, T, ld_x, packed, W_enc, d, N, k, margin, clamp_feature, clamp_value,
-                                out_vals, out_idx, status_out, workspace, workspace_bytes, stream);
+  rc = saeb_encode_candidates(ws, T, 0, T, packed, d, N, k, margin, clamp_feature, clamp_value, ws + prep_bytes,
+                              workspace_bytes - prep_bytes, stream);
+  if (rc) return rc;
+  return saeb_refine_candidates(x, x_dtype, ld_x, ws, T, 0, T, packed, W_enc, d, N, k, margin, clamp_feature,
+                                clamp_value, out_vals, out_idx, status_out, ws + prep_bytes,
+                                workspace_bytes - prep_bytes, stream);
 }
 
 int saeb_dense_topk(const float* dense, int64_t T, int64_t ld, int64_t N, int k, float* out_vals, int64_t* out_idx,

@@ -52,6 +52,7 @@ struct EncodeArgs {
   int pass_mask;      // bit (a*BP+b) set -> issue MMA for (A plane a, B plane b)
   int clamp_col;      // steering: column forced to clamp_val before TopK (-1 = none)
   float clamp_val;
+  int dbg;   // diagnostics only (wrong results): bit0 = every cluster loads token tile 0, bit1 = every step loads feature tile 0
   unsigned long long hint_a, hint_b;   // L2 eviction policies of the activation / weight TMA loads
   unsigned int idesc;       // tcgen05 instruction descriptor (operand formats are a run-time choice: bf16 or fp16)
   const float* row_scale;   // optional [T]: per-row power-of-two factor undoing the activation pre-scale
@@ -168,9 +169,9 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         const int split = u % args.S, m_tile = u / args.S;
         const int nt0 = (int)((long long)split * args.num_n_tiles / args.S);
         const int nt1 = (int)((long long)(split + 1) * args.num_n_tiles / args.S);
-        const int m0 = (m_tile * PAIR + (int)cta_rank) * BM;
+        const int m0 = (((args.dbg & 1) ? 0 : m_tile) * PAIR + (int)cta_rank) * BM;
         for (int nt = nt0; nt < nt1; ++nt) {
-          const int n0 = nt * BN + (int)cta_rank * Cfg::B_ROWS;
+          const int n0 = ((args.dbg & 2) ? 0 : nt) * BN + (int)cta_rank * Cfg::B_ROWS;
           for (int kb = 0; kb < args.num_k_blocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::STAGE;
@@ -525,6 +526,25 @@ int set_l2_hints(int v) {
   g_l2_hints = v;
   return 0;
 }
+static int g_persist_a = 1;   // 1: pin the activation planes in the persisting part of L2 for the duration of the launch
+static size_t g_persist_bytes = 0;
+int set_persist_a(int v) {
+  g_persist_a = v;
+  if (v && g_persist_bytes == 0) {
+    int dev = 0, max_persist = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    if (max_persist > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess)
+      g_persist_bytes = (size_t)max_persist;
+  }
+  return 0;
+}
+long long persist_bytes() { return (long long)g_persist_bytes; }
+static int g_dbg = 0;
+int set_dbg(int v) {
+  g_dbg = v;
+  return 0;
+}
 static int g_splits = 0;     // 0 = automatic
 int set_splits(int v) {
   if (v < 0 || v > 64) {
@@ -535,53 +555,93 @@ int set_splits(int v) {
   return 0;
 }
 
-// How the feature range is split: (token tiles x splits) must fill the machine.  Few token tiles (small T) raise S so
-// that every SM has work; `saeb_set_option("splits", n)` overrides.
 static int merge_max_splits(int cap, int k) {
   int kp2 = 2;
   while (kp2 < k) kp2 <<= 1;
   const int s = (200 * 1024 - kp2 * 8) / (cap * 8);   // the merge kernel stages a row's candidates in shared memory
   return s < 1 ? 1 : s;
 }
+
+// Feature-range splits for a launch over `num_m_tiles` token tiles: (token tiles x splits) should fill the machine in
+// whole waves.  Every split restarts its running threshold from zero (a compaction-heavy first few tiles), so the
+// smallest S with the best wave efficiency wins.
 static int choose_splits(int num_m_tiles, int num_n_tiles, int num_clusters, int cap, int k) {
-  const int s_max_smem = merge_max_splits(cap, k);
-  int s_cap = num_n_tiles < s_max_smem ? num_n_tiles : s_max_smem;
+  int s_cap = merge_max_splits(cap, k);
+  if (s_cap > num_n_tiles) s_cap = num_n_tiles;
   if (s_cap < 1) s_cap = 1;
   int S;
   if (g_splits > 0) {
     S = g_splits;
-  } else if (num_m_tiles * 2 <= num_clusters) {
-    S = (num_clusters + num_m_tiles - 1) / num_m_tiles;
-  } else {
-    // measured (profiles/r01_probe_splits.log): S = 2 is fastest at large T -- every split restarts its running
-    // threshold from zero, and that early compaction-heavy phase costs more than the L2 over-fetch it would save
+  } else if (num_m_tiles > num_clusters) {
     S = 2;
+  } else {
+    int s0 = num_clusters / num_m_tiles;
+    if (s0 < 1) s0 = 1;
+    S = s0;
+    double best = -1.0;
+    for (int c = s0; c <= s0 + 2; ++c) {
+      const long long units = (long long)num_m_tiles * c;
+      const long long waves = (units + num_clusters - 1) / num_clusters;
+      const double eff = (double)units / (double)(waves * num_clusters);
+      if (eff > best + 1e-9) {
+        best = eff;
+        S = c;
+      }
+    }
   }
   if (S > s_cap) S = s_cap;
   if (S < 1) S = 1;
   return S;
 }
 
-struct EncodePlan {
-  int pair, S, cap, num_m_tiles, num_n_tiles, grid;
-  size_t cand_bytes, cnt_bytes;
+// A call is executed as a sequence of launches over row chunks.  One launch covers at most (clusters / 2) token tiles
+// = one wave of (tile, split) units at S = 2: measured with ncu, a single-wave launch keeps its 37 live activation
+// tiles (74 MB) L2-resident (3.6 GB of DRAM reads per 9472 tokens with the persisting window, 13 GB without), while
+// a multi-wave launch lets waves drift apart and re-fetches the activations from HBM (233 GB per 65536 tokens),
+// which costs ~20 % of the SM clock under the power cap.
+struct ChunkPlan {
+  long long t0, rows;
+  int num_m_tiles, S, grid;
+  size_t cnt_off, cand_off;
 };
+struct EncodePlan {
+  int pair, cap, num_n_tiles, n_chunks;
+  ChunkPlan chunks[512];
+  size_t total_bytes;
+};
+static int g_chunking = 1;   // 0: one launch for the whole call
+int set_chunking(int v) {
+  g_chunking = v;
+  return 0;
+}
 
-static EncodePlan make_plan(long long T, long long N, int k, int pair, long long d = 4096, int ap = 1) {
-  EncodePlan p;
+static bool make_plan(EncodePlan& p, long long T, long long N, int k, int pair) {
   p.pair = pair;
   p.cap = cap_for_k(k);
-  p.num_m_tiles = (int)((T + BM * pair - 1) / (BM * pair));
   p.num_n_tiles = (int)((N + BN - 1) / BN);
   const int sms = num_sms() > 0 ? num_sms() : 148;
   const int clusters = sms / pair;
-  p.S = choose_splits(p.num_m_tiles, p.num_n_tiles, clusters, p.cap, k);
-  int units = p.num_m_tiles * p.S;
-  int use = units < clusters ? units : clusters;
-  p.grid = use * pair;
-  p.cand_bytes = (size_t)T * p.S * p.cap * sizeof(uint2);
-  p.cnt_bytes = (((size_t)T * p.S * sizeof(int)) + 255) & ~(size_t)255;
-  return p;
+  const long long tile_rows = (long long)BM * pair;
+  long long rows_full = (long long)(clusters / 2 > 0 ? clusters / 2 : 1) * tile_rows;
+  if (!g_chunking || g_splits > 0) rows_full = T;
+  p.n_chunks = 0;
+  size_t off = 0;
+  for (long long t0 = 0; t0 < T; t0 += rows_full) {
+    if (p.n_chunks >= 512) return false;
+    ChunkPlan& c = p.chunks[p.n_chunks++];
+    c.t0 = t0;
+    c.rows = (T - t0 < rows_full) ? T - t0 : rows_full;
+    c.num_m_tiles = (int)((c.rows + tile_rows - 1) / tile_rows);
+    c.S = choose_splits(c.num_m_tiles, p.num_n_tiles, clusters, p.cap, k);
+    const int units = c.num_m_tiles * c.S;
+    c.grid = (units < clusters ? units : clusters) * pair;
+    c.cnt_off = off;
+    off += (((size_t)c.rows * c.S * sizeof(int)) + 255) & ~(size_t)255;
+    c.cand_off = off;
+    off += (size_t)c.rows * c.S * p.cap * sizeof(uint2);
+  }
+  p.total_bytes = off;
+  return true;
 }
 
 static int g_profile = 0;
@@ -623,21 +683,26 @@ int set_cta_pair(int v) {
 }
 
 size_t encode_workspace_bytes(long long T, long long d, long long N, int k) {
-  // worst case over both pair modes so that a caller-sized workspace is always enough
-  // upper bound over pair modes, plane counts and split overrides: S never exceeds the merge kernel's limit
-  const int cap = cap_for_k(k);
-  long long s_max = merge_max_splits(cap, k);
-  const long long n_tiles = (N + BN - 1) / BN;
-  if (s_max > n_tiles) s_max = n_tiles;
-  EncodePlan p1 = make_plan(T, N, k, 1, d, 2), p2 = make_plan(T, N, k, 2, d, 2);
-  long long S = p1.S > p2.S ? p1.S : p2.S;
-  if (g_splits > S) S = g_splits;
-  if (S > s_max) S = s_max;
-  if (T > 4096 && S < 8) S = 8 < s_max ? 8 : s_max;   // room for later tuning without re-querying
-  const size_t cand = (size_t)T * S * cap * sizeof(uint2);
-  const size_t cnt = (((size_t)T * S * sizeof(int)) + 255) & ~(size_t)255;
-  return cand + cnt + 1024;
+  // upper bound over both tile modes (the plan depends on the option values at call time)
+  (void)d;
+  size_t best = 0;
+  for (int pair = 1; pair <= 2; ++pair) {
+    static thread_local EncodePlan plan;
+    if (!make_plan(plan, T, N, k, pair)) continue;
+    if (plan.total_bytes > best) best = plan.total_bytes;
+  }
+  // headroom for option changes between the query and the call (splits override, chunking off)
+  const size_t cap = cap_for_k(k);
+  const size_t s8 = (size_t)T * 8 * cap * sizeof(uint2) + (size_t)T * 8 * sizeof(int) + 4096;
+  if (T > 4096 && s8 > best && merge_max_splits((int)cap, k) >= 8) best = s8;
+  return best + 1024;
 }
+
+struct PersistWindow {
+  void* base = nullptr;
+  size_t bytes = 0;
+};
+static PersistWindow g_window;
 
 template <int AP, int BP, int PAIR, int SLOTS>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const EncodeArgs& args, int grid,
@@ -650,13 +715,24 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const Encode
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (g_persist_a && g_persist_bytes > 0 && g_window.bytes > 0) {
+    // the activation tiles are re-read once per feature tile: keep them in the persisting set-aside of L2
+    attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[1].val.accessPolicyWindow.base_ptr = g_window.base;
+    attr[1].val.accessPolicyWindow.num_bytes = g_window.bytes;
+    double ratio = (double)g_persist_bytes / (double)g_window.bytes;
+    attr[1].val.accessPolicyWindow.hitRatio = ratio > 1.0 ? 1.0f : (float)ratio;
+    attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.numAttrs = 2;
+  }
   SAEB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, args));
   return 0;
 }
@@ -686,11 +762,12 @@ static int launch_planes(int ap, int bp, const CUtensorMap& ta, const CUtensorMa
 
 // x_planes: [ap][T][ld_x] bf16 (ap==1: the caller's bf16 activations in place)
 // w_planes: [bp][N][d] bf16; bias: folded bias [N]
-int encode_topk_launch(const void* x_planes, int ap, long long T, long long ld_x, long long x_plane_stride,
+// Phase 1: the fused GEMM launches (one per row chunk) -> candidate lists in the workspace (and/or dense output)
+int encode_gemm_launch(const void* x_planes, int ap, long long T, long long ld_x, long long x_plane_stride,
                        const void* w_planes, int bp, long long ld_w, const float* bias, long long d, long long N, int k,
-                       long long clamp_feature, float clamp_value, float* out_vals, long long* out_idx,
-                       float* dense_out, long long ld_dense, void* workspace, size_t workspace_bytes, int pass_mask,
-                       int operand_fmt, const float* row_scale, const float* w_unscale, cudaStream_t stream) {
+                       long long clamp_feature, float clamp_value, bool do_topk, float* dense_out, long long ld_dense,
+                       void* workspace, size_t workspace_bytes, int pass_mask, int operand_fmt, const float* row_scale,
+                       const float* w_unscale, cudaStream_t stream) {
   SAEB_REQUIRE(T > 0 && d > 0 && N > 0, "empty problem T=%lld d=%lld N=%lld", T, d, N);
   SAEB_REQUIRE(ld_w % 8 == 0 && ld_x % 8 == 0, "ld_w and ld_x must be multiples of 8 (16-byte TMA strides)");
   SAEB_REQUIRE(k >= 1 && k <= 512 && k <= N, "k=%d out of range (1..min(512,N))", k);
@@ -698,64 +775,102 @@ int encode_topk_launch(const void* x_planes, int ap, long long T, long long ld_x
   SAEB_REQUIRE((reinterpret_cast<uintptr_t>(x_planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_planes) & 15) == 0,
                "x / packed weights must be 16-byte aligned");
   const int pair = default_pair();
-  EncodePlan plan = make_plan(T, N, k, pair, d, ap);
-  const bool do_topk = out_vals != nullptr;
+  static thread_local EncodePlan plan;
+  SAEB_REQUIRE(make_plan(plan, T, N, k, pair), "too many row chunks");
   if (do_topk)
-    SAEB_REQUIRE(workspace != nullptr && workspace_bytes >= plan.cand_bytes + plan.cnt_bytes,
-                 "workspace too small: have %zu need %zu", workspace_bytes, plan.cand_bytes + plan.cnt_bytes);
+    SAEB_REQUIRE(workspace != nullptr && workspace_bytes >= plan.total_bytes,
+                 "workspace too small: have %zu need %zu", workspace_bytes, plan.total_bytes);
+  if (g_persist_a && g_persist_bytes == 0) set_persist_a(1);
 
-  CUtensorMap ta, tb;
-  int rc = make_map(&ta, x_planes, d, T, ap, ld_x * 2, x_plane_stride * 2, BM);
+  CUtensorMap tb;
+  int rc = make_map(&tb, w_planes, d, N, bp, ld_w * 2, N * ld_w * 2, BN / pair);
   if (rc) return rc;
-  rc = make_map(&tb, w_planes, d, N, bp, ld_w * 2, N * ld_w * 2, BN / pair);
-  if (rc) return rc;
-
-  EncodeArgs args;
-  args.T = (int)T; args.d = (int)d; args.N = (int)N; args.k = k;
-  args.num_m_tiles = plan.num_m_tiles;
-  args.num_n_tiles = plan.num_n_tiles;
-  args.S = plan.S;
-  args.num_k_blocks = (int)((d + BK - 1) / BK);
-  args.pass_mask = pass_mask;
-  args.clamp_col = (int)clamp_feature;
-  args.clamp_val = clamp_value;
-  args.hint_a = (g_l2_hints & 1) ? L2_EVICT_LAST : L2_EVICT_NORMAL;
-  args.hint_b = (g_l2_hints & 2) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
-  args.idesc = make_idesc_f16(BM * pair, BN, operand_fmt, operand_fmt);   // 0 = fp16 operands, 1 = bf16
-  args.row_scale = row_scale;
-  args.w_unscale = w_unscale;
-  args.bias = bias;
-  args.cand_cnt = do_topk ? reinterpret_cast<int*>(workspace) : nullptr;
-  args.cand = do_topk ? reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(workspace) + plan.cnt_bytes) : nullptr;
-  args.dense_out = dense_out;
-  args.ld_dense = ld_dense;
-
   if (g_profile) cudaEventRecord(g_ev0, stream);
-  rc = (pair == 2) ? launch_planes<2>(ap, bp, ta, tb, args, plan.grid, plan.cap, stream)
-                   : launch_planes<1>(ap, bp, ta, tb, args, plan.grid, plan.cap, stream);
-  if (rc) return rc;
+  for (int ci = 0; ci < plan.n_chunks; ++ci) {
+    const ChunkPlan& c = plan.chunks[ci];
+    const uint8_t* xa = reinterpret_cast<const uint8_t*>(x_planes) + (size_t)c.t0 * ld_x * 2;
+    CUtensorMap ta;
+    rc = make_map(&ta, xa, d, c.rows, ap, ld_x * 2, x_plane_stride * 2, BM);
+    if (rc) return rc;
+    EncodeArgs args;
+    args.T = (int)c.rows; args.d = (int)d; args.N = (int)N; args.k = k;
+    args.num_m_tiles = c.num_m_tiles;
+    args.num_n_tiles = plan.num_n_tiles;
+    args.S = c.S;
+    args.num_k_blocks = (int)((d + BK - 1) / BK);
+    args.pass_mask = pass_mask;
+    args.clamp_col = (int)clamp_feature;
+    args.clamp_val = clamp_value;
+    args.dbg = g_dbg;
+    args.hint_a = (g_l2_hints & 1) ? L2_EVICT_LAST : L2_EVICT_NORMAL;
+    args.hint_b = (g_l2_hints & 2) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+    args.idesc = make_idesc_f16(BM * pair, BN, operand_fmt, operand_fmt);   // 0 = fp16 operands, 1 = bf16
+    args.row_scale = row_scale ? row_scale + c.t0 : nullptr;
+    args.w_unscale = w_unscale;
+    args.bias = bias;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    args.cand_cnt = do_topk ? reinterpret_cast<int*>(ws + c.cnt_off) : nullptr;
+    args.cand = do_topk ? reinterpret_cast<uint2*>(ws + c.cand_off) : nullptr;
+    args.dense_out = dense_out ? dense_out + (size_t)c.t0 * ld_dense : nullptr;
+    args.ld_dense = ld_dense;
+    g_window.base = const_cast<uint8_t*>(xa);
+    g_window.bytes = (plan.n_chunks > 1 || c.rows * ld_x * 2 <= (long long)g_persist_bytes + (8 << 20))
+                         ? (size_t)c.rows * (size_t)ld_x * 2 : 0;   // plane 0 of this chunk
+    rc = (pair == 2) ? launch_planes<2>(ap, bp, ta, tb, args, c.grid, plan.cap, stream)
+                     : launch_planes<1>(ap, bp, ta, tb, args, c.grid, plan.cap, stream);
+    if (rc) return rc;
+  }
   if (g_profile) {
     cudaEventRecord(g_ev1, stream);
     g_ev_valid = true;
   }
+  return 0;
+}
 
-  if (do_topk) {
-    int kp2 = 1;
-    while (kp2 < k) kp2 <<= 1;
-    if (kp2 < 2) kp2 = 2;
-    const int max_entries = plan.S * plan.cap;
+// Phase 2: exact top-k per row over the candidate lists of phase 1
+int encode_merge_launch(long long T, long long N, int k, float* out_vals, long long* out_idx, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream) {
+  const int pair = default_pair();
+  static thread_local EncodePlan plan;
+  SAEB_REQUIRE(make_plan(plan, T, N, k, pair), "too many row chunks");
+  SAEB_REQUIRE(workspace != nullptr && workspace_bytes >= plan.total_bytes, "merge: workspace too small");
+  int kp2 = 2;
+  while (kp2 < k) kp2 <<= 1;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  for (int ci = 0; ci < plan.n_chunks; ++ci) {
+    const ChunkPlan& c = plan.chunks[ci];
+    // consecutive chunks with the same split count share one launch (their lists are contiguous per chunk only, so
+    // each chunk is launched on its own row range)
+    const int max_entries = c.S * plan.cap;
     const size_t per_warp = (size_t)(max_entries + kp2) * sizeof(uint2);
     int wpb = (int)((200 * 1024) / per_warp);
     if (wpb > 8) wpb = 8;
     SAEB_REQUIRE(wpb >= 1, "merge: candidate set too large for shared memory");
     const size_t smem = per_warp * wpb;
     SAEB_CHECK_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int blocks = (int)((T + wpb - 1) / wpb);
-    topk_merge_kernel<<<blocks, wpb * 32, smem, stream>>>(args.cand, args.cand_cnt, (int)T, plan.S, plan.cap, k, kp2,
-                                                         (int)N, max_entries, out_vals, out_idx);
+    const int blocks = (int)((c.rows + wpb - 1) / wpb);
+    topk_merge_kernel<<<blocks, wpb * 32, smem, stream>>>(
+        reinterpret_cast<const uint2*>(ws + c.cand_off), reinterpret_cast<const int*>(ws + c.cnt_off), (int)c.rows, c.S,
+        plan.cap, k, kp2, (int)N, max_entries, out_vals + (size_t)c.t0 * k, out_idx + (size_t)c.t0 * k);
     SAEB_CHECK_CUDA(cudaGetLastError());
   }
   return 0;
+}
+
+// x_planes: [ap][T][ld_x] 16-bit (ap==1: the caller's bf16 activations in place)
+// w_planes: [bp][N][ld_w] 16-bit; bias: folded bias [N]
+int encode_topk_launch(const void* x_planes, int ap, long long T, long long ld_x, long long x_plane_stride,
+                       const void* w_planes, int bp, long long ld_w, const float* bias, long long d, long long N, int k,
+                       long long clamp_feature, float clamp_value, float* out_vals, long long* out_idx,
+                       float* dense_out, long long ld_dense, void* workspace, size_t workspace_bytes, int pass_mask,
+                       int operand_fmt, const float* row_scale, const float* w_unscale, cudaStream_t stream) {
+  const bool do_topk = out_vals != nullptr;
+  int rc = encode_gemm_launch(x_planes, ap, T, ld_x, x_plane_stride, w_planes, bp, ld_w, bias, d, N, k, clamp_feature,
+                              clamp_value, do_topk, dense_out, ld_dense, workspace, workspace_bytes, pass_mask,
+                              operand_fmt, row_scale, w_unscale, stream);
+  if (rc) return rc;
+  if (do_topk) rc = encode_merge_launch(T, N, k, out_vals, out_idx, workspace, workspace_bytes, stream);
+  return rc;
 }
 
 }  // namespace saeb

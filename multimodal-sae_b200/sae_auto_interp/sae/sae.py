@@ -62,7 +62,7 @@ class Sae(nn.Module):
         self.encoder_planes = 3
         self._packed = {}
         self._overlap = None
-        self.overlap_chunk = 8192
+        self.overlap_chunk = 18944  # two waves of 37 token tiles
 
     # ------------------------------------------------------------------ loading / saving
     @staticmethod

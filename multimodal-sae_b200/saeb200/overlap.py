@@ -17,25 +17,29 @@ from . import _capi, engine
 from ._capi import check
 
 
+WAVE_TOKENS = 9472  # 37 token tiles of 256 rows: one wave of (tile, split) units on a 148-SM part at S = 2
+
+
 class OverlappedForward:
-    def __init__(self, enc: engine.PackedEncoder, W_dec: torch.Tensor, b_dec: torch.Tensor, k: int, chunk: int = 8192):
+    def __init__(self, enc: engine.PackedEncoder, W_dec: torch.Tensor, b_dec: torch.Tensor, k: int,
+                 chunk: int = 2 * WAVE_TOKENS):
         if enc.planes != 3:
             raise _capi.SaebError("OverlappedForward needs the refine-mode packed encoder (planes=3)")
         self.enc, self.W_dec, self.b_dec, self.k, self.chunk = enc, W_dec, b_dec, k, chunk
         dev = enc.blob.device
         self.dev = dev
         L = _capi.lib()
-        self.ws_bytes = L.saeb_encode_topk_refine_workspace_bytes(chunk, enc.d_in, enc.num_latents, k, 0)
+        self.ws_bytes = L.saeb_candidates_workspace_bytes(chunk, enc.d_in, enc.num_latents, k, 0)
         self.ws = [torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.prep = None
         self.status = torch.zeros(2, dtype=torch.int32, device=dev)
-        lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
         self.s_gemm = torch.cuda.Stream(dev, priority=0)
         self.s_mem = torch.cuda.Stream(dev, priority=-1)   # gathers first: their CTAs slot in beside the GEMM's
 
     def run(self, x: torch.Tensor, acts: torch.Tensor, idx: torch.Tensor, sae_out: Optional[torch.Tensor] = None,
             sq_err: Optional[torch.Tensor] = None, ready_events=None, done_events=None) -> None:
-        """x [T, d] (bf16 / fp16 / fp32, 2-D, row stride a multiple of 8 elements); acts [T,k] f32, idx [T,k] i64,
-        sae_out [T,d] (optional) are filled; sq_err (0-dim f64, optional) accumulates sum((sae_out - x)^2).
+        """x [T, d] (bf16 / fp16 / fp32, 2-D, unit column stride); acts [T,k] f32, idx [T,k] i64 and sae_out [T,d]
+        (optional) are filled; sq_err (0-dim f64, optional) accumulates sum((sae_out - x)^2).
         `ready_events[c]` (optional) gates chunk c's input (H2D copies); `done_events[c]` is recorded when chunk c's
         outputs are complete.  Returns after ENQUEUEING; the caller's current stream waits for completion."""
         L = _capi.lib()
@@ -46,35 +50,69 @@ class OverlappedForward:
         self.s_gemm.wait_stream(main)
         self.s_mem.wait_stream(main)
         code = engine._code(x)
+        esz = x.element_size()
         ev_a = [torch.cuda.Event() for _ in range(n_chunks)]
         ev_b = [torch.cuda.Event() for _ in range(n_chunks)]
         ldx = x.stride(0) if T > 1 else enc.d_in
+        need = L.saeb_prep_bytes(T, enc.d_in)
+        if self.prep is None or self.prep.numel() < need:
+            self.prep = torch.empty(need, dtype=torch.uint8, device=self.dev)
+        prep = self.prep
         with torch.cuda.device(self.dev):
             for c in range(n_chunks):
                 a, b = c * self.chunk, min(T, (c + 1) * self.chunk)
-                xc = x[a:b]
                 ws = self.ws[c & 1]
                 with torch.cuda.stream(self.s_gemm):
-                    if c >= 2:
-                        self.s_gemm.wait_event(ev_b[c - 2])   # workspace reuse
                     if ready_events is not None:
                         self.s_gemm.wait_event(ready_events[c])
-                    check(L.saeb_encode_candidates(xc.data_ptr(), code, b - a, ldx, enc.blob.data_ptr(), enc.d_in,
+                    if c == 0 and ready_events is None:
+                        # whole batch at once: 16 KB of traffic per token, negligible next to the GEMM
+                        check(L.saeb_prep_activations(x.data_ptr(), code, T, ldx, enc.d_in, prep.data_ptr(),
+                                                      self.s_gemm.cuda_stream), "saeb_prep_activations")
+                    elif ready_events is not None:
+                        # inputs arrive chunk by chunk (host copies): prepare each chunk when it lands
+                        self._prep_rows(L, x, code, ldx, T, a, b, prep)
+                    if c >= 2:
+                        self.s_gemm.wait_event(ev_b[c - 2])   # scratch reuse
+                    check(L.saeb_encode_candidates(prep.data_ptr(), T, a, b - a, enc.blob.data_ptr(), enc.d_in,
                                                    enc.num_latents, k, 0, -1, 0.0, ws.data_ptr(), ws.numel(),
                                                    self.s_gemm.cuda_stream), "saeb_encode_candidates")
                     ev_a[c].record(self.s_gemm)
                 with torch.cuda.stream(self.s_mem):
                     self.s_mem.wait_event(ev_a[c])
-                    check(L.saeb_refine_candidates(xc.data_ptr(), code, b - a, ldx, enc.blob.data_ptr(),
-                                                   enc.W_enc.data_ptr(), enc.d_in, enc.num_latents, k, 0, -1, 0.0,
-                                                   acts[a:b].data_ptr(), idx[a:b].data_ptr(),
-                                                   self.status[c & 1:].data_ptr(), ws.data_ptr(), ws.numel(),
-                                                   self.s_mem.cuda_stream), "saeb_refine_candidates")
+                    check(L.saeb_refine_candidates(x.data_ptr() + a * ldx * esz, code, ldx, prep.data_ptr(), T, a,
+                                                   b - a, enc.blob.data_ptr(), enc.W_enc.data_ptr(), enc.d_in,
+                                                   enc.num_latents, k, 0, -1, 0.0, acts[a:b].data_ptr(),
+                                                   idx[a:b].data_ptr(), self.status[c & 1:].data_ptr(), ws.data_ptr(),
+                                                   ws.numel(), self.s_mem.cuda_stream), "saeb_refine_candidates")
                     if sae_out is not None:
-                        engine.decode(idx[a:b], acts[a:b], self.W_dec, self.b_dec, x=xc if sq_err is not None else None,
-                                      sq_err=sq_err, out=sae_out[a:b])
+                        engine.decode(idx[a:b], acts[a:b], self.W_dec, self.b_dec,
+                                      x=x[a:b] if sq_err is not None else None, sq_err=sq_err, out=sae_out[a:b])
                     ev_b[c].record(self.s_mem)
                     if done_events is not None:
                         done_events[c].record(self.s_mem)
         main.wait_stream(self.s_mem)
         main.wait_stream(self.s_gemm)
+
+    def _prep_rows(self, L, x, code, ldx, T, a, b, prep):
+        """Prepare rows [a, b) in place inside the whole-batch `prep` layout (x16 | row_scale | xnorm)."""
+        d = self.enc.d_in
+        d_pad = (d + 7) // 8 * 8
+        # the per-row outputs are independent, so a chunk is prepared through a view of the batch layout: the C entry
+        # point lays out its three arrays from the base pointer and T, hence one call per chunk on a temporary and a
+        # strided copy would be wasteful -- instead prepare directly with row offsets via three sub-calls' worth of
+        # pointer arithmetic (x16 rows are contiguous per row; scales / norms are plain arrays).
+        tmp_bytes = L.saeb_prep_bytes(b - a, d)
+        if not hasattr(self, "_tmp") or self._tmp.numel() < tmp_bytes:
+            self._tmp = torch.empty(tmp_bytes, dtype=torch.uint8, device=self.dev)
+        tmp = self._tmp
+        check(L.saeb_prep_activations(x.data_ptr() + a * ldx * x.element_size(), code, b - a, ldx, d, tmp.data_ptr(),
+                                      self.s_gemm.cuda_stream), "saeb_prep_activations")
+        n = b - a
+        rs_off_c = (n * d_pad * 2 + 1023) // 1024 * 1024
+        xn_off_c = rs_off_c + (n * 4 + 255) // 256 * 256
+        rs_off = (T * d_pad * 2 + 1023) // 1024 * 1024
+        xn_off = rs_off + (T * 4 + 255) // 256 * 256
+        prep[a * d_pad * 2:b * d_pad * 2].copy_(tmp[:n * d_pad * 2], non_blocking=True)
+        prep[rs_off + a * 4:rs_off + b * 4].copy_(tmp[rs_off_c:rs_off_c + n * 4], non_blocking=True)
+        prep[xn_off + a * 4:xn_off + b * 4].copy_(tmp[xn_off_c:xn_off_c + n * 4], non_blocking=True)

@@ -9,7 +9,7 @@ from . import engine
 
 
 class HostForward:
-    def __init__(self, sae, num_tokens: int, chunk: int = 8192, x_dtype=torch.bfloat16):
+    def __init__(self, sae, num_tokens: int, chunk: int = 9472, x_dtype=torch.bfloat16):
         dev = sae.device
         self.sae, self.T, self.chunk = sae, num_tokens, min(chunk, num_tokens)
         k, d = sae.cfg.k, sae.d_in

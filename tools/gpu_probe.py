@@ -70,9 +70,12 @@ def exp_topk(pair, planes, T, d, N, k, xdt="bf16"):
     return dict(rows=T, rows_with_set_mismatch=bad_rows, max_rel_val_err=maxrel, sorted_desc=sorted_ok)
 
 
-def exp_time(pair, planes, T, d, N, k, iters=3, splits=0):
+def exp_time(pair, planes, T, d, N, k, iters=3, splits=0, dbg=0, hints=1, persist=0):
     torch, engine = _setup(pair)
     from saeb200 import _capi
+    _capi.check(_capi.lib().saeb_set_option(b"debug_tiles", dbg), "set_option")
+    _capi.check(_capi.lib().saeb_set_option(b"l2_hints", hints), "set_option")
+    _capi.check(_capi.lib().saeb_set_option(b"persist_a", persist), "set_option")
     _capi.check(_capi.lib().saeb_set_option(b"splits", splits), "set_option")
     _capi.check(_capi.lib().saeb_set_option(b"profile", 1), "set_option")
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -125,11 +128,13 @@ def exp_decode(T, d, N, k):
     return dict(max_abs_err=(y.double() - ref).abs().max().item(), ref_absmax=ref.abs().max().item())
 
 
-def exp_overlap(T, chunk, planes=3, overlap=True, l2_hints=1, splits=0, iters=3):
+def exp_overlap(T, chunk, planes=3, overlap=True, l2_hints=1, splits=0, iters=3, persist=1, chunking=1):
     torch, engine = _setup(2)
     from saeb200 import _capi, synth
     from saeb200.overlap import OverlappedForward
     L = _capi.lib()
+    _capi.check(L.saeb_set_option(b"persist_a", persist), "set_option")
+    _capi.check(L.saeb_set_option(b"chunking", chunking), "set_option")
     _capi.check(L.saeb_set_option(b"l2_hints", l2_hints), "set_option")
     _capi.check(L.saeb_set_option(b"splits", splits), "set_option")
     sae = synth.make_sae(4096, 131072, 64, "cuda", seed=1234)
@@ -192,9 +197,38 @@ EXPS = {
     "time_refine_16k": lambda: exp_time(2, 3, 16384, 4096, 131072, 64),
     "time_refine_64k": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2),
     "time_refine_64k_s2": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=2),
+    "t_h0": lambda: exp_time(2, 1, 65536, 4096, 131072, 64, iters=2, hints=0),
+    "t_h1": lambda: exp_time(2, 1, 65536, 4096, 131072, 64, iters=2, hints=1),
+    "t_h2": lambda: exp_time(2, 1, 65536, 4096, 131072, 64, iters=2, hints=2),
+    "t_h3": lambda: exp_time(2, 1, 65536, 4096, 131072, 64, iters=2, hints=3),
+    "t_s8": lambda: exp_time(2, 1, 65536, 4096, 131072, 64, iters=2, splits=8),
+    "t_9472": lambda: exp_time(2, 1, 9472, 4096, 131072, 64, iters=3, splits=2),
+    "t_9472_persist": lambda: exp_time(2, 1, 9472, 4096, 131072, 64, iters=3, splits=2, persist=1),
+    "t_9472_persist_h2": lambda: exp_time(2, 1, 9472, 4096, 131072, 64, iters=3, splits=2, persist=1, hints=2),
+    "t_4736_persist_s4": lambda: exp_time(2, 1, 4736, 4096, 131072, 64, iters=3, splits=4, persist=1),
+    "time_dbg_a": lambda: exp_time(2, 1, 65536, 4096, 131072, 64, iters=2, dbg=1),
+    "time_dbg_b": lambda: exp_time(2, 1, 65536, 4096, 131072, 64, iters=2, dbg=2),
+    "time_dbg_ab": lambda: exp_time(2, 1, 65536, 4096, 131072, 64, iters=2, dbg=3),
+    "time_dbg_0": lambda: exp_time(2, 1, 65536, 4096, 131072, 64, iters=2, dbg=0),
+    "time_refine_64k_s3": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=3),
     "time_refine_64k_s4": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=4),
     "time_refine_64k_s6": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=6),
     "time_refine_64k_s8": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=8),
+    "ov2_c9472": lambda: exp_overlap(65536, 9472),
+    "ov2_c18944": lambda: exp_overlap(65536, 18944),
+    "ov2_c28416": lambda: exp_overlap(65536, 28416),
+    "ov2_c18944_nopersist": lambda: exp_overlap(65536, 18944, persist=0),
+    "seq2_refine": lambda: exp_overlap(65536, 18944, overlap=False),
+    "seq2_refine_nochunk": lambda: exp_overlap(65536, 18944, overlap=False, chunking=0),
+    "seq2_hilo": lambda: exp_overlap(65536, 18944, planes=2, overlap=False),
+    "seq2_hilo_nochunk": lambda: exp_overlap(65536, 18944, planes=2, overlap=False, chunking=0),
+    "ov_s2_c18944": lambda: exp_overlap(65536, 18944, splits=2),
+    "ov_s3_c18944": lambda: exp_overlap(65536, 18944, splits=3),
+    "ov_s4_c18944": lambda: exp_overlap(65536, 18944, splits=4),
+    "ov_s4_c9472": lambda: exp_overlap(65536, 9472, splits=4),
+    "ov_s2_c9472": lambda: exp_overlap(65536, 9472, splits=2),
+    "ov_s6_c18944": lambda: exp_overlap(65536, 18944, splits=6),
+    "seq_s4": lambda: exp_overlap(65536, 18944, splits=4, overlap=False),
     "ov_64k_c8k": lambda: exp_overlap(65536, 8192),
     "ov_64k_c16k": lambda: exp_overlap(65536, 16384),
     "ov_64k_c4k": lambda: exp_overlap(65536, 4096),
