@@ -35,6 +35,16 @@ __device__ __forceinline__ float4 load_w4<__nv_bfloat16>(const __nv_bfloat16* ro
   return f;
 }
 
+template <>
+__device__ __forceinline__ float4 load_w4<__half>(const __half* row, int col4) {
+  uint2 u;
+  const uint2* p = reinterpret_cast<const uint2*>(row) + col4;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(u.x), "=r"(u.y) : "l"(p));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
 template <typename XT>
 __device__ __forceinline__ float4 load_x4(const XT* row, int col4);
 template <>
@@ -308,6 +318,9 @@ int decode_launch(const long long* idx, const float* vals, long long T, int k, c
   if (w_dtype == DT_BF16)
     return decode_dispatch_o<__nv_bfloat16>(idx, vals, T, k, reinterpret_cast<const __nv_bfloat16*>(W_dec), d, N,
                                             b_dec, out, out_dtype, ld_out, x, x_dtype, ld_x, sq_err, err_flag, stream);
+  if (w_dtype == DT_F16)
+    return decode_dispatch_o<__half>(idx, vals, T, k, reinterpret_cast<const __half*>(W_dec), d, N, b_dec, out,
+                                     out_dtype, ld_out, x, x_dtype, ld_x, sq_err, err_flag, stream);
   set_error("decode: unsupported W_dec dtype %d", w_dtype);
   return -1;
 }
