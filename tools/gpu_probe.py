@@ -217,6 +217,9 @@ EXPS = {
     "seq3_refine": lambda: exp_overlap(65536, 18944, overlap=False),
     "ov3_c18944": lambda: exp_overlap(65536, 18944),
     "ov3_c9472": lambda: exp_overlap(65536, 9472),
+    "seq3_refine": lambda: exp_overlap(65536, 18944, overlap=False),
+    "ov3_c18944": lambda: exp_overlap(65536, 18944),
+    "ov3_c9472": lambda: exp_overlap(65536, 9472),
     "ov2_c9472": lambda: exp_overlap(65536, 9472),
     "ov2_c18944": lambda: exp_overlap(65536, 18944),
     "ov2_c28416": lambda: exp_overlap(65536, 28416),
