@@ -75,17 +75,17 @@ int saeb_encode_topk(const void* x, int x_dtype, int64_t T, int64_t ld_x, const 
 
 /* ---- fused encode + TopK, single tensor-core pass with exact refinement ("fp16 + refine") -------------------------
  * Same result contract as saeb_encode_topk (parity grade) at half the tensor-core work.  `packed` must have been
- * produced by saeb_pack_weights(..., planes = 3): fp16 plane of W_enc (power-of-two scaled) + fp16 residual plane
- * (their sum reproduces W_enc to 2^-22), folded bias, per-feature norms.  The GEMM (first plane only) ranks by
- * approximate values; for every candidate that can still belong to the TopK under the rigorous rounding bound
- * (2^-11 [+2^-11 for fp32 x] + 2^-12) * ||x||_2 * ||w_j||_2  the residual product x . W_lo[j] is added in fp32, so the
- * returned values carry only fp32 accumulation noise and the index set is the fp32 reference's.  `margin` = extra candidates kept per row (0 = max(64, k/2)).  Rows whose candidate list could be too short
+ * produced by saeb_pack_weights(..., planes = 3): one fp16 plane of W_enc (power-of-two scaled), folded bias,
+ * per-feature norms.  The GEMM ranks by approximate values; every candidate that can still belong to the TopK under the
+ * rigorous rounding bound  (2^-11 [+2^-11 for fp32 x] + 2^-12) * ||x||_2 * ||w_j||_2  is re-evaluated exactly in fp32
+ * against `W_enc` (the [N,d] fp32 parameter itself), so the returned values are fp32-exact and the index set is the
+ * fp32 reference's.  `margin` = extra candidates kept per row (0 = max(64, k/2)).  Rows whose candidate list could be too short
  * for the bound (never observed) are recomputed by an exact dense fp32 kernel, up to 64 per call; *status_out (device
  * int, may be NULL) receives the number of such rows -- more than 64 means the call must be repeated with a larger
  * margin. */
 size_t saeb_encode_topk_refine_workspace_bytes(int64_t T, int64_t d, int64_t N, int k, int margin);
-int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed, int64_t d,
-                            int64_t N, int k, int margin, int64_t clamp_feature,
+int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed,
+                            const float* W_enc, int64_t d, int64_t N, int k, int margin, int64_t clamp_feature,
                             float clamp_value, float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
                             size_t workspace_bytes, void* stream);
 
@@ -94,7 +94,7 @@ int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x,
  *   saeb_prep_activations   whole batch: activations -> power-of-two scaled fp16 plane + per-row scale + norms
  *                           (`prep`, saeb_prep_bytes(T, d) bytes);
  *   saeb_encode_candidates  rows [t0, t0+Tc): single-pass GEMM with fused candidate selection (tensor bound);
- *   saeb_refine_candidates  same rows: candidate merge + fp32 residual correction + dense fallback (HBM bound); `x`
+ *   saeb_refine_candidates  same rows: candidate merge + exact fp32 re-evaluation + dense fallback (HBM bound); `x`
  *                           points at row t0 of the original activations.
  * Both row-range calls share a scratch buffer of saeb_candidates_workspace_bytes(Tc, ...) bytes. */
 size_t saeb_prep_bytes(int64_t T, int64_t d);
@@ -104,7 +104,7 @@ int saeb_encode_candidates(const void* prep, int64_t T_total, int64_t t0, int64_
                            int64_t N, int k, int margin, int64_t clamp_feature, float clamp_value, void* workspace,
                            size_t workspace_bytes, void* stream);
 int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total, int64_t t0,
-                           int64_t Tc, const void* packed, int64_t d, int64_t N, int k, int margin,
+                           int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N, int k, int margin,
                            int64_t clamp_feature, float clamp_value, float* out_vals, int64_t* out_idx,
                            int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream);
 

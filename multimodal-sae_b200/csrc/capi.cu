@@ -40,8 +40,7 @@ int pack_weights_f16_launch(const float* W_enc, const float* b_enc, const float*
 int prep_x_f16_launch(const void* x, int x_dtype, long long T, long long d, long long ld_x, long long d_pad, void* out,
                       float* row_scale, float* xnorm, cudaStream_t stream);
 size_t refine_fallback_bytes(long long N);
-int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const void* w_hi, const void* w_lo,
-                  long long ld_w, long long d, long long N,
+int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const float* W, long long d, long long N,
                   const float* bias, const float* wnorm, const float* trailer, const float* xnorm, float c_eps,
                   const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                   float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
@@ -80,8 +79,8 @@ float last_encode_ms();
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline long long pad8(long long d) { return (d + 7) / 8 * 8; }   // 16-byte row strides for TMA
-// planes: 1 / 2 = bf16 planes; 3 = "fp16 + refine" mode (scaled fp16 plane + fp16 residual plane + norms + trailer)
-static inline int n_planes(int planes) { return planes == 3 ? 2 : planes; }   // mode 3: fp16 hi + fp16 residual
+// planes: 1 / 2 = bf16 planes; 3 = "fp16 + refine" mode (one scaled fp16 plane + per-feature norms + trailer)
+static inline int n_planes(int planes) { return planes == 3 ? 1 : planes; }
 static inline size_t planes_bytes(long long N, long long d, int planes) {
   return align_up((size_t)n_planes(planes) * (size_t)N * (size_t)pad8(d) * 2, 256);
 }
@@ -289,11 +288,11 @@ int saeb_encode_candidates(const void* prep, int64_t T_total, int64_t t0, int64_
 // phase B: candidate merge + exact fp32 re-evaluation (+ dense fallback) for the same rows (HBM bound).
 // x points at row t0 of the ORIGINAL activations.
 int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total, int64_t t0,
-                           int64_t Tc, const void* packed, int64_t d, int64_t N, int k, int margin,
+                           int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N, int k, int margin,
                            int64_t clamp_feature, float clamp_value, float* out_vals, int64_t* out_idx,
                            int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream) {
   g_err[0] = 0;
-  SAEB_REQUIRE(x && prep && packed && out_vals && out_idx && workspace, "refine_candidates: null pointer");
+  SAEB_REQUIRE(x && prep && packed && W_enc && out_vals && out_idx && workspace, "refine_candidates: null pointer");
   SAEB_REQUIRE(t0 >= 0 && Tc >= 0 && t0 + Tc <= T_total, "refine_candidates: bad row range");
   if (Tc == 0) return 0;
   const int K2raw = refine_k2(k, margin);
@@ -316,7 +315,7 @@ int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void*
   if (rc) return rc;
   // error-bound constant: fp16 rounding of W (2^-11), of x when it is fp32 (2^-11), and 2^-12 for the fp32 accumulation
   const float c_eps = ldexpf(1.0f, -11) + (x_dtype == DT_F32 ? ldexpf(1.0f, -11) : 0.f) + ldexpf(1.0f, -12);
-  rc = refine_launch(x, x_dtype, Tc, ld_x, pk, pk + (size_t)N * pad8(d) * 2, pad8(d), d, N, bias, wnorm, trailer,
+  rc = refine_launch(x, x_dtype, Tc, ld_x, W_enc, d, N, bias, wnorm, trailer,
                      reinterpret_cast<const float*>(pb + p.xnorm) + t0, c_eps, mvals, midx, K2, k < K2 ? k : K2,
                      clamp_feature, clamp_value, out_vals, reinterpret_cast<long long*>(out_idx), status,
                      reinterpret_cast<int*>(ws + w.flag_rows), reinterpret_cast<float*>(ws + w.dense), st);
@@ -331,8 +330,8 @@ size_t saeb_encode_topk_refine_workspace_bytes(int64_t T, int64_t d, int64_t N, 
   return align_up(prep_layout(T, d).total, 1024) + refine_ws(T, d, N, k, margin).total;
 }
 
-int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed, int64_t d,
-                            int64_t N, int k, int margin, int64_t clamp_feature,
+int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed,
+                            const float* W_enc, int64_t d, int64_t N, int k, int margin, int64_t clamp_feature,
                             float clamp_value, float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
                             size_t workspace_bytes, void* stream) {
   g_err[0] = 0;
@@ -347,7 +346,7 @@ int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x,
   rc = saeb_encode_candidates(ws, T, 0, T, packed, d, N, k, margin, clamp_feature, clamp_value, ws + prep_bytes,
                               workspace_bytes - prep_bytes, stream);
   if (rc) return rc;
-  return saeb_refine_candidates(x, x_dtype, ld_x, ws, T, 0, T, packed, d, N, k, margin, clamp_feature,
+  return saeb_refine_candidates(x, x_dtype, ld_x, ws, T, 0, T, packed, W_enc, d, N, k, margin, clamp_feature,
                                 clamp_value, out_vals, out_idx, status_out, ws + prep_bytes,
                                 workspace_bytes - prep_bytes, stream);
 }

@@ -127,19 +127,12 @@ __global__ void pack_w_f16_kernel(const float* __restrict__ W, long long N, long
   int e = 0;
   if (amax > 0.f) frexpf(amax, &e);            // amax = m * 2^e, m in [0.5, 1)
   const float scale = ldexpf(1.0f, 14 - e);    // largest |W| lands in [2^13, 2^14): far from fp16 overflow/underflow
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    trailer[0] = ldexpf(1.0f, e - 14);         // undoes the hi scale
-    trailer[3] = ldexpf(1.0f, e - 14 - 11);    // undoes the lo scale (the residual is 2^11 times smaller)
-  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) trailer[0] = ldexpf(1.0f, e - 14);
   const long long total = N * d_pad;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const long long r = i / d_pad, c = i - r * d_pad;
-    const float ws = (c < d) ? W[r * d + c] * scale : 0.f;   // exact: power-of-two scale
-    const __half hi = __float2half_rn(ws);
-    out[i] = hi;
-    // residual after fp16 rounding, scaled by 2^11 back into the comfortable fp16 range; hi + lo reproduces W to 2^-22
-    out[total + i] = __float2half_rn((ws - __half2float(hi)) * 2048.0f);
+    out[i] = __float2half_rn((c < d) ? W[r * d + c] * scale : 0.f);
   }
 }
 
@@ -147,7 +140,7 @@ int pack_weights_f16_launch(const float* W_enc, const float* b_enc, const float*
                             long long d_pad, void* w_plane, float* bias, float* wnorm, float* trailer,
                             cudaStream_t stream) {
   SAEB_REQUIRE(N > 0 && d > 0, "pack: need N>0 and d>0 (got N=%lld d=%lld)", N, d);
-  // trailer[0] = w_unscale, trailer[1] = wnorm_max, trailer[2] = |W|max (scratch bits), trailer[3] = lo_unscale
+  // trailer[0] = w_unscale, trailer[1] = wnorm_max, trailer[2] = |W|max (scratch bits)
   SAEB_CHECK_CUDA(cudaMemsetAsync(trailer, 0, 16, stream));
   w_stats_kernel<<<(int)((N + 7) / 8), 256, 0, stream>>>(W_enc, b_enc, b_dec, N, d, bias, wnorm,
                                                          reinterpret_cast<unsigned int*>(trailer + 2),

@@ -4,14 +4,12 @@
 // K2 = k + margin best candidates by APPROXIMATE value a_j.  With u = 2^-11 the rounding error of candidate j is
 // bounded by  eps_j = c_eps * ||x||_2 * ||w_j||_2  (Cauchy-Schwarz; c_eps = u_w + u_x + accumulation slack).  Hence
 //   * the true k-th value is at least L = k-th largest of (a_j - eps_j);
-//   * only candidates with a_j + eps_j >= L can belong to the true TopK; for those the missing part of the product is
-//     added here: a_j + x . W_lo[j], where W_lo = fp16 residual plane (W_hi + W_lo = W to 2^-22), fp32 accumulate --
-//     the corrected values carry only fp32 accumulation noise, like the reference's own fp32 GEMM -- and the final TopK
-//     is taken over the corrected values;
+//   * only candidates with a_j + eps_j >= L can belong to the true TopK; they are re-evaluated EXACTLY here
+//     (fp32 dot product with the fp32 W_enc row + folded bias), and the final TopK is taken over the exact values;
 //   * a non-candidate has a <= a_last (the smallest kept approximation); if a_last + c_eps*||x||*max_j||w_j|| >= L
 //     the candidate list might be too short: the row is FLAGGED and recomputed by the exact dense kernels below.
-// Output values are fp32-grade like the reference's (sae/sae.py:172-181), the index set is the reference's up to
-// fp32 summation noise; the gather is HBM-bound (about (k + 20) fp16 rows of 2*d bytes per token).
+// Output values are fp32-exact like the reference's (sae/sae.py:172-181), the index set is the reference's up to
+// fp32 summation noise; the gather is HBM-bound (about (k + 20) fp32 rows per token).
 #include "common.cuh"
 
 namespace saeb {
@@ -21,8 +19,7 @@ constexpr int RF_MAX_FLAG = 64;   // rows the dense fallback can absorb per call
 
 template <typename XT>
 __global__ void __launch_bounds__(RF_THREADS)
-refine_kernel(const XT* __restrict__ x, long long ld_x, const __half* __restrict__ Wlo, long long ld_w, long long d,
-              long long N,
+refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict__ W, long long d, long long N,
               const float* __restrict__ bias, const float* __restrict__ wnorm, const float* __restrict__ trailer,
               const float* __restrict__ xnorm, float c_eps, const float* __restrict__ cand_vals,
               const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
@@ -30,7 +27,7 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const __half* __restrict
               int* __restrict__ flag_rows) {
   extern __shared__ float rsm[];
   float* xs = rsm;                                   // [d4] activations of this row as fp32
-  const int d4 = (int)((d + 7) & ~7ll);              // padded like the weight rows
+  const int d4 = (int)((d + 3) & ~3ll);
   float* a = xs + d4;                                // [K2] approximate values
   float* lb = a + K2;                                // [K2]
   float* ub = lb + K2;                               // [K2]
@@ -84,8 +81,8 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const __half* __restrict
       if (slot < RF_MAX_FLAG) flag_rows[slot] = (int)t;
     }
   }
-  // residual correction of every candidate that can still be in the TopK
-  const float lo_unscale = trailer[3];
+  // exact re-evaluation of every candidate that can still be in the TopK
+  const bool vec = (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
   for (int j = warp; j < K2; j += RF_THREADS / 32) {
     if (!(ub[j] >= L) || !(a[j] > 0.f)) continue;
     const int fj = f[j];
@@ -93,38 +90,41 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const __half* __restrict
     if (fj == clamp_feature) {
       val = clamp_value;
     } else {
-      const uint4* w8 = reinterpret_cast<const uint4*>(Wlo + (long long)fj * ld_w);   // 8 halves per 16-byte load
-      const float4* x4 = reinterpret_cast<const float4*>(xs);
-      const int n8 = (int)((d + 7) >> 3);   // rows are zero padded to a multiple of 8 elements, xs to d4
+      const float* wr = W + (long long)fj * d;
       float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-      auto fma8 = [&](const uint4& wv, int c8) {
-        const float2 w0 = __half22float2(*reinterpret_cast<const __half2*>(&wv.x));
-        const float2 w1 = __half22float2(*reinterpret_cast<const __half2*>(&wv.y));
-        const float2 w2 = __half22float2(*reinterpret_cast<const __half2*>(&wv.z));
-        const float2 w3 = __half22float2(*reinterpret_cast<const __half2*>(&wv.w));
-        const float4 xa = x4[2 * c8], xb = x4[2 * c8 + 1];
-        acc0 = fmaf(w0.x, xa.x, acc0);
-        acc1 = fmaf(w0.y, xa.y, acc1);
-        acc2 = fmaf(w1.x, xa.z, acc2);
-        acc3 = fmaf(w1.y, xa.w, acc3);
-        acc0 = fmaf(w2.x, xb.x, acc0);
-        acc1 = fmaf(w2.y, xb.y, acc1);
-        acc2 = fmaf(w3.x, xb.z, acc2);
-        acc3 = fmaf(w3.y, xb.w, acc3);
-      };
-      int c = lane;
-      for (; c + 7 * 32 < n8; c += 8 * 32) {
-        uint4 wv[8];
+      if (vec) {
+        const float4* w4 = reinterpret_cast<const float4*>(wr);
+        const float4* x4 = reinterpret_cast<const float4*>(xs);
+        const int n4 = (int)(d >> 2);
+        int c = lane;
+        for (; c + 7 * 32 < n4; c += 8 * 32) {
+          float4 wv[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) wv[u] = ldg_nc_u4(w8 + c + u * 32);
+          for (int u = 0; u < 8; ++u) wv[u] = ldg_nc_f4(w4 + c + u * 32);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) fma8(wv[u], c + u * 32);
+          for (int u = 0; u < 8; ++u) {
+            const float4 xv = x4[c + u * 32];
+            acc0 = fmaf(wv[u].x, xv.x, acc0);
+            acc1 = fmaf(wv[u].y, xv.y, acc1);
+            acc2 = fmaf(wv[u].z, xv.z, acc2);
+            acc3 = fmaf(wv[u].w, xv.w, acc3);
+          }
+        }
+        for (; c < n4; c += 32) {
+          const float4 wv = ldg_nc_f4(w4 + c);
+          const float4 xv = x4[c];
+          acc0 = fmaf(wv.x, xv.x, acc0);
+          acc1 = fmaf(wv.y, xv.y, acc1);
+          acc2 = fmaf(wv.z, xv.z, acc2);
+          acc3 = fmaf(wv.w, xv.w, acc3);
+        }
+      } else {
+        for (long long i = lane; i < d; i += 32) acc0 = fmaf(wr[i], xs[i], acc0);
       }
-      for (; c < n8; c += 32) fma8(ldg_nc_u4(w8 + c), c);
       float acc = (acc0 + acc1) + (acc2 + acc3);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      val = fmaf(acc, lo_unscale, a[j]);   // a_j already holds x . W_hi + folded bias
+      val = acc + bias[fj];
     }
     if (lane == 0) ex[j] = (val > 0.f) ? val : -1.f;
   }
@@ -171,11 +171,9 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const __half* __restrict
 // ---------------------------------------------------------------------------------------------
 template <typename XT>
 __global__ void __launch_bounds__(256)
-exact_rows_kernel(const XT* __restrict__ x, long long ld_x, const __half* __restrict__ Whi,
-                  const __half* __restrict__ Wlo, long long ld_w, long long d, long long N,
-                  const float* __restrict__ bias, const float* __restrict__ trailer, const int* __restrict__ status,
-                  const int* __restrict__ flag_rows, long long clamp_feature, float clamp_value,
-                  float* __restrict__ dense) {
+exact_rows_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict__ W, long long d, long long N,
+                  const float* __restrict__ bias, const int* __restrict__ status, const int* __restrict__ flag_rows,
+                  long long clamp_feature, float clamp_value, float* __restrict__ dense) {
   extern __shared__ float esm[];
   const int slot = blockIdx.y;
   const int nflag = min(status[0], RF_MAX_FLAG);
@@ -183,26 +181,18 @@ exact_rows_kernel(const XT* __restrict__ x, long long ld_x, const __half* __rest
   const long long t = flag_rows[slot];
   for (long long i = threadIdx.x; i < d; i += blockDim.x) esm[i] = (float)x[t * ld_x + i];
   __syncthreads();
-  const float hi_unscale = trailer[0], lo_unscale = trailer[3];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const long long per_block = (N + gridDim.x - 1) / gridDim.x;
   const long long n0 = (long long)blockIdx.x * per_block;
   const long long n1 = (n0 + per_block < N) ? n0 + per_block : N;
   for (long long n = n0 + warp; n < n1; n += nw) {
-    const __half* hr = Whi + n * ld_w;
-    const __half* lr = Wlo + n * ld_w;
-    float ah = 0.f, al = 0.f;
-    for (long long i = lane; i < d; i += 32) {
-      ah = fmaf(__half2float(hr[i]), esm[i], ah);
-      al = fmaf(__half2float(lr[i]), esm[i], al);
-    }
+    const float* wr = W + n * d;
+    float acc = 0.f;
+    for (long long i = lane; i < d; i += 32) acc = fmaf(wr[i], esm[i], acc);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ah += __shfl_xor_sync(0xffffffffu, ah, o);
-      al += __shfl_xor_sync(0xffffffffu, al, o);
-    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
-      float v = fmaf(al, lo_unscale, fmaf(ah, hi_unscale, bias[n]));
+      float v = acc + bias[n];
       if (n == clamp_feature) v = clamp_value;
       dense[(long long)slot * N + n] = fmaxf(v, 0.f);
     }
@@ -304,18 +294,17 @@ dense_topk_kernel(const float* __restrict__ dense, long long ld, long long N, in
 size_t refine_fallback_bytes(long long N) { return (size_t)RF_MAX_FLAG * (size_t)N * sizeof(float) + 1024; }
 
 template <typename XT>
-static int refine_launch_t(const XT* x, long long T, long long ld_x, const __half* Whi, const __half* Wlo,
-                           long long ld_w, long long d, long long N,
+static int refine_launch_t(const XT* x, long long T, long long ld_x, const float* W, long long d, long long N,
                            const float* bias, const float* wnorm, const float* trailer, const float* xnorm, float c_eps,
                            const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                            float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
                            float* dense_scratch, cudaStream_t stream) {
-  const int d4 = (int)((d + 7) & ~7ll);
+  const int d4 = (int)((d + 3) & ~3ll);
   const size_t smem = (size_t)(d4 + 5 * K2) * sizeof(float);
   SAEB_REQUIRE(smem <= 200 * 1024, "refine: d=%lld too large for the shared-memory row buffer", d);
   auto kern = refine_kernel<XT>;
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)T, RF_THREADS, smem, stream>>>(x, ld_x, Wlo, ld_w, d, N, bias, wnorm, trailer, xnorm, c_eps, cand_vals,
+  kern<<<(unsigned)T, RF_THREADS, smem, stream>>>(x, ld_x, W, d, N, bias, wnorm, trailer, xnorm, c_eps, cand_vals,
                                                  cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx,
                                                  status, flag_rows);
   SAEB_CHECK_CUDA(cudaGetLastError());
@@ -324,8 +313,8 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const __hal
   const size_t esmem = (size_t)d * sizeof(float);
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(ek, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
   dim3 eg(128, RF_MAX_FLAG);
-  ek<<<eg, 256, esmem, stream>>>(x, ld_x, Whi, Wlo, ld_w, d, N, bias, trailer, status, flag_rows, clamp_feature,
-                                 clamp_value, dense_scratch);
+  ek<<<eg, 256, esmem, stream>>>(x, ld_x, W, d, N, bias, status, flag_rows, clamp_feature, clamp_value,
+                                 dense_scratch);
   SAEB_CHECK_CUDA(cudaGetLastError());
   int kp2 = 2;
   while (kp2 < k) kp2 <<= 1;
@@ -335,15 +324,13 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const __hal
   return 0;
 }
 
-int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const void* w_hi, const void* w_lo,
-                  long long ld_w, long long d, long long N,
+int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const float* W, long long d, long long N,
                   const float* bias, const float* wnorm, const float* trailer, const float* xnorm, float c_eps,
                   const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                   float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
                   float* dense_scratch, cudaStream_t stream) {
 #define SAEB_RF(XT)                                                                                                  \
-  return refine_launch_t<XT>(reinterpret_cast<const XT*>(x), T, ld_x, reinterpret_cast<const __half*>(w_hi),         \
-                             reinterpret_cast<const __half*>(w_lo), ld_w, d, N, bias, wnorm, trailer, xnorm, c_eps,  \
+  return refine_launch_t<XT>(reinterpret_cast<const XT*>(x), T, ld_x, W, d, N, bias, wnorm, trailer, xnorm, c_eps,   \
                              cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx, status,      \
                              flag_rows, dense_scratch, stream)
   if (x_dtype == DT_F32) SAEB_RF(float);

@@ -34,7 +34,7 @@ SIGNATURES = {
                                  c_int64, c_float, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t,
                                  c_void_p]),
     "saeb_encode_topk_refine_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int, c_int]),
-    "saeb_encode_topk_refine": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int,
+    "saeb_encode_topk_refine": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int,
                                         c_int, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                         c_void_p]),
     "saeb_prep_bytes": (c_size_t, [c_int64, c_int64]),
@@ -43,7 +43,7 @@ SIGNATURES = {
     "saeb_encode_candidates": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int,
                                        c_int64, c_float, c_void_p, c_size_t, c_void_p]),
     "saeb_refine_candidates": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p,
-                                       c_int64, c_int64, c_int, c_int, c_int64, c_float, c_void_p, c_void_p,
+                                       c_void_p, c_int64, c_int64, c_int, c_int, c_int64, c_float, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_size_t, c_void_p]),
     "saeb_dense_topk": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "saeb_decode": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p,

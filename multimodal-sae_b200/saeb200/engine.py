@@ -59,7 +59,8 @@ class PackedEncoder:
     blob: torch.Tensor  # uint8
     num_latents: int
     d_in: int
-    planes: int  # 1 / 2: bf16 planes (2 = hi+lo, parity grade); 3: fp16 pass + fp16 residual refinement (parity grade)
+    planes: int  # 1 / 2: bf16 planes (2 = hi+lo, parity grade); 3: one fp16 plane + exact refinement (parity grade)
+    W_enc: Optional[torch.Tensor] = None  # mode 3 re-evaluates candidates against the fp32 parameter itself
 
     @staticmethod
     def pack(W_enc: torch.Tensor, b_enc: torch.Tensor, b_dec: torch.Tensor, planes: int = 2) -> "PackedEncoder":
@@ -74,7 +75,7 @@ class PackedEncoder:
         with torch.cuda.device(W.device):
             check(L.saeb_pack_weights(W.data_ptr(), be.data_ptr(), bd.data_ptr(), N, d, planes, blob.data_ptr(),
                                       _stream()), "saeb_pack_weights")
-        return PackedEncoder(blob, N, d, planes)
+        return PackedEncoder(blob, N, d, planes, W if planes == 3 else None)
 
     def folded_bias(self) -> torch.Tensor:
         off = _capi.lib().saeb_packed_bias_offset(self.num_latents, self.d_in, self.planes)
@@ -127,7 +128,8 @@ def encode_topk(x: torch.Tensor, enc: PackedEncoder, k: int, *, clamp_feature: i
             nbytes = L.saeb_encode_topk_refine_workspace_bytes(T, enc.d_in, enc.num_latents, k, refine_margin)
             ws = _workspace(dev, nbytes)
             check(L.saeb_encode_topk_refine(x2.data_ptr(), _code(x2), T, x2.stride(0) if T > 1 else enc.d_in,
-                                            enc.blob.data_ptr(), enc.d_in, enc.num_latents, k, refine_margin,
+                                            enc.blob.data_ptr(), enc.W_enc.data_ptr(), enc.d_in, enc.num_latents, k,
+                                            refine_margin,
                                             clamp_feature, float(clamp_value), vals.data_ptr(), idx.data_ptr(),
                                             status.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
                   "saeb_encode_topk_refine")
