@@ -409,7 +409,7 @@ def test_full_size_properties():
     dense = sae.pre_acts(x[rows])
     dv, di = dense.topk(64)
     assert torch.equal(torch.sort(di, 1).values, srt[rows])
-    assert torch.equal(dv, v[rows])
+    torch.testing.assert_close(dv, v[rows], rtol=1e-4, atol=1e-6)   # two independent arithmetic paths
     # decode is linear in the activations and the bias is added once
     y1 = engine.decode(i[:512], v[:512], sae.W_dec.data, sae.b_dec.data)
     y2 = engine.decode(i[:512], 2 * v[:512], sae.W_dec.data, None)

@@ -214,6 +214,9 @@ EXPS = {
     "time_refine_64k_s4": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=4),
     "time_refine_64k_s6": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=6),
     "time_refine_64k_s8": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=8),
+    "seq3_refine": lambda: exp_overlap(65536, 18944, overlap=False),
+    "ov3_c18944": lambda: exp_overlap(65536, 18944),
+    "ov3_c9472": lambda: exp_overlap(65536, 9472),
     "ov2_c9472": lambda: exp_overlap(65536, 9472),
     "ov2_c18944": lambda: exp_overlap(65536, 18944),
     "ov2_c28416": lambda: exp_overlap(65536, 28416),
