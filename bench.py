@@ -243,7 +243,12 @@ def run_gpu(args):
             traffic = json.load(open(summ)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    wave_tokens = 9472
+    n_launch = (TOKENS + wave_tokens - 1) // wave_tokens
     roofline = {"bound": "tensor", "kernel": "encode_topk_kernel (tcgen05 GEMM + fused TopK)", "achieved": achieved,
+                "launches_per_step": n_launch, "tokens_per_launch": wave_tokens,
+                "algorithmic_flops_per_launch": ENC_FLOPS_PER_TOKEN * wave_tokens,
+                "avg_launch_ms": k_avg * wave_tokens / TOKENS,
                 "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
                 "traffic": traffic, "peak_source": f"{peaks['source']} bf16 sustained (cuBLAS, MEASURED_PEAKS.json)",
                 "kernel_ms": k_avg, "mma_passes": 1 if enc.planes == 3 else enc.planes,

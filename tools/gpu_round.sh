@@ -9,8 +9,10 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.jso
 if [ "$1" == "ncu" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --scan-tokens 0 > gpurun_out/bench_under_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:encode_topk_kernel -s 2 -c 1 -f -o gpurun_out/prof_encode \
+ncu --set full --clock-control none --import-source on -k regex:encode_topk_kernel -s 9 -c 1 -f -o gpurun_out/prof_encode \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --scan-tokens 0 > gpurun_out/ncu_encode.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:refine_kernel -s 2 -c 1 -f -o gpurun_out/prof_refine \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --scan-tokens 0 > gpurun_out/ncu_refine.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:decode_kernel -s 2 -c 1 -f -o gpurun_out/prof_decode \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --scan-tokens 0 > gpurun_out/ncu_decode.log 2>&1
 ls -la gpurun_out
