@@ -44,6 +44,11 @@ int saeb_set_option(const char* name, int value);
 /* With option "profile" = 1 the library brackets the fused encode kernel (main kernel only) with CUDA events on the
  * launching stream; this returns the duration in ms of the most recent one (synchronises on it), < 0 if none. */
 float saeb_profile_last_encode_ms(void);
+/* Diagnostics (option "stats" = 1 zeroes and enables device cycle counters of the fused encode kernel): host array of 8
+ * counters summed over CTA pairs = {producer waiting for a free smem stage, MMA issuer waiting for a free TMEM stage,
+ * MMA issuer waiting for TMA data, epilogue warp waiting for an accumulator, epilogue compaction time, kernel time,
+ * number of CTA pairs summed, 0}.  Synchronises. */
+int saeb_debug_stats(unsigned long long* out8);
 
 /* ---- one-time weight repack -------------------------------------------------------------------------------
  * Reference parameters: `encoder.weight [N,d]`, `encoder.bias [N]`, `b_dec [d]` fp32 (sae/sae.py:59-66, loaded by

@@ -50,6 +50,8 @@ int dense_topk_launch(const float* dense, long long T, long long ld, long long N
 int set_splits(int v);
 int set_l2_hints(int v);
 int set_dbg(int v);
+int set_stats(int v);
+int read_stats(unsigned long long* out8);
 int set_persist_a(int v);
 long long persist_bytes();
 int pack_weights_launch(const float* W_enc, const float* b_enc, const float* b_dec, long long N, long long d,
@@ -109,6 +111,7 @@ int saeb_set_option(const char* name, int value) {
   if (strcmp(name, "splits") == 0) return set_splits(value);
   if (strcmp(name, "l2_hints") == 0) return set_l2_hints(value);
   if (strcmp(name, "debug_tiles") == 0) return set_dbg(value);
+  if (strcmp(name, "stats") == 0) return set_stats(value);
   if (strcmp(name, "persist_a") == 0) return set_persist_a(value);
   if (strcmp(name, "chunking") == 0) return set_chunking(value);
   set_error("set_option: unknown option '%s'", name);
@@ -116,6 +119,7 @@ int saeb_set_option(const char* name, int value) {
 }
 
 float saeb_profile_last_encode_ms(void) { return last_encode_ms(); }
+int saeb_debug_stats(unsigned long long* out8) { return read_stats(out8); }
 
 size_t saeb_packed_bias_offset(int64_t N, int64_t d, int planes) { return planes_bytes(N, d, planes); }
 size_t saeb_packed_weights_bytes(int64_t N, int64_t d, int planes) {

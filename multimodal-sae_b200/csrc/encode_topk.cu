@@ -29,7 +29,7 @@ constexpr int BK = 64;    // K elements per pipeline stage (128 bytes of bf16 = 
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 256;
 constexpr int SMEM_BUDGET = 232448;   // 227 KB
-constexpr int SMEM_MISC = 8192;       // barriers + tmem ptr + bias staging
+constexpr int SMEM_MISC = 12288;      // barriers + tmem ptr + bias staging + compaction histograms
 
 template <int AP, int BP, int PAIR>
 struct EncCfg {
@@ -52,6 +52,7 @@ struct EncodeArgs {
   int pass_mask;      // bit (a*BP+b) set -> issue MMA for (A plane a, B plane b)
   int clamp_col;      // steering: column forced to clamp_val before TopK (-1 = none)
   float clamp_val;
+  unsigned long long* stats;   // optional diagnostics: cycle counters summed over CTAs (see saeb_debug_stats)
   int dbg;   // diagnostics only (wrong results): bit0 = every cluster loads token tile 0, bit1 = every step loads feature tile 0
   unsigned long long hint_a, hint_b;   // L2 eviction policies of the activation / weight TMA loads
   unsigned int idesc;       // tcgen05 instruction descriptor (operand formats are a run-time choice: bf16 or fp16)
@@ -65,45 +66,102 @@ struct EncodeArgs {
 };
 
 // ---------------------------------------------------------------------------------------------
-// warp-cooperative compaction of one row's candidate list: keep every entry >= the k-th largest value
+// warp-cooperative compaction of one row's candidate list
+//
+// Any threshold that keeps at least k entries is valid (the merge kernel does the exact selection), so the common path
+// takes the threshold from a 256-bin histogram of the value bits over the list's [min, max] range: one shared-memory
+// atomic per entry + an 8-bins-per-lane suffix scan instead of a 31-step bit search.  If that would keep too many
+// entries (heavy ties), the exact path selects the k-th value and keeps exactly k entries, ties by arrival order
+// (= ascending column, since appends and compactions preserve order).
 // ---------------------------------------------------------------------------------------------
 template <int SLOTS>
-__device__ __forceinline__ void compact_row(uint2* buf, int cnt_in, int k, uint32_t lane, float& thr_out,
+__device__ __forceinline__ void compact_row(uint2* buf, int cnt_in, int k, uint32_t lane, int* hist, float& thr_out,
                                             int& cnt_out) {
+  constexpr int CAP = 32 * SLOTS;
+  const uint32_t full = 0xffffffffu;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   uint32_t key[SLOTS], col[SLOTS];
+  uint32_t kmax = 0, kmin = 0xffffffffu;
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
-    int i = s * 32 + lane;
+    const int i = s * 32 + lane;
     if (i < cnt_in) {
-      uint2 e = buf[i];
+      const uint2 e = buf[i];
       key[s] = e.x;
       col[s] = e.y;
+      kmax = max(kmax, e.x);
+      kmin = min(kmin, e.x);
     } else {
       key[s] = 0;
       col[s] = 0;
     }
   }
-  // values are strictly positive floats, so their bit patterns order like unsigned integers.
-  uint32_t prefix = 0;
-  for (int bit = 30; bit >= 0; --bit) {
-    uint32_t trial = prefix | (1u << bit);
-    int c = 0;
+  kmax = __reduce_max_sync(full, kmax);
+  kmin = __reduce_min_sync(full, kmin);
+  // values are strictly positive floats, so their bit patterns order like unsigned integers
+  const uint32_t range = kmax - kmin;
+  const int shift = (range >> 8) ? (32 - __clz(range) - 8) : 0;
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) c += (key[s] >= trial) ? 1 : 0;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (c >= k) prefix = trial;
+  for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s)
+    if (key[s] != 0) atomicAdd(&hist[(key[s] - kmin) >> shift], 1);
+  __syncwarp();
+  int c8 = 0;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) c8 += hist[lane * 8 + b];
+  int suffix = c8;   // inclusive suffix sum over lanes >= this one
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_down_sync(full, suffix, o);
+    if (lane + o < 32) suffix += up;
   }
-  int base = 0;
-  const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t ok = __ballot_sync(full, suffix >= k);
+  const int lstar = 31 - __clz(ok);   // highest lane whose suffix still reaches k (lane 0 always does)
+  int acc = __shfl_sync(full, suffix, lstar) - __shfl_sync(full, c8, lstar);
+  int bin = lstar * 8;
+#pragma unroll
+  for (int b = 7; b >= 0; --b) {
+    const int h = hist[lstar * 8 + b];
+    if (acc < k) {
+      acc += h;
+      bin = lstar * 8 + b;
+    }
+  }
+  uint32_t thr_key = kmin + ((uint32_t)bin << shift);
+  int need_eq = CAP;   // ties at thr_key that may be kept (all of them on the histogram path)
+  if (acc > CAP - 64) {
+    // exact path: k-th largest key by bit search, keep exactly k
+    uint32_t prefix = 0;
+    for (int bit = 30; bit >= 0; --bit) {
+      const uint32_t trial = prefix | (1u << bit);
+      int c = 0;
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s) c += (key[s] >= trial) ? 1 : 0;
+      c = __reduce_add_sync(full, c);
+      if (c >= k) prefix = trial;
+    }
+    int c_gt = 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) c_gt += (key[s] > prefix) ? 1 : 0;
+    c_gt = __reduce_add_sync(full, c_gt);
+    thr_key = prefix;
+    need_eq = k - c_gt;
+  }
+  int base = 0, ties = 0;
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
-    bool keep = key[s] >= prefix && key[s] != 0;
-    uint32_t m = __ballot_sync(0xffffffffu, keep);
+    const bool tie = key[s] == thr_key;
+    const uint32_t mt = __ballot_sync(full, tie);
+    const bool keep = key[s] > thr_key || (tie && ties + __popc(mt & lt_mask) < need_eq);
+    const uint32_t m = __ballot_sync(full, keep);
     if (keep) buf[base + __popc(m & lt_mask)] = make_uint2(key[s], col[s]);
     base += __popc(m);
+    ties += __popc(mt);
   }
   __syncwarp();
-  thr_out = __uint_as_float(prefix);
+  thr_out = __uint_as_float(thr_key);
   cnt_out = base;
 }
 
@@ -128,6 +186,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   uint64_t* tempty_bar = tfull_bar + 2;                     // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* bias_s = reinterpret_cast<float*>(misc + 1024);    // [4 warps][BN]
+  int* hist_s = reinterpret_cast<int*>(misc + 1024 + 4 * BN * 4);   // [4 warps][256]
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
@@ -165,6 +224,8 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long w_prod = 0;
+      const long long t_begin = clock64();
       for (int u = cluster_id; u < num_units; u += num_clusters) {
         const int split = u % args.S, m_tile = u / args.S;
         const int nt0 = (int)((long long)split * args.num_n_tiles / args.S);
@@ -173,7 +234,9 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         for (int nt = nt0; nt < nt1; ++nt) {
           const int n0 = ((args.dbg & 2) ? 0 : nt) * BN + (int)cta_rank * Cfg::B_ROWS;
           for (int kb = 0; kb < args.num_k_blocks; ++kb) {
+            const long long tw0 = clock64();
             mbar_wait(&empty_bar[stage], phase ^ 1);
+            w_prod += clock64() - tw0;
             uint8_t* sa = smem + stage * Cfg::STAGE;
             uint8_t* sb = sa + AP * Cfg::A_PLANE;
             if constexpr (PAIR == 1) {
@@ -198,6 +261,11 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           }
         }
       }
+      if (args.stats != nullptr && leader) {
+        atomicAdd(args.stats + 0, (unsigned long long)w_prod);
+        atomicAdd(args.stats + 5, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(args.stats + 6, 1ull);
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
@@ -206,17 +274,22 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tile_iter = 0;
+      long long w_tempty = 0, w_full = 0;
       for (int u = cluster_id; u < num_units; u += num_clusters) {
         const int split = u % args.S;
         const int nt0 = (int)((long long)split * args.num_n_tiles / args.S);
         const int nt1 = (int)((long long)(split + 1) * args.num_n_tiles / args.S);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_iter) {
           const uint32_t acc_stage = tile_iter & 1, acc_phase = (tile_iter >> 1) & 1;
+          const long long tw0 = clock64();
           mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
+          w_tempty += clock64() - tw0;
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc_stage * BN;
           for (int kb = 0; kb < args.num_k_blocks; ++kb) {
+            const long long tw1 = clock64();
             mbar_wait(&full_bar[stage], phase);
+            w_full += clock64() - tw1;
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
             const uint32_t sb = sa + AP * Cfg::A_PLANE;
@@ -242,6 +315,10 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           }
         }
       }
+      if (args.stats != nullptr) {
+        atomicAdd(args.stats + 1, (unsigned long long)w_tempty);
+        atomicAdd(args.stats + 2, (unsigned long long)w_full);
+      }
     }
   } else if (warp >= 4) {
     // ===================== epilogue: bias + ReLU + running TopK filter =====================
@@ -249,6 +326,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     float* bias_w = bias_s + q * BN;
     const uint32_t full = 0xffffffffu;
     uint32_t tile_iter = 0;
+    long long w_tfull = 0, w_compact = 0;
     for (int u = cluster_id; u < num_units; u += num_clusters) {
       const int split = u % args.S, m_tile = u / args.S;
       const int nt0 = (int)((long long)split * args.num_n_tiles / args.S);
@@ -272,7 +350,9 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           bias_w[i * 32 + lane] = (c < args.N) ? __ldg(args.bias + c) : __int_as_float(0xff800000);
         }
         __syncwarp();
+        const long long twe = clock64();
         mbar_wait(&tfull_bar[acc_stage], acc_phase);
+        w_tfull += clock64() - twe;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc_stage * BN;
 #pragma unroll 1
@@ -327,6 +407,8 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           }
           // compaction when a list could overflow during the next chunk
           uint32_t need = __ballot_sync(full, cnt > CAP - 32);
+          const long long twc = need ? clock64() : 0;
+          const bool had = need != 0;
           while (need) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
@@ -335,15 +417,21 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             float nthr;
             int ncnt;
             __syncwarp();
-            compact_row<SLOTS>(reinterpret_cast<uint2*>((uintptr_t)p), src_cnt, args.k, lane, nthr, ncnt);
+            compact_row<SLOTS>(reinterpret_cast<uint2*>((uintptr_t)p), src_cnt, args.k, lane, hist_s + q * 256, nthr,
+                               ncnt);
             if ((int)lane == src) {
               thr = nthr;
               cnt = ncnt;
             }
           }
+          if (had) w_compact += clock64() - twc;
         }
       }
       if (do_topk && valid) args.cand_cnt[(size_t)row * args.S + split] = cnt;
+    }
+    if (args.stats != nullptr && leader && warp == 4 && lane == 0) {
+      atomicAdd(args.stats + 3, (unsigned long long)w_tfull);
+      atomicAdd(args.stats + 4, (unsigned long long)w_compact);
     }
   }
 
@@ -540,6 +628,22 @@ int set_persist_a(int v) {
   return 0;
 }
 long long persist_bytes() { return (long long)g_persist_bytes; }
+static unsigned long long* g_stats = nullptr;   // device counters [8] when option "stats" is on
+int set_stats(int v) {
+  if (v && g_stats == nullptr) {
+    if (cudaMalloc(&g_stats, 64) != cudaSuccess) return -2;
+  }
+  if (g_stats) cudaMemset(g_stats, 0, 64);
+  if (!v && g_stats) {
+    cudaFree(g_stats);
+    g_stats = nullptr;
+  }
+  return 0;
+}
+int read_stats(unsigned long long* out8) {
+  if (!g_stats) return -1;
+  return cudaMemcpy(out8, g_stats, 64, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
 static int g_dbg = 0;
 int set_dbg(int v) {
   g_dbg = v;
@@ -802,6 +906,7 @@ int encode_gemm_launch(const void* x_planes, int ap, long long T, long long ld_x
     args.clamp_col = (int)clamp_feature;
     args.clamp_val = clamp_value;
     args.dbg = g_dbg;
+    args.stats = g_stats;
     args.hint_a = (g_l2_hints & 1) ? L2_EVICT_LAST : L2_EVICT_NORMAL;
     args.hint_b = (g_l2_hints & 2) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
     args.idesc = make_idesc_f16(BM * pair, BN, operand_fmt, operand_fmt);   // 0 = fp16 operands, 1 = bf16

@@ -172,6 +172,33 @@ def exp_overlap(T, chunk, planes=3, overlap=True, l2_hints=1, splits=0, iters=3,
     return res
 
 
+def exp_stats(planes, T=9472, margin_k=64):
+    """cycle accounting of one single-wave launch of the fused encode kernel"""
+    import ctypes
+    torch, engine = _setup(2)
+    from saeb200 import _capi, synth
+    L = _capi.lib()
+    sae = synth.make_sae(4096, 131072, 64, "cuda", seed=1234)
+    sae.encoder_planes = planes
+    enc = sae.packed_encoder()
+    x = synth.make_activations(T, 4096, "cuda", seed=3)
+    for _ in range(2):
+        engine.encode_topk(x, enc, margin_k)
+    torch.cuda.synchronize()
+    _capi.check(L.saeb_set_option(b"stats", 1), "set_option")
+    _capi.check(L.saeb_set_option(b"profile", 1), "set_option")
+    engine.encode_topk(x, enc, margin_k)
+    torch.cuda.synchronize()
+    buf = (ctypes.c_ulonglong * 8)()
+    L.saeb_debug_stats(buf)
+    v = list(buf)
+    n = max(v[6], 1)
+    tot = v[5] / n
+    return dict(gemm_ms=float(L.saeb_profile_last_encode_ms()), pairs=v[6], kernel_cycles=tot,
+                producer_wait_empty=v[0] / n / tot, mma_wait_tmem=v[1] / n / tot, mma_wait_tma=v[2] / n / tot,
+                epi_wait_acc=v[3] / n / tot, epi_compaction=v[4] / n / tot)
+
+
 EXPS = {
     "gemm_p1_small": lambda: exp_gemm(1, 1, 256, 128, 512),
     "gemm_p2_small": lambda: exp_gemm(2, 1, 256, 128, 512),
@@ -214,6 +241,9 @@ EXPS = {
     "time_refine_64k_s4": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=4),
     "time_refine_64k_s6": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=6),
     "time_refine_64k_s8": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=8),
+    "stats_refine": lambda: exp_stats(3),
+    "stats_hilo": lambda: exp_stats(2),
+    "stats_bf16x1": lambda: exp_stats(1),
     "seq3_refine": lambda: exp_overlap(65536, 18944, overlap=False),
     "ov3_c18944": lambda: exp_overlap(65536, 18944),
     "ov3_c9472": lambda: exp_overlap(65536, 9472),
