@@ -100,7 +100,8 @@ int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x,
  *                           (`prep`, saeb_prep_bytes(T, d) bytes);
  *   saeb_encode_candidates  rows [t0, t0+Tc): single-pass GEMM with fused candidate selection (tensor bound);
  *   saeb_refine_candidates  same rows: candidate merge + exact fp32 re-evaluation + dense fallback (HBM bound); `x`
- *                           points at row t0 of the original activations.
+ *                           points at row t0 of the original activations; ext_lower = NULL, already_merged = 0 unless
+ *                           feature sharded (below).
  * Both row-range calls share a scratch buffer of saeb_candidates_workspace_bytes(Tc, ...) bytes. */
 size_t saeb_prep_bytes(int64_t T, int64_t d);
 int saeb_prep_activations(const void* x, int x_dtype, int64_t T, int64_t ld_x, int64_t d, void* prep, void* stream);
@@ -110,8 +111,18 @@ int saeb_encode_candidates(const void* prep, int64_t T_total, int64_t t0, int64_
                            size_t workspace_bytes, void* stream);
 int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total, int64_t t0,
                            int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N, int k, int margin,
-                           int64_t clamp_feature, float clamp_value, float* out_vals, int64_t* out_idx,
-                           int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream);
+                           int64_t clamp_feature, float clamp_value, const float* ext_lower, int already_merged,
+                           float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
+/* Feature-sharded use (every GPU holds N/R features, sees all tokens): after saeb_encode_candidates,
+ * saeb_candidate_bounds merges this shard's candidates and writes, per token, its k largest LOWER bounds
+ * a_j - eps_j (descending, lb_out [Tc,k]).  All-gather them, take the per-token k-th largest (saeb_kth_of_gathered):
+ * that is a lower bound of the token's GLOBAL k-th activation; pass it as `ext_lower` (with already_merged = 1) and
+ * the shard only re-evaluates candidates that can still be in the global TopK (about k/R + a few per token instead of
+ * k + 25). */
+int saeb_candidate_bounds(const void* prep, int64_t T_total, int64_t t0, int64_t Tc, const void* packed, int x_dtype,
+                          int64_t d, int64_t N, int k, int margin, int64_t clamp_feature, float* lb_out,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* TopK of dense non-negative rows, (value desc, index asc): Sae.select_topk (sae/sae.py:179-181) for callers that hold
  * a dense [T, ld] latent tensor. */

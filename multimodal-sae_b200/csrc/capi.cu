@@ -44,7 +44,10 @@ int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const
                   const float* bias, const float* wnorm, const float* trailer, const float* xnorm, float c_eps,
                   const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                   float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
-                  float* dense_scratch, cudaStream_t stream);
+                  float* dense_scratch, const float* ext_lower, cudaStream_t stream);
+int candidate_bounds_launch(const float* cand_vals, const long long* cand_idx, long long T, int K2, int k,
+                            const float* wnorm, const float* xnorm, float c_eps, long long clamp_feature,
+                            float* lb_out, cudaStream_t stream);
 int dense_topk_launch(const float* dense, long long T, long long ld, long long N, int k, float* out_vals,
                       long long* out_idx, cudaStream_t stream);
 int set_splits(int v);
@@ -291,10 +294,47 @@ int saeb_encode_candidates(const void* prep, int64_t T_total, int64_t t0, int64_
 
 // phase B: candidate merge + exact fp32 re-evaluation (+ dense fallback) for the same rows (HBM bound).
 // x points at row t0 of the ORIGINAL activations.
+static inline float refine_c_eps(int x_dtype) {
+  // fp16 rounding of W (2^-11), of x when it is fp32 (2^-11), and 2^-12 of slack for the fp32 accumulation
+  return ldexpf(1.0f, -11) + (x_dtype == DT_F32 ? ldexpf(1.0f, -11) : 0.f) + ldexpf(1.0f, -12);
+}
+
+// feature-sharded scan, step 1: merge this shard's candidates and emit, per token, the k largest lower bounds
+// (a_j - eps_j, descending).  Leaves the merged candidates in the workspace for saeb_refine_candidates(...,
+// already_merged = 1).
+int saeb_candidate_bounds(const void* prep, int64_t T_total, int64_t t0, int64_t Tc, const void* packed, int x_dtype,
+                          int64_t d, int64_t N, int k, int margin, int64_t clamp_feature, float* lb_out,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  g_err[0] = 0;
+  SAEB_REQUIRE(prep && packed && lb_out && workspace, "candidate_bounds: null pointer");
+  SAEB_REQUIRE(t0 >= 0 && Tc >= 0 && t0 + Tc <= T_total, "candidate_bounds: bad row range");
+  if (Tc == 0) return 0;
+  const int K2raw = refine_k2(k, margin);
+  const int K2 = K2raw < N ? K2raw : (int)N;
+  const RefineWs w = refine_ws(Tc, d, N, k, margin);
+  SAEB_REQUIRE(workspace_bytes >= w.total, "candidate_bounds: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const PrepLayout p = prep_layout(T_total, d);
+  const uint8_t* pb = reinterpret_cast<const uint8_t*>(prep);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
+  const float* wnorm = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + bias_bytes(N));
+  float* mvals = reinterpret_cast<float*>(ws + w.mvals);
+  long long* midx = reinterpret_cast<long long*>(ws + w.midx);
+  int rc = encode_merge_launch(Tc, N, K2, mvals, midx, ws + w.enc, w.total - w.enc, st);
+  if (rc) return rc;
+  rc = candidate_bounds_launch(mvals, midx, Tc, K2, k < K2 ? k : K2, wnorm,
+                               reinterpret_cast<const float*>(pb + p.xnorm) + t0, refine_c_eps(x_dtype), clamp_feature,
+                               lb_out, st);
+  if (rc == 0) g_launches += 2;
+  return rc;
+}
+
 int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total, int64_t t0,
                            int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N, int k, int margin,
-                           int64_t clamp_feature, float clamp_value, float* out_vals, int64_t* out_idx,
-                           int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream) {
+                           int64_t clamp_feature, float clamp_value, const float* ext_lower, int already_merged,
+                           float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
   g_err[0] = 0;
   SAEB_REQUIRE(x && prep && packed && W_enc && out_vals && out_idx && workspace, "refine_candidates: null pointer");
   SAEB_REQUIRE(t0 >= 0 && Tc >= 0 && t0 + Tc <= T_total, "refine_candidates: bad row range");
@@ -315,14 +355,15 @@ int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void*
   float* mvals = reinterpret_cast<float*>(ws + w.mvals);
   long long* midx = reinterpret_cast<long long*>(ws + w.midx);
   SAEB_CHECK_CUDA(cudaMemsetAsync(status, 0, 256, st));
-  int rc = encode_merge_launch(Tc, N, K2, mvals, midx, ws + w.enc, w.total - w.enc, st);
-  if (rc) return rc;
-  // error-bound constant: fp16 rounding of W (2^-11), of x when it is fp32 (2^-11), and 2^-12 for the fp32 accumulation
-  const float c_eps = ldexpf(1.0f, -11) + (x_dtype == DT_F32 ? ldexpf(1.0f, -11) : 0.f) + ldexpf(1.0f, -12);
+  int rc = 0;
+  if (!already_merged) {
+    rc = encode_merge_launch(Tc, N, K2, mvals, midx, ws + w.enc, w.total - w.enc, st);
+    if (rc) return rc;
+  }
   rc = refine_launch(x, x_dtype, Tc, ld_x, W_enc, d, N, bias, wnorm, trailer,
-                     reinterpret_cast<const float*>(pb + p.xnorm) + t0, c_eps, mvals, midx, K2, k < K2 ? k : K2,
-                     clamp_feature, clamp_value, out_vals, reinterpret_cast<long long*>(out_idx), status,
-                     reinterpret_cast<int*>(ws + w.flag_rows), reinterpret_cast<float*>(ws + w.dense), st);
+                     reinterpret_cast<const float*>(pb + p.xnorm) + t0, refine_c_eps(x_dtype), mvals, midx, K2,
+                     k < K2 ? k : K2, clamp_feature, clamp_value, out_vals, reinterpret_cast<long long*>(out_idx), status,
+                     reinterpret_cast<int*>(ws + w.flag_rows), reinterpret_cast<float*>(ws + w.dense), ext_lower, st);
   if (rc) return rc;
   if (status_out != nullptr)
     SAEB_CHECK_CUDA(cudaMemcpyAsync(status_out, status, sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -351,7 +392,7 @@ int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x,
                               workspace_bytes - prep_bytes, stream);
   if (rc) return rc;
   return saeb_refine_candidates(x, x_dtype, ld_x, ws, T, 0, T, packed, W_enc, d, N, k, margin, clamp_feature,
-                                clamp_value, out_vals, out_idx, status_out, ws + prep_bytes,
+                                clamp_value, nullptr, 0, out_vals, out_idx, status_out, ws + prep_bytes,
                                 workspace_bytes - prep_bytes, stream);
 }
 

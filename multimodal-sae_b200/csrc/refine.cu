@@ -24,7 +24,7 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict_
               const float* __restrict__ xnorm, float c_eps, const float* __restrict__ cand_vals,
               const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
               float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
-              int* __restrict__ flag_rows) {
+              int* __restrict__ flag_rows, const float* __restrict__ ext_lower) {
   extern __shared__ float rsm[];
   float* xs = rsm;                                   // [d4] activations of this row as fp32
   const int d4 = (int)((d + 3) & ~3ll);
@@ -72,7 +72,9 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict_
   if (my_valid) atomicAdd(&s_cnt[0], my_valid);
   __syncthreads();
   const int nv = s_cnt[0];
-  const float L = (nv >= k) ? s_L : 0.f;
+  float L = (nv >= k) ? s_L : 0.f;
+  // feature-sharded use: a lower bound of the GLOBAL k-th value (k-th largest lower bound over all shards)
+  if (ext_lower != nullptr) L = fmaxf(L, ext_lower[t]);
   // list possibly too short?  (only when the list is full: otherwise every positive latent is already in it)
   if (tid == 0 && nv == K2) {
     const float a_last = a[K2 - 1];
@@ -164,6 +166,44 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict_
       filled += __popc(m);
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-row lower bounds of the k best candidates (feature-sharded scan): lb_out[t][0..k) = the k largest values of
+// a_j - eps_j, descending, floored at 0.  All-gathered across shards, their k-th largest is a lower bound of the
+// token's global k-th activation.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+candidate_bounds_kernel(const float* __restrict__ cand_vals, const long long* __restrict__ cand_idx, int K2, int k,
+                        const float* __restrict__ wnorm, const float* __restrict__ xnorm, float c_eps,
+                        long long clamp_feature, float* __restrict__ lb_out) {
+  extern __shared__ float bsm[];   // [K2]
+  const long long t = blockIdx.x;
+  const float xn = xnorm[t];
+  for (int j = threadIdx.x; j < K2; j += blockDim.x) {
+    const float av = cand_vals[t * K2 + j];
+    const long long fj = cand_idx[t * K2 + j];
+    const float eps = (fj == clamp_feature) ? 0.f : c_eps * xn * wnorm[fj];
+    bsm[j] = (av > 0.f) ? fmaxf(av - eps, 0.f) : 0.f;
+  }
+  for (int j = threadIdx.x; j < k; j += blockDim.x) lb_out[t * k + j] = 0.f;
+  __syncthreads();
+  for (int j = threadIdx.x; j < K2; j += blockDim.x) {
+    const float l = bsm[j];
+    int rank = 0;
+    for (int i = 0; i < K2; ++i) rank += (bsm[i] > l || (bsm[i] == l && i < j)) ? 1 : 0;
+    if (rank < k) lb_out[t * k + rank] = l;
+  }
+}
+
+int candidate_bounds_launch(const float* cand_vals, const long long* cand_idx, long long T, int K2, int k,
+                            const float* wnorm, const float* xnorm, float c_eps, long long clamp_feature,
+                            float* lb_out, cudaStream_t stream) {
+  if (T == 0) return 0;
+  candidate_bounds_kernel<<<(unsigned)T, 128, (size_t)K2 * sizeof(float), stream>>>(cand_vals, cand_idx, K2, k, wnorm,
+                                                                                    xnorm, c_eps, clamp_feature, lb_out);
+  SAEB_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -298,7 +338,7 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
                            const float* bias, const float* wnorm, const float* trailer, const float* xnorm, float c_eps,
                            const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                            float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
-                           float* dense_scratch, cudaStream_t stream) {
+                           float* dense_scratch, const float* ext_lower, cudaStream_t stream) {
   const int d4 = (int)((d + 3) & ~3ll);
   const size_t smem = (size_t)(d4 + 5 * K2) * sizeof(float);
   SAEB_REQUIRE(smem <= 200 * 1024, "refine: d=%lld too large for the shared-memory row buffer", d);
@@ -306,7 +346,7 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)T, RF_THREADS, smem, stream>>>(x, ld_x, W, d, N, bias, wnorm, trailer, xnorm, c_eps, cand_vals,
                                                  cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx,
-                                                 status, flag_rows);
+                                                 status, flag_rows, ext_lower);
   SAEB_CHECK_CUDA(cudaGetLastError());
   // exact dense fallback for the (normally zero) flagged rows; the grids exit at once when nothing is flagged
   auto ek = exact_rows_kernel<XT>;
@@ -328,11 +368,11 @@ int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const
                   const float* bias, const float* wnorm, const float* trailer, const float* xnorm, float c_eps,
                   const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                   float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
-                  float* dense_scratch, cudaStream_t stream) {
+                  float* dense_scratch, const float* ext_lower, cudaStream_t stream) {
 #define SAEB_RF(XT)                                                                                                  \
   return refine_launch_t<XT>(reinterpret_cast<const XT*>(x), T, ld_x, W, d, N, bias, wnorm, trailer, xnorm, c_eps,   \
                              cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx, status,      \
-                             flag_rows, dense_scratch, stream)
+                             flag_rows, dense_scratch, ext_lower, stream)
   if (x_dtype == DT_F32) SAEB_RF(float);
   if (x_dtype == DT_BF16) SAEB_RF(__nv_bfloat16);
   if (x_dtype == DT_F16) SAEB_RF(__half);

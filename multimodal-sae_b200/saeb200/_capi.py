@@ -44,8 +44,10 @@ SIGNATURES = {
     "saeb_encode_candidates": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int,
                                        c_int64, c_float, c_void_p, c_size_t, c_void_p]),
     "saeb_refine_candidates": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p,
-                                       c_void_p, c_int64, c_int64, c_int, c_int, c_int64, c_float, c_void_p, c_void_p,
-                                       c_void_p, c_void_p, c_size_t, c_void_p]),
+                                       c_void_p, c_int64, c_int64, c_int, c_int, c_int64, c_float, c_void_p, c_int,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "saeb_candidate_bounds": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int64, c_int64, c_int,
+                                      c_int, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "saeb_dense_topk": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "saeb_decode": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p,
                             c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),

@@ -35,20 +35,77 @@ def token_slice(num_tokens: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 class EngineOps:
-    """CUDA implementation of the per-rank steps (thin calls into saeb200.engine)."""
+    """CUDA implementation of the per-rank steps of the feature-sharded scan (thin calls into the C ABI).
 
-    def __init__(self, W_enc_shard, b_enc_shard, b_dec, feat_lo, feat_hi, n_top, ctx_len, device, planes=2,
+    Interface used by `sharded_scan` (the CPU gloo test injects an oracle-backed object with the same methods):
+      local_bounds(x, k)  -> [Tc, k] per-token lower bounds of this shard's k best latents (descending)
+      local_topk(ext_L)   -> (vals [Tc, k], global ids [Tc, k]) exact local TopK of the chunk given to local_bounds;
+                             `ext_L` [Tc] (optional) = lower bound of each token's GLOBAL k-th value, lets the shard skip
+                             the exact re-evaluation of latents that cannot be in the global TopK
+      kth_of_gathered, scan_update, scan_finalize
+    """
+
+    def __init__(self, W_enc_shard, b_enc_shard, b_dec, feat_lo, feat_hi, n_top, ctx_len, device, planes=3,
                  bucket_cap=256):
-        from . import engine
+        from . import _capi, engine
 
-        self.engine = engine
+        self.engine, self._capi = engine, _capi
         self.enc = engine.PackedEncoder.pack(W_enc_shard, b_enc_shard, b_dec, planes)
         self.feat_lo, self.feat_hi = feat_lo, feat_hi
         self.scan = engine.TopActivationScan(feat_lo, feat_hi, n_top, ctx_len, device, bucket_cap=bucket_cap)
+        self._x = self._k = self._prep = self._ws = None
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
 
-    def encode_topk(self, x, k):
-        vals, idx, _ = self.engine.encode_topk(x, self.enc, k)
-        return vals, idx + self.feat_lo  # global feature ids
+    # ---- mode 3: GEMM -> bounds -> (exchange) -> refinement restricted by the global lower bound
+    def local_bounds(self, x, k):
+        eng, L = self.engine, self._capi.lib()
+        enc = self.enc
+        x2 = eng._as_2d(x, enc.d_in)
+        self._x, self._k = x2, k
+        T = x2.shape[0]
+        if enc.planes != 3:
+            vals, idx, _ = eng.encode_topk(x2, enc, k)
+            self._cached = (vals, idx + self.feat_lo)
+            return vals
+        dev = x2.device
+        with torch.cuda.device(dev):
+            need = L.saeb_prep_bytes(T, enc.d_in)
+            if self._prep is None or self._prep.numel() < need:
+                self._prep = torch.empty(need, dtype=torch.uint8, device=dev)
+            need = L.saeb_candidates_workspace_bytes(T, enc.d_in, enc.num_latents, k, 0)
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            st = torch.cuda.current_stream().cuda_stream
+            code = eng._code(x2)
+            ldx = x2.stride(0) if T > 1 else enc.d_in
+            self._capi.check(L.saeb_prep_activations(x2.data_ptr(), code, T, ldx, enc.d_in, self._prep.data_ptr(), st),
+                             "saeb_prep_activations")
+            self._capi.check(L.saeb_encode_candidates(self._prep.data_ptr(), T, 0, T, enc.blob.data_ptr(), enc.d_in,
+                                                      enc.num_latents, k, 0, -1, 0.0, self._ws.data_ptr(),
+                                                      self._ws.numel(), st), "saeb_encode_candidates")
+            lb = torch.empty((T, k), dtype=torch.float32, device=dev)
+            self._capi.check(L.saeb_candidate_bounds(self._prep.data_ptr(), T, 0, T, enc.blob.data_ptr(), code, enc.d_in,
+                                                     enc.num_latents, k, 0, -1, lb.data_ptr(), self._ws.data_ptr(),
+                                                     self._ws.numel(), st), "saeb_candidate_bounds")
+        return lb
+
+    def local_topk(self, ext_L=None):
+        eng, L = self.engine, self._capi.lib()
+        enc, x2, k = self.enc, self._x, self._k
+        if enc.planes != 3:
+            return self._cached
+        T = x2.shape[0]
+        dev = x2.device
+        vals = torch.empty((T, k), dtype=torch.float32, device=dev)
+        idx = torch.empty((T, k), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream().cuda_stream
+            self._capi.check(L.saeb_refine_candidates(
+                x2.data_ptr(), eng._code(x2), x2.stride(0) if T > 1 else enc.d_in, self._prep.data_ptr(), T, 0, T,
+                enc.blob.data_ptr(), enc.W_enc.data_ptr(), enc.d_in, enc.num_latents, k, 0, -1, 0.0,
+                None if ext_L is None else ext_L.data_ptr(), 1, vals.data_ptr(), idx.data_ptr(), self.status.data_ptr(),
+                self._ws.data_ptr(), self._ws.numel(), st), "saeb_refine_candidates")
+        return vals, idx + self.feat_lo
 
     def kth_of_gathered(self, gathered):
         return self.engine.kth_of_gathered(gathered)
@@ -78,19 +135,26 @@ def _all_gather_cat(t: torch.Tensor, group, sizes=None) -> torch.Tensor:
 
 def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_latents: int, *, exact: bool = True,
                  group=None) -> ScanResult:
-    """Feature-sharded scan.  `chunks` yields the SAME token chunks ([Tc, d], Tc a multiple of ctx_len) on every rank."""
+    """Feature-sharded scan.  `chunks` yields the SAME token chunks ([Tc, d], Tc a multiple of ctx_len) on every rank.
+
+    exact=True, per chunk: (1) every shard computes lower bounds of its k best latents per token and all-gathers
+    them -> per-token lower bound of the global k-th value; (2) the shard evaluates exactly only the latents that can
+    still reach it and all-gathers its exact local top-k values -> the per-token global k-th value, which filters what
+    enters the per-feature lists (the cache keeps a latent only if it is in the token's global TopK,
+    features/cache.py:210-218).  Both exchanges are [Tc, k] fp32 per rank (256 B/token/rank at k = 64)."""
     distributed = dist.is_available() and dist.is_initialized()
     world = dist.get_world_size(group) if distributed else 1
     k_local = min(k, ops.feat_hi - ops.feat_lo)
     window_base = 0
     for x in chunks:
-        vals, idx = ops.encode_topk(x, k_local)
-        vals2 = vals.reshape(-1, k_local)
-        tok_thr = None
+        lb = ops.local_bounds(x, k_local)
+        ext_L = tok_thr = None
         if exact and world > 1:
-            gathered = torch.stack(_all_gather_cat(vals2, group), 0)  # [R, Tc, k_local]
-            # per-token global k-th value among the R*k_local shard-local leaders
-            tok_thr = ops.kth_of_gathered(gathered) if k_local == k else _kth_host(gathered, k)
+            ext_L = _kth(ops, torch.stack(_all_gather_cat(lb, group), 0), k, k_local)
+        vals, idx = ops.local_topk(ext_L)
+        vals2 = vals.reshape(-1, k_local)
+        if exact and world > 1:
+            tok_thr = _kth(ops, torch.stack(_all_gather_cat(vals2, group), 0), k, k_local)
         ops.scan_update(vals2, idx.reshape(-1, k_local), window_base, tok_thr)
         window_base += vals2.shape[0] // ctx_len
     top_vals, top_win = ops.scan_finalize()
@@ -102,10 +166,13 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
     return ScanResult(top_vals, top_win)
 
 
-def _kth_host(gathered: torch.Tensor, k: int) -> torch.Tensor:
+def _kth(ops, gathered: torch.Tensor, k: int, k_local: int) -> torch.Tensor:
+    """per-token k-th largest of the R * k_local gathered values"""
+    if k_local == k:
+        return ops.kth_of_gathered(gathered)
     R, T, kl = gathered.shape
     flat = gathered.permute(1, 0, 2).reshape(T, R * kl)
-    return flat.topk(k, dim=-1).values[:, -1].contiguous()
+    return flat.topk(min(k, R * kl), dim=-1).values[:, -1].contiguous()
 
 
 def token_parallel_forward(sae, x_local: torch.Tensor):

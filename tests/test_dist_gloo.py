@@ -22,10 +22,16 @@ class OracleOps:
         self.sub = O.SaeParams(p.W_enc[lo:hi], p.b_enc[lo:hi], p.W_dec[lo:hi], p.b_dec, p.k)
         self.acts, self.idx, self.thr = [], [], []
 
-    def encode_topk(self, x, k):
+    def local_bounds(self, x, k):
         pa = O.pre_acts(self.sub, x.float())
-        v, i = pa.topk(k, sorted=True)
-        return v, i + self.feat_lo
+        self._v, self._i = pa.topk(k, sorted=True)
+        return self._v * (1 - 1e-3)   # a lower bound, like the engine's a_j - eps_j
+
+    def local_topk(self, ext_L=None):
+        v = self._v
+        if ext_L is not None:   # latents that cannot reach the global k-th value are not evaluated (reported as 0)
+            v = torch.where(v >= ext_L[:, None], v, torch.zeros_like(v))
+        return v, self._i + self.feat_lo
 
     def kth_of_gathered(self, gathered):
         R, T, k = gathered.shape

@@ -380,6 +380,38 @@ def test_scan_matches_oracle():
     np.testing.assert_array_equal(torch.cat([b for _, b in parts]).cpu().numpy(), ref_w)
 
 
+def test_feature_sharded_scan_logical_shards():
+    """The multi-GPU choreography of saeb200.dist (bounds exchange -> restricted exact refinement -> value exchange ->
+    per-feature lists) with 4 logical shards on one device must reproduce the unsharded result exactly."""
+    from saeb200 import dist as sdist, engine
+
+    N, d, k, ctx, n_top, R = 2048, 256, 16, 16, 4, 4
+    p = O.init_params(d, N, k, seed=51)
+    x = torch.randn(ctx * 40, d, generator=torch.Generator().manual_seed(52)).to(torch.bfloat16).to(DEV)
+    shards = [sdist.shard_range(N, R, r) for r in range(R)]
+    ops = [sdist.EngineOps(p.W_enc[lo:hi].to(DEV), p.b_enc[lo:hi].to(DEV), p.b_dec.to(DEV), lo, hi, n_top, ctx, DEV)
+           for lo, hi in shards]
+    n_eval = 0
+    for c0 in range(0, x.shape[0], ctx * 16):
+        xc = x[c0:c0 + ctx * 16]
+        lbs = torch.stack([o.local_bounds(xc, k) for o in ops], 0)
+        ext_L = engine.kth_of_gathered(lbs)
+        outs = [o.local_topk(ext_L) for o in ops]
+        n_eval += sum(int((v > 0).sum()) for v, _ in outs)
+        tok_thr = engine.kth_of_gathered(torch.stack([v for v, _ in outs], 0))
+        for o, (v, i) in zip(ops, outs):
+            o.scan_update(v, i, c0 // ctx, tok_thr)
+    parts = [o.scan_finalize() for o in ops]
+    vals = torch.cat([a for a, _ in parts]).cpu().numpy()
+    wins = torch.cat([b for _, b in parts]).cpu().numpy()
+    enc = O.encode(p, x.float().cpu())
+    ref_s, ref_w = O.scan_top_windows(enc.top_acts, enc.top_indices, N, ctx, n_top)
+    np.testing.assert_allclose(vals, ref_s, rtol=1e-5, atol=1e-6)
+    np.testing.assert_array_equal(wins, ref_w)
+    # the bounds exchange is what makes sharding pay: far fewer exact evaluations than R * k per token
+    assert n_eval < 0.6 * R * k * x.shape[0]
+
+
 def test_kth_of_gathered():
     from saeb200 import engine
 

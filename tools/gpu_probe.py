@@ -199,6 +199,28 @@ def exp_stats(planes, T=9472, margin_k=64):
                 epi_wait_acc=v[3] / n / tot, epi_compaction=v[4] / n / tot)
 
 
+def exp_scan(T=131072, world=1, rank=0, planes=3):
+    """feature-sharded scan of one (simulated) rank: features [rank*N/world, (rank+1)*N/world), no collectives"""
+    torch, engine = _setup(2)
+    from saeb200 import dist as sdist, synth
+    sae = synth.make_sae(4096, 131072, 64, "cuda", seed=1234)
+    lo, hi = sdist.shard_range(131072, world, rank)
+    ops = sdist.EngineOps(sae.encoder.weight.data[lo:hi], sae.encoder.bias.data[lo:hi], sae.b_dec.data, lo, hi, 20, 64,
+                          "cuda", planes=planes)
+    x = synth.make_activations(T, 4096, "cuda", seed=5)
+    chunk = 18944
+
+    def run():
+        ops.scan = engine.TopActivationScan(lo, hi, 20, 64, "cuda")
+        sdist.sharded_scan((x[t:t + chunk] for t in range(0, T, chunk)), ops, 64, 64, 131072)
+    run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); run(); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return dict(ms=ms, tokens_per_s=T / (ms * 1e-3), world=world)
+
+
 EXPS = {
     "gemm_p1_small": lambda: exp_gemm(1, 1, 256, 128, 512),
     "gemm_p2_small": lambda: exp_gemm(2, 1, 256, 128, 512),
@@ -241,6 +263,8 @@ EXPS = {
     "time_refine_64k_s4": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=4),
     "time_refine_64k_s6": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=6),
     "time_refine_64k_s8": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=8),
+    "scan_w1": lambda: exp_scan(world=1),
+    "scan_w8": lambda: exp_scan(world=8),
     "stats_refine": lambda: exp_stats(3),
     "stats_hilo": lambda: exp_stats(2),
     "stats_bf16x1": lambda: exp_stats(1),
