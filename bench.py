@@ -279,7 +279,7 @@ def run_gpu(args):
     # ---- feature-sharded top-activation scan (bounded token count; one all-gather of top lists at the end)
     scan = None
     if args.scan_tokens > 0:
-        ctx_len, n_top, chunk = 64, 20, 16384
+        ctx_len, n_top, chunk = 64, 20, 18944
         lo, hi = sdist.shard_range(WIDTH, world, rank)
         ops = sdist.EngineOps(sae.encoder.weight.data[lo:hi], sae.encoder.bias.data[lo:hi], sae.b_dec.data, lo, hi,
                               n_top, ctx_len, dev, planes=args.planes)
@@ -293,13 +293,15 @@ def run_gpu(args):
         ops.scan = engine.TopActivationScan(lo, hi, n_top, ctx_len, dev)
         barrier()
         e0.record()
-        res = sdist.sharded_scan(chunks(), ops, K, ctx_len, WIDTH)
+        phases = {}
+        res = sdist.sharded_scan(chunks(), ops, K, ctx_len, WIDTH, phase_times=phases if args.scan_phases else None)
         e1.record()
         barrier()
         sms = max_over_ranks(e0.elapsed_time(e1))
         scan = {"tokens": args.scan_tokens, "features": WIDTH, "n_top": n_top, "ctx_len": ctx_len, "ms": sms,
                 "tokens_per_s": args.scan_tokens / (sms * 1e-3), "sharding": f"features/{world}", "exact_topk_mask": True,
-                "filled_features": int((res.top_win[:, 0] >= 0).sum().item())}
+                "filled_features": int((res.top_win[:, 0] >= 0).sum().item()),
+                "phase_ms_rank0": {k_: round(v_, 2) for k_, v_ in phases.items()} or None}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -334,6 +336,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scan-tokens", type=int, default=262144)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scan-phases", action="store_true", help="per-phase CUDA-event timing of the scan (diagnostic)")
     ap.add_argument("--no-overlap", action="store_true", help="run the phases of a step back to back on one stream")
     ap.add_argument("--chunk", type=int, default=18944, help="tokens per pipeline chunk (multiple of 9472 = one wave)")
     ap.add_argument("--planes", type=int, default=3, choices=[1, 2, 3],

@@ -133,8 +133,30 @@ def _all_gather_cat(t: torch.Tensor, group, sizes=None) -> torch.Tensor:
     return out
 
 
+class _PhaseTimer:
+    """optional CUDA-event phase timing of sharded_scan (diagnostics; synchronises at the end only)"""
+
+    def __init__(self, enabled: bool):
+        self.enabled, self.marks = enabled, []
+
+    def mark(self, name: str):
+        if self.enabled:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((name, ev))
+
+    def totals(self):
+        out = {}
+        if not self.enabled:
+            return out
+        torch.cuda.synchronize()
+        for (n0, e0), (n1, e1) in zip(self.marks, self.marks[1:]):
+            out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        return out
+
+
 def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_latents: int, *, exact: bool = True,
-                 group=None) -> ScanResult:
+                 group=None, phase_times: Optional[dict] = None) -> ScanResult:
     """Feature-sharded scan.  `chunks` yields the SAME token chunks ([Tc, d], Tc a multiple of ctx_len) on every rank.
 
     exact=True, per chunk: (1) every shard computes lower bounds of its k best latents per token and all-gathers
@@ -146,24 +168,45 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
     world = dist.get_world_size(group) if distributed else 1
     k_local = min(k, ops.feat_hi - ops.feat_lo)
     window_base = 0
+    tm = _PhaseTimer(phase_times is not None and torch.cuda.is_available())
+    tm.mark("start")
     for x in chunks:
         lb = ops.local_bounds(x, k_local)
+        tm.mark("gemm+bounds")
         ext_L = tok_thr = None
         if exact and world > 1:
-            ext_L = _kth(ops, torch.stack(_all_gather_cat(lb, group), 0), k, k_local)
+            ext_L = _kth(ops, _gather_stack(lb, group), k, k_local)
+            tm.mark("exchange1")
         vals, idx = ops.local_topk(ext_L)
+        tm.mark("refine")
         vals2 = vals.reshape(-1, k_local)
         if exact and world > 1:
-            tok_thr = _kth(ops, torch.stack(_all_gather_cat(vals2, group), 0), k, k_local)
+            tok_thr = _kth(ops, _gather_stack(vals2, group), k, k_local)
+            tm.mark("exchange2")
         ops.scan_update(vals2, idx.reshape(-1, k_local), window_base, tok_thr)
+        tm.mark("scan_update")
         window_base += vals2.shape[0] // ctx_len
     top_vals, top_win = ops.scan_finalize()
+    tm.mark("scan_finalize")
+    if phase_times is not None:
+        phase_times.update(tm.totals())
     if world > 1:
         sizes = [shard_range(num_latents, world, r) for r in range(world)]
         sizes = [hi - lo for lo, hi in sizes]
         top_vals = torch.cat(_all_gather_cat(top_vals, group, sizes), 0)   # the single end-of-job all-gather
         top_win = torch.cat(_all_gather_cat(top_win, group, sizes), 0)
     return ScanResult(top_vals, top_win)
+
+
+def _gather_stack(t: torch.Tensor, group) -> torch.Tensor:
+    """all-gather equal-shaped [T, k] tensors into one [R, T, k] tensor (no extra copy)"""
+    world = dist.get_world_size(group)
+    out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    if hasattr(dist, "all_gather_into_tensor") and t.is_cuda:
+        dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    else:
+        dist.all_gather(list(out.unbind(0)), t.contiguous(), group=group)
+    return out
 
 
 def _kth(ops, gathered: torch.Tensor, k: int, k_local: int) -> torch.Tensor:
