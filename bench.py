@@ -279,7 +279,7 @@ def run_gpu(args):
     # ---- feature-sharded top-activation scan (bounded token count; one all-gather of top lists at the end)
     scan = None
     if args.scan_tokens > 0:
-        ctx_len, n_top, chunk = 64, 20, 18944
+        ctx_len, n_top, chunk = 64, 20, 37888  # four single-wave launches per exchange round
         lo, hi = sdist.shard_range(WIDTH, world, rank)
         ops = sdist.EngineOps(sae.encoder.weight.data[lo:hi], sae.encoder.bias.data[lo:hi], sae.b_dec.data, lo, hi,
                               n_top, ctx_len, dev, planes=args.planes)

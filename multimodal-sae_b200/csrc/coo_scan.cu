@@ -269,6 +269,10 @@ __global__ void scan_merge_kernel(uint2* __restrict__ bucket, int* __restrict__ 
   if (cnt == 0) return;
   if (cnt > bucket_cap) cnt = bucket_cap;
   uint2* e = ssm + (size_t)warp * sort_n;
+  // sort only as many slots as this feature needs (most features receive a handful of new entries per flush)
+  int need = 2;
+  while (need < n_top + cnt) need <<= 1;
+  if (need < sort_n) sort_n = need;
   for (int i = lane; i < sort_n; i += 32) {
     uint2 ent = make_uint2(0u, 0xffffffffu);
     if (i < n_top) {

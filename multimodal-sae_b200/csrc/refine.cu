@@ -36,12 +36,12 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict_
   __shared__ float s_L;
   __shared__ int s_cnt[2];
   const long long t = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
 
-  for (int i = tid; i < d4; i += RF_THREADS) xs[i] = (i < d) ? (float)x[t * ld_x + i] : 0.f;
+  for (int i = tid; i < d4; i += nthr) xs[i] = (i < d) ? (float)x[t * ld_x + i] : 0.f;
   const float xn = xnorm[t];
   const float wmax = trailer[1];
-  for (int j = tid; j < K2; j += RF_THREADS) {
+  for (int j = tid; j < K2; j += nthr) {
     const float av = cand_vals[t * K2 + j];
     const int fj = (int)cand_idx[t * K2 + j];
     const bool valid = av > 0.f;
@@ -60,7 +60,7 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict_
   __syncthreads();
   // L = k-th largest lower bound (0 if fewer than k positive candidates exist)
   int my_valid = 0;
-  for (int j = tid; j < K2; j += RF_THREADS) {
+  for (int j = tid; j < K2; j += nthr) {
     if (a[j] > 0.f) {
       ++my_valid;
       int rank = 0;
@@ -85,7 +85,7 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict_
   }
   // exact re-evaluation of every candidate that can still be in the TopK
   const bool vec = (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
-  for (int j = warp; j < K2; j += RF_THREADS / 32) {
+  for (int j = warp; j < K2; j += nthr >> 5) {
     if (!(ub[j] >= L) || !(a[j] > 0.f)) continue;
     const int fj = f[j];
     float val;
@@ -133,7 +133,7 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict_
   __syncthreads();
   // final TopK over the exact values: rank by (value desc, feature id asc)
   int my_pos = 0;
-  for (int j = tid; j < K2; j += RF_THREADS) {
+  for (int j = tid; j < K2; j += nthr) {
     const float v = ex[j];
     if (v > 0.f) {
       ++my_pos;
@@ -344,7 +344,9 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
   SAEB_REQUIRE(smem <= 200 * 1024, "refine: d=%lld too large for the shared-memory row buffer", d);
   auto kern = refine_kernel<XT>;
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)T, RF_THREADS, smem, stream>>>(x, ld_x, W, d, N, bias, wnorm, trailer, xnorm, c_eps, cand_vals,
+  // feature-sharded calls evaluate only a handful of candidates per token: smaller blocks, more tokens in flight
+  const int threads = ext_lower != nullptr ? 128 : RF_THREADS;
+  kern<<<(unsigned)T, threads, smem, stream>>>(x, ld_x, W, d, N, bias, wnorm, trailer, xnorm, c_eps, cand_vals,
                                                  cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx,
                                                  status, flag_rows, ext_lower);
   SAEB_CHECK_CUDA(cudaGetLastError());

@@ -221,6 +221,46 @@ def exp_scan(T=131072, world=1, rank=0, planes=3):
     return dict(ms=ms, tokens_per_s=T / (ms * 1e-3), world=world)
 
 
+def exp_scan_sim(T=151552, world=8, rank=3):
+    """per-rank cost of the feature-sharded scan with a realistic external lower bound (no collectives): the global
+    k-th values come from a full single-GPU encode, ext_L = 0.985 * kth"""
+    torch, engine = _setup(2)
+    from saeb200 import dist as sdist, synth
+    sae = synth.make_sae(4096, 131072, 64, "cuda", seed=1234)
+    x = synth.make_activations(T, 4096, "cuda", seed=5)
+    kth = sae.encode(x).top_acts[:, -1].contiguous()
+    lo, hi = sdist.shard_range(131072, world, rank)
+    ops = sdist.EngineOps(sae.encoder.weight.data[lo:hi], sae.encoder.bias.data[lo:hi], sae.b_dec.data, lo, hi, 20, 64,
+                          "cuda")
+    chunk = 37888
+    ph = {}
+
+    def run(timed):
+        ops.scan = engine.TopActivationScan(lo, hi, 20, 64, "cuda")
+        marks = []
+
+        def mark(n):
+            if timed:
+                e = torch.cuda.Event(enable_timing=True); e.record(); marks.append((n, e))
+        mark("start")
+        for t in range(0, T, chunk):
+            xc = x[t:t + chunk]
+            lb = ops.local_bounds(xc, 64); mark("gemm+bounds")
+            v, i = ops.local_topk(kth[t:t + chunk] * 0.985); mark("refine")
+            ops.scan_update(v, i, t // 64, kth[t:t + chunk]); mark("scan_update")
+        ops.scan_finalize(); mark("finalize")
+        if timed:
+            torch.cuda.synchronize()
+            for (n0, e0), (n1, e1) in zip(marks, marks[1:]):
+                ph[n1] = ph.get(n1, 0.0) + e0.elapsed_time(e1)
+    run(False); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); run(True); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return dict(ms=ms, tokens_per_s=T / (ms * 1e-3), phases={k: round(v, 2) for k, v in ph.items()},
+                flagged=int(ops.status.item()))
+
+
 EXPS = {
     "gemm_p1_small": lambda: exp_gemm(1, 1, 256, 128, 512),
     "gemm_p2_small": lambda: exp_gemm(2, 1, 256, 128, 512),
@@ -263,6 +303,7 @@ EXPS = {
     "time_refine_64k_s4": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=4),
     "time_refine_64k_s6": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=6),
     "time_refine_64k_s8": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=8),
+    "scan_sim8": lambda: exp_scan_sim(),
     "scan_w1": lambda: exp_scan(world=1),
     "scan_w8": lambda: exp_scan(world=8),
     "stats_refine": lambda: exp_stats(3),
