@@ -149,7 +149,13 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict_
   if (my_pos) atomicAdd(&s_cnt[1], my_pos);
   __syncthreads();
   const int npos = s_cnt[1];
-  if (npos < k && warp == 0) {
+  if (npos < k && ext_lower != nullptr) {
+    // feature-sharded call: the tail only has to read as "nothing here" (value 0); ids need not be distinct
+    for (int j = npos + tid; j < k; j += nthr) {
+      out_vals[t * k + j] = 0.f;
+      out_idx[t * k + j] = 0;
+    }
+  } else if (npos < k && warp == 0) {
     // fewer than k positive latents: pad with zeros on the smallest unused feature ids (as topk_merge_kernel does)
     int filled = npos;
     const uint32_t lt_mask = (1u << lane) - 1u;
