@@ -64,7 +64,7 @@ class Cache:
         """Legacy entry for callers holding a dense (already TopK-masked) [batch, seq, feature] tensor: dense ->
         per-token top entries -> the same extraction kernel."""
         k = int((latents.abs() > engine.ACT_THRESHOLD).sum(-1).max().clamp_min(1).item())
-        vals, idx = latents.topk(min(k, latents.shape[-1]), dim=-1)
+        vals, idx = engine.dense_topk(latents, min(k, latents.shape[-1]))
         return engine.coo_extract(vals, idx, latents.shape[-2],
                                   filter_bitmap=self._bitmap(module_path, latents.shape[-1], latents.device))
 
