@@ -49,6 +49,9 @@ float saeb_profile_last_encode_ms(void);
  * MMA issuer waiting for TMA data, epilogue warp waiting for an accumulator, epilogue compaction time, kernel time,
  * number of CTA pairs summed, 0}.  Synchronises. */
 int saeb_debug_stats(unsigned long long* out8);
+/* Device facts used by the launch heuristics: "num_sms", "l2_bytes", "persisting_l2_max_bytes",
+ * "access_policy_max_window_bytes", "persisting_l2_in_use_bytes"; < 0 if unknown. */
+long long saeb_query(const char* name);
 
 /* ---- one-time weight repack -------------------------------------------------------------------------------
  * Reference parameters: `encoder.weight [N,d]`, `encoder.bias [N]`, `b_dec [d]` fp32 (sae/sae.py:59-66, loaded by

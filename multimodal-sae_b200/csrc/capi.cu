@@ -35,19 +35,20 @@ int encode_merge_launch(long long T, long long N, int k, float* out_vals, long l
                         size_t workspace_bytes, cudaStream_t stream);
 int set_chunking(int v);
 int pack_weights_f16_launch(const float* W_enc, const float* b_enc, const float* b_dec, long long N, long long d,
-                            long long d_pad, void* w_plane, float* bias, float* wnorm, float* trailer,
+                            long long d_pad, void* w_plane, float* bias, float* wnorm, float* dnorm, float* trailer,
                             cudaStream_t stream);
 int prep_x_f16_launch(const void* x, int x_dtype, long long T, long long d, long long ld_x, long long d_pad, void* out,
-                      float* row_scale, float* xnorm, cudaStream_t stream);
+                      float* row_scale, float* xnorm, float* xdnorm, cudaStream_t stream);
 size_t refine_fallback_bytes(long long N);
 int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const float* W, long long d, long long N,
-                  const float* bias, const float* wnorm, const float* trailer, const float* xnorm, float c_eps,
+                  const float* bias, const float* wnorm, const float* dnorm, const float* trailer, const float* xnorm,
+                  const float* xdnorm, float c_eps,
                   const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                   float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
                   float* dense_scratch, const float* ext_lower, cudaStream_t stream);
 int candidate_bounds_launch(const float* cand_vals, const long long* cand_idx, long long T, int K2, int k,
-                            const float* wnorm, const float* xnorm, float c_eps, long long clamp_feature,
-                            float* lb_out, cudaStream_t stream);
+                            const float* wnorm, const float* dnorm, const float* xnorm, const float* xdnorm,
+                            float c_eps, long long clamp_feature, float* lb_out, cudaStream_t stream);
 int dense_topk_launch(const float* dense, long long T, long long ld, long long N, int k, float* out_vals,
                       long long* out_idx, cudaStream_t stream);
 int set_splits(int v);
@@ -123,11 +124,35 @@ int saeb_set_option(const char* name, int value) {
 
 float saeb_profile_last_encode_ms(void) { return last_encode_ms(); }
 int saeb_debug_stats(unsigned long long* out8) { return read_stats(out8); }
+long long saeb_query(const char* name) {
+  if (name == nullptr) return -1;
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -2;
+  if (strcmp(name, "persisting_l2_max_bytes") == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    return v;
+  }
+  if (strcmp(name, "access_policy_max_window_bytes") == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    return v;
+  }
+  if (strcmp(name, "l2_bytes") == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev);
+    return v;
+  }
+  if (strcmp(name, "num_sms") == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+  }
+  if (strcmp(name, "persisting_l2_in_use_bytes") == 0) return persist_bytes();
+  return -1;
+}
 
 size_t saeb_packed_bias_offset(int64_t N, int64_t d, int planes) { return planes_bytes(N, d, planes); }
 size_t saeb_packed_weights_bytes(int64_t N, int64_t d, int planes) {
-  // bias [N]; mode 3 appends wnorm [N] and a 256-byte trailer {w_unscale, wnorm_max, scratch}
-  return planes_bytes(N, d, planes) + bias_bytes(N) + (planes == 3 ? bias_bytes(N) + 256 : 0);
+  // bias [N]; mode 3 appends ||w_j|| [N], ||w_j - fp16(w_j)|| [N] and a 256-byte trailer
+  // {w_unscale, max ||w_j||, scratch, max rounding-error norm}
+  return planes_bytes(N, d, planes) + bias_bytes(N) + (planes == 3 ? 2 * bias_bytes(N) + 256 : 0);
 }
 
 int saeb_pack_weights(const float* W_enc, const float* b_enc, const float* b_dec, int64_t N, int64_t d, int planes,
@@ -138,8 +163,9 @@ int saeb_pack_weights(const float* W_enc, const float* b_enc, const float* b_dec
   float* bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + planes_bytes(N, d, planes));
   if (planes == 3) {
     float* wnorm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bias) + bias_bytes(N));
-    float* trailer = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(wnorm) + bias_bytes(N));
-    int rc3 = pack_weights_f16_launch(W_enc, b_enc, b_dec, N, d, pad8(d), packed, bias, wnorm, trailer,
+    float* dnorm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(wnorm) + bias_bytes(N));
+    float* trailer = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(dnorm) + bias_bytes(N));
+    int rc3 = pack_weights_f16_launch(W_enc, b_enc, b_dec, N, d, pad8(d), packed, bias, wnorm, dnorm, trailer,
                                       (cudaStream_t)stream);
     if (rc3 == 0) g_launches += 2;
     return rc3;
@@ -208,16 +234,17 @@ static inline int refine_k2(int k, int margin) {
   if (K2 > 512) K2 = 512;
   return K2;
 }
-// prepared activations of a whole batch: x16 [T][d_pad] fp16 | row_scale [T] f32 | xnorm [T] f32
+// prepared activations of a whole batch: x16 [T][d_pad] fp16 | row_scale [T] | xnorm [T] | xdnorm [T]  (f32)
 struct PrepLayout {
-  size_t x16, row_scale, xnorm, total;
+  size_t x16, row_scale, xnorm, xdnorm, total;
 };
 static PrepLayout prep_layout(long long T, long long d) {
   PrepLayout p;
   p.x16 = 0;
   p.row_scale = align_up((size_t)T * pad8(d) * 2, 1024);
   p.xnorm = p.row_scale + align_up((size_t)T * 4, 256);
-  p.total = p.xnorm + align_up((size_t)T * 4, 256);
+  p.xdnorm = p.xnorm + align_up((size_t)T * 4, 256);
+  p.total = p.xdnorm + align_up((size_t)T * 4, 256);
   return p;
 }
 // per-call (or per-chunk) scratch of the candidate pipeline
@@ -254,7 +281,8 @@ int saeb_prep_activations(const void* x, int x_dtype, int64_t T, int64_t ld_x, i
   const PrepLayout p = prep_layout(T, d);
   uint8_t* b = reinterpret_cast<uint8_t*>(prep);
   int rc = prep_x_f16_launch(x, x_dtype, T, d, ld_x, pad8(d), b + p.x16, reinterpret_cast<float*>(b + p.row_scale),
-                             reinterpret_cast<float*>(b + p.xnorm), (cudaStream_t)stream);
+                             reinterpret_cast<float*>(b + p.xnorm), reinterpret_cast<float*>(b + p.xdnorm),
+                             (cudaStream_t)stream);
   if (rc == 0) g_launches += 1;
   return rc;
 }
@@ -283,7 +311,8 @@ int saeb_encode_candidates(const void* prep, int64_t T_total, int64_t t0, int64_
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
   const float* bias = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3));
-  const float* trailer = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + 2 * bias_bytes(N));
+  const float* dnorm = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + 2 * bias_bytes(N));
+  const float* trailer = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + 3 * bias_bytes(N));
   int rc = encode_gemm_launch(pb + p.x16 + (size_t)t0 * pad8(d) * 2, 1, Tc, pad8(d), (long long)Tc * pad8(d), packed, 1,
                               pad8(d), bias, d, N, K2, clamp_feature, clamp_value, true, nullptr, 0, ws + w.enc,
                               w.total - w.enc, 1, /*operand_fmt=fp16*/ 0,
@@ -294,9 +323,10 @@ int saeb_encode_candidates(const void* prep, int64_t T_total, int64_t t0, int64_
 
 // phase B: candidate merge + exact fp32 re-evaluation (+ dense fallback) for the same rows (HBM bound).
 // x points at row t0 of the ORIGINAL activations.
-static inline float refine_c_eps(int x_dtype) {
-  // fp16 rounding of W (2^-11), of x when it is fp32 (2^-11), and 2^-12 of slack for the fp32 accumulation
-  return ldexpf(1.0f, -11) + (x_dtype == DT_F32 ? ldexpf(1.0f, -11) : 0.f) + ldexpf(1.0f, -12);
+static inline float refine_c_eps(int /*x_dtype*/) {
+  // slack for the fp32 accumulation inside the tensor cores (the operand rounding errors are bounded exactly through
+  // the stored error norms): 256 block additions of <= 2^-23 relative error each, doubled
+  return ldexpf(1.0f, -14);
 }
 
 // feature-sharded scan, step 1: merge this shard's candidates and emit, per token, the k largest lower bounds
@@ -319,12 +349,14 @@ int saeb_candidate_bounds(const void* prep, int64_t T_total, int64_t t0, int64_t
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
   const float* wnorm = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + bias_bytes(N));
+  const float* dnorm = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + 2 * bias_bytes(N));
   float* mvals = reinterpret_cast<float*>(ws + w.mvals);
   long long* midx = reinterpret_cast<long long*>(ws + w.midx);
   int rc = encode_merge_launch(Tc, N, K2, mvals, midx, ws + w.enc, w.total - w.enc, st);
   if (rc) return rc;
-  rc = candidate_bounds_launch(mvals, midx, Tc, K2, k < K2 ? k : K2, wnorm,
-                               reinterpret_cast<const float*>(pb + p.xnorm) + t0, refine_c_eps(x_dtype), clamp_feature,
+  rc = candidate_bounds_launch(mvals, midx, Tc, K2, k < K2 ? k : K2, wnorm, dnorm,
+                               reinterpret_cast<const float*>(pb + p.xnorm) + t0,
+                               reinterpret_cast<const float*>(pb + p.xdnorm) + t0, refine_c_eps(x_dtype), clamp_feature,
                                lb_out, st);
   if (rc == 0) g_launches += 2;
   return rc;
@@ -350,7 +382,8 @@ int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void*
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
   const float* bias = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3));
   const float* wnorm = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + bias_bytes(N));
-  const float* trailer = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + 2 * bias_bytes(N));
+  const float* dnorm = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + 2 * bias_bytes(N));
+  const float* trailer = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + 3 * bias_bytes(N));
   int* status = reinterpret_cast<int*>(ws + w.status);
   float* mvals = reinterpret_cast<float*>(ws + w.mvals);
   long long* midx = reinterpret_cast<long long*>(ws + w.midx);
@@ -360,8 +393,9 @@ int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void*
     rc = encode_merge_launch(Tc, N, K2, mvals, midx, ws + w.enc, w.total - w.enc, st);
     if (rc) return rc;
   }
-  rc = refine_launch(x, x_dtype, Tc, ld_x, W_enc, d, N, bias, wnorm, trailer,
-                     reinterpret_cast<const float*>(pb + p.xnorm) + t0, refine_c_eps(x_dtype), mvals, midx, K2,
+  rc = refine_launch(x, x_dtype, Tc, ld_x, W_enc, d, N, bias, wnorm, dnorm, trailer,
+                     reinterpret_cast<const float*>(pb + p.xnorm) + t0,
+                     reinterpret_cast<const float*>(pb + p.xdnorm) + t0, refine_c_eps(x_dtype), mvals, midx, K2,
                      k < K2 ? k : K2, clamp_feature, clamp_value, out_vals, reinterpret_cast<long long*>(out_idx), status,
                      reinterpret_cast<int*>(ws + w.flag_rows), reinterpret_cast<float*>(ws + w.dense), ext_lower, st);
   if (rc) return rc;

@@ -832,9 +832,11 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const Encode
     attr[1].val.accessPolicyWindow.base_ptr = g_window.base;
     attr[1].val.accessPolicyWindow.num_bytes = g_window.bytes;
     double ratio = (double)g_persist_bytes / (double)g_window.bytes;
-    attr[1].val.accessPolicyWindow.hitRatio = ratio > 1.0 ? 1.0f : (float)ratio;
+    // mode 1: persisting fraction limited to the set-aside size, the rest streams; 2: everything persisting, the
+    // hardware arbitrates; 3: limited fraction, the rest normal
+    attr[1].val.accessPolicyWindow.hitRatio = (ratio > 1.0 || g_persist_a == 2) ? 1.0f : (float)ratio;
     attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    attr[1].val.accessPolicyWindow.missProp = g_persist_a == 1 ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
     cfg.numAttrs = 2;
   }
   SAEB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, args));

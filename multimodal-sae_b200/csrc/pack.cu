@@ -120,37 +120,49 @@ __global__ void w_stats_kernel(const float* __restrict__ W, const float* __restr
   }
 }
 
+// one warp per feature row: scaled fp16 plane + the exact norm of its rounding error
 __global__ void pack_w_f16_kernel(const float* __restrict__ W, long long N, long long d, long long d_pad,
                                   const unsigned int* __restrict__ absmax_bits, __half* __restrict__ out,
-                                  float* __restrict__ trailer) {
+                                  float* __restrict__ dnorm, float* __restrict__ trailer) {
   const float amax = __uint_as_float(*absmax_bits);
   int e = 0;
   if (amax > 0.f) frexpf(amax, &e);            // amax = m * 2^e, m in [0.5, 1)
   const float scale = ldexpf(1.0f, 14 - e);    // largest |W| lands in [2^13, 2^14): far from fp16 overflow/underflow
-  if (blockIdx.x == 0 && threadIdx.x == 0) trailer[0] = ldexpf(1.0f, e - 14);
-  const long long total = N * d_pad;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const long long r = i / d_pad, c = i - r * d_pad;
-    out[i] = __float2half_rn((c < d) ? W[r * d + c] * scale : 0.f);
+  const float unscale = ldexpf(1.0f, e - 14);
+  if (blockIdx.x == 0 && threadIdx.x == 0) trailer[0] = unscale;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  double sq = 0.0;
+  for (long long c = lane; c < d_pad; c += 32) {
+    const float ws = (c < d) ? W[row * d + c] * scale : 0.f;   // exact: power-of-two scale
+    const __half h = __float2half_rn(ws);
+    out[row * d_pad + c] = h;
+    const double dw = (double)ws - (double)__half2float(h);
+    sq += dw * dw;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if (lane == 0) {
+    const float dn = (float)(sqrt(sq) * (double)unscale) * (1.0f + 1e-6f);   // rounded up: used in an upper bound
+    dnorm[row] = dn;
+    atomicMax(reinterpret_cast<unsigned int*>(trailer + 3), __float_as_uint(dn));
   }
 }
 
 int pack_weights_f16_launch(const float* W_enc, const float* b_enc, const float* b_dec, long long N, long long d,
-                            long long d_pad, void* w_plane, float* bias, float* wnorm, float* trailer,
+                            long long d_pad, void* w_plane, float* bias, float* wnorm, float* dnorm, float* trailer,
                             cudaStream_t stream) {
   SAEB_REQUIRE(N > 0 && d > 0, "pack: need N>0 and d>0 (got N=%lld d=%lld)", N, d);
-  // trailer[0] = w_unscale, trailer[1] = wnorm_max, trailer[2] = |W|max (scratch bits)
+  // trailer[0] = w_unscale, trailer[1] = max ||w_j||, trailer[2] = |W|max (scratch bits), trailer[3] = max dnorm_j
   SAEB_CHECK_CUDA(cudaMemsetAsync(trailer, 0, 16, stream));
   w_stats_kernel<<<(int)((N + 7) / 8), 256, 0, stream>>>(W_enc, b_enc, b_dec, N, d, bias, wnorm,
                                                          reinterpret_cast<unsigned int*>(trailer + 2),
                                                          reinterpret_cast<unsigned int*>(trailer + 1));
   SAEB_CHECK_CUDA(cudaGetLastError());
-  const long long n = N * d_pad;
-  int blocks = (int)((n + 255) / 256);
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  pack_w_f16_kernel<<<blocks, 256, 0, stream>>>(W_enc, N, d, d_pad, reinterpret_cast<unsigned int*>(trailer + 2),
-                                                reinterpret_cast<__half*>(w_plane), trailer);
+  pack_w_f16_kernel<<<(int)((N + 7) / 8), 256, 0, stream>>>(W_enc, N, d, d_pad,
+                                                           reinterpret_cast<unsigned int*>(trailer + 2),
+                                                           reinterpret_cast<__half*>(w_plane), dnorm, trailer);
   SAEB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -160,7 +172,8 @@ int pack_weights_f16_launch(const float* W_enc, const float* b_enc, const float*
 // represented exactly (up to fp16 underflow 2^-28 below the row maximum); fp32 inputs are rounded to 11 bits.
 template <typename Tin>
 __global__ void prep_x_f16_kernel(const Tin* __restrict__ x, long long T, long long d, long long ld_x, long long d_pad,
-                                  __half* __restrict__ out, float* __restrict__ row_scale, float* __restrict__ xnorm) {
+                                  __half* __restrict__ out, float* __restrict__ row_scale, float* __restrict__ xnorm,
+                                  float* __restrict__ xdnorm) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= T) return;
@@ -184,23 +197,33 @@ __global__ void prep_x_f16_kernel(const Tin* __restrict__ x, long long T, long l
     xnorm[row] = sqrtf(sq) * (1.0f + 1e-5f);
   }
   __half* o = out + row * d_pad;
-  for (long long i = lane; i < d_pad; i += 32) o[i] = __float2half_rn((i < d) ? (float)xr[i] * scale : 0.f);
+  float dsq = 0.f;   // squared norm of the rounding error (0 for bf16 / fp16 inputs away from underflow)
+  for (long long i = lane; i < d_pad; i += 32) {
+    const float xs = (i < d) ? (float)xr[i] * scale : 0.f;
+    const __half h = __float2half_rn(xs);
+    o[i] = h;
+    const float dx = xs - __half2float(h);
+    dsq = fmaf(dx, dx, dsq);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) dsq += __shfl_xor_sync(0xffffffffu, dsq, off);
+  if (lane == 0) xdnorm[row] = sqrtf(dsq) * ldexpf(1.0f, e - 14) * (1.0f + 1e-5f);
 }
 
 int prep_x_f16_launch(const void* x, int x_dtype, long long T, long long d, long long ld_x, long long d_pad, void* out,
-                      float* row_scale, float* xnorm, cudaStream_t stream) {
+                      float* row_scale, float* xnorm, float* xdnorm, cudaStream_t stream) {
   const int wpb = 8;
   const unsigned blocks = (unsigned)((T + wpb - 1) / wpb);
   __half* o = reinterpret_cast<__half*>(out);
   if (x_dtype == DT_F32)
     prep_x_f16_kernel<float><<<blocks, wpb * 32, 0, stream>>>(reinterpret_cast<const float*>(x), T, d, ld_x, d_pad, o,
-                                                             row_scale, xnorm);
+                                                             row_scale, xnorm, xdnorm);
   else if (x_dtype == DT_F16)
     prep_x_f16_kernel<__half><<<blocks, wpb * 32, 0, stream>>>(reinterpret_cast<const __half*>(x), T, d, ld_x, d_pad, o,
-                                                              row_scale, xnorm);
+                                                              row_scale, xnorm, xdnorm);
   else if (x_dtype == DT_BF16)
     prep_x_f16_kernel<__nv_bfloat16><<<blocks, wpb * 32, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), T, d,
-                                                                     ld_x, d_pad, o, row_scale, xnorm);
+                                                                     ld_x, d_pad, o, row_scale, xnorm, xdnorm);
   else {
     set_error("prep_x: unsupported dtype %d", x_dtype);
     return -1;

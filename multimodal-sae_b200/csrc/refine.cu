@@ -1,8 +1,12 @@
 // Exact refinement of an approximate TopK ("fp16 + refine" mode) and the exact dense fallback.
 //
 // The fused GEMM runs ONE tensor-core pass with W_enc rounded to fp16 (11-bit significand) and returns, per row, the
-// K2 = k + margin best candidates by APPROXIMATE value a_j.  With u = 2^-11 the rounding error of candidate j is
-// bounded by  eps_j = c_eps * ||x||_2 * ||w_j||_2  (Cauchy-Schwarz; c_eps = u_w + u_x + accumulation slack).  Hence
+// K2 = k + margin best candidates by APPROXIMATE value a_j.  With x = xh + dx, w_j = wh_j + dw_j (h = what the tensor
+// cores saw) the error of candidate j is  xh.dw_j + dx.wh_j + dx.dw_j  plus fp32 accumulation error, hence bounded by
+//   eps_j = 1.001 * (||x|| * ||dw_j|| + ||dx|| * ||w_j||) + slack * ||x|| * ||w_j||        (Cauchy-Schwarz)
+// where ||dw_j|| is the EXACT norm of the feature's fp16 rounding error (computed once at pack time, ~0.4 * 2^-11
+// ||w_j||), ||dx|| the exact norm of the activation row's rounding error (0 for bf16 / fp16 inputs) and slack = 2^-14
+// covers the accumulation (256 block additions of <= 2^-23 relative error each, doubled).  Hence
 //   * the true k-th value is at least L = k-th largest of (a_j - eps_j);
 //   * only candidates with a_j + eps_j >= L can belong to the true TopK; they are re-evaluated EXACTLY here
 //     (fp32 dot product with the fp32 W_enc row + folded bias), and the final TopK is taken over the exact values;
@@ -20,8 +24,9 @@ constexpr int RF_MAX_FLAG = 64;   // rows the dense fallback can absorb per call
 template <typename XT>
 __global__ void __launch_bounds__(RF_THREADS)
 refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict__ W, long long d, long long N,
-              const float* __restrict__ bias, const float* __restrict__ wnorm, const float* __restrict__ trailer,
-              const float* __restrict__ xnorm, float c_eps, const float* __restrict__ cand_vals,
+              const float* __restrict__ bias, const float* __restrict__ wnorm, const float* __restrict__ dnorm,
+              const float* __restrict__ trailer, const float* __restrict__ xnorm, const float* __restrict__ xdnorm,
+              float c_eps, const float* __restrict__ cand_vals,
               const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
               float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
               int* __restrict__ flag_rows, const float* __restrict__ ext_lower) {
@@ -39,13 +44,14 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
 
   for (int i = tid; i < d4; i += nthr) xs[i] = (i < d) ? (float)x[t * ld_x + i] : 0.f;
-  const float xn = xnorm[t];
-  const float wmax = trailer[1];
+  const float xn = xnorm[t], xdn = xdnorm[t];
+  const float wmax = trailer[1], dmax = trailer[3];
   for (int j = tid; j < K2; j += nthr) {
     const float av = cand_vals[t * K2 + j];
     const int fj = (int)cand_idx[t * K2 + j];
     const bool valid = av > 0.f;
-    const float eps = (fj == clamp_feature) ? 0.f : c_eps * xn * wnorm[fj];
+    const float wn = wnorm[fj];
+    const float eps = (fj == clamp_feature) ? 0.f : 1.001f * (xn * dnorm[fj] + xdn * wn) + c_eps * xn * wn;
     a[j] = av;
     f[j] = fj;
     lb[j] = valid ? av - eps : -INFINITY;
@@ -78,7 +84,7 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict_
   // list possibly too short?  (only when the list is full: otherwise every positive latent is already in it)
   if (tid == 0 && nv == K2) {
     const float a_last = a[K2 - 1];
-    if (a_last + c_eps * xn * wmax >= L) {
+    if (a_last + 1.001f * (xn * dmax + xdn * wmax) + c_eps * xn * wmax >= L) {
       const int slot = atomicAdd(&status[0], 1);
       if (slot < RF_MAX_FLAG) flag_rows[slot] = (int)t;
     }
@@ -181,15 +187,17 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict_
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 candidate_bounds_kernel(const float* __restrict__ cand_vals, const long long* __restrict__ cand_idx, int K2, int k,
-                        const float* __restrict__ wnorm, const float* __restrict__ xnorm, float c_eps,
+                        const float* __restrict__ wnorm, const float* __restrict__ dnorm,
+                        const float* __restrict__ xnorm, const float* __restrict__ xdnorm, float c_eps,
                         long long clamp_feature, float* __restrict__ lb_out) {
   extern __shared__ float bsm[];   // [K2]
   const long long t = blockIdx.x;
-  const float xn = xnorm[t];
+  const float xn = xnorm[t], xdn = xdnorm[t];
   for (int j = threadIdx.x; j < K2; j += blockDim.x) {
     const float av = cand_vals[t * K2 + j];
     const long long fj = cand_idx[t * K2 + j];
-    const float eps = (fj == clamp_feature) ? 0.f : c_eps * xn * wnorm[fj];
+    const float wn = wnorm[fj];
+    const float eps = (fj == clamp_feature) ? 0.f : 1.001f * (xn * dnorm[fj] + xdn * wn) + c_eps * xn * wn;
     bsm[j] = (av > 0.f) ? fmaxf(av - eps, 0.f) : 0.f;
   }
   for (int j = threadIdx.x; j < k; j += blockDim.x) lb_out[t * k + j] = 0.f;
@@ -203,11 +211,11 @@ candidate_bounds_kernel(const float* __restrict__ cand_vals, const long long* __
 }
 
 int candidate_bounds_launch(const float* cand_vals, const long long* cand_idx, long long T, int K2, int k,
-                            const float* wnorm, const float* xnorm, float c_eps, long long clamp_feature,
-                            float* lb_out, cudaStream_t stream) {
+                            const float* wnorm, const float* dnorm, const float* xnorm, const float* xdnorm,
+                            float c_eps, long long clamp_feature, float* lb_out, cudaStream_t stream) {
   if (T == 0) return 0;
-  candidate_bounds_kernel<<<(unsigned)T, 128, (size_t)K2 * sizeof(float), stream>>>(cand_vals, cand_idx, K2, k, wnorm,
-                                                                                    xnorm, c_eps, clamp_feature, lb_out);
+  candidate_bounds_kernel<<<(unsigned)T, 128, (size_t)K2 * sizeof(float), stream>>>(
+      cand_vals, cand_idx, K2, k, wnorm, dnorm, xnorm, xdnorm, c_eps, clamp_feature, lb_out);
   SAEB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -341,7 +349,8 @@ size_t refine_fallback_bytes(long long N) { return (size_t)RF_MAX_FLAG * (size_t
 
 template <typename XT>
 static int refine_launch_t(const XT* x, long long T, long long ld_x, const float* W, long long d, long long N,
-                           const float* bias, const float* wnorm, const float* trailer, const float* xnorm, float c_eps,
+                           const float* bias, const float* wnorm, const float* dnorm, const float* trailer,
+                           const float* xnorm, const float* xdnorm, float c_eps,
                            const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                            float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
                            float* dense_scratch, const float* ext_lower, cudaStream_t stream) {
@@ -352,7 +361,7 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // feature-sharded calls evaluate only a handful of candidates per token: smaller blocks, more tokens in flight
   const int threads = ext_lower != nullptr ? 128 : RF_THREADS;
-  kern<<<(unsigned)T, threads, smem, stream>>>(x, ld_x, W, d, N, bias, wnorm, trailer, xnorm, c_eps, cand_vals,
+  kern<<<(unsigned)T, threads, smem, stream>>>(x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals,
                                                  cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx,
                                                  status, flag_rows, ext_lower);
   SAEB_CHECK_CUDA(cudaGetLastError());
@@ -373,12 +382,14 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
 }
 
 int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const float* W, long long d, long long N,
-                  const float* bias, const float* wnorm, const float* trailer, const float* xnorm, float c_eps,
+                  const float* bias, const float* wnorm, const float* dnorm, const float* trailer, const float* xnorm,
+                  const float* xdnorm, float c_eps,
                   const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                   float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
                   float* dense_scratch, const float* ext_lower, cudaStream_t stream) {
 #define SAEB_RF(XT)                                                                                                  \
-  return refine_launch_t<XT>(reinterpret_cast<const XT*>(x), T, ld_x, W, d, N, bias, wnorm, trailer, xnorm, c_eps,   \
+  return refine_launch_t<XT>(reinterpret_cast<const XT*>(x), T, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm,   \
+                             xdnorm, c_eps,                                                                          \
                              cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx, status,      \
                              flag_rows, dense_scratch, ext_lower, stream)
   if (x_dtype == DT_F32) SAEB_RF(float);

@@ -27,6 +27,7 @@ SIGNATURES = {
     "saeb_set_option": (c_int, [c_char_p, c_int]),
     "saeb_profile_last_encode_ms": (c_float, []),
     "saeb_debug_stats": (c_int, [c_void_p]),
+    "saeb_query": (c_longlong, [c_char_p]),
     "saeb_packed_weights_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "saeb_packed_bias_offset": (c_size_t, [c_int64, c_int64, c_int]),
     "saeb_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),

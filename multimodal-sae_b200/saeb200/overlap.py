@@ -109,10 +109,13 @@ class OverlappedForward:
         check(L.saeb_prep_activations(x.data_ptr() + a * ldx * x.element_size(), code, b - a, ldx, d, tmp.data_ptr(),
                                       self.s_gemm.cuda_stream), "saeb_prep_activations")
         n = b - a
-        rs_off_c = (n * d_pad * 2 + 1023) // 1024 * 1024
-        xn_off_c = rs_off_c + (n * 4 + 255) // 256 * 256
-        rs_off = (T * d_pad * 2 + 1023) // 1024 * 1024
-        xn_off = rs_off + (T * 4 + 255) // 256 * 256
+
+        def layout(rows):  # mirrors prep_layout() of csrc/capi.cu: x16 | row_scale | xnorm | xdnorm
+            rs = (rows * d_pad * 2 + 1023) // 1024 * 1024
+            step = (rows * 4 + 255) // 256 * 256
+            return rs, rs + step, rs + 2 * step
+
+        src, dst = layout(n), layout(T)
         prep[a * d_pad * 2:b * d_pad * 2].copy_(tmp[:n * d_pad * 2], non_blocking=True)
-        prep[rs_off + a * 4:rs_off + b * 4].copy_(tmp[rs_off_c:rs_off_c + n * 4], non_blocking=True)
-        prep[xn_off + a * 4:xn_off + b * 4].copy_(tmp[xn_off_c:xn_off_c + n * 4], non_blocking=True)
+        for so, do in zip(src, dst):
+            prep[do + a * 4:do + b * 4].copy_(tmp[so:so + n * 4], non_blocking=True)

@@ -292,6 +292,10 @@ EXPS = {
     "t_h3": lambda: exp_time(2, 1, 65536, 4096, 131072, 64, iters=2, hints=3),
     "t_s8": lambda: exp_time(2, 1, 65536, 4096, 131072, 64, iters=2, splits=8),
     "t_9472": lambda: exp_time(2, 1, 9472, 4096, 131072, 64, iters=3, splits=2),
+    "t_p1": lambda: exp_time(2, 3, 9472, 4096, 131072, 64, iters=3, persist=1),
+    "t_p2": lambda: exp_time(2, 3, 9472, 4096, 131072, 64, iters=3, persist=2),
+    "t_p3": lambda: exp_time(2, 3, 9472, 4096, 131072, 64, iters=3, persist=3),
+    "t_p0": lambda: exp_time(2, 3, 9472, 4096, 131072, 64, iters=3, persist=0),
     "t_9472_persist": lambda: exp_time(2, 1, 9472, 4096, 131072, 64, iters=3, splits=2, persist=1),
     "t_9472_persist_h2": lambda: exp_time(2, 1, 9472, 4096, 131072, 64, iters=3, splits=2, persist=1, hints=2),
     "t_4736_persist_s4": lambda: exp_time(2, 1, 4736, 4096, 131072, 64, iters=3, splits=4, persist=1),

@@ -1,14 +1,18 @@
 #!/bin/bash
 python - <<'PY'
-import ctypes
-rt = ctypes.CDLL("libcudart.so") if False else None
+import sys
+sys.path.insert(0, "multimodal-sae_b200")
 import torch
-p = torch.cuda.get_device_properties(0)
-print("L2", p.L2_cache_size, "persistingL2CacheMaxSize", getattr(p, "persisting_l2_cache_max_size", None), "accessPolicyMaxWindowSize", getattr(p, "access_policy_max_window_size", None))
+torch.zeros(1, device="cuda")
+from saeb200 import _capi
+L = _capi.lib()
+for n in (b"num_sms", b"l2_bytes", b"persisting_l2_max_bytes", b"access_policy_max_window_bytes"):
+    print(n.decode(), L.saeb_query(n))
 PY
-for E in t_h0 t_h1 t_h2 t_h3 t_s8 t_9472 t_9472_persist t_9472_persist_h2 t_4736_persist_s4; do
+for E in t_p0 t_p1 t_p2 t_p3; do
   ncu --metrics dram__bytes_read.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__cycles_elapsed.avg.per_second \
       --clock-control none -k regex:encode_topk_kernel -s 1 -c 1 --csv --log-file gpurun_out/ncu_$E.csv \
       python tools/gpu_probe.py --child $E > gpurun_out/ncu_$E.log 2>&1
   grep -E "dram__|gpu__time|lts__|tensor|per_second" gpurun_out/ncu_$E.csv | awk -F'","' '{printf "%s %s %s | ", "'$E'", $(NF-2), $NF}'; echo
 done
+python tools/gpu_probe.py t_p0 t_p1 t_p2 t_p3 2>&1 | grep RESULT | cut -c1-330
