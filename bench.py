@@ -279,7 +279,7 @@ def run_gpu(args):
     # ---- feature-sharded top-activation scan (bounded token count; one all-gather of top lists at the end)
     scan = None
     if args.scan_tokens > 0:
-        ctx_len, n_top, chunk = 64, 20, 37888  # four single-wave launches per exchange round
+        ctx_len, n_top, chunk = 64, args.scan_top, 37888  # four single-wave launches per exchange round
         lo, hi = sdist.shard_range(WIDTH, world, rank)
         ops = sdist.EngineOps(sae.encoder.weight.data[lo:hi], sae.encoder.bias.data[lo:hi], sae.b_dec.data, lo, hi,
                               n_top, ctx_len, dev, planes=args.planes)
@@ -334,7 +334,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scan-tokens", type=int, default=262144)
+    ap.add_argument("--scan-tokens", type=int, default=262144,
+                    help="tokens of the feature-sharded top-activation scan (BASELINE C3: 1048576, C4: 4194304)")
+    ap.add_argument("--scan-top", type=int, default=20, help="examples kept per feature (C3: 5, C4: 20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scan-phases", action="store_true", help="per-phase CUDA-event timing of the scan (diagnostic)")
     ap.add_argument("--no-overlap", action="store_true", help="run the phases of a step back to back on one stream")

@@ -87,7 +87,7 @@ int saeb_encode_topk(const void* x, int x_dtype, int64_t T, int64_t ld_x, const 
  * per-feature norms.  The GEMM ranks by approximate values; every candidate that can still belong to the TopK under the
  * rigorous rounding bound  (2^-11 [+2^-11 for fp32 x] + 2^-12) * ||x||_2 * ||w_j||_2  is re-evaluated exactly in fp32
  * against `W_enc` (the [N,d] fp32 parameter itself), so the returned values are fp32-exact and the index set is the
- * fp32 reference's.  `margin` = extra candidates kept per row (0 = max(64, k/2)).  Rows whose candidate list could be too short
+ * fp32 reference's.  `margin` = extra candidates kept per row (0 = max(48, k/2), or the value of option "refine_margin").  Rows whose candidate list could be too short
  * for the bound (never observed) are recomputed by an exact dense fp32 kernel, up to 64 per call; *status_out (device
  * int, may be NULL) receives the number of such rows -- more than 64 means the call must be repeated with a larger
  * margin. */

@@ -10,6 +10,7 @@
 namespace saeb {
 
 static thread_local char g_err[512] = {0};
+static int g_default_margin = 0;   // extra candidates per row in refine mode; 0: max(48, k/2)
 static std::atomic<long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
@@ -118,6 +119,10 @@ int saeb_set_option(const char* name, int value) {
   if (strcmp(name, "stats") == 0) return set_stats(value);
   if (strcmp(name, "persist_a") == 0) return set_persist_a(value);
   if (strcmp(name, "chunking") == 0) return set_chunking(value);
+  if (strcmp(name, "refine_margin") == 0) {
+    g_default_margin = value;
+    return 0;
+  }
   set_error("set_option: unknown option '%s'", name);
   return -1;
 }
@@ -229,7 +234,8 @@ int saeb_encode_topk(const void* x, int x_dtype, int64_t T, int64_t ld_x, const 
 
 // ---- "fp16 + refine": one tensor-core pass + exact fp32 re-evaluation of the candidates near the k-th value
 static inline int refine_k2(int k, int margin) {
-  int m = margin > 0 ? margin : (k / 2 > 64 ? k / 2 : 64);   // denser spectra (large k / N) need more room below the k-th value
+  const int auto_m = g_default_margin > 0 ? g_default_margin : (k / 2 > 48 ? k / 2 : 48);
+  int m = margin > 0 ? margin : auto_m;   // denser spectra (large k / N) need more room below the k-th value
   int K2 = k + m;
   if (K2 > 512) K2 = 512;
   return K2;

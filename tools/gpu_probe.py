@@ -128,11 +128,12 @@ def exp_decode(T, d, N, k):
     return dict(max_abs_err=(y.double() - ref).abs().max().item(), ref_absmax=ref.abs().max().item())
 
 
-def exp_overlap(T, chunk, planes=3, overlap=True, l2_hints=1, splits=0, iters=3, persist=1, chunking=1):
+def exp_overlap(T, chunk, planes=3, overlap=True, l2_hints=1, splits=0, iters=3, persist=1, chunking=1, margin=0):
     torch, engine = _setup(2)
     from saeb200 import _capi, synth
     from saeb200.overlap import OverlappedForward
     L = _capi.lib()
+    _capi.check(L.saeb_set_option(b"refine_margin", margin), "set_option")
     _capi.check(L.saeb_set_option(b"persist_a", persist), "set_option")
     _capi.check(L.saeb_set_option(b"chunking", chunking), "set_option")
     _capi.check(L.saeb_set_option(b"l2_hints", l2_hints), "set_option")
@@ -261,6 +262,50 @@ def exp_scan_sim(T=151552, world=8, rank=3):
                 flagged=int(ops.status.item()))
 
 
+def exp_steering(T=32768):
+    """BASELINE config 5: fp16 hidden stream [1, T, 4096] -> encode with one latent clamped -> fp16 reconstruction"""
+    torch, engine = _setup(2)
+    from saeb200 import synth
+    from sae_auto_interp.features.steering import steering_hook_output
+    sae = synth.make_sae(4096, 131072, 64, "cuda", seed=1234)
+    h = synth.make_activations(T, 4096, "cuda", seed=7, dtype=torch.float16).unsqueeze(0)
+    for _ in range(2):
+        out = steering_hook_output(sae, h, 12345, 50.0)
+    step = steering_hook_output(sae, h[:, :1], 12345, 50.0)   # decode step (T = 1): no clamp
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record(); out = steering_hook_output(sae, h, 12345, 50.0); e1.record()
+    for _ in range(20):
+        step = steering_hook_output(sae, h[:, :1], 12345, 50.0)
+    e2.record(); torch.cuda.synchronize()
+    enc = sae.encode(h, clamp_feature=12345, clamp_value=50.0)
+    clamped = bool(((enc.top_indices[0] == 12345) & (enc.top_acts[0] == 50.0)).any(-1).all())
+    return dict(prefill_ms=e0.elapsed_time(e1), prefill_tokens_per_s=T / (e0.elapsed_time(e1) * 1e-3),
+                decode_step_ms=e1.elapsed_time(e2) / 20, out_dtype=str(out.dtype), clamp_in_every_row=clamped)
+
+
+def exp_cache(T=65536, seq=2048):
+    """cache path (features/cache.py:206-218 + :73-92): hidden [B, seq, d] bf16 -> encode -> COO triples on device"""
+    torch, engine = _setup(2)
+    from saeb200 import synth
+    sae = synth.make_sae(4096, 131072, 64, "cuda", seed=1234)
+    h = synth.make_activations(T, 4096, "cuda", seed=8).view(T // seq, seq, 4096)
+    filt = engine.make_filter_bitmap(torch.arange(5000, device="cuda"), 131072)   # README: first-5k-feature filter
+    res = {}
+    for name, bm in (("nofilter", None), ("filter5k", filt)):
+        for _ in range(2):
+            enc = sae.encode(h)
+            loc, act = engine.coo_extract(enc.top_acts, enc.top_indices, seq, filter_bitmap=bm)
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(); enc = sae.encode(h); e1.record()
+        loc, act = engine.coo_extract(enc.top_acts, enc.top_indices, seq, filter_bitmap=bm); e2.record()
+        torch.cuda.synchronize()
+        res[name] = dict(encode_ms=e0.elapsed_time(e1), coo_ms=e1.elapsed_time(e2), nnz=int(loc.shape[0]),
+                         tokens_per_s=T / ((e0.elapsed_time(e1) + e1.elapsed_time(e2)) * 1e-3))
+    return res
+
+
 EXPS = {
     "gemm_p1_small": lambda: exp_gemm(1, 1, 256, 128, 512),
     "gemm_p2_small": lambda: exp_gemm(2, 1, 256, 128, 512),
@@ -307,12 +352,18 @@ EXPS = {
     "time_refine_64k_s4": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=4),
     "time_refine_64k_s6": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=6),
     "time_refine_64k_s8": lambda: exp_time(2, 3, 65536, 4096, 131072, 64, iters=2, splits=8),
+    "steering_32k": lambda: exp_steering(),
+    "cache_64k": lambda: exp_cache(),
     "scan_sim8": lambda: exp_scan_sim(),
     "scan_w1": lambda: exp_scan(world=1),
     "scan_w8": lambda: exp_scan(world=8),
     "stats_refine": lambda: exp_stats(3),
     "stats_hilo": lambda: exp_stats(2),
     "stats_bf16x1": lambda: exp_stats(1),
+    "m32": lambda: exp_overlap(65536, 18944, margin=32),
+    "m48": lambda: exp_overlap(65536, 18944, margin=48),
+    "m64": lambda: exp_overlap(65536, 18944, margin=64),
+    "m24": lambda: exp_overlap(65536, 18944, margin=24),
     "seq3_refine": lambda: exp_overlap(65536, 18944, overlap=False),
     "ov3_c18944": lambda: exp_overlap(65536, 18944),
     "ov3_c9472": lambda: exp_overlap(65536, 9472),
