@@ -188,11 +188,12 @@ def run_gpu(args):
     sae_out = torch.empty((TOKENS, D_IN), dtype=torch.float32, device=dev)
     sq_err = torch.zeros((), dtype=torch.float64, device=dev)
 
+    W_dec_used = sae.W_dec.data if args.decode_dtype == "fp32" else sae.W_dec.data.to(torch.float16)
     ov = None
     if args.planes == 3 and not args.no_overlap:
         from saeb200.overlap import OverlappedForward
 
-        ov = OverlappedForward(enc, sae.W_dec.data, sae.b_dec.data, K, chunk=args.chunk)
+        ov = OverlappedForward(enc, W_dec_used, sae.b_dec.data, K, chunk=args.chunk)
 
     def step():
         sq_err.zero_()
@@ -200,7 +201,7 @@ def run_gpu(args):
             ov.run(x, acts, idx, sae_out, sq_err)
         else:
             engine.encode_topk(x, enc, K, out_vals=acts, out_idx=idx)
-            engine.decode(idx, acts, sae.W_dec.data, sae.b_dec.data, x=x, sq_err=sq_err, out=sae_out)
+            engine.decode(idx, acts, W_dec_used, sae.b_dec.data, x=x, sq_err=sq_err, out=sae_out)
         return (sq_err / engine.total_variance(x)).to(torch.float32)
 
     # ---- device-resident throughput (`value`)
@@ -318,7 +319,7 @@ def run_gpu(args):
             "config": {"workload": "C2: d_model=4096 width=131072 k=64 SAE forward over 65536 bf16 tokens per GPU "
                                    "(encode+TopK+decode+FVU), inputs resident in HBM",
                        "global_batch_tokens": world * TOKENS, "parallelism": f"token-parallel x{world}, SAE replicated",
-                       "precision": PRECISION[args.planes],
+                       "precision": PRECISION[args.planes].replace("fp32 W_dec", f"{args.decode_dtype} W_dec"),
                        "l2": "inputs (x 512 MiB, weights 6 GiB) larger than the 126 MB L2"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "scan": scan, "fvu": fvu_val,
@@ -341,6 +342,8 @@ def main():
     ap.add_argument("--scan-phases", action="store_true", help="per-phase CUDA-event timing of the scan (diagnostic)")
     ap.add_argument("--no-overlap", action="store_true", help="run the phases of a step back to back on one stream")
     ap.add_argument("--chunk", type=int, default=18944, help="tokens per pipeline chunk (multiple of 9472 = one wave)")
+    ap.add_argument("--decode-dtype", default="fp32", choices=["fp32", "fp16"],
+                    help="W_dec copy the decode gathers from: fp32 (parity default) or fp16 (half the bytes, ~2e-4 row error)")
     ap.add_argument("--planes", type=int, default=3, choices=[1, 2, 3],
                     help="encoder mode: 3 = fp16 pass + exact refinement (default), 2 = bf16 hi+lo, 1 = bf16 (diagnostic)")
     args = ap.parse_args()

@@ -55,6 +55,7 @@ int dense_topk_launch(const float* dense, long long T, long long ld, long long N
 int set_splits(int v);
 int set_l2_hints(int v);
 int set_dbg(int v);
+int set_prefetch_b(int v);
 int set_stats(int v);
 int read_stats(unsigned long long* out8);
 int set_persist_a(int v);
@@ -116,6 +117,7 @@ int saeb_set_option(const char* name, int value) {
   if (strcmp(name, "splits") == 0) return set_splits(value);
   if (strcmp(name, "l2_hints") == 0) return set_l2_hints(value);
   if (strcmp(name, "debug_tiles") == 0) return set_dbg(value);
+  if (strcmp(name, "prefetch_b") == 0) return set_prefetch_b(value);
   if (strcmp(name, "stats") == 0) return set_stats(value);
   if (strcmp(name, "persist_a") == 0) return set_persist_a(value);
   if (strcmp(name, "chunking") == 0) return set_chunking(value);

@@ -133,6 +133,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const void* desc, uint64_
       "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
       : "memory");
 }
+// L2 prefetch of a tile (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_3d(const void* desc, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
+                   reinterpret_cast<uint64_t>(desc)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // CTA-pair variant: executed by both CTAs of the pair, the transaction bytes are signalled on the
 // barrier of the even (leader) CTA (peer bit of the shared::cluster address cleared).
 __device__ __forceinline__ void tma_load_3d_pair(void* dst, const void* desc, uint64_t* bar, int c0, int c1, int c2,

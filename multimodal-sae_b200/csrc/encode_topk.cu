@@ -53,6 +53,7 @@ struct EncodeArgs {
   int clamp_col;      // steering: column forced to clamp_val before TopK (-1 = none)
   float clamp_val;
   unsigned long long* stats;   // optional diagnostics: cycle counters summed over CTAs (see saeb_debug_stats)
+  int prefetch_b;   // weight tiles are pulled into L2 this many feature tiles ahead (0 = off), one pair per tile
   int dbg;   // diagnostics only (wrong results): bit0 = every cluster loads token tile 0, bit1 = every step loads feature tile 0
   unsigned long long hint_a, hint_b;   // L2 eviction policies of the activation / weight TMA loads
   unsigned int idesc;       // tcgen05 instruction descriptor (operand formats are a run-time choice: bf16 or fp16)
@@ -233,6 +234,18 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         const int m0 = (((args.dbg & 1) ? 0 : m_tile) * PAIR + (int)cta_rank) * BM;
         for (int nt = nt0; nt < nt1; ++nt) {
           const int n0 = ((args.dbg & 2) ? 0 : nt) * BN + (int)cta_rank * Cfg::B_ROWS;
+          if (args.prefetch_b > 0) {
+            // every pair of a split sweeps the same weight tiles; exactly one of them (round robin over the token
+            // tiles of this launch) asks L2 for a tile a few steps before the whole group needs it, so that the
+            // group's demand loads hit in L2 instead of stalling on HBM together
+            const int ntp = nt + args.prefetch_b;
+            if (ntp < nt1 && (ntp % args.num_m_tiles) == m_tile) {
+              const int np0 = ntp * BN + (int)cta_rank * Cfg::B_ROWS;
+              for (int kb = 0; kb < args.num_k_blocks; ++kb)
+#pragma unroll
+                for (int b = 0; b < BP; ++b) tma_prefetch_3d(&tm_b, kb * BK, np0, b);
+            }
+          }
           for (int kb = 0; kb < args.num_k_blocks; ++kb) {
             const long long tw0 = clock64();
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -644,6 +657,11 @@ int read_stats(unsigned long long* out8) {
   if (!g_stats) return -1;
   return cudaMemcpy(out8, g_stats, 64, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }
+static int g_prefetch_b = 0;   // measured: no gain (7.07-7.12 ms per wave without, 7.03-7.19 with), kept as an option
+int set_prefetch_b(int v) {
+  g_prefetch_b = v < 0 ? 0 : v;
+  return 0;
+}
 static int g_dbg = 0;
 int set_dbg(int v) {
   g_dbg = v;
@@ -908,6 +926,7 @@ int encode_gemm_launch(const void* x_planes, int ap, long long T, long long ld_x
     args.clamp_col = (int)clamp_feature;
     args.clamp_val = clamp_value;
     args.dbg = g_dbg;
+    args.prefetch_b = g_prefetch_b;
     args.stats = g_stats;
     args.hint_a = (g_l2_hints & 1) ? L2_EVICT_LAST : L2_EVICT_NORMAL;
     args.hint_b = (g_l2_hints & 2) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;

@@ -70,9 +70,10 @@ def exp_topk(pair, planes, T, d, N, k, xdt="bf16"):
     return dict(rows=T, rows_with_set_mismatch=bad_rows, max_rel_val_err=maxrel, sorted_desc=sorted_ok)
 
 
-def exp_time(pair, planes, T, d, N, k, iters=3, splits=0, dbg=0, hints=1, persist=0):
+def exp_time(pair, planes, T, d, N, k, iters=3, splits=0, dbg=0, hints=1, persist=0, prefetch=2):
     torch, engine = _setup(pair)
     from saeb200 import _capi
+    _capi.check(_capi.lib().saeb_set_option(b"prefetch_b", prefetch), "set_option")
     _capi.check(_capi.lib().saeb_set_option(b"debug_tiles", dbg), "set_option")
     _capi.check(_capi.lib().saeb_set_option(b"l2_hints", hints), "set_option")
     _capi.check(_capi.lib().saeb_set_option(b"persist_a", persist), "set_option")
@@ -337,6 +338,10 @@ EXPS = {
     "t_h3": lambda: exp_time(2, 1, 65536, 4096, 131072, 64, iters=2, hints=3),
     "t_s8": lambda: exp_time(2, 1, 65536, 4096, 131072, 64, iters=2, splits=8),
     "t_9472": lambda: exp_time(2, 1, 9472, 4096, 131072, 64, iters=3, splits=2),
+    "t_pf0": lambda: exp_time(2, 3, 9472, 4096, 131072, 64, iters=4, persist=1, prefetch=0),
+    "t_pf1": lambda: exp_time(2, 3, 9472, 4096, 131072, 64, iters=4, persist=1, prefetch=1),
+    "t_pf2": lambda: exp_time(2, 3, 9472, 4096, 131072, 64, iters=4, persist=1, prefetch=2),
+    "t_pf4": lambda: exp_time(2, 3, 9472, 4096, 131072, 64, iters=4, persist=1, prefetch=4),
     "t_p1": lambda: exp_time(2, 3, 9472, 4096, 131072, 64, iters=3, persist=1),
     "t_p2": lambda: exp_time(2, 3, 9472, 4096, 131072, 64, iters=3, persist=2),
     "t_p3": lambda: exp_time(2, 3, 9472, 4096, 131072, 64, iters=3, persist=3),
