@@ -216,6 +216,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  const bool timed = args.stats != nullptr;   // cycle accounting only when diagnostics are on
   const int cluster_id = blockIdx.x / PAIR;
   const int num_clusters = gridDim.x / PAIR;
   const int num_units = args.num_m_tiles * args.S;
@@ -226,7 +227,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       long long w_prod = 0;
-      const long long t_begin = clock64();
+      const long long t_begin = timed ? clock64() : 0;
       for (int u = cluster_id; u < num_units; u += num_clusters) {
         const int split = u % args.S, m_tile = u / args.S;
         const int nt0 = (int)((long long)split * args.num_n_tiles / args.S);
@@ -247,9 +248,9 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             }
           }
           for (int kb = 0; kb < args.num_k_blocks; ++kb) {
-            const long long tw0 = clock64();
+            const long long tw0 = timed ? clock64() : 0;
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            w_prod += clock64() - tw0;
+            if (timed) w_prod += clock64() - tw0;
             uint8_t* sa = smem + stage * Cfg::STAGE;
             uint8_t* sb = sa + AP * Cfg::A_PLANE;
             if constexpr (PAIR == 1) {
@@ -294,15 +295,15 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         const int nt1 = (int)((long long)(split + 1) * args.num_n_tiles / args.S);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_iter) {
           const uint32_t acc_stage = tile_iter & 1, acc_phase = (tile_iter >> 1) & 1;
-          const long long tw0 = clock64();
+          const long long tw0 = timed ? clock64() : 0;
           mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
-          w_tempty += clock64() - tw0;
+          if (timed) w_tempty += clock64() - tw0;
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc_stage * BN;
           for (int kb = 0; kb < args.num_k_blocks; ++kb) {
-            const long long tw1 = clock64();
+            const long long tw1 = timed ? clock64() : 0;
             mbar_wait(&full_bar[stage], phase);
-            w_full += clock64() - tw1;
+            if (timed) w_full += clock64() - tw1;
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
             const uint32_t sb = sa + AP * Cfg::A_PLANE;
@@ -363,9 +364,9 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           bias_w[i * 32 + lane] = (c < args.N) ? __ldg(args.bias + c) : __int_as_float(0xff800000);
         }
         __syncwarp();
-        const long long twe = clock64();
+        const long long twe = timed ? clock64() : 0;
         mbar_wait(&tfull_bar[acc_stage], acc_phase);
-        w_tfull += clock64() - twe;
+        if (timed) w_tfull += clock64() - twe;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc_stage * BN;
 #pragma unroll 1
@@ -420,8 +421,8 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           }
           // compaction when a list could overflow during the next chunk
           uint32_t need = __ballot_sync(full, cnt > CAP - 32);
-          const long long twc = need ? clock64() : 0;
-          const bool had = need != 0;
+          const bool had = timed && need != 0;
+          const long long twc = had ? clock64() : 0;
           while (need) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
