@@ -290,7 +290,11 @@ def run_gpu(args):
             for t0 in range(0, args.scan_tokens, chunk):
                 yield xs[t0:t0 + chunk]
 
-        sdist.sharded_scan(chunks(), ops, K, ctx_len, WIDTH)  # warm-up
+        def warm_chunks():
+            for t0 in range(0, min(args.scan_tokens, 4 * chunk), chunk):
+                yield xs[t0:t0 + chunk]
+
+        sdist.sharded_scan(warm_chunks(), ops, K, ctx_len, WIDTH)  # warm-up (NCCL channels, scratch, lists)
         ops.scan = engine.TopActivationScan(lo, hi, n_top, ctx_len, dev)
         barrier()
         e0.record()
@@ -302,6 +306,8 @@ def run_gpu(args):
         scan = {"tokens": args.scan_tokens, "features": WIDTH, "n_top": n_top, "ctx_len": ctx_len, "ms": sms,
                 "tokens_per_s": args.scan_tokens / (sms * 1e-3), "sharding": f"features/{world}", "exact_topk_mask": True,
                 "filled_features": int((res.top_win[:, 0] >= 0).sum().item()),
+                "schedule": "sequential (phase timing)" if args.scan_phases else
+                            "two streams: GEMM of chunk c+1 overlaps exchange/refine/list update of chunk c",
                 "phase_ms_rank0": {k_: round(v_, 2) for k_, v_ in phases.items()} or None}
 
     cpu = None
@@ -335,7 +341,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scan-tokens", type=int, default=262144,
+    ap.add_argument("--scan-tokens", type=int, default=1048576,
                     help="tokens of the feature-sharded top-activation scan (BASELINE C3: 1048576, C4: 4194304)")
     ap.add_argument("--scan-top", type=int, default=20, help="examples kept per feature (C3: 5, C4: 20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -270,7 +270,7 @@ static RefineWs refine_ws(long long T, long long d, long long N, int k, int marg
     return at;
   };
   w.status = take(256, 256);
-  w.flag_rows = take(256, 256);
+  w.flag_rows = take((size_t)(T > 64 ? T : 64) * 4, 256);   // every row of the call can be flagged
   w.mvals = take((size_t)T * K2 * 4, 256);
   w.midx = take((size_t)T * K2 * 8, 256);
   w.dense = take(refine_fallback_bytes(N), 256);
@@ -409,7 +409,7 @@ int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void*
   if (rc) return rc;
   if (status_out != nullptr)
     SAEB_CHECK_CUDA(cudaMemcpyAsync(status_out, status, sizeof(int), cudaMemcpyDeviceToDevice, st));
-  g_launches += 5;
+  g_launches += 6;
   return 0;
 }
 

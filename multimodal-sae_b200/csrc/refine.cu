@@ -9,7 +9,9 @@
 // covers the accumulation (256 block additions of <= 2^-23 relative error each, doubled).  Hence
 //   * the true k-th value is at least L = k-th largest of (a_j - eps_j);
 //   * only candidates with a_j + eps_j >= L can belong to the true TopK; they are re-evaluated EXACTLY here
-//     (fp32 dot product with the fp32 W_enc row + folded bias), and the final TopK is taken over the exact values;
+//     (fp32 dot product with the fp32 W_enc row + folded bias), and the final TopK is taken over the exact values.
+//     Two stages: first the k best by a_j; the smallest of their exact values replaces L (it is a lower bound of
+//     the k-th value that does not sit a full eps below it), which roughly halves the rest of the work;
 //   * a non-candidate has a <= a_last (the smallest kept approximation); if a_last + c_eps*||x||*max_j||w_j|| >= L
 //     the candidate list might be too short: the row is FLAGGED and recomputed by the exact dense kernels below.
 // Output values are fp32-exact like the reference's (sae/sae.py:172-181), the index set is the reference's up to
@@ -19,7 +21,8 @@
 namespace saeb {
 
 constexpr int RF_THREADS = 256;
-constexpr int RF_MAX_FLAG = 64;   // rows the dense fallback can absorb per call
+constexpr int RF_MAX_FLAG = 64;   // flagged rows handled by the wide (all-SM) fallback; further rows take the
+                                  // one-block-per-row overflow path, so any number of flagged rows stays exact
 
 template <typename XT>
 __global__ void __launch_bounds__(RF_THREADS)
@@ -81,18 +84,9 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict_
   float L = (nv >= k) ? s_L : 0.f;
   // feature-sharded use: a lower bound of the GLOBAL k-th value (k-th largest lower bound over all shards)
   if (ext_lower != nullptr) L = fmaxf(L, ext_lower[t]);
-  // list possibly too short?  (only when the list is full: otherwise every positive latent is already in it)
-  if (tid == 0 && nv == K2) {
-    const float a_last = a[K2 - 1];
-    if (a_last + 1.001f * (xn * dmax + xdn * wmax) + c_eps * xn * wmax >= L) {
-      const int slot = atomicAdd(&status[0], 1);
-      if (slot < RF_MAX_FLAG) flag_rows[slot] = (int)t;
-    }
-  }
-  // exact re-evaluation of every candidate that can still be in the TopK
+  // exact value of candidate j (all lanes of the calling warp): fp32 dot product with the fp32 W_enc row + bias
   const bool vec = (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
-  for (int j = warp; j < K2; j += nthr >> 5) {
-    if (!(ub[j] >= L) || !(a[j] > 0.f)) continue;
+  auto evaluate = [&](int j) {
     const int fj = f[j];
     float val;
     if (fj == clamp_feature) {
@@ -135,7 +129,34 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict_
       val = acc + bias[fj];
     }
     if (lane == 0) ex[j] = (val > 0.f) ? val : -1.f;
+  };
+  const int nwarps = nthr >> 5;
+  // stage A: the k best candidates by approximate value (the merged list is sorted by a, descending)
+  for (int j = warp; j < k; j += nwarps)
+    if (ub[j] >= L && a[j] > 0.f) evaluate(j);
+  __syncthreads();
+  // k exact values are now known: their smallest is a far tighter lower bound of the k-th value than L (which sits a
+  // full eps below it), so fewer of the remaining candidates can still reach the TopK
+  if (warp == 0) {
+    float mn = INFINITY;
+    for (int j = lane; j < k; j += 32) mn = fminf(mn, ex[j]);   // -1 = not evaluated or not positive
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if (lane == 0) s_L = (mn > L) ? mn : L;
   }
+  __syncthreads();
+  L = s_L;
+  // list possibly too short?  (only when the list is full: otherwise every positive latent is already in it)
+  if (tid == 0 && nv == K2) {
+    const float a_last = a[K2 - 1];
+    if (a_last + 1.001f * (xn * dmax + xdn * wmax) + c_eps * xn * wmax >= L) {
+      const int slot = atomicAdd(&status[0], 1);
+      flag_rows[slot] = (int)t;   // capacity = number of rows of the call
+    }
+  }
+  // stage B: every remaining candidate that can still be in the TopK
+  for (int j = k + warp; j < K2; j += nwarps)
+    if (ub[j] >= L && a[j] > 0.f) evaluate(j);
   __syncthreads();
   // final TopK over the exact values: rank by (value desc, feature id asc)
   int my_pos = 0;
@@ -253,20 +274,11 @@ exact_rows_kernel(const XT* __restrict__ x, long long ld_x, const float* __restr
   }
 }
 
-// TopK of dense non-negative rows (value desc, index asc).  `row_map` (optional) redirects output rows; rows beyond
-// `*n_rows_dev` (optional device count) exit.  One block per row.  Also serves Sae.select_topk on dense tensors.
-__global__ void __launch_bounds__(1024)
-dense_topk_kernel(const float* __restrict__ dense, long long ld, long long N, int k, const int* __restrict__ n_rows_dev,
-                  int max_rows, const int* __restrict__ row_map, float* __restrict__ out_vals,
-                  long long* __restrict__ out_idx) {
-  extern __shared__ uint2 dsm[];   // [kp2] selected (value bits, index)
+// TopK of one dense non-negative row (value desc, index asc) by a whole block; `dsm` = kp2 uint2 of shared memory.
+__device__ __forceinline__ void dense_topk_block(const float* row, long long N, int k, uint2* dsm, long long orow,
+                                                 float* __restrict__ out_vals, long long* __restrict__ out_idx) {
   __shared__ int s_red[32];
   __shared__ int s_count;
-  __shared__ uint32_t s_idx_cut;
-  const int slot = blockIdx.x;
-  if (n_rows_dev != nullptr && slot >= min(*n_rows_dev, max_rows)) return;
-  const long long orow = row_map ? row_map[slot] : slot;
-  const float* row = dense + (long long)slot * ld;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   auto block_sum = [&](int v) {
 #pragma unroll
@@ -309,6 +321,7 @@ dense_topk_kernel(const float* __restrict__ dense, long long ld, long long N, in
     }
     idx_cut = p2;
   }
+  __syncthreads();
   if (tid == 0) s_count = 0;
   for (int i = tid; i < kp2; i += blockDim.x) dsm[i] = make_uint2(0u, 0xffffffffu);
   __syncthreads();
@@ -339,6 +352,58 @@ dense_topk_kernel(const float* __restrict__ dense, long long ld, long long N, in
   for (int i = tid; i < k; i += blockDim.x) {
     out_vals[orow * k + i] = __uint_as_float(dsm[i].x);
     out_idx[orow * k + i] = (long long)dsm[i].y;
+  }
+  __syncthreads();
+}
+
+// TopK of dense non-negative rows.  `row_map` (optional) redirects output rows; rows beyond `*n_rows_dev` (optional
+// device count) exit.  One block per row.  Also serves Sae.select_topk on dense tensors.
+__global__ void __launch_bounds__(1024)
+dense_topk_kernel(const float* __restrict__ dense, long long ld, long long N, int k, const int* __restrict__ n_rows_dev,
+                  int max_rows, const int* __restrict__ row_map, float* __restrict__ out_vals,
+                  long long* __restrict__ out_idx) {
+  extern __shared__ uint2 dsm[];   // [kp2] selected (value bits, index)
+  const int slot = blockIdx.x;
+  if (n_rows_dev != nullptr && slot >= min(*n_rows_dev, max_rows)) return;
+  const long long orow = row_map ? row_map[slot] : slot;
+  dense_topk_block(dense + (long long)slot * ld, N, k, dsm, orow, out_vals, out_idx);
+}
+
+// Flagged rows beyond the first RF_MAX_FLAG (degenerate inputs: massive ties, k close to N): block b walks the slots
+// RF_MAX_FLAG + b, RF_MAX_FLAG + b + gridDim.x, ...; per slot it writes the exact dense row into its private scratch
+// row and takes the TopK from it.  Exits at once in the normal case.
+template <typename XT>
+__global__ void __launch_bounds__(1024)
+overflow_rows_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict__ W, long long d, long long N,
+                     const float* __restrict__ bias, const int* __restrict__ status, const int* __restrict__ flag_rows,
+                     long long clamp_feature, float clamp_value, float* dense, int k, float* __restrict__ out_vals,
+                     long long* __restrict__ out_idx) {
+  extern __shared__ uint2 osm[];   // [kp2] uint2 | [d] float
+  const int nflag = status[0];
+  if (nflag <= RF_MAX_FLAG) return;
+  int kp2 = 2;
+  while (kp2 < k) kp2 <<= 1;
+  float* xs = reinterpret_cast<float*>(osm + kp2);
+  float* my = dense + (long long)blockIdx.x * N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int slot = RF_MAX_FLAG + blockIdx.x; slot < nflag; slot += gridDim.x) {
+    const long long t = flag_rows[slot];
+    for (long long i = threadIdx.x; i < d; i += blockDim.x) xs[i] = (float)x[t * ld_x + i];
+    __syncthreads();
+    for (long long n = warp; n < N; n += nw) {
+      const float* wr = W + n * d;
+      float acc = 0.f;
+      for (long long i = lane; i < d; i += 32) acc = fmaf(wr[i], xs[i], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        float v = acc + bias[n];
+        if (n == clamp_feature) v = clamp_value;
+        my[n] = fmaxf(v, 0.f);
+      }
+    }
+    __syncthreads();
+    dense_topk_block(my, N, k, osm, t, out_vals, out_idx);
   }
 }
 
@@ -377,6 +442,12 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
   while (kp2 < k) kp2 <<= 1;
   dense_topk_kernel<<<RF_MAX_FLAG, 1024, (size_t)kp2 * sizeof(uint2), stream>>>(
       dense_scratch, N, N, k, status, RF_MAX_FLAG, flag_rows, out_vals, out_idx);
+  SAEB_CHECK_CUDA(cudaGetLastError());
+  auto ok = overflow_rows_kernel<XT>;
+  const size_t osmem = (size_t)kp2 * sizeof(uint2) + (size_t)d * sizeof(float);
+  SAEB_CHECK_CUDA(cudaFuncSetAttribute(ok, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osmem));
+  ok<<<RF_MAX_FLAG, 1024, osmem, stream>>>(x, ld_x, W, d, N, bias, status, flag_rows, clamp_feature, clamp_value,
+                                           dense_scratch, k, out_vals, out_idx);
   SAEB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -43,7 +43,11 @@ class EngineOps:
                              `ext_L` [Tc] (optional) = lower bound of each token's GLOBAL k-th value, lets the shard skip
                              the exact re-evaluation of latents that cannot be in the global TopK
       kth_of_gathered, scan_update, scan_finalize
+    `slot` (0/1) selects one of two private scratch sets, so that the GEMM of chunk c+1 can be in flight on
+    `stream_gemm` while chunk c is exchanged / refined / scanned on `stream_aux` (`pipelined = True`).
     """
+
+    pipelined = True
 
     def __init__(self, W_enc_shard, b_enc_shard, b_dec, feat_lo, feat_hi, n_top, ctx_len, device, planes=3,
                  bucket_cap=256):
@@ -53,47 +57,54 @@ class EngineOps:
         self.enc = engine.PackedEncoder.pack(W_enc_shard, b_enc_shard, b_dec, planes)
         self.feat_lo, self.feat_hi = feat_lo, feat_hi
         self.scan = engine.TopActivationScan(feat_lo, feat_hi, n_top, ctx_len, device, bucket_cap=bucket_cap)
-        self._x = self._k = self._prep = self._ws = None
+        self._x, self._k, self._prep, self._ws = [None, None], [0, 0], [None, None], [None, None]
+        self._lb, self._cached = [None, None], [None, None]
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        self.stream_gemm = torch.cuda.Stream(device)
+        self.stream_aux = torch.cuda.Stream(device)
 
     # ---- mode 3: GEMM -> bounds -> (exchange) -> refinement restricted by the global lower bound
-    def local_bounds(self, x, k):
+    def _scratch(self, store, slot, nbytes, dev):
+        """per-slot scratch that is never handed back to the allocator while the scan runs (it is shared between the
+        two streams, ordered by events)"""
+        if store[slot] is None or store[slot].numel() < nbytes:
+            store[slot] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        return store[slot]
+
+    def local_bounds(self, x, k, slot=0):
         eng, L = self.engine, self._capi.lib()
         enc = self.enc
         x2 = eng._as_2d(x, enc.d_in)
-        self._x, self._k = x2, k
+        self._x[slot], self._k[slot] = x2, k
         T = x2.shape[0]
         if enc.planes != 3:
             vals, idx, _ = eng.encode_topk(x2, enc, k)
-            self._cached = (vals, idx + self.feat_lo)
+            self._cached[slot] = (vals, idx + self.feat_lo)
             return vals
         dev = x2.device
         with torch.cuda.device(dev):
-            need = L.saeb_prep_bytes(T, enc.d_in)
-            if self._prep is None or self._prep.numel() < need:
-                self._prep = torch.empty(need, dtype=torch.uint8, device=dev)
-            need = L.saeb_candidates_workspace_bytes(T, enc.d_in, enc.num_latents, k, 0)
-            if self._ws is None or self._ws.numel() < need:
-                self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            prep = self._scratch(self._prep, slot, L.saeb_prep_bytes(T, enc.d_in), dev)
+            ws = self._scratch(self._ws, slot, L.saeb_candidates_workspace_bytes(T, enc.d_in, enc.num_latents, k, 0),
+                               dev)
+            lb = self._scratch(self._lb, slot, T * k * 4, dev)[: T * k * 4].view(torch.float32).view(T, k)
             st = torch.cuda.current_stream().cuda_stream
             code = eng._code(x2)
             ldx = x2.stride(0) if T > 1 else enc.d_in
-            self._capi.check(L.saeb_prep_activations(x2.data_ptr(), code, T, ldx, enc.d_in, self._prep.data_ptr(), st),
+            self._capi.check(L.saeb_prep_activations(x2.data_ptr(), code, T, ldx, enc.d_in, prep.data_ptr(), st),
                              "saeb_prep_activations")
-            self._capi.check(L.saeb_encode_candidates(self._prep.data_ptr(), T, 0, T, enc.blob.data_ptr(), enc.d_in,
-                                                      enc.num_latents, k, 0, -1, 0.0, self._ws.data_ptr(),
-                                                      self._ws.numel(), st), "saeb_encode_candidates")
-            lb = torch.empty((T, k), dtype=torch.float32, device=dev)
-            self._capi.check(L.saeb_candidate_bounds(self._prep.data_ptr(), T, 0, T, enc.blob.data_ptr(), code, enc.d_in,
-                                                     enc.num_latents, k, 0, -1, lb.data_ptr(), self._ws.data_ptr(),
-                                                     self._ws.numel(), st), "saeb_candidate_bounds")
+            self._capi.check(L.saeb_encode_candidates(prep.data_ptr(), T, 0, T, enc.blob.data_ptr(), enc.d_in,
+                                                      enc.num_latents, k, 0, -1, 0.0, ws.data_ptr(), ws.numel(), st),
+                             "saeb_encode_candidates")
+            self._capi.check(L.saeb_candidate_bounds(prep.data_ptr(), T, 0, T, enc.blob.data_ptr(), code, enc.d_in,
+                                                     enc.num_latents, k, 0, -1, lb.data_ptr(), ws.data_ptr(),
+                                                     ws.numel(), st), "saeb_candidate_bounds")
         return lb
 
-    def local_topk(self, ext_L=None):
+    def local_topk(self, ext_L=None, slot=0):
         eng, L = self.engine, self._capi.lib()
-        enc, x2, k = self.enc, self._x, self._k
+        enc, x2, k = self.enc, self._x[slot], self._k[slot]
         if enc.planes != 3:
-            return self._cached
+            return self._cached[slot]
         T = x2.shape[0]
         dev = x2.device
         vals = torch.empty((T, k), dtype=torch.float32, device=dev)
@@ -101,10 +112,10 @@ class EngineOps:
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream().cuda_stream
             self._capi.check(L.saeb_refine_candidates(
-                x2.data_ptr(), eng._code(x2), x2.stride(0) if T > 1 else enc.d_in, self._prep.data_ptr(), T, 0, T,
+                x2.data_ptr(), eng._code(x2), x2.stride(0) if T > 1 else enc.d_in, self._prep[slot].data_ptr(), T, 0, T,
                 enc.blob.data_ptr(), enc.W_enc.data_ptr(), enc.d_in, enc.num_latents, k, 0, -1, 0.0,
                 None if ext_L is None else ext_L.data_ptr(), 1, vals.data_ptr(), idx.data_ptr(), self.status.data_ptr(),
-                self._ws.data_ptr(), self._ws.numel(), st), "saeb_refine_candidates")
+                self._ws[slot].data_ptr(), self._ws[slot].numel(), st), "saeb_refine_candidates")
         return vals, idx + self.feat_lo
 
     def kth_of_gathered(self, gathered):
@@ -156,28 +167,34 @@ class _PhaseTimer:
 
 
 def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_latents: int, *, exact: bool = True,
-                 group=None, phase_times: Optional[dict] = None) -> ScanResult:
+                 group=None, phase_times: Optional[dict] = None, pipelined: Optional[bool] = None) -> ScanResult:
     """Feature-sharded scan.  `chunks` yields the SAME token chunks ([Tc, d], Tc a multiple of ctx_len) on every rank.
 
     exact=True, per chunk: (1) every shard computes lower bounds of its k best latents per token and all-gathers
     them -> per-token lower bound of the global k-th value; (2) the shard evaluates exactly only the latents that can
     still reach it and all-gathers its exact local top-k values -> the per-token global k-th value, which filters what
     enters the per-feature lists (the cache keeps a latent only if it is in the token's global TopK,
-    features/cache.py:210-218).  Both exchanges are [Tc, k] fp32 per rank (256 B/token/rank at k = 64)."""
+    features/cache.py:210-218).  Both exchanges are [Tc, k] fp32 per rank (256 B/token/rank at k = 64).
+
+    With `ops.pipelined` (the CUDA ops) the loop is software-pipelined over two streams: step (1)'s GEMM of chunk c+1
+    runs on `ops.stream_gemm` while the exchanges, the refinement and the list update of chunk c run on
+    `ops.stream_aux`, so the collectives' latency is hidden behind tensor-core work.  `phase_times` (diagnostic
+    per-phase CUDA-event timing) forces the sequential schedule."""
     distributed = dist.is_available() and dist.is_initialized()
     world = dist.get_world_size(group) if distributed else 1
     k_local = min(k, ops.feat_hi - ops.feat_lo)
-    window_base = 0
+    if pipelined is None:
+        pipelined = bool(getattr(ops, "pipelined", False)) and phase_times is None
     tm = _PhaseTimer(phase_times is not None and torch.cuda.is_available())
     tm.mark("start")
-    for x in chunks:
-        lb = ops.local_bounds(x, k_local)
-        tm.mark("gemm+bounds")
+
+    def finish(x, lb, slot, window_base):
+        """exchange 1 -> restricted exact local TopK -> exchange 2 -> per-feature list update, for one chunk"""
         ext_L = tok_thr = None
         if exact and world > 1:
             ext_L = _kth(ops, _gather_stack(lb, group), k, k_local)
             tm.mark("exchange1")
-        vals, idx = ops.local_topk(ext_L)
+        vals, idx = ops.local_topk(ext_L, slot) if slot is not None else ops.local_topk(ext_L)
         tm.mark("refine")
         vals2 = vals.reshape(-1, k_local)
         if exact and world > 1:
@@ -185,7 +202,50 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
             tm.mark("exchange2")
         ops.scan_update(vals2, idx.reshape(-1, k_local), window_base, tok_thr)
         tm.mark("scan_update")
-        window_base += vals2.shape[0] // ctx_len
+        return vals2.shape[0] // ctx_len
+
+    window_base = 0
+    if not pipelined:
+        for x in chunks:
+            lb = ops.local_bounds(x, k_local)
+            tm.mark("gemm+bounds")
+            window_base += finish(x, lb, None, window_base)
+    else:
+        sg, sa = ops.stream_gemm, ops.stream_aux
+        cur = torch.cuda.current_stream()
+        sa.wait_stream(cur)
+        slot_free = [None, None]   # event: the chunk that last used this slot's scratch has left stream_aux
+        prev = None
+
+        def drain(item):
+            x, lb, ready, slot, base = item
+            with torch.cuda.stream(sa):
+                sa.wait_event(ready)
+                n_win = finish(x, lb, slot, base)
+                slot_free[slot] = torch.cuda.Event()
+                slot_free[slot].record(sa)
+            return n_win
+
+        for c, x in enumerate(chunks):
+            slot = c & 1
+            x.record_stream(sg)
+            x.record_stream(sa)
+            with torch.cuda.stream(sg):
+                sg.wait_stream(cur)   # whatever produced this chunk on the caller's stream
+                if slot_free[slot] is not None:
+                    sg.wait_event(slot_free[slot])
+                lb = ops.local_bounds(x, k_local, slot)
+                ready = torch.cuda.Event()
+                ready.record(sg)
+            n_tok = x.shape[0] if x.dim() == 2 else x.numel() // x.shape[-1]
+            if prev is not None:
+                drain(prev)
+            prev = (x, lb, ready, slot, window_base)
+            window_base += n_tok // ctx_len
+        if prev is not None:
+            drain(prev)
+        cur.wait_stream(sg)
+        cur.wait_stream(sa)
     top_vals, top_win = ops.scan_finalize()
     tm.mark("scan_finalize")
     if phase_times is not None:

@@ -195,6 +195,44 @@ def test_refine_dense_fallback_rows():
     _assert_topk_parity(p, x.float(), acts, idx)
 
 
+def test_refine_fallback_overflow_rows():
+    """More flagged rows than the wide fallback absorbs (64): the remaining ones take the one-block-per-row overflow
+    path and must be just as exact."""
+    from saeb200 import engine
+
+    p = O.init_params(128, 2048, 16, seed=45)
+    x = torch.randn(400, 128, generator=torch.Generator().manual_seed(46)).to(torch.bfloat16)
+    sae = _sae_from_params(p, 3)
+    acts, idx, _ = engine.encode_topk(x.to(DEV), sae.packed_encoder(), 16, refine_margin=1)
+    n_flag = int(engine.encode_topk.last_status.item())
+    assert n_flag > 64, n_flag
+    _assert_topk_parity(p, x.float(), acts, idx)
+
+
+def test_duplicated_latents_exact_ties():
+    """Every latent exists twice (identical encoder rows and biases): each row's k-th value is an exact tie.  The
+    values must match the oracle everywhere, the index sets wherever the oracle's own choice is not a tie."""
+    base = O.init_params(256, 1024, 8, seed=47)
+    W = torch.cat([base.W_enc, base.W_enc], 0)
+    p = O.SaeParams(W_enc=W, b_enc=torch.cat([base.b_enc, base.b_enc]), W_dec=torch.cat([base.W_dec, base.W_dec], 0),
+                    b_dec=base.b_dec, k=9)
+    x = torch.randn(200, 256, generator=torch.Generator().manual_seed(48)).to(torch.bfloat16)
+    sae = _sae_from_params(p, 3)
+    enc = sae.encode(x.to(DEV))
+    ref = O.encode(p, x.float())
+    gv = enc.top_acts.cpu().sort(-1, descending=True).values
+    rv = ref.top_acts.sort(-1, descending=True).values
+    np.testing.assert_allclose(gv.numpy(), rv.numpy(), rtol=1e-5, atol=1e-6)
+    # ties broken towards the smaller feature id: of a duplicated pair (j, j + 1024) the copy j is taken first
+    gi = enc.top_indices.cpu()
+    hi_half = gi >= 1024
+    assert bool(((gi % 1024).sort(-1).values[:, 1:] >= (gi % 1024).sort(-1).values[:, :-1]).all())
+    for r in range(gi.shape[0]):
+        ids = set(gi[r].tolist())
+        for j in gi[r][hi_half[r]].tolist():
+            assert (j - 1024) in ids
+
+
 def test_refine_values_are_fp32_exact():
     """In refine mode the returned activations are fp32 dot products against the fp32 weights: they agree with the
     oracle to fp32 summation noise (1e-5 relative), far inside the 1e-3 bar."""
