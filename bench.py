@@ -163,6 +163,9 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # the scan's per-chunk all-gathers run beside the persistent GEMM grid on the few SMs it leaves free
+        # (saeb200.dist.EngineOps.reserve_sms = 4): keep NCCL's kernels that small
+        os.environ.setdefault("NCCL_MAX_CTAS", "4")
         dist.init_process_group("nccl", device_id=dev)
     L = _capi.lib()
     _capi.check(L.saeb_set_option(b"profile", 1), "set_option")
@@ -280,10 +283,11 @@ def run_gpu(args):
     # ---- feature-sharded top-activation scan (bounded token count; one all-gather of top lists at the end)
     scan = None
     if args.scan_tokens > 0:
-        ctx_len, n_top, chunk = 64, args.scan_top, 37888  # four single-wave launches per exchange round
+        ctx_len, n_top = 64, args.scan_top
         lo, hi = sdist.shard_range(WIDTH, world, rank)
         ops = sdist.EngineOps(sae.encoder.weight.data[lo:hi], sae.encoder.bias.data[lo:hi], sae.b_dec.data, lo, hi,
                               n_top, ctx_len, dev, planes=args.planes)
+        chunk = ops.chunk_tokens(world)  # four single-wave GEMM launches per exchange round
         xs = synth.make_activations(args.scan_tokens, D_IN, dev, seed=99)  # same tokens on every rank
 
         def chunks():
@@ -305,6 +309,7 @@ def run_gpu(args):
         sms = max_over_ranks(e0.elapsed_time(e1))
         scan = {"tokens": args.scan_tokens, "features": WIDTH, "n_top": n_top, "ctx_len": ctx_len, "ms": sms,
                 "tokens_per_s": args.scan_tokens / (sms * 1e-3), "sharding": f"features/{world}", "exact_topk_mask": True,
+                "chunk_tokens": chunk,
                 "filled_features": int((res.top_win[:, 0] >= 0).sum().item()),
                 "schedule": "sequential (phase timing)" if args.scan_phases else
                             "two streams: GEMM of chunk c+1 overlaps exchange/refine/list update of chunk c",

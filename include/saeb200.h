@@ -39,7 +39,9 @@ long long saeb_launch_count(void);
  * tiles.  Results are identical; only throughput differs.  "profile": see saeb_profile_last_encode_ms.  "splits": feature-range splits per token tile
  * (0 = automatic).  "chunking": 1 (default) = long calls run as one launch per wave of token tiles (keeps the live
  * activation tiles L2-resident).  "persist_a": 1 (default) = pin each launch's activation rows in the persisting part
- * of L2.  "l2_hints", "debug_tiles": diagnostics. */
+ * of L2.  "reserve_sms": SMs the persistent GEMM grid leaves free (default 0) so that kernels of another stream --
+ * the collectives of the feature-sharded scan -- have somewhere to run while a GEMM launch is in flight.
+ * "l2_hints", "debug_tiles": diagnostics. */
 int saeb_set_option(const char* name, int value);
 /* With option "profile" = 1 the library brackets the fused encode kernel (main kernel only) with CUDA events on the
  * launching stream; this returns the duration in ms of the most recent one (synchronises on it), < 0 if none. */

@@ -35,6 +35,7 @@ int encode_gemm_launch(const void* x_planes, int ap, long long T, long long ld_x
 int encode_merge_launch(long long T, long long N, int k, float* out_vals, long long* out_idx, void* workspace,
                         size_t workspace_bytes, cudaStream_t stream);
 int set_chunking(int v);
+int set_reserve_sms(int v);
 int pack_weights_f16_launch(const float* W_enc, const float* b_enc, const float* b_dec, long long N, long long d,
                             long long d_pad, void* w_plane, float* bias, float* wnorm, float* dnorm, float* trailer,
                             cudaStream_t stream);
@@ -121,6 +122,7 @@ int saeb_set_option(const char* name, int value) {
   if (strcmp(name, "stats") == 0) return set_stats(value);
   if (strcmp(name, "persist_a") == 0) return set_persist_a(value);
   if (strcmp(name, "chunking") == 0) return set_chunking(value);
+  if (strcmp(name, "reserve_sms") == 0) return set_reserve_sms(value);
   if (strcmp(name, "refine_margin") == 0) {
     g_default_margin = value;
     return 0;

@@ -733,6 +733,15 @@ struct EncodePlan {
   size_t total_bytes;
 };
 static int g_chunking = 1;   // 0: one launch for the whole call
+// SMs left free by the persistent GEMM grid.  The feature-sharded scan runs its collectives, refinement and list
+// update on a second stream while the next chunk's GEMM is in flight; a grid that owns every SM would make those
+// kernels (NCCL's in particular: too many registers to co-reside) wait for a launch boundary and then displace GEMM
+// CTAs, which doubles that launch.
+static int g_reserve_sms = 0;
+int set_reserve_sms(int v) {
+  g_reserve_sms = v < 0 ? 0 : v;
+  return 0;
+}
 int set_chunking(int v) {
   g_chunking = v;
   return 0;
@@ -742,7 +751,8 @@ static bool make_plan(EncodePlan& p, long long T, long long N, int k, int pair) 
   p.pair = pair;
   p.cap = cap_for_k(k);
   p.num_n_tiles = (int)((N + BN - 1) / BN);
-  const int sms = num_sms() > 0 ? num_sms() : 148;
+  int sms = num_sms() > 0 ? num_sms() : 148;
+  if (g_reserve_sms > 0 && sms - g_reserve_sms >= 2 * pair) sms -= g_reserve_sms;
   const int clusters = sms / pair;
   const long long tile_rows = (long long)BM * pair;
   long long rows_full = (long long)(clusters / 2 > 0 ? clusters / 2 : 1) * tile_rows;

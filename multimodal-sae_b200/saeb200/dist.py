@@ -61,7 +61,27 @@ class EngineOps:
         self._lb, self._cached = [None, None], [None, None]
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         self.stream_gemm = torch.cuda.Stream(device)
-        self.stream_aux = torch.cuda.Stream(device)
+        self.stream_aux = torch.cuda.Stream(device, priority=-1)   # exchange / refine / list update: first pick
+        # of the SMs the GEMM grid leaves free (`reserve_sms`), see begin_pipeline
+        self.reserve_sms = 4
+
+    def begin_pipeline(self, world: int):
+        """The persistent GEMM grid normally owns every SM; while the scan is pipelined it leaves a few free so that
+        NCCL's kernels (which cannot co-reside with a GEMM CTA) never have to displace one.  Pair this with
+        NCCL_MAX_CTAS <= reserve_sms in the environment (bench.py does)."""
+        if world > 1:
+            self._capi.check(self._capi.lib().saeb_set_option(b"reserve_sms", self.reserve_sms), "set_option")
+
+    def chunk_tokens(self, world: int, waves: int = 4) -> int:
+        """Tokens per scan chunk = `waves` full single-wave GEMM launches (256-row tiles on half of the CTA pairs the
+        grid may use), so that no launch runs partly empty."""
+        sms = int(self._capi.lib().saeb_query(b"num_sms")) or 148
+        if world > 1:
+            sms -= self.reserve_sms
+        return waves * 256 * max(1, (sms // 2) // 2)
+
+    def end_pipeline(self):
+        self._capi.check(self._capi.lib().saeb_set_option(b"reserve_sms", 0), "set_option")
 
     # ---- mode 3: GEMM -> bounds -> (exchange) -> refinement restricted by the global lower bound
     def _scratch(self, store, slot, nbytes, dev):
@@ -213,39 +233,12 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
     else:
         sg, sa = ops.stream_gemm, ops.stream_aux
         cur = torch.cuda.current_stream()
-        sa.wait_stream(cur)
-        slot_free = [None, None]   # event: the chunk that last used this slot's scratch has left stream_aux
-        prev = None
+        ops.begin_pipeline(world)
+        try:
+            window_base = _pipelined_loop(chunks, ops, finish, k_local, ctx_len, sg, sa, cur)
+        finally:
+            ops.end_pipeline()
 
-        def drain(item):
-            x, lb, ready, slot, base = item
-            with torch.cuda.stream(sa):
-                sa.wait_event(ready)
-                n_win = finish(x, lb, slot, base)
-                slot_free[slot] = torch.cuda.Event()
-                slot_free[slot].record(sa)
-            return n_win
-
-        for c, x in enumerate(chunks):
-            slot = c & 1
-            x.record_stream(sg)
-            x.record_stream(sa)
-            with torch.cuda.stream(sg):
-                sg.wait_stream(cur)   # whatever produced this chunk on the caller's stream
-                if slot_free[slot] is not None:
-                    sg.wait_event(slot_free[slot])
-                lb = ops.local_bounds(x, k_local, slot)
-                ready = torch.cuda.Event()
-                ready.record(sg)
-            n_tok = x.shape[0] if x.dim() == 2 else x.numel() // x.shape[-1]
-            if prev is not None:
-                drain(prev)
-            prev = (x, lb, ready, slot, window_base)
-            window_base += n_tok // ctx_len
-        if prev is not None:
-            drain(prev)
-        cur.wait_stream(sg)
-        cur.wait_stream(sa)
     top_vals, top_win = ops.scan_finalize()
     tm.mark("scan_finalize")
     if phase_times is not None:
@@ -256,6 +249,44 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
         top_vals = torch.cat(_all_gather_cat(top_vals, group, sizes), 0)   # the single end-of-job all-gather
         top_win = torch.cat(_all_gather_cat(top_win, group, sizes), 0)
     return ScanResult(top_vals, top_win)
+
+
+def _pipelined_loop(chunks, ops, finish, k_local, ctx_len, sg, sa, cur) -> int:
+    """two-stream software pipeline of sharded_scan; returns the number of windows consumed"""
+    sa.wait_stream(cur)
+    window_base = 0
+    slot_free = [None, None]   # event: the chunk that last used this slot's scratch has left stream_aux
+    prev = None
+
+    def drain(item):
+        x, lb, ready, slot, base = item
+        with torch.cuda.stream(sa):
+            sa.wait_event(ready)
+            finish(x, lb, slot, base)
+            slot_free[slot] = torch.cuda.Event()
+            slot_free[slot].record(sa)
+
+    for c, x in enumerate(chunks):
+        slot = c & 1
+        x.record_stream(sg)
+        x.record_stream(sa)
+        with torch.cuda.stream(sg):
+            sg.wait_stream(cur)   # whatever produced this chunk on the caller's stream
+            if slot_free[slot] is not None:
+                sg.wait_event(slot_free[slot])
+            lb = ops.local_bounds(x, k_local, slot)
+            ready = torch.cuda.Event()
+            ready.record(sg)
+        n_tok = x.shape[0] if x.dim() == 2 else x.numel() // x.shape[-1]
+        if prev is not None:
+            drain(prev)
+        prev = (x, lb, ready, slot, window_base)
+        window_base += n_tok // ctx_len
+    if prev is not None:
+        drain(prev)
+    cur.wait_stream(sg)
+    cur.wait_stream(sa)
+    return window_base
 
 
 def _gather_stack(t: torch.Tensor, group) -> torch.Tensor:
