@@ -21,17 +21,18 @@ class OracleOps:
         self.p, self.feat_lo, self.feat_hi, self.n_top, self.ctx_len = p, lo, hi, n_top, ctx_len
         self.sub = O.SaeParams(p.W_enc[lo:hi], p.b_enc[lo:hi], p.W_dec[lo:hi], p.b_dec, p.k)
         self.acts, self.idx, self.thr = [], [], []
+        self._v, self._i = {}, {}
 
-    def local_bounds(self, x, k):
+    def local_bounds(self, x, k, slot=0):
         pa = O.pre_acts(self.sub, x.float())
-        self._v, self._i = pa.topk(k, sorted=True)
-        return self._v * (1 - 1e-3)   # a lower bound, like the engine's a_j - eps_j
+        self._v[slot], self._i[slot] = pa.topk(k, sorted=True)
+        return self._v[slot] * (1 - 1e-3)   # a lower bound, like the engine's a_j - eps_j
 
-    def local_topk(self, ext_L=None):
-        v = self._v
+    def local_topk(self, ext_L=None, slot=0):
+        v = self._v[slot]
         if ext_L is not None:   # latents that cannot reach the global k-th value are not evaluated (reported as 0)
             v = torch.where(v >= ext_L[:, None], v, torch.zeros_like(v))
-        return v, self._i + self.feat_lo
+        return v, self._i[slot] + self.feat_lo
 
     def kth_of_gathered(self, gathered):
         R, T, k = gathered.shape
@@ -49,7 +50,7 @@ class OracleOps:
         return torch.from_numpy(s), torch.from_numpy(w)
 
 
-def _worker(rank, world, port, exact, out_dir):
+def _worker(rank, world, port, exact, pipelined, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, os.path.join(root, "multimodal-sae_b200"))
@@ -63,8 +64,9 @@ def _worker(rank, world, port, exact, out_dir):
         x = torch.randn(ctx * 12, d, generator=torch.Generator().manual_seed(78)).to(torch.bfloat16)
         lo, hi = sdist.shard_range(N, world, rank)
         ops = OracleOps(p, lo, hi, n_top, ctx)
-        chunks = [x[i:i + ctx * 4] for i in range(0, x.shape[0], ctx * 4)]
-        res = sdist.sharded_scan(chunks, ops, k, ctx, N, exact=exact)
+        step = ctx * (2 if pipelined else 4)   # 6 / 3 chunks
+        chunks = [x[i:i + step] for i in range(0, x.shape[0], step)]
+        res = sdist.sharded_scan(chunks, ops, k, ctx, N, exact=exact, pipelined=pipelined)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), vals=res.top_vals.numpy(), win=res.top_win.numpy())
     finally:
         dist.destroy_process_group()
@@ -78,10 +80,11 @@ def _free_port():
     return port
 
 
-@pytest.mark.parametrize("exact", [True, False])
-def test_feature_sharded_scan_two_ranks(tmp_path, exact):
+@pytest.mark.parametrize("exact,pipelined", [(True, False), (False, False), (True, True), (False, True)])
+def test_feature_sharded_scan_two_ranks(tmp_path, exact, pipelined):
+    """sequential schedule and the one-chunk-lookahead schedule with asynchronous all-gathers"""
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), exact, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), exact, pipelined, str(tmp_path)), nprocs=world, join=True)
     r0, r1 = (np.load(tmp_path / f"rank{r}.npz") for r in range(world))
     assert np.array_equal(r0["vals"], r1["vals"]) and np.array_equal(r0["win"], r1["win"])  # all ranks agree
     assert r0["vals"].shape == (96, 3)
