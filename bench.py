@@ -312,8 +312,10 @@ def run_gpu(args):
                 "chunk_tokens": chunk,
                 "filled_features": int((res.top_win[:, 0] >= 0).sum().item()),
                 "schedule": "sequential (phase timing)" if args.scan_phases else
-                            ("one-chunk lookahead, both all-gathers asynchronous behind the next chunk's GEMM"
-                             if world > 1 else "two streams: GEMM of chunk c+1 overlaps refine/list update of chunk c"),
+                            {"lookahead": "one-chunk lookahead, both all-gathers asynchronous behind the next "
+                                          "chunk's GEMM",
+                             "streams": "two streams: GEMM of chunk c+1 overlaps exchange/refine/list update of "
+                                        "chunk c"}[sdist.scan_schedule(world)],
                 "phase_ms_rank0": {k_: round(v_, 2) for k_, v_ in phases.items()} or None}
 
     cpu = None

@@ -17,8 +17,17 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Iterable, Optional, Tuple
 
+import os
+
 import torch
 import torch.distributed as dist
+
+LOOKAHEAD_MIN_WORLD = 4   # see sharded_scan
+
+
+def scan_schedule(world: int) -> str:
+    """schedule sharded_scan uses for CUDA ops (SAEB_SCAN_SCHEDULE = lookahead | streams overrides, diagnostics)"""
+    return os.environ.get("SAEB_SCAN_SCHEDULE") or ("lookahead" if world >= LOOKAHEAD_MIN_WORLD else "streams")
 
 
 def shard_range(num_latents: int, world: int, rank: int) -> Tuple[int, int]:
@@ -197,12 +206,13 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
     features/cache.py:210-218).  Both exchanges are [Tc, k] fp32 per rank (256 B/token/rank at k = 64).
 
     Schedules (`pipelined`, default = `ops.pipelined` unless `phase_times` asks for the sequential diagnostic one):
-      * world > 1: one compute stream with a one-chunk lookahead; both all-gathers are issued asynchronously on the
+      * world >= LOOKAHEAD_MIN_WORLD: one compute stream with a one-chunk lookahead; both all-gathers are issued asynchronously on the
         collective stream -- exchange 1 of chunk c right after its GEMM, consumed after the GEMM of chunk c+1;
         exchange 2 of chunk c after its refinement, consumed after the refinement of chunk c+1 -- so their latency
         and the skew between ranks hide behind tensor-core work (measured on 8 GPUs: waiting for the two exchanges
         was 26 % of the sequential schedule);
-      * world == 1: two streams, the GEMM of chunk c+1 overlaps refinement + list update of chunk c."""
+      * fewer ranks (the GEMM dominates, there is little to wait for): two streams, the GEMM of chunk c+1 overlaps
+        exchange + refinement + list update of chunk c (measured at 2 GPUs: 1.78 M tokens/s vs 1.70 M)."""
     distributed = dist.is_available() and dist.is_initialized()
     world = dist.get_world_size(group) if distributed else 1
     k_local = min(k, ops.feat_hi - ops.feat_lo)
@@ -234,19 +244,22 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
             lb = ops.local_bounds(x, k_local)
             tm.mark("gemm+bounds")
             window_base += finish(x, lb, None, window_base)
-    elif world > 1:
+    else:
+        schedule = scan_schedule(world)
+        if not hasattr(ops, "stream_gemm"):
+            schedule = "lookahead"
         begin, end = getattr(ops, "begin_pipeline", None), getattr(ops, "end_pipeline", None)
         if begin is not None:
             begin(world)
         try:
-            _lookahead_loop(chunks, ops, k, k_local, ctx_len, exchange, group)
+            if schedule == "lookahead":
+                _lookahead_loop(chunks, ops, k, k_local, ctx_len, exchange, group)
+            else:
+                _pipelined_loop(chunks, ops, finish, k_local, ctx_len, ops.stream_gemm, ops.stream_aux,
+                                torch.cuda.current_stream())
         finally:
             if end is not None:
                 end()
-    else:
-        sg, sa = ops.stream_gemm, ops.stream_aux
-        cur = torch.cuda.current_stream()
-        _pipelined_loop(chunks, ops, finish, k_local, ctx_len, sg, sa, cur)
 
     top_vals, top_win = ops.scan_finalize()
     tm.mark("scan_finalize")
