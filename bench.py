@@ -163,9 +163,6 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # the scan's per-chunk all-gathers run beside the persistent GEMM grid on the few SMs it leaves free
-        # (saeb200.dist.EngineOps.reserve_sms = 4): keep NCCL's kernels that small
-        os.environ.setdefault("NCCL_MAX_CTAS", "4")
         dist.init_process_group("nccl", device_id=dev)
     L = _capi.lib()
     _capi.check(L.saeb_set_option(b"profile", 1), "set_option")

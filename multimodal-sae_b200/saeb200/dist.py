@@ -22,7 +22,7 @@ import os
 import torch
 import torch.distributed as dist
 
-LOOKAHEAD_MIN_WORLD = 4   # see sharded_scan
+LOOKAHEAD_MIN_WORLD = 1 << 30   # see sharded_scan: the lookahead schedule never beat the two-stream one so far
 
 
 def scan_schedule(world: int) -> str:
@@ -71,14 +71,16 @@ class EngineOps:
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         self.stream_gemm = torch.cuda.Stream(device)
         self.stream_aux = torch.cuda.Stream(device, priority=-1)   # exchange / refine / list update: first pick
-        # of the SMs the GEMM grid leaves free (`reserve_sms`), see begin_pipeline
-        self.reserve_sms = 4
+        # of whatever SM resources the GEMM grid leaves free
+        # SMs the GEMM grid leaves idle while a multi-rank scan is pipelined (see begin_pipeline).  Measured at 8 GPUs
+        # (1 M tokens): 0 -> 4.85 M tokens/s, 4 (with NCCL_MAX_CTAS=4) -> 4.65-4.76 M: off by default
+        self.reserve_sms = 0
 
     def begin_pipeline(self, world: int):
-        """The persistent GEMM grid normally owns every SM; while the scan is pipelined it leaves a few free so that
-        NCCL's kernels (which cannot co-reside with a GEMM CTA) never have to displace one.  Pair this with
-        NCCL_MAX_CTAS <= reserve_sms in the environment (bench.py does)."""
-        if world > 1:
+        """The persistent GEMM grid normally owns every SM; with `reserve_sms` > 0 it leaves a few free while the scan
+        is pipelined so that NCCL's kernels (which cannot co-reside with a GEMM CTA) never have to displace one
+        (pair it with NCCL_MAX_CTAS <= reserve_sms in the environment)."""
+        if world > 1 and self.reserve_sms > 0:
             self._capi.check(self._capi.lib().saeb_set_option(b"reserve_sms", self.reserve_sms), "set_option")
 
     def chunk_tokens(self, world: int, waves: int = 4) -> int:
@@ -206,13 +208,14 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
     features/cache.py:210-218).  Both exchanges are [Tc, k] fp32 per rank (256 B/token/rank at k = 64).
 
     Schedules (`pipelined`, default = `ops.pipelined` unless `phase_times` asks for the sequential diagnostic one):
-      * world >= LOOKAHEAD_MIN_WORLD: one compute stream with a one-chunk lookahead; both all-gathers are issued asynchronously on the
-        collective stream -- exchange 1 of chunk c right after its GEMM, consumed after the GEMM of chunk c+1;
-        exchange 2 of chunk c after its refinement, consumed after the refinement of chunk c+1 -- so their latency
-        and the skew between ranks hide behind tensor-core work (measured on 8 GPUs: waiting for the two exchanges
-        was 26 % of the sequential schedule);
-      * fewer ranks (the GEMM dominates, there is little to wait for): two streams, the GEMM of chunk c+1 overlaps
-        exchange + refinement + list update of chunk c (measured at 2 GPUs: 1.78 M tokens/s vs 1.70 M)."""
+      * "streams" (default): the GEMM of chunk c+1 runs on `ops.stream_gemm` while exchange + refinement + list
+        update of chunk c run on `ops.stream_aux`;
+      * "lookahead" (SAEB_SCAN_SCHEDULE=lookahead, and what ops without streams get): one compute stream with a
+        one-chunk lookahead; both all-gathers are issued asynchronously -- exchange 1 of chunk c right after its
+        GEMM, consumed after the GEMM of chunk c+1; exchange 2 of chunk c after its refinement, consumed after the
+        refinement of chunk c+1.
+    Measured, 1 M tokens, tokens/s (sequential / streams / lookahead): 8 GPUs 4.55 M / 4.76-4.85 M / 4.64 M;
+    4 GPUs - / 3.14 M / 2.97 M; 2 GPUs - / 1.78 M / 1.70 M; 1 GPU 0.916 M / 0.951 M / -."""
     distributed = dist.is_available() and dist.is_initialized()
     world = dist.get_world_size(group) if distributed else 1
     k_local = min(k, ops.feat_hi - ops.feat_lo)

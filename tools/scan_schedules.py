@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--tokens", type=int, default=1048576)
     ap.add_argument("--schedules", default="lookahead,streams")
     ap.add_argument("--top", type=int, default=20)
+    ap.add_argument("--reserve-sms", type=int, default=0, help="SMs the GEMM grid leaves free (set NCCL_MAX_CTAS too)")
     args = ap.parse_args()
 
     import torch
@@ -29,13 +30,13 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_MAX_CTAS", "4")
         dist.init_process_group("nccl", device_id=dev)
     D, N, K, ctx = 4096, 131072, 64, 64
     sae = synth.make_sae(D, N, K, dev, seed=1234)
     lo, hi = sdist.shard_range(N, world, rank)
     ops = sdist.EngineOps(sae.encoder.weight.data[lo:hi], sae.encoder.bias.data[lo:hi], sae.b_dec.data, lo, hi,
                           args.top, ctx, dev)
+    ops.reserve_sms = args.reserve_sms
     del sae
     chunk = ops.chunk_tokens(world)
     xs = synth.make_activations(args.tokens, D, dev, seed=99)
