@@ -178,8 +178,13 @@ int saeb_scan_pool(const float* vals, const int64_t* idx, int64_t T, int k, int 
                    void* stream);
 int saeb_scan_merge(void* bucket, int* bucket_cnt, int bucket_cap, int64_t F, int n_top, float base_threshold,
                     float* top_vals, int64_t* top_win, float* feat_thr, void* stream);
-/* Per-token k-th largest of R gathered per-shard top-k value lists, gathered [R][T][k] f32 (after the NCCL
- * all-gather of local top-k values). */
+/* Per-token kth-largest of R gathered per-shard value lists, gathered [R][T][m] f32 (after the all-gather of each
+ * shard's m best values per token): tok_thr[t] = the kth-largest of the R*m values of token t, values
+ * <= 0 count as 0; 1 <= kth <= R*m.  The feature-sharded scan uses it twice per token chunk: on the gathered lower
+ * bounds (m may be smaller than k: the kth-largest of ANY >= kth lower bounds of distinct latents is a lower bound of
+ * the global k-th activation) and on the gathered exact local TopK values (m = k).  saeb_kth_of_gathered is the
+ * m = kth = k form.  Option "kth_impl" = 0 selects the first, memory-resident version of the kernel (diagnostics). */
+int saeb_kth_largest_gathered(const float* gathered, int R, int64_t T, int m, int kth, float* tok_thr, void* stream);
 int saeb_kth_of_gathered(const float* gathered, int R, int64_t T, int k, float* tok_thr, void* stream);
 
 #ifdef __cplusplus

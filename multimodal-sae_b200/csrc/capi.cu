@@ -74,7 +74,9 @@ size_t coo_workspace_bytes(long long T);
 int coo_extract_launch(const float* vals, const long long* idx, long long T, int k, float threshold,
                        const uint32_t* filter, long long seq_len, long long row_offset, long long* locations,
                        float* activations, long long* nnz_out, void* ws, size_t ws_bytes, cudaStream_t stream);
-int kth_gathered_launch(const float* gathered, int R, long long T, int k, float* tok_thr, cudaStream_t stream);
+int kth_gathered_launch(const float* gathered, int R, long long T, int m, int kth, float* tok_thr,
+                        cudaStream_t stream);
+int set_kth_impl(int v);
 int scan_pool_launch(const float* vals, const long long* idx, long long T, int k, int ctx_len, float threshold,
                      long long feat_lo, long long feat_hi, long long window_base, const float* tok_thr,
                      const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap, int* overflow,
@@ -123,6 +125,7 @@ int saeb_set_option(const char* name, int value) {
   if (strcmp(name, "persist_a") == 0) return set_persist_a(value);
   if (strcmp(name, "chunking") == 0) return set_chunking(value);
   if (strcmp(name, "reserve_sms") == 0) return set_reserve_sms(value);
+  if (strcmp(name, "kth_impl") == 0) return set_kth_impl(value);
   if (strcmp(name, "refine_margin") == 0) {
     g_default_margin = value;
     return 0;
@@ -506,12 +509,17 @@ int saeb_scan_merge(void* bucket, int* bucket_cnt, int bucket_cap, int64_t F, in
   return rc;
 }
 
-int saeb_kth_of_gathered(const float* gathered, int R, int64_t T, int k, float* tok_thr, void* stream) {
+int saeb_kth_largest_gathered(const float* gathered, int R, int64_t T, int m, int kth, float* tok_thr, void* stream) {
   g_err[0] = 0;
-  SAEB_REQUIRE(gathered && tok_thr, "kth_of_gathered: null pointer");
-  int rc = kth_gathered_launch(gathered, R, T, k, tok_thr, (cudaStream_t)stream);
+  SAEB_REQUIRE(gathered && tok_thr, "kth_largest_gathered: null pointer");
+  if (T == 0) return 0;
+  int rc = kth_gathered_launch(gathered, R, T, m, kth, tok_thr, (cudaStream_t)stream);
   if (rc == 0) g_launches += 1;
   return rc;
+}
+
+int saeb_kth_of_gathered(const float* gathered, int R, int64_t T, int k, float* tok_thr, void* stream) {
+  return saeb_kth_largest_gathered(gathered, R, T, k, k, tok_thr, stream);
 }
 
 }  // extern "C"

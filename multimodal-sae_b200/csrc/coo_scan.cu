@@ -172,32 +172,88 @@ int coo_extract_launch(const float* vals, const long long* idx, long long T, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// per-token global k-th value from R gathered per-shard top-k value lists  [R][T][k]
+// per-token kth-largest of R gathered per-shard value lists  [R][T][m]  (m values per shard and token)
+//
+// One warp per token.  The R*m values are loaded ONCE into registers (VPL per lane, coalesced along a shard's row) and
+// the kth-largest bit pattern is found by a 31-step bit search over the registers: the scan calls this twice per token
+// chunk between two collectives, so it sits on the critical path of the multi-GPU schedule (the first version re-read
+// the values from memory in every search step: ~0.8 ms per 37 888-token chunk at R*m = 512).
 // ---------------------------------------------------------------------------------------------
-__global__ void kth_gathered_kernel(const float* __restrict__ g, int R, long long T, int k,
-                                    float* __restrict__ tok_thr) {
+template <int VPL>
+__global__ void __launch_bounds__(256)
+kth_gathered_reg_kernel(const float* __restrict__ g, int R, long long T, int m, int kth, float* __restrict__ tok_thr) {
+  const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= T) return;   // t is per warp: the whole warp leaves together
+  const int M = R * m;
+  uint32_t key[VPL];
+#pragma unroll
+  for (int s = 0; s < VPL; ++s) {
+    const int i = s * 32 + lane;
+    uint32_t b = 0;
+    if (i < M) {
+      const int r = i / m, j = i - r * m;
+      const float v = __ldg(g + ((long long)r * T + t) * m + j);
+      if (v > 0.f) b = __float_as_uint(v);   // positive floats order like their bit patterns; <= 0 and NaN count as 0
+    }
+    key[s] = b;
+  }
+  uint32_t prefix = 0;
+  for (int bit = 30; bit >= 0; --bit) {
+    const uint32_t trial = prefix | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) c += (key[s] >= trial) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= kth) prefix = trial;
+  }
+  if (lane == 0) tok_thr[t] = __uint_as_float(prefix);
+}
+
+// any R*m: the values stay in memory (L1/L2) and are re-read in every search step
+__global__ void kth_gathered_mem_kernel(const float* __restrict__ g, int R, long long T, int m, int kth,
+                                        float* __restrict__ tok_thr) {
   const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (t >= T) return;
-  const int M = R * k;
+  const int M = R * m;
   uint32_t prefix = 0;
   for (int bit = 30; bit >= 0; --bit) {
     const uint32_t trial = prefix | (1u << bit);
     int c = 0;
     for (int i = lane; i < M; i += 32) {
-      const int r = i / k, j = i - r * k;
-      c += (__float_as_uint(fmaxf(g[((long long)r * T + t) * k + j], 0.f)) >= trial) ? 1 : 0;
+      const int r = i / m, j = i - r * m;
+      const float v = g[((long long)r * T + t) * m + j];
+      c += (v > 0.f && __float_as_uint(v) >= trial) ? 1 : 0;
     }
     c = __reduce_add_sync(0xffffffffu, c);
-    if (c >= k) prefix = trial;
+    if (c >= kth) prefix = trial;
   }
   if (lane == 0) tok_thr[t] = __uint_as_float(prefix);
 }
 
-int kth_gathered_launch(const float* gathered, int R, long long T, int k, float* tok_thr, cudaStream_t stream) {
-  SAEB_REQUIRE(R >= 1 && T > 0 && k >= 1, "kth_gathered: bad arguments");
+static int g_kth_impl = 1;   // 1: register-resident search (default); 0: memory-resident (first version, diagnostics)
+int set_kth_impl(int v) {
+  g_kth_impl = v ? 1 : 0;
+  return 0;
+}
+
+int kth_gathered_launch(const float* gathered, int R, long long T, int m, int kth, float* tok_thr,
+                        cudaStream_t stream) {
+  SAEB_REQUIRE(R >= 1 && T > 0 && m >= 1, "kth_gathered: bad arguments R=%d T=%lld m=%d", R, T, m);
+  SAEB_REQUIRE((long long)R * m < (1ll << 30), "kth_gathered: R*m too large");
+  SAEB_REQUIRE(kth >= 1 && kth <= R * m, "kth_gathered: kth=%d must be in 1..R*m=%d", kth, R * m);
   const int wpb = 8;
-  kth_gathered_kernel<<<(unsigned)((T + wpb - 1) / wpb), wpb * 32, 0, stream>>>(gathered, R, T, k, tok_thr);
+  const unsigned blocks = (unsigned)((T + wpb - 1) / wpb);
+  const int M = R * m;
+  if (g_kth_impl == 1 && M <= 128)
+    kth_gathered_reg_kernel<4><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m, kth, tok_thr);
+  else if (g_kth_impl == 1 && M <= 512)
+    kth_gathered_reg_kernel<16><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m, kth, tok_thr);
+  else if (g_kth_impl == 1 && M <= 2048)
+    kth_gathered_reg_kernel<64><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m, kth, tok_thr);
+  else
+    kth_gathered_mem_kernel<<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m, kth, tok_thr);
   SAEB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -61,6 +61,7 @@ SIGNATURES = {
     "saeb_scan_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
     "saeb_kth_of_gathered": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
+    "saeb_kth_largest_gathered": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -30,6 +30,20 @@ def scan_schedule(world: int) -> str:
     return os.environ.get("SAEB_SCAN_SCHEDULE") or ("lookahead" if world >= LOOKAHEAD_MIN_WORLD else "streams")
 
 
+def bounds_width(k: int, k_local: int, world: int) -> int:
+    """Columns of the per-token lower-bound lists a shard contributes to exchange 1.
+
+    The k-th largest of ANY set of >= k lower bounds of distinct latents is a valid lower bound of the token's global
+    k-th activation, so a shard need not send all k of its bounds: with the global TopK spread over `world` shards a
+    shard holds about k / world of them, and 2 k / world + 8 columns lose nothing in practice (a shard that does hold
+    more only makes the bound a little looser, i.e. a few more exact re-evaluations -- the result stays exact).  The
+    width never drops below ceil(k / world), so the union always has k entries.  SAEB_SCAN_BOUNDS_WIDTH overrides."""
+    env = os.environ.get("SAEB_SCAN_BOUNDS_WIDTH")
+    lo = -(-k // max(world, 1))
+    m = int(env) if env else max(16, 2 * lo + 8)
+    return max(1, min(k_local, max(m, lo)))
+
+
 def shard_range(num_latents: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous, balanced feature range of `rank` (sizes differ by at most one)."""
     base, rem = divmod(num_latents, world)
@@ -83,9 +97,12 @@ class EngineOps:
         if world > 1 and self.reserve_sms > 0:
             self._capi.check(self._capi.lib().saeb_set_option(b"reserve_sms", self.reserve_sms), "set_option")
 
-    def chunk_tokens(self, world: int, waves: int = 4) -> int:
+    def chunk_tokens(self, world: int, waves: Optional[int] = None) -> int:
         """Tokens per scan chunk = `waves` full single-wave GEMM launches (256-row tiles on half of the CTA pairs the
-        grid may use), so that no launch runs partly empty."""
+        grid may use), so that no launch runs partly empty.  Default 4 waves (SAEB_SCAN_WAVES overrides): every chunk
+        costs two cross-rank synchronisation points under sharding, larger chunks mean fewer of them."""
+        if waves is None:
+            waves = int(os.environ.get("SAEB_SCAN_WAVES", "4"))
         sms = int(self._capi.lib().saeb_query(b"num_sms")) or 148
         if world > 1:
             sms -= self.reserve_sms
@@ -149,8 +166,8 @@ class EngineOps:
                 self._ws[slot].data_ptr(), self._ws[slot].numel(), st), "saeb_refine_candidates")
         return vals, idx + self.feat_lo
 
-    def kth_of_gathered(self, gathered):
-        return self.engine.kth_of_gathered(gathered)
+    def kth_of_gathered(self, gathered, kth=None):
+        return self.engine.kth_of_gathered(gathered, kth)
 
     def scan_update(self, vals, idx, window_base, tok_thr):
         self.scan.update(vals, idx, window_base, tok_thr)
@@ -198,14 +215,16 @@ class _PhaseTimer:
 
 
 def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_latents: int, *, exact: bool = True,
-                 group=None, phase_times: Optional[dict] = None, pipelined: Optional[bool] = None) -> ScanResult:
+                 group=None, phase_times: Optional[dict] = None, pipelined: Optional[bool] = None,
+                 lb_width: Optional[int] = None) -> ScanResult:
     """Feature-sharded scan.  `chunks` yields the SAME token chunks ([Tc, d], Tc a multiple of ctx_len) on every rank.
 
     exact=True, per chunk: (1) every shard computes lower bounds of its k best latents per token and all-gathers
     them -> per-token lower bound of the global k-th value; (2) the shard evaluates exactly only the latents that can
     still reach it and all-gathers its exact local top-k values -> the per-token global k-th value, which filters what
     enters the per-feature lists (the cache keeps a latent only if it is in the token's global TopK,
-    features/cache.py:210-218).  Both exchanges are [Tc, k] fp32 per rank (256 B/token/rank at k = 64).
+    features/cache.py:210-218).  Exchange 1 is [Tc, lb_width] fp32 per rank (`bounds_width`: 24 columns at k = 64 on
+    8 ranks), exchange 2 [Tc, k] (256 B/token/rank at k = 64).
 
     Schedules (`pipelined`, default = `ops.pipelined` unless `phase_times` asks for the sequential diagnostic one):
       * "streams" (default): the GEMM of chunk c+1 runs on `ops.stream_gemm` while exchange + refinement + list
@@ -219,6 +238,7 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
     distributed = dist.is_available() and dist.is_initialized()
     world = dist.get_world_size(group) if distributed else 1
     k_local = min(k, ops.feat_hi - ops.feat_lo)
+    m1 = bounds_width(k, k_local, world) if lb_width is None else max(1, min(k_local, int(lb_width)))
     if pipelined is None:
         pipelined = bool(getattr(ops, "pipelined", False)) and phase_times is None
     tm = _PhaseTimer(phase_times is not None and torch.cuda.is_available())
@@ -229,13 +249,13 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
         """exchange 1 -> restricted exact local TopK -> exchange 2 -> per-feature list update, for one chunk"""
         ext_L = tok_thr = None
         if exchange:
-            ext_L = _kth(ops, _gather_stack(lb, group), k, k_local)
+            ext_L = _kth(ops, _gather_stack(_head(lb, m1), group), k)
             tm.mark("exchange1")
         vals, idx = ops.local_topk(ext_L, slot) if slot is not None else ops.local_topk(ext_L)
         tm.mark("refine")
         vals2 = vals.reshape(-1, k_local)
         if exchange:
-            tok_thr = _kth(ops, _gather_stack(vals2, group), k, k_local)
+            tok_thr = _kth(ops, _gather_stack(vals2, group), k)
             tm.mark("exchange2")
         ops.scan_update(vals2, idx.reshape(-1, k_local), window_base, tok_thr)
         tm.mark("scan_update")
@@ -256,7 +276,7 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
             begin(world)
         try:
             if schedule == "lookahead":
-                _lookahead_loop(chunks, ops, k, k_local, ctx_len, exchange, group)
+                _lookahead_loop(chunks, ops, k, k_local, ctx_len, exchange, group, m1)
             else:
                 _pipelined_loop(chunks, ops, finish, k_local, ctx_len, ops.stream_gemm, ops.stream_aux,
                                 torch.cuda.current_stream())
@@ -276,7 +296,7 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
     return ScanResult(top_vals, top_win)
 
 
-def _lookahead_loop(chunks, ops, k, k_local, ctx_len, exchange, group) -> None:
+def _lookahead_loop(chunks, ops, k, k_local, ctx_len, exchange, group, m1) -> None:
     """world > 1 schedule of sharded_scan: per iteration c
          A(c)    GEMM + bounds of chunk c;            exchange 1 of chunk c   issued (async)
          B1(c-1) wait exchange 1 of c-1, refine c-1;  exchange 2 of chunk c-1 issued (async)
@@ -292,7 +312,7 @@ def _lookahead_loop(chunks, ops, k, k_local, ctx_len, exchange, group) -> None:
         ext_L = None
         if exchange:
             work.wait()
-            ext_L = _kth(ops, gathered, k, k_local)
+            ext_L = _kth(ops, gathered, k)
         vals, idx = ops.local_topk(ext_L, slot)
         vals2, idx2 = vals.reshape(-1, k_local), idx.reshape(-1, k_local)
         g2, w2 = _gather_stack(vals2, group, async_op=True) if exchange else (None, None)
@@ -303,13 +323,13 @@ def _lookahead_loop(chunks, ops, k, k_local, ctx_len, exchange, group) -> None:
         tok_thr = None
         if exchange:
             work.wait()
-            tok_thr = _kth(ops, gathered, k, k_local)
+            tok_thr = _kth(ops, gathered, k)
         ops.scan_update(vals2, idx2, base, tok_thr)
 
     for c, x in enumerate(chunks):
         slot = c & 1
         lb = ops.local_bounds(x, k_local, slot)
-        g1, w1 = _gather_stack(lb, group, async_op=True) if exchange else (None, None)
+        g1, w1 = _gather_stack(_head(lb, m1), group, async_op=True) if exchange else (None, None)
         if stage1 is not None:
             nxt = b1(stage1)
             if stage2 is not None:
@@ -377,13 +397,15 @@ def _gather_stack(t: torch.Tensor, group, async_op: bool = False):
     return (out, work) if async_op else out
 
 
-def _kth(ops, gathered: torch.Tensor, k: int, k_local: int) -> torch.Tensor:
-    """per-token k-th largest of the R * k_local gathered values"""
-    if k_local == k:
-        return ops.kth_of_gathered(gathered)
-    R, T, kl = gathered.shape
-    flat = gathered.permute(1, 0, 2).reshape(T, R * kl)
-    return flat.topk(min(k, R * kl), dim=-1).values[:, -1].contiguous()
+def _head(lb: torch.Tensor, m: int) -> torch.Tensor:
+    """first m columns of the (descending) per-token bound lists"""
+    return lb if m >= lb.shape[-1] else lb[..., :m]
+
+
+def _kth(ops, gathered: torch.Tensor, k: int) -> torch.Tensor:
+    """per-token k-th largest of the R * m gathered values ([R, T, m]); with fewer than k values, the smallest"""
+    R, T, m = gathered.shape
+    return ops.kth_of_gathered(gathered, min(k, R * m))
 
 
 def token_parallel_forward(sae, x_local: torch.Tensor):

@@ -341,13 +341,19 @@ class TopActivationScan:
         return self.top_vals, self.top_win
 
 
-def kth_of_gathered(gathered: torch.Tensor) -> torch.Tensor:
-    """gathered [R, T, k] f32 (all-gathered per-shard top-k values) -> per-token global k-th value [T]."""
+def kth_of_gathered(gathered: torch.Tensor, kth: Optional[int] = None) -> torch.Tensor:
+    """gathered [R, T, m] f32 (all-gathered per-shard value lists, m values per shard and token) -> per-token
+    kth-largest of the R*m values [T] (values <= 0 count as 0).  kth defaults to m: the per-token global k-th value from
+    the shards' local top-k values."""
     _need_cuda(gathered)
     L = _capi.lib()
-    R, T, k = gathered.shape
+    R, T, m = gathered.shape
+    kth = m if kth is None else int(kth)
     g = gathered.contiguous()
+    if g.dtype != torch.float32:
+        raise SaebError("kth_of_gathered needs float32 values")
     out = torch.empty((T,), dtype=torch.float32, device=g.device)
     with torch.cuda.device(g.device):
-        check(L.saeb_kth_of_gathered(g.data_ptr(), R, T, k, out.data_ptr(), _stream()), "saeb_kth_of_gathered")
+        check(L.saeb_kth_largest_gathered(g.data_ptr(), R, T, m, kth, out.data_ptr(), _stream()),
+              "saeb_kth_largest_gathered")
     return out

@@ -34,9 +34,10 @@ class OracleOps:
             v = torch.where(v >= ext_L[:, None], v, torch.zeros_like(v))
         return v, self._i[slot] + self.feat_lo
 
-    def kth_of_gathered(self, gathered):
-        R, T, k = gathered.shape
-        return gathered.permute(1, 0, 2).reshape(T, R * k).topk(k).values[:, -1].contiguous()
+    def kth_of_gathered(self, gathered, kth=None):
+        R, T, m = gathered.shape
+        kth = m if kth is None else kth
+        return gathered.permute(1, 0, 2).reshape(T, R * m).topk(kth).values[:, -1].contiguous()
 
     def scan_update(self, vals, idx, window_base, tok_thr):
         if tok_thr is not None:
@@ -50,7 +51,7 @@ class OracleOps:
         return torch.from_numpy(s), torch.from_numpy(w)
 
 
-def _worker(rank, world, port, exact, pipelined, out_dir):
+def _worker(rank, world, port, exact, pipelined, out_dir, lb_width=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, os.path.join(root, "multimodal-sae_b200"))
@@ -66,7 +67,7 @@ def _worker(rank, world, port, exact, pipelined, out_dir):
         ops = OracleOps(p, lo, hi, n_top, ctx)
         step = ctx * (2 if pipelined else 4)   # 6 / 3 chunks
         chunks = [x[i:i + step] for i in range(0, x.shape[0], step)]
-        res = sdist.sharded_scan(chunks, ops, k, ctx, N, exact=exact, pipelined=pipelined)
+        res = sdist.sharded_scan(chunks, ops, k, ctx, N, exact=exact, pipelined=pipelined, lb_width=lb_width)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), vals=res.top_vals.numpy(), win=res.top_win.numpy())
     finally:
         dist.destroy_process_group()
@@ -80,11 +81,13 @@ def _free_port():
     return port
 
 
-@pytest.mark.parametrize("exact,pipelined", [(True, False), (False, False), (True, True), (False, True)])
-def test_feature_sharded_scan_two_ranks(tmp_path, exact, pipelined):
-    """sequential schedule and the one-chunk-lookahead schedule with asynchronous all-gathers"""
+@pytest.mark.parametrize("exact,pipelined,lb_width", [(True, False, None), (False, False, None), (True, True, None),
+                                                      (False, True, None), (True, False, 3), (True, True, 4)])
+def test_feature_sharded_scan_two_ranks(tmp_path, exact, pipelined, lb_width):
+    """sequential schedule and the one-chunk-lookahead schedule with asynchronous all-gathers; `lb_width` = columns of
+    the lower-bound lists in exchange 1 (3 = k / world, the narrowest legal width: the result must stay exact)"""
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), exact, pipelined, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), exact, pipelined, str(tmp_path), lb_width), nprocs=world, join=True)
     r0, r1 = (np.load(tmp_path / f"rank{r}.npz") for r in range(world))
     assert np.array_equal(r0["vals"], r1["vals"]) and np.array_equal(r0["win"], r1["win"])  # all ranks agree
     assert r0["vals"].shape == (96, 3)
@@ -99,6 +102,15 @@ def test_feature_sharded_scan_two_ranks(tmp_path, exact, pipelined):
         np.testing.assert_array_equal(r0["win"], ref_w)
     else:  # shard-local TopK keeps a superset of each token's latents: scores can only grow
         assert (r0["vals"] >= ref_s - 1e-7).all() and not np.array_equal(r0["vals"], ref_s)
+
+
+def test_bounds_width():
+    from saeb200.dist import bounds_width
+
+    assert bounds_width(64, 64, 8) == 24 and bounds_width(64, 64, 4) == 40 and bounds_width(64, 64, 2) == 64
+    assert bounds_width(64, 10, 8) == 10           # never wider than the shard's own list
+    for k, w in ((64, 8), (6, 2), (256, 8), (5, 3)):
+        assert w * bounds_width(k, k, w) >= k      # the union of the shards' lists always holds k bounds
 
 
 def test_shard_and_token_ranges():

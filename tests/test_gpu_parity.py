@@ -429,11 +429,12 @@ def test_feature_sharded_scan_logical_shards():
     shards = [sdist.shard_range(N, R, r) for r in range(R)]
     ops = [sdist.EngineOps(p.W_enc[lo:hi].to(DEV), p.b_enc[lo:hi].to(DEV), p.b_dec.to(DEV), lo, hi, n_top, ctx, DEV)
            for lo, hi in shards]
-    n_eval = 0
+    n_eval, m1 = 0, 8   # k / R = 4 is the narrowest legal width
     for c0 in range(0, x.shape[0], ctx * 16):
         xc = x[c0:c0 + ctx * 16]
-        lbs = torch.stack([o.local_bounds(xc, k) for o in ops], 0)
-        ext_L = engine.kth_of_gathered(lbs)
+        # exchange 1 carries only the first m1 columns of each shard's bound list (saeb200.dist.bounds_width)
+        lbs = torch.stack([o.local_bounds(xc, k)[:, :m1] for o in ops], 0)
+        ext_L = engine.kth_of_gathered(lbs, k)
         outs = [o.local_topk(ext_L) for o in ops]
         n_eval += sum(int((v > 0).sum()) for v, _ in outs)
         tok_thr = engine.kth_of_gathered(torch.stack([v for v, _ in outs], 0))
@@ -451,12 +452,25 @@ def test_feature_sharded_scan_logical_shards():
 
 
 def test_kth_of_gathered():
-    from saeb200 import engine
+    from saeb200 import _capi, engine
 
     g = torch.rand(4, 100, 16, generator=torch.Generator().manual_seed(23))
     out = engine.kth_of_gathered(g.to(DEV))
     ref = g.permute(1, 0, 2).reshape(100, 64).topk(16).values[:, -1]
     assert torch.equal(out.cpu(), ref)
+    # every register tier of the kernel (R*m <= 128 / 512 / 2048) and the memory-resident one, list width m != rank
+    # kth (narrow exchange 1 of the sharded scan), non-positive entries (padding of short lists) counting as 0
+    gen = torch.Generator().manual_seed(24)
+    for R, T, m, kth in ((8, 333, 64, 64), (8, 50, 24, 64), (2, 7, 3, 6), (8, 20, 256, 100), (3, 10, 700, 64),
+                         (5, 9, 13, 1), (5, 9, 13, 65)):
+        g = torch.randn(R, T, m, generator=gen)
+        g[:, ::3, m // 2:] = 0.0
+        ref = g.clamp_min(0).permute(1, 0, 2).reshape(T, R * m).topk(kth).values[:, -1]
+        for impl in (1, 0):
+            _capi.check(_capi.lib().saeb_set_option(b"kth_impl", impl), "set_option")
+            out = engine.kth_of_gathered(g.to(DEV), kth)
+            assert torch.equal(out.cpu(), ref), (R, T, m, kth, impl)
+    _capi.check(_capi.lib().saeb_set_option(b"kth_impl", 1), "set_option")
 
 
 # ---------------------------------------------------------------------------------------------
