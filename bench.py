@@ -284,6 +284,8 @@ def run_gpu(args):
         lo, hi = sdist.shard_range(WIDTH, world, rank)
         ops = sdist.EngineOps(sae.encoder.weight.data[lo:hi], sae.encoder.bias.data[lo:hi], sae.b_dec.data, lo, hi,
                               n_top, ctx_len, dev, planes=args.planes)
+        if args.scan_exchange:
+            ops.exchange = args.scan_exchange
         chunk = ops.chunk_tokens(world)  # four single-wave GEMM launches per exchange round
         xs = synth.make_activations(args.scan_tokens, D_IN, dev, seed=99)  # same tokens on every rank
 
@@ -307,6 +309,10 @@ def run_gpu(args):
         scan = {"tokens": args.scan_tokens, "features": WIDTH, "n_top": n_top, "ctx_len": ctx_len, "ms": sms,
                 "tokens_per_s": args.scan_tokens / (sms * 1e-3), "sharding": f"features/{world}", "exact_topk_mask": True,
                 "chunk_tokens": chunk,
+                "exchange": None if world == 1 else
+                            {"nccl": "2 NCCL all-gathers per chunk", "push": "2 saeb_push_gather kernels per chunk (" +
+                             (ops._push.transport if ops._push is not None else "not used") + ")"}[ops.exchange],
+                "exchange1_columns": sdist.bounds_width(K, min(K, hi - lo), world) if world > 1 else None,
                 "filled_features": int((res.top_win[:, 0] >= 0).sum().item()),
                 "schedule": "sequential (phase timing)" if args.scan_phases else
                             {"lookahead": "one-chunk lookahead, both all-gathers asynchronous behind the next "
@@ -350,6 +356,9 @@ def main():
                     help="tokens of the feature-sharded top-activation scan (BASELINE C3: 1048576, C4: 4194304)")
     ap.add_argument("--scan-top", type=int, default=20, help="examples kept per feature (C3: 5, C4: 20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scan-exchange", default=None, choices=["nccl", "push"],
+                    help="per-chunk exchanges of the sharded scan: NCCL all-gathers (default) or the library's own "
+                         "peer-memory all-gather (saeb_push_gather)")
     ap.add_argument("--scan-phases", action="store_true", help="per-phase CUDA-event timing of the scan (diagnostic)")
     ap.add_argument("--no-overlap", action="store_true", help="run the phases of a step back to back on one stream")
     ap.add_argument("--chunk", type=int, default=18944, help="tokens per pipeline chunk (multiple of 9472 = one wave)")

@@ -187,6 +187,24 @@ int saeb_scan_merge(void* bucket, int* bucket_cnt, int bucket_cap, int64_t F, in
 int saeb_kth_largest_gathered(const float* gathered, int R, int64_t T, int m, int kth, float* tok_thr, void* stream);
 int saeb_kth_of_gathered(const float* gathered, int R, int64_t T, int k, float* tok_thr, void* stream);
 
+/* ---- peer-memory all-gather for the feature-sharded scan (optional replacement of the two per-chunk NCCL
+ * all-gathers) -------------------------------------------------------------------------------------
+ * Every rank holds a SYMMETRIC buffer (same size and offsets on all R ranks of one NVLink/NVSwitch box; mapped into
+ * each other's address space, e.g. by torch.distributed._symmetric_memory) laid out by the caller as
+ *   [flags: uint32 [channels][R], zero-initialised] ... [gathered region: R slabs of `bytes` each] ...
+ * saeb_push_gather copies this rank's slab `src` (device, 16-byte aligned, bytes % 16 == 0) into slab `self_rank` of the
+ * region at `region_offset` in EVERY rank's buffer -- 16-byte stores to the mapped peer pointers
+ * `peer_bases_dev` (DEVICE array of R base pointers, own buffer included), or one multimem.st per vector through
+ * `multicast_base` (the buffer's NVSwitch multicast mapping; NULL = unicast stores) -- then publishes sequence number
+ * `seq` for (channel, self_rank) on every rank (system-scope release) and waits until all R ranks' numbers for this
+ * channel have reached `seq` in the local flags (acquire).  When the kernel ends the local region [R][bytes] is
+ * complete; work enqueued later on `stream` may read it.  All ranks must call with the same channel / seq / bytes /
+ * offsets; `seq` must grow by one per call on a channel (start at 1); `counter` is a zero-initialised device int per
+ * channel (local memory, restored to 0 by the kernel).  A rank that never arrives makes the kernel trap after 20 s. */
+int saeb_push_gather(const void* src, size_t bytes, void* const* peer_bases_dev, int R, int self_rank,
+                     size_t region_offset, void* multicast_base, size_t flags_offset, int channel, uint32_t seq,
+                     int* counter, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

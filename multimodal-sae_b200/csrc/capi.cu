@@ -77,6 +77,9 @@ int coo_extract_launch(const float* vals, const long long* idx, long long T, int
 int kth_gathered_launch(const float* gathered, int R, long long T, int m, int kth, float* tok_thr,
                         cudaStream_t stream);
 int set_kth_impl(int v);
+int push_gather_launch(const void* src, size_t bytes, void* const* peer_bases_dev, int R, int self_rank,
+                       size_t region_offset, void* multicast_base, size_t flags_offset, int channel, unsigned int seq,
+                       int* counter, cudaStream_t stream);
 int scan_pool_launch(const float* vals, const long long* idx, long long T, int k, int ctx_len, float threshold,
                      long long feat_lo, long long feat_hi, long long window_base, const float* tok_thr,
                      const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap, int* overflow,
@@ -520,6 +523,18 @@ int saeb_kth_largest_gathered(const float* gathered, int R, int64_t T, int m, in
 
 int saeb_kth_of_gathered(const float* gathered, int R, int64_t T, int k, float* tok_thr, void* stream) {
   return saeb_kth_largest_gathered(gathered, R, T, k, k, tok_thr, stream);
+}
+
+int saeb_push_gather(const void* src, size_t bytes, void* const* peer_bases_dev, int R, int self_rank,
+                     size_t region_offset, void* multicast_base, size_t flags_offset, int channel, uint32_t seq,
+                     int* counter, void* stream) {
+  g_err[0] = 0;
+  SAEB_REQUIRE(src && peer_bases_dev && counter, "push_gather: null pointer");
+  if (bytes == 0) return 0;
+  int rc = push_gather_launch(src, bytes, peer_bases_dev, R, self_rank, region_offset, multicast_base, flags_offset,
+                              channel, seq, counter, (cudaStream_t)stream);
+  if (rc == 0) g_launches += 1;
+  return rc;
 }
 
 }  // extern "C"

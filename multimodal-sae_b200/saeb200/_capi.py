@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_size_t, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_size_t, c_uint32, c_void_p
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(PKG_DIR, "lib", "libsaeb200.so")
@@ -62,6 +62,8 @@ SIGNATURES = {
                                 c_void_p]),
     "saeb_kth_of_gathered": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
     "saeb_kth_largest_gathered": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "saeb_push_gather": (c_int, [c_void_p, c_size_t, c_void_p, c_int, c_int, c_size_t, c_void_p, c_size_t, c_int,
+                                 c_uint32, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -89,6 +89,23 @@ class EngineOps:
         # SMs the GEMM grid leaves idle while a multi-rank scan is pipelined (see begin_pipeline).  Measured at 8 GPUs
         # (1 M tokens): 0 -> 4.85 M tokens/s, 4 (with NCCL_MAX_CTAS=4) -> 4.65-4.76 M: off by default
         self.reserve_sms = 0
+        # per-chunk exchanges: "nccl" (all_gather_into_tensor) or "push" (saeb_push_gather: this library's own
+        # peer-memory all-gather, small enough to run beside the GEMM CTAs; NOT yet measured -> opt-in,
+        # SAEB_SCAN_EXCHANGE=push or bench.py --scan-exchange push)
+        self.exchange = os.environ.get("SAEB_SCAN_EXCHANGE", "nccl")
+        self.push_widths = None   # (exchange-1 width, exchange-2 width), set by sharded_scan
+        self._push = None
+
+    def push_gather(self, t, group, channel, slot):
+        """[T, m] -> [R, T, m] through the peer-memory exchange, or None when it is not selected (caller uses NCCL).
+        The symmetric buffer is created at the first call (a collective: every rank gets here with the same chunk)."""
+        if self.exchange != "push" or self.push_widths is None:
+            return None
+        if self._push is None or self._push.max_rows < t.shape[0] or tuple(self._push.widths) != tuple(self.push_widths):
+            from .p2p import PushExchange
+
+            self._push = PushExchange(group, t.device, t.shape[0], self.push_widths)
+        return self._push.gather(t, channel, slot)
 
     def begin_pipeline(self, world: int):
         """The persistent GEMM grid normally owns every SM; with `reserve_sms` > 0 it leaves a few free while the scan
@@ -245,17 +262,20 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
     tm.mark("start")
     exchange = exact and world > 1
 
+    if exchange and hasattr(ops, "push_widths"):
+        ops.push_widths = (m1, k_local)
+
     def finish(x, lb, slot, window_base):
         """exchange 1 -> restricted exact local TopK -> exchange 2 -> per-feature list update, for one chunk"""
         ext_L = tok_thr = None
         if exchange:
-            ext_L = _kth(ops, _gather_stack(_head(lb, m1), group), k)
+            ext_L = _kth(ops, _exchange(ops, _head(lb, m1), group, 0, slot), k)
             tm.mark("exchange1")
         vals, idx = ops.local_topk(ext_L, slot) if slot is not None else ops.local_topk(ext_L)
         tm.mark("refine")
         vals2 = vals.reshape(-1, k_local)
         if exchange:
-            tok_thr = _kth(ops, _gather_stack(vals2, group), k)
+            tok_thr = _kth(ops, _exchange(ops, vals2, group, 1, slot), k)
             tm.mark("exchange2")
         ops.scan_update(vals2, idx.reshape(-1, k_local), window_base, tok_thr)
         tm.mark("scan_update")
@@ -383,6 +403,17 @@ def _pipelined_loop(chunks, ops, finish, k_local, ctx_len, sg, sa, cur) -> int:
     cur.wait_stream(sg)
     cur.wait_stream(sa)
     return window_base
+
+
+def _exchange(ops, t: torch.Tensor, group, channel: int, slot) -> torch.Tensor:
+    """per-chunk exchange of [T, m] lists -> [R, T, m]: the ops' own peer-memory all-gather when it offers one
+    (EngineOps.push_gather), else NCCL / gloo"""
+    push = getattr(ops, "push_gather", None)
+    if push is not None:
+        g = push(t, group, channel, slot or 0)
+        if g is not None:
+            return g
+    return _gather_stack(t, group)
 
 
 def _gather_stack(t: torch.Tensor, group, async_op: bool = False):
