@@ -147,6 +147,21 @@ int saeb_decode(const int64_t* idx, const float* vals, int64_t T, int k, const v
                 int64_t N, const float* b_dec, void* out, int out_dtype, int64_t ld_out, const void* x, int x_dtype,
                 int64_t ld_x, double* sq_err, int* err_flag, void* stream);
 
+/* ---- backward of the sparse decode -------------------------------------------------------------------------
+ * The decoder seam is a torch.autograd.Function in the reference (TritonDecoder, sae/kernels.py:403-429); these are
+ * its two backward products, fp32:
+ *   saeb_decode_backward_acts    d_vals[t,j] = grad_out[t,:] . W_dec[idx[t,j],:]   (triton_dense_dense_sparseout_matmul,
+ *                                sae/kernels.py:287-400; computed for zero activations too)
+ *   saeb_decode_backward_weight  dW_dec[n,:] += sum over (t,j) with idx[t,j] == n of vals[t,j] * grad_out[t,:]
+ *                                (triton_sparse_transpose_dense_matmul, sae/kernels.py:10-175; zero values skipped).
+ *                                ACCUMULATES into dW_dec [N,d] with fp32 atomics (like the reference's tl.atomic_add,
+ *                                the summation order is not fixed): zero it before the first call.
+ * grad_out [T, ld_g] f32; err_flag as in saeb_decode. */
+int saeb_decode_backward_acts(const float* grad_out, int64_t ld_g, const int64_t* idx, int64_t T, int k,
+                              const float* W_dec, int64_t d, int64_t N, float* d_vals, int* err_flag, void* stream);
+int saeb_decode_backward_weight(const float* grad_out, int64_t ld_g, const int64_t* idx, const float* vals, int64_t T,
+                                int k, int64_t d, int64_t N, float* dW_dec, int* err_flag, void* stream);
+
 /* FVU denominator  sum((x - x.mean(0))^2)  (sae/sae.py:204); scratch = 2*d doubles. */
 int saeb_total_variance(const void* x, int x_dtype, int64_t T, int64_t d, int64_t ld_x, double* scratch, double* out,
                         void* stream);

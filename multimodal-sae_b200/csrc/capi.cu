@@ -77,6 +77,12 @@ int coo_extract_launch(const float* vals, const long long* idx, long long T, int
 int kth_gathered_launch(const float* gathered, int R, long long T, int m, int kth, float* tok_thr,
                         cudaStream_t stream);
 int set_kth_impl(int v);
+int decode_bwd_acts_launch(const float* grad_out, long long ld_g, const long long* idx, long long T, int k,
+                           const float* W_dec, long long d, long long N, float* d_vals, int* err_flag,
+                           cudaStream_t stream);
+int decode_bwd_weight_launch(const float* grad_out, long long ld_g, const long long* idx, const float* vals,
+                             long long T, int k, long long d, long long N, float* dW, int* err_flag,
+                             cudaStream_t stream);
 int push_gather_launch(const void* src, size_t bytes, void* const* peer_bases_dev, int R, int self_rank,
                        size_t region_offset, void* multicast_base, size_t flags_offset, int channel, unsigned int seq,
                        int* counter, cudaStream_t stream);
@@ -462,6 +468,26 @@ int saeb_decode(const int64_t* idx, const float* vals, int64_t T, int k, const v
   SAEB_REQUIRE(idx && vals && W_dec && out, "decode: null pointer");
   int rc = decode_launch(reinterpret_cast<const long long*>(idx), vals, T, k, W_dec, w_dtype, d, N, b_dec, out,
                          out_dtype, ld_out, x, x_dtype, ld_x, sq_err, err_flag, (cudaStream_t)stream);
+  if (rc == 0 && T > 0) g_launches += 1;
+  return rc;
+}
+
+int saeb_decode_backward_acts(const float* grad_out, int64_t ld_g, const int64_t* idx, int64_t T, int k,
+                              const float* W_dec, int64_t d, int64_t N, float* d_vals, int* err_flag, void* stream) {
+  g_err[0] = 0;
+  SAEB_REQUIRE(grad_out && idx && W_dec && d_vals, "decode_backward_acts: null pointer");
+  int rc = decode_bwd_acts_launch(grad_out, ld_g, reinterpret_cast<const long long*>(idx), T, k, W_dec, d, N, d_vals,
+                                  err_flag, (cudaStream_t)stream);
+  if (rc == 0 && T > 0) g_launches += 1;
+  return rc;
+}
+
+int saeb_decode_backward_weight(const float* grad_out, int64_t ld_g, const int64_t* idx, const float* vals, int64_t T,
+                                int k, int64_t d, int64_t N, float* dW_dec, int* err_flag, void* stream) {
+  g_err[0] = 0;
+  SAEB_REQUIRE(grad_out && idx && vals && dW_dec, "decode_backward_weight: null pointer");
+  int rc = decode_bwd_weight_launch(grad_out, ld_g, reinterpret_cast<const long long*>(idx), vals, T, k, d, N, dW_dec,
+                                    err_flag, (cudaStream_t)stream);
   if (rc == 0 && T > 0) g_launches += 1;
   return rc;
 }

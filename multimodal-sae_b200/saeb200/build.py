@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(LIB_DIR, "libsaeb200.so")
-SOURCES = ["capi.cu", "encode_topk.cu", "decode.cu", "pack.cu", "coo_scan.cu", "refine.cu", "exchange.cu"]
+SOURCES = ["capi.cu", "encode_topk.cu", "decode.cu", "pack.cu", "coo_scan.cu", "refine.cu", "exchange.cu", "decode_bwd.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "saeb200.h")]
 
 NVCC_FLAGS = [

@@ -220,6 +220,44 @@ def decode(top_indices: torch.Tensor, top_acts: torch.Tensor, W_dec: torch.Tenso
 decode.last_err_flag = None
 
 
+def decode_backward(top_indices: torch.Tensor, top_acts: torch.Tensor, W_dec: torch.Tensor, grad_out: torch.Tensor,
+                    *, need_acts: bool = True, need_weight: bool = True
+                    ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """Backward products of `decode` (reference TritonDecoder.backward, sae/kernels.py:411-429), fp32:
+    d_acts[..., j] = grad_out[..., :] . W_dec[idx[..., j], :]  and  dW_dec [N, d] = sparse(acts)^T @ grad_out."""
+    _need_cuda(top_indices, top_acts, W_dec, grad_out)
+    L = _capi.lib()
+    N, d = W_dec.shape
+    if W_dec.dtype != torch.float32 or not W_dec.is_contiguous():
+        raise SaebError("decode_backward: W_dec must be the contiguous fp32 [N, d] parameter")
+    k = top_indices.shape[-1]
+    idx = top_indices.reshape(-1, k).to(torch.int64).contiguous()
+    vals = top_acts.reshape(-1, k).to(torch.float32).contiguous()
+    g = grad_out.reshape(-1, d).to(torch.float32).contiguous()
+    T = idx.shape[0]
+    if g.shape[0] != T:
+        raise SaebError(f"decode_backward: grad_out has {g.shape[0]} rows, the TopK tensors {T}")
+    err_flag = torch.zeros(1, dtype=torch.int32, device=idx.device)
+    d_acts = dW = None
+    with torch.cuda.device(idx.device):
+        if need_acts:
+            d_acts = torch.empty((T, k), dtype=torch.float32, device=idx.device)
+            check(L.saeb_decode_backward_acts(g.data_ptr(), d, idx.data_ptr(), T, k, W_dec.data_ptr(), d, N,
+                                              d_acts.data_ptr(), err_flag.data_ptr(), _stream()),
+                  "saeb_decode_backward_acts")
+            d_acts = d_acts.view(*top_indices.shape)
+        if need_weight:
+            dW = torch.zeros((N, d), dtype=torch.float32, device=idx.device)
+            check(L.saeb_decode_backward_weight(g.data_ptr(), d, idx.data_ptr(), vals.data_ptr(), T, k, d, N,
+                                                dW.data_ptr(), err_flag.data_ptr(), _stream()),
+                  "saeb_decode_backward_weight")
+    decode_backward.last_err_flag = err_flag
+    return d_acts, dW
+
+
+decode_backward.last_err_flag = None
+
+
 def total_variance(x: torch.Tensor) -> torch.Tensor:
     """sum((x - x.mean(0))**2) as a 0-dim float64 tensor (reference sae/sae.py:204)."""
     _need_cuda(x)

@@ -79,6 +79,41 @@ def gen_decode_test(ref):
                         top_vals=top_vals.numpy(), top_idx=top_idx.numpy(), eager=res.numpy())
 
 
+def gen_decode_backward(ref):
+    """Gradients of the decoder seam (`decoder_impl(top_indices, top_acts, W_dec.mT)`, sae/utils.py:107-129; autograd
+    contract of TritonDecoder, sae/kernels.py:403-429) from the reference's own CPU path: autograd through
+    `eager_decode`, and through `Sae.decode` (adds b_dec).  One activation is exactly zero: its gradient is still the
+    gathered dot product."""
+    from sae_auto_interp.sae.utils import eager_decode
+
+    d, N, k, T = 48, 160, 6, 20
+    p = O.init_params(d, N, k, seed=31)
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(T, d, generator=g)
+    sae = build_ref_sae(ref.sae, p)
+    with torch.no_grad():
+        enc = sae.encode(x)
+    top_idx = enc.top_indices.clone()
+    top_vals = enc.top_acts.clone()
+    top_vals[3, 2] = 0.0
+    grad_out = torch.randn(T, d, generator=g)
+    vals_a = top_vals.clone().requires_grad_(True)
+    W = p.W_dec.clone().requires_grad_(True)
+    out = eager_decode(top_idx, vals_a, W.mT)
+    out.backward(grad_out)
+    # through the module: Sae.decode = decoder_impl(...) + b_dec (sae/sae.py:187-191)
+    sae.zero_grad()
+    vals_b = top_vals.clone().requires_grad_(True)
+    out2 = sae.decode(vals_b, top_idx)
+    out2.backward(grad_out)
+    np.savez_compressed(os.path.join(GOLD, "decode_backward.npz"), W_dec=p.W_dec.numpy(), b_dec=p.b_dec.numpy(),
+                        top_idx=top_idx.numpy(), top_vals=top_vals.numpy(), grad_out=grad_out.numpy(),
+                        out=out.detach().numpy(), d_vals=vals_a.grad.numpy(), d_W_dec=W.grad.numpy(),
+                        sae_d_vals=vals_b.grad.numpy(), sae_d_W_dec=sae.W_dec.grad.numpy(),
+                        sae_d_b_dec=sae.b_dec.grad.numpy())
+    print("decode_backward |dW|", float(W.grad.abs().sum()))
+
+
 class ToyLM(torch.nn.Module):
     """Stand-in host model: embedding -> one 'layer' whose output is hooked (features/cache.py:178-191)."""
 
@@ -204,6 +239,12 @@ def main():
     import sae_auto_interp.sae as ref_sae
 
     ref.sae = ref_sae
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
+    if only is not None:   # regenerate one fixture without touching the others
+        {"decode_backward": gen_decode_backward, "decode_test": gen_decode_test, "cache_chain": gen_cache_chain,
+         "steering": gen_steering}[only](ref)
+        return
+    gen_decode_backward(ref)
     gen_forward(ref, "forward_c1.npz", d=128, N=512, k=16, T=256, seed=1234, bf16_x=False)
     gen_forward(ref, "forward_c1_bf16.npz", d=128, N=512, k=16, T=256, seed=1235, bf16_x=True)
     gen_forward(ref, "forward_wide.npz", d=64, N=2048, k=32, T=96, seed=1236, bf16_x=True)

@@ -123,6 +123,24 @@ def sparse_decode(top_indices: torch.Tensor, top_acts: torch.Tensor, W_dec: torc
     return out.to(top_acts.dtype)
 
 
+def decode_backward(top_indices: torch.Tensor, top_acts: torch.Tensor, W_dec: torch.Tensor, grad_out: torch.Tensor
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Backward of the decoder seam, reference `TritonDecoder.backward` (sae/kernels.py:411-429):
+      d_acts[a, j] = grad_out[a, :] . W_dec[idx[a, j], :]          (`triton_dense_dense_sparseout_matmul`, :287-400:
+                                                                    "(dense1 @ dense2).gather(1, at_indices)")
+      dW_dec[n, :] = sum_{(a, j): idx[a, j] == n} acts[a, j] * grad_out[a, :]   (`triton_sparse_transpose_dense_matmul`,
+                                                                    :10-175: sparse.T @ dense, zero values skipped)
+    Both in fp32.  The same numbers come out of autograd through `eager_decode` (sae/utils.py:108-111), which is what
+    the golden fixture was generated with."""
+    A, K = top_indices.shape
+    g = grad_out.to(torch.float32)
+    d_acts = (g @ W_dec.to(torch.float32).T).gather(1, top_indices)
+    dW = torch.zeros(W_dec.shape, dtype=torch.float32)
+    dW.index_add_(0, top_indices.reshape(-1),
+                  (top_acts.to(torch.float32)[:, :, None] * g[:, None, :]).reshape(A * K, -1))
+    return d_acts, dW
+
+
 def decode(p: SaeParams, top_acts: torch.Tensor, top_indices: torch.Tensor) -> torch.Tensor:
     """reference sae/sae.py:187-191: decoder_impl(idx, acts.to(dtype), W_dec.mT) + b_dec."""
     y = eager_decode(top_indices, top_acts.to(torch.float32), p.W_dec.mT)

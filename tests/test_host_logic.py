@@ -126,3 +126,54 @@ def test_filter_bitmap_bits():
     bm = make_filter_bitmap(torch.tensor([0, 31, 32, 63, 95]), 96)
     words = bm.to(torch.int64) & 0xFFFFFFFF
     assert words.tolist() == [(1 << 0) | (1 << 31), (1 << 0) | (1 << 31), 1 << 31]
+
+
+def test_decoder_seam_autograd_plumbing(monkeypatch):
+    """`decoder_impl` is a torch.autograd.Function like the reference's TritonDecoder (sae/kernels.py:403-429).  The
+    CUDA kernels behind it are exercised by the -m gpu tests; here the two engine calls are replaced by oracle
+    stand-ins so that the plumbing is checked on CPU against the reference's own gradients (fixture generated by
+    autograd through the reference's eager_decode / Sae.decode): which inputs get gradients, the layout of the gradient
+    of the transposed view `W_dec.mT`, and `+ b_dec` in Sae.decode."""
+    import sae_oracle as O
+    from saeb200 import engine
+    from sae_auto_interp.sae import Sae, SaeConfig
+    from sae_auto_interp.sae import utils as seam
+
+    calls = []
+
+    def fake_decode(top_indices, top_acts, W_dec, b_dec, *, out_dtype=torch.float32, **kw):
+        assert W_dec.is_contiguous() and b_dec is None
+        return O.sparse_decode(top_indices, top_acts, W_dec).to(out_dtype)
+
+    def fake_backward(top_indices, top_acts, W_dec, grad_out, *, need_acts=True, need_weight=True):
+        calls.append((need_acts, need_weight))
+        d_acts, dW = O.decode_backward(top_indices, top_acts, W_dec, grad_out)
+        return (d_acts if need_acts else None), (dW if need_weight else None)
+
+    monkeypatch.setattr(engine, "decode", fake_decode)
+    monkeypatch.setattr(engine, "decode_backward", fake_backward)
+    g = np.load(os.path.join(GOLDEN, "decode_backward.npz"))
+    idx, go = torch.from_numpy(g["top_idx"]), torch.from_numpy(g["grad_out"])
+    # the bare seam, gradients for both inputs
+    vals = torch.from_numpy(g["top_vals"]).requires_grad_(True)
+    W = torch.from_numpy(g["W_dec"]).requires_grad_(True)
+    out = seam.decoder_impl(idx, vals, W.mT)
+    np.testing.assert_allclose(out.detach().numpy(), g["out"], rtol=1e-5, atol=1e-6)
+    out.backward(go)
+    np.testing.assert_allclose(vals.grad.numpy(), g["d_vals"], rtol=1e-5, atol=1e-6)
+    assert W.grad.shape == W.shape
+    np.testing.assert_allclose(W.grad.numpy(), g["d_W_dec"], rtol=1e-5, atol=1e-6)
+    # through the module (sae/sae.py:187-191): W_dec and b_dec are parameters, the activations a plain tensor
+    sae = Sae(g["W_dec"].shape[1], SaeConfig(num_latents=g["W_dec"].shape[0], k=idx.shape[1]))
+    with torch.no_grad():
+        sae.W_dec.copy_(torch.from_numpy(g["W_dec"]))
+        sae.b_dec.copy_(torch.from_numpy(g["b_dec"]))
+    out2 = sae.decode(torch.from_numpy(g["top_vals"]), idx)
+    assert out2.requires_grad   # what features/patching/attribution.py:160-161 (`tensor.retain_grad()`) relies on
+    out2.backward(go)
+    np.testing.assert_allclose(sae.W_dec.grad.numpy(), g["sae_d_W_dec"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(sae.b_dec.grad.numpy(), g["sae_d_b_dec"], rtol=1e-5, atol=1e-6)
+    assert calls == [(True, True), (False, True)]
+    # no autograd graph under no_grad (cache / steering paths: features/cache.py:175, features/steering.py:85)
+    with torch.no_grad():
+        assert not sae.decode(torch.from_numpy(g["top_vals"]), idx).requires_grad

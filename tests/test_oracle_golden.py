@@ -53,6 +53,23 @@ def test_decode_property_of_reference_test():
     torch.testing.assert_close(sparse, torch.from_numpy(g["eager"]))  # same tolerance family as assert_allclose
 
 
+def test_decode_backward_matches_reference_autograd():
+    """Gradients of the decoder seam (TritonDecoder.backward, sae/kernels.py:411-429) against autograd through the
+    reference's eager_decode / Sae.decode."""
+    g = np.load(os.path.join(GOLDEN, "decode_backward.npz"))
+    idx, val = torch.from_numpy(g["top_idx"]), torch.from_numpy(g["top_vals"])
+    W, go = torch.from_numpy(g["W_dec"]), torch.from_numpy(g["grad_out"])
+    assert float(val[3, 2]) == 0.0   # a zero activation still receives its gathered-dot-product gradient
+    d_vals, dW = O.decode_backward(idx, val, W, go)
+    np.testing.assert_allclose(d_vals.numpy(), g["d_vals"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(dW.numpy(), g["d_W_dec"], rtol=1e-5, atol=1e-6)
+    # through the module the same gradients reach W_dec, and b_dec receives the column sums of grad_out
+    np.testing.assert_allclose(g["sae_d_vals"], g["d_vals"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(g["sae_d_W_dec"], g["d_W_dec"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(go.sum(0).numpy(), g["sae_d_b_dec"], rtol=1e-5, atol=1e-6)
+    assert np.count_nonzero(np.abs(g["d_W_dec"]).sum(1)) <= idx.numel()   # only selected rows receive gradient
+
+
 def test_cache_chain_matches_reference():
     """FeatureCache.run -> Cache.add/get_nonzeros (features/cache.py:42-92,206-218)."""
     g = np.load(os.path.join(GOLDEN, "cache_chain.npz"))
