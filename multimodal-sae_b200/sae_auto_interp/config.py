@@ -50,3 +50,12 @@ class CacheConfig(Serializable):
     save_dir: str = "./features_cache"
     verbosity: str = "INFO"
     filters_path: str = None
+
+
+@dataclass
+class AttributionConfig(Serializable):
+    model: str = field(default="EleutherAI/pythia-160m", positional=True)
+    data_path: str = "./data/digit.json"  # list of {"prompt", "answer", "baseline", "image"}
+    sae_path: Union[str, None] = None
+    selected_sae: str = "layers.24"
+    save_dir: str = "./attribution_cache"

@@ -1,6 +1,7 @@
 """`sae_auto_interp.features`: cache writer, cache reader, example constructors, samplers, steering (hot-path mirror)."""
 from . import cache as _cache, constructors as _ctor, features as _types, loader as _loader, samplers as _samplers
 from . import steering as _steering
+from .patching import Attribution
 
 FeatureCache, FeatureImageCache = _cache.FeatureCache, _cache.FeatureImageCache
 FeatureDataset = _loader.FeatureDataset
@@ -12,8 +13,8 @@ Feature, FeatureRecord, Example = _types.Feature, _types.FeatureRecord, _types.E
 sample, sample_with_explanation = _samplers.sample, _samplers.sample_with_explanation
 SteeringController = _steering.SteeringController
 
-# same public names as the reference package (its stats / patching helpers are outside the accelerated path)
+# same public names as the reference package (its stats helpers are outside the accelerated path)
 __all__ = ("FeatureCache FeatureImageCache FeatureDataset Feature FeatureRecord Example "
            "pool_max_activation_windows pool_max_activations_windows_image random_activation_windows "
            "random_activations_image default_constructor top_windows_all_features sample sample_with_explanation "
-           "SteeringController").split()
+           "SteeringController Attribution").split()

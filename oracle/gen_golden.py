@@ -114,6 +114,87 @@ def gen_decode_backward(ref):
     print("decode_backward |dW|", float(W.grad.abs().sum()))
 
 
+class ToyLogitLM(torch.nn.Module):
+    """Host model for the patching fixtures: embedding -> hooked layer (returns a tuple, like a decoder layer: the
+    reference hook only handles tuple outputs) -> vocabulary head; `model(**inputs)["logits"]`."""
+
+    class Layer(torch.nn.Module):
+        def __init__(self, d):
+            super().__init__()
+            self.lin = torch.nn.Linear(d, d)
+
+        def forward(self, h):
+            return (self.lin(h), None)
+
+    def __init__(self, vocab, d, seed):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.emb = torch.nn.Embedding(vocab, d)
+        self.layers = torch.nn.ModuleList([ToyLogitLM.Layer(d)])
+        self.head = torch.nn.Linear(d, vocab, bias=False)
+        with torch.no_grad():
+            self.emb.weight.copy_(torch.randn(vocab, d, generator=g))
+            self.layers[0].lin.weight.copy_(torch.randn(d, d, generator=g) / d ** 0.5)
+            self.layers[0].lin.bias.zero_()
+            self.head.weight.copy_(torch.randn(vocab, d, generator=g) / d ** 0.5)
+
+    def forward(self, input_ids):
+        h = self.layers[0](self.emb(input_ids))[0]
+        return {"logits": self.head(h.float())}
+
+
+def gen_attribution(ref):
+    """Attribution patching: reference get_model_forward_cache_with_sae / get_model_backward_cache_with_sae
+    (features/patching/utils.py:22-80) and the attribution formula of Attribution.get_attribution
+    (features/patching/attribution.py:131-184, restated here as glue around the reference functions because the class
+    constructor needs a tokenizer, an image processor and image files)."""
+    from functools import partial
+
+    from sae_auto_interp.features.patching.utils import (get_logit_diff, get_model_backward_cache_with_sae,
+                                                         get_model_forward_cache_with_sae)
+
+    d, N, k, vocab = 32, 64, 4, 40
+    p = O.init_params(d, N, k, seed=41)
+    sae = build_ref_sae(ref.sae, p)
+    model = ToyLogitLM(vocab, d, seed=42)
+    g = torch.Generator().manual_seed(43)
+    input_ids = torch.randint(0, vocab, (2, 6), generator=g)
+    answers = torch.tensor([[3, 7], [11, 2]])
+    metric = partial(get_logit_diff, answer_token_indices=answers)
+    sae_dict = {"layers.0": sae}
+    module_to_name = {model.layers[0]: "layers.0"}
+    # latents that are active somewhere in the clean pass, plus one that never fires
+    with torch.no_grad():
+        h = model.layers[0](model.emb(input_ids))[0]
+        enc = sae.encode(h.flatten(0, 1))
+    active = torch.unique(enc.top_indices)
+    never = [i for i in range(N) if i not in set(active.tolist())][:1]
+    # the metric reads the last position only: latents firing there give non-zero attribution, the others exactly 0
+    last = torch.unique(enc.top_indices.view(2, 6, k)[:, -1, :]).tolist()
+    elsewhere = [i for i in active.tolist() if i not in last][:1]
+    feats = last[:5] + elsewhere + never
+    out = {}
+    for f in feats:
+        model.zero_grad(), sae.zero_grad()
+        clean_logits, clean = get_model_forward_cache_with_sae(model, {"input_ids": input_ids}, sae_dict,
+                                                               module_to_name)
+        cor_logits, cor = get_model_forward_cache_with_sae(model, {"input_ids": input_ids}, sae_dict, module_to_name,
+                                                           off_features=f)
+        for t in cor.values():
+            t.retain_grad()
+        val = get_model_backward_cache_with_sae(logits=cor_logits, metrics=metric)
+        att = ((clean["layers.0"] - cor["layers.0"]) * cor["layers.0"].grad).detach().sum(dim=-1)
+        out[f"att_{f}"] = att.float().numpy()
+        out[f"metric_{f}"] = np.float32(val.item())
+        out[f"logits_{f}"] = cor_logits.detach().numpy()
+    np.savez_compressed(os.path.join(GOLD, "attribution.npz"), W_enc=p.W_enc.numpy(), b_enc=p.b_enc.numpy(),
+                        W_dec=p.W_dec.numpy(), b_dec=p.b_dec.numpy(), k=np.int64(k), input_ids=input_ids.numpy(),
+                        answers=answers.numpy(), features=np.array(feats), clean_logits=clean_logits.detach().numpy(),
+                        clean_rec=clean["layers.0"].detach().float().numpy(),
+                        logit_diff_clean=np.float32(metric(clean_logits).item()), **out)
+    print("attribution features", feats, "max |att|", max(float(np.abs(out[f"att_{f}"]).max()) for f in feats))
+
+
 class ToyLM(torch.nn.Module):
     """Stand-in host model: embedding -> one 'layer' whose output is hooked (features/cache.py:178-191)."""
 
@@ -241,10 +322,11 @@ def main():
     ref.sae = ref_sae
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
     if only is not None:   # regenerate one fixture without touching the others
-        {"decode_backward": gen_decode_backward, "decode_test": gen_decode_test, "cache_chain": gen_cache_chain,
+        {"decode_backward": gen_decode_backward, "attribution": gen_attribution, "decode_test": gen_decode_test, "cache_chain": gen_cache_chain,
          "steering": gen_steering}[only](ref)
         return
     gen_decode_backward(ref)
+    gen_attribution(ref)
     gen_forward(ref, "forward_c1.npz", d=128, N=512, k=16, T=256, seed=1234, bf16_x=False)
     gen_forward(ref, "forward_c1_bf16.npz", d=128, N=512, k=16, T=256, seed=1235, bf16_x=True)
     gen_forward(ref, "forward_wide.npz", d=64, N=2048, k=32, T=96, seed=1236, bf16_x=True)

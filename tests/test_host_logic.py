@@ -177,3 +177,105 @@ def test_decoder_seam_autograd_plumbing(monkeypatch):
     # no autograd graph under no_grad (cache / steering paths: features/cache.py:175, features/steering.py:85)
     with torch.no_grad():
         assert not sae.decode(torch.from_numpy(g["top_vals"]), idx).requires_grad
+
+
+def _oracle_backend(monkeypatch):
+    """CPU stand-ins for the engine calls behind the mirror `Sae` (the CUDA kernels have their own -m gpu tests): lets
+    the host-side glue above them run on CPU."""
+    import sae_oracle as O
+    from saeb200 import engine
+    from sae_auto_interp.sae import Sae
+    from sae_auto_interp.sae.sae import EncoderOutput
+
+    def params(sae):
+        return O.SaeParams(sae.encoder.weight.detach(), sae.encoder.bias.detach(), sae.W_dec.detach(),
+                           sae.b_dec.detach(), sae.cfg.k)
+
+    def pre_acts(self, x):
+        return O.pre_acts(params(self), x.detach().float())
+
+    def encode(self, x, *, clamp_feature=-1, clamp_value=0.0):
+        lat = pre_acts(self, x)
+        if clamp_feature >= 0:
+            lat[..., clamp_feature] = clamp_value
+        return EncoderOutput(*O.select_topk(lat, self.cfg.k))
+
+    monkeypatch.setattr(Sae, "pre_acts", pre_acts)
+    monkeypatch.setattr(Sae, "encode", encode)
+    monkeypatch.setattr(Sae, "select_topk", lambda self, lat: EncoderOutput(*O.select_topk(lat, self.cfg.k)))
+    monkeypatch.setattr(engine, "decode", lambda i, a, W, b, *, out_dtype=torch.float32, **kw:
+                        O.sparse_decode(i, a, W).to(out_dtype))
+
+    def bwd(i, a, W, g, *, need_acts=True, need_weight=True):
+        da, dw = O.decode_backward(i, a, W, g)
+        return (da if need_acts else None), (dw if need_weight else None)
+
+    monkeypatch.setattr(engine, "decode_backward", bwd)
+
+
+class _ToyLogitLM(torch.nn.Module):
+    """same host model as oracle/gen_golden.py::ToyLogitLM (the fixture stores its random seed, not its weights)"""
+
+    class Layer(torch.nn.Module):
+        def __init__(self, d):
+            super().__init__()
+            self.lin = torch.nn.Linear(d, d)
+
+        def forward(self, h):
+            return (self.lin(h), None)
+
+    def __init__(self, vocab, d, seed):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.emb = torch.nn.Embedding(vocab, d)
+        self.layers = torch.nn.ModuleList([_ToyLogitLM.Layer(d)])
+        self.head = torch.nn.Linear(d, vocab, bias=False)
+        with torch.no_grad():
+            self.emb.weight.copy_(torch.randn(vocab, d, generator=g))
+            self.layers[0].lin.weight.copy_(torch.randn(d, d, generator=g) / d ** 0.5)
+            self.layers[0].lin.bias.zero_()
+            self.head.weight.copy_(torch.randn(vocab, d, generator=g) / d ** 0.5)
+
+    def forward(self, input_ids):
+        h = self.layers[0](self.emb(input_ids))[0]
+        return {"logits": self.head(h.float())}
+
+
+def test_attribution_patching_matches_reference(monkeypatch):
+    """features/patching (utils.py:22-80, attribution.py:131-184): clean / corrupted passes with the SAE
+    reconstruction spliced in, one latent switched off through the clamp argument of `encode`, gradient of the
+    logit difference retained on the reconstruction."""
+    from functools import partial
+
+    from sae_auto_interp.features.patching import (attribution_for_feature, get_logit_diff,
+                                                   get_model_forward_cache_with_sae)
+    from sae_auto_interp.sae import Sae, SaeConfig
+
+    _oracle_backend(monkeypatch)
+    g = np.load(os.path.join(GOLDEN, "attribution.npz"))
+    N, d = g["W_enc"].shape
+    sae = Sae(d, SaeConfig(num_latents=N, k=int(g["k"])))
+    with torch.no_grad():
+        sae.encoder.weight.copy_(torch.from_numpy(g["W_enc"]))
+        sae.encoder.bias.copy_(torch.from_numpy(g["b_enc"]))
+        sae.W_dec.copy_(torch.from_numpy(g["W_dec"]))
+        sae.b_dec.copy_(torch.from_numpy(g["b_dec"]))
+    model = _ToyLogitLM(40, d, seed=42)
+    inputs = {"input_ids": torch.from_numpy(g["input_ids"])}
+    metric = partial(get_logit_diff, answer_token_indices=torch.from_numpy(g["answers"]))
+    sae_dict, m2n = {"layers.0": sae}, {model.layers[0]: "layers.0"}
+    with torch.no_grad():
+        logits, clean = get_model_forward_cache_with_sae(model, inputs, sae_dict, m2n)
+    assert clean["layers.0"].dtype == torch.float16 and clean["layers.0"].shape == (2, 6, d)
+    np.testing.assert_allclose(logits.numpy(), g["clean_logits"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(float(metric(logits)), float(g["logit_diff_clean"]), rtol=1e-5)
+    nonzero = 0
+    for f in g["features"].tolist():
+        att = attribution_for_feature(model, inputs, sae_dict, m2n, metric, f, clean_cache=clean)["layers.0"]
+        np.testing.assert_allclose(att.float().numpy(), g[f"att_{f}"], rtol=2e-3, atol=1e-4)   # fp16 products
+        nonzero += int(np.abs(g[f"att_{f}"]).max() > 0)
+    assert nonzero >= 3
+    # several latents at once take the dense route (pre_acts -> mask -> select_topk) like the reference
+    feats = g["features"].tolist()[:2]
+    lg2, _ = get_model_forward_cache_with_sae(model, inputs, sae_dict, m2n, off_features=feats)
+    assert not np.allclose(lg2.detach().numpy(), g["clean_logits"])

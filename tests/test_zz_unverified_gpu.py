@@ -50,3 +50,30 @@ def test_decode_backward_vs_oracle(T, d, N, k):
     torch.testing.assert_close(d_acts.cpu(), ref_a, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(dW.cpu(), ref_w, rtol=1e-4, atol=1e-4)
     assert int(engine.decode_backward.last_err_flag.item()) == 0
+
+
+def test_attribution_patching_matches_reference_golden():
+    """features/patching on the device: fused encode with the latent clamped to 0, decode through the autograd seam
+    (its backward kernels run because W_dec requires grad), attribution values vs the reference's."""
+    from functools import partial
+
+    from sae_auto_interp.features.patching import attribution_for_feature, get_logit_diff
+    from sae_auto_interp.sae import Sae, SaeConfig
+    from test_host_logic import _ToyLogitLM
+
+    g = np.load(os.path.join(GOLDEN, "attribution.npz"))
+    N, d = g["W_enc"].shape
+    sae = Sae(d, SaeConfig(num_latents=N, k=int(g["k"])), device=DEV)
+    with torch.no_grad():
+        sae.encoder.weight.copy_(torch.from_numpy(g["W_enc"]))
+        sae.encoder.bias.copy_(torch.from_numpy(g["b_enc"]))
+        sae.W_dec.copy_(torch.from_numpy(g["W_dec"]))
+        sae.b_dec.copy_(torch.from_numpy(g["b_dec"]))
+    model = _ToyLogitLM(40, d, seed=42).to(DEV)
+    inputs = {"input_ids": torch.from_numpy(g["input_ids"]).to(DEV)}
+    metric = partial(get_logit_diff, answer_token_indices=torch.from_numpy(g["answers"]).to(DEV))
+    sae_dict, m2n = {"layers.0": sae}, {model.layers[0]: "layers.0"}
+    for f in g["features"].tolist():
+        att = attribution_for_feature(model, inputs, sae_dict, m2n, metric, f)["layers.0"]
+        np.testing.assert_allclose(att.float().numpy(), g[f"att_{f}"], rtol=5e-3, atol=2e-4)
+    assert sae.W_dec.grad is not None and sae.W_dec.grad.shape == sae.W_dec.shape
