@@ -11,7 +11,7 @@ from __future__ import annotations
 import torch
 
 from ..config import FeatureConfig
-from .features import FeatureRecord, prepare_examples
+from .features import FeatureRecord, prepare_examples, prepare_image_examples
 from .loader import BufferOutput
 
 
@@ -63,27 +63,69 @@ def default_constructor(record: FeatureRecord, tokens: torch.Tensor, buffer_outp
     random_activation_windows(record, tokens=tokens, buffer_output=buffer_output, n_random=n_random, ctx_len=ctx_len)
 
 
+IMAGE_SEQ_LEN = 8000   # the reference's stand-in sequence length for image rows (constructors.py:103)
+
+
+def _image_rows(locations: torch.Tensor, activations: torch.Tensor, rows, seq_len: int = IMAGE_SEQ_LEN) -> torch.Tensor:
+    """dense activation rows [len(rows), seq_len] of the selected images only (the reference densifies all
+    n_images x 8000, constructors.py:104-107)"""
+    rows_t = torch.as_tensor(rows, dtype=torch.long)
+    dense = torch.zeros((len(rows_t), seq_len), dtype=activations.dtype)
+    for slot, r in enumerate(rows_t.tolist()):
+        sel = locations[:, 0] == r
+        dense[slot].index_put_((locations[sel, 1],), activations[sel], accumulate=True)
+    return dense
+
+
+def image_scores(locations: torch.Tensor, activations: torch.Tensor, n_images: int, n_base: int) -> torch.Tensor:
+    """per-image mean activation over the first `n_base` positions = avg_pool1d(dense[:, :n_base], n_base)
+    (reference constructors.py:109-114), without the dense tensor"""
+    score = torch.zeros(n_images, dtype=activations.dtype)
+    inside = locations[:, 1] < n_base
+    score.index_add_(0, locations[inside, 0], activations[inside])
+    return score / n_base
+
+
+def _dedup_ranked(ranked, ids, max_examples: int):
+    """keep the first occurrence of every dataset id in rank order, `max_examples` of them (reference :121-135).  With
+    fewer distinct images than `max_examples` the reference raises (`len()` of an int, :131); here the best image is
+    repeated, which is what that line set out to do."""
+    seen, keep = set(), []
+    for idx, image_id in zip(ranked, ids):
+        if image_id not in seen:
+            seen.add(image_id)
+            keep.append(idx)
+    if len(keep) < max_examples:
+        keep += [keep[0]] * (max_examples - len(keep))
+    return keep[:max_examples]
+
+
 def pool_max_activations_windows_image(record: FeatureRecord, buffer_output: BufferOutput, tokens, cfg: FeatureConfig,
                                        processor=None):
-    """Image variant (reference :88-148): rank images by the mean activation over the first `num_image_tokens`
-    (576) positions.  Returns the ranked image rows in `record.examples` as (row, score) pairs; rendering the
-    activation masks onto PIL images is presentation code outside this engine."""
+    """Image variant (reference :88-148): rank images by the mean activation over the first `num_image_tokens` (576)
+    positions, take the best `max_examples + 50`, drop repeated dataset ids, keep `max_examples`; `record.examples`
+    holds one ImageExample per kept image.  `tokens` is the image dataset (`len`, `.features`, `.select(indices=)`)."""
     n_base = getattr(processor, "num_image_tokens", 576)
     loc, act = buffer_output.locations, buffer_output.activations
-    n_images = len(tokens)
-    score = torch.zeros(n_images, dtype=act.dtype)
-    inside = loc[:, 1] < n_base
-    score.index_add_(0, loc[inside, 0], act[inside])
-    score /= n_base
-    k = min(cfg.max_examples, n_images)
-    top = torch.topk(score, k)
-    record.examples = [(int(i), float(s)) for i, s in zip(top.indices, top.values)]
+    score = image_scores(loc, act, len(tokens), n_base)
+    ranked = torch.topk(score, cfg.max_examples + 50).indices.tolist()
+    if "id" in tokens.features:
+        ranked = _dedup_ranked(ranked, tokens.select(indices=ranked)["id"], cfg.max_examples)
+    else:
+        ranked = ranked[: cfg.max_examples]
+    images = tokens.select(indices=ranked)["image"]
+    record.examples = prepare_image_examples(torch.zeros(len(ranked), IMAGE_SEQ_LEN), _image_rows(loc, act, ranked),
+                                             images, processor)
 
 
 def random_activations_image(record: FeatureRecord, buffer_output: BufferOutput, tokens, cfg: FeatureConfig,
                              processor=None):
+    """`max_examples` images drawn uniformly (reference :151-181)"""
     pick = torch.randint(0, len(tokens), (cfg.max_examples,))
-    record.examples = [(int(i), 0.0) for i in pick]
+    images = tokens.select(indices=pick)["image"]
+    record.examples = prepare_image_examples(torch.zeros(len(pick), IMAGE_SEQ_LEN),
+                                             _image_rows(buffer_output.locations, buffer_output.activations, pick),
+                                             images, processor)
 
 
 def top_windows_all_features(top_acts: torch.Tensor, top_indices: torch.Tensor, num_latents: int, ctx_len: int,

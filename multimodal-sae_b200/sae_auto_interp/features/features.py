@@ -1,5 +1,5 @@
-"""Record types handed to explainers / scorers (reference features/features.py).  Only the data carriers are kept;
-image mask compositing (PIL) is host-side presentation code outside the accelerated path."""
+"""Record types handed to explainers / scorers (reference features/features.py): the data carriers, and the image
+examples (activation mask upsampled onto the resized image) that `explain_images` shows to the explainer."""
 from __future__ import annotations
 
 import json
@@ -32,6 +32,34 @@ class ImageExample(Example):
 
 def prepare_examples(tokens, activations) -> List[Example]:
     return [Example(tokens=t, activations=a) for t, a in zip(tokens, activations)]
+
+
+def upsample_mask(mask, image_size, value: int = 224):
+    """[p, p] activations -> PIL "L" mask of `image_size`: `value` where the patch is inactive (< 1e-5), 0 where it
+    fired, bilinearly resized (reference features.py:134-141)."""
+    import numpy as np
+    from PIL import Image
+
+    grey = ((mask < 1e-5).to(dtype=int).numpy() * value).astype(np.uint8)
+    return Image.fromarray(grey, mode="L").resize(image_size, Image.BILINEAR)
+
+
+def prepare_image_examples(tokens, activations, images, processor=None) -> List[ImageExample]:
+    """One `ImageExample` per (token row, activation row, PIL image): the first `num_image_tokens` activations are the
+    base image patches (24 x 24 at 576 tokens -> 336 px, else 27 x 27 -> 384 px); inactive regions of the resized
+    image are blacked out through the upsampled mask (reference features.py:49-92)."""
+    from PIL import Image
+
+    n_base = getattr(processor, "num_image_tokens", 576)
+    patches = 24 if n_base == 576 else 27
+    side = 336 if patches == 24 else 384
+    black = Image.new("L", (side, side), 0).convert("RGB")
+    out = []
+    for toks, acts, img in zip(tokens, activations, images):
+        mask = upsample_mask(acts[:n_base].view(patches, patches), (side, side))
+        shown = Image.composite(black, img.resize((side, side)), mask).convert("RGB")
+        out.append(ImageExample(tokens=toks, activations=acts, image=img, activation_image=shown, mask=mask))
+    return out
 
 
 @dataclass

@@ -23,6 +23,7 @@ sys.path.insert(0, HERE)
 
 import ref_shims  # noqa: E402
 import sae_oracle as O  # noqa: E402  (only for the synthetic-parameter generator)
+from synth_images import synth_image_cache  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 
@@ -112,6 +113,36 @@ def gen_decode_backward(ref):
                         sae_d_vals=vals_b.grad.numpy(), sae_d_W_dec=sae.W_dec.grad.numpy(),
                         sae_d_b_dec=sae.b_dec.grad.numpy())
     print("decode_backward |dW|", float(W.grad.abs().sum()))
+
+
+def gen_image_constructor(ref):
+    """pool_max_activations_windows_image / random_activations_image (features/constructors.py:88-181) +
+    prepare_image_examples (features/features.py:49-92) on a synthetic image dataset with repeated ids."""
+    from sae_auto_interp.config import FeatureConfig
+    from sae_auto_interp.features import pool_max_activations_windows_image, random_activations_image
+    from sae_auto_interp.features.features import Feature, FeatureRecord
+    from sae_auto_interp.features.loader import BufferOutput
+
+    ds, loc, act = synth_image_cache()
+    cfg = FeatureConfig(width=64, max_examples=6)
+    bo = BufferOutput(Feature("layers.0", 7), loc, act)
+    rec = FeatureRecord(bo.feature)
+    pool_max_activations_windows_image(rec, bo, ds, cfg, None)
+    out = {"n_examples": np.int64(len(rec.examples))}
+    for i, ex in enumerate(rec.examples):
+        out[f"top{i}_acts"] = ex.activations.numpy()
+        out[f"top{i}_mask"] = np.asarray(ex.mask)
+        out[f"top{i}_shown"] = np.asarray(ex.activation_image)
+        out[f"top{i}_image"] = np.asarray(ex.image)
+    torch.manual_seed(5)
+    rec2 = FeatureRecord(bo.feature)
+    random_activations_image(rec2, bo, ds, cfg, None)
+    for i, ex in enumerate(rec2.examples):
+        out[f"rand{i}_acts"] = ex.activations.numpy()
+        out[f"rand{i}_image"] = np.asarray(ex.image)
+    np.savez_compressed(os.path.join(GOLD, "image_constructor.npz"), locations=loc.numpy(), activations=act.numpy(),
+                        max_examples=np.int64(cfg.max_examples), **out)
+    print("image_constructor examples", len(rec.examples), len(rec2.examples))
 
 
 class ToyLogitLM(torch.nn.Module):
@@ -322,11 +353,12 @@ def main():
     ref.sae = ref_sae
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
     if only is not None:   # regenerate one fixture without touching the others
-        {"decode_backward": gen_decode_backward, "attribution": gen_attribution, "decode_test": gen_decode_test, "cache_chain": gen_cache_chain,
+        {"decode_backward": gen_decode_backward, "attribution": gen_attribution, "image_constructor": gen_image_constructor, "decode_test": gen_decode_test, "cache_chain": gen_cache_chain,
          "steering": gen_steering}[only](ref)
         return
     gen_decode_backward(ref)
     gen_attribution(ref)
+    gen_image_constructor(ref)
     gen_forward(ref, "forward_c1.npz", d=128, N=512, k=16, T=256, seed=1234, bf16_x=False)
     gen_forward(ref, "forward_c1_bf16.npz", d=128, N=512, k=16, T=256, seed=1235, bf16_x=True)
     gen_forward(ref, "forward_wide.npz", d=64, N=2048, k=32, T=96, seed=1236, bf16_x=True)

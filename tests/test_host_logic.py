@@ -279,3 +279,38 @@ def test_attribution_patching_matches_reference(monkeypatch):
     feats = g["features"].tolist()[:2]
     lg2, _ = get_model_forward_cache_with_sae(model, inputs, sae_dict, m2n, off_features=feats)
     assert not np.allclose(lg2.detach().numpy(), g["clean_logits"])
+
+
+def test_image_constructor_matches_reference():
+    """pool_max_activations_windows_image (features/constructors.py:88-148: mean over the 576 base image tokens, best
+    max_examples + 50, repeated dataset ids dropped) and prepare_image_examples (features/features.py:49-92: mask
+    upsampling + compositing), against the reference's examples on the same synthetic dataset."""
+    from sae_auto_interp.config import FeatureConfig
+    from sae_auto_interp.features import pool_max_activations_windows_image, random_activations_image
+    from sae_auto_interp.features.features import Feature, FeatureRecord, ImageExample
+    from sae_auto_interp.features.loader import BufferOutput
+    from synth_images import synth_image_cache
+
+    g = np.load(os.path.join(GOLDEN, "image_constructor.npz"))
+    ds, loc, act = synth_image_cache()
+    assert np.array_equal(loc.numpy(), g["locations"]) and np.array_equal(act.numpy(), g["activations"])
+    cfg = FeatureConfig(width=64, max_examples=int(g["max_examples"]))
+    bo = BufferOutput(Feature("layers.0", 7), loc, act)
+    rec = FeatureRecord(bo.feature)
+    pool_max_activations_windows_image(rec, bo, ds, cfg, None)
+    assert len(rec.examples) == int(g["n_examples"]) == cfg.max_examples
+    for i, ex in enumerate(rec.examples):
+        assert isinstance(ex, ImageExample) and ex.tokens.shape == (8000,)
+        assert np.array_equal(ex.activations.numpy(), g[f"top{i}_acts"])        # same image, same dense row
+        assert np.array_equal(np.asarray(ex.image), g[f"top{i}_image"])
+        assert np.array_equal(np.asarray(ex.mask), g[f"top{i}_mask"])
+        assert np.array_equal(np.asarray(ex.activation_image), g[f"top{i}_shown"])
+    # ranked by the mean over the base tokens, no dataset id twice
+    means = [float(ex.activations[:576].mean()) for ex in rec.examples]
+    assert means == sorted(means, reverse=True)
+    torch.manual_seed(5)
+    rec2 = FeatureRecord(bo.feature)
+    random_activations_image(rec2, bo, ds, cfg, None)
+    for i, ex in enumerate(rec2.examples):
+        assert np.array_equal(ex.activations.numpy(), g[f"rand{i}_acts"])
+        assert np.array_equal(np.asarray(ex.image), g[f"rand{i}_image"])
