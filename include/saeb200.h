@@ -41,7 +41,9 @@ long long saeb_launch_count(void);
  * activation tiles L2-resident).  "persist_a": 1 (default) = pin each launch's activation rows in the persisting part
  * of L2.  "reserve_sms": SMs the persistent GEMM grid leaves free (default 0) so that kernels of another stream --
  * the collectives of the feature-sharded scan -- have somewhere to run while a GEMM launch is in flight.
- * "l2_hints", "debug_tiles": diagnostics. */
+ * "refine_threads": threads per refinement CTA in feature-sharded calls (default 128; 256 keeps more loads in flight
+ * when the kernel runs beside a GEMM launch, where only one CTA fits per SM).  "kth_impl": see
+ * saeb_kth_largest_gathered.  "l2_hints", "debug_tiles": diagnostics. */
 int saeb_set_option(const char* name, int value);
 /* With option "profile" = 1 the library brackets the fused encode kernel (main kernel only) with CUDA events on the
  * launching stream; this returns the duration in ms of the most recent one (synchronises on it), < 0 if none. */

@@ -77,6 +77,7 @@ int coo_extract_launch(const float* vals, const long long* idx, long long T, int
 int kth_gathered_launch(const float* gathered, int R, long long T, int m, int kth, float* tok_thr,
                         cudaStream_t stream);
 int set_kth_impl(int v);
+int set_refine_threads(int v);
 int decode_bwd_acts_launch(const float* grad_out, long long ld_g, const long long* idx, long long T, int k,
                            const float* W_dec, long long d, long long N, float* d_vals, int* err_flag,
                            cudaStream_t stream);
@@ -135,6 +136,7 @@ int saeb_set_option(const char* name, int value) {
   if (strcmp(name, "chunking") == 0) return set_chunking(value);
   if (strcmp(name, "reserve_sms") == 0) return set_reserve_sms(value);
   if (strcmp(name, "kth_impl") == 0) return set_kth_impl(value);
+  if (strcmp(name, "refine_threads") == 0) return set_refine_threads(value);
   if (strcmp(name, "refine_margin") == 0) {
     g_default_margin = value;
     return 0;

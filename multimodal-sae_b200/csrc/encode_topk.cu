@@ -835,7 +835,7 @@ struct PersistWindow {
   void* base = nullptr;
   size_t bytes = 0;
 };
-static PersistWindow g_window;
+static thread_local PersistWindow g_window;   // set by the launching thread just before each launch
 
 template <int AP, int BP, int PAIR, int SLOTS>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const EncodeArgs& args, int grid,

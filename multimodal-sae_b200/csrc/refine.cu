@@ -410,6 +410,19 @@ overflow_rows_kernel(const XT* __restrict__ x, long long ld_x, const float* __re
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
+// threads per refinement CTA in feature-sharded calls (ext_lower given): a shard evaluates only ~k/R + a few candidates
+// per token, so smaller blocks keep more tokens in flight when the kernel has the GPU to itself (128, the measured
+// default); beside a persistent GEMM grid only one CTA fits per SM and 256 threads keep more loads in flight
+static int g_refine_threads_sharded = 128;
+int set_refine_threads(int v) {
+  if (v < 32 || v > RF_THREADS || (v & 31)) {
+    set_error("refine_threads must be a multiple of 32 in 32..%d", RF_THREADS);
+    return -1;
+  }
+  g_refine_threads_sharded = v;
+  return 0;
+}
+
 size_t refine_fallback_bytes(long long N) { return (size_t)RF_MAX_FLAG * (size_t)N * sizeof(float) + 1024; }
 
 template <typename XT>
@@ -425,7 +438,7 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
   auto kern = refine_kernel<XT>;
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // feature-sharded calls evaluate only a handful of candidates per token: smaller blocks, more tokens in flight
-  const int threads = ext_lower != nullptr ? 128 : RF_THREADS;
+  const int threads = ext_lower != nullptr ? g_refine_threads_sharded : RF_THREADS;
   kern<<<(unsigned)T, threads, smem, stream>>>(x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals,
                                                  cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx,
                                                  status, flag_rows, ext_lower);

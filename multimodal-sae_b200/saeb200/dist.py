@@ -113,6 +113,9 @@ class EngineOps:
         (pair it with NCCL_MAX_CTAS <= reserve_sms in the environment)."""
         if world > 1 and self.reserve_sms > 0:
             self._capi.check(self._capi.lib().saeb_set_option(b"reserve_sms", self.reserve_sms), "set_option")
+        rt = os.environ.get("SAEB_REFINE_THREADS")   # tuning knob of the co-resident refinement (see saeb200.h)
+        if rt:
+            self._capi.check(self._capi.lib().saeb_set_option(b"refine_threads", int(rt)), "set_option")
 
     def chunk_tokens(self, world: int, waves: Optional[int] = None) -> int:
         """Tokens per scan chunk = `waves` full single-wave GEMM launches (256-row tiles on half of the CTA pairs the
