@@ -125,6 +125,26 @@ def cpu_forward_tokens_per_s(sample_tokens: int, batch: int, repeats: int, seed:
     return sample_tokens / best, threads, best
 
 
+def cpu_cache_chain_tokens_per_s(sample_tokens: int, batch: int, seed: int = 1234):
+    """the reference's cache-path chain (features/cache.py:206-218 + :73-92: pre_acts -> topk -> zeros_like + scatter_
+    -> nonzero(|x| > 1e-5)) through the oracle port, on the host cores: the CPU baseline of the scan's per-token work"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import sae_oracle as O
+
+    p = O.init_params(D_IN, WIDTH, K, seed)
+    x = torch.randn(sample_tokens, D_IN, generator=torch.Generator().manual_seed(seed + 2)).to(torch.bfloat16)
+    with torch.no_grad():
+        O.get_nonzeros(O.topk_masked_latents(p, x[:64].view(1, 64, D_IN)))  # warm-up
+        t = time.perf_counter()
+        nnz = 0
+        for b0 in range(0, sample_tokens, batch):
+            loc, _ = O.get_nonzeros(O.topk_masked_latents(p, x[b0:b0 + batch].view(1, -1, D_IN)))
+            nnz += loc.shape[0]
+        dt = time.perf_counter() - t
+    return sample_tokens / dt, torch.get_num_threads(), dt, nnz
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -327,6 +347,14 @@ def run_gpu(args):
         cpu = {"value": tok_s, "unit": "tokens/s", "cores": threads, "kind": "port",
                "sample": f"oracle port of reference Sae.forward (PyTorch CPU fp32), 2048 tokens in 512-token batches, "
                          f"best of 2 ({secs:.1f} s)"}
+
+    if cpu is not None and scan is not None:
+        tok_s, threads, secs, nnz = cpu_cache_chain_tokens_per_s(1024, 512)
+        scan["cpu_baseline"] = {"value": tok_s, "unit": "tokens/s", "cores": threads, "kind": "port",
+                                "sample": f"oracle port of the reference cache chain (pre_acts -> topk -> scatter -> "
+                                          f"nonzero, features/cache.py:206-218,73-92), 1024 tokens in 512-token "
+                                          f"batches ({secs:.1f} s, {nnz} cached activations); the per-feature window "
+                                          f"ranking the reference then runs feature by feature is not included"}
 
     if rank == 0:
         line = {
