@@ -40,6 +40,8 @@ METRIC = "SAE tokens/sec (d=4096, width=131k, k=64, encode+TopK+decode)"
 PRECISION = {
     3: "one fp16 tensor-core pass (activations exact after a power-of-two row scale, W_enc rounded to fp16, fp32 "
        "accumulate) + exact fp32 re-evaluation of every candidate inside the rigorous rounding bound; fp32 W_dec",
+    4: "one fp16 tensor-core pass + refinement by residual correction (x . fp16 residual plane of W_enc added to the "
+       "tensor-core value for every candidate inside the rounding bound; values to ~1e-6 relative); fp32 W_dec",
     2: "bf16 activations (exact) x bf16 hi+lo W_enc planes (two tensor-core passes), fp32 accumulate; fp32 W_dec",
     1: "single bf16 pass (NOT parity grade; diagnostic only)",
 }
@@ -210,7 +212,7 @@ def run_gpu(args):
 
     W_dec_used = sae.W_dec.data if args.decode_dtype == "fp32" else sae.W_dec.data.to(torch.float16)
     ov = None
-    if args.planes == 3 and not args.no_overlap:
+    if args.planes in (3, 4) and not args.no_overlap:
         from saeb200.overlap import OverlappedForward
 
         ov = OverlappedForward(enc, W_dec_used, sae.b_dec.data, K, chunk=args.chunk)
@@ -272,10 +274,10 @@ def run_gpu(args):
                 "avg_launch_ms": k_avg * wave_tokens / TOKENS,
                 "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
                 "traffic": traffic, "peak_source": f"{peaks['source']} bf16 sustained (cuBLAS, MEASURED_PEAKS.json)",
-                "kernel_ms": k_avg, "mma_passes": 1 if enc.planes == 3 else enc.planes,
+                "kernel_ms": k_avg, "mma_passes": 1 if enc.planes >= 3 else enc.planes,
                 "path_frac": (value / world) * FLOPS_PER_TOKEN / 1e12 / peaks["tflops_sustained"],
                 "hbm_frac": (value / world) * (2 * D_IN + K * 12 + K * 4 * D_IN + 4 * D_IN
-                                               + 2.0 * D_IN * WIDTH * (1 if enc.planes == 3 else enc.planes) / TOKENS)
+                                               + 2.0 * D_IN * WIDTH * (1 if enc.planes >= 3 else enc.planes) / TOKENS)
                 / 1e9 / peaks["hbm_gbs"]}
 
     # ---- the same step with an fp16 copy of W_dec: half the decode gather bytes, row error ~2e-4 -- inside the 1e-3
@@ -427,8 +429,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=18944, help="tokens per pipeline chunk (multiple of 9472 = one wave)")
     ap.add_argument("--decode-dtype", default="fp32", choices=["fp32", "fp16"],
                     help="W_dec copy the decode gathers from: fp32 (parity default) or fp16 (half the bytes, ~2e-4 row error)")
-    ap.add_argument("--planes", type=int, default=3, choices=[1, 2, 3],
-                    help="encoder mode: 3 = fp16 pass + exact refinement (default), 2 = bf16 hi+lo, 1 = bf16 (diagnostic)")
+    ap.add_argument("--planes", type=int, default=3, choices=[1, 2, 3, 4],
+                    help="encoder mode: 3 = fp16 pass + exact refinement (default), 4 = fp16 pass + residual-correction "
+                         "refinement, 2 = bf16 hi+lo, 1 = bf16 (diagnostic)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

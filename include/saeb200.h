@@ -60,7 +60,8 @@ long long saeb_query(const char* name);
 /* ---- one-time weight repack -------------------------------------------------------------------------------
  * Reference parameters: `encoder.weight [N,d]`, `encoder.bias [N]`, `b_dec [d]` fp32 (sae/sae.py:59-66, loaded by
  * Sae.load_from_disk sae/sae.py:126-148).  Produces `planes` bf16 planes of W_enc (1: bf16(W); 2: hi + lo, the
- * parity-grade mode; 3: the "fp16 + refine" layout used by saeb_encode_topk_refine) followed by the folded bias b_enc - W_enc b_dec (sae/sae.py:174-175 rewritten as
+ * parity-grade mode; 3: the "fp16 + refine" layout used by saeb_encode_topk_refine; 4: layout 3 plus the fp16 residual
+ * plane used by saeb_refine_candidates_lo) followed by the folded bias b_enc - W_enc b_dec (sae/sae.py:174-175 rewritten as
  * W x + (b_enc - W b_dec)).  Layout of `packed`: [planes][N][d_pad] bf16 with d_pad = d rounded up to 8 (16-byte
  * rows for TMA, zero padded), then [N] fp32 at saeb_packed_bias_offset().  Any d >= 1 is accepted. */
 size_t saeb_packed_weights_bytes(int64_t N, int64_t d, int planes);
@@ -121,6 +122,19 @@ int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void*
                            int64_t clamp_feature, float clamp_value, const float* ext_lower, int already_merged,
                            float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
                            size_t workspace_bytes, void* stream);
+/* "fp16 hi + lo" refinement (packed mode 4 = saeb_pack_weights(..., planes = 4): the mode-3 blob followed by an fp16
+ * plane of the residual W - fp16(W), scaled by 2^11; every mode-3 entry point accepts a mode-4 blob unchanged).
+ * saeb_refine_candidates_lo is saeb_refine_candidates with the exact re-evaluation replaced by a correction: the
+ * approximate value x . W_hi + bias already came out of the tensor cores, only x . W_lo is added -- the gather reads
+ * 2*d instead of 4*d bytes per candidate.  Exact in the operands for bf16 / fp16 activations (fp32 activations are
+ * rounded on their way into the tensor cores, so they silently take the exact route); the corrected values carry the
+ * tensor cores' fp32 accumulation noise (~1e-6 relative, the grade of any fp32 GEMM) instead of 3e-7.  The flagged-row
+ * fallback is the same exact dense path (needs W_enc). */
+int saeb_refine_candidates_lo(const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total, int64_t t0,
+                              int64_t Tc, const void* packed4, const float* W_enc, int64_t d, int64_t N, int k,
+                              int margin, int64_t clamp_feature, float clamp_value, const float* ext_lower,
+                              int already_merged, float* out_vals, int64_t* out_idx, int32_t* status_out,
+                              void* workspace, size_t workspace_bytes, void* stream);
 /* Feature-sharded use (every GPU holds N/R features, sees all tokens): after saeb_encode_candidates,
  * saeb_candidate_bounds merges this shard's candidates and writes, per token, its k largest LOWER bounds
  * a_j - eps_j (descending, lb_out [Tc,k]).  All-gather them, take the per-token k-th largest (saeb_kth_of_gathered):

@@ -47,7 +47,9 @@ int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const
                   const float* xdnorm, float c_eps,
                   const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                   float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
-                  float* dense_scratch, const float* ext_lower, cudaStream_t stream);
+                  float* dense_scratch, const float* ext_lower, const void* w_lo, long long ld_w, cudaStream_t stream);
+int pack_weights_lo_launch(const float* W_enc, long long N, long long d, long long d_pad, const float* trailer,
+                           void* lo_plane, cudaStream_t stream);
 int candidate_bounds_launch(const float* cand_vals, const long long* cand_idx, long long T, int K2, int k,
                             const float* wnorm, const float* dnorm, const float* xnorm, const float* xdnorm,
                             float c_eps, long long clamp_feature, float* lb_out, cudaStream_t stream);
@@ -100,8 +102,10 @@ float last_encode_ms();
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline long long pad8(long long d) { return (d + 7) / 8 * 8; }   // 16-byte row strides for TMA
-// planes: 1 / 2 = bf16 planes; 3 = "fp16 + refine" mode (one scaled fp16 plane + per-feature norms + trailer)
-static inline int n_planes(int planes) { return planes == 3 ? 1 : planes; }
+// planes: 1 / 2 = bf16 planes; 3 = "fp16 + refine" mode (one scaled fp16 plane + per-feature norms + trailer);
+// 4 = mode 3 followed by the fp16 residual plane (every mode-3 offset is unchanged: a mode-4 blob IS a mode-3 blob)
+static inline int n_planes(int planes) { return planes >= 3 ? 1 : planes; }
+static inline size_t mode3_bytes(long long N, long long d);
 static inline size_t planes_bytes(long long N, long long d, int planes) {
   return align_up((size_t)n_planes(planes) * (size_t)N * (size_t)pad8(d) * 2, 256);
 }
@@ -111,6 +115,10 @@ static inline size_t bias_bytes(long long N) { return align_up((size_t)N * sizeo
 static inline size_t x_split_bytes(long long T, long long d, int x_dtype) {
   if (x_dtype == DT_BF16 && d % 8 == 0) return 0;
   return align_up((size_t)(x_dtype == DT_BF16 ? 1 : 2) * (size_t)T * (size_t)pad8(d) * 2, 1024);
+}
+
+static inline size_t mode3_bytes(long long N, long long d) {
+  return align_up(planes_bytes(N, d, 3) + 3 * bias_bytes(N) + 256, 1024);
 }
 
 }  // namespace saeb
@@ -174,7 +182,8 @@ long long saeb_query(const char* name) {
 size_t saeb_packed_bias_offset(int64_t N, int64_t d, int planes) { return planes_bytes(N, d, planes); }
 size_t saeb_packed_weights_bytes(int64_t N, int64_t d, int planes) {
   // bias [N]; mode 3 appends ||w_j|| [N], ||w_j - fp16(w_j)|| [N] and a 256-byte trailer
-  // {w_unscale, max ||w_j||, scratch, max rounding-error norm}
+  // {w_unscale, max ||w_j||, scratch, max rounding-error norm}; mode 4 appends the residual plane after that
+  if (planes == 4) return mode3_bytes(N, d) + planes_bytes(N, d, 3);
   return planes_bytes(N, d, planes) + bias_bytes(N) + (planes == 3 ? 2 * bias_bytes(N) + 256 : 0);
 }
 
@@ -182,15 +191,20 @@ int saeb_pack_weights(const float* W_enc, const float* b_enc, const float* b_dec
                       void* packed, void* stream) {
   g_err[0] = 0;
   SAEB_REQUIRE(W_enc && b_enc && b_dec && packed, "pack_weights: null pointer");
-  SAEB_REQUIRE(planes >= 1 && planes <= 3, "pack_weights: planes must be 1, 2 or 3");
+  SAEB_REQUIRE(planes >= 1 && planes <= 4, "pack_weights: planes must be 1, 2, 3 or 4");
   float* bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + planes_bytes(N, d, planes));
-  if (planes == 3) {
+  if (planes >= 3) {
     float* wnorm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bias) + bias_bytes(N));
     float* dnorm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(wnorm) + bias_bytes(N));
     float* trailer = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(dnorm) + bias_bytes(N));
     int rc3 = pack_weights_f16_launch(W_enc, b_enc, b_dec, N, d, pad8(d), packed, bias, wnorm, dnorm, trailer,
                                       (cudaStream_t)stream);
     if (rc3 == 0) g_launches += 2;
+    if (rc3 == 0 && planes == 4) {
+      rc3 = pack_weights_lo_launch(W_enc, N, d, pad8(d), trailer, reinterpret_cast<uint8_t*>(packed) + mode3_bytes(N, d),
+                                   (cudaStream_t)stream);
+      if (rc3 == 0) g_launches += 1;
+    }
     return rc3;
   }
   int rc = pack_weights_launch(W_enc, b_enc, b_dec, N, d, pad8(d), planes, packed, bias, (cudaStream_t)stream);
@@ -386,11 +400,11 @@ int saeb_candidate_bounds(const void* prep, int64_t T_total, int64_t t0, int64_t
   return rc;
 }
 
-int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total, int64_t t0,
-                           int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N, int k, int margin,
-                           int64_t clamp_feature, float clamp_value, const float* ext_lower, int already_merged,
-                           float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
-                           size_t workspace_bytes, void* stream) {
+static int refine_candidates_impl(bool lo, const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total,
+                                  int64_t t0, int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N,
+                                  int k, int margin, int64_t clamp_feature, float clamp_value, const float* ext_lower,
+                                  int already_merged, float* out_vals, int64_t* out_idx, int32_t* status_out,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
   g_err[0] = 0;
   SAEB_REQUIRE(x && prep && packed && W_enc && out_vals && out_idx && workspace, "refine_candidates: null pointer");
   SAEB_REQUIRE(t0 >= 0 && Tc >= 0 && t0 + Tc <= T_total, "refine_candidates: bad row range");
@@ -421,12 +435,33 @@ int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void*
                      reinterpret_cast<const float*>(pb + p.xnorm) + t0,
                      reinterpret_cast<const float*>(pb + p.xdnorm) + t0, refine_c_eps(x_dtype), mvals, midx, K2,
                      k < K2 ? k : K2, clamp_feature, clamp_value, out_vals, reinterpret_cast<long long*>(out_idx), status,
-                     reinterpret_cast<int*>(ws + w.flag_rows), reinterpret_cast<float*>(ws + w.dense), ext_lower, st);
+                     reinterpret_cast<int*>(ws + w.flag_rows), reinterpret_cast<float*>(ws + w.dense), ext_lower,
+                     lo ? pk + mode3_bytes(N, d) : nullptr, pad8(d), st);
   if (rc) return rc;
   if (status_out != nullptr)
     SAEB_CHECK_CUDA(cudaMemcpyAsync(status_out, status, sizeof(int), cudaMemcpyDeviceToDevice, st));
   g_launches += 6;
   return 0;
+}
+
+int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total, int64_t t0,
+                           int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N, int k, int margin,
+                           int64_t clamp_feature, float clamp_value, const float* ext_lower, int already_merged,
+                           float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  return refine_candidates_impl(false, x, x_dtype, ld_x, prep, T_total, t0, Tc, packed, W_enc, d, N, k, margin,
+                                clamp_feature, clamp_value, ext_lower, already_merged, out_vals, out_idx, status_out,
+                                workspace, workspace_bytes, stream);
+}
+
+int saeb_refine_candidates_lo(const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total, int64_t t0,
+                              int64_t Tc, const void* packed4, const float* W_enc, int64_t d, int64_t N, int k,
+                              int margin, int64_t clamp_feature, float clamp_value, const float* ext_lower,
+                              int already_merged, float* out_vals, int64_t* out_idx, int32_t* status_out,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  return refine_candidates_impl(true, x, x_dtype, ld_x, prep, T_total, t0, Tc, packed4, W_enc, d, N, k, margin,
+                                clamp_feature, clamp_value, ext_lower, already_merged, out_vals, out_idx, status_out,
+                                workspace, workspace_bytes, stream);
 }
 
 size_t saeb_encode_topk_refine_workspace_bytes(int64_t T, int64_t d, int64_t N, int k, int margin) {

@@ -167,6 +167,32 @@ int pack_weights_f16_launch(const float* W_enc, const float* b_enc, const float*
   return 0;
 }
 
+// mode 4 = mode 3 + the residual plane: lo = fp16((W * scale - hi) * 2^11) with the hi plane's power-of-two scale (read
+// back from trailer[0], written by pack_w_f16_kernel earlier in the stream); hi + lo / 2^11 reproduces W * scale to
+// 2^-22 relative.  The fp16 rounding error of a value below 2^14 is at most 4, so the scaled residual stays below 2^13.
+__global__ void pack_w_lo_kernel(const float* __restrict__ W, long long N, long long d, long long d_pad,
+                                 const float* __restrict__ trailer, __half* __restrict__ lo) {
+  const float scale = 1.0f / trailer[0];   // exact: trailer[0] is a power of two
+  const long long total = N * d_pad;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / d_pad, c = i - r * d_pad;
+    const float ws = (c < d) ? W[r * d + c] * scale : 0.f;
+    const float hi = __half2float(__float2half_rn(ws));
+    lo[i] = __float2half_rn((ws - hi) * 2048.0f);
+  }
+}
+
+int pack_weights_lo_launch(const float* W_enc, long long N, long long d, long long d_pad, const float* trailer,
+                           void* lo_plane, cudaStream_t stream) {
+  const long long total = N * d_pad;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  pack_w_lo_kernel<<<(int)blocks, 256, 0, stream>>>(W_enc, N, d, d_pad, trailer, reinterpret_cast<__half*>(lo_plane));
+  SAEB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // activations -> one fp16 plane [T][d_pad], each row scaled by a power of two so that its largest element lands in
 // [2^13, 2^14); row_scale[t] undoes it; xnorm[t] >= ||x_t||_2 (of the original activations).  bf16 / fp16 inputs are
 // represented exactly (up to fp16 underflow 2^-28 below the row maximum); fp32 inputs are rounded to 11 bits.

@@ -16,6 +16,8 @@
 //     the candidate list might be too short: the row is FLAGGED and recomputed by the exact dense kernels below.
 // Output values are fp32-exact like the reference's (sae/sae.py:172-181), the index set is the reference's up to
 // fp32 summation noise; the gather is HBM-bound (about (k + 20) fp32 rows per token).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace saeb {
@@ -24,18 +26,25 @@ constexpr int RF_THREADS = 256;
 constexpr int RF_MAX_FLAG = 64;   // flagged rows handled by the wide (all-SM) fallback; further rows take the
                                   // one-block-per-row overflow path, so any number of flagged rows stays exact
 
-template <typename XT>
-__global__ void __launch_bounds__(RF_THREADS)
-refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict__ W, long long d, long long N,
-              const float* __restrict__ bias, const float* __restrict__ wnorm, const float* __restrict__ dnorm,
-              const float* __restrict__ trailer, const float* __restrict__ xnorm, const float* __restrict__ xdnorm,
-              float c_eps, const float* __restrict__ cand_vals,
-              const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
-              float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
-              int* __restrict__ flag_rows, const float* __restrict__ ext_lower) {
+// LO = false: candidates are re-evaluated exactly against the fp32 row W[f] (the parity default).
+// LO = true ("fp16 hi + lo", packed mode 4): the approximate value a_j = x . W_hi[f] + bias already comes out of the
+// tensor cores; only the missing part x . W_lo[f] is added, W_lo = fp16 plane of the residual (W_hi + W_lo = W to
+// 2^-22) -- half the gather bytes.  Exact for bf16 / fp16 activations (they reach the tensor cores unrounded); the
+// corrected values carry the tensor cores' fp32 accumulation noise (~1e-6 relative, like any fp32 GEMM) instead of
+// the 3e-7 of the exact route.
+template <typename XT, bool LO>
+__device__ __forceinline__ void
+refine_body(const XT* __restrict__ x, long long ld_x, const float* __restrict__ W, long long d, long long N,
+            const float* __restrict__ bias, const float* __restrict__ wnorm, const float* __restrict__ dnorm,
+            const float* __restrict__ trailer, const float* __restrict__ xnorm, const float* __restrict__ xdnorm,
+            float c_eps, const float* __restrict__ cand_vals,
+            const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
+            float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
+            int* __restrict__ flag_rows, const float* __restrict__ ext_lower, const __half* __restrict__ Wlo,
+            long long ld_w) {
   extern __shared__ float rsm[];
   float* xs = rsm;                                   // [d4] activations of this row as fp32
-  const int d4 = (int)((d + 3) & ~3ll);
+  const int d4 = LO ? (int)((d + 7) & ~7ll) : (int)((d + 3) & ~3ll);   // LO: padded like the packed weight rows
   float* a = xs + d4;                                // [K2] approximate values
   float* lb = a + K2;                                // [K2]
   float* ub = lb + K2;                               // [K2]
@@ -91,6 +100,41 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict_
     float val;
     if (fj == clamp_feature) {
       val = clamp_value;
+    } else if constexpr (LO) {
+      // residual correction: 8 halves per 16-byte load; rows are zero padded to d_pad (multiple of 8), xs to d4
+      const uint4* w8 = reinterpret_cast<const uint4*>(Wlo + (long long)fj * ld_w);
+      const float4* x4 = reinterpret_cast<const float4*>(xs);
+      const int n8 = d4 >> 3;
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      auto fma8 = [&](uint4 wv, int c8) {
+        const float2 w0 = __half22float2(*reinterpret_cast<const __half2*>(&wv.x));
+        const float2 w1 = __half22float2(*reinterpret_cast<const __half2*>(&wv.y));
+        const float2 w2 = __half22float2(*reinterpret_cast<const __half2*>(&wv.z));
+        const float2 w3 = __half22float2(*reinterpret_cast<const __half2*>(&wv.w));
+        const float4 xa = x4[2 * c8], xb = x4[2 * c8 + 1];
+        acc0 = fmaf(w0.x, xa.x, acc0);
+        acc1 = fmaf(w0.y, xa.y, acc1);
+        acc2 = fmaf(w1.x, xa.z, acc2);
+        acc3 = fmaf(w1.y, xa.w, acc3);
+        acc0 = fmaf(w2.x, xb.x, acc0);
+        acc1 = fmaf(w2.y, xb.y, acc1);
+        acc2 = fmaf(w3.x, xb.z, acc2);
+        acc3 = fmaf(w3.y, xb.w, acc3);
+      };
+      int c = lane;
+      for (; c + 7 * 32 < n8; c += 8 * 32) {
+        uint4 wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) wv[u] = ldg_nc_u4(w8 + c + u * 32);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) fma8(wv[u], c + u * 32);
+      }
+      for (; c < n8; c += 32) fma8(ldg_nc_u4(w8 + c), c);
+      float acc = (acc0 + acc1) + (acc2 + acc3);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      // a_j = x . W_hi + folded bias (tensor cores); W_lo carries the residual times 2^11 in the hi plane's scale
+      val = fmaf(acc, trailer[0] * (1.0f / 2048.0f), a[j]);
     } else {
       const float* wr = W + (long long)fj * d;
       float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
@@ -199,6 +243,32 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict_
       filled += __popc(m);
     }
   }
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(RF_THREADS)
+refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict__ W, long long d, long long N,
+              const float* __restrict__ bias, const float* __restrict__ wnorm, const float* __restrict__ dnorm,
+              const float* __restrict__ trailer, const float* __restrict__ xnorm, const float* __restrict__ xdnorm,
+              float c_eps, const float* __restrict__ cand_vals,
+              const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
+              float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
+              int* __restrict__ flag_rows, const float* __restrict__ ext_lower) {
+  refine_body<XT, false>(x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k,
+                         clamp_feature, clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, nullptr, 0);
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(RF_THREADS)
+refine_lo_kernel(const XT* __restrict__ x, long long ld_x, const __half* __restrict__ Wlo, long long ld_w, long long d,
+                 long long N, const float* __restrict__ bias, const float* __restrict__ wnorm,
+                 const float* __restrict__ dnorm, const float* __restrict__ trailer, const float* __restrict__ xnorm,
+                 const float* __restrict__ xdnorm, float c_eps, const float* __restrict__ cand_vals,
+                 const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
+                 float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
+                 int* __restrict__ flag_rows, const float* __restrict__ ext_lower) {
+  refine_body<XT, true>(x, ld_x, nullptr, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx,
+                        K2, k, clamp_feature, clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, Wlo, ld_w);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -431,17 +501,38 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
                            const float* xnorm, const float* xdnorm, float c_eps,
                            const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                            float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
-                           float* dense_scratch, const float* ext_lower, cudaStream_t stream) {
-  const int d4 = (int)((d + 3) & ~3ll);
-  const size_t smem = (size_t)(d4 + 5 * K2) * sizeof(float);
-  SAEB_REQUIRE(smem <= 200 * 1024, "refine: d=%lld too large for the shared-memory row buffer", d);
-  auto kern = refine_kernel<XT>;
-  SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                           float* dense_scratch, const float* ext_lower, const __half* w_lo, long long ld_w,
+                           cudaStream_t stream) {
   // feature-sharded calls evaluate only a handful of candidates per token: smaller blocks, more tokens in flight
   const int threads = ext_lower != nullptr ? g_refine_threads_sharded : RF_THREADS;
-  kern<<<(unsigned)T, threads, smem, stream>>>(x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals,
-                                                 cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx,
-                                                 status, flag_rows, ext_lower);
+  bool use_lo = false;
+  if constexpr (!std::is_same<XT, float>::value) {
+    use_lo = w_lo != nullptr;
+  }
+  if constexpr (!std::is_same<XT, float>::value) if (use_lo) {
+    // residual-plane correction (packed mode 4); fp32 activations are rounded on their way into the tensor cores,
+    // which the residual of W cannot correct, so they always take the exact route below
+    const int d8 = (int)((d + 7) & ~7ll);
+    const size_t smem = (size_t)(d8 + 5 * K2) * sizeof(float);
+    SAEB_REQUIRE(smem <= 200 * 1024, "refine: d=%lld too large for the shared-memory row buffer", d);
+    SAEB_REQUIRE(ld_w >= d8 && (reinterpret_cast<uintptr_t>(w_lo) & 15) == 0 && ld_w % 8 == 0,
+                 "refine: residual plane must be 16-byte aligned with rows padded to a multiple of 8");
+    auto kern = refine_lo_kernel<XT>;
+    SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)T, threads, smem, stream>>>(x, ld_x, w_lo, ld_w, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm,
+                                                   c_eps, cand_vals, cand_idx, K2, k, clamp_feature, clamp_value,
+                                                   out_vals, out_idx, status, flag_rows, ext_lower);
+  }
+  if (!use_lo) {
+    const int d4 = (int)((d + 3) & ~3ll);
+    const size_t smem = (size_t)(d4 + 5 * K2) * sizeof(float);
+    SAEB_REQUIRE(smem <= 200 * 1024, "refine: d=%lld too large for the shared-memory row buffer", d);
+    auto kern = refine_kernel<XT>;
+    SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)T, threads, smem, stream>>>(x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps,
+                                                   cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals,
+                                                   out_idx, status, flag_rows, ext_lower);
+  }
   SAEB_CHECK_CUDA(cudaGetLastError());
   // exact dense fallback for the (normally zero) flagged rows; the grids exit at once when nothing is flagged
   auto ek = exact_rows_kernel<XT>;
@@ -470,12 +561,12 @@ int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const
                   const float* xdnorm, float c_eps,
                   const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                   float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
-                  float* dense_scratch, const float* ext_lower, cudaStream_t stream) {
+                  float* dense_scratch, const float* ext_lower, const void* w_lo, long long ld_w, cudaStream_t stream) {
 #define SAEB_RF(XT)                                                                                                  \
   return refine_launch_t<XT>(reinterpret_cast<const XT*>(x), T, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm,   \
                              xdnorm, c_eps,                                                                          \
                              cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx, status,      \
-                             flag_rows, dense_scratch, ext_lower, stream)
+                             flag_rows, dense_scratch, ext_lower, reinterpret_cast<const __half*>(w_lo), ld_w, stream)
   if (x_dtype == DT_F32) SAEB_RF(float);
   if (x_dtype == DT_BF16) SAEB_RF(__nv_bfloat16);
   if (x_dtype == DT_F16) SAEB_RF(__half);

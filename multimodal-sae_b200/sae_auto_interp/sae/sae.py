@@ -58,7 +58,8 @@ class Sae(nn.Module):
             self.set_decoder_norm_to_unit_norm()
         self.b_dec = nn.Parameter(torch.zeros(d_in, dtype=dtype, device=device))
         # device-side repack of the encoder, rebuilt when parameters change.  encoder_planes selects the parity-grade
-        # mode of `encode`: 3 = one fp16 tensor-core pass + exact fp32 refinement (default), 2 = bf16 hi+lo (two passes)
+        # mode of `encode`: 3 = one fp16 tensor-core pass + exact fp32 refinement (default), 2 = bf16 hi+lo (two passes),
+        # 4 = mode 3 with the refinement done by residual correction (half the gather bytes, values to ~1e-6)
         self.encoder_planes = 3
         self._packed = {}
         self._overlap = None
@@ -168,7 +169,7 @@ class Sae(nn.Module):
         assert self.W_dec is not None, "Decoder weight was not initialized."
         x2 = x.reshape(-1, self.d_in)
         T = x2.shape[0]
-        if self.encoder_planes == 3 and T >= 2 * self.overlap_chunk and x2.is_cuda:
+        if self.encoder_planes in (3, 4) and T >= 2 * self.overlap_chunk and x2.is_cuda:
             # large batches: GEMM of chunk c+1 overlaps the HBM-bound refinement + decode of chunk c (two streams)
             from saeb200.overlap import OverlappedForward
 

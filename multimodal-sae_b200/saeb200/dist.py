@@ -145,7 +145,7 @@ class EngineOps:
         x2 = eng._as_2d(x, enc.d_in)
         self._x[slot], self._k[slot] = x2, k
         T = x2.shape[0]
-        if enc.planes != 3:
+        if enc.planes < 3:
             vals, idx, _ = eng.encode_topk(x2, enc, k)
             self._cached[slot] = (vals, idx + self.feat_lo)
             return vals
@@ -171,15 +171,16 @@ class EngineOps:
     def local_topk(self, ext_L=None, slot=0):
         eng, L = self.engine, self._capi.lib()
         enc, x2, k = self.enc, self._x[slot], self._k[slot]
-        if enc.planes != 3:
+        if enc.planes < 3:
             return self._cached[slot]
+        refine = L.saeb_refine_candidates_lo if enc.planes == 4 else L.saeb_refine_candidates
         T = x2.shape[0]
         dev = x2.device
         vals = torch.empty((T, k), dtype=torch.float32, device=dev)
         idx = torch.empty((T, k), dtype=torch.int64, device=dev)
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream().cuda_stream
-            self._capi.check(L.saeb_refine_candidates(
+            self._capi.check(refine(
                 x2.data_ptr(), eng._code(x2), x2.stride(0) if T > 1 else enc.d_in, self._prep[slot].data_ptr(), T, 0, T,
                 enc.blob.data_ptr(), enc.W_enc.data_ptr(), enc.d_in, enc.num_latents, k, 0, -1, 0.0,
                 None if ext_L is None else ext_L.data_ptr(), 1, vals.data_ptr(), idx.data_ptr(), self.status.data_ptr(),

@@ -59,8 +59,9 @@ class PackedEncoder:
     blob: torch.Tensor  # uint8
     num_latents: int
     d_in: int
-    planes: int  # 1 / 2: bf16 planes (2 = hi+lo, parity grade); 3: one fp16 plane + exact refinement (parity grade)
-    W_enc: Optional[torch.Tensor] = None  # mode 3 re-evaluates candidates against the fp32 parameter itself
+    planes: int  # 1 / 2: bf16 planes (2 = hi+lo, parity grade); 3: one fp16 plane + exact refinement (parity grade);
+    # 4: mode 3 plus the fp16 residual plane -- refinement by residual correction (half the gather bytes, ~1e-6 values)
+    W_enc: Optional[torch.Tensor] = None  # modes 3 / 4 re-evaluate candidates against the fp32 parameter itself
 
     @staticmethod
     def pack(W_enc: torch.Tensor, b_enc: torch.Tensor, b_dec: torch.Tensor, planes: int = 2) -> "PackedEncoder":
@@ -75,7 +76,7 @@ class PackedEncoder:
         with torch.cuda.device(W.device):
             check(L.saeb_pack_weights(W.data_ptr(), be.data_ptr(), bd.data_ptr(), N, d, planes, blob.data_ptr(),
                                       _stream()), "saeb_pack_weights")
-        return PackedEncoder(blob, N, d, planes, W if planes == 3 else None)
+        return PackedEncoder(blob, N, d, planes, W if planes >= 3 else None)
 
     def folded_bias(self) -> torch.Tensor:
         off = _capi.lib().saeb_packed_bias_offset(self.num_latents, self.d_in, self.planes)
@@ -112,7 +113,7 @@ def encode_topk(x: torch.Tensor, enc: PackedEncoder, k: int, *, clamp_feature: i
         x2 = x2.to(torch.float32)
     T = x2.shape[0]
     dev = x2.device
-    if enc.planes == 3 and want_dense:
+    if enc.planes >= 3 and want_dense:
         raise SaebError("dense pre-activations need a bf16 hi+lo packed encoder (planes=2), not the refine mode")
     vals = idx = None
     if want_topk:
@@ -133,6 +134,25 @@ def encode_topk(x: torch.Tensor, enc: PackedEncoder, k: int, *, clamp_feature: i
                                             clamp_feature, float(clamp_value), vals.data_ptr(), idx.data_ptr(),
                                             status.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
                   "saeb_encode_topk_refine")
+        encode_topk.last_status = status
+    elif T > 0 and enc.planes == 4:
+        # the staged entry points, with the residual-correction refinement
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            prep = _workspace(dev, L.saeb_prep_bytes(T, enc.d_in), "prep4")
+            ws = _workspace(dev, L.saeb_candidates_workspace_bytes(T, enc.d_in, enc.num_latents, k, refine_margin),
+                            "cand4")
+            st, code, ldx = _stream(), _code(x2), (x2.stride(0) if T > 1 else enc.d_in)
+            check(L.saeb_prep_activations(x2.data_ptr(), code, T, ldx, enc.d_in, prep.data_ptr(), st),
+                  "saeb_prep_activations")
+            check(L.saeb_encode_candidates(prep.data_ptr(), T, 0, T, enc.blob.data_ptr(), enc.d_in, enc.num_latents, k,
+                                           refine_margin, clamp_feature, float(clamp_value), ws.data_ptr(), ws.numel(),
+                                           st), "saeb_encode_candidates")
+            check(L.saeb_refine_candidates_lo(x2.data_ptr(), code, ldx, prep.data_ptr(), T, 0, T, enc.blob.data_ptr(),
+                                              enc.W_enc.data_ptr(), enc.d_in, enc.num_latents, k, refine_margin,
+                                              clamp_feature, float(clamp_value), None, 0, vals.data_ptr(),
+                                              idx.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), st),
+                  "saeb_refine_candidates_lo")
         encode_topk.last_status = status
     elif T > 0:
         with torch.cuda.device(dev):

@@ -23,8 +23,8 @@ WAVE_TOKENS = 9472  # 37 token tiles of 256 rows: one wave of (tile, split) unit
 class OverlappedForward:
     def __init__(self, enc: engine.PackedEncoder, W_dec: torch.Tensor, b_dec: torch.Tensor, k: int,
                  chunk: int = 2 * WAVE_TOKENS):
-        if enc.planes != 3:
-            raise _capi.SaebError("OverlappedForward needs the refine-mode packed encoder (planes=3)")
+        if enc.planes not in (3, 4):
+            raise _capi.SaebError("OverlappedForward needs a refine-mode packed encoder (planes = 3 or 4)")
         self.enc, self.W_dec, self.b_dec, self.k, self.chunk = enc, W_dec, b_dec, k, chunk
         dev = enc.blob.device
         self.dev = dev
@@ -44,6 +44,7 @@ class OverlappedForward:
         outputs are complete.  Returns after ENQUEUEING; the caller's current stream waits for completion."""
         L = _capi.lib()
         enc, k = self.enc, self.k
+        refine = L.saeb_refine_candidates_lo if enc.planes == 4 else L.saeb_refine_candidates
         T = x.shape[0]
         n_chunks = (T + self.chunk - 1) // self.chunk
         main = torch.cuda.current_stream()
@@ -80,7 +81,7 @@ class OverlappedForward:
                     ev_a[c].record(self.s_gemm)
                 with torch.cuda.stream(self.s_mem):
                     self.s_mem.wait_event(ev_a[c])
-                    check(L.saeb_refine_candidates(x.data_ptr() + a * ldx * esz, code, ldx, prep.data_ptr(), T, a,
+                    check(refine(x.data_ptr() + a * ldx * esz, code, ldx, prep.data_ptr(), T, a,
                                                    b - a, enc.blob.data_ptr(), enc.W_enc.data_ptr(), enc.d_in,
                                                    enc.num_latents, k, 0, -1, 0.0, None, 0, acts[a:b].data_ptr(),
                                                    idx[a:b].data_ptr(), self.status[c & 1:].data_ptr(), ws.data_ptr(),

@@ -24,7 +24,7 @@ class HostForward:
         self.h2d_bytes = num_tokens * d * self.x_dev.element_size()
         self.d2h_bytes = num_tokens * k * 12 + 4
         self.overlap = None
-        if sae.encoder_planes == 3:
+        if sae.encoder_planes in (3, 4):
             from .overlap import OverlappedForward
 
             self.overlap = OverlappedForward(sae.packed_encoder(), sae.W_dec.data, sae.b_dec.data, k, self.chunk)
