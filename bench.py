@@ -314,6 +314,46 @@ def run_gpu(args):
         except Exception as exc:   # a diagnostic line must never take the benchmark down
             alt = {"error": repr(exc)[:300]}
 
+    # ---- opt-in (--alt-mode4): the same step with the residual-correction refinement (packed mode 4) and, on top of
+    # it, the fp16 W_dec copy; both inside the 1e-3 bar, reported next to `value`
+    alt4 = None
+    if world == 1 and args.alt_mode4 and args.planes == 3 and not args.no_overlap:
+        try:
+            from saeb200.overlap import OverlappedForward
+
+            enc4 = sae.packed_encoder(4)
+            out4 = torch.empty_like(sae_out)
+            acts4, idx4, sq4 = torch.empty_like(acts), torch.empty_like(idx), torch.zeros_like(sq_err)
+            alt4 = {}
+            for tag, Wd in (("fp32_decode", sae.W_dec.data), ("fp16_decode", sae.W_dec.data.to(torch.float16))):
+                ov4 = OverlappedForward(enc4, Wd, sae.b_dec.data, K, chunk=args.chunk)
+                for _ in range(2):
+                    ov4.run(x, acts4, idx4, out4, sq4)
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(args.steps):
+                    sq4.zero_()
+                    ov4.run(x, acts4, idx4, out4, sq4)
+                    fvu4 = (sq4 / engine.total_variance(x)).to(torch.float32)
+                a1.record()
+                torch.cuda.synchronize()
+                ms4 = a0.elapsed_time(a1) / args.steps
+                same = (torch.sort(idx4, 1).values == torch.sort(idx, 1).values).all(1)
+                v4 = torch.gather(acts4, 1, torch.argsort(idx4, 1))[same]
+                v3 = torch.gather(acts, 1, torch.argsort(idx, 1))[same]
+                rows = slice(0, 8192)
+                alt4[tag] = {"value": TOKENS / (ms4 * 1e-3), "unit": "tokens/s", "ms_per_step": ms4,
+                             "path_frac": TOKENS / (ms4 * 1e-3) * FLOPS_PER_TOKEN / 1e12 / peaks["tflops_sustained"],
+                             "rows_with_different_topk_set_vs_mode3": int((~same).sum().item()),
+                             "max_rel_value_diff_vs_mode3": float(((v4 - v3).abs() / v3.abs()).max().item()),
+                             "max_rel_row_err_vs_mode3_fp32_decode":
+                                 float(((out4[rows] - sae_out[rows]).norm(dim=1) / sae_out[rows].norm(dim=1)).max().item()),
+                             "fvu": float(fvu4.item())}
+                del ov4
+        except Exception as exc:
+            alt4 = {"error": repr(exc)[:300]}
+
     # ---- end to end through the reference-facing objects with host buffers (`e2e`)
     x_host = synth.make_activations(TOKENS, D_IN, dev, seed=1 + rank, pinned_host=True)
     acts_host = torch.empty((TOKENS, K), dtype=torch.float32, pin_memory=True)
@@ -403,7 +443,7 @@ def run_gpu(args):
                        "precision": PRECISION[args.planes].replace("fp32 W_dec", f"{args.decode_dtype} W_dec"),
                        "l2": "inputs (x 512 MiB, weights 6 GiB) larger than the 126 MB L2"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "scan": scan, "fvu": fvu_val, "alt_fp16_decode": alt,
+            "scan": scan, "fvu": fvu_val, "alt_fp16_decode": alt, "alt_mode4": alt4,
         }
         print(json.dumps(line))
     if world > 1:
@@ -424,6 +464,8 @@ def main():
                     help="per-chunk exchanges of the sharded scan: NCCL all-gathers (default) or the library's own "
                          "peer-memory all-gather (saeb_push_gather)")
     ap.add_argument("--scan-phases", action="store_true", help="per-phase CUDA-event timing of the scan (diagnostic)")
+    ap.add_argument("--alt-mode4", action="store_true",
+                    help="also measure packed mode 4 (residual-correction refinement), with fp32 and fp16 W_dec")
     ap.add_argument("--no-alt", action="store_true", help="skip the secondary fp16-W_dec measurement")
     ap.add_argument("--no-overlap", action="store_true", help="run the phases of a step back to back on one stream")
     ap.add_argument("--chunk", type=int, default=18944, help="tokens per pipeline chunk (multiple of 9472 = one wave)")
