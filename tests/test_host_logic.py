@@ -314,3 +314,32 @@ def test_image_constructor_matches_reference():
     for i, ex in enumerate(rec2.examples):
         assert np.array_equal(ex.activations.numpy(), g[f"rand{i}_acts"])
         assert np.array_equal(np.asarray(ex.image), g[f"rand{i}_image"])
+
+
+def test_mode4_hi_lo_arithmetic_model():
+    """CPU model of packed mode 4 with the scale conventions of csrc/pack.cu (hi = fp16(W * 2^s), the largest |W| landing
+    in [2^13, 2^14); lo = fp16((W * 2^s - hi) * 2^11); activations scaled per row by a power of two into fp16): the
+    tensor-core value x . hi plus the correction x . lo * 2^-s * 2^-11 (csrc/refine.cu, refine_body<.., true>) must
+    reproduce the fp64 product to fp32 grade, and bf16 activations must survive the row scaling exactly."""
+    rng = np.random.default_rng(0)
+    d, N = 512, 96
+    W = (rng.uniform(-1, 1, (N, d)) / np.sqrt(d)).astype(np.float32)
+    W[5] *= 1e-4   # a tiny-norm feature: its residual still has to stay inside the fp16 range
+    x = torch.randn(d, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16).float().numpy()
+    _, e = np.frexp(np.abs(W).max())
+    scale, unscale = np.float32(2.0 ** (14 - e)), np.float32(2.0 ** (e - 14))
+    ws = (W * scale).astype(np.float32)
+    hi = ws.astype(np.float16)
+    lo = ((ws - hi.astype(np.float32)) * np.float32(2048)).astype(np.float16)
+    assert np.isfinite(lo.astype(np.float32)).all() and np.abs(lo.astype(np.float32)).max() <= 8192
+    _, ex = np.frexp(np.abs(x).max())
+    x16 = (x * np.float32(2.0 ** (14 - ex))).astype(np.float16)
+    row_scale = np.float32(2.0 ** (ex - 14))
+    assert np.array_equal(x16.astype(np.float32) * row_scale, x)
+    exact = W.astype(np.float64) @ x.astype(np.float64)
+    a = (hi.astype(np.float64) @ x16.astype(np.float64)) * float(row_scale) * float(unscale)
+    corrected = a + (lo.astype(np.float64) @ x.astype(np.float64)) * float(unscale) / 2048.0
+    ref = np.abs(exact).max()
+    assert np.abs(a - exact).max() / ref > 1e-5          # the single fp16 pass alone is not parity grade
+    assert np.abs(corrected - exact).max() / ref < 2e-7  # with the residual plane it is
+    assert abs(corrected[5] - exact[5]) <= 2e-7 * np.abs(exact[5]) + 1e-12 * ref
