@@ -104,7 +104,21 @@ class EngineOps:
         if self._push is None or self._push.max_rows < t.shape[0] or tuple(self._push.widths) != tuple(self.push_widths):
             from .p2p import PushExchange
 
-            self._push = PushExchange(group, t.device, t.shape[0], self.push_widths)
+            # setting up the symmetric buffer can fail on one rank only (no peer access, no symmetric-memory support):
+            # every rank tries, then all agree -- either everybody pushes or everybody stays on NCCL
+            err = None
+            try:
+                push = PushExchange(group, t.device, t.shape[0], self.push_widths)
+            except Exception as exc:   # noqa: BLE001 - any failure means "fall back", the reason is reported below
+                push, err = None, exc
+            ok = torch.tensor([0 if push is None else 1], dtype=torch.int32, device=t.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                if dist.get_rank(group) == 0 or err is not None:
+                    print(f"saeb200: peer-memory exchange unavailable ({err!r}); using NCCL all-gathers", flush=True)
+                self.exchange, self._push = "nccl", None
+                return None
+            self._push = push
         return self._push.gather(t, channel, slot)
 
     def begin_pipeline(self, world: int):
