@@ -343,3 +343,60 @@ def test_mode4_hi_lo_arithmetic_model():
     assert np.abs(a - exact).max() / ref > 1e-5          # the single fp16 pass alone is not parity grade
     assert np.abs(corrected - exact).max() / ref < 2e-7  # with the residual plane it is
     assert abs(corrected[5] - exact[5]) <= 2e-7 * np.abs(exact[5]) + 1e-12 * ref
+
+
+@pytest.mark.parametrize("slots", [1, 2])
+def test_push_exchange_protocol_simulation(slots):
+    """Host simulation of the peer-memory exchange protocol (csrc/exchange.cu + saeb200/dist.py): R ranks as threads,
+    symmetric buffers as shared arrays, one monotonically increasing sequence number per (channel, source rank), a rank
+    waits only for "everybody has delivered THIS exchange" -- there is no barrier protecting a region from the next
+    write.  The claim it checks: because the two exchanges of a chunk alternate, a region is never overwritten while a
+    peer still reads it, with one region per channel (sequential schedule) as well as with two (pipelined).  Random
+    delays shake the interleavings; a torn or stale slab fails the content check."""
+    import random
+    import threading
+    import time
+
+    R, chunks, width = 4, 40, 8
+    region = [[np.zeros((slots, R, width), np.int64) for _ in range(2)] for _ in range(R)]   # [rank][channel]
+    flags = [np.zeros((2, R), np.int64) for _ in range(R)]                                     # [rank][channel, source]
+    errors = []
+
+    def push_gather(rank, channel, slot, seq, payload, rng):
+        for q in range(R):                       # the kernel's peer walk, starting with the own copy
+            p = (rank + q) % R
+            region[p][channel][slot, rank, :] = payload
+            if rng.random() < 0.3:
+                time.sleep(rng.random() * 1e-4)
+        for p in range(R):                       # publish after all stores (release), then wait for all peers (acquire)
+            flags[p][channel, rank] = seq
+        deadline = time.time() + 20
+        while (flags[rank][channel] < seq).any():
+            if time.time() > deadline:
+                errors.append(f"rank {rank}: timeout at seq {seq}")
+                return None
+            time.sleep(0)
+        return region[rank][channel][slot]       # a VIEW: consumed after the call, like the kth kernel does
+
+    def rank_main(rank):
+        rng = random.Random(rank)
+        seq = [0, 0]
+        for c in range(chunks):
+            for channel in (0, 1):               # exchange 1 (bounds), exchange 2 (exact values)
+                seq[channel] += 1
+                got = push_gather(rank, channel, c % slots, seq[channel], 1000 * c + 10 * channel + rank, rng)
+                if got is None:
+                    return
+                if rng.random() < 0.5:
+                    time.sleep(rng.random() * 2e-4)   # the consumer kernel runs some time after the exchange
+                want = np.array([1000 * c + 10 * channel + r for r in range(R)])[:, None].repeat(width, 1)
+                if not np.array_equal(got, want):
+                    errors.append(f"rank {rank} chunk {c} channel {channel}: stale or torn slab")
+                    return
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(R)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(60)
+    assert not errors, errors[:3]
