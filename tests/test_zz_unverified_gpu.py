@@ -178,3 +178,23 @@ def test_full_size_scan_properties():
         sc.update(acts[t0:t0 + ctx * 256], idx[t0:t0 + ctx * 256], t0 // ctx)
     ss, sw = sc.finalize()
     assert torch.equal(ss, s[lo:hi]) and torch.equal(sw, w[lo:hi])
+
+
+@pytest.mark.parametrize("wdt,tol", [(torch.float16, 5e-4), (torch.bfloat16, 4e-3)])
+def test_decode_with_16bit_weight_copy(wdt, tol):
+    """decode from an fp16 / bf16 copy of W_dec (half the gather bytes): row-wise relative error of the reconstruction
+    vs the fp32 decode -- fp16 stays inside the 1e-3 bar, bf16 does not (hard part 1)."""
+    from saeb200 import engine
+
+    g = torch.Generator().manual_seed(11)
+    N, d, k, T = 8192, 4096, 64, 256
+    W = torch.randn(N, d, generator=g)
+    W /= W.norm(dim=1, keepdim=True)
+    b = torch.randn(d, generator=g) * 0.1
+    vals = torch.rand(T, k, generator=g) * 3
+    idx = torch.stack([torch.randperm(N, generator=g)[:k] for _ in range(T)])
+    ref = engine.decode(idx.to(DEV), vals.to(DEV), W.to(DEV), b.to(DEV))
+    out = engine.decode(idx.to(DEV), vals.to(DEV), W.to(DEV).to(wdt), b.to(DEV))
+    rel = ((out - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
+    assert rel < tol
+    torch.testing.assert_close(ref.cpu(), O.eager_decode(idx, vals, W.mT) + b, rtol=1e-4, atol=1e-4)
