@@ -400,3 +400,17 @@ def test_push_exchange_protocol_simulation(slots):
     for t in threads:
         t.join(60)
     assert not errors, errors[:3]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/sae_auto_interp"), reason="needs the reference checkout")
+def test_dropin_overlay_on_the_real_reference():
+    """saeb200.dropin.install(): the reference's own launchers / loaders pick up the fused classes (also when they are
+    imported after the call), `eager_decode` and everything outside the hot path stay the reference's, `uninstall()`
+    restores.  Build-container only: it imports the unmodified reference."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "_dropin_check.py"), root], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "DROPIN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
