@@ -37,4 +37,61 @@ with tempfile.TemporaryDirectory() as td:
 assert dropin.install() == {}          # idempotent
 dropin.uninstall()
 assert rs.Sae is ref_Sae and rf.FeatureCache is ref_FC and launcher.Sae is ref_Sae
+
+# ---- the host-side glue the mirror restates (utils helpers, sae/data.py) against the reference's own functions
+import itertools
+import json
+import numpy as np
+
+mu = importlib.import_module("_saeb200_mirror.utils")
+md = importlib.import_module("_saeb200_mirror.sae.data")
+import sae_auto_interp.sae.data as rd
+
+pins = [[336, 672], [672, 336], [672, 672], [1008, 336], [336, 1008]]
+
+
+def call(f, *a):
+    try:
+        return tuple(f(*a))
+    except ZeroDivisionError:   # the reference divides by zero when the grid cell is smaller than the base size
+        return "ZeroDivisionError"
+
+
+for oh, ow in itertools.product([100, 300, 336, 480, 500, 640, 700, 1000, 1333], [100, 300, 336, 480, 640, 777, 1000, 1500]):
+    for h, w, ps in [(336, 336, 14), (384, 384, 14), (336, 336, 24), (336, 224, 14), (224, 336, 16)]:
+        args = (oh, ow, h, w, pins, ps)
+        assert call(ru.get_anyres_unpadded_size, *args) == call(mu.get_anyres_unpadded_size, *args), args
+for ids, t in [([1, 2, 9, 5, 6, 7], 9), ([9, 1], 9), ([3, 4, 9], 9)]:
+    assert tuple(ru.get_llava_image_pos(ids, t)) == tuple(mu.get_llava_image_pos(ids, t))
+with tempfile.TemporaryDirectory() as td:
+    json.dump([{"layers.0_feature1": "a", "prompt": "p"}, {"layers.0_feature2": "b", "prompt": "q"}],
+              open(os.path.join(td, "x.json"), "w"))
+    os.mkdir(os.path.join(td, "sub"))
+    assert ru.load_explanation(td) == mu.load_explanation(td) == {"layers.0_feature1": "a", "layers.0_feature2": "b"}
+    path = os.path.join(td, "t.bin")
+    np.arange(7 * 16, dtype=np.uint16).tofile(path)
+    a, b = rd.MemmapDataset(path, 16, max_examples=6), md.MemmapDataset(path, 16, max_examples=6)
+    assert len(a) == len(b) == 6 and (a[3]["input_ids"] == b[3]["input_ids"]).all()
+    assert (a.select(range(1, 4)).mmap == b.select(range(1, 4)).mmap).all()
+    assert all((a.shard(4, s).mmap == b.shard(4, s).mmap).all() for s in range(4))
+try:   # GPT-style chunking with a toy word-level tokenizer (needs `tokenizers` + `datasets`)
+    from datasets import Dataset
+    from tokenizers import Tokenizer, models, pre_tokenizers
+    from transformers import PreTrainedTokenizerFast
+except Exception:
+    Dataset = None
+if Dataset is not None:
+    words = [f"w{i}" for i in range(50)]
+    vocab = {"<eos>": 0, "<unk>": 1, **{w: i + 2 for i, w in enumerate(words)}}
+    tk = Tokenizer(models.WordLevel(vocab, unk_token="<unk>"))
+    tk.pre_tokenizer = pre_tokenizers.WhitespaceSplit()
+    tok = PreTrainedTokenizerFast(tokenizer_object=tk, eos_token="<eos>", unk_token="<unk>", model_max_length=4096)
+    rng = np.random.default_rng(0)
+    texts = [" ".join(rng.choice(words, size=int(rng.integers(3, 40)))) for _ in range(60)]
+    ds = Dataset.from_dict({"text": texts, "meta": list(range(60))})
+    for kw in ({}, {"return_final_batch": True}):
+        common = dict(format=None, num_proc=1, max_seq_len=32, load_from_cache_file=False, **kw)
+        ra, rb = rd.chunk_and_tokenize(ds, tok, **common), md.chunk_and_tokenize(ds, tok, **common)
+        A = [list(map(int, r["input_ids"])) for r in ra]
+        assert A == [list(map(int, r["input_ids"])) for r in rb] and len(A) > 3
 print("DROPIN_OK", sorted(counts.items()))
