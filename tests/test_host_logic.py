@@ -414,3 +414,36 @@ def test_dropin_overlay_on_the_real_reference():
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "_dropin_check.py"), root], capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and "DROPIN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/sae_auto_interp"), reason="needs the reference checkout")
+def test_reference_launchers_import_against_the_mirror():
+    """The "replace the package" route: with the mirror installed under the reference's package name, the reference's
+    cache / steering / attribution launchers (loaded from their own files, unmodified) find every name they import."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = f"""
+import sys, importlib.util, types
+sys.path[:0] = [{os.path.join(root, 'oracle')!r}, {os.path.join(root, 'multimodal-sae_b200')!r}]
+import ref_shims; ref_shims.install_shims()
+try:
+    import loguru
+except Exception:
+    lg = types.ModuleType("loguru")
+    lg.logger = types.SimpleNamespace(info=print, warning=print, error=print)
+    sys.modules["loguru"] = lg
+import sae_auto_interp
+assert sae_auto_interp.__file__.startswith({os.path.join(root, 'multimodal-sae_b200')!r})
+for rel in ("launch/cache/cache.py", "launch/cache/cache_image.py", "launch/features/steering.py",
+            "launch/features/attribution_patching.py"):
+    spec = importlib.util.spec_from_file_location("ref_" + rel.replace("/", "_")[:-3],
+                                                  "/root/reference/sae_auto_interp/" + rel)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert hasattr(mod, "main")
+print("LAUNCHERS_OK")
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd="/tmp")
+    assert r.returncode == 0 and "LAUNCHERS_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
