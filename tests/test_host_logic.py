@@ -447,3 +447,65 @@ print("LAUNCHERS_OK")
 """
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd="/tmp")
     assert r.returncode == 0 and "LAUNCHERS_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def _oracle_coo_extract(top_acts, top_indices, seq_len, *, row_offset=0, threshold=1e-5, filter_bitmap=None):
+    """CPU stand-in for engine.coo_extract: (row, pos, feature) triples in torch.nonzero order"""
+    k = top_acts.shape[-1]
+    vals, idx = top_acts.reshape(-1, k).float(), top_indices.reshape(-1, k).long()
+    keep = vals.abs() > threshold
+    if filter_bitmap is not None:
+        words = filter_bitmap.to(torch.int64) & 0xFFFFFFFF
+        keep &= ((words[idx >> 5] >> (idx & 31)) & 1).bool()
+    tok = torch.arange(vals.shape[0])[:, None].expand_as(idx)
+    t, f, a = tok[keep], idx[keep], vals[keep]
+    order = torch.argsort(t * (1 << 32) + f)
+    t, f, a = t[order], f[order], a[order]
+    return torch.stack([row_offset + t // seq_len, t % seq_len, f], 1), a
+
+
+@pytest.mark.parametrize("tag", ["nofilter", "filter"])
+def test_feature_cache_run_host_glue_matches_reference(monkeypatch, tag):
+    """FeatureCache.run of the mirror (hooks, batching, row offsets, filter bitmap, host accumulation) against the
+    reference's cached triples; the two engine calls are oracle stand-ins here, the kernels have the same test with
+    -m gpu (tests/test_gpu_parity.py::test_feature_cache_matches_reference_golden)."""
+    from saeb200 import engine
+    from sae_auto_interp.features import FeatureCache
+    from sae_auto_interp.sae import Sae, SaeConfig
+
+    _oracle_backend(monkeypatch)
+    monkeypatch.setattr(engine, "coo_extract", _oracle_coo_extract)
+    g = np.load(os.path.join(GOLDEN, "cache_chain.npz"))
+    N, d = g["W_enc"].shape
+    sae = Sae(d, SaeConfig(num_latents=N, k=int(g["k"])))
+    with torch.no_grad():
+        sae.encoder.weight.copy_(torch.from_numpy(g["W_enc"]))
+        sae.encoder.bias.copy_(torch.from_numpy(g["b_enc"]))
+        sae.W_dec.copy_(torch.from_numpy(g["W_dec"]))
+        sae.b_dec.copy_(torch.from_numpy(g["b_dec"]))
+
+    class ToyLM(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.emb = torch.nn.Embedding.from_pretrained(torch.from_numpy(g["emb"]).clone())
+            self.layers = torch.nn.ModuleList([torch.nn.Linear(d, d)])
+            with torch.no_grad():
+                self.layers[0].weight.copy_(torch.from_numpy(g["layer_w"]))
+                self.layers[0].bias.zero_()
+
+        @property
+        def device(self):
+            return self.emb.weight.device
+
+        def forward(self, input_ids):
+            return self.layers[0](self.emb(input_ids))
+
+    tokens = torch.from_numpy(g["tokens"])
+    dataset = [{"input_ids": tokens[i]} for i in range(tokens.shape[0])]
+    filters = {"layers.0": torch.tensor([1, 5, 15, 16, 31, 40, 63])} if tag == "filter" else None
+    fc = FeatureCache(ToyLM(), None, {"layers.0": sae}, batch_size=2, shard_size=100, filters=filters)
+    fc.run(16, dataset)
+    loc, act = fc.cache.feature_locations["layers.0"], fc.cache.feature_activations["layers.0"]
+    assert loc.dtype == torch.int64 and act.dtype == torch.float32
+    assert np.array_equal(loc.numpy(), g[f"{tag}_locations"])
+    np.testing.assert_allclose(act.numpy(), g[f"{tag}_activations"], rtol=1e-5)
