@@ -203,8 +203,11 @@ def _oracle_backend(monkeypatch):
     monkeypatch.setattr(Sae, "pre_acts", pre_acts)
     monkeypatch.setattr(Sae, "encode", encode)
     monkeypatch.setattr(Sae, "select_topk", lambda self, lat: EncoderOutput(*O.select_topk(lat, self.cfg.k)))
-    monkeypatch.setattr(engine, "decode", lambda i, a, W, b, *, out_dtype=torch.float32, **kw:
-                        O.sparse_decode(i, a, W).to(out_dtype))
+    def decode(i, a, W, b, *, out_dtype=torch.float32, **kw):
+        y = O.sparse_decode(i, a.float(), W.float())
+        return (y if b is None else y + b).to(out_dtype)
+
+    monkeypatch.setattr(engine, "decode", decode)
 
     def bwd(i, a, W, g, *, need_acts=True, need_weight=True):
         da, dw = O.decode_backward(i, a, W, g)
@@ -509,3 +512,37 @@ def test_feature_cache_run_host_glue_matches_reference(monkeypatch, tag):
     assert loc.dtype == torch.int64 and act.dtype == torch.float32
     assert np.array_equal(loc.numpy(), g[f"{tag}_locations"])
     np.testing.assert_allclose(act.numpy(), g[f"{tag}_activations"], rtol=1e-5)
+
+
+def test_steering_hook_host_glue_matches_reference(monkeypatch):
+    """SteeringController.clamp_features_max (features/steering.py:102-128): the hook replaces the layer output by the
+    fp16 reconstruction with one latent clamped at prefill and unclamped at single-token steps.  Oracle stand-ins for
+    the engine calls; same fixture as the -m gpu test."""
+    from sae_auto_interp.features.steering import SteeringController
+    from sae_auto_interp.sae import Sae, SaeConfig
+
+    _oracle_backend(monkeypatch)
+    g = np.load(os.path.join(GOLDEN, "steering.npz"))
+    N, d = g["W_enc"].shape
+    sae = Sae(d, SaeConfig(num_latents=N, k=int(g["k"])))
+    with torch.no_grad():
+        sae.encoder.weight.copy_(torch.from_numpy(g["W_enc"]))
+        sae.encoder.bias.copy_(torch.from_numpy(g["b_enc"]))
+        sae.W_dec.copy_(torch.from_numpy(g["W_dec"]))
+        sae.b_dec.copy_(torch.from_numpy(g["b_dec"]))
+
+    class Layer(torch.nn.Module):
+        def forward(self, h):
+            return (h, None)
+
+    layer = Layer()
+    handles = SteeringController.clamp_features_max(None, sae, int(g["feature"]), layer, k=float(g["clamp"]))
+    try:
+        for tag in ("prefill", "step"):
+            out = layer(torch.from_numpy(g[f"{tag}_in"]))
+            assert out[0].dtype == torch.float16 and out[1] is None and out[0].shape == g[f"{tag}_out"].shape
+            ref = g[f"{tag}_out"].astype(np.float32)
+            assert np.linalg.norm(out[0].float().numpy() - ref) / np.linalg.norm(ref) < 1e-3
+    finally:
+        for h in handles:
+            h.remove()
