@@ -418,6 +418,31 @@ def run_gpu(args):
                                         "chunk c"}[sdist.scan_schedule(world)],
                 "phase_ms_rank0": {k_: round(v_, 2) for k_, v_ in phases.items()} or None}
 
+    # ---- opt-in cross-check (--scan-crosscheck, N > 1): the token-parallel form of the same scan (full SAE on every
+    # rank, tokens split, no per-chunk exchange, one all-gather + merge at the end) must give the same lists
+    if scan is not None and world > 1 and args.scan_crosscheck:
+        ops_tp = sdist.EngineOps(sae.encoder.weight.data, sae.encoder.bias.data, sae.b_dec.data, 0, WIDTH, n_top,
+                                 ctx_len, dev, planes=args.planes)
+        w_lo, w_hi = sdist.token_slice(args.scan_tokens // ctx_len, world, rank)
+        x_tp = xs[w_lo * ctx_len:w_hi * ctx_len]
+        chunk_tp = ops_tp.chunk_tokens(1)
+
+        def chunks_tp():
+            for t0 in range(0, x_tp.shape[0], chunk_tp):
+                yield x_tp[t0:t0 + chunk_tp]
+
+        barrier()
+        e0.record()
+        res_tp = sdist.token_parallel_scan(chunks_tp(), ops_tp, K, ctx_len, WIDTH, w_lo, n_top=n_top)
+        e1.record()
+        barrier()
+        tp_ms = max_over_ranks(e0.elapsed_time(e1))
+        same_w = bool(torch.equal(res_tp.top_win, res.top_win))
+        rel = ((res_tp.top_vals - res.top_vals).abs() / res.top_vals.abs().clamp_min(1e-30)).max()
+        scan["crosscheck_token_parallel"] = {"ms": tp_ms, "tokens_per_s": args.scan_tokens / (tp_ms * 1e-3),
+                                             "same_windows": same_w, "max_rel_score_diff": float(rel.item())}
+        del ops_tp
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         tok_s, threads, secs = cpu_forward_tokens_per_s(2048, 512, repeats=2)
@@ -464,6 +489,9 @@ def main():
     ap.add_argument("--scan-exchange", default=None, choices=["nccl", "push"],
                     help="per-chunk exchanges of the sharded scan: NCCL all-gathers (default) or the library's own "
                          "peer-memory all-gather (saeb_push_gather)")
+    ap.add_argument("--scan-crosscheck", action="store_true",
+                    help="N > 1: also run the token-parallel form of the scan and compare its lists with the "
+                         "feature-sharded ones")
     ap.add_argument("--scan-phases", action="store_true", help="per-phase CUDA-event timing of the scan (diagnostic)")
     ap.add_argument("--alt-mode4", action="store_true",
                     help="also measure packed mode 4 (residual-correction refinement), with fp32 and fp16 W_dec")

@@ -457,6 +457,35 @@ def _kth(ops, gathered: torch.Tensor, k: int) -> torch.Tensor:
     return ops.kth_of_gathered(gathered, min(k, R * m))
 
 
+def token_parallel_scan(chunks_local: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_latents: int,
+                        window_base: int, *, n_top: int, group=None) -> ScanResult:
+    """The other exact multi-GPU form of the scan: tokens are split across ranks, every rank holds the
+    FULL SAE (`ops` covers features [0, num_latents)) and scans its own token slice with no per-chunk exchange at all
+    -- a token's TopK is complete on the rank that owns it.  The job ends with one all-gather of the per-rank
+    [N, n_top] lists and a per-feature merge.  It needs the whole SAE on every GPU (the feature-sharded form does
+    not) and is used as its cross-check: both must produce identical lists.
+
+    `chunks_local` yields this rank's token chunks ([Tc, d], Tc a multiple of ctx_len); `window_base` is the global id
+    of its first window (ranks own consecutive, increasing window ranges, so concatenating the per-rank lists in rank
+    order keeps equal scores ordered by window id and a stable sort finishes the merge)."""
+    distributed = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if distributed else 1
+    base = int(window_base)
+    for x in chunks_local:
+        ops.local_bounds(x, k)
+        vals, idx = ops.local_topk(None)
+        ops.scan_update(vals.reshape(-1, k), idx.reshape(-1, k), base, None)
+        n_tok = x.shape[0] if x.dim() == 2 else x.numel() // x.shape[-1]
+        base += n_tok // ctx_len
+    top_vals, top_win = ops.scan_finalize()
+    if world == 1:
+        return ScanResult(top_vals, top_win)
+    vals_all = torch.cat(_all_gather_cat(top_vals, group), 1)   # [N, R * n_top], rank-major
+    wins_all = torch.cat(_all_gather_cat(top_win, group), 1)
+    order = torch.sort(vals_all, dim=1, descending=True, stable=True).indices[:, :n_top]
+    return ScanResult(torch.gather(vals_all, 1, order), torch.gather(wins_all, 1, order))
+
+
 def token_parallel_forward(sae, x_local: torch.Tensor):
     """Token-parallel forward: each rank runs the fused forward on its token slice; nothing is communicated."""
     return sae(x_local)

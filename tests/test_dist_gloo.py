@@ -22,6 +22,7 @@ class OracleOps:
         self.sub = O.SaeParams(p.W_enc[lo:hi], p.b_enc[lo:hi], p.W_dec[lo:hi], p.b_dec, p.k)
         self.acts, self.idx, self.thr = [], [], []
         self._v, self._i = {}, {}
+        self.first_window = None
 
     def local_bounds(self, x, k, slot=0):
         pa = O.pre_acts(self.sub, x.float())
@@ -42,12 +43,15 @@ class OracleOps:
     def scan_update(self, vals, idx, window_base, tok_thr):
         if tok_thr is not None:
             vals = torch.where(vals >= tok_thr[:, None], vals, torch.zeros_like(vals))
+        if self.first_window is None:
+            self.first_window = window_base   # chunks arrive in order: later ones continue this numbering
         self.acts.append(vals)
         self.idx.append(idx)
 
     def scan_finalize(self):
         acts, idx = torch.cat(self.acts), torch.cat(self.idx)
         s, w = O.scan_top_windows(acts, idx - self.feat_lo, self.feat_hi - self.feat_lo, self.ctx_len, self.n_top)
+        w = np.where(w >= 0, w + (self.first_window or 0), w)
         return torch.from_numpy(s), torch.from_numpy(w)
 
 
@@ -71,6 +75,48 @@ def _worker(rank, world, port, exact, pipelined, out_dir, lb_width=None):
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), vals=res.top_vals.numpy(), win=res.top_win.numpy())
     finally:
         dist.destroy_process_group()
+
+
+def _worker_token_parallel(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "multimodal-sae_b200"))
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    from saeb200 import dist as sdist
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        N, d, k, ctx, n_top = 96, 32, 6, 8, 3
+        p = O.init_params(d, N, k, seed=77)
+        x = torch.randn(ctx * 12, d, generator=torch.Generator().manual_seed(78)).to(torch.bfloat16)
+        x[ctx * 7:ctx * 8] = x[ctx * 2:ctx * 3]   # a window repeated on the other rank: equal scores, ids decide
+        ops = OracleOps(p, 0, N, n_top, ctx)
+        lo, hi = sdist.token_slice(x.shape[0] // ctx, world, rank)   # whole windows per rank
+        mine = x[lo * ctx:hi * ctx]
+        chunks = [mine[i:i + 2 * ctx] for i in range(0, mine.shape[0], 2 * ctx)]
+        res = sdist.token_parallel_scan(chunks, ops, k, ctx, N, lo, n_top=n_top)
+        np.savez(os.path.join(out_dir, f"tp_rank{rank}.npz"), vals=res.top_vals.numpy(), win=res.top_win.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_token_parallel_scan_two_ranks(tmp_path):
+    """token-parallel form of the scan: no per-chunk exchange, one all-gather + per-feature merge at the end; must
+    equal the single-process scan, including the window order of equal scores that come from different ranks"""
+    world = 2
+    mp.spawn(_worker_token_parallel, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = (np.load(tmp_path / f"tp_rank{r}.npz") for r in range(world))
+    assert np.array_equal(r0["vals"], r1["vals"]) and np.array_equal(r0["win"], r1["win"])
+    N, d, k, ctx, n_top = 96, 32, 6, 8, 3
+    p = O.init_params(d, N, k, seed=77)
+    x = torch.randn(ctx * 12, d, generator=torch.Generator().manual_seed(78)).to(torch.bfloat16)
+    x[ctx * 7:ctx * 8] = x[ctx * 2:ctx * 3]
+    enc = O.encode(p, x.float())
+    ref_s, ref_w = O.scan_top_windows(enc.top_acts, enc.top_indices, N, ctx, n_top)
+    np.testing.assert_array_equal(r0["vals"], ref_s)
+    np.testing.assert_array_equal(r0["win"], ref_w)
+    both = (ref_w == 2).any(1) & (ref_w == 7).any(1)   # features whose list holds both copies of the repeated window
+    assert both.any()
 
 
 def _free_port():
