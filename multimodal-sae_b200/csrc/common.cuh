@@ -3,9 +3,15 @@
 // instruction descriptor).  No CUTLASS/CuTe types are used.
 #pragma once
 
+#if defined(SAEB_CPU_EMU)
+// CPU emulation of the execution model (threads as host threads, warp / block collectives as barriers): lets the
+// kernels_*.cuh device code run on the host in tests/test_kernel_emu.py.  Never defined in the GPU build.
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 

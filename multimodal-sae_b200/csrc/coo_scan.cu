@@ -9,7 +9,7 @@
 //              activations and the `n_top` best windows per feature.
 // kth_*      : per-token global k-th value from all-gathered per-shard top-k values (feature-sharded exactness,
 //              SURVEY.md section 8(e)).
-#include "common.cuh"
+#include "kernels_kth.cuh"
 
 namespace saeb {
 
@@ -179,59 +179,6 @@ int coo_extract_launch(const float* vals, const long long* idx, long long T, int
 // chunk between two collectives, so it sits on the critical path of the multi-GPU schedule (the first version re-read
 // the values from memory in every search step: ~0.8 ms per 37 888-token chunk at R*m = 512).
 // ---------------------------------------------------------------------------------------------
-template <int VPL>
-__global__ void __launch_bounds__(256)
-kth_gathered_reg_kernel(const float* __restrict__ g, int R, long long T, int m, int kth, float* __restrict__ tok_thr) {
-  const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (t >= T) return;   // t is per warp: the whole warp leaves together
-  const int M = R * m;
-  uint32_t key[VPL];
-#pragma unroll
-  for (int s = 0; s < VPL; ++s) {
-    const int i = s * 32 + lane;
-    uint32_t b = 0;
-    if (i < M) {
-      const int r = i / m, j = i - r * m;
-      const float v = __ldg(g + ((long long)r * T + t) * m + j);
-      if (v > 0.f) b = __float_as_uint(v);   // positive floats order like their bit patterns; <= 0 and NaN count as 0
-    }
-    key[s] = b;
-  }
-  uint32_t prefix = 0;
-  for (int bit = 30; bit >= 0; --bit) {
-    const uint32_t trial = prefix | (1u << bit);
-    int c = 0;
-#pragma unroll
-    for (int s = 0; s < VPL; ++s) c += (key[s] >= trial) ? 1 : 0;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (c >= kth) prefix = trial;
-  }
-  if (lane == 0) tok_thr[t] = __uint_as_float(prefix);
-}
-
-// any R*m: the values stay in memory (L1/L2) and are re-read in every search step
-__global__ void kth_gathered_mem_kernel(const float* __restrict__ g, int R, long long T, int m, int kth,
-                                        float* __restrict__ tok_thr) {
-  const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (t >= T) return;
-  const int M = R * m;
-  uint32_t prefix = 0;
-  for (int bit = 30; bit >= 0; --bit) {
-    const uint32_t trial = prefix | (1u << bit);
-    int c = 0;
-    for (int i = lane; i < M; i += 32) {
-      const int r = i / m, j = i - r * m;
-      const float v = g[((long long)r * T + t) * m + j];
-      c += (v > 0.f && __float_as_uint(v) >= trial) ? 1 : 0;
-    }
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (c >= kth) prefix = trial;
-  }
-  if (lane == 0) tok_thr[t] = __uint_as_float(prefix);
-}
-
 static int g_kth_impl = 1;   // 1: register-resident search (default); 0: memory-resident (first version, diagnostics)
 int set_kth_impl(int v) {
   g_kth_impl = v ? 1 : 0;

@@ -1,0 +1,287 @@
+// Device code only (no launch syntax): included by refine.cu for the GPU build and, with SAEB_CPU_EMU defined, by the CPU
+// emulation harness under tests/emu, which runs these kernels thread by thread on the host (tests/test_kernel_emu.py).
+#pragma once
+#include "common.cuh"
+
+namespace saeb {
+
+constexpr int RF_THREADS = 256;
+constexpr int RF_MAX_FLAG = 64;   // flagged rows handled by the wide (all-SM) fallback; further rows take the
+                                  // one-block-per-row overflow path, so any number of flagged rows stays exact
+
+// LO = false: candidates are re-evaluated exactly against the fp32 row W[f] (the parity default).
+// LO = true ("fp16 hi + lo", packed mode 4): the approximate value a_j = x . W_hi[f] + bias already comes out of the
+// tensor cores; only the missing part x . W_lo[f] is added, W_lo = fp16 plane of the residual (W_hi + W_lo = W to
+// 2^-22) -- half the gather bytes.  Exact for bf16 / fp16 activations (they reach the tensor cores unrounded); the
+// corrected values carry the tensor cores' fp32 accumulation noise (~1e-6 relative, like any fp32 GEMM) instead of
+// the 3e-7 of the exact route.
+template <typename XT, bool LO>
+__device__ __forceinline__ void
+refine_body(const XT* __restrict__ x, long long ld_x, const float* __restrict__ W, long long d, long long N,
+            const float* __restrict__ bias, const float* __restrict__ wnorm, const float* __restrict__ dnorm,
+            const float* __restrict__ trailer, const float* __restrict__ xnorm, const float* __restrict__ xdnorm,
+            float c_eps, const float* __restrict__ cand_vals,
+            const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
+            float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
+            int* __restrict__ flag_rows, const float* __restrict__ ext_lower, const __half* __restrict__ Wlo,
+            long long ld_w) {
+  extern __shared__ float rsm[];
+  float* xs = rsm;                                   // [d4] activations of this row as fp32
+  const int d4 = LO ? (int)((d + 7) & ~7ll) : (int)((d + 3) & ~3ll);   // LO: padded like the packed weight rows
+  float* a = xs + d4;                                // [K2] approximate values
+  float* lb = a + K2;                                // [K2]
+  float* ub = lb + K2;                               // [K2]
+  float* ex = ub + K2;                               // [K2] exact values (or -1)
+  int* f = reinterpret_cast<int*>(ex + K2);          // [K2] feature ids
+  __shared__ float s_L;
+  __shared__ int s_cnt[2];
+  const long long t = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+
+  for (int i = tid; i < d4; i += nthr) xs[i] = (i < d) ? (float)x[t * ld_x + i] : 0.f;
+  const float xn = xnorm[t], xdn = xdnorm[t];
+  const float wmax = trailer[1], dmax = trailer[3];
+  for (int j = tid; j < K2; j += nthr) {
+    const float av = cand_vals[t * K2 + j];
+    const int fj = (int)cand_idx[t * K2 + j];
+    const bool valid = av > 0.f;
+    const float wn = wnorm[fj];
+    const float eps = (fj == clamp_feature) ? 0.f : 1.001f * (xn * dnorm[fj] + xdn * wn) + c_eps * xn * wn;
+    a[j] = av;
+    f[j] = fj;
+    lb[j] = valid ? av - eps : -INFINITY;
+    ub[j] = valid ? av + eps : -INFINITY;
+    ex[j] = -1.f;
+  }
+  if (tid == 0) {
+    s_L = 0.f;
+    s_cnt[0] = 0;
+    s_cnt[1] = 0;
+  }
+  __syncthreads();
+  // L = k-th largest lower bound (0 if fewer than k positive candidates exist)
+  int my_valid = 0;
+  for (int j = tid; j < K2; j += nthr) {
+    if (a[j] > 0.f) {
+      ++my_valid;
+      int rank = 0;
+      const float l = lb[j];
+      for (int i = 0; i < K2; ++i) rank += (lb[i] > l || (lb[i] == l && i < j)) ? 1 : 0;
+      if (rank == k - 1) s_L = fmaxf(l, 0.f);
+    }
+  }
+  if (my_valid) atomicAdd(&s_cnt[0], my_valid);
+  __syncthreads();
+  const int nv = s_cnt[0];
+  float L = (nv >= k) ? s_L : 0.f;
+  // feature-sharded use: a lower bound of the GLOBAL k-th value (k-th largest lower bound over all shards)
+  if (ext_lower != nullptr) L = fmaxf(L, ext_lower[t]);
+  // exact value of candidate j (all lanes of the calling warp): fp32 dot product with the fp32 W_enc row + bias
+  const bool vec = (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  auto evaluate = [&](int j) {
+    const int fj = f[j];
+    float val;
+    if (fj == clamp_feature) {
+      val = clamp_value;
+    } else if constexpr (LO) {
+      // residual correction: 8 halves per 16-byte load; rows are zero padded to d_pad (multiple of 8), xs to d4
+      const uint4* w8 = reinterpret_cast<const uint4*>(Wlo + (long long)fj * ld_w);
+      const float4* x4 = reinterpret_cast<const float4*>(xs);
+      const int n8 = d4 >> 3;
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      auto fma8 = [&](uint4 wv, int c8) {
+        const float2 w0 = __half22float2(*reinterpret_cast<const __half2*>(&wv.x));
+        const float2 w1 = __half22float2(*reinterpret_cast<const __half2*>(&wv.y));
+        const float2 w2 = __half22float2(*reinterpret_cast<const __half2*>(&wv.z));
+        const float2 w3 = __half22float2(*reinterpret_cast<const __half2*>(&wv.w));
+        const float4 xa = x4[2 * c8], xb = x4[2 * c8 + 1];
+        acc0 = fmaf(w0.x, xa.x, acc0);
+        acc1 = fmaf(w0.y, xa.y, acc1);
+        acc2 = fmaf(w1.x, xa.z, acc2);
+        acc3 = fmaf(w1.y, xa.w, acc3);
+        acc0 = fmaf(w2.x, xb.x, acc0);
+        acc1 = fmaf(w2.y, xb.y, acc1);
+        acc2 = fmaf(w3.x, xb.z, acc2);
+        acc3 = fmaf(w3.y, xb.w, acc3);
+      };
+      int c = lane;
+      for (; c + 7 * 32 < n8; c += 8 * 32) {
+        uint4 wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) wv[u] = ldg_nc_u4(w8 + c + u * 32);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) fma8(wv[u], c + u * 32);
+      }
+      for (; c < n8; c += 32) fma8(ldg_nc_u4(w8 + c), c);
+      float acc = (acc0 + acc1) + (acc2 + acc3);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      // a_j = x . W_hi + folded bias (tensor cores); W_lo carries the residual times 2^11 in the hi plane's scale
+      val = fmaf(acc, trailer[0] * (1.0f / 2048.0f), a[j]);
+    } else {
+      const float* wr = W + (long long)fj * d;
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      if (vec) {
+        const float4* w4 = reinterpret_cast<const float4*>(wr);
+        const float4* x4 = reinterpret_cast<const float4*>(xs);
+        const int n4 = (int)(d >> 2);
+        int c = lane;
+        for (; c + 7 * 32 < n4; c += 8 * 32) {
+          float4 wv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) wv[u] = ldg_nc_f4(w4 + c + u * 32);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 xv = x4[c + u * 32];
+            acc0 = fmaf(wv[u].x, xv.x, acc0);
+            acc1 = fmaf(wv[u].y, xv.y, acc1);
+            acc2 = fmaf(wv[u].z, xv.z, acc2);
+            acc3 = fmaf(wv[u].w, xv.w, acc3);
+          }
+        }
+        for (; c < n4; c += 32) {
+          const float4 wv = ldg_nc_f4(w4 + c);
+          const float4 xv = x4[c];
+          acc0 = fmaf(wv.x, xv.x, acc0);
+          acc1 = fmaf(wv.y, xv.y, acc1);
+          acc2 = fmaf(wv.z, xv.z, acc2);
+          acc3 = fmaf(wv.w, xv.w, acc3);
+        }
+      } else {
+        for (long long i = lane; i < d; i += 32) acc0 = fmaf(wr[i], xs[i], acc0);
+      }
+      float acc = (acc0 + acc1) + (acc2 + acc3);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      val = acc + bias[fj];
+    }
+    if (lane == 0) ex[j] = (val > 0.f) ? val : -1.f;
+  };
+  const int nwarps = nthr >> 5;
+  // stage A: the k best candidates by approximate value (the merged list is sorted by a, descending)
+  for (int j = warp; j < k; j += nwarps)
+    if (ub[j] >= L && a[j] > 0.f) evaluate(j);
+  __syncthreads();
+  // k exact values are now known: their smallest is a far tighter lower bound of the k-th value than L (which sits a
+  // full eps below it), so fewer of the remaining candidates can still reach the TopK
+  if (warp == 0) {
+    float mn = INFINITY;
+    for (int j = lane; j < k; j += 32) mn = fminf(mn, ex[j]);   // -1 = not evaluated or not positive
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if (lane == 0) s_L = (mn > L) ? mn : L;
+  }
+  __syncthreads();
+  L = s_L;
+  // list possibly too short?  (only when the list is full: otherwise every positive latent is already in it)
+  if (tid == 0 && nv == K2) {
+    const float a_last = a[K2 - 1];
+    if (a_last + 1.001f * (xn * dmax + xdn * wmax) + c_eps * xn * wmax >= L) {
+      const int slot = atomicAdd(&status[0], 1);
+      flag_rows[slot] = (int)t;   // capacity = number of rows of the call
+    }
+  }
+  // stage B: every remaining candidate that can still be in the TopK
+  for (int j = k + warp; j < K2; j += nwarps)
+    if (ub[j] >= L && a[j] > 0.f) evaluate(j);
+  __syncthreads();
+  // final TopK over the exact values: rank by (value desc, feature id asc)
+  int my_pos = 0;
+  for (int j = tid; j < K2; j += nthr) {
+    const float v = ex[j];
+    if (v > 0.f) {
+      ++my_pos;
+      int rank = 0;
+      const int fj = f[j];
+      for (int i = 0; i < K2; ++i) rank += (ex[i] > v || (ex[i] == v && f[i] < fj)) ? 1 : 0;
+      if (rank < k) {
+        out_vals[t * k + rank] = v;
+        out_idx[t * k + rank] = fj;
+      }
+    }
+  }
+  if (my_pos) atomicAdd(&s_cnt[1], my_pos);
+  __syncthreads();
+  const int npos = s_cnt[1];
+  if (npos < k && ext_lower != nullptr) {
+    // feature-sharded call: the tail only has to read as "nothing here" (value 0); ids need not be distinct
+    for (int j = npos + tid; j < k; j += nthr) {
+      out_vals[t * k + j] = 0.f;
+      out_idx[t * k + j] = 0;
+    }
+  } else if (npos < k && warp == 0) {
+    // fewer than k positive latents: pad with zeros on the smallest unused feature ids (as topk_merge_kernel does)
+    int filled = npos;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (long long base = 0; base < N && filled < k; base += 32) {
+      const long long jf = base + lane;
+      bool free_idx = jf < N;
+      for (int i = 0; i < K2 && free_idx; ++i) free_idx = !(ex[i] > 0.f && f[i] == (int)jf);
+      const uint32_t m = __ballot_sync(0xffffffffu, free_idx);
+      const int pos = filled + __popc(m & lt_mask);
+      if (free_idx && pos < k) {
+        out_vals[t * k + pos] = 0.f;
+        out_idx[t * k + pos] = jf;
+      }
+      filled += __popc(m);
+    }
+  }
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(RF_THREADS)
+refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict__ W, long long d, long long N,
+              const float* __restrict__ bias, const float* __restrict__ wnorm, const float* __restrict__ dnorm,
+              const float* __restrict__ trailer, const float* __restrict__ xnorm, const float* __restrict__ xdnorm,
+              float c_eps, const float* __restrict__ cand_vals,
+              const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
+              float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
+              int* __restrict__ flag_rows, const float* __restrict__ ext_lower) {
+  refine_body<XT, false>(x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k,
+                         clamp_feature, clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, nullptr, 0);
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(RF_THREADS)
+refine_lo_kernel(const XT* __restrict__ x, long long ld_x, const __half* __restrict__ Wlo, long long ld_w, long long d,
+                 long long N, const float* __restrict__ bias, const float* __restrict__ wnorm,
+                 const float* __restrict__ dnorm, const float* __restrict__ trailer, const float* __restrict__ xnorm,
+                 const float* __restrict__ xdnorm, float c_eps, const float* __restrict__ cand_vals,
+                 const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
+                 float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
+                 int* __restrict__ flag_rows, const float* __restrict__ ext_lower) {
+  refine_body<XT, true>(x, ld_x, nullptr, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx,
+                        K2, k, clamp_feature, clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, Wlo, ld_w);
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-row lower bounds of the k best candidates (feature-sharded scan): lb_out[t][0..k) = the k largest values of
+// a_j - eps_j, descending, floored at 0.  All-gathered across shards, their k-th largest is a lower bound of the
+// token's global k-th activation.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+candidate_bounds_kernel(const float* __restrict__ cand_vals, const long long* __restrict__ cand_idx, int K2, int k,
+                        const float* __restrict__ wnorm, const float* __restrict__ dnorm,
+                        const float* __restrict__ xnorm, const float* __restrict__ xdnorm, float c_eps,
+                        long long clamp_feature, float* __restrict__ lb_out) {
+  extern __shared__ float bsm[];   // [K2]
+  const long long t = blockIdx.x;
+  const float xn = xnorm[t], xdn = xdnorm[t];
+  for (int j = threadIdx.x; j < K2; j += blockDim.x) {
+    const float av = cand_vals[t * K2 + j];
+    const long long fj = cand_idx[t * K2 + j];
+    const float wn = wnorm[fj];
+    const float eps = (fj == clamp_feature) ? 0.f : 1.001f * (xn * dnorm[fj] + xdn * wn) + c_eps * xn * wn;
+    bsm[j] = (av > 0.f) ? fmaxf(av - eps, 0.f) : 0.f;
+  }
+  for (int j = threadIdx.x; j < k; j += blockDim.x) lb_out[t * k + j] = 0.f;
+  __syncthreads();
+  for (int j = threadIdx.x; j < K2; j += blockDim.x) {
+    const float l = bsm[j];
+    int rank = 0;
+    for (int i = 0; i < K2; ++i) rank += (bsm[i] > l || (bsm[i] == l && i < j)) ? 1 : 0;
+    if (rank < k) lb_out[t * k + rank] = l;
+  }
+}
+
+}  // namespace saeb

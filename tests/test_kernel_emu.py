@@ -1,0 +1,237 @@
+"""CPU: the device code of `multimodal-sae_b200/csrc/kernels_*.cuh` executed on the host by a small emulation of the CUDA
+execution model (tests/emu/cuda_emu.h: CUDA threads as host threads, warp / block collectives as barriers).
+
+There is no GPU in the build container; this tier checks the LOGIC of the simple SIMT kernels -- indexing, warp
+reductions, shared-memory phases, scale conventions -- against the oracle before they ever run on a B200 (the tcgen05 /
+TMA kernel cannot be emulated this way and is covered by the -m gpu parity tests only).  Nothing here is a product
+path: the emulation library is built from the kernel headers into a temporary directory and only used by this file.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+from ctypes import c_float, c_int, c_longlong, c_void_p
+
+import numpy as np
+import pytest
+import torch
+
+import sae_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "multimodal-sae_b200", "csrc")
+EMU = os.path.join(ROOT, "tests", "emu")
+CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+HEADERS = ["common.cuh", "kernels_kth.cuh", "kernels_decode_bwd.cuh", "kernels_pack.cuh", "kernels_refine.cuh"]
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_fp16.h")):
+        pytest.skip("needs g++ and the CUDA toolkit headers")
+    build = tmp_path_factory.mktemp("emu_build")
+    for h in HEADERS:   # shared memory becomes ordinary static storage shared by the block's host threads
+        src = open(os.path.join(CSRC, h)).read()
+        open(build / h, "w").write(src.replace("extern __shared__", "extern").replace("__shared__", "static"))
+    lib = build / "libemu.so"
+    cmd = ["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-Wno-attributes", f"-I{build}", f"-I{EMU}", f"-I{CUDA_INC}",
+           os.path.join(EMU, "emu_kernels.cpp"), "-o", str(lib), "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return ctypes.CDLL(str(lib))
+
+
+def _p(a):
+    return c_void_p(a.ctypes.data)
+
+
+def _bf16_raw(t: torch.Tensor) -> np.ndarray:
+    return t.to(torch.bfloat16).view(torch.int16).numpy().copy()
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("vpl", [4, 16, 64, 0])
+def test_kth_largest_kernels(emu, vpl):
+    """every register tier of kth_gathered_reg_kernel and the memory-resident kernel vs torch.topk"""
+    cases = {4: [(4, 13, 16, 16), (2, 7, 3, 6), (5, 9, 13, 65), (8, 5, 16, 1)],
+             16: [(8, 11, 24, 64), (8, 9, 64, 64), (3, 10, 100, 17)],
+             64: [(8, 6, 256, 100), (16, 5, 64, 64)],
+             0: [(3, 5, 700, 64), (4, 9, 16, 16)]}[vpl]
+    gen = torch.Generator().manual_seed(24 + vpl)
+    for R, T, m, kth in cases:
+        g = torch.randn(R, T, m, generator=gen)
+        g[:, ::3, m // 2:] = 0.0
+        ref = g.clamp_min(0).permute(1, 0, 2).reshape(T, R * m).topk(kth).values[:, -1].numpy()
+        ga = np.ascontiguousarray(g.numpy())
+        out = np.full(T, -1.0, np.float32)
+        emu.emu_kth(c_int(vpl), _p(ga), c_int(R), c_longlong(T), c_int(m), c_int(kth), _p(out))
+        assert np.array_equal(out, ref), (R, T, m, kth)
+
+
+@pytest.mark.parametrize("T,d,N,k", [(5, 64, 40, 7), (3, 50, 30, 30), (2, 260, 64, 9)])
+def test_decode_backward_kernels(emu, T, d, N, k):
+    """decode_bwd_acts_kernel / decode_bwd_weight_kernel (vector and scalar paths, zero activations, an out-of-range
+    index) vs the oracle's restatement of TritonDecoder.backward"""
+    gen = torch.Generator().manual_seed(T * d)
+    W = torch.randn(N, d, generator=gen)
+    idx = torch.stack([torch.randperm(N, generator=gen)[:k] for _ in range(T)])
+    vals = torch.rand(T, k, generator=gen)
+    vals[::2, 0] = 0.0
+    go = torch.randn(T, d, generator=gen)
+    ref_a, ref_w = O.decode_backward(idx, vals, W, go)
+    Wn, idn, vn, gn = (np.ascontiguousarray(a.numpy()) for a in (W, idx, vals, go))
+    d_vals = np.full((T, k), np.nan, np.float32)
+    dW = np.zeros((N, d), np.float32)
+    err = np.zeros(1, np.int32)
+    emu.emu_decode_bwd_acts(_p(gn), c_longlong(d), _p(idn), c_longlong(T), c_int(k), _p(Wn), c_longlong(d),
+                            c_longlong(N), _p(d_vals), _p(err))
+    emu.emu_decode_bwd_weight(_p(gn), c_longlong(d), _p(idn), _p(vn), c_longlong(T), c_int(k), c_longlong(d),
+                              c_longlong(N), _p(dW), _p(err))
+    np.testing.assert_allclose(d_vals, ref_a.numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(dW, ref_w.numpy(), rtol=1e-5, atol=1e-5)
+    assert err[0] == 0
+    bad = idn.copy()
+    bad[0, 1] = N + 5
+    emu.emu_decode_bwd_acts(_p(gn), c_longlong(d), _p(bad), c_longlong(T), c_int(k), _p(Wn), c_longlong(d),
+                            c_longlong(N), _p(d_vals), _p(err))
+    assert err[0] == 1 and d_vals[0, 1] == 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+def _pipeline_inputs(emu, d, N, k, T, margin, seed):
+    """pack (mode 4) + activation prep through the emulated kernels, and the candidate lists the fused GEMM epilogue +
+    merge kernel would hand to the refinement (approximate values from the fp16 planes, top-K2 per row)."""
+    p = O.init_params(d, N, k, seed=seed)
+    x = torch.randn(T, d, generator=torch.Generator().manual_seed(seed + 1)).to(torch.bfloat16)
+    d_pad = (d + 7) // 8 * 8
+    W = np.ascontiguousarray(p.W_enc.numpy())
+    hi = np.zeros((N, d_pad), np.float16)
+    lo = np.zeros((N, d_pad), np.float16)
+    bias, wnorm, dnorm = (np.zeros(N, np.float32) for _ in range(3))
+    trailer = np.zeros(64, np.float32)
+    emu.emu_pack(_p(W), _p(p.b_enc.numpy()), _p(p.b_dec.numpy()), c_longlong(N), c_longlong(d), c_longlong(d_pad),
+                 _p(hi), _p(lo), _p(bias), _p(wnorm), _p(dnorm), _p(trailer))
+    xraw = _bf16_raw(x)
+    x16 = np.zeros((T, d_pad), np.float16)
+    row_scale, xnorm, xdnorm = (np.zeros(T, np.float32) for _ in range(3))
+    emu.emu_prep_x_bf16(_p(xraw), c_longlong(T), c_longlong(d), c_longlong(d), c_longlong(d_pad), _p(x16),
+                        _p(row_scale), _p(xnorm), _p(xdnorm))
+    # what the tensor cores + epilogue produce: (x16 . hi) * row_scale * w_unscale + folded bias
+    acc = x16.astype(np.float64) @ hi.astype(np.float64).T
+    a = (acc * row_scale[:, None].astype(np.float64) * float(trailer[0]) + bias[None, :]).astype(np.float32)
+    K2 = k + margin
+    order = np.lexsort((np.arange(N)[None, :].repeat(T, 0), -a), axis=1)[:, :K2]   # (value desc, index asc)
+    cand_idx = order.astype(np.int64)
+    cand_vals = np.take_along_axis(a, order, 1).astype(np.float32)
+    assert (cand_vals > 0).all(), "the toy shape must give every row K2 positive candidates"
+    return dict(p=p, x=x, xraw=xraw, W=W, hi=hi, lo=lo, bias=bias, wnorm=wnorm, dnorm=dnorm, trailer=trailer,
+                row_scale=row_scale, xnorm=xnorm, xdnorm=xdnorm, cand_idx=np.ascontiguousarray(cand_idx),
+                cand_vals=np.ascontiguousarray(cand_vals), K2=K2, d_pad=d_pad, a=a)
+
+
+def test_pack_and_prep_kernels(emu):
+    """w_stats / pack_w_f16 / pack_w_lo / prep_x_f16: folded bias, norms, power-of-two scales, hi + lo = W"""
+    s = _pipeline_inputs(emu, d=100, N=96, k=6, T=5, margin=8, seed=3)
+    p, W = s["p"], s["W"].astype(np.float64)
+    unscale = float(s["trailer"][0])
+    assert unscale > 0 and np.log2(unscale) == int(np.log2(unscale))
+    np.testing.assert_allclose(s["bias"], (p.b_enc.double() - p.W_enc.double() @ p.b_dec.double()).numpy(), rtol=1e-6,
+                               atol=1e-7)
+    assert (s["wnorm"] >= np.linalg.norm(W, axis=1) * (1 - 1e-7)).all()
+    np.testing.assert_allclose(s["wnorm"], np.linalg.norm(W, axis=1), rtol=1e-5)
+    hi, lo = s["hi"].astype(np.float64)[:, :100], s["lo"].astype(np.float64)[:, :100]
+    assert 2 ** 13 <= np.abs(s["hi"].astype(np.float32)).max() < 2 ** 14
+    assert np.abs(hi * unscale - W).max() > 1e-6 * np.abs(W).max()                  # fp16 alone is lossy ...
+    assert np.abs((hi + lo / 2048) * unscale - W).max() < 3e-7 * np.abs(W).max()     # ... hi + lo is not
+    np.testing.assert_allclose(s["dnorm"], np.linalg.norm(hi * unscale - W, axis=1), rtol=1e-4)
+    assert (s["hi"][:, 100:] == 0).all() and (s["lo"][:, 100:] == 0).all()           # zero padded rows
+    x = s["x"].float().numpy()
+    assert np.array_equal(s["hi"].shape, (96, 104))
+    np.testing.assert_allclose(s["xnorm"], np.linalg.norm(x.astype(np.float64), axis=1), rtol=2e-5)
+    assert (s["xdnorm"] == 0).all()                                                    # bf16 rows scale exactly
+    prep = np.zeros((5, 104), np.float16)
+    emu.emu_prep_x_bf16(_p(s["xraw"]), c_longlong(5), c_longlong(100), c_longlong(100), c_longlong(104), _p(prep),
+                        _p(s["row_scale"]), _p(s["xnorm"]), _p(s["xdnorm"]))
+    assert np.array_equal(prep.astype(np.float32)[:, :100] * s["row_scale"][:, None], x)
+
+
+def _run_refine(emu, s, k, *, lo, ext_lower=None, threads=256, clamp=(-1, 0.0)):
+    T, K2 = s["cand_vals"].shape
+    d, N = s["W"].shape[1], s["W"].shape[0]
+    out_vals = np.full((T, k), np.nan, np.float32)
+    out_idx = np.full((T, k), -7, np.int64)
+    status = np.zeros(64, np.int32)
+    flag_rows = np.full(max(T, 64), -1, np.int32)
+    emu.emu_refine_bf16(_p(s["xraw"]), c_longlong(T), c_longlong(d), _p(s["W"]), c_longlong(d), c_longlong(N),
+                        _p(s["bias"]), _p(s["wnorm"]), _p(s["dnorm"]), _p(s["trailer"]), _p(s["xnorm"]), _p(s["xdnorm"]),
+                        c_float(2.0 ** -14), _p(s["cand_vals"]), _p(s["cand_idx"]), c_int(K2), c_int(k),
+                        c_longlong(clamp[0]), c_float(clamp[1]), _p(out_vals), _p(out_idx), _p(status), _p(flag_rows),
+                        None if ext_lower is None else _p(ext_lower), _p(s["lo"]) if lo else None,
+                        c_longlong(s["d_pad"]), c_int(threads))
+    return out_vals, out_idx, int(status[0])
+
+
+@pytest.mark.parametrize("lo", [False, True])
+@pytest.mark.parametrize("d,N,k,margin", [(64, 256, 6, 10), (100, 300, 8, 12)])
+def test_refinement_kernels_end_to_end(emu, lo, d, N, k, margin):
+    """refine_kernel (exact fp32 re-evaluation) and refine_lo_kernel (residual-plane correction) on candidate lists
+    built from the fp16 planes: TopK index sets equal the oracle's fp32 encode, rows ordered (value desc, index asc),
+    values fp32 grade, no row flagged; the feature-sharded variant (ext_lower, 128 threads) agrees."""
+    T = 6
+    s = _pipeline_inputs(emu, d=d, N=N, k=k, T=T, margin=margin, seed=11 + d)
+    ref = O.encode(s["p"], s["x"].float())
+    ri, rv = O.canonical_topk(ref.top_acts, ref.top_indices)
+    # the single fp16 pass alone is not good enough to pass as the result
+    assert not np.allclose(np.sort(s["cand_vals"][:, :k], 1), np.sort(rv, 1), rtol=1e-6)
+    vals, idx, flagged = _run_refine(emu, s, k, lo=lo)
+    assert flagged == 0
+    gi, gv = O.canonical_topk(torch.from_numpy(vals), torch.from_numpy(idx))
+    assert np.array_equal(gi, ri)
+    np.testing.assert_allclose(gv, rv, rtol=3e-6, atol=1e-7)
+    assert (vals[:, :-1] >= vals[:, 1:]).all()
+    tie = vals[:, :-1] == vals[:, 1:]
+    assert (idx[:, :-1][tie] < idx[:, 1:][tie]).all()
+    # feature-sharded call: a lower bound of the "global" k-th value just below the true one changes nothing
+    ext = (np.sort(rv, 1)[:, 0] * 0.999).astype(np.float32)
+    v2, i2, _ = _run_refine(emu, s, k, lo=lo, ext_lower=ext, threads=128)
+    assert np.array_equal(i2, idx) and np.array_equal(v2, vals)
+    # ... and one just above the 3rd best value leaves only the latents whose upper bound still reaches it: a prefix of
+    # the true list (at least the two best), then zeros
+    ext_hi = (np.sort(rv, 1)[:, -3] * 1.0005).astype(np.float32)
+    v3, i3, _ = _run_refine(emu, s, k, lo=lo, ext_lower=ext_hi, threads=128)
+    n_kept = (v3 > 0).sum(1)
+    assert (n_kept >= 2).all() and (n_kept < k).all()
+    for r in range(T):
+        assert np.array_equal(v3[r, :n_kept[r]], vals[r, :n_kept[r]]) and np.array_equal(i3[r, :n_kept[r]], idx[r, :n_kept[r]])
+        assert (v3[r, n_kept[r]:] == 0).all()
+    # steering clamp: the GEMM epilogue overrides the clamped column before the candidate selection; the refinement
+    # takes that value verbatim (no re-evaluation) and the latent leads every row
+    f = int(idx[0, -1])
+    a = s["a"].copy()
+    a[:, f] = 50.0
+    order = np.lexsort((np.arange(N)[None, :].repeat(T, 0), -a), axis=1)[:, :s["K2"]]
+    sc = dict(s, cand_idx=np.ascontiguousarray(order.astype(np.int64)),
+              cand_vals=np.ascontiguousarray(np.take_along_axis(a, order, 1).astype(np.float32)))
+    v4, i4, _ = _run_refine(emu, sc, k, lo=lo, clamp=(f, 50.0))
+    assert (i4[:, 0] == f).all() and (v4[:, 0] == 50.0).all()
+    for r in range(T):   # the other k - 1 entries are the row's best latents apart from f
+        rest = [(v, i) for v, i in zip(vals[r], idx[r]) if i != f][:k - 1]
+        assert [int(i) for i in i4[r, 1:]] == [int(i) for _, i in rest]
+
+
+def test_candidate_bounds_kernel(emu):
+    """per-token k best lower bounds a_j - eps_j (descending, floored at 0) of candidate_bounds_kernel"""
+    k = 6
+    s = _pipeline_inputs(emu, d=64, N=256, k=k, T=5, margin=10, seed=5)
+    T, K2 = s["cand_vals"].shape
+    lb = np.full((T, k), np.nan, np.float32)
+    emu.emu_candidate_bounds(_p(s["cand_vals"]), _p(s["cand_idx"]), c_longlong(T), c_int(K2), c_int(k), _p(s["wnorm"]),
+                             _p(s["dnorm"]), _p(s["xnorm"]), _p(s["xdnorm"]), c_float(2.0 ** -14), c_longlong(-1), _p(lb))
+    wn, dn = s["wnorm"][s["cand_idx"]], s["dnorm"][s["cand_idx"]]
+    xn, xdn = s["xnorm"][:, None], s["xdnorm"][:, None]
+    eps = np.float32(1.001) * (xn * dn + xdn * wn) + np.float32(2.0 ** -14) * xn * wn
+    want = -np.sort(-np.maximum(s["cand_vals"] - eps, 0), axis=1)[:, :k]
+    np.testing.assert_allclose(lb, want, rtol=1e-6, atol=1e-7)
+    # every bound really is a lower bound of the exact activation of some latent, and the k-th one of the k-th value
+    exact = np.sort(O.pre_acts(s["p"], s["x"].float()).numpy(), axis=1)[:, ::-1]
+    assert (lb <= exact[:, :k] + 1e-7).all() and (lb[:, -1] > 0).all()
