@@ -5,6 +5,7 @@
 #include <cstdarg>
 
 #include "kernels_decode_bwd.cuh"
+#include "kernels_exchange.cuh"
 #include "kernels_kth.cuh"
 #include "kernels_pack.cuh"
 #include "kernels_refine.cuh"
@@ -95,6 +96,18 @@ void emu_refine_bf16(const void* x, long long T, long long ld_x, const float* W,
       refine_lo_kernel<__nv_bfloat16>(xb, ld_x, reinterpret_cast<const __half*>(lo), ld_w, d, N, bias, wnorm, dnorm,
                                       trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k, clamp_feature,
                                       clamp_value, out_vals, out_idx, status, flag_rows, ext_lower);
+  });
+}
+
+// one rank of the peer-memory all-gather, launched like push_gather_launch does (`blocks` CTAs); `peer_bases` holds
+// this process' mappings of all R symmetric buffers
+void emu_push_gather(const void* src, size_t bytes, void* const* peer_bases, int R, int self, size_t region_offset,
+                     size_t flags_offset, int channel, unsigned seq, int* counter, int blocks) {
+  const size_t n_vec = bytes / 16;
+  const size_t slab_off = region_offset + (size_t)self * bytes;
+  emu::launch({(unsigned)blocks}, {(unsigned)PUSH_THREADS}, [&] {
+    push_gather_kernel(reinterpret_cast<const uint4*>(src), n_vec, peer_bases, R, self, slab_off, nullptr, flags_offset,
+                       channel, seq, counter);
   });
 }
 

@@ -22,7 +22,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "multimodal-sae_b200", "csrc")
 EMU = os.path.join(ROOT, "tests", "emu")
 CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-HEADERS = ["common.cuh", "kernels_kth.cuh", "kernels_decode_bwd.cuh", "kernels_pack.cuh", "kernels_refine.cuh"]
+HEADERS = ["common.cuh", "kernels_kth.cuh", "kernels_decode_bwd.cuh", "kernels_pack.cuh", "kernels_refine.cuh",
+           "kernels_exchange.cuh"]
 
 
 @pytest.fixture(scope="module")
@@ -38,7 +39,9 @@ def emu(tmp_path_factory):
            os.path.join(EMU, "emu_kernels.cpp"), "-o", str(lib), "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
-    return ctypes.CDLL(str(lib))
+    handle = ctypes.CDLL(str(lib))
+    handle.path = str(lib)
+    return handle
 
 
 def _p(a):
@@ -235,3 +238,79 @@ def test_candidate_bounds_kernel(emu):
     # every bound really is a lower bound of the exact activation of some latent, and the k-th one of the k-th value
     exact = np.sort(O.pre_acts(s["p"], s["x"].float()).numpy(), axis=1)[:, ::-1]
     assert (lb <= exact[:, :k] + 1e-7).all() and (lb[:, -1] > 0).all()
+
+
+# ---------------------------------------------------------------------------------------------
+def _push_rank(lib_path, names, total_bytes, rank, R, chunks, rows, widths, blocks, q):
+    """one emulated rank of the peer-memory exchange: a process that maps all R symmetric buffers (at its own
+    addresses, like peer mappings) and runs push_gather_kernel for both exchanges of every chunk"""
+    import random
+    import time
+    from ctypes import c_size_t, c_uint32
+    from multiprocessing import shared_memory
+
+    try:
+        lib = ctypes.CDLL(lib_path)
+        shms = [shared_memory.SharedMemory(name=n) for n in names]
+        bases = (c_void_p * R)(*[ctypes.addressof(ctypes.c_char.from_buffer(s.buf)) for s in shms])
+        mine = np.frombuffer(shms[rank].buf, dtype=np.uint8)
+        flags_bytes, off, region = 4096, 4096, {}
+        for c, w in enumerate(widths):
+            region[c] = off
+            off += (R * rows * w * 4 + 1023) // 1024 * 1024
+        counters = np.zeros(len(widths), np.int32)
+        rng = random.Random(rank)
+        seq = [0] * len(widths)
+        for chunk in range(chunks):
+            T = rows if chunk % 4 else rows // 2          # a shorter chunk now and then: slab offsets follow T
+            for c, w in enumerate(widths):
+                seq[c] += 1
+                src = np.full((T, w), 1000 * chunk + 10 * c + rank, np.float32) + np.arange(w, dtype=np.float32)[None, :] / 64
+                lib.emu_push_gather(_p(src), c_size_t(src.nbytes), bases, c_int(R), c_int(rank), c_size_t(region[c]),
+                                    c_size_t(0), c_int(c), c_uint32(seq[c]), c_void_p(counters[c:].ctypes.data),
+                                    c_int(blocks))
+                if rng.random() < 0.5:
+                    time.sleep(rng.random() * 2e-3)       # the consumer kernel runs some time after the exchange
+                got = mine[region[c]:region[c] + R * T * w * 4].view(np.float32).reshape(R, T, w)
+                want = (np.array([1000 * chunk + 10 * c + r for r in range(R)], np.float32)[:, None, None]
+                        + np.arange(w, dtype=np.float32)[None, None, :] / 64).repeat(T, 1)
+                if not np.array_equal(got, want):
+                    q.put((rank, f"chunk {chunk} channel {c}: stale or torn slab"))
+                    return
+                if counters[c] != 0:
+                    q.put((rank, "the CTA counter was not restored"))
+                    return
+        q.put((rank, "ok"))   # the mappings go away with the process
+    except Exception as exc:   # noqa: BLE001
+        q.put((rank, repr(exc)))
+
+
+@pytest.mark.filterwarnings("ignore:This process .* is multi-threaded:DeprecationWarning")
+@pytest.mark.parametrize("R,blocks", [(2, 1), (4, 3)])
+def test_push_gather_kernel_ranks_as_processes(emu, R, blocks):
+    """push_gather_kernel itself (slab offsets, peer walk, last-CTA pattern, per-(channel, source) sequence flags with
+    release / acquire, wait loop) with R emulated ranks as processes over shared memory, alternating the two channels
+    like the scan does; every rank checks every gathered region after every exchange."""
+    import multiprocessing as mp
+    from multiprocessing import shared_memory
+
+    rows, widths, chunks = 48, (8, 16), 12
+    total = 4096 + sum((R * rows * w * 4 + 1023) // 1024 * 1024 for w in widths)
+    shms = [shared_memory.SharedMemory(create=True, size=total) for _ in range(R)]
+    try:
+        for s in shms:
+            np.frombuffer(s.buf, dtype=np.uint8)[:] = 0
+        ctx = mp.get_context("fork")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_push_rank, args=(emu.path, [s.name for s in shms], total, r, R, chunks, rows,
+                                                      widths, blocks, q)) for r in range(R)]
+        for pr in procs:
+            pr.start()
+        results = [q.get(timeout=120) for _ in range(R)]
+        for pr in procs:
+            pr.join(30)
+        assert sorted(results) == [(r, "ok") for r in range(R)], results
+    finally:
+        for s in shms:
+            s.close()
+            s.unlink()
