@@ -284,4 +284,170 @@ candidate_bounds_kernel(const float* __restrict__ cand_vals, const long long* __
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// exact dense fallback for flagged rows: dense[slot][n] = relu(x_row . W[n] + bias[n]) in fp32, then a dense TopK
+// ---------------------------------------------------------------------------------------------
+template <typename XT>
+__global__ void __launch_bounds__(256)
+exact_rows_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict__ W, long long d, long long N,
+                  const float* __restrict__ bias, const int* __restrict__ status, const int* __restrict__ flag_rows,
+                  long long clamp_feature, float clamp_value, float* __restrict__ dense) {
+  extern __shared__ float xsm[];
+  const int slot = blockIdx.y;
+  const int nflag = min(status[0], RF_MAX_FLAG);
+  if (slot >= nflag) return;
+  const long long t = flag_rows[slot];
+  for (long long i = threadIdx.x; i < d; i += blockDim.x) xsm[i] = (float)x[t * ld_x + i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long per_block = (N + gridDim.x - 1) / gridDim.x;
+  const long long n0 = (long long)blockIdx.x * per_block;
+  const long long n1 = (n0 + per_block < N) ? n0 + per_block : N;
+  for (long long n = n0 + warp; n < n1; n += nw) {
+    const float* wr = W + n * d;
+    float acc = 0.f;
+    for (long long i = lane; i < d; i += 32) acc = fmaf(wr[i], xsm[i], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      float v = acc + bias[n];
+      if (n == clamp_feature) v = clamp_value;
+      dense[(long long)slot * N + n] = fmaxf(v, 0.f);
+    }
+  }
+}
+
+// TopK of one dense non-negative row (value desc, index asc) by a whole block; `dsm` = kp2 uint2 of shared memory.
+__device__ __forceinline__ void dense_topk_block(const float* row, long long N, int k, uint2* dsm, long long orow,
+                                                 float* __restrict__ out_vals, long long* __restrict__ out_idx) {
+  __shared__ int s_red[32];
+  __shared__ int s_count;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  auto block_sum = [&](int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    int s = 0;
+    for (int w = 0; w < nw; ++w) s += s_red[w];
+    return s;
+  };
+  auto keyof = [&](long long i) { return __float_as_uint(fmaxf(row[i], 0.f)); };
+  int kp2 = 2;
+  while (kp2 < k) kp2 <<= 1;
+  // k-th largest key
+  uint32_t prefix = 0;
+  for (int bit = 30; bit >= 0; --bit) {
+    const uint32_t trial = prefix | (1u << bit);
+    int c = 0;
+    for (long long i = tid; i < N; i += blockDim.x) c += (keyof(i) >= trial) ? 1 : 0;
+    if (block_sum(c) >= k) prefix = trial;
+  }
+  int c_gt = 0, c_eq = 0;
+  for (long long i = tid; i < N; i += blockDim.x) {
+    const uint32_t key = keyof(i);
+    c_gt += key > prefix;
+    c_eq += key == prefix;
+  }
+  c_gt = block_sum(c_gt);
+  c_eq = block_sum(c_eq);
+  const int need_eq = k - c_gt;
+  uint32_t idx_cut = 0xffffffffu;
+  if (c_eq > need_eq) {
+    uint32_t p2 = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t trial = p2 | (1u << bit);
+      int c = 0;
+      for (long long i = tid; i < N; i += blockDim.x) c += (keyof(i) == prefix && (uint32_t)i < trial) ? 1 : 0;
+      if (block_sum(c) < need_eq) p2 = trial;
+    }
+    idx_cut = p2;
+  }
+  __syncthreads();
+  if (tid == 0) s_count = 0;
+  for (int i = tid; i < kp2; i += blockDim.x) dsm[i] = make_uint2(0u, 0xffffffffu);
+  __syncthreads();
+  for (long long i = tid; i < N; i += blockDim.x) {
+    const uint32_t key = keyof(i);
+    if (key > prefix || (key == prefix && (uint32_t)i <= idx_cut)) {
+      const int p = atomicAdd(&s_count, 1);
+      if (p < kp2) dsm[p] = make_uint2(key, (uint32_t)i);
+    }
+  }
+  __syncthreads();
+  for (int size = 2; size <= kp2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int p = tid; p < (kp2 >> 1); p += blockDim.x) {
+        const int lo = ((p / stride) * stride * 2) + (p % stride);
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const uint2 a = dsm[lo], b = dsm[hi];
+        const bool a_first = (a.x > b.x) || (a.x == b.x && a.y < b.y);
+        if (a_first != desc) {
+          dsm[lo] = b;
+          dsm[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < k; i += blockDim.x) {
+    out_vals[orow * k + i] = __uint_as_float(dsm[i].x);
+    out_idx[orow * k + i] = (long long)dsm[i].y;
+  }
+  __syncthreads();
+}
+
+// TopK of dense non-negative rows.  `row_map` (optional) redirects output rows; rows beyond `*n_rows_dev` (optional
+// device count) exit.  One block per row.  Also serves Sae.select_topk on dense tensors.
+__global__ void __launch_bounds__(1024)
+dense_topk_kernel(const float* __restrict__ dense, long long ld, long long N, int k, const int* __restrict__ n_rows_dev,
+                  int max_rows, const int* __restrict__ row_map, float* __restrict__ out_vals,
+                  long long* __restrict__ out_idx) {
+  extern __shared__ uint2 dsm[];   // [kp2] selected (value bits, index)
+  const int slot = blockIdx.x;
+  if (n_rows_dev != nullptr && slot >= min(*n_rows_dev, max_rows)) return;
+  const long long orow = row_map ? row_map[slot] : slot;
+  dense_topk_block(dense + (long long)slot * ld, N, k, dsm, orow, out_vals, out_idx);
+}
+
+// Flagged rows beyond the first RF_MAX_FLAG (degenerate inputs: massive ties, k close to N): block b walks the slots
+// RF_MAX_FLAG + b, RF_MAX_FLAG + b + gridDim.x, ...; per slot it writes the exact dense row into its private scratch
+// row and takes the TopK from it.  Exits at once in the normal case.
+template <typename XT>
+__global__ void __launch_bounds__(1024)
+overflow_rows_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict__ W, long long d, long long N,
+                     const float* __restrict__ bias, const int* __restrict__ status, const int* __restrict__ flag_rows,
+                     long long clamp_feature, float clamp_value, float* dense, int k, float* __restrict__ out_vals,
+                     long long* __restrict__ out_idx) {
+  extern __shared__ uint2 osm[];   // [kp2] uint2 | [d] float
+  const int nflag = status[0];
+  if (nflag <= RF_MAX_FLAG) return;
+  int kp2 = 2;
+  while (kp2 < k) kp2 <<= 1;
+  float* xs = reinterpret_cast<float*>(osm + kp2);
+  float* my = dense + (long long)blockIdx.x * N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int slot = RF_MAX_FLAG + blockIdx.x; slot < nflag; slot += gridDim.x) {
+    const long long t = flag_rows[slot];
+    for (long long i = threadIdx.x; i < d; i += blockDim.x) xs[i] = (float)x[t * ld_x + i];
+    __syncthreads();
+    for (long long n = warp; n < N; n += nw) {
+      const float* wr = W + n * d;
+      float acc = 0.f;
+      for (long long i = lane; i < d; i += 32) acc = fmaf(wr[i], xs[i], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        float v = acc + bias[n];
+        if (n == clamp_feature) v = clamp_value;
+        my[n] = fmaxf(v, 0.f);
+      }
+    }
+    __syncthreads();
+    dense_topk_block(my, N, k, osm, t, out_vals, out_idx);
+  }
+}
+
 }  // namespace saeb

@@ -18,7 +18,7 @@ LIB_DIR = os.path.join(PKG_DIR, "lib")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(LIB_DIR, "libsaeb200.so")
 SOURCES = ["capi.cu", "encode_topk.cu", "decode.cu", "pack.cu", "coo_scan.cu", "refine.cu", "exchange.cu", "decode_bwd.cu"]
-HEADERS = ["common.cuh", "kernels_refine.cuh", "kernels_kth.cuh", "kernels_decode_bwd.cuh", "kernels_pack.cuh", "kernels_exchange.cuh",
+HEADERS = ["common.cuh", "kernels_refine.cuh", "kernels_kth.cuh", "kernels_decode_bwd.cuh", "kernels_pack.cuh", "kernels_exchange.cuh", "kernels_coo_scan.cuh", "kernels_topk_select.cuh", "kernels_decode.cuh",
            os.path.join("..", "..", "include", "saeb200.h")]
 
 NVCC_FLAGS = [

@@ -14,6 +14,7 @@
 #include <vector_functions.h>
 #include <vector_types.h>
 
+#include <algorithm>
 #include <barrier>
 #include <cmath>
 #include <cstdint>
@@ -234,6 +235,8 @@ inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
 
 // the two streaming-load helpers of common.cuh that the emulated kernels use (inline PTX on the GPU)
 namespace saeb {
+using std::max;
+using std::min;
 inline float4 ldg_nc_f4(const float4* p) { return *p; }
 inline uint4 ldg_nc_u4(const uint4* p) { return *p; }
 }  // namespace saeb

@@ -4,11 +4,14 @@
 #define SAEB_CPU_EMU 1
 #include <cstdarg>
 
+#include "kernels_coo_scan.cuh"
+#include "kernels_decode.cuh"
 #include "kernels_decode_bwd.cuh"
 #include "kernels_exchange.cuh"
 #include "kernels_kth.cuh"
 #include "kernels_pack.cuh"
 #include "kernels_refine.cuh"
+#include "kernels_topk_select.cuh"
 
 namespace saeb {
 void set_error(const char*, ...) {}
@@ -16,6 +19,26 @@ void set_error(const char*, ...) {}
 alignas(16) float rsm[1 << 16];
 alignas(16) float bsm[1 << 12];
 alignas(16) float gsm[1 << 16];
+alignas(16) float xsm[1 << 14];
+alignas(16) uint2 esm[1 << 14];
+alignas(16) uint2 ssm[1 << 15];
+alignas(16) uint2 msm[1 << 16];
+alignas(16) uint2 dsm[1 << 12];
+alignas(16) uint2 osm[1 << 14];
+alignas(16) uint32_t hsm[1 << 16];
+
+// compact_row is a device function of the fused tcgen05 kernel's epilogue: run it from a one-warp wrapper
+template <int SLOTS>
+void compact_row_wrapper(uint2* buf, int cnt_in, int k, float* thr_out, int* cnt_out) {
+  static int hist[256];
+  float thr = 0.f;
+  int cnt = 0;
+  compact_row<SLOTS>(buf, cnt_in, k, threadIdx.x & 31u, hist, thr, cnt);
+  if (threadIdx.x == 0) {
+    *thr_out = thr;
+    *cnt_out = cnt;
+  }
+}
 }  // namespace saeb
 
 using namespace saeb;
@@ -97,6 +120,98 @@ void emu_refine_bf16(const void* x, long long T, long long ld_x, const float* W,
                                       trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k, clamp_feature,
                                       clamp_value, out_vals, out_idx, status, flag_rows, ext_lower);
   });
+}
+
+void emu_compact_row(int slots, void* buf, int cnt_in, int k, float* thr_out, int* cnt_out) {
+  uint2* b = reinterpret_cast<uint2*>(buf);
+  emu::launch({1}, {32}, [&] {
+    if (slots == 8) compact_row_wrapper<8>(b, cnt_in, k, thr_out, cnt_out);
+    else if (slots == 16) compact_row_wrapper<16>(b, cnt_in, k, thr_out, cnt_out);
+    else compact_row_wrapper<32>(b, cnt_in, k, thr_out, cnt_out);
+  });
+}
+
+// exactly the launch geometry of encode_merge_launch for one chunk
+void emu_topk_merge(const void* cand, const int* cand_cnt, int T, int S, int CAP, int k, int N, float* out_vals,
+                    long long* out_idx) {
+  int kp2 = 2;
+  while (kp2 < k) kp2 <<= 1;
+  const int max_entries = S * CAP;
+  const size_t per_warp = (size_t)(max_entries + kp2) * sizeof(uint2);
+  int wpb = (int)((200 * 1024) / per_warp);
+  if (wpb > 8) wpb = 8;
+  const unsigned blocks = (unsigned)((T + wpb - 1) / wpb);
+  emu::launch({blocks}, {(unsigned)wpb * 32}, [&] {
+    topk_merge_kernel(reinterpret_cast<const uint2*>(cand), cand_cnt, T, S, CAP, k, kp2, N, max_entries, out_vals,
+                      out_idx);
+  });
+}
+
+// the five launches of coo_extract_launch
+void emu_coo_extract(const float* vals, const long long* idx, long long T, int k, float threshold,
+                     const uint32_t* filter, long long seq_len, long long row_offset, long long* locations,
+                     float* activations, long long* nnz_out) {
+  std::vector<int> counts(T);
+  std::vector<long long> offsets(T + 1);
+  const long long nchunks = (T + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  std::vector<long long> sums(nchunks + 1);
+  const unsigned g8 = (unsigned)((T + 7) / 8);
+  emu::launch({g8}, {256}, [&] { coo_count_kernel(vals, idx, T, k, threshold, filter, counts.data()); });
+  emu::launch({(unsigned)nchunks}, {(unsigned)SCAN_CHUNK}, [&] { scan_chunk_sum_kernel(counts.data(), T, sums.data()); });
+  emu::launch({1}, {(unsigned)SCAN_CHUNK}, [&] { scan_sums_kernel(sums.data(), nchunks, nnz_out); });
+  emu::launch({(unsigned)nchunks}, {(unsigned)SCAN_CHUNK},
+              [&] { scan_chunks_kernel(counts.data(), T, sums.data(), offsets.data()); });
+  int kp2 = 2;
+  while (kp2 < k) kp2 <<= 1;
+  emu::launch({g8}, {256}, [&] {
+    coo_emit_kernel(vals, idx, T, k, kp2, threshold, filter, offsets.data(), seq_len, row_offset, locations, activations);
+  });
+}
+
+void emu_scan_pool(const float* vals, const long long* idx, long long T, int k, int ctx_len, float threshold,
+                   long long feat_lo, long long feat_hi, long long window_base, const float* tok_thr,
+                   const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap, int* overflow) {
+  const long long n_win = (T + ctx_len - 1) / ctx_len;
+  int slots = 64;
+  while (slots < 2 * (long long)ctx_len * k) slots <<= 1;
+  emu::launch({(unsigned)n_win}, {256}, [&] {
+    scan_pool_kernel(vals, idx, T, k, ctx_len, threshold, feat_lo, feat_hi, window_base, tok_thr, feat_thr,
+                     reinterpret_cast<uint2*>(bucket), bucket_cnt, bucket_cap, slots, overflow);
+  });
+}
+
+void emu_scan_merge(void* bucket, int* bucket_cnt, int bucket_cap, long long F, int n_top, float base_thr,
+                    float* top_vals, long long* top_win, float* feat_thr) {
+  int sort_n = 2;
+  while (sort_n < n_top + bucket_cap) sort_n <<= 1;
+  emu::launch({(unsigned)((F + 7) / 8)}, {256}, [&] {
+    scan_merge_kernel(reinterpret_cast<uint2*>(bucket), bucket_cnt, bucket_cap, F, n_top, sort_n, base_thr, top_vals,
+                      top_win, feat_thr);
+  });
+}
+
+// decode: W as fp32 (w16 == 0) or as an fp16 copy; x (bf16, optional) + sq_err accumulate; `scalar` forces the
+// one-column-per-thread kernel
+void emu_decode(const long long* idx, const float* vals, long long T, int k, const void* W, int w16, long long d,
+                long long N, const float* b_dec, float* out, const void* x, double* sq_err, int* err_flag, int scalar) {
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  emu::launch({(unsigned)T}, {(unsigned)DEC_THREADS}, [&] {
+    if (scalar)
+      decode_scalar_kernel<float, float, __nv_bfloat16>(idx, vals, k, reinterpret_cast<const float*>(W), d, N, b_dec,
+                                                         out, d, xb, d, sq_err, err_flag);
+    else if (w16)
+      decode_kernel<__half, float, __nv_bfloat16>(idx, vals, k, reinterpret_cast<const __half*>(W), d, N, b_dec, out, d,
+                                                  xb, d, sq_err, err_flag);
+    else
+      decode_kernel<float, float, __nv_bfloat16>(idx, vals, k, reinterpret_cast<const float*>(W), d, N, b_dec, out, d,
+                                                 xb, d, sq_err, err_flag);
+  });
+}
+
+void emu_dense_topk(const float* dense, long long T, long long ld, long long N, int k, float* out_vals,
+                    long long* out_idx, int threads) {
+  emu::launch({(unsigned)T}, {(unsigned)threads},
+              [&] { dense_topk_kernel(dense, ld, N, k, nullptr, 0, nullptr, out_vals, out_idx); });
 }
 
 // one rank of the peer-memory all-gather, launched like push_gather_launch does (`blocks` CTAs); `peer_bases` holds

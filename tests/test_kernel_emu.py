@@ -22,8 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "multimodal-sae_b200", "csrc")
 EMU = os.path.join(ROOT, "tests", "emu")
 CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-HEADERS = ["common.cuh", "kernels_kth.cuh", "kernels_decode_bwd.cuh", "kernels_pack.cuh", "kernels_refine.cuh",
-           "kernels_exchange.cuh"]
+HEADERS = ["common.cuh"] + sorted(f for f in os.listdir(CSRC) if f.startswith("kernels_") and f.endswith(".cuh"))
 
 
 @pytest.fixture(scope="module")
@@ -238,6 +237,185 @@ def test_candidate_bounds_kernel(emu):
     # every bound really is a lower bound of the exact activation of some latent, and the k-th one of the k-th value
     exact = np.sort(O.pre_acts(s["p"], s["x"].float()).numpy(), axis=1)[:, ::-1]
     assert (lb <= exact[:, :k] + 1e-7).all() and (lb[:, -1] > 0).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# kernels that are verified on the GPU as well: kept under emulation as regression tests of their logic
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("slots,k,cnt,ties", [(8, 64, 250, False), (8, 112, 256, False), (8, 16, 230, True),
+                                               (16, 200, 500, False), (32, 300, 1000, True)])
+def test_compact_row_keeps_a_superset_of_the_top_k(emu, slots, k, cnt, ties):
+    """compact_row (epilogue of the fused tcgen05 kernel): histogram threshold with the exact tie-capped fallback.
+    Whatever path it takes, the compacted list keeps at least k entries including every entry above the k-th value,
+    in arrival order, and the threshold it returns excludes nothing that could still belong to the top k."""
+    rng = np.random.default_rng(slots + k)
+    vals = rng.random(cnt).astype(np.float32) + 0.01
+    if ties:
+        vals[rng.random(cnt) < 0.9] = 0.5   # heavy ties force the exact path
+    buf = np.zeros((32 * slots, 2), np.uint32)
+    buf[:cnt, 0] = vals.view(np.uint32)
+    buf[:cnt, 1] = np.arange(cnt) * 3 + 1
+    before = buf[:cnt].copy()
+    thr = np.zeros(1, np.float32)
+    n_out = np.zeros(1, np.int32)
+    emu.emu_compact_row(c_int(slots), _p(buf), c_int(cnt), c_int(k), _p(thr), _p(n_out))
+    n = int(n_out[0])
+    kept = buf[:n]
+    assert k <= n <= cnt and n <= 32 * slots - 32
+    kth = np.sort(vals)[-k]
+    kept_vals = kept[:, 0].view(np.float32)
+    assert (kept_vals >= thr[0]).all() and thr[0] <= kth
+    gt = before[before[:, 0].view(np.float32) > kth]
+    assert set(map(tuple, gt)) <= set(map(tuple, kept))                       # nothing above the k-th value is lost
+    assert np.sort(kept_vals)[-k:].tolist() == np.sort(vals)[-k:].tolist()     # the top-k multiset survives
+    pos = {tuple(e): i for i, e in enumerate(before)}
+    order = [pos[tuple(e)] for e in kept]
+    assert order == sorted(order)                                               # arrival order is preserved
+
+
+@pytest.mark.parametrize("T,S,CAP,k,N", [(11, 2, 256, 64, 5000), (5, 3, 256, 7, 1200), (4, 1, 512, 200, 3000)])
+def test_topk_merge_kernel(emu, T, S, CAP, k, N):
+    """topk_merge_kernel: exact top-k over the S candidate lists of a row, canonical order (value desc, index asc),
+    ties at the k-th value resolved towards the smaller index, zero padding on unused indices for short rows"""
+    rng = np.random.default_rng(T * S)
+    cand = np.zeros((T, S, CAP, 2), np.uint32)
+    cnt = np.zeros((T, S), np.int32)
+    want_v, want_i = np.zeros((T, k), np.float32), np.zeros((T, k), np.int64)
+    for t in range(T):
+        rows = []
+        for s in range(S):
+            n = int(rng.integers(k // S + 1, CAP)) if t != 1 else 2   # row 1 is short: fewer than k candidates
+            cols = rng.choice(np.arange(s * (N // S), (s + 1) * (N // S)), size=n, replace=False)
+            v = np.round(rng.random(n).astype(np.float32) * 8, 1 if t == 2 else 6) + np.float32(0.5)   # row 2: many ties
+            cand[t, s, :n, 0] = v.view(np.uint32)
+            cand[t, s, :n, 1] = cols
+            cnt[t, s] = n
+            rows += list(zip(v.tolist(), cols.tolist()))
+        rows.sort(key=lambda e: (-e[0], e[1]))
+        top = rows[:k]
+        want_v[t, :len(top)] = [e[0] for e in top]
+        want_i[t, :len(top)] = [e[1] for e in top]
+        if len(top) < k:   # padded with value 0 on the smallest unused indices
+            used, fill, j = {e[1] for e in top}, [], 0
+            while len(fill) < k - len(top):
+                if j not in used:
+                    fill.append(j)
+                j += 1
+            want_i[t, len(top):] = fill
+    out_v = np.full((T, k), np.nan, np.float32)
+    out_i = np.full((T, k), -1, np.int64)
+    emu.emu_topk_merge(_p(cand), _p(cnt), c_int(T), c_int(S), c_int(CAP), c_int(k), c_int(N), _p(out_v), _p(out_i))
+    assert np.array_equal(out_v, want_v) and np.array_equal(out_i, want_i)
+
+
+@pytest.mark.parametrize("tag", ["nofilter", "filter"])
+def test_coo_extract_kernels(emu, tag):
+    """coo_count / scan / emit: the reference's (row, pos, feature) triples in torch.nonzero order (features/cache.py:
+    73-92), threshold and filter bitmap included; T spans two scan chunks"""
+    from saeb200.engine import make_filter_bitmap
+
+    N, k, seq, rows = 300, 6, 37, 31    # T = 1147 tokens > SCAN_CHUNK
+    T = seq * rows
+    gen = torch.Generator().manual_seed(8)
+    vals = torch.rand(T, k, generator=gen)
+    vals[vals < 0.15] = 0.0
+    vals[5, 2] = 5e-6                    # below the 1e-5 threshold
+    idx = torch.stack([torch.randperm(N, generator=gen)[:k] for _ in range(T)])
+    sel = torch.tensor([1, 5, 15, 16, 31, 40, 63, 200, 299]) if tag == "filter" else None
+    dense = torch.zeros(rows, seq, N).scatter_(-1, idx.view(rows, seq, k), vals.view(rows, seq, k))
+    ref_loc, ref_act = O.get_nonzeros(dense, sel)
+    ref_loc = ref_loc.clone()
+    ref_loc[:, 0] += 100
+    bitmap = None if sel is None else np.ascontiguousarray(make_filter_bitmap(sel, N).numpy())
+    loc = np.full((T * k, 3), -1, np.int64)
+    act = np.full(T * k, np.nan, np.float32)
+    nnz = np.zeros(1, np.int64)
+    emu.emu_coo_extract(_p(np.ascontiguousarray(vals.numpy())), _p(np.ascontiguousarray(idx.numpy())), c_longlong(T),
+                        c_int(k), c_float(1e-5), None if bitmap is None else _p(bitmap), c_longlong(seq),
+                        c_longlong(100), _p(loc), _p(act), _p(nnz))
+    n = int(nnz[0])
+    assert n == ref_loc.shape[0]
+    assert np.array_equal(loc[:n], ref_loc.numpy()) and np.array_equal(act[:n], ref_act.numpy())
+
+
+def test_scan_pool_and_merge_kernels(emu):
+    """scan_pool_kernel + scan_merge_kernel over several chunks and flushes vs the oracle's scan, for a feature shard
+    with a per-token threshold (the feature-sharded form)"""
+    N, k, ctx, n_top, n_win, cap = 120, 5, 8, 3, 20, 8
+    T = ctx * n_win
+    gen = torch.Generator().manual_seed(9)
+    vals = torch.rand(T, k, generator=gen)
+    vals[vals < 0.1] = 0.0
+    idx = torch.stack([torch.randperm(N, generator=gen)[:k] for _ in range(T)])
+    tok_thr = (vals.max(1).values * 0.5).contiguous()                 # drops the smaller half of every token's entries
+    masked = torch.where(vals >= tok_thr[:, None], vals, torch.zeros_like(vals))
+    lo, hi = 30, 100
+    ref_s, ref_w = O.scan_top_windows(masked, idx, N, ctx, n_top)
+    F = hi - lo
+    top_vals = np.zeros((F, n_top), np.float32)
+    top_win = np.full((F, n_top), -1, np.int64)
+    feat_thr = np.full(F, 1e-5, np.float32)
+    bucket = np.zeros((F, cap, 2), np.uint32)
+    bucket_cnt = np.zeros(F, np.int32)
+    overflow = np.zeros(1, np.int32)
+    vn, inn, tn = (np.ascontiguousarray(a.numpy()) for a in (vals, idx, tok_thr))
+    for w0 in range(0, n_win, cap):                                    # at most bucket_cap windows between two merges
+        t0, t1 = w0 * ctx, min(T, (w0 + cap) * ctx)
+        emu.emu_scan_pool(_p(vn[t0:t1]), _p(inn[t0:t1]), c_longlong(t1 - t0), c_int(k), c_int(ctx), c_float(1e-5),
+                          c_longlong(lo), c_longlong(hi), c_longlong(w0), _p(tn[t0:t1]), _p(feat_thr), _p(bucket),
+                          _p(bucket_cnt), c_int(cap), _p(overflow))
+        emu.emu_scan_merge(_p(bucket), _p(bucket_cnt), c_int(cap), c_longlong(F), c_int(n_top), c_float(1e-5),
+                           _p(top_vals), _p(top_win), _p(feat_thr))
+    assert overflow[0] == 0
+    assert np.array_equal(top_vals, ref_s[lo:hi]) and np.array_equal(top_win, ref_w[lo:hi])
+
+
+@pytest.mark.parametrize("w16,scalar,d", [(0, 0, 64), (1, 0, 64), (0, 1, 50)])
+def test_decode_kernels(emu, w16, scalar, d):
+    """decode_kernel (fp32 and fp16 weight rows) and decode_scalar_kernel: gather decode + bias + residual sum of
+    squares, zero activations skipped, an out-of-range index flagged"""
+    N, k, T = 90, 9, 7
+    gen = torch.Generator().manual_seed(d + w16)
+    W = torch.randn(N, d, generator=gen)
+    b = torch.randn(d, generator=gen)
+    vals = torch.rand(T, k, generator=gen)
+    vals[::2, 1] = 0.0
+    idx = torch.stack([torch.randperm(N, generator=gen)[:k] for _ in range(T)])
+    x = torch.randn(T, d, generator=gen).to(torch.bfloat16)
+    Wd = W.to(torch.float16) if w16 else W
+    ref = O.sparse_decode(idx, vals, Wd.float()) + b
+    Wn = np.ascontiguousarray(Wd.view(torch.int16).numpy() if w16 else Wd.numpy())
+    out = np.full((T, d), np.nan, np.float32)
+    sq = np.zeros(1, np.float64)
+    err = np.zeros(1, np.int32)
+    idn, vn = np.ascontiguousarray(idx.numpy()), np.ascontiguousarray(vals.numpy())
+    emu.emu_decode(_p(idn), _p(vn), c_longlong(T), c_int(k), _p(Wn), c_int(w16), c_longlong(d), c_longlong(N),
+                   _p(np.ascontiguousarray(b.numpy())), _p(out), _p(_bf16_raw(x)), _p(sq), _p(err), c_int(scalar))
+    np.testing.assert_allclose(out, ref.numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(sq[0], float(((ref - x.float()) ** 2).sum()), rtol=1e-5)
+    assert err[0] == 0
+    idn[0, 0] = N
+    emu.emu_decode(_p(idn), _p(vn), c_longlong(T), c_int(k), _p(Wn), c_int(w16), c_longlong(d), c_longlong(N), None,
+                   _p(out), None, None, _p(err), c_int(scalar))
+    assert err[0] == 1
+
+
+def test_dense_topk_kernel(emu):
+    """dense_topk_kernel (Sae.select_topk on dense tensors, and the refine fallback): (value desc, index asc), ties at
+    the k-th value towards the smaller index"""
+    N, k, T = 500, 12, 2
+    gen = torch.Generator().manual_seed(12)
+    dense = torch.relu(torch.randn(T, N, generator=gen))
+    dense[1] = torch.round(dense[1] * 4) / 4                          # a row full of ties
+    want_v, want_i = np.zeros((T, k), np.float32), np.zeros((T, k), np.int64)
+    for t in range(T):
+        order = sorted(range(N), key=lambda j: (-float(dense[t, j]), j))[:k]
+        want_i[t], want_v[t] = order, dense[t, order].numpy()
+    out_v = np.full((T, k), np.nan, np.float32)
+    out_i = np.full((T, k), -1, np.int64)
+    emu.emu_dense_topk(_p(np.ascontiguousarray(dense.numpy())), c_longlong(T), c_longlong(N), c_longlong(N), c_int(k),
+                       _p(out_v), _p(out_i), c_int(256))
+    assert np.array_equal(out_v, want_v) and np.array_equal(out_i, want_i)
 
 
 # ---------------------------------------------------------------------------------------------
