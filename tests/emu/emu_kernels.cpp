@@ -214,6 +214,35 @@ void emu_dense_topk(const float* dense, long long T, long long ld, long long N, 
               [&] { dense_topk_kernel(dense, ld, N, k, nullptr, 0, nullptr, out_vals, out_idx); });
 }
 
+// the three fallback launches of refine_launch_t for flagged rows (bf16 activations): exact dense rows of the first
+// RF_MAX_FLAG flagged tokens + their dense TopK, then the overflow kernel for the rest
+void emu_refine_fallback(const void* x, long long ld_x, const float* W, long long d, long long N, const float* bias,
+                         const int* status, const int* flag_rows, long long clamp_feature, float clamp_value,
+                         float* dense_scratch, int k, float* out_vals, long long* out_idx, int gx, int threads) {
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  emu::launch({(unsigned)gx, (unsigned)RF_MAX_FLAG}, {256}, [&] {
+    exact_rows_kernel<__nv_bfloat16>(xb, ld_x, W, d, N, bias, status, flag_rows, clamp_feature, clamp_value,
+                                     dense_scratch);
+  });
+  emu::launch({(unsigned)RF_MAX_FLAG}, {(unsigned)threads}, [&] {
+    dense_topk_kernel(dense_scratch, N, N, k, status, RF_MAX_FLAG, flag_rows, out_vals, out_idx);
+  });
+  emu::launch({3}, {(unsigned)threads}, [&] {
+    overflow_rows_kernel<__nv_bfloat16>(xb, ld_x, W, d, N, bias, status, flag_rows, clamp_feature, clamp_value,
+                                        dense_scratch, k, out_vals, out_idx);
+  });
+}
+
+// FVU denominator: colstats_kernel + totvar_kernel as total_variance_launch enqueues them (bf16 activations)
+void emu_total_variance_bf16(const void* x, long long T, long long d, long long ld_x, double* scratch, double* out) {
+  std::memset(scratch, 0, sizeof(double) * 2 * d);
+  const int rpb = 64;
+  emu::launch({(unsigned)((T + rpb - 1) / rpb)}, {256}, [&] {
+    colstats_kernel<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(x), T, d, ld_x, rpb, scratch, scratch + d);
+  });
+  emu::launch({1}, {256}, [&] { totvar_kernel(scratch, scratch + d, T, d, out); });
+}
+
 // one rank of the peer-memory all-gather, launched like push_gather_launch does (`blocks` CTAs); `peer_bases` holds
 // this process' mappings of all R symmetric buffers
 void emu_push_gather(const void* src, size_t bytes, void* const* peer_bases, int R, int self, size_t region_offset,

@@ -44,6 +44,7 @@ def emu(tmp_path_factory):
 
 
 def _p(a):
+    """pointer to a numpy array the CALLER keeps alive (never pass a temporary: its memory is gone after this line)"""
     return c_void_p(a.ctypes.data)
 
 
@@ -111,7 +112,8 @@ def _pipeline_inputs(emu, d, N, k, T, margin, seed):
     lo = np.zeros((N, d_pad), np.float16)
     bias, wnorm, dnorm = (np.zeros(N, np.float32) for _ in range(3))
     trailer = np.zeros(64, np.float32)
-    emu.emu_pack(_p(W), _p(p.b_enc.numpy()), _p(p.b_dec.numpy()), c_longlong(N), c_longlong(d), c_longlong(d_pad),
+    b_enc, b_dec = np.ascontiguousarray(p.b_enc.numpy()), np.ascontiguousarray(p.b_dec.numpy())
+    emu.emu_pack(_p(W), _p(b_enc), _p(b_dec), c_longlong(N), c_longlong(d), c_longlong(d_pad),
                  _p(hi), _p(lo), _p(bias), _p(wnorm), _p(dnorm), _p(trailer))
     xraw = _bf16_raw(x)
     x16 = np.zeros((T, d_pad), np.float16)
@@ -330,7 +332,8 @@ def test_coo_extract_kernels(emu, tag):
     loc = np.full((T * k, 3), -1, np.int64)
     act = np.full(T * k, np.nan, np.float32)
     nnz = np.zeros(1, np.int64)
-    emu.emu_coo_extract(_p(np.ascontiguousarray(vals.numpy())), _p(np.ascontiguousarray(idx.numpy())), c_longlong(T),
+    vn, inn = np.ascontiguousarray(vals.numpy()), np.ascontiguousarray(idx.numpy())
+    emu.emu_coo_extract(_p(vn), _p(inn), c_longlong(T),
                         c_int(k), c_float(1e-5), None if bitmap is None else _p(bitmap), c_longlong(seq),
                         c_longlong(100), _p(loc), _p(act), _p(nnz))
     n = int(nnz[0])
@@ -389,8 +392,9 @@ def test_decode_kernels(emu, w16, scalar, d):
     sq = np.zeros(1, np.float64)
     err = np.zeros(1, np.int32)
     idn, vn = np.ascontiguousarray(idx.numpy()), np.ascontiguousarray(vals.numpy())
+    bn, xraw = np.ascontiguousarray(b.numpy()), _bf16_raw(x)
     emu.emu_decode(_p(idn), _p(vn), c_longlong(T), c_int(k), _p(Wn), c_int(w16), c_longlong(d), c_longlong(N),
-                   _p(np.ascontiguousarray(b.numpy())), _p(out), _p(_bf16_raw(x)), _p(sq), _p(err), c_int(scalar))
+                   _p(bn), _p(out), _p(xraw), _p(sq), _p(err), c_int(scalar))
     np.testing.assert_allclose(out, ref.numpy(), rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(sq[0], float(((ref - x.float()) ** 2).sum()), rtol=1e-5)
     assert err[0] == 0
@@ -413,9 +417,50 @@ def test_dense_topk_kernel(emu):
         want_i[t], want_v[t] = order, dense[t, order].numpy()
     out_v = np.full((T, k), np.nan, np.float32)
     out_i = np.full((T, k), -1, np.int64)
-    emu.emu_dense_topk(_p(np.ascontiguousarray(dense.numpy())), c_longlong(T), c_longlong(N), c_longlong(N), c_int(k),
+    dn = np.ascontiguousarray(dense.numpy())
+    emu.emu_dense_topk(_p(dn), c_longlong(T), c_longlong(N), c_longlong(N), c_int(k),
                        _p(out_v), _p(out_i), c_int(256))
     assert np.array_equal(out_v, want_v) and np.array_equal(out_i, want_i)
+
+
+def test_refine_fallback_kernels(emu):
+    """exact_rows_kernel + dense_topk_kernel (first 64 flagged rows, redirected through the row map) and
+    overflow_rows_kernel (the rest): flagged tokens come out as the exact fp32 TopK, the others are left untouched"""
+    d, N, k, T = 32, 96, 8, 80
+    p = O.init_params(d, N, k, seed=17)
+    x = torch.randn(T, d, generator=torch.Generator().manual_seed(18)).to(torch.bfloat16)
+    folded = (p.b_enc.double() - p.W_enc.double() @ p.b_dec.double()).float().numpy()
+    flagged = np.array([t for t in range(T) if t % 7 != 3], np.int32)          # 69 rows: 64 wide + 5 overflow
+    status = np.array([len(flagged)] + [0] * 63, np.int32)
+    flag_rows = np.zeros(T, np.int32)
+    flag_rows[:len(flagged)] = flagged
+    out_v = np.full((T, k), -5.0, np.float32)
+    out_i = np.full((T, k), -5, np.int64)
+    dense = np.zeros((64, N), np.float32)
+    xraw, Wn = _bf16_raw(x), np.ascontiguousarray(p.W_enc.numpy())
+    emu.emu_refine_fallback(_p(xraw), c_longlong(d), _p(Wn), c_longlong(d),
+                            c_longlong(N), _p(folded), _p(status), _p(flag_rows), c_longlong(-1), c_float(0.0),
+                            _p(dense), c_int(k), _p(out_v), _p(out_i), c_int(2), c_int(128))
+    ref = O.encode(p, x.float())
+    ri, rv = O.canonical_topk(ref.top_acts, ref.top_indices)
+    gi, gv = O.canonical_topk(torch.from_numpy(out_v[flagged]), torch.from_numpy(out_i[flagged]))
+    assert np.array_equal(gi, ri[flagged])
+    np.testing.assert_allclose(gv, rv[flagged], rtol=2e-6, atol=1e-7)
+    assert (out_v[flagged][:, :-1] >= out_v[flagged][:, 1:]).all()
+    untouched = np.setdiff1d(np.arange(T), flagged)
+    assert (out_v[untouched] == -5.0).all() and (out_i[untouched] == -5).all()
+
+
+def test_total_variance_kernels(emu):
+    """colstats_kernel + totvar_kernel: sum((x - x.mean(0))**2), the FVU denominator of sae/sae.py:204"""
+    T, d = 150, 70
+    x = (torch.randn(T, d, generator=torch.Generator().manual_seed(19)) * 3 + 1).to(torch.bfloat16)
+    scratch = np.zeros(2 * d, np.float64)
+    out = np.zeros(1, np.float64)
+    xraw = _bf16_raw(x)
+    emu.emu_total_variance_bf16(_p(xraw), c_longlong(T), c_longlong(d), c_longlong(d), _p(scratch), _p(out))
+    xd = x.double()
+    np.testing.assert_allclose(out[0], float(((xd - xd.mean(0)) ** 2).sum()), rtol=1e-10)
 
 
 # ---------------------------------------------------------------------------------------------
