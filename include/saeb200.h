@@ -209,6 +209,22 @@ int saeb_scan_pool(const float* vals, const int64_t* idx, int64_t T, int k, int 
                    void* stream);
 int saeb_scan_merge(void* bucket, int* bucket_cnt, int bucket_cap, int64_t F, int n_top, float base_threshold,
                     float* top_vals, int64_t* top_win, float* feat_thr, void* stream);
+/* Image form of the scan (replaces, for all features at once, pool_max_activations_windows_image,
+ * features/constructors.py:88-148): the score of (feature, image) is the MEAN of the feature's TopK-masked activations
+ * over the first n_base positions of the image's token row (avg_pool1d over the 576 base image tokens, :109-114).
+ * saeb_image_pool processes the TopK output of n_images rows of tokens_per_image tokens each (at most bucket_cap images
+ * per call) and appends (score, image_base + i) to the same per-feature buckets as saeb_scan_pool; saeb_scan_merge
+ * then keeps the n_top best images per feature, ordered (score desc, image id asc) -- ask for max_examples + 50 and
+ * drop repeated dataset ids on the host like the reference does (:117-135).  Sums are accumulated in 32.32 fixed
+ * point (order independent); scores agree with the reference's fp32 mean to ~1e-7 relative.  The scratch
+ * (saeb_image_pool_workspace_bytes) must be initialised ONCE with saeb_image_pool_init and is left initialised by
+ * every call. */
+size_t saeb_image_pool_workspace_bytes(int k, int n_base, int64_t F);
+int saeb_image_pool_init(void* workspace, size_t workspace_bytes, int k, int n_base, int64_t F, void* stream);
+int saeb_image_pool(const float* vals, const int64_t* idx, int64_t n_images, int64_t tokens_per_image, int k,
+                    int n_base, float threshold, int64_t feat_lo, int64_t feat_hi, int64_t image_base,
+                    const float* tok_thr, const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap,
+                    int* overflow_flag, void* workspace, size_t workspace_bytes, void* stream);
 /* Per-token kth-largest of R gathered per-shard value lists, gathered [R][T][m] f32 (after the all-gather of each
  * shard's m best values per token): tok_thr[t] = the kth-largest of the R*m values of token t, values
  * <= 0 count as 0; 1 <= kth <= R*m.  The feature-sharded scan uses it twice per token chunk: on the gathered lower

@@ -79,6 +79,12 @@ int coo_extract_launch(const float* vals, const long long* idx, long long T, int
 int kth_gathered_launch(const float* gathered, int R, long long T, int m, int kth, float* tok_thr,
                         cudaStream_t stream);
 int set_kth_impl(int v);
+size_t image_pool_workspace_bytes(int k, int n_base, long long F);
+int image_pool_init(void* ws, size_t ws_bytes, int k, int n_base, long long F, cudaStream_t stream);
+int image_pool_launch(const float* vals, const long long* idx, long long n_images, long long tokens_per_image, int k,
+                      int n_base, float threshold, long long feat_lo, long long feat_hi, long long image_base,
+                      const float* tok_thr, const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap,
+                      int* overflow, void* ws, size_t ws_bytes, cudaStream_t stream);
 int set_refine_threads(int v);
 int decode_bwd_acts_launch(const float* grad_out, long long ld_g, const long long* idx, long long T, int k,
                            const float* W_dec, long long d, long long N, float* d_vals, int* err_flag,
@@ -571,6 +577,26 @@ int saeb_scan_merge(void* bucket, int* bucket_cnt, int bucket_cap, int64_t F, in
   SAEB_REQUIRE(bucket && bucket_cnt && top_vals && top_win && feat_thr, "scan_merge: null pointer");
   int rc = scan_merge_launch(bucket, bucket_cnt, bucket_cap, F, n_top, base_threshold, top_vals,
                              reinterpret_cast<long long*>(top_win), feat_thr, (cudaStream_t)stream);
+  if (rc == 0) g_launches += 1;
+  return rc;
+}
+
+size_t saeb_image_pool_workspace_bytes(int k, int n_base, int64_t F) { return image_pool_workspace_bytes(k, n_base, F); }
+
+int saeb_image_pool_init(void* workspace, size_t workspace_bytes, int k, int n_base, int64_t F, void* stream) {
+  g_err[0] = 0;
+  return image_pool_init(workspace, workspace_bytes, k, n_base, F, (cudaStream_t)stream);
+}
+
+int saeb_image_pool(const float* vals, const int64_t* idx, int64_t n_images, int64_t tokens_per_image, int k,
+                    int n_base, float threshold, int64_t feat_lo, int64_t feat_hi, int64_t image_base,
+                    const float* tok_thr, const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap,
+                    int* overflow_flag, void* workspace, size_t workspace_bytes, void* stream) {
+  g_err[0] = 0;
+  SAEB_REQUIRE(vals && idx && feat_thr && bucket && bucket_cnt && workspace, "image_pool: null pointer");
+  int rc = image_pool_launch(vals, reinterpret_cast<const long long*>(idx), n_images, tokens_per_image, k, n_base,
+                             threshold, feat_lo, feat_hi, image_base, tok_thr, feat_thr, bucket, bucket_cnt, bucket_cap,
+                             overflow_flag, workspace, workspace_bytes, (cudaStream_t)stream);
   if (rc == 0) g_launches += 1;
   return rc;
 }

@@ -123,4 +123,62 @@ int scan_merge_launch(void* bucket, int* bucket_cnt, int bucket_cap, long long F
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// image scan
+// ---------------------------------------------------------------------------------------------
+struct ImagePoolPlan {
+  int grid, slots;
+  size_t keys_off, sums_off, list_off, total;
+};
+static ImagePoolPlan image_pool_plan(int k, int n_base, long long F) {
+  ImagePoolPlan p;
+  long long distinct = (long long)n_base * k;   // an image cannot touch more features than it has TopK entries ...
+  if (distinct > F) distinct = F;               // ... nor more than the shard owns
+  p.slots = 64;
+  while (p.slots < 2 * distinct) p.slots <<= 1;
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  p.grid = sms > 0 ? sms : 148;
+  const size_t n = (size_t)p.grid * p.slots;
+  p.sums_off = 0;
+  p.keys_off = n * sizeof(unsigned long long);
+  p.list_off = p.keys_off + n * sizeof(uint32_t);
+  p.total = p.list_off + n * sizeof(int);
+  return p;
+}
+size_t image_pool_workspace_bytes(int k, int n_base, long long F) { return image_pool_plan(k, n_base, F).total; }
+
+int image_pool_init(void* ws, size_t ws_bytes, int k, int n_base, long long F, cudaStream_t stream) {
+  const ImagePoolPlan p = image_pool_plan(k, n_base, F);
+  SAEB_REQUIRE(ws != nullptr && ws_bytes >= p.total, "image_pool: workspace too small");
+  uint8_t* b = reinterpret_cast<uint8_t*>(ws);
+  SAEB_CHECK_CUDA(cudaMemsetAsync(b + p.sums_off, 0, p.keys_off - p.sums_off, stream));
+  SAEB_CHECK_CUDA(cudaMemsetAsync(b + p.keys_off, 0xff, p.list_off - p.keys_off, stream));   // HASH_EMPTY
+  return 0;
+}
+
+int image_pool_launch(const float* vals, const long long* idx, long long n_images, long long tokens_per_image, int k,
+                      int n_base, float threshold, long long feat_lo, long long feat_hi, long long image_base,
+                      const float* tok_thr, const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap,
+                      int* overflow, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  SAEB_REQUIRE(n_images > 0 && k >= 1 && n_base >= 1 && tokens_per_image >= n_base,
+               "image_pool: need n_images > 0, k >= 1 and 1 <= n_base <= tokens_per_image");
+  SAEB_REQUIRE(n_images <= bucket_cap, "image_pool: %lld images per call exceed the bucket capacity %d", n_images,
+               bucket_cap);
+  SAEB_REQUIRE(image_base >= 0 && image_base + n_images < (1ll << 32), "image_pool: image ids must fit 32 bits");
+  const ImagePoolPlan p = image_pool_plan(k, n_base, feat_hi - feat_lo);
+  SAEB_REQUIRE(ws != nullptr && ws_bytes >= p.total, "image_pool: workspace too small");
+  uint8_t* b = reinterpret_cast<uint8_t*>(ws);
+  const int grid = n_images < p.grid ? (int)n_images : p.grid;
+  image_pool_kernel<<<grid, 256, 0, stream>>>(vals, idx, n_images, tokens_per_image, k, n_base, threshold, feat_lo,
+                                              feat_hi, image_base, tok_thr, feat_thr,
+                                              reinterpret_cast<uint32_t*>(b + p.keys_off),
+                                              reinterpret_cast<unsigned long long*>(b + p.sums_off),
+                                              reinterpret_cast<int*>(b + p.list_off), p.slots,
+                                              reinterpret_cast<uint2*>(bucket), bucket_cnt, bucket_cap, overflow);
+  SAEB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace saeb

@@ -240,4 +240,68 @@ __global__ void scan_merge_kernel(uint2* __restrict__ bucket, int* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// image scan: per-feature MEAN of the TopK-masked activations over the first `n_base` positions of every image row
+// (reference pool_max_activations_windows_image, features/constructors.py:109-114: avg_pool1d over the 576 base image
+// tokens), feeding the same per-feature buckets / top lists as the window scan (image id in place of the window id).
+//
+// One persistent CTA walks images blockIdx.x, blockIdx.x + gridDim.x, ...  Its hash table (feature -> sum) lives in
+// global scratch: an image can touch up to n_base * k distinct features, far more than shared memory holds.  Sums are
+// kept in 32.32 fixed point, so they do not depend on the order in which the threads add (deterministic lists); the
+// slots an image occupied are remembered in a list and restored to "empty" when its scores have been emitted, so the
+// scratch only has to be initialised once (keys = HASH_EMPTY, sums = 0).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+image_pool_kernel(const float* __restrict__ vals, const long long* __restrict__ idx, long long n_images,
+                  long long tokens_per_image, int k, int n_base, float threshold, long long feat_lo, long long feat_hi,
+                  long long image_base, const float* __restrict__ tok_thr, const float* __restrict__ feat_thr,
+                  uint32_t* __restrict__ hkeys, unsigned long long* __restrict__ hsums, int* __restrict__ hlist,
+                  int slots, uint2* __restrict__ bucket, int* __restrict__ bucket_cnt, int bucket_cap,
+                  int* __restrict__ overflow) {
+  __shared__ int s_n;
+  uint32_t* keys = hkeys + (size_t)blockIdx.x * slots;
+  unsigned long long* sums = hsums + (size_t)blockIdx.x * slots;
+  int* list = hlist + (size_t)blockIdx.x * slots;
+  const uint32_t mask = (uint32_t)slots - 1u;
+  const long long n_ent = (long long)n_base * k;
+  for (long long img = blockIdx.x; img < n_images; img += gridDim.x) {
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (long long e = threadIdx.x; e < n_ent; e += blockDim.x) {
+      const long long t = img * tokens_per_image + e / k;
+      const float v = vals[t * k + (e % k)];
+      const long long f = idx[t * k + (e % k)];
+      if (!(v > threshold) || f < feat_lo || f >= feat_hi) continue;
+      if (tok_thr != nullptr && v < tok_thr[t]) continue;   // not in the token's global top-k
+      const uint32_t key = (uint32_t)(f - feat_lo);
+      const unsigned long long q = (unsigned long long)((double)v * 4294967296.0 + 0.5);
+      uint32_t s = (key * 2654435761u) & mask;
+      while (true) {
+        const uint32_t old = atomicCAS(&keys[s], HASH_EMPTY, key);
+        if (old == HASH_EMPTY) list[atomicAdd(&s_n, 1)] = (int)s;
+        if (old == HASH_EMPTY || old == key) {
+          atomicAdd(&sums[s], q);
+          break;
+        }
+        s = (s + 1) & mask;
+      }
+    }
+    __syncthreads();
+    const int n = s_n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int s = list[i];
+      const uint32_t key = keys[s];
+      const unsigned long long sum = sums[s];
+      keys[s] = HASH_EMPTY;
+      sums[s] = 0ull;
+      const float score = (float)((double)sum * (1.0 / 4294967296.0) / (double)n_base);
+      if (!(score > feat_thr[key])) continue;
+      const int pos = atomicAdd(&bucket_cnt[key], 1);
+      if (pos < bucket_cap) bucket[(size_t)key * bucket_cap + pos] = make_uint2(__float_as_uint(score), (uint32_t)(image_base + img));
+      else if (overflow) atomicExch(overflow, 1);
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace saeb

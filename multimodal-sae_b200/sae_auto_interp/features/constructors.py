@@ -138,3 +138,18 @@ def top_windows_all_features(top_acts: torch.Tensor, top_indices: torch.Tensor, 
     scan = TopActivationScan(feat_lo, feat_hi, n_top, ctx_len, top_acts.device)
     scan.update(top_acts, top_indices, window_base)
     return scan.finalize()
+
+
+def top_images_all_features(top_acts: torch.Tensor, top_indices: torch.Tensor, num_latents: int, tokens_per_image: int,
+                            n_top: int, *, n_base: int = 576, feat_lo: int = 0, feat_hi: int = None,
+                            image_base: int = 0):
+    """Device route of the image constructor: TopK stream of whole image rows [n_images * tokens_per_image, k] ->
+    (scores [F, n_top], image ids [F, n_top]) for features [feat_lo, feat_hi): the images with the largest mean
+    activation over their first `n_base` positions, ordered (score desc, image id asc); -1 marks empty slots.  Ask for
+    `max_examples + 50` and drop repeated dataset ids with `_dedup_ranked` to reproduce the reference's selection."""
+    from saeb200.engine import TopImageScan
+
+    feat_hi = num_latents if feat_hi is None else feat_hi
+    scan = TopImageScan(feat_lo, feat_hi, n_top, tokens_per_image, n_base, top_acts.device)
+    scan.update(top_acts, top_indices, image_base)
+    return scan.finalize()

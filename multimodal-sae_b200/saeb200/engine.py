@@ -399,6 +399,59 @@ class TopActivationScan:
         return self.top_vals, self.top_win
 
 
+class TopImageScan(TopActivationScan):
+    """Image form of the scan: per feature the `n_top` images with the largest MEAN TopK-masked activation over the first
+    `n_base` positions of their token row (reference pool_max_activations_windows_image, features/constructors.py:
+    88-148, for every feature of the shard at once).  `finalize()` -> (scores [F, n_top], image ids [F, n_top], -1 =
+    empty), ordered (score desc, image id asc)."""
+
+    def __init__(self, feat_lo: int, feat_hi: int, n_top: int, tokens_per_image: int, n_base: int, device, *,
+                 bucket_cap: int = 256, threshold: float = ACT_THRESHOLD):
+        super().__init__(feat_lo, feat_hi, n_top, tokens_per_image, device, bucket_cap=bucket_cap, threshold=threshold)
+        if not 1 <= n_base <= tokens_per_image:
+            raise SaebError("TopImageScan: need 1 <= n_base <= tokens_per_image")
+        self.tokens_per_image, self.n_base = int(tokens_per_image), int(n_base)
+        self._ws, self._ws_k = None, None
+
+    def _workspace(self, k: int) -> torch.Tensor:
+        if self._ws is None or self._ws_k != k:
+            L = _capi.lib()
+            with torch.cuda.device(self.device):
+                nbytes = L.saeb_image_pool_workspace_bytes(k, self.n_base, self.F)
+                self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                check(L.saeb_image_pool_init(self._ws.data_ptr(), nbytes, k, self.n_base, self.F, _stream()),
+                      "saeb_image_pool_init")
+            self._ws_k = k
+        return self._ws
+
+    def update(self, top_acts: torch.Tensor, top_indices: torch.Tensor, image_base: int,
+               tok_thr: Optional[torch.Tensor] = None) -> None:
+        """Feed the TopK output of whole image rows ([n_images * tokens_per_image, k]); the first row is image
+        `image_base`."""
+        L = _capi.lib()
+        k = top_acts.shape[-1]
+        vals = top_acts.reshape(-1, k)
+        idx = top_indices.reshape(-1, k)
+        tpi = self.tokens_per_image
+        if vals.shape[0] % tpi != 0:
+            raise SaebError("TopImageScan.update needs whole image rows")
+        n_img = vals.shape[0] // tpi
+        ws = self._workspace(k)
+        with torch.cuda.device(self.device):
+            for i0 in range(0, n_img, self.bucket_cap):
+                i1 = min(n_img, i0 + self.bucket_cap)
+                if self._pending + (i1 - i0) > self.bucket_cap:
+                    self.flush()
+                v, i = vals[i0 * tpi:i1 * tpi], idx[i0 * tpi:i1 * tpi]
+                check(L.saeb_image_pool(v.data_ptr(), i.data_ptr(), i1 - i0, tpi, k, self.n_base, self.threshold,
+                                        self.feat_lo, self.feat_hi, image_base + i0,
+                                        None if tok_thr is None else tok_thr[i0 * tpi:i1 * tpi].data_ptr(),
+                                        self.feat_thr.data_ptr(), self.bucket.data_ptr(), self.bucket_cnt.data_ptr(),
+                                        self.bucket_cap, self.overflow.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        _stream()), "saeb_image_pool")
+                self._pending += i1 - i0
+
+
 def kth_of_gathered(gathered: torch.Tensor, kth: Optional[int] = None) -> torch.Tensor:
     """gathered [R, T, m] f32 (all-gathered per-shard value lists, m values per shard and token) -> per-token
     kth-largest of the R*m values [T] (values <= 0 count as 0).  kth defaults to m: the per-token global k-th value from

@@ -180,6 +180,18 @@ void emu_scan_pool(const float* vals, const long long* idx, long long T, int k, 
   });
 }
 
+// image scan: `grid` persistent CTAs over the images, scratch laid out by the caller (keys = 0xffffffff, sums = 0)
+void emu_image_pool(const float* vals, const long long* idx, long long n_images, long long tokens_per_image, int k,
+                    int n_base, float threshold, long long feat_lo, long long feat_hi, long long image_base,
+                    const float* tok_thr, const float* feat_thr, uint32_t* hkeys, unsigned long long* hsums, int* hlist,
+                    int slots, void* bucket, int* bucket_cnt, int bucket_cap, int* overflow, int grid) {
+  emu::launch({(unsigned)grid}, {256}, [&] {
+    image_pool_kernel(vals, idx, n_images, tokens_per_image, k, n_base, threshold, feat_lo, feat_hi, image_base,
+                      tok_thr, feat_thr, hkeys, hsums, hlist, slots, reinterpret_cast<uint2*>(bucket), bucket_cnt,
+                      bucket_cap, overflow);
+  });
+}
+
 void emu_scan_merge(void* bucket, int* bucket_cnt, int bucket_cap, long long F, int n_top, float base_thr,
                     float* top_vals, long long* top_win, float* feat_thr) {
   int sort_n = 2;

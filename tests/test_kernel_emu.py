@@ -373,6 +373,56 @@ def test_scan_pool_and_merge_kernels(emu):
     assert np.array_equal(top_vals, ref_s[lo:hi]) and np.array_equal(top_win, ref_w[lo:hi])
 
 
+def test_image_pool_kernel_and_merge(emu):
+    """image_pool_kernel + scan_merge_kernel: per-feature best images by the mean activation over the first n_base
+    positions of every image row (features/constructors.py:109-122), for a feature shard, over several calls and
+    flushes with fewer persistent CTAs than images; the scratch hash must come back clean after every call"""
+    from sae_auto_interp.features.constructors import image_scores
+
+    N, k, tpi, n_base, n_img, n_top, cap, grid, slots = 150, 6, 14, 9, 23, 4, 8, 3, 256
+    T = n_img * tpi
+    gen = torch.Generator().manual_seed(31)
+    vals = torch.rand(T, k, generator=gen)
+    vals[vals < 0.2] = 0.0
+    idx = torch.stack([torch.randperm(N, generator=gen)[:k] for _ in range(T)])
+    lo, hi = 20, 130
+    F = hi - lo
+    # the reference's per-feature route: COO entries of a feature -> mean over the base positions -> ranking
+    pos = torch.arange(T) % tpi
+    img = torch.arange(T) // tpi
+    want_s = np.zeros((F, n_top), np.float32)
+    want_i = np.full((F, n_top), -1, np.int64)
+    for f in range(lo, hi):
+        hit = (idx == f) & (vals > 1e-5)
+        tok, col = hit.nonzero(as_tuple=True)
+        sc = image_scores(torch.stack([img[tok], pos[tok]], 1), vals[tok, col], n_img, n_base).numpy()
+        order = sorted((i for i in range(n_img) if sc[i] > 1e-5), key=lambda i: (-sc[i], i))[:n_top]
+        want_s[f - lo, :len(order)] = sc[order]
+        want_i[f - lo, :len(order)] = order
+    top_vals = np.zeros((F, n_top), np.float32)
+    top_img = np.full((F, n_top), -1, np.int64)
+    feat_thr = np.full(F, 1e-5, np.float32)
+    bucket = np.zeros((F, cap, 2), np.uint32)
+    bucket_cnt = np.zeros(F, np.int32)
+    overflow = np.zeros(1, np.int32)
+    hkeys = np.full((grid, slots), 0xFFFFFFFF, np.uint32)
+    hsums = np.zeros((grid, slots), np.uint64)
+    hlist = np.zeros((grid, slots), np.int32)
+    vn, inn = np.ascontiguousarray(vals.numpy()), np.ascontiguousarray(idx.numpy())
+    for i0 in range(0, n_img, cap):
+        i1 = min(n_img, i0 + cap)
+        emu.emu_image_pool(_p(vn[i0 * tpi:]), _p(inn[i0 * tpi:]), c_longlong(i1 - i0), c_longlong(tpi), c_int(k),
+                           c_int(n_base), c_float(1e-5), c_longlong(lo), c_longlong(hi), c_longlong(i0), None,
+                           _p(feat_thr), _p(hkeys), _p(hsums), _p(hlist), c_int(slots), _p(bucket), _p(bucket_cnt),
+                           c_int(cap), _p(overflow), c_int(grid))
+        assert (hkeys == 0xFFFFFFFF).all() and (hsums == 0).all()
+        emu.emu_scan_merge(_p(bucket), _p(bucket_cnt), c_int(cap), c_longlong(F), c_int(n_top), c_float(1e-5),
+                           _p(top_vals), _p(top_img), _p(feat_thr))
+    assert overflow[0] == 0
+    assert np.array_equal(top_img, want_i)
+    np.testing.assert_allclose(top_vals, want_s, rtol=1e-6, atol=1e-9)
+
+
 @pytest.mark.parametrize("w16,scalar,d", [(0, 0, 64), (1, 0, 64), (0, 1, 50)])
 def test_decode_kernels(emu, w16, scalar, d):
     """decode_kernel (fp32 and fp16 weight rows) and decode_scalar_kernel: gather decode + bias + residual sum of

@@ -198,3 +198,33 @@ def test_decode_with_16bit_weight_copy(wdt, tol):
     rel = ((out - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
     assert rel < tol
     torch.testing.assert_close(ref.cpu(), O.eager_decode(idx, vals, W.mT) + b, rtol=1e-4, atol=1e-4)
+
+
+def test_image_scan_matches_the_per_feature_route():
+    """TopImageScan (image_pool_kernel + scan_merge_kernel) vs the host route of the image constructor: per feature,
+    mean over the base image tokens -> ranking (features/constructors.py:109-122); chunked updates, a feature shard"""
+    from saeb200.engine import TopImageScan
+    from sae_auto_interp.features.constructors import image_scores
+
+    N, d, k, tpi, n_base, n_img, n_top = 1024, 64, 8, 40, 24, 70, 6
+    p = O.init_params(d, N, k, seed=61)
+    x = torch.randn(n_img * tpi, d, generator=torch.Generator().manual_seed(62)).to(torch.bfloat16)
+    from test_gpu_parity import _sae_from_params
+
+    enc = _sae_from_params(p).encode(x.to(DEV))
+    acts, idx = enc.top_acts, enc.top_indices
+    lo, hi = 128, 640
+    scan = TopImageScan(lo, hi, n_top, tpi, n_base, DEV, bucket_cap=32)
+    for i0 in range(0, n_img, 25):
+        i1 = min(n_img, i0 + 25)
+        scan.update(acts[i0 * tpi:i1 * tpi], idx[i0 * tpi:i1 * tpi], i0)
+    s, w = (t.cpu() for t in scan.finalize())
+    assert int(scan.overflow.item()) == 0
+    a_c, i_c = acts.cpu(), idx.cpu()
+    pos, img = torch.arange(n_img * tpi) % tpi, torch.arange(n_img * tpi) // tpi
+    for f in range(lo, hi, 7):
+        tok, col = ((i_c == f) & (a_c > 1e-5)).nonzero(as_tuple=True)
+        sc = image_scores(torch.stack([img[tok], pos[tok]], 1), a_c[tok, col], n_img, n_base)
+        order = sorted((i for i in range(n_img) if sc[i] > 1e-5), key=lambda i: (-float(sc[i]), i))[:n_top]
+        assert w[f - lo, :len(order)].tolist() == order and bool((w[f - lo, len(order):] == -1).all())
+        torch.testing.assert_close(s[f - lo, :len(order)], sc[order], rtol=1e-6, atol=1e-9)
