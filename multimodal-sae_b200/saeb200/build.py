@@ -18,8 +18,8 @@ LIB_DIR = os.path.join(PKG_DIR, "lib")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(LIB_DIR, "libsaeb200.so")
 SOURCES = ["capi.cu", "encode_topk.cu", "decode.cu", "pack.cu", "coo_scan.cu", "refine.cu", "exchange.cu", "decode_bwd.cu"]
-HEADERS = ["common.cuh", "kernels_refine.cuh", "kernels_kth.cuh", "kernels_decode_bwd.cuh", "kernels_pack.cuh", "kernels_exchange.cuh", "kernels_coo_scan.cuh", "kernels_topk_select.cuh", "kernels_decode.cuh",
-           os.path.join("..", "..", "include", "saeb200.h")]
+# every header a translation unit may include: common helpers, the device code (kernels_*.cuh) and the C ABI
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "saeb200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
