@@ -40,3 +40,22 @@ except Exception:  # pragma: no cover
             return [int(tok) if tok.isdigit() else tok for tok in re.split(r"(\d+)", text)]
 
         return sorted(seq, key=nat_key)
+
+
+def table_dataclass(name: str, doc: str, module: str, *rows, positional=(), post_init=None):
+    """A `Serializable` dataclass from a table of (field name, type, default) rows -- `dataclasses.MISSING` marks a
+    required field, a list default becomes a `list_field`, `positional` names take no flag on the command line."""
+    fields = []
+    for fname, ftype, default in rows:
+        if default is dataclasses.MISSING:
+            fields.append((fname, ftype))
+        elif fname in positional:
+            fields.append((fname, ftype, field(default=default, positional=True)))
+        elif isinstance(default, list):
+            fields.append((fname, ftype, list_field(*default)))
+        else:
+            fields.append((fname, ftype, field(default=default)))
+    namespace = {} if post_init is None else {"__post_init__": post_init}
+    cls = dataclasses.make_dataclass(name, fields, bases=(Serializable,), namespace=namespace)
+    cls.__doc__, cls.__module__ = doc, module
+    return cls

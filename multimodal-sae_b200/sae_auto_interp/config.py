@@ -5,28 +5,16 @@ The classes are built from one table per class (name, type, default); `positiona
 command lines take without a flag."""
 from __future__ import annotations
 
-from dataclasses import MISSING, make_dataclass
+from dataclasses import MISSING
 from typing import Literal, Union
 
-from ._compat import Serializable, field, list_field
+from ._compat import table_dataclass
 
 _PYTHIA, _REDPAJAMA = "EleutherAI/pythia-160m", "togethercomputer/RedPajama-Data-1T-Sample"
 
 
 def _config(name: str, doc: str, *rows, positional=()):
-    fields = []
-    for fname, ftype, default in rows:
-        if default is MISSING:
-            fields.append((fname, ftype))
-        elif fname in positional:
-            fields.append((fname, ftype, field(default=default, positional=True)))
-        elif isinstance(default, list):
-            fields.append((fname, ftype, list_field(*default)))
-        else:
-            fields.append((fname, ftype, field(default=default)))
-    cls = make_dataclass(name, fields, bases=(Serializable,))
-    cls.__doc__, cls.__module__ = doc, __name__
-    return cls
+    return table_dataclass(name, doc, __name__, *rows, positional=positional)
 
 
 ExperimentConfig = _config(
