@@ -273,6 +273,7 @@ def run_gpu(args):
                 "algorithmic_flops_per_launch": ENC_FLOPS_PER_TOKEN * wave_tokens,
                 "avg_launch_ms": k_avg * wave_tokens / TOKENS,
                 "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
+                "peak_burst": peaks["tflops_burst"], "frac_of_burst_peak": achieved / peaks["tflops_burst"],
                 "traffic": traffic, "peak_source": f"{peaks['source']} bf16 sustained (cuBLAS, MEASURED_PEAKS.json)",
                 "kernel_ms": k_avg, "mma_passes": 1 if enc.planes >= 3 else enc.planes,
                 "path_frac": (value / world) * FLOPS_PER_TOKEN / 1e12 / peaks["tflops_sustained"],
