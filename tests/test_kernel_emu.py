@@ -513,6 +513,54 @@ def test_total_variance_kernels(emu):
     np.testing.assert_allclose(out[0], float(((xd - xd.mean(0)) ** 2).sum()), rtol=1e-10)
 
 
+@pytest.mark.parametrize("lo", [False, True])
+def test_forward_chain_on_the_emulator(emu, lo):
+    """The SIMT half of the forward chained on the emulator, fed with what the tensor-core kernel produces (emulated
+    in numpy from the packed fp16 planes): per-split candidate lists -> topk_merge_kernel -> refine[_lo]_kernel ->
+    decode_kernel (+ residual sum of squares) -> colstats / totvar.  TopK sets, reconstruction and FVU vs the oracle's
+    forward (reference Sae.forward, sae/sae.py:193-247)."""
+    d, N, k, T, margin, S, CAP = 64, 512, 8, 6, 12, 2, 256
+    s = _pipeline_inputs(emu, d=d, N=N, k=k, T=T, margin=margin, seed=71)
+    K2 = s["K2"]
+    a = s["a"]
+    # candidate lists as the epilogue leaves them: per (row, split) a superset of the split's top-K2, in column order
+    cand = np.zeros((T, S, CAP, 2), np.uint32)
+    cnt = np.zeros((T, S), np.int32)
+    for t in range(T):
+        for sp in range(S):
+            cols = np.arange(sp * N // S, (sp + 1) * N // S)
+            v = a[t, cols]
+            thr = max(np.sort(v)[-K2], 0.0)
+            keep = cols[(v >= thr) & (v > 0)][:CAP]
+            cand[t, sp, :len(keep), 0] = a[t, keep].view(np.uint32)
+            cand[t, sp, :len(keep), 1] = keep
+            cnt[t, sp] = len(keep)
+    mvals = np.zeros((T, K2), np.float32)
+    midx = np.zeros((T, K2), np.int64)
+    emu.emu_topk_merge(_p(cand), _p(cnt), c_int(T), c_int(S), c_int(CAP), c_int(K2), c_int(N), _p(mvals), _p(midx))
+    assert np.array_equal(mvals, s["cand_vals"]) and np.array_equal(midx, s["cand_idx"])
+    sm = dict(s, cand_vals=mvals, cand_idx=midx)
+    vals, idx, flagged = _run_refine(emu, sm, k, lo=lo)
+    assert flagged == 0
+    p, x = s["p"], s["x"]
+    ref = O.forward(p, x.float())
+    ri, rv = O.canonical_topk(ref.latent_acts, ref.latent_indices)
+    gi, gv = O.canonical_topk(torch.from_numpy(vals), torch.from_numpy(idx))
+    assert np.array_equal(gi, ri)
+    np.testing.assert_allclose(gv, rv, rtol=3e-6, atol=1e-7)
+    out = np.zeros((T, d), np.float32)
+    sq = np.zeros(1, np.float64)
+    err = np.zeros(1, np.int32)
+    Wd, bd = np.ascontiguousarray(p.W_dec.numpy()), np.ascontiguousarray(p.b_dec.numpy())
+    emu.emu_decode(_p(idx), _p(vals), c_longlong(T), c_int(k), _p(Wd), c_int(0), c_longlong(d), c_longlong(N), _p(bd),
+                   _p(out), _p(s["xraw"]), _p(sq), _p(err), c_int(0))
+    np.testing.assert_allclose(out, ref.sae_out.numpy(), rtol=1e-5, atol=1e-6)
+    scratch = np.zeros(2 * d, np.float64)
+    tv = np.zeros(1, np.float64)
+    emu.emu_total_variance_bf16(_p(s["xraw"]), c_longlong(T), c_longlong(d), c_longlong(d), _p(scratch), _p(tv))
+    np.testing.assert_allclose(sq[0] / tv[0], float(ref.fvu), rtol=1e-5)
+
+
 # ---------------------------------------------------------------------------------------------
 def _push_rank(lib_path, names, total_bytes, rank, R, chunks, rows, widths, blocks, q):
     """one emulated rank of the peer-memory exchange: a process that maps all R symmetric buffers (at its own
