@@ -101,11 +101,12 @@ def test_decode_backward_kernels(emu, T, d, N, k):
 
 
 # ---------------------------------------------------------------------------------------------
-def _pipeline_inputs(emu, d, N, k, T, margin, seed):
+def _pipeline_inputs(emu, d, N, k, T, margin, seed, p=None, x=None):
     """pack (mode 4) + activation prep through the emulated kernels, and the candidate lists the fused GEMM epilogue +
     merge kernel would hand to the refinement (approximate values from the fp16 planes, top-K2 per row)."""
-    p = O.init_params(d, N, k, seed=seed)
-    x = torch.randn(T, d, generator=torch.Generator().manual_seed(seed + 1)).to(torch.bfloat16)
+    if p is None:
+        p = O.init_params(d, N, k, seed=seed)
+        x = torch.randn(T, d, generator=torch.Generator().manual_seed(seed + 1)).to(torch.bfloat16)
     d_pad = (d + 7) // 8 * 8
     W = np.ascontiguousarray(p.W_enc.numpy())
     hi = np.zeros((N, d_pad), np.float16)
@@ -559,6 +560,73 @@ def test_forward_chain_on_the_emulator(emu, lo):
     tv = np.zeros(1, np.float64)
     emu.emu_total_variance_bf16(_p(s["xraw"]), c_longlong(T), c_longlong(d), c_longlong(d), _p(scratch), _p(tv))
     np.testing.assert_allclose(sq[0] / tv[0], float(ref.fvu), rtol=1e-5)
+
+
+def test_feature_sharded_scan_chain_on_the_emulator(emu):
+    """The per-chunk data path of the feature-sharded scan with 2 logical shards, every SIMT kernel on the emulator:
+    candidate_bounds -> (gather of the first m1 bound columns) -> kth-largest -> refinement restricted by the global
+    lower bound -> (gather of the exact local values) -> kth-largest -> scan_pool with the per-token threshold ->
+    scan_merge.  The concatenated per-feature lists must equal the unsharded oracle scan: the cache keeps a latent
+    only if it is in the token's GLOBAL top-k (features/cache.py:210-218)."""
+    d, N, k, ctx, n_top, margin, R, m1 = 64, 512, 8, 8, 3, 12, 2, 6
+    T = ctx * 6
+    p = O.init_params(d, N, k, seed=81)
+    x = torch.randn(T, d, generator=torch.Generator().manual_seed(82)).to(torch.bfloat16)
+    shards = []
+    for r in range(R):
+        lo, hi = r * N // R, (r + 1) * N // R
+        sub = O.SaeParams(p.W_enc[lo:hi].contiguous(), p.b_enc[lo:hi].contiguous(), p.W_dec[lo:hi].contiguous(),
+                          p.b_dec, k)
+        sh = _pipeline_inputs(emu, d, hi - lo, k, T, margin, 0, p=sub, x=x)
+        sh["lo"], sh["hi"] = lo, hi
+        shards.append(sh)
+    # exchange 1: the shards' k best lower bounds, first m1 columns only
+    lbs = []
+    for sh in shards:
+        lb = np.zeros((T, k), np.float32)
+        emu.emu_candidate_bounds(_p(sh["cand_vals"]), _p(sh["cand_idx"]), c_longlong(T), c_int(sh["K2"]), c_int(k),
+                                 _p(sh["wnorm"]), _p(sh["dnorm"]), _p(sh["xnorm"]), _p(sh["xdnorm"]),
+                                 c_float(2.0 ** -14), c_longlong(-1), _p(lb))
+        lbs.append(lb[:, :m1])
+    g1 = np.ascontiguousarray(np.stack(lbs, 0))
+    ext_L = np.zeros(T, np.float32)
+    emu.emu_kth(c_int(4), _p(g1), c_int(R), c_longlong(T), c_int(m1), c_int(k), _p(ext_L))
+    ref = O.encode(p, x.float())
+    kth_true = ref.top_acts.min(1).values.numpy()
+    assert (ext_L <= kth_true).all() and (ext_L > 0.9 * kth_true).all()      # a valid, tight lower bound
+    # restricted refinement per shard, then exchange 2: the exact local values
+    outs = []
+    for sh in shards:
+        v, i, flagged = _run_refine(emu, sh, k, lo=False, ext_lower=ext_L, threads=128)
+        assert flagged == 0
+        outs.append((v, i + sh["lo"]))
+    n_eval = sum(int((v > 0).sum()) for v, _ in outs)
+    assert n_eval < 0.8 * R * k * T                                            # far fewer than k per shard and token
+    g2 = np.ascontiguousarray(np.stack([v for v, _ in outs], 0))
+    tok_thr = np.zeros(T, np.float32)
+    emu.emu_kth(c_int(4), _p(g2), c_int(R), c_longlong(T), c_int(k), c_int(k), _p(tok_thr))
+    np.testing.assert_allclose(tok_thr, kth_true, rtol=2e-6)
+    # per-feature lists of each shard, filtered by the token's global k-th value
+    parts = []
+    for sh, (v, i) in zip(shards, outs):
+        F = sh["hi"] - sh["lo"]
+        top_vals = np.zeros((F, n_top), np.float32)
+        top_win = np.full((F, n_top), -1, np.int64)
+        feat_thr = np.full(F, 1e-5, np.float32)
+        bucket = np.zeros((F, 8, 2), np.uint32)
+        bucket_cnt = np.zeros(F, np.int32)
+        overflow = np.zeros(1, np.int32)
+        vc, ic = np.ascontiguousarray(v), np.ascontiguousarray(i)
+        emu.emu_scan_pool(_p(vc), _p(ic), c_longlong(T), c_int(k), c_int(ctx), c_float(1e-5), c_longlong(sh["lo"]),
+                          c_longlong(sh["hi"]), c_longlong(0), _p(tok_thr), _p(feat_thr), _p(bucket), _p(bucket_cnt),
+                          c_int(8), _p(overflow))
+        emu.emu_scan_merge(_p(bucket), _p(bucket_cnt), c_int(8), c_longlong(F), c_int(n_top), c_float(1e-5),
+                           _p(top_vals), _p(top_win), _p(feat_thr))
+        assert overflow[0] == 0
+        parts.append((top_vals, top_win))
+    ref_s, ref_w = O.scan_top_windows(ref.top_acts, ref.top_indices, N, ctx, n_top)
+    np.testing.assert_allclose(np.concatenate([a for a, _ in parts]), ref_s, rtol=3e-6, atol=1e-7)
+    assert np.array_equal(np.concatenate([b for _, b in parts]), ref_w)
 
 
 # ---------------------------------------------------------------------------------------------
