@@ -92,6 +92,20 @@ void emu_prep_x_bf16(const void* x, long long T, long long d, long long ld_x, lo
                                      reinterpret_cast<__half*>(out), row_scale, xnorm, xdnorm);
   });
 }
+// the same for fp16 activations (the steering path's hidden stream) and fp32 activations (rounded to 11 bits)
+void emu_prep_x_f16(const void* x, long long T, long long d, long long ld_x, long long d_pad, void* out,
+                    float* row_scale, float* xnorm, float* xdnorm) {
+  emu::launch({(unsigned)((T + 7) / 8)}, {256}, [&] {
+    prep_x_f16_kernel<__half>(reinterpret_cast<const __half*>(x), T, d, ld_x, d_pad, reinterpret_cast<__half*>(out),
+                              row_scale, xnorm, xdnorm);
+  });
+}
+void emu_prep_x_f32(const float* x, long long T, long long d, long long ld_x, long long d_pad, void* out,
+                    float* row_scale, float* xnorm, float* xdnorm) {
+  emu::launch({(unsigned)((T + 7) / 8)}, {256}, [&] {
+    prep_x_f16_kernel<float>(x, T, d, ld_x, d_pad, reinterpret_cast<__half*>(out), row_scale, xnorm, xdnorm);
+  });
+}
 
 void emu_candidate_bounds(const float* cand_vals, const long long* cand_idx, long long T, int K2, int k,
                           const float* wnorm, const float* dnorm, const float* xnorm, const float* xdnorm, float c_eps,
@@ -264,6 +278,35 @@ void emu_push_gather(const void* src, size_t bytes, void* const* peer_bases, int
   emu::launch({(unsigned)blocks}, {(unsigned)PUSH_THREADS}, [&] {
     push_gather_kernel(reinterpret_cast<const uint4*>(src), n_vec, peer_bases, R, self, slab_off, nullptr, flags_offset,
                        channel, seq, counter);
+  });
+}
+
+// refinement on fp16 activations (exact or residual-plane) and on fp32 activations (exact only: refine_launch_t never
+// takes the residual route for them)
+void emu_refine_f16(const void* x, long long T, long long ld_x, const float* W, long long d, long long N,
+                    const float* bias, const float* wnorm, const float* dnorm, const float* trailer,
+                    const float* xnorm, const float* xdnorm, float c_eps, const float* cand_vals,
+                    const long long* cand_idx, int K2, int k, float* out_vals, long long* out_idx, int* status,
+                    int* flag_rows, const void* lo, long long ld_w) {
+  const __half* xh = reinterpret_cast<const __half*>(x);
+  emu::launch({(unsigned)T}, {256}, [&] {
+    if (lo == nullptr)
+      refine_kernel<__half>(xh, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx,
+                            K2, k, -1, 0.f, out_vals, out_idx, status, flag_rows, nullptr);
+    else
+      refine_lo_kernel<__half>(xh, ld_x, reinterpret_cast<const __half*>(lo), ld_w, d, N, bias, wnorm, dnorm, trailer,
+                               xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k, -1, 0.f, out_vals, out_idx, status,
+                               flag_rows, nullptr);
+  });
+}
+void emu_refine_f32(const float* x, long long T, long long ld_x, const float* W, long long d, long long N,
+                    const float* bias, const float* wnorm, const float* dnorm, const float* trailer,
+                    const float* xnorm, const float* xdnorm, float c_eps, const float* cand_vals,
+                    const long long* cand_idx, int K2, int k, float* out_vals, long long* out_idx, int* status,
+                    int* flag_rows) {
+  emu::launch({(unsigned)T}, {256}, [&] {
+    refine_kernel<float>(x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k,
+                         -1, 0.f, out_vals, out_idx, status, flag_rows, nullptr);
   });
 }
 

@@ -224,6 +224,60 @@ def test_refinement_kernels_end_to_end(emu, lo, d, N, k, margin):
         assert [int(i) for i in i4[r, 1:]] == [int(i) for _, i in rest]
 
 
+@pytest.mark.parametrize("xdt,lo", [("f16", False), ("f16", True), ("f32", False)])
+def test_refinement_with_fp16_and_fp32_activations(emu, xdt, lo):
+    """fp16 activations (the steering path's hidden stream) survive the row scaling exactly, so both refinement
+    variants apply; fp32 activations are rounded to 11 bits on their way into the tensor cores (a non-zero
+    ||x - fp16(x)|| enters the bound) and only the exact route is used.  TopK sets vs the oracle in both cases."""
+    d, N, k, T, margin = 64, 256, 6, 5, 12
+    p = O.init_params(d, N, k, seed=91)
+    xf = torch.randn(T, d, generator=torch.Generator().manual_seed(92))
+    x = xf.to(torch.float16) if xdt == "f16" else xf
+    d_pad = d
+    W = np.ascontiguousarray(p.W_enc.numpy())
+    hi, lo_pl = np.zeros((N, d_pad), np.float16), np.zeros((N, d_pad), np.float16)
+    bias, wnorm, dnorm = (np.zeros(N, np.float32) for _ in range(3))
+    trailer = np.zeros(64, np.float32)
+    b_enc, b_dec = np.ascontiguousarray(p.b_enc.numpy()), np.ascontiguousarray(p.b_dec.numpy())
+    emu.emu_pack(_p(W), _p(b_enc), _p(b_dec), c_longlong(N), c_longlong(d), c_longlong(d_pad), _p(hi), _p(lo_pl),
+                 _p(bias), _p(wnorm), _p(dnorm), _p(trailer))
+    xraw = np.ascontiguousarray(x.view(torch.int16).numpy() if xdt == "f16" else x.numpy())
+    x16 = np.zeros((T, d_pad), np.float16)
+    row_scale, xnorm, xdnorm = (np.zeros(T, np.float32) for _ in range(3))
+    prep = emu.emu_prep_x_f16 if xdt == "f16" else emu.emu_prep_x_f32
+    prep(_p(xraw), c_longlong(T), c_longlong(d), c_longlong(d), c_longlong(d_pad), _p(x16), _p(row_scale), _p(xnorm),
+         _p(xdnorm))
+    if xdt == "f16":
+        assert (xdnorm == 0).all() and np.array_equal(x16.astype(np.float32) * row_scale[:, None], x.float().numpy())
+    else:
+        assert (xdnorm > 0).all()
+        err = np.linalg.norm(x16.astype(np.float64) * row_scale[:, None] - x.double().numpy(), axis=1)
+        assert (xdnorm >= err * (1 - 1e-6)).all() and (xdnorm < 1.01 * err + 1e-12).all()
+    acc = x16.astype(np.float64) @ hi.astype(np.float64).T
+    a = (acc * row_scale[:, None].astype(np.float64) * float(trailer[0]) + bias[None, :]).astype(np.float32)
+    K2 = k + margin
+    order = np.lexsort((np.arange(N)[None, :].repeat(T, 0), -a), axis=1)[:, :K2]
+    cand_idx = np.ascontiguousarray(order.astype(np.int64))
+    cand_vals = np.ascontiguousarray(np.take_along_axis(a, order, 1).astype(np.float32))
+    out_vals = np.full((T, k), np.nan, np.float32)
+    out_idx = np.full((T, k), -7, np.int64)
+    status = np.zeros(64, np.int32)
+    flag_rows = np.full(64, -1, np.int32)
+    common = (c_longlong(T), c_longlong(d), _p(W), c_longlong(d), c_longlong(N), _p(bias), _p(wnorm), _p(dnorm),
+              _p(trailer), _p(xnorm), _p(xdnorm), c_float(2.0 ** -14), _p(cand_vals), _p(cand_idx), c_int(K2), c_int(k),
+              _p(out_vals), _p(out_idx), _p(status), _p(flag_rows))
+    if xdt == "f16":
+        emu.emu_refine_f16(_p(xraw), *common, _p(lo_pl) if lo else None, c_longlong(d_pad))
+    else:
+        emu.emu_refine_f32(_p(xraw), *common)
+    assert status[0] == 0
+    ref = O.encode(p, x.float())
+    ri, rv = O.canonical_topk(ref.top_acts, ref.top_indices)
+    gi, gv = O.canonical_topk(torch.from_numpy(out_vals), torch.from_numpy(out_idx))
+    assert np.array_equal(gi, ri)
+    np.testing.assert_allclose(gv, rv, rtol=3e-6, atol=1e-7)
+
+
 def test_candidate_bounds_kernel(emu):
     """per-token k best lower bounds a_j - eps_j (descending, floored at 0) of candidate_bounds_kernel"""
     k = 6
