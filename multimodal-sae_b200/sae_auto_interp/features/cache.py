@@ -174,7 +174,7 @@ class FeatureCache:
         for module_path in self.cache.feature_locations.keys():
             loc = self.cache.feature_locations[module_path]
             act = self.cache.feature_activations[module_path]
-            feat = loc[:, 2]
+            feat = loc[:, 2].contiguous()
             sid = torch.bucketize(feat, starts, right=True) - 1
             upper = ends[sid] + (1 if self.fix_split_bounds else 0)
             keep = feat < upper

@@ -546,3 +546,50 @@ def test_steering_hook_host_glue_matches_reference(monkeypatch):
     finally:
         for h in handles:
             h.remove()
+
+
+def test_save_splits_property_vs_oracle(tmp_path):
+    """save_splits for random widths / split counts / feature multisets (empty splits, uneven boundaries, one split)
+    against the oracle's restatement of the reference's boolean-mask passes (features/cache.py:243-309), in both
+    bound modes: the reference's (last feature id of every split dropped) and the fixed one."""
+    from hypothesis import given, settings, strategies as st
+    from safetensors.torch import load_file
+    from sae_auto_interp.features import FeatureCache
+    import sae_oracle as O
+
+    counter = [0]
+
+    @settings(max_examples=25, deadline=None)
+    @given(width=st.integers(4, 300), n_splits=st.integers(1, 7), nnz=st.integers(0, 200), seed=st.integers(0, 10 ** 6),
+           fix=st.booleans())
+    def check(width, n_splits, nnz, seed, fix):
+        n_splits = min(n_splits, width)
+        g = torch.Generator().manual_seed(seed)
+        feats = torch.randint(0, width, (nnz,), generator=g)
+        loc = torch.stack([torch.randint(0, 50, (nnz,), generator=g), torch.randint(0, 16, (nnz,), generator=g), feats], 1)
+        act = torch.rand(nnz, generator=g)
+
+        class _S:
+            class cfg:
+                num_latents = width
+                expansion_factor = 1
+            d_in = width
+            num_latents = width
+
+        fc = FeatureCache(_FakeModel(), None, {"layers.0": _S()}, batch_size=2, shard_size=0)
+        fc.fix_split_bounds = fix
+        fc.cache.feature_locations["layers.0"], fc.cache.feature_activations["layers.0"] = loc, act
+        out = tmp_path / f"case{counter[0]}"
+        counter[0] += 1
+        out.mkdir()
+        fc.save_splits(n_splits, str(out), rank=0)
+        total = 0
+        for start, end in O.generate_split_indices(width, n_splits):
+            data = load_file(str(out / "layers.0" / f"Rank0_{start}_{end}.safetensors"))
+            mask = O.split_mask(feats, start, end + 1 if fix else end)
+            assert torch.equal(data["locations"], loc[mask]) and torch.equal(data["activations"], act[mask])
+            total += int(mask.sum())
+        if fix:
+            assert total == nnz
+
+    check()
