@@ -38,7 +38,9 @@ _ws_cache = {}
 
 
 def _workspace(device: torch.device, nbytes: int, tag: str = "enc") -> torch.Tensor:
-    key = (device.index, tag)
+    """scratch cached per (device, purpose, stream): kernels of one stream reuse it in stream order, calls issued on
+    different streams never share it"""
+    key = (device.index, tag, torch.cuda.current_stream(device).cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = None
