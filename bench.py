@@ -499,7 +499,7 @@ def main():
     ap.add_argument("--alt-fp16-decode", action="store_true",
                     help="also measure the step with an fp16 copy of W_dec (reported as alt_fp16_decode)")
     ap.add_argument("--no-overlap", action="store_true", help="run the phases of a step back to back on one stream")
-    ap.add_argument("--chunk", type=int, default=18944, help="tokens per pipeline chunk (multiple of 9472 = one wave)")
+    ap.add_argument("--chunk", type=int, default=9472, help="tokens per pipeline chunk (multiple of 9472 = one wave of the GEMM grid)")
     ap.add_argument("--decode-dtype", default="fp32", choices=["fp32", "fp16"],
                     help="W_dec copy the decode gathers from: fp32 (parity default) or fp16 (half the bytes, ~2e-4 row error)")
     ap.add_argument("--planes", type=int, default=3, choices=[1, 2, 3, 4],

@@ -121,7 +121,12 @@ int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void*
                            int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N, int k, int margin,
                            int64_t clamp_feature, float clamp_value, const float* ext_lower, int already_merged,
                            float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
-                           size_t workspace_bytes, void* stream);
+                           size_t workspace_bytes, int max_ctas, void* stream);
+/* max_ctas (saeb_refine_candidates[_lo], saeb_decode): 0 = one CTA per token.  > 0 = a persistent grid of at most that
+ * many CTAs walks the tokens, and every helper launch of the call uses blocks small enough (<= 256 threads, <= 21 KB
+ * of shared memory) to be scheduled on an SM that already hosts a CTA of the fused GEMM: with max_ctas = (1..2) x
+ * number of SMs the HBM-bound gathers of chunk c run INSIDE the tensor-core-bound GEMM launches of chunk c+1 instead
+ * of queueing behind them (saeb200.overlap.OverlappedForward).  Results do not depend on max_ctas. */
 /* "fp16 hi + lo" refinement (packed mode 4 = saeb_pack_weights(..., planes = 4): the mode-3 blob followed by an fp16
  * plane of the residual W - fp16(W), scaled by 2^11; every mode-3 entry point accepts a mode-4 blob unchanged).
  * saeb_refine_candidates_lo is saeb_refine_candidates with the exact re-evaluation replaced by a correction: the
@@ -134,7 +139,7 @@ int saeb_refine_candidates_lo(const void* x, int x_dtype, int64_t ld_x, const vo
                               int64_t Tc, const void* packed4, const float* W_enc, int64_t d, int64_t N, int k,
                               int margin, int64_t clamp_feature, float clamp_value, const float* ext_lower,
                               int already_merged, float* out_vals, int64_t* out_idx, int32_t* status_out,
-                              void* workspace, size_t workspace_bytes, void* stream);
+                              void* workspace, size_t workspace_bytes, int max_ctas, void* stream);
 /* Feature-sharded use (every GPU holds N/R features, sees all tokens): after saeb_encode_candidates,
  * saeb_candidate_bounds merges this shard's candidates and writes, per token, its k largest LOWER bounds
  * a_j - eps_j (descending, lb_out [Tc,k]).  All-gather them, take the per-token k-th largest (saeb_kth_of_gathered):
@@ -158,10 +163,10 @@ int saeb_dense_topk(const float* dense, int64_t T, int64_t ld, int64_t N, int k,
  *   w_dtype SAEB_F32 (parity grade) or SAEB_BF16; b_dec may be NULL; out_dtype any of the three codes.
  *   If sq_err != NULL, x (same shape as out) is read and sum((out - x)^2) is ADDED to *sq_err (double) -- the
  *   numerator of the FVU (sae/sae.py:201,229).  err_flag (int, may be NULL) is set to 1 if an index is out of
- *   range (tl.device_assert at sae/kernels.py:276). */
+ *   range (tl.device_assert at sae/kernels.py:276).  max_ctas: see saeb_refine_candidates. */
 int saeb_decode(const int64_t* idx, const float* vals, int64_t T, int k, const void* W_dec, int w_dtype, int64_t d,
                 int64_t N, const float* b_dec, void* out, int out_dtype, int64_t ld_out, const void* x, int x_dtype,
-                int64_t ld_x, double* sq_err, int* err_flag, void* stream);
+                int64_t ld_x, double* sq_err, int* err_flag, int max_ctas, void* stream);
 
 /* ---- backward of the sparse decode -------------------------------------------------------------------------
  * The decoder seam is a torch.autograd.Function in the reference (TritonDecoder, sae/kernels.py:403-429); these are

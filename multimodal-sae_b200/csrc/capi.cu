@@ -33,9 +33,10 @@ int encode_gemm_launch(const void* x_planes, int ap, long long T, long long ld_x
                        void* workspace, size_t workspace_bytes, int pass_mask, int operand_fmt, const float* row_scale,
                        const float* w_unscale, cudaStream_t stream);
 int encode_merge_launch(long long T, long long N, int k, float* out_vals, long long* out_idx, void* workspace,
-                        size_t workspace_bytes, cudaStream_t stream);
+                        size_t workspace_bytes, int coresident, cudaStream_t stream);
 int set_chunking(int v);
 int set_reserve_sms(int v);
+int set_gemm_stages(int v);
 int pack_weights_f16_launch(const float* W_enc, const float* b_enc, const float* b_dec, long long N, long long d,
                             long long d_pad, void* w_plane, float* bias, float* wnorm, float* dnorm, float* trailer,
                             cudaStream_t stream);
@@ -47,7 +48,8 @@ int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const
                   const float* xdnorm, float c_eps,
                   const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                   float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
-                  float* dense_scratch, const float* ext_lower, const void* w_lo, long long ld_w, cudaStream_t stream);
+                  float* dense_scratch, const float* ext_lower, const void* w_lo, long long ld_w, int max_ctas,
+                  cudaStream_t stream);
 int pack_weights_lo_launch(const float* W_enc, long long N, long long d, long long d_pad, const float* trailer,
                            void* lo_plane, cudaStream_t stream);
 int candidate_bounds_launch(const float* cand_vals, const long long* cand_idx, long long T, int K2, int k,
@@ -69,7 +71,8 @@ int split_x_launch(const void* x, int x_dtype, long long T, long long d, long lo
                    void* out, cudaStream_t stream);
 int decode_launch(const long long* idx, const float* vals, long long T, int k, const void* W_dec, int w_dtype,
                   long long d, long long N, const float* b_dec, void* out, int out_dtype, long long ld_out,
-                  const void* x, int x_dtype, long long ld_x, double* sq_err, int* err_flag, cudaStream_t stream);
+                  const void* x, int x_dtype, long long ld_x, double* sq_err, int* err_flag, int max_ctas,
+                  cudaStream_t stream);
 int total_variance_launch(const void* x, int x_dtype, long long T, long long d, long long ld_x, double* scratch,
                           double* out, cudaStream_t stream);
 size_t coo_workspace_bytes(long long T);
@@ -149,6 +152,7 @@ int saeb_set_option(const char* name, int value) {
   if (strcmp(name, "persist_a") == 0) return set_persist_a(value);
   if (strcmp(name, "chunking") == 0) return set_chunking(value);
   if (strcmp(name, "reserve_sms") == 0) return set_reserve_sms(value);
+  if (strcmp(name, "gemm_stages") == 0) return set_gemm_stages(value);
   if (strcmp(name, "kth_impl") == 0) return set_kth_impl(value);
   if (strcmp(name, "refine_threads") == 0) return set_refine_threads(value);
   if (strcmp(name, "refine_margin") == 0) {
@@ -396,7 +400,7 @@ int saeb_candidate_bounds(const void* prep, int64_t T_total, int64_t t0, int64_t
   const float* dnorm = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + 2 * bias_bytes(N));
   float* mvals = reinterpret_cast<float*>(ws + w.mvals);
   long long* midx = reinterpret_cast<long long*>(ws + w.midx);
-  int rc = encode_merge_launch(Tc, N, K2, mvals, midx, ws + w.enc, w.total - w.enc, st);
+  int rc = encode_merge_launch(Tc, N, K2, mvals, midx, ws + w.enc, w.total - w.enc, 0, st);
   if (rc) return rc;
   rc = candidate_bounds_launch(mvals, midx, Tc, K2, k < K2 ? k : K2, wnorm, dnorm,
                                reinterpret_cast<const float*>(pb + p.xnorm) + t0,
@@ -410,9 +414,10 @@ static int refine_candidates_impl(bool lo, const void* x, int x_dtype, int64_t l
                                   int64_t t0, int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N,
                                   int k, int margin, int64_t clamp_feature, float clamp_value, const float* ext_lower,
                                   int already_merged, float* out_vals, int64_t* out_idx, int32_t* status_out,
-                                  void* workspace, size_t workspace_bytes, void* stream) {
+                                  void* workspace, size_t workspace_bytes, int max_ctas, void* stream) {
   g_err[0] = 0;
   SAEB_REQUIRE(x && prep && packed && W_enc && out_vals && out_idx && workspace, "refine_candidates: null pointer");
+  SAEB_REQUIRE(max_ctas >= 0, "refine_candidates: max_ctas must be >= 0");
   SAEB_REQUIRE(t0 >= 0 && Tc >= 0 && t0 + Tc <= T_total, "refine_candidates: bad row range");
   if (Tc == 0) return 0;
   const int K2raw = refine_k2(k, margin);
@@ -434,7 +439,7 @@ static int refine_candidates_impl(bool lo, const void* x, int x_dtype, int64_t l
   SAEB_CHECK_CUDA(cudaMemsetAsync(status, 0, 256, st));
   int rc = 0;
   if (!already_merged) {
-    rc = encode_merge_launch(Tc, N, K2, mvals, midx, ws + w.enc, w.total - w.enc, st);
+    rc = encode_merge_launch(Tc, N, K2, mvals, midx, ws + w.enc, w.total - w.enc, max_ctas > 0, st);
     if (rc) return rc;
   }
   rc = refine_launch(x, x_dtype, Tc, ld_x, W_enc, d, N, bias, wnorm, dnorm, trailer,
@@ -442,7 +447,7 @@ static int refine_candidates_impl(bool lo, const void* x, int x_dtype, int64_t l
                      reinterpret_cast<const float*>(pb + p.xdnorm) + t0, refine_c_eps(x_dtype), mvals, midx, K2,
                      k < K2 ? k : K2, clamp_feature, clamp_value, out_vals, reinterpret_cast<long long*>(out_idx), status,
                      reinterpret_cast<int*>(ws + w.flag_rows), reinterpret_cast<float*>(ws + w.dense), ext_lower,
-                     lo ? pk + mode3_bytes(N, d) : nullptr, pad8(d), st);
+                     lo ? pk + mode3_bytes(N, d) : nullptr, pad8(d), max_ctas, st);
   if (rc) return rc;
   if (status_out != nullptr)
     SAEB_CHECK_CUDA(cudaMemcpyAsync(status_out, status, sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -454,20 +459,20 @@ int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void*
                            int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N, int k, int margin,
                            int64_t clamp_feature, float clamp_value, const float* ext_lower, int already_merged,
                            float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
-                           size_t workspace_bytes, void* stream) {
+                           size_t workspace_bytes, int max_ctas, void* stream) {
   return refine_candidates_impl(false, x, x_dtype, ld_x, prep, T_total, t0, Tc, packed, W_enc, d, N, k, margin,
                                 clamp_feature, clamp_value, ext_lower, already_merged, out_vals, out_idx, status_out,
-                                workspace, workspace_bytes, stream);
+                                workspace, workspace_bytes, max_ctas, stream);
 }
 
 int saeb_refine_candidates_lo(const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total, int64_t t0,
                               int64_t Tc, const void* packed4, const float* W_enc, int64_t d, int64_t N, int k,
                               int margin, int64_t clamp_feature, float clamp_value, const float* ext_lower,
                               int already_merged, float* out_vals, int64_t* out_idx, int32_t* status_out,
-                              void* workspace, size_t workspace_bytes, void* stream) {
+                              void* workspace, size_t workspace_bytes, int max_ctas, void* stream) {
   return refine_candidates_impl(true, x, x_dtype, ld_x, prep, T_total, t0, Tc, packed4, W_enc, d, N, k, margin,
                                 clamp_feature, clamp_value, ext_lower, already_merged, out_vals, out_idx, status_out,
-                                workspace, workspace_bytes, stream);
+                                workspace, workspace_bytes, max_ctas, stream);
 }
 
 size_t saeb_encode_topk_refine_workspace_bytes(int64_t T, int64_t d, int64_t N, int k, int margin) {
@@ -492,7 +497,7 @@ int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x,
   if (rc) return rc;
   return saeb_refine_candidates(x, x_dtype, ld_x, ws, T, 0, T, packed, W_enc, d, N, k, margin, clamp_feature,
                                 clamp_value, nullptr, 0, out_vals, out_idx, status_out, ws + prep_bytes,
-                                workspace_bytes - prep_bytes, stream);
+                                workspace_bytes - prep_bytes, 0, stream);
 }
 
 int saeb_dense_topk(const float* dense, int64_t T, int64_t ld, int64_t N, int k, float* out_vals, int64_t* out_idx,
@@ -506,11 +511,12 @@ int saeb_dense_topk(const float* dense, int64_t T, int64_t ld, int64_t N, int k,
 
 int saeb_decode(const int64_t* idx, const float* vals, int64_t T, int k, const void* W_dec, int w_dtype, int64_t d,
                 int64_t N, const float* b_dec, void* out, int out_dtype, int64_t ld_out, const void* x, int x_dtype,
-                int64_t ld_x, double* sq_err, int* err_flag, void* stream) {
+                int64_t ld_x, double* sq_err, int* err_flag, int max_ctas, void* stream) {
   g_err[0] = 0;
   SAEB_REQUIRE(idx && vals && W_dec && out, "decode: null pointer");
+  SAEB_REQUIRE(max_ctas >= 0, "decode: max_ctas must be >= 0");
   int rc = decode_launch(reinterpret_cast<const long long*>(idx), vals, T, k, W_dec, w_dtype, d, N, b_dec, out,
-                         out_dtype, ld_out, x, x_dtype, ld_x, sq_err, err_flag, (cudaStream_t)stream);
+                         out_dtype, ld_out, x, x_dtype, ld_x, sq_err, err_flag, max_ctas, (cudaStream_t)stream);
   if (rc == 0 && T > 0) g_launches += 1;
   return rc;
 }

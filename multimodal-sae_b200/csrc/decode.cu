@@ -15,8 +15,10 @@ namespace saeb {
 template <typename WT, typename OT>
 static int decode_dispatch_x(const long long* idx, const float* vals, long long T, int k, const WT* W, long long d,
                              long long N, const float* b_dec, OT* out, long long ld_out, const void* x, int x_dtype,
-                             long long ld_x, double* sq_err, int* err_flag, cudaStream_t stream) {
-  dim3 grid((unsigned)T), block(DEC_THREADS);
+                             long long ld_x, double* sq_err, int* err_flag, int max_ctas, cudaStream_t stream) {
+  // max_ctas > 0: persistent grid (tokens walked with stride gridDim.x) so that a fixed number of CTAs per SM rides
+  // beside a resident GEMM grid; 0: one CTA per token
+  dim3 grid((unsigned)((max_ctas > 0 && max_ctas < T) ? max_ctas : T)), block(DEC_THREADS);
   const bool with_x = sq_err != nullptr && x != nullptr;
   const bool vec = d % 4 == 0 && ld_out % 4 == 0 && (!with_x || ld_x % 4 == 0) &&
                    (reinterpret_cast<uintptr_t>(W) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
@@ -26,10 +28,10 @@ static int decode_dispatch_x(const long long* idx, const float* vals, long long 
   do {                                                                                                              \
     if (vec)                                                                                                        \
       decode_kernel<WT, OT, XT><<<grid, block, 0, stream>>>(idx, vals, k, W, d, N, b_dec, out, ld_out, XP, LDX, SQ,  \
-                                                            err_flag);                                              \
+                                                            err_flag, T);                                           \
     else                                                                                                            \
       decode_scalar_kernel<WT, OT, XT><<<grid, block, 0, stream>>>(idx, vals, k, W, d, N, b_dec, out, ld_out, XP,    \
-                                                                   LDX, SQ, err_flag);                              \
+                                                                   LDX, SQ, err_flag, T);                           \
   } while (0)
   if (!with_x)
     SAEB_DEC_LAUNCH(float, (const float*)nullptr, 0, (double*)nullptr);
@@ -50,36 +52,37 @@ static int decode_dispatch_x(const long long* idx, const float* vals, long long 
 template <typename WT>
 static int decode_dispatch_o(const long long* idx, const float* vals, long long T, int k, const WT* W, long long d,
                              long long N, const float* b_dec, void* out, int out_dtype, long long ld_out,
-                             const void* x, int x_dtype, long long ld_x, double* sq_err, int* err_flag,
+                             const void* x, int x_dtype, long long ld_x, double* sq_err, int* err_flag, int max_ctas,
                              cudaStream_t stream) {
   if (out_dtype == DT_F32)
     return decode_dispatch_x<WT, float>(idx, vals, T, k, W, d, N, b_dec, reinterpret_cast<float*>(out), ld_out, x,
-                                        x_dtype, ld_x, sq_err, err_flag, stream);
+                                        x_dtype, ld_x, sq_err, err_flag, max_ctas, stream);
   if (out_dtype == DT_F16)
     return decode_dispatch_x<WT, __half>(idx, vals, T, k, W, d, N, b_dec, reinterpret_cast<__half*>(out), ld_out, x,
-                                         x_dtype, ld_x, sq_err, err_flag, stream);
+                                         x_dtype, ld_x, sq_err, err_flag, max_ctas, stream);
   if (out_dtype == DT_BF16)
     return decode_dispatch_x<WT, __nv_bfloat16>(idx, vals, T, k, W, d, N, b_dec, reinterpret_cast<__nv_bfloat16*>(out),
-                                                ld_out, x, x_dtype, ld_x, sq_err, err_flag, stream);
+                                                ld_out, x, x_dtype, ld_x, sq_err, err_flag, max_ctas, stream);
   set_error("decode: unsupported output dtype %d", out_dtype);
   return -1;
 }
 
 int decode_launch(const long long* idx, const float* vals, long long T, int k, const void* W_dec, int w_dtype,
                   long long d, long long N, const float* b_dec, void* out, int out_dtype, long long ld_out,
-                  const void* x, int x_dtype, long long ld_x, double* sq_err, int* err_flag, cudaStream_t stream) {
+                  const void* x, int x_dtype, long long ld_x, double* sq_err, int* err_flag, int max_ctas,
+                  cudaStream_t stream) {
   if (T == 0) return 0;
   SAEB_REQUIRE(k >= 1 && k <= DEC_KMAX, "decode: k=%d out of range (1..%d)", k, DEC_KMAX);
   SAEB_REQUIRE(d >= 1 && ld_out >= d, "decode: bad d / ld_out");
   if (w_dtype == DT_F32)
     return decode_dispatch_o<float>(idx, vals, T, k, reinterpret_cast<const float*>(W_dec), d, N, b_dec, out,
-                                    out_dtype, ld_out, x, x_dtype, ld_x, sq_err, err_flag, stream);
+                                    out_dtype, ld_out, x, x_dtype, ld_x, sq_err, err_flag, max_ctas, stream);
   if (w_dtype == DT_BF16)
     return decode_dispatch_o<__nv_bfloat16>(idx, vals, T, k, reinterpret_cast<const __nv_bfloat16*>(W_dec), d, N,
-                                            b_dec, out, out_dtype, ld_out, x, x_dtype, ld_x, sq_err, err_flag, stream);
+                                            b_dec, out, out_dtype, ld_out, x, x_dtype, ld_x, sq_err, err_flag, max_ctas, stream);
   if (w_dtype == DT_F16)
     return decode_dispatch_o<__half>(idx, vals, T, k, reinterpret_cast<const __half*>(W_dec), d, N, b_dec, out,
-                                     out_dtype, ld_out, x, x_dtype, ld_x, sq_err, err_flag, stream);
+                                     out_dtype, ld_out, x, x_dtype, ld_x, sq_err, err_flag, max_ctas, stream);
   set_error("decode: unsupported W_dec dtype %d", w_dtype);
   return -1;
 }

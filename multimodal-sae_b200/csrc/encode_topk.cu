@@ -53,6 +53,7 @@ struct EncodeArgs {
   int clamp_col;      // steering: column forced to clamp_val before TopK (-1 = none)
   float clamp_val;
   unsigned long long* stats;   // optional diagnostics: cycle counters summed over CTAs (see saeb_debug_stats)
+  int stages;       // depth of the TMA -> MMA shared-memory ring actually used (<= EncCfg::STAGES)
   int prefetch_b;   // weight tiles are pulled into L2 this many feature tiles ahead (0 = off), one pair per tile
   int dbg;   // diagnostics only (wrong results): bit0 = every cluster loads token tile 0, bit1 = every step loads feature tile 0
   unsigned long long hint_a, hint_b;   // L2 eviction policies of the activation / weight TMA loads
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const EncodeArgs args) {
   using Cfg = EncCfg<AP, BP, PAIR>;
-  constexpr int STAGES = Cfg::STAGES;
+  const int STAGES = args.stages;   // run-time ring depth: a shallower ring leaves shared memory for co-resident gather CTAs
   constexpr int CAP = 32 * SLOTS;
   constexpr uint32_t TMEM_COLS = 512;
 
@@ -610,6 +611,18 @@ size_t encode_workspace_bytes(long long T, long long d, long long N, int k) {
   return best + 1024;
 }
 
+// depth of the smem ring (0 = as deep as fits: 6 stages of 32 KB in the single-pass pair mode).  5 leaves ~54 KB of
+// shared memory per SM to the gather CTAs that run beside the GEMM (saeb200.overlap).
+static int g_gemm_stages = 0;
+int set_gemm_stages(int v) {
+  if (v != 0 && (v < 2 || v > 8)) {
+    set_error("gemm_stages must be 0 (automatic) or 2..8");
+    return -1;
+  }
+  g_gemm_stages = v;
+  return 0;
+}
+
 struct PersistWindow {
   void* base = nullptr;
   size_t bytes = 0;
@@ -622,10 +635,12 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const Encode
   using Cfg = EncCfg<AP, BP, PAIR>;
   auto kern = encode_topk_kernel<AP, BP, PAIR, SLOTS>;
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  EncodeArgs largs = args;
+  largs.stages = (g_gemm_stages >= 2 && g_gemm_stages < Cfg::STAGES) ? g_gemm_stages : Cfg::STAGES;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.dynamicSmemBytes = largs.stages * Cfg::STAGE + SMEM_MISC + 1024;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -647,7 +662,7 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const Encode
     attr[1].val.accessPolicyWindow.missProp = g_persist_a == 1 ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
     cfg.numAttrs = 2;
   }
-  SAEB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, args));
+  SAEB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, largs));
   return 0;
 }
 
@@ -744,8 +759,9 @@ int encode_gemm_launch(const void* x_planes, int ap, long long T, long long ld_x
 }
 
 // Phase 2: exact top-k per row over the candidate lists of phase 1
+// coresident != 0: blocks small enough (<= 20 KB of shared memory, 4 warps) to be scheduled beside a resident GEMM CTA
 int encode_merge_launch(long long T, long long N, int k, float* out_vals, long long* out_idx, void* workspace,
-                        size_t workspace_bytes, cudaStream_t stream) {
+                        size_t workspace_bytes, int coresident, cudaStream_t stream) {
   const int pair = default_pair();
   static thread_local EncodePlan plan;
   SAEB_REQUIRE(make_plan(plan, T, N, k, pair), "too many row chunks");
@@ -761,6 +777,7 @@ int encode_merge_launch(long long T, long long N, int k, float* out_vals, long l
     const size_t per_warp = (size_t)(max_entries + kp2) * sizeof(uint2);
     int wpb = (int)((200 * 1024) / per_warp);
     if (wpb > 8) wpb = 8;
+    if (coresident && (size_t)wpb * per_warp > 20 * 1024) wpb = (int)((20 * 1024) / per_warp) > 0 ? (int)((20 * 1024) / per_warp) : 1;
     SAEB_REQUIRE(wpb >= 1, "merge: candidate set too large for shared memory");
     const size_t smem = per_warp * wpb;
     SAEB_CHECK_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -785,7 +802,7 @@ int encode_topk_launch(const void* x_planes, int ap, long long T, long long ld_x
                               clamp_value, do_topk, dense_out, ld_dense, workspace, workspace_bytes, pass_mask,
                               operand_fmt, row_scale, w_unscale, stream);
   if (rc) return rc;
-  if (do_topk) rc = encode_merge_launch(T, N, k, out_vals, out_idx, workspace, workspace_bytes, stream);
+  if (do_topk) rc = encode_merge_launch(T, N, k, out_vals, out_idx, workspace, workspace_bytes, 0, stream);
   return rc;
 }
 

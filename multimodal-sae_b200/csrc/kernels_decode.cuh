@@ -93,13 +93,16 @@ template <typename WT, typename OT, typename XT>
 __global__ void __launch_bounds__(DEC_THREADS)
 decode_kernel(const long long* __restrict__ idx, const float* __restrict__ vals, int k, const WT* __restrict__ W,
               long long d, long long N, const float* __restrict__ b_dec, OT* __restrict__ out, long long ld_out,
-              const XT* __restrict__ x, long long ld_x, double* __restrict__ sq_err, int* __restrict__ err_flag) {
+              const XT* __restrict__ x, long long ld_x, double* __restrict__ sq_err, int* __restrict__ err_flag,
+              long long T) {
   __shared__ long long s_row[DEC_KMAX];
   __shared__ float s_val[DEC_KMAX];
   __shared__ int s_n;
   __shared__ float s_red[DEC_THREADS / 32];
-  const long long t = blockIdx.x;
   const int tid = threadIdx.x;
+  float local_sq = 0.f;
+  // one token per CTA when gridDim.x >= T; a smaller (persistent) grid walks the tokens with stride gridDim.x
+  for (long long t = blockIdx.x; t < T; t += gridDim.x) {
   if (tid == 0) s_n = 0;
   __syncthreads();
   // compact away zero activations (sae/kernels.py:277) keeping j order; validate indices (kernels.py:276)
@@ -131,7 +134,6 @@ decode_kernel(const long long* __restrict__ idx, const float* __restrict__ vals,
   __syncthreads();
   const int n = s_n;
   const int ncol4 = (int)(d >> 2);
-  float local_sq = 0.f;
   for (int c4 = tid; c4 < ncol4; c4 += DEC_THREADS) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int j = 0;
@@ -168,6 +170,7 @@ decode_kernel(const long long* __restrict__ idx, const float* __restrict__ vals,
     }
   }
   if (sq_err != nullptr) {
+    // per token: warp sums -> one double add (same rounding whether the grid is one CTA per token or persistent)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) local_sq += __shfl_xor_sync(0xffffffffu, local_sq, o);
     if ((tid & 31) == 0) s_red[tid >> 5] = local_sq;
@@ -177,6 +180,9 @@ decode_kernel(const long long* __restrict__ idx, const float* __restrict__ vals,
       for (int w = 0; w < DEC_THREADS / 32; ++w) s += (double)s_red[w];
       atomicAdd(sq_err, s);
     }
+    local_sq = 0.f;
+  }
+  __syncthreads();   // s_row / s_val / s_red are reused by the next token
   }
 }
 
@@ -187,10 +193,10 @@ __global__ void __launch_bounds__(DEC_THREADS)
 decode_scalar_kernel(const long long* __restrict__ idx, const float* __restrict__ vals, int k,
                      const WT* __restrict__ W, long long d, long long N, const float* __restrict__ b_dec,
                      OT* __restrict__ out, long long ld_out, const XT* __restrict__ x, long long ld_x,
-                     double* __restrict__ sq_err, int* __restrict__ err_flag) {
+                     double* __restrict__ sq_err, int* __restrict__ err_flag, long long T) {
   __shared__ float s_red[DEC_THREADS / 32];
-  const long long t = blockIdx.x;
   const int tid = threadIdx.x;
+  for (long long t = blockIdx.x; t < T; t += gridDim.x) {
   float local_sq = 0.f;
   for (long long c = tid; c < d; c += DEC_THREADS) {
     float acc = 0.f;
@@ -220,6 +226,8 @@ decode_scalar_kernel(const long long* __restrict__ idx, const float* __restrict_
       for (int w = 0; w < DEC_THREADS / 32; ++w) s2 += (double)s_red[w];
       atomicAdd(sq_err, s2);
     }
+    __syncthreads();
+  }
   }
 }
 

@@ -24,7 +24,7 @@ refine_body(const XT* __restrict__ x, long long ld_x, const float* __restrict__ 
             const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
             float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
             int* __restrict__ flag_rows, const float* __restrict__ ext_lower, const __half* __restrict__ Wlo,
-            long long ld_w) {
+            long long ld_w, long long T) {
   extern __shared__ float rsm[];
   float* xs = rsm;                                   // [d4] activations of this row as fp32
   const int d4 = LO ? (int)((d + 7) & ~7ll) : (int)((d + 3) & ~3ll);   // LO: padded like the packed weight rows
@@ -35,9 +35,10 @@ refine_body(const XT* __restrict__ x, long long ld_x, const float* __restrict__ 
   int* f = reinterpret_cast<int*>(ex + K2);          // [K2] feature ids
   __shared__ float s_L;
   __shared__ int s_cnt[2];
-  const long long t = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
-
+  // one token per CTA when gridDim.x >= T; a smaller (persistent) grid walks the tokens with stride gridDim.x so that
+  // a fixed number of CTAs per SM can ride beside the persistent GEMM grid
+  for (long long t = blockIdx.x; t < T; t += gridDim.x) {
   for (int i = tid; i < d4; i += nthr) xs[i] = (i < d) ? (float)x[t * ld_x + i] : 0.f;
   const float xn = xnorm[t], xdn = xdnorm[t];
   const float wmax = trailer[1], dmax = trailer[3];
@@ -226,6 +227,8 @@ refine_body(const XT* __restrict__ x, long long ld_x, const float* __restrict__ 
       filled += __popc(m);
     }
   }
+  __syncthreads();   // the shared row / candidate buffers are reused by the next token
+  }
 }
 
 template <typename XT>
@@ -236,9 +239,9 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict_
               float c_eps, const float* __restrict__ cand_vals,
               const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
               float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
-              int* __restrict__ flag_rows, const float* __restrict__ ext_lower) {
+              int* __restrict__ flag_rows, const float* __restrict__ ext_lower, long long T) {
   refine_body<XT, false>(x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k,
-                         clamp_feature, clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, nullptr, 0);
+                         clamp_feature, clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, nullptr, 0, T);
 }
 
 template <typename XT>
@@ -249,9 +252,9 @@ refine_lo_kernel(const XT* __restrict__ x, long long ld_x, const __half* __restr
                  const float* __restrict__ xdnorm, float c_eps, const float* __restrict__ cand_vals,
                  const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
                  float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
-                 int* __restrict__ flag_rows, const float* __restrict__ ext_lower) {
+                 int* __restrict__ flag_rows, const float* __restrict__ ext_lower, long long T) {
   refine_body<XT, true>(x, ld_x, nullptr, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx,
-                        K2, k, clamp_feature, clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, Wlo, ld_w);
+                        K2, k, clamp_feature, clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, Wlo, ld_w, T);
 }
 
 // ---------------------------------------------------------------------------------------------

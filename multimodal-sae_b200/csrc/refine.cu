@@ -57,9 +57,12 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
                            const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                            float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
                            float* dense_scratch, const float* ext_lower, const __half* w_lo, long long ld_w,
-                           cudaStream_t stream) {
+                           int max_ctas, cudaStream_t stream) {
   // feature-sharded calls evaluate only a handful of candidates per token: smaller blocks, more tokens in flight
   const int threads = ext_lower != nullptr ? g_refine_threads_sharded : RF_THREADS;
+  // max_ctas > 0: persistent grid (tokens walked with stride gridDim.x), sized by the caller so that a fixed number of
+  // CTAs per SM rides beside a resident GEMM grid; 0: one CTA per token
+  const unsigned grid = (unsigned)((max_ctas > 0 && max_ctas < T) ? max_ctas : T);
   bool use_lo = false;
   if constexpr (!std::is_same<XT, float>::value) {
     use_lo = w_lo != nullptr;
@@ -74,9 +77,9 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
                  "refine: residual plane must be 16-byte aligned with rows padded to a multiple of 8");
     auto kern = refine_lo_kernel<XT>;
     SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)T, threads, smem, stream>>>(x, ld_x, w_lo, ld_w, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm,
-                                                   c_eps, cand_vals, cand_idx, K2, k, clamp_feature, clamp_value,
-                                                   out_vals, out_idx, status, flag_rows, ext_lower);
+    kern<<<grid, threads, smem, stream>>>(x, ld_x, w_lo, ld_w, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps,
+                                            cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx,
+                                            status, flag_rows, ext_lower, T);
   }
   if (!use_lo) {
     const int d4 = (int)((d + 3) & ~3ll);
@@ -84,9 +87,9 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
     SAEB_REQUIRE(smem <= 200 * 1024, "refine: d=%lld too large for the shared-memory row buffer", d);
     auto kern = refine_kernel<XT>;
     SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)T, threads, smem, stream>>>(x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps,
-                                                   cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals,
-                                                   out_idx, status, flag_rows, ext_lower);
+    kern<<<grid, threads, smem, stream>>>(x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps,
+                                            cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx,
+                                            status, flag_rows, ext_lower, T);
   }
   SAEB_CHECK_CUDA(cudaGetLastError());
   // exact dense fallback for the (normally zero) flagged rows; the grids exit at once when nothing is flagged
@@ -99,13 +102,16 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
   SAEB_CHECK_CUDA(cudaGetLastError());
   int kp2 = 2;
   while (kp2 < k) kp2 <<= 1;
-  dense_topk_kernel<<<RF_MAX_FLAG, 1024, (size_t)kp2 * sizeof(uint2), stream>>>(
+  // beside a resident GEMM grid only small blocks can be scheduled (registers): the fallback grids, which exit at once
+  // when nothing is flagged, must never make the stream wait for a GEMM launch boundary
+  const int fb_threads = max_ctas > 0 ? 256 : 1024;
+  dense_topk_kernel<<<RF_MAX_FLAG, fb_threads, (size_t)kp2 * sizeof(uint2), stream>>>(
       dense_scratch, N, N, k, status, RF_MAX_FLAG, flag_rows, out_vals, out_idx);
   SAEB_CHECK_CUDA(cudaGetLastError());
   auto ok = overflow_rows_kernel<XT>;
   const size_t osmem = (size_t)kp2 * sizeof(uint2) + (size_t)d * sizeof(float);
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(ok, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osmem));
-  ok<<<RF_MAX_FLAG, 1024, osmem, stream>>>(x, ld_x, W, d, N, bias, status, flag_rows, clamp_feature, clamp_value,
+  ok<<<RF_MAX_FLAG, fb_threads, osmem, stream>>>(x, ld_x, W, d, N, bias, status, flag_rows, clamp_feature, clamp_value,
                                            dense_scratch, k, out_vals, out_idx);
   SAEB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -116,12 +122,14 @@ int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const
                   const float* xdnorm, float c_eps,
                   const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                   float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
-                  float* dense_scratch, const float* ext_lower, const void* w_lo, long long ld_w, cudaStream_t stream) {
+                  float* dense_scratch, const float* ext_lower, const void* w_lo, long long ld_w, int max_ctas,
+                  cudaStream_t stream) {
 #define SAEB_RF(XT)                                                                                                  \
   return refine_launch_t<XT>(reinterpret_cast<const XT*>(x), T, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm,   \
                              xdnorm, c_eps,                                                                          \
                              cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx, status,      \
-                             flag_rows, dense_scratch, ext_lower, reinterpret_cast<const __half*>(w_lo), ld_w, stream)
+                             flag_rows, dense_scratch, ext_lower, reinterpret_cast<const __half*>(w_lo), ld_w,       \
+                             max_ctas, stream)
   if (x_dtype == DT_F32) SAEB_RF(float);
   if (x_dtype == DT_BF16) SAEB_RF(__nv_bfloat16);
   if (x_dtype == DT_F16) SAEB_RF(__half);

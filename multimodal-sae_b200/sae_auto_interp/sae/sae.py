@@ -63,7 +63,7 @@ class Sae(nn.Module):
         self.encoder_planes = 3
         self._packed = {}
         self._overlap = None
-        self.overlap_chunk = 18944  # two waves of 37 token tiles
+        self.overlap_chunk = 9472  # one wave of 37 token tiles: one GEMM launch per pipeline chunk
 
     # ------------------------------------------------------------------ loading / saving
     @staticmethod

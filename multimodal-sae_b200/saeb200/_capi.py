@@ -46,15 +46,15 @@ SIGNATURES = {
                                        c_int64, c_float, c_void_p, c_size_t, c_void_p]),
     "saeb_refine_candidates": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                                        c_void_p, c_int64, c_int64, c_int, c_int, c_int64, c_float, c_void_p, c_int,
-                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "saeb_refine_candidates_lo": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                                           c_void_p, c_int64, c_int64, c_int, c_int, c_int64, c_float, c_void_p, c_int,
-                                          c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "saeb_candidate_bounds": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int64, c_int64, c_int,
                                       c_int, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "saeb_dense_topk": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "saeb_decode": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p,
-                            c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+                            c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "saeb_decode_backward_acts": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64,
                                           c_void_p, c_void_p, c_void_p]),
     "saeb_decode_backward_weight": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64,

@@ -153,7 +153,7 @@ def encode_topk(x: torch.Tensor, enc: PackedEncoder, k: int, *, clamp_feature: i
             check(L.saeb_refine_candidates_lo(x2.data_ptr(), code, ldx, prep.data_ptr(), T, 0, T, enc.blob.data_ptr(),
                                               enc.W_enc.data_ptr(), enc.d_in, enc.num_latents, k, refine_margin,
                                               clamp_feature, float(clamp_value), None, 0, vals.data_ptr(),
-                                              idx.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), st),
+                                              idx.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), 0, st),
                   "saeb_refine_candidates_lo")
         encode_topk.last_status = status
     elif T > 0:
@@ -197,10 +197,11 @@ def dense_topk(latents: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tenso
 
 def decode(top_indices: torch.Tensor, top_acts: torch.Tensor, W_dec: torch.Tensor, b_dec: Optional[torch.Tensor],
            *, out_dtype: torch.dtype = torch.float32, x: Optional[torch.Tensor] = None,
-           sq_err: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+           sq_err: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, max_ctas: int = 0
+           ) -> torch.Tensor:
     """out[..., :] = sum_j acts[..., j] * W_dec[idx[..., j], :] + b_dec.  W_dec is the [N, d] parameter
     (fp32 parity grade, or a bf16 copy).  If `x` and `sq_err` (0-dim float64) are given, sum((out-x)^2) is added
-    to sq_err."""
+    to sq_err.  max_ctas > 0: persistent grid of that many CTAs (rides beside a resident GEMM grid; same results)."""
     _need_cuda(top_indices, top_acts, W_dec, b_dec, x, sq_err)
     L = _capi.lib()
     N, d = W_dec.shape
@@ -234,7 +235,7 @@ def decode(top_indices: torch.Tensor, top_acts: torch.Tensor, W_dec: torch.Tenso
                             None if x2 is None else x2.data_ptr(), 0 if x2 is None else _code(x2),
                             0 if x2 is None else (x2.stride(0) if T > 1 else d),
                             None if (sq_err is None or x2 is None) else sq_err.data_ptr(), err_flag.data_ptr(),
-                            _stream()), "saeb_decode")
+                            int(max_ctas), _stream()), "saeb_decode")
     decode.last_err_flag = err_flag
     return out.view(*lead, d)
 

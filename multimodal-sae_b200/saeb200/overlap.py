@@ -1,14 +1,24 @@
 """Chunked forward with the tensor-core-bound and the HBM-bound halves on different streams.
 
 Per token chunk the "fp16 + refine" path has two phases with opposite bottlenecks:
-  A  activation prep + single-pass tcgen05 GEMM with fused candidate selection + merge   (tensor pipe)
-  B  exact fp32 refinement of the candidates + sparse decode (+ residual sum of squares)  (HBM row gathers)
-Phase A of chunk c+1 is issued on the GEMM stream while phase B of chunk c runs on the memory stream; the persistent
-GEMM kernel leaves enough shared memory / registers per SM for the gather kernels' CTAs to co-reside, so the gathers
-ride in the HBM bandwidth the GEMM does not use.  Two workspaces alternate between consecutive chunks.
+  A  activation prep + single-pass tcgen05 GEMM with fused candidate selection             (tensor pipe)
+  B  candidate merge + exact fp32 refinement + sparse decode (+ residual sum of squares)    (HBM row gathers)
+Phase A of chunk c+1 is issued on the GEMM stream while phase B of chunk c runs on the memory stream.
+
+What makes the two phases actually share the SMs (round 1 measured ~1 % gain from two plain streams):
+  * the GEMM is one persistent CTA per SM that owns ~206 KB of its shared memory, so a gather kernel can only run
+    beside it if EVERY launch of phase B fits in what is left (~21 KB, 24 K registers per SM).  Phase B therefore runs
+    as persistent grids of `ctas_per_sm` x #SM small CTAs that walk the chunk's tokens (`max_ctas` of the C ABI), its
+    helper launches (merge, the flagged-row fallback grids that normally exit at once) use small blocks, and nothing
+    in it ever has to wait for a GEMM launch boundary;
+  * a one-CTA-per-token gather grid would flood every SM that a finishing GEMM CTA frees and keep the next GEMM launch
+    out until it has drained -- with a bounded grid the GEMM CTAs always find their SM;
+  * the GEMM stream has the higher priority, so at a launch boundary its CTAs are placed first.
+The last chunk's phase B has nothing to hide behind and runs with full grids.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -20,21 +30,37 @@ from ._capi import check
 WAVE_TOKENS = 9472  # 37 token tiles of 256 rows: one wave of (tile, split) units on a 148-SM part at S = 2
 
 
+def _env_int(name: str, default: int) -> int:
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
 class OverlappedForward:
+    N_WS = 3   # candidate workspaces in rotation: the GEMM may run two chunks ahead of the gathers
+
     def __init__(self, enc: engine.PackedEncoder, W_dec: torch.Tensor, b_dec: torch.Tensor, k: int,
-                 chunk: int = 2 * WAVE_TOKENS):
+                 chunk: int = WAVE_TOKENS, ctas_per_sm: Optional[int] = None, priority: Optional[str] = None):
         if enc.planes not in (3, 4):
             raise _capi.SaebError("OverlappedForward needs a refine-mode packed encoder (planes = 3 or 4)")
         self.enc, self.W_dec, self.b_dec, self.k, self.chunk = enc, W_dec, b_dec, k, chunk
         dev = enc.blob.device
         self.dev = dev
         L = _capi.lib()
+        with torch.cuda.device(dev):
+            self.num_sms = int(L.saeb_query(b"num_sms"))
+        # gather CTAs per SM while a GEMM launch is resident (0: one CTA per token, the round-1 behaviour)
+        self.ctas_per_sm = _env_int("SAEB_OV_CTAS_PER_SM", 1) if ctas_per_sm is None else int(ctas_per_sm)
+        priority = os.environ.get("SAEB_OV_PRIORITY", "gemm") if priority is None else priority
         self.ws_bytes = L.saeb_candidates_workspace_bytes(chunk, enc.d_in, enc.num_latents, k, 0)
-        self.ws = [torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.ws = [torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev) for _ in range(self.N_WS)]
         self.prep = None
-        self.status = torch.zeros(2, dtype=torch.int32, device=dev)
-        self.s_gemm = torch.cuda.Stream(dev, priority=0)
-        self.s_mem = torch.cuda.Stream(dev, priority=-1)   # gathers first: their CTAs slot in beside the GEMM's
+        self.status = torch.zeros(self.N_WS, dtype=torch.int32, device=dev)
+        lo, hi = 0, -1   # CUDA: a numerically lower priority is the higher one
+        pg, pm = {"gemm": (hi, lo), "mem": (lo, hi), "none": (lo, lo)}[priority]
+        self.s_gemm = torch.cuda.Stream(dev, priority=pg)
+        self.s_mem = torch.cuda.Stream(dev, priority=pm)
 
     def run(self, x: torch.Tensor, acts: torch.Tensor, idx: torch.Tensor, sae_out: Optional[torch.Tensor] = None,
             sq_err: Optional[torch.Tensor] = None, ready_events=None, done_events=None) -> None:
@@ -59,10 +85,13 @@ class OverlappedForward:
         if self.prep is None or self.prep.numel() < need:
             self.prep = torch.empty(need, dtype=torch.uint8, device=self.dev)
         prep = self.prep
+        nws = self.N_WS
         with torch.cuda.device(self.dev):
             for c in range(n_chunks):
                 a, b = c * self.chunk, min(T, (c + 1) * self.chunk)
-                ws = self.ws[c & 1]
+                ws = self.ws[c % nws]
+                # a GEMM launch follows this chunk's gathers -> bounded persistent grids; last chunk -> full grids
+                max_ctas = self.ctas_per_sm * self.num_sms if c + 1 < n_chunks else 0
                 with torch.cuda.stream(self.s_gemm):
                     if ready_events is not None:
                         self.s_gemm.wait_event(ready_events[c])
@@ -73,8 +102,8 @@ class OverlappedForward:
                     elif ready_events is not None:
                         # inputs arrive chunk by chunk (host copies): prepare each chunk when it lands
                         self._prep_rows(L, x, code, ldx, T, a, b, prep)
-                    if c >= 2:
-                        self.s_gemm.wait_event(ev_b[c - 2])   # scratch reuse
+                    if c >= nws:
+                        self.s_gemm.wait_event(ev_b[c - nws])   # scratch reuse
                     check(L.saeb_encode_candidates(prep.data_ptr(), T, a, b - a, enc.blob.data_ptr(), enc.d_in,
                                                    enc.num_latents, k, 0, -1, 0.0, ws.data_ptr(), ws.numel(),
                                                    self.s_gemm.cuda_stream), "saeb_encode_candidates")
@@ -82,13 +111,14 @@ class OverlappedForward:
                 with torch.cuda.stream(self.s_mem):
                     self.s_mem.wait_event(ev_a[c])
                     check(refine(x.data_ptr() + a * ldx * esz, code, ldx, prep.data_ptr(), T, a,
-                                                   b - a, enc.blob.data_ptr(), enc.W_enc.data_ptr(), enc.d_in,
-                                                   enc.num_latents, k, 0, -1, 0.0, None, 0, acts[a:b].data_ptr(),
-                                                   idx[a:b].data_ptr(), self.status[c & 1:].data_ptr(), ws.data_ptr(),
-                                                   ws.numel(), self.s_mem.cuda_stream), "saeb_refine_candidates")
+                                 b - a, enc.blob.data_ptr(), enc.W_enc.data_ptr(), enc.d_in,
+                                 enc.num_latents, k, 0, -1, 0.0, None, 0, acts[a:b].data_ptr(),
+                                 idx[a:b].data_ptr(), self.status[c % nws:].data_ptr(), ws.data_ptr(),
+                                 ws.numel(), max_ctas, self.s_mem.cuda_stream), "saeb_refine_candidates")
                     if sae_out is not None:
                         engine.decode(idx[a:b], acts[a:b], self.W_dec, self.b_dec,
-                                      x=x[a:b] if sq_err is not None else None, sq_err=sq_err, out=sae_out[a:b])
+                                      x=x[a:b] if sq_err is not None else None, sq_err=sq_err, out=sae_out[a:b],
+                                      max_ctas=max_ctas)
                     ev_b[c].record(self.s_mem)
                     if done_events is not None:
                         done_events[c].record(self.s_mem)

@@ -29,7 +29,7 @@ def make_sae(d_in: int, num_latents: int, k: int, device, seed: int = 1234):
     sae.encoder_planes = 3
     sae._packed = {}
     sae._overlap = None
-    sae.overlap_chunk = 18944
+    sae.overlap_chunk = 9472
     sae.requires_grad_(False)
     return sae
 

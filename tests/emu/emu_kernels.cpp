@@ -124,15 +124,16 @@ void emu_refine_bf16(const void* x, long long T, long long ld_x, const float* W,
                      float* out_vals, long long* out_idx, int* status, int* flag_rows, const float* ext_lower,
                      const void* lo, long long ld_w, int threads) {
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
-  emu::launch({(unsigned)T}, {(unsigned)threads}, [&] {
+  // fewer CTAs than tokens: the persistent token loop of the kernels is what runs beside the GEMM on the GPU
+  emu::launch({(unsigned)((T + 1) / 2)}, {(unsigned)threads}, [&] {
     if (lo == nullptr)
       refine_kernel<__nv_bfloat16>(xb, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals,
                                    cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx, status, flag_rows,
-                                   ext_lower);
+                                   ext_lower, T);
     else
       refine_lo_kernel<__nv_bfloat16>(xb, ld_x, reinterpret_cast<const __half*>(lo), ld_w, d, N, bias, wnorm, dnorm,
                                       trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k, clamp_feature,
-                                      clamp_value, out_vals, out_idx, status, flag_rows, ext_lower);
+                                      clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, T);
   });
 }
 
@@ -221,16 +222,16 @@ void emu_scan_merge(void* bucket, int* bucket_cnt, int bucket_cap, long long F, 
 void emu_decode(const long long* idx, const float* vals, long long T, int k, const void* W, int w16, long long d,
                 long long N, const float* b_dec, float* out, const void* x, double* sq_err, int* err_flag, int scalar) {
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
-  emu::launch({(unsigned)T}, {(unsigned)DEC_THREADS}, [&] {
+  emu::launch({(unsigned)((T + 2) / 3)}, {(unsigned)DEC_THREADS}, [&] {
     if (scalar)
       decode_scalar_kernel<float, float, __nv_bfloat16>(idx, vals, k, reinterpret_cast<const float*>(W), d, N, b_dec,
-                                                         out, d, xb, d, sq_err, err_flag);
+                                                         out, d, xb, d, sq_err, err_flag, T);
     else if (w16)
       decode_kernel<__half, float, __nv_bfloat16>(idx, vals, k, reinterpret_cast<const __half*>(W), d, N, b_dec, out, d,
-                                                  xb, d, sq_err, err_flag);
+                                                  xb, d, sq_err, err_flag, T);
     else
       decode_kernel<float, float, __nv_bfloat16>(idx, vals, k, reinterpret_cast<const float*>(W), d, N, b_dec, out, d,
-                                                 xb, d, sq_err, err_flag);
+                                                 xb, d, sq_err, err_flag, T);
   });
 }
 
@@ -292,11 +293,11 @@ void emu_refine_f16(const void* x, long long T, long long ld_x, const float* W, 
   emu::launch({(unsigned)T}, {256}, [&] {
     if (lo == nullptr)
       refine_kernel<__half>(xh, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx,
-                            K2, k, -1, 0.f, out_vals, out_idx, status, flag_rows, nullptr);
+                            K2, k, -1, 0.f, out_vals, out_idx, status, flag_rows, nullptr, T);
     else
       refine_lo_kernel<__half>(xh, ld_x, reinterpret_cast<const __half*>(lo), ld_w, d, N, bias, wnorm, dnorm, trailer,
                                xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k, -1, 0.f, out_vals, out_idx, status,
-                               flag_rows, nullptr);
+                               flag_rows, nullptr, T);
   });
 }
 void emu_refine_f32(const float* x, long long T, long long ld_x, const float* W, long long d, long long N,
@@ -306,7 +307,7 @@ void emu_refine_f32(const float* x, long long T, long long ld_x, const float* W,
                     int* flag_rows) {
   emu::launch({(unsigned)T}, {256}, [&] {
     refine_kernel<float>(x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k,
-                         -1, 0.f, out_vals, out_idx, status, flag_rows, nullptr);
+                         -1, 0.f, out_vals, out_idx, status, flag_rows, nullptr, T);
   });
 }
 

@@ -1,8 +1,6 @@
-"""GPU tests of kernels that were written while no GPU was available (end of round 1) and have not run on a B200 yet.
-
-They sort last and are `xfail(strict=False)`: a pass shows up as XPASS, a failure as XFAIL -- neither can mask or
-block the verified parity tests in test_gpu_parity.py.  Once a kernel has passed here on a B200 its test moves to
-test_gpu_parity.py as a plain test."""
+"""GPU parity tests, second file: decoder backward, attribution patching, packed mode 4, the full-size scan, 16-bit
+decoder copies and the image scan.  Written at the end of round 1 without GPU access as non-strict xfail; all of them
+passed on the driver's B200 at round end (GPUTEST_r01.json: 22 xpassed), so they are plain strict tests now."""
 import os
 
 import numpy as np
@@ -13,8 +11,7 @@ import sae_oracle as O
 
 from conftest import GOLDEN
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="kernel not yet run on a GPU (written without GPU access)")]
+pytestmark = [pytest.mark.gpu]
 DEV = torch.device("cuda:0")
 
 
@@ -228,3 +225,55 @@ def test_image_scan_matches_the_per_feature_route():
         order = sorted((i for i in range(n_img) if sc[i] > 1e-5), key=lambda i: (-float(sc[i]), i))[:n_top]
         assert w[f - lo, :len(order)].tolist() == order and bool((w[f - lo, len(order):] == -1).all())
         torch.testing.assert_close(s[f - lo, :len(order)], sc[order], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("planes", [3, 4])
+def test_overlapped_forward_with_bounded_gather_grids_equals_sequential(planes):
+    """The two-stream forward (GEMM launches of chunk c+1 beside persistent, bounded gather grids of chunk c) must give
+    bit-identical TopK / reconstruction / residual to the one-stream path, and both must match the oracle."""
+    from saeb200 import engine, synth
+    from saeb200.overlap import OverlappedForward
+
+    T, d, N, k = 2000, 1024, 16384, 32
+    sae = synth.make_sae(d, N, k, DEV, seed=11)
+    sae.encoder_planes = planes
+    enc = sae.packed_encoder()
+    x = synth.make_activations(T, d, DEV, seed=12)
+    a0, i0, _ = engine.encode_topk(x, enc, k)
+    sq0 = torch.zeros((), dtype=torch.float64, device=DEV)
+    o0 = engine.decode(i0, a0, sae.W_dec.data, sae.b_dec.data, x=x, sq_err=sq0)
+    for chunk, cps in ((512, 1), (768, 2), (4096, 1)):
+        ov = OverlappedForward(enc, sae.W_dec.data, sae.b_dec.data, k, chunk=chunk, ctas_per_sm=cps)
+        a1 = torch.empty_like(a0); i1 = torch.empty_like(i0); o1 = torch.empty_like(o0)
+        sq1 = torch.zeros((), dtype=torch.float64, device=DEV)
+        ov.run(x, a1, i1, o1, sq1)
+        torch.cuda.synchronize()
+        assert torch.equal(a1, a0) and torch.equal(i1, i0) and torch.equal(o1, o0)
+        assert abs(float(sq1) - float(sq0)) <= 1e-9 * abs(float(sq0))
+        assert int(ov.status.sum().item()) == 0
+    p = O.SaeParams(sae.encoder.weight.data.cpu(), sae.encoder.bias.data.cpu(), sae.W_dec.data.cpu(),
+                    sae.b_dec.data.cpu(), k)
+    ref = O.forward(p, x[:256].float().cpu())
+    gi, gv = O.canonical_topk(a0[:256].cpu(), i0[:256].cpu())
+    ri, rv = O.canonical_topk(ref.latent_acts, ref.latent_indices)
+    assert np.array_equal(gi, ri)
+    np.testing.assert_allclose(gv, rv, rtol=1e-3, atol=1e-5)
+
+
+def test_decode_persistent_grid_equals_one_cta_per_token():
+    from saeb200 import engine
+
+    gen = torch.Generator().manual_seed(5)
+    T, d, N, k = 333, 512, 4096, 24
+    W = torch.randn(N, d, generator=gen).to(DEV)
+    b = torch.randn(d, generator=gen).to(DEV)
+    idx = torch.stack([torch.randperm(N, generator=gen)[:k] for _ in range(T)]).to(DEV)
+    vals = torch.rand(T, k, generator=gen).to(DEV)
+    x = torch.randn(T, d, generator=gen).to(DEV).to(torch.bfloat16)
+    sq0 = torch.zeros((), dtype=torch.float64, device=DEV)
+    o0 = engine.decode(idx, vals, W, b, x=x, sq_err=sq0)
+    for mc in (1, 7, 148, 1000):
+        sq1 = torch.zeros((), dtype=torch.float64, device=DEV)
+        o1 = engine.decode(idx, vals, W, b, x=x, sq_err=sq1, max_ctas=mc)
+        assert torch.equal(o0, o1)
+        assert abs(float(sq1) - float(sq0)) <= 1e-12 * abs(float(sq0))

@@ -1,0 +1,178 @@
+"""Round-2 probe: does the HBM-bound half of the forward (refine + decode) really run INSIDE the tensor-core-bound GEMM
+launches?  Each experiment runs in its own process (timeout) and prints one RESULT line; results -> gpurun_out/.
+
+    python tools/probe_overlap.py [exp ...]
+"""
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "multimodal-sae_b200"))
+
+T, D, N, K = 65536, 4096, 131072, 64
+
+
+def _common(stages=0, planes=3):
+    import torch
+    from saeb200 import _capi, engine, synth
+    L = _capi.lib()
+    _capi.check(L.saeb_set_option(b"gemm_stages", stages), "set_option")
+    sae = synth.make_sae(D, N, K, "cuda", seed=1234)
+    sae.encoder_planes = planes
+    enc = sae.packed_encoder()
+    x = synth.make_activations(T, D, "cuda", seed=3)
+    return torch, _capi, engine, L, sae, enc, x
+
+
+def _time(torch, fn, iters=3, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ms.append(round(e0.elapsed_time(e1), 3))
+    return ms
+
+
+def exp_forward(overlap=True, chunk=9472, ctas_per_sm=1, priority="gemm", stages=0, planes=3, check=True):
+    torch, _capi, engine, L, sae, enc, x = _common(stages, planes)
+    from saeb200.overlap import OverlappedForward
+    acts = torch.empty((T, K), dtype=torch.float32, device="cuda")
+    idx = torch.empty((T, K), dtype=torch.int64, device="cuda")
+    out = torch.empty((T, D), dtype=torch.float32, device="cuda")
+    sq = torch.zeros((), dtype=torch.float64, device="cuda")
+    ov = OverlappedForward(enc, sae.W_dec.data, sae.b_dec.data, K, chunk=chunk, ctas_per_sm=ctas_per_sm,
+                           priority=priority) if overlap else None
+
+    def step():
+        sq.zero_()
+        if ov is not None:
+            ov.run(x, acts, idx, out, sq)
+        else:
+            engine.encode_topk(x, enc, K, out_vals=acts, out_idx=idx)
+            engine.decode(idx, acts, sae.W_dec.data, sae.b_dec.data, x=x, sq_err=sq, out=out)
+    ms = _time(torch, step)
+    res = dict(ms=ms, tokens_per_s=round(T / (min(ms) * 1e-3)), path_tflops=round(T / (min(ms) * 1e-3) * 1.0743e9 / 1e12, 1))
+    if check and ov is not None:
+        n = 20000
+        a2, i2, _ = engine.encode_topk(x[:n], enc, K)
+        o2 = engine.decode(i2, a2, sae.W_dec.data, sae.b_dec.data)
+        res["equals_sequential"] = bool(torch.equal(a2, acts[:n]) and torch.equal(i2, idx[:n]) and torch.equal(o2, out[:n]))
+        res["flagged"] = int(ov.status.sum().item())
+    return res
+
+
+def exp_parts(stages=0, max_ctas=0, chunk=9472):
+    """GEMM launches alone, gathers alone (bounded grid or not), and both at once WITHOUT data dependencies (the
+    gathers work on the candidate lists of a previous pass): separates scheduling / co-residency from pipeline logic"""
+    torch, _capi, engine, L, sae, enc, x = _common(stages)
+    check = _capi.check
+    n_chunks = (T + chunk - 1) // chunk
+    prep = torch.empty(L.saeb_prep_bytes(T, D), dtype=torch.uint8, device="cuda")
+    wsb = L.saeb_candidates_workspace_bytes(chunk, D, N, K, 0)
+    ws_a = [torch.empty(wsb, dtype=torch.uint8, device="cuda") for _ in range(n_chunks)]   # read by the gathers
+    ws_b = [torch.empty(wsb, dtype=torch.uint8, device="cuda") for _ in range(2)]          # written by the timed GEMMs
+    acts = torch.empty((T, K), dtype=torch.float32, device="cuda")
+    idx = torch.empty((T, K), dtype=torch.int64, device="cuda")
+    out = torch.empty((T, D), dtype=torch.float32, device="cuda")
+    sq = torch.zeros((), dtype=torch.float64, device="cuda")
+    status = torch.zeros(4, dtype=torch.int32, device="cuda")
+    s_g = torch.cuda.Stream(priority=-1)
+    s_m = torch.cuda.Stream(priority=0)
+    code = engine._code(x)
+    check(L.saeb_prep_activations(x.data_ptr(), code, T, D, D, prep.data_ptr(), torch.cuda.current_stream().cuda_stream), "prep")
+
+    def gemm(c, ws, st):
+        a, b = c * chunk, min(T, (c + 1) * chunk)
+        check(L.saeb_encode_candidates(prep.data_ptr(), T, a, b - a, enc.blob.data_ptr(), D, N, K, 0, -1, 0.0,
+                                       ws.data_ptr(), ws.numel(), st.cuda_stream), "gemm")
+
+    def gather(c, ws, st, mc):
+        a, b = c * chunk, min(T, (c + 1) * chunk)
+        with torch.cuda.stream(st):
+            check(L.saeb_refine_candidates(x.data_ptr() + a * D * 2, code, D, prep.data_ptr(), T, a, b - a,
+                                           enc.blob.data_ptr(), enc.W_enc.data_ptr(), D, N, K, 0, -1, 0.0, None, 0,
+                                           acts[a:b].data_ptr(), idx[a:b].data_ptr(), status.data_ptr(), ws.data_ptr(),
+                                           ws.numel(), mc, st.cuda_stream), "refine")
+            engine.decode(idx[a:b], acts[a:b], sae.W_dec.data, sae.b_dec.data, x=x[a:b], sq_err=sq, out=out[a:b],
+                          max_ctas=mc)
+
+    main = torch.cuda.current_stream()
+    for c in range(n_chunks):   # candidate lists for the gathers
+        gemm(c, ws_a[c], main)
+    torch.cuda.synchronize()
+
+    def only_gemm():
+        s_g.wait_stream(main)
+        for c in range(n_chunks):
+            gemm(c, ws_b[c & 1], s_g)
+        main.wait_stream(s_g)
+
+    def only_gather():
+        s_m.wait_stream(main)
+        for c in range(n_chunks):
+            gather(c, ws_a[c], s_m, max_ctas)
+        main.wait_stream(s_m)
+
+    def both():
+        s_g.wait_stream(main)
+        s_m.wait_stream(main)
+        for c in range(n_chunks):
+            gemm(c, ws_b[c & 1], s_g)
+            gather(c, ws_a[c], s_m, max_ctas)
+        main.wait_stream(s_g)
+        main.wait_stream(s_m)
+
+    r = dict(gemm_ms=_time(torch, only_gemm), gather_ms=_time(torch, only_gather), both_ms=_time(torch, both))
+    r["sum_ms"] = round(min(r["gemm_ms"]) + min(r["gather_ms"]), 2)
+    r["overlap_gain"] = round(1.0 - min(r["both_ms"]) / r["sum_ms"], 3)
+    return r
+
+
+EXPS = {
+    "seq": lambda: exp_forward(overlap=False),
+    "ov_r1": lambda: exp_forward(chunk=18944, ctas_per_sm=0, priority="mem"),
+    "ov_c0_pgemm": lambda: exp_forward(chunk=18944, ctas_per_sm=0, priority="gemm"),
+    "ov1": lambda: exp_forward(ctas_per_sm=1),
+    "ov1_c18944": lambda: exp_forward(chunk=18944, ctas_per_sm=1),
+    "ov1_pnone": lambda: exp_forward(ctas_per_sm=1, priority="none"),
+    "ov1_s5": lambda: exp_forward(ctas_per_sm=1, stages=5),
+    "ov2_s5": lambda: exp_forward(ctas_per_sm=2, stages=5),
+    "ov3_s5": lambda: exp_forward(ctas_per_sm=3, stages=5),
+    "ov2_s5_c18944": lambda: exp_forward(chunk=18944, ctas_per_sm=2, stages=5),
+    "ov4_s4": lambda: exp_forward(ctas_per_sm=4, stages=4),
+    "ov2_s5_m4": lambda: exp_forward(ctas_per_sm=2, stages=5, planes=4),
+    "parts_s6_full": lambda: exp_parts(0, 0),
+    "parts_s6_c1": lambda: exp_parts(0, 148),
+    "parts_s5_c1": lambda: exp_parts(5, 148),
+    "parts_s5_c2": lambda: exp_parts(5, 296),
+    "parts_s5_c3": lambda: exp_parts(5, 444),
+    "parts_s4_c4": lambda: exp_parts(4, 592),
+}
+
+if __name__ == "__main__":
+    if len(sys.argv) >= 3 and sys.argv[1] == "--child":
+        name = sys.argv[2]
+        t = time.time()
+        res = EXPS[name]()
+        res["wall_s"] = round(time.time() - t, 2)
+        print("RESULT " + json.dumps({name: res}))
+        sys.exit(0)
+    names = sys.argv[1:] or list(EXPS)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    log = open(os.path.join(ROOT, "gpurun_out", "probe_overlap.log"), "a")
+    for n in names:
+        try:
+            r = subprocess.run([sys.executable, __file__, "--child", n], capture_output=True, text=True, timeout=200)
+            lines = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+            msg = lines[-1] if lines else f"FAIL {n} rc={r.returncode}\n--stdout--\n{r.stdout[-1500:]}\n--stderr--\n{r.stderr[-2500:]}"
+        except subprocess.TimeoutExpired as e:
+            msg = f"TIMEOUT {n}\n{(e.stdout or b'')[-1000:]}\n{(e.stderr or b'')[-1000:]}"
+        print(msg, flush=True)
+        log.write(msg + "\n")
+        log.flush()
