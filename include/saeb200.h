@@ -51,7 +51,7 @@ float saeb_profile_last_encode_ms(void);
 /* Diagnostics (option "stats" = 1 zeroes and enables device cycle counters of the fused encode kernel): host array of 8
  * counters summed over CTA pairs = {producer waiting for a free smem stage, MMA issuer waiting for a free TMEM stage,
  * MMA issuer waiting for TMA data, epilogue warp waiting for an accumulator, epilogue compaction time, kernel time,
- * number of CTA pairs summed, 0}.  Synchronises. */
+ * number of CTA pairs summed, rows gathered by the refinement kernels since the option was set}.  Synchronises. */
 int saeb_debug_stats(unsigned long long* out8);
 /* Device facts used by the launch heuristics: "num_sms", "l2_bytes", "persisting_l2_max_bytes",
  * "access_policy_max_window_bytes", "persisting_l2_in_use_bytes"; < 0 if unknown. */
@@ -100,7 +100,7 @@ size_t saeb_encode_topk_refine_workspace_bytes(int64_t T, int64_t d, int64_t N, 
 int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed,
                             const float* W_enc, int64_t d, int64_t N, int k, int margin, int64_t clamp_feature,
                             float clamp_value, float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
-                            size_t workspace_bytes, void* stream);
+                            size_t workspace_bytes, int value_mode, void* stream);
 
 /* The stages of saeb_encode_topk_refine as separate calls, so that a caller can run the tensor-core-bound GEMM of the
  * next token chunk concurrently (on another stream) with the HBM-bound refinement and decode of the previous one:
@@ -121,8 +121,16 @@ int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void*
                            int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N, int k, int margin,
                            int64_t clamp_feature, float clamp_value, const float* ext_lower, int already_merged,
                            float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
-                           size_t workspace_bytes, int max_ctas, void* stream);
-/* max_ctas (saeb_refine_candidates[_lo], saeb_decode): 0 = one CTA per token.  > 0 = a persistent grid of at most that
+                           size_t workspace_bytes, int max_ctas, int value_mode, void* stream);
+/* value_mode (saeb_encode_topk_refine, saeb_refine_candidates[_lo]): which outputs are re-evaluated exactly.
+ *   0  every member of the TopK carries its exact fp32 value (reference grade, ~3e-7 relative);
+ *   1  "boundary only": the index SET is still decided rigorously -- every candidate whose error interval
+ *      [a_j - eps_j, a_j + eps_j] straddles the k-th boundary is re-evaluated exactly -- but members that are in the
+ *      TopK whatever their exact value keep the tensor-core value a_j (W_enc rounded to fp16: |a_j - exact| <= eps_j
+ *      rigorously, ~5e-5 relative in practice at d = 4096; a member whose bound exceeds 2^-7 of its value is
+ *      re-evaluated too).  About 10 instead of 70 gathered rows per token at k = 64, N = 131072.  Ignored (treated as
+ *      0) for feature-sharded calls (ext_lower != NULL).
+ * max_ctas (saeb_refine_candidates[_lo], saeb_decode): 0 = one CTA per token.  > 0 = a persistent grid of at most that
  * many CTAs walks the tokens, and every helper launch of the call uses blocks small enough (<= 256 threads, <= 21 KB
  * of shared memory) to be scheduled on an SM that already hosts a CTA of the fused GEMM: with max_ctas = (1..2) x
  * number of SMs the HBM-bound gathers of chunk c run INSIDE the tensor-core-bound GEMM launches of chunk c+1 instead
@@ -139,7 +147,7 @@ int saeb_refine_candidates_lo(const void* x, int x_dtype, int64_t ld_x, const vo
                               int64_t Tc, const void* packed4, const float* W_enc, int64_t d, int64_t N, int k,
                               int margin, int64_t clamp_feature, float clamp_value, const float* ext_lower,
                               int already_merged, float* out_vals, int64_t* out_idx, int32_t* status_out,
-                              void* workspace, size_t workspace_bytes, int max_ctas, void* stream);
+                              void* workspace, size_t workspace_bytes, int max_ctas, int value_mode, void* stream);
 /* Feature-sharded use (every GPU holds N/R features, sees all tokens): after saeb_encode_candidates,
  * saeb_candidate_bounds merges this shard's candidates and writes, per token, its k largest LOWER bounds
  * a_j - eps_j (descending, lb_out [Tc,k]).  All-gather them, take the per-token k-th largest (saeb_kth_of_gathered):

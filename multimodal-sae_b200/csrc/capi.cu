@@ -49,7 +49,7 @@ int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const
                   const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                   float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
                   float* dense_scratch, const float* ext_lower, const void* w_lo, long long ld_w, int max_ctas,
-                  cudaStream_t stream);
+                  int value_mode, cudaStream_t stream);
 int pack_weights_lo_launch(const float* W_enc, long long N, long long d, long long d_pad, const float* trailer,
                            void* lo_plane, cudaStream_t stream);
 int candidate_bounds_launch(const float* cand_vals, const long long* cand_idx, long long T, int K2, int k,
@@ -414,10 +414,12 @@ static int refine_candidates_impl(bool lo, const void* x, int x_dtype, int64_t l
                                   int64_t t0, int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N,
                                   int k, int margin, int64_t clamp_feature, float clamp_value, const float* ext_lower,
                                   int already_merged, float* out_vals, int64_t* out_idx, int32_t* status_out,
-                                  void* workspace, size_t workspace_bytes, int max_ctas, void* stream) {
+                                  void* workspace, size_t workspace_bytes, int max_ctas, int value_mode,
+                                  void* stream) {
   g_err[0] = 0;
   SAEB_REQUIRE(x && prep && packed && W_enc && out_vals && out_idx && workspace, "refine_candidates: null pointer");
   SAEB_REQUIRE(max_ctas >= 0, "refine_candidates: max_ctas must be >= 0");
+  SAEB_REQUIRE(value_mode == 0 || value_mode == 1, "refine_candidates: value_mode must be 0 (exact values) or 1");
   SAEB_REQUIRE(t0 >= 0 && Tc >= 0 && t0 + Tc <= T_total, "refine_candidates: bad row range");
   if (Tc == 0) return 0;
   const int K2raw = refine_k2(k, margin);
@@ -447,7 +449,7 @@ static int refine_candidates_impl(bool lo, const void* x, int x_dtype, int64_t l
                      reinterpret_cast<const float*>(pb + p.xdnorm) + t0, refine_c_eps(x_dtype), mvals, midx, K2,
                      k < K2 ? k : K2, clamp_feature, clamp_value, out_vals, reinterpret_cast<long long*>(out_idx), status,
                      reinterpret_cast<int*>(ws + w.flag_rows), reinterpret_cast<float*>(ws + w.dense), ext_lower,
-                     lo ? pk + mode3_bytes(N, d) : nullptr, pad8(d), max_ctas, st);
+                     lo ? pk + mode3_bytes(N, d) : nullptr, pad8(d), max_ctas, value_mode, st);
   if (rc) return rc;
   if (status_out != nullptr)
     SAEB_CHECK_CUDA(cudaMemcpyAsync(status_out, status, sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -459,20 +461,20 @@ int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void*
                            int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N, int k, int margin,
                            int64_t clamp_feature, float clamp_value, const float* ext_lower, int already_merged,
                            float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
-                           size_t workspace_bytes, int max_ctas, void* stream) {
+                           size_t workspace_bytes, int max_ctas, int value_mode, void* stream) {
   return refine_candidates_impl(false, x, x_dtype, ld_x, prep, T_total, t0, Tc, packed, W_enc, d, N, k, margin,
                                 clamp_feature, clamp_value, ext_lower, already_merged, out_vals, out_idx, status_out,
-                                workspace, workspace_bytes, max_ctas, stream);
+                                workspace, workspace_bytes, max_ctas, value_mode, stream);
 }
 
 int saeb_refine_candidates_lo(const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total, int64_t t0,
                               int64_t Tc, const void* packed4, const float* W_enc, int64_t d, int64_t N, int k,
                               int margin, int64_t clamp_feature, float clamp_value, const float* ext_lower,
                               int already_merged, float* out_vals, int64_t* out_idx, int32_t* status_out,
-                              void* workspace, size_t workspace_bytes, int max_ctas, void* stream) {
+                              void* workspace, size_t workspace_bytes, int max_ctas, int value_mode, void* stream) {
   return refine_candidates_impl(true, x, x_dtype, ld_x, prep, T_total, t0, Tc, packed4, W_enc, d, N, k, margin,
                                 clamp_feature, clamp_value, ext_lower, already_merged, out_vals, out_idx, status_out,
-                                workspace, workspace_bytes, max_ctas, stream);
+                                workspace, workspace_bytes, max_ctas, value_mode, stream);
 }
 
 size_t saeb_encode_topk_refine_workspace_bytes(int64_t T, int64_t d, int64_t N, int k, int margin) {
@@ -482,7 +484,7 @@ size_t saeb_encode_topk_refine_workspace_bytes(int64_t T, int64_t d, int64_t N, 
 int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x, const void* packed,
                             const float* W_enc, int64_t d, int64_t N, int k, int margin, int64_t clamp_feature,
                             float clamp_value, float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
-                            size_t workspace_bytes, void* stream) {
+                            size_t workspace_bytes, int value_mode, void* stream) {
   g_err[0] = 0;
   SAEB_REQUIRE(workspace != nullptr, "encode_topk_refine: null workspace");
   if (T == 0) return 0;
@@ -497,7 +499,7 @@ int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x,
   if (rc) return rc;
   return saeb_refine_candidates(x, x_dtype, ld_x, ws, T, 0, T, packed, W_enc, d, N, k, margin, clamp_feature,
                                 clamp_value, nullptr, 0, out_vals, out_idx, status_out, ws + prep_bytes,
-                                workspace_bytes - prep_bytes, 0, stream);
+                                workspace_bytes - prep_bytes, 0, value_mode, stream);
 }
 
 int saeb_dense_topk(const float* dense, int64_t T, int64_t ld, int64_t N, int k, float* out_vals, int64_t* out_idx,

@@ -434,6 +434,7 @@ int set_stats(int v) {
   }
   return 0;
 }
+unsigned long long* stats_ptr() { return g_stats; }
 int read_stats(unsigned long long* out8) {
   if (!g_stats) return -1;
   return cudaMemcpy(out8, g_stats, 64, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;

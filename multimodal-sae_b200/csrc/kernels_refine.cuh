@@ -24,7 +24,7 @@ refine_body(const XT* __restrict__ x, long long ld_x, const float* __restrict__ 
             const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
             float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
             int* __restrict__ flag_rows, const float* __restrict__ ext_lower, const __half* __restrict__ Wlo,
-            long long ld_w, long long T) {
+            long long ld_w, long long T, unsigned long long* __restrict__ stats, int value_mode) {
   extern __shared__ float rsm[];
   float* xs = rsm;                                   // [d4] activations of this row as fp32
   const int d4 = LO ? (int)((d + 7) & ~7ll) : (int)((d + 3) & ~3ll);   // LO: padded like the packed weight rows
@@ -33,8 +33,9 @@ refine_body(const XT* __restrict__ x, long long ld_x, const float* __restrict__ 
   float* ub = lb + K2;                               // [K2]
   float* ex = ub + K2;                               // [K2] exact values (or -1)
   int* f = reinterpret_cast<int*>(ex + K2);          // [K2] feature ids
-  __shared__ float s_L;
-  __shared__ int s_cnt[2];
+  int* st = f + K2;                                  // [K2] boundary-only mode: 1 = certainly in the TopK, 2 = evaluate
+  __shared__ float s_L, s_U;
+  __shared__ int s_cnt[4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
   // one token per CTA when gridDim.x >= T; a smaller (persistent) grid walks the tokens with stride gridDim.x so that
   // a fixed number of CTAs per SM can ride beside the persistent GEMM grid
@@ -58,6 +59,9 @@ refine_body(const XT* __restrict__ x, long long ld_x, const float* __restrict__ 
     s_L = 0.f;
     s_cnt[0] = 0;
     s_cnt[1] = 0;
+    s_cnt[2] = 0;
+    s_cnt[3] = 0;
+    s_U = 0.f;
   }
   __syncthreads();
   // L = k-th largest lower bound (0 if fewer than k positive candidates exist)
@@ -156,9 +160,77 @@ refine_body(const XT* __restrict__ x, long long ld_x, const float* __restrict__ 
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       val = acc + bias[fj];
     }
-    if (lane == 0) ex[j] = (val > 0.f) ? val : -1.f;
+    if (lane == 0) {
+      ex[j] = (val > 0.f) ? val : -1.f;
+      if (stats != nullptr) atomicAdd(&s_cnt[2], 1);   // diagnostics: rows gathered (saeb_debug_stats slot 7)
+    }
   };
   const int nwarps = nthr >> 5;
+  // value_mode 1 ("boundary only", unsharded calls): exact values are only needed where they decide the index SET.
+  //   U = (k+1)-th largest upper bound: at most k candidates lie above it, so a candidate with a_j - eps_j > U is in
+  //   the true TopK whatever the exact values are (non-candidates lie below L <= U unless the row is flagged);
+  //   candidates with a_j + eps_j < L are out; only the ones in between are gathered and re-evaluated, and the best
+  //   (k - #certain) of them complete the set.  Certain members keep the tensor-core value a_j (|a_j - exact| <= eps_j
+  //   rigorously; a member whose bound is looser than 2^-7 of its value is re-evaluated as well).
+  const bool boundary_only = value_mode == 1 && ext_lower == nullptr;
+  if (boundary_only) {
+    for (int j = tid; j < K2; j += nthr) {
+      if (a[j] > 0.f) {
+        int rank = 0;
+        const float u = ub[j];
+        for (int i = 0; i < K2; ++i) rank += (ub[i] > u || (ub[i] == u && i < j)) ? 1 : 0;
+        if (rank == k) s_U = u;
+      }
+    }
+    __syncthreads();
+    const float U = (nv > k) ? s_U : 0.f;
+    int my_in = 0;
+    for (int j = tid; j < K2; j += nthr) {
+      int c = 0;
+      if (a[j] > 0.f) {
+        const float l = lb[j], eps = 0.5f * (ub[j] - l);
+        if (l > U && l > 0.f && eps <= a[j] * 0.0078125f) {
+          c = 1;
+          ex[j] = a[j];
+          ++my_in;
+        } else if (ub[j] >= L) {
+          c = 2;
+        }
+      }
+      st[j] = c;
+    }
+    if (my_in) atomicAdd(&s_cnt[3], my_in);
+    if (tid == 0 && nv == K2) {   // list possibly too short?  (same test as below)
+      const float a_last = a[K2 - 1];
+      if (a_last + 1.001f * (xn * dmax + xdn * wmax) + c_eps * xn * wmax >= L) {
+        const int slot = atomicAdd(&status[0], 1);
+        flag_rows[slot] = (int)t;
+      }
+    }
+    __syncthreads();
+    for (int j = warp; j < K2; j += nwarps)
+      if (st[j] == 2) evaluate(j);
+    __syncthreads();
+    // keep the best (k - #certain) evaluated candidates, drop the rest: afterwards exactly the members of the TopK are
+    // positive in ex[] and the common final pass only has to order them
+    const int need = k - s_cnt[3];
+    int* drop = reinterpret_cast<int*>(lb);   // the bounds are not needed any more
+    for (int j = tid; j < K2; j += nthr) {
+      int dr = 0;
+      if (st[j] == 2 && ex[j] > 0.f) {
+        const float v = ex[j];
+        const int fj = f[j];
+        int rank = 0;
+        for (int i = 0; i < K2; ++i) rank += (st[i] == 2 && (ex[i] > v || (ex[i] == v && f[i] < fj))) ? 1 : 0;
+        dr = rank >= need;
+      }
+      drop[j] = dr;
+    }
+    __syncthreads();
+    for (int j = tid; j < K2; j += nthr)
+      if (drop[j]) ex[j] = -1.f;
+    __syncthreads();
+  } else {
   // stage A: the k best candidates by approximate value (the merged list is sorted by a, descending)
   for (int j = warp; j < k; j += nwarps)
     if (ub[j] >= L && a[j] > 0.f) evaluate(j);
@@ -186,6 +258,7 @@ refine_body(const XT* __restrict__ x, long long ld_x, const float* __restrict__ 
   for (int j = k + warp; j < K2; j += nwarps)
     if (ub[j] >= L && a[j] > 0.f) evaluate(j);
   __syncthreads();
+  }
   // final TopK over the exact values: rank by (value desc, feature id asc)
   int my_pos = 0;
   for (int j = tid; j < K2; j += nthr) {
@@ -228,6 +301,7 @@ refine_body(const XT* __restrict__ x, long long ld_x, const float* __restrict__ 
     }
   }
   __syncthreads();   // the shared row / candidate buffers are reused by the next token
+  if (stats != nullptr && tid == 0) atomicAdd(stats + 7, (unsigned long long)s_cnt[2]);
   }
 }
 
@@ -239,9 +313,11 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict_
               float c_eps, const float* __restrict__ cand_vals,
               const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
               float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
-              int* __restrict__ flag_rows, const float* __restrict__ ext_lower, long long T) {
+              int* __restrict__ flag_rows, const float* __restrict__ ext_lower, long long T,
+              unsigned long long* __restrict__ stats, int value_mode) {
   refine_body<XT, false>(x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k,
-                         clamp_feature, clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, nullptr, 0, T);
+                         clamp_feature, clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, nullptr, 0, T,
+                         stats, value_mode);
 }
 
 template <typename XT>
@@ -252,9 +328,11 @@ refine_lo_kernel(const XT* __restrict__ x, long long ld_x, const __half* __restr
                  const float* __restrict__ xdnorm, float c_eps, const float* __restrict__ cand_vals,
                  const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
                  float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
-                 int* __restrict__ flag_rows, const float* __restrict__ ext_lower, long long T) {
+                 int* __restrict__ flag_rows, const float* __restrict__ ext_lower, long long T,
+                 unsigned long long* __restrict__ stats, int value_mode) {
   refine_body<XT, true>(x, ld_x, nullptr, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx,
-                        K2, k, clamp_feature, clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, Wlo, ld_w, T);
+                        K2, k, clamp_feature, clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, Wlo, ld_w, T,
+                        stats, value_mode);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -22,6 +22,8 @@
 
 namespace saeb {
 
+unsigned long long* stats_ptr();   // encode_topk.cu: device counters of option "stats" (nullptr when off)
+
 int candidate_bounds_launch(const float* cand_vals, const long long* cand_idx, long long T, int K2, int k,
                             const float* wnorm, const float* dnorm, const float* xnorm, const float* xdnorm,
                             float c_eps, long long clamp_feature, float* lb_out, cudaStream_t stream) {
@@ -57,7 +59,7 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
                            const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                            float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
                            float* dense_scratch, const float* ext_lower, const __half* w_lo, long long ld_w,
-                           int max_ctas, cudaStream_t stream) {
+                           int max_ctas, int value_mode, cudaStream_t stream) {
   // feature-sharded calls evaluate only a handful of candidates per token: smaller blocks, more tokens in flight
   const int threads = ext_lower != nullptr ? g_refine_threads_sharded : RF_THREADS;
   // max_ctas > 0: persistent grid (tokens walked with stride gridDim.x), sized by the caller so that a fixed number of
@@ -71,7 +73,7 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
     // residual-plane correction (packed mode 4); fp32 activations are rounded on their way into the tensor cores,
     // which the residual of W cannot correct, so they always take the exact route below
     const int d8 = (int)((d + 7) & ~7ll);
-    const size_t smem = (size_t)(d8 + 5 * K2) * sizeof(float);
+    const size_t smem = (size_t)(d8 + 6 * K2) * sizeof(float);
     SAEB_REQUIRE(smem <= 200 * 1024, "refine: d=%lld too large for the shared-memory row buffer", d);
     SAEB_REQUIRE(ld_w >= d8 && (reinterpret_cast<uintptr_t>(w_lo) & 15) == 0 && ld_w % 8 == 0,
                  "refine: residual plane must be 16-byte aligned with rows padded to a multiple of 8");
@@ -79,17 +81,17 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
     SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, threads, smem, stream>>>(x, ld_x, w_lo, ld_w, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps,
                                             cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx,
-                                            status, flag_rows, ext_lower, T);
+                                            status, flag_rows, ext_lower, T, stats_ptr(), value_mode);
   }
   if (!use_lo) {
     const int d4 = (int)((d + 3) & ~3ll);
-    const size_t smem = (size_t)(d4 + 5 * K2) * sizeof(float);
+    const size_t smem = (size_t)(d4 + 6 * K2) * sizeof(float);
     SAEB_REQUIRE(smem <= 200 * 1024, "refine: d=%lld too large for the shared-memory row buffer", d);
     auto kern = refine_kernel<XT>;
     SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, threads, smem, stream>>>(x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps,
                                             cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx,
-                                            status, flag_rows, ext_lower, T);
+                                            status, flag_rows, ext_lower, T, stats_ptr(), value_mode);
   }
   SAEB_CHECK_CUDA(cudaGetLastError());
   // exact dense fallback for the (normally zero) flagged rows; the grids exit at once when nothing is flagged
@@ -123,13 +125,13 @@ int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const
                   const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                   float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
                   float* dense_scratch, const float* ext_lower, const void* w_lo, long long ld_w, int max_ctas,
-                  cudaStream_t stream) {
+                  int value_mode, cudaStream_t stream) {
 #define SAEB_RF(XT)                                                                                                  \
   return refine_launch_t<XT>(reinterpret_cast<const XT*>(x), T, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm,   \
                              xdnorm, c_eps,                                                                          \
                              cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx, status,      \
                              flag_rows, dense_scratch, ext_lower, reinterpret_cast<const __half*>(w_lo), ld_w,       \
-                             max_ctas, stream)
+                             max_ctas, value_mode, stream)
   if (x_dtype == DT_F32) SAEB_RF(float);
   if (x_dtype == DT_BF16) SAEB_RF(__nv_bfloat16);
   if (x_dtype == DT_F16) SAEB_RF(__half);

@@ -135,7 +135,7 @@ class FeatureCache:
             sae = self.submodule_dict[module_path]
             if drop_first:  # the image path drops the BOS position (reference features/cache.py:407-409)
                 hidden = hidden[:, 1:, :]
-            top_acts, top_indices = sae.encode(hidden)
+            top_acts, top_indices = sae.encode(hidden, exact_values=True)   # the cache ranks by these values
             self.cache.add_topk(top_acts, top_indices, batch_number, module_path, sae.num_latents)
 
     def run(self, n_tokens: int, tokens):

@@ -61,6 +61,10 @@ class Sae(nn.Module):
         # mode of `encode`: 3 = one fp16 tensor-core pass + exact fp32 refinement (default), 2 = bf16 hi+lo (two passes),
         # 4 = mode 3 with the refinement done by residual correction (half the gather bytes, values to ~1e-6)
         self.encoder_planes = 3
+        # which TopK values the refinement re-evaluates exactly (modes 3 / 4): "boundary" = the index set is decided
+        # rigorously, exact fp32 values only where they decide it, the other members keep the tensor-core value (fp16
+        # W_enc: ~5e-5 relative at d = 4096, inside the 1e-3 bar; ~7x fewer gathered rows); "all" = every value exact
+        self.refine_values = "boundary"
         self._packed = {}
         self._overlap = None
         self.overlap_chunk = 9472  # one wave of 37 token tiles: one GEMM launch per pipeline chunk
@@ -148,12 +152,19 @@ class Sae(nn.Module):
         built the dense tensor themselves (e.g. after editing it); the fused path is `encode`."""
         return EncoderOutput(*engine.dense_topk(latents, self.cfg.k))
 
-    def encode(self, x: Tensor, *, clamp_feature: int = -1, clamp_value: float = 0.0) -> EncoderOutput:
+    def encode(self, x: Tensor, *, clamp_feature: int = -1, clamp_value: float = 0.0,
+               exact_values: Optional[bool] = None) -> EncoderOutput:
         """Fused encoder GEMM + TopK (reference sae/sae.py:183-185).  Rows come back ordered by
-        (activation desc, index asc); the reference's order is unspecified (`sorted=False`)."""
+        (activation desc, index asc); the reference's order is unspecified (`sorted=False`).  `exact_values` overrides
+        `self.refine_values` for this call (the activation cache asks for exact values: it ranks by them)."""
         acts, idx, _ = engine.encode_topk(x, self.packed_encoder(), self.cfg.k, clamp_feature=clamp_feature,
-                                          clamp_value=clamp_value)
+                                          clamp_value=clamp_value, value_mode=self._value_mode(exact_values))
         return EncoderOutput(acts, idx)
+
+    def _value_mode(self, exact_values: Optional[bool] = None) -> int:
+        if exact_values is None:
+            exact_values = getattr(self, "refine_values", "boundary") == "all"
+        return engine.VALUES_EXACT if exact_values else engine.VALUES_BOUNDARY
 
     def decode(self, top_acts: Tensor, top_indices: Tensor) -> Tensor:
         """sum_j acts_j W_dec[idx_j] + b_dec (reference sae/sae.py:187-191)."""
@@ -174,8 +185,10 @@ class Sae(nn.Module):
             from saeb200.overlap import OverlappedForward
 
             enc = self.packed_encoder()
-            if self._overlap is None or self._overlap.enc is not enc:
-                self._overlap = OverlappedForward(enc, self.W_dec.data, self.b_dec.data, self.cfg.k, self.overlap_chunk)
+            if (self._overlap is None or self._overlap.enc is not enc
+                    or self._overlap.value_mode != self._value_mode()):
+                self._overlap = OverlappedForward(enc, self.W_dec.data, self.b_dec.data, self.cfg.k, self.overlap_chunk,
+                                                  value_mode=self._value_mode())
             xin = engine._as_2d(x2, self.d_in)
             top_acts = torch.empty((T, self.cfg.k), dtype=torch.float32, device=x.device)
             top_indices = torch.empty((T, self.cfg.k), dtype=torch.int64, device=x.device)

@@ -38,7 +38,7 @@ SIGNATURES = {
     "saeb_encode_topk_refine_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int, c_int]),
     "saeb_encode_topk_refine": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int,
                                         c_int, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
-                                        c_void_p]),
+                                        c_int, c_void_p]),
     "saeb_prep_bytes": (c_size_t, [c_int64, c_int64]),
     "saeb_prep_activations": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "saeb_candidates_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int, c_int]),
@@ -46,10 +46,10 @@ SIGNATURES = {
                                        c_int64, c_float, c_void_p, c_size_t, c_void_p]),
     "saeb_refine_candidates": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                                        c_void_p, c_int64, c_int64, c_int, c_int, c_int64, c_float, c_void_p, c_int,
-                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "saeb_refine_candidates_lo": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                                           c_void_p, c_int64, c_int64, c_int, c_int, c_int64, c_float, c_void_p, c_int,
-                                          c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "saeb_candidate_bounds": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int64, c_int64, c_int,
                                       c_int, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "saeb_dense_topk": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),

@@ -198,7 +198,7 @@ class EngineOps:
                 x2.data_ptr(), eng._code(x2), x2.stride(0) if T > 1 else enc.d_in, self._prep[slot].data_ptr(), T, 0, T,
                 enc.blob.data_ptr(), enc.W_enc.data_ptr(), enc.d_in, enc.num_latents, k, 0, -1, 0.0,
                 None if ext_L is None else ext_L.data_ptr(), 1, vals.data_ptr(), idx.data_ptr(), self.status.data_ptr(),
-                self._ws[slot].data_ptr(), self._ws[slot].numel(), int(getattr(self, "refine_max_ctas", 0)), st),
+                self._ws[slot].data_ptr(), self._ws[slot].numel(), int(getattr(self, "refine_max_ctas", 0)), 0, st),
                 "saeb_refine_candidates")
         return vals, idx + self.feat_lo
 

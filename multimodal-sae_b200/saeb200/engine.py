@@ -14,6 +14,7 @@ from ._capi import SaebError, check
 
 _DT = {torch.float32: _capi.F32, torch.bfloat16: _capi.BF16, torch.float16: _capi.F16}
 ACT_THRESHOLD = 1e-5  # reference features/cache.py:80-81
+VALUES_EXACT, VALUES_BOUNDARY = 0, 1  # `value_mode` of the refinement (include/saeb200.h)
 
 
 def _code(t: torch.Tensor) -> int:
@@ -103,10 +104,11 @@ def _as_2d(x: torch.Tensor, d: int) -> torch.Tensor:
 
 def encode_topk(x: torch.Tensor, enc: PackedEncoder, k: int, *, clamp_feature: int = -1, clamp_value: float = 0.0,
                 want_dense: bool = False, want_topk: bool = True, out_vals: Optional[torch.Tensor] = None,
-                out_idx: Optional[torch.Tensor] = None, refine_margin: int = 0
+                out_idx: Optional[torch.Tensor] = None, refine_margin: int = 0, value_mode: int = 0
                 ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
     """x [..., d] (bf16 / fp16 / fp32) -> (top_acts [..., k] f32, top_indices [..., k] i64, dense [..., N] f32 | None).
-    Rows are ordered by (value desc, index asc)."""
+    Rows are ordered by (value desc, index asc).  value_mode (refine modes 3 / 4): VALUES_EXACT = every value exact
+    fp32; VALUES_BOUNDARY = exact index set, exact values only where they decide the set (include/saeb200.h)."""
     _need_cuda(x, enc.blob)
     L = _capi.lib()
     lead = x.shape[:-1]
@@ -134,7 +136,7 @@ def encode_topk(x: torch.Tensor, enc: PackedEncoder, k: int, *, clamp_feature: i
                                             enc.blob.data_ptr(), enc.W_enc.data_ptr(), enc.d_in, enc.num_latents, k,
                                             refine_margin,
                                             clamp_feature, float(clamp_value), vals.data_ptr(), idx.data_ptr(),
-                                            status.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                                            status.data_ptr(), ws.data_ptr(), ws.numel(), int(value_mode), _stream()),
                   "saeb_encode_topk_refine")
         encode_topk.last_status = status
     elif T > 0 and enc.planes == 4:
@@ -153,7 +155,8 @@ def encode_topk(x: torch.Tensor, enc: PackedEncoder, k: int, *, clamp_feature: i
             check(L.saeb_refine_candidates_lo(x2.data_ptr(), code, ldx, prep.data_ptr(), T, 0, T, enc.blob.data_ptr(),
                                               enc.W_enc.data_ptr(), enc.d_in, enc.num_latents, k, refine_margin,
                                               clamp_feature, float(clamp_value), None, 0, vals.data_ptr(),
-                                              idx.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), 0, st),
+                                              idx.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), 0,
+                                              int(value_mode), st),
                   "saeb_refine_candidates_lo")
         encode_topk.last_status = status
     elif T > 0:

@@ -41,10 +41,12 @@ class OverlappedForward:
     N_WS = 3   # candidate workspaces in rotation: the GEMM may run two chunks ahead of the gathers
 
     def __init__(self, enc: engine.PackedEncoder, W_dec: torch.Tensor, b_dec: torch.Tensor, k: int,
-                 chunk: int = WAVE_TOKENS, ctas_per_sm: Optional[int] = None, priority: Optional[str] = None):
+                 chunk: int = WAVE_TOKENS, ctas_per_sm: Optional[int] = None, priority: Optional[str] = None,
+                 value_mode: int = engine.VALUES_EXACT):
         if enc.planes not in (3, 4):
             raise _capi.SaebError("OverlappedForward needs a refine-mode packed encoder (planes = 3 or 4)")
         self.enc, self.W_dec, self.b_dec, self.k, self.chunk = enc, W_dec, b_dec, k, chunk
+        self.value_mode = int(value_mode)
         dev = enc.blob.device
         self.dev = dev
         L = _capi.lib()
@@ -53,14 +55,24 @@ class OverlappedForward:
         # gather CTAs per SM while a GEMM launch is resident (0: one CTA per token, the round-1 behaviour)
         self.ctas_per_sm = _env_int("SAEB_OV_CTAS_PER_SM", 1) if ctas_per_sm is None else int(ctas_per_sm)
         priority = os.environ.get("SAEB_OV_PRIORITY", "gemm") if priority is None else priority
-        self.ws_bytes = L.saeb_candidates_workspace_bytes(chunk, enc.d_in, enc.num_latents, k, 0)
-        self.ws = [torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev) for _ in range(self.N_WS)]
+        self.ws_bytes, self.ws = 0, [None] * self.N_WS
+        self._reserve(chunk)
         self.prep = None
         self.status = torch.zeros(self.N_WS, dtype=torch.int32, device=dev)
         lo, hi = 0, -1   # CUDA: a numerically lower priority is the higher one
         pg, pm = {"gemm": (hi, lo), "mem": (lo, hi), "none": (lo, lo)}[priority]
         self.s_gemm = torch.cuda.Stream(dev, priority=pg)
         self.s_mem = torch.cuda.Stream(dev, priority=pm)
+
+    def _reserve(self, *chunk_rows: int) -> None:
+        """candidate workspaces large enough for every chunk size of a call (the requirement is not monotonic in the
+        row count: fewer token tiles mean more feature-range splits per tile)"""
+        L = _capi.lib()
+        enc = self.enc
+        need = max(L.saeb_candidates_workspace_bytes(r, enc.d_in, enc.num_latents, self.k, 0) for r in chunk_rows if r > 0)
+        if need > self.ws_bytes:
+            self.ws_bytes = need
+            self.ws = [torch.empty(need, dtype=torch.uint8, device=self.dev) for _ in range(self.N_WS)]
 
     def run(self, x: torch.Tensor, acts: torch.Tensor, idx: torch.Tensor, sae_out: Optional[torch.Tensor] = None,
             sq_err: Optional[torch.Tensor] = None, ready_events=None, done_events=None) -> None:
@@ -73,6 +85,7 @@ class OverlappedForward:
         refine = L.saeb_refine_candidates_lo if enc.planes == 4 else L.saeb_refine_candidates
         T = x.shape[0]
         n_chunks = (T + self.chunk - 1) // self.chunk
+        self._reserve(min(T, self.chunk), T - (n_chunks - 1) * self.chunk)
         main = torch.cuda.current_stream()
         self.s_gemm.wait_stream(main)
         self.s_mem.wait_stream(main)
@@ -114,7 +127,8 @@ class OverlappedForward:
                                  b - a, enc.blob.data_ptr(), enc.W_enc.data_ptr(), enc.d_in,
                                  enc.num_latents, k, 0, -1, 0.0, None, 0, acts[a:b].data_ptr(),
                                  idx[a:b].data_ptr(), self.status[c % nws:].data_ptr(), ws.data_ptr(),
-                                 ws.numel(), max_ctas, self.s_mem.cuda_stream), "saeb_refine_candidates")
+                                 ws.numel(), max_ctas, self.value_mode, self.s_mem.cuda_stream),
+                          "saeb_refine_candidates")
                     if sae_out is not None:
                         engine.decode(idx[a:b], acts[a:b], self.W_dec, self.b_dec,
                                       x=x[a:b] if sq_err is not None else None, sq_err=sq_err, out=sae_out[a:b],

@@ -1,6 +1,6 @@
-"""Reference-facing forward with HOST buffers: x lives in pinned host memory, TopK results and the FVU come back to
-the host.  Token chunks are double-buffered over three streams (H2D copy / compute / D2H copy) so that the PCIe
-traffic hides behind the tensor-core work."""
+"""Reference-facing forward with HOST buffers: x lives in pinned host memory, TopK results and the FVU (and, when
+asked for, the reconstruction `sae_out`) come back to the host.  Token chunks are pipelined over three streams (H2D
+copy / compute / D2H copy) so that the PCIe traffic hides behind the tensor-core work."""
 from __future__ import annotations
 
 import torch
@@ -22,16 +22,23 @@ class HostForward:
         self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.n_chunks = (num_tokens + self.chunk - 1) // self.chunk
         self.h2d_bytes = num_tokens * d * self.x_dev.element_size()
-        self.d2h_bytes = num_tokens * k * 12 + 4
+        self._d2h_topk = num_tokens * k * 12 + 4
+        self._d2h_out = num_tokens * d * 4
         self.overlap = None
         if sae.encoder_planes in (3, 4):
             from .overlap import OverlappedForward
 
-            self.overlap = OverlappedForward(sae.packed_encoder(), sae.W_dec.data, sae.b_dec.data, k, self.chunk)
+            self.overlap = OverlappedForward(sae.packed_encoder(), sae.W_dec.data, sae.b_dec.data, k, self.chunk,
+                                             value_mode=sae._value_mode())
 
-    def run(self, x_host: torch.Tensor, acts_host: torch.Tensor, idx_host: torch.Tensor) -> torch.Tensor:
-        """x_host [T, d] pinned; acts_host [T, k] f32 / idx_host [T, k] i64 pinned outputs.  Returns the pinned
-        0-dim FVU tensor (valid after the call, which synchronises)."""
+    def d2h_bytes(self, with_sae_out: bool) -> int:
+        return self._d2h_topk + (self._d2h_out if with_sae_out else 0)
+
+    def run(self, x_host: torch.Tensor, acts_host: torch.Tensor, idx_host: torch.Tensor,
+            out_host: torch.Tensor = None) -> torch.Tensor:
+        """x_host [T, d] pinned; acts_host [T, k] f32 / idx_host [T, k] i64 pinned outputs; out_host [T, d] f32 pinned
+        (optional): the reconstruction, copied back chunk by chunk on the D2H stream.  Returns the pinned 0-dim FVU
+        tensor (valid after the call, which synchronises)."""
         sae, main = self.sae, torch.cuda.current_stream()
         self.sq_err.zero_()
         ev_in = [torch.cuda.Event() for _ in range(self.n_chunks)]
@@ -60,6 +67,8 @@ class HostForward:
                 self.s_out.wait_event(ev_done[c])
                 acts_host[a:b].copy_(self.acts[a:b], non_blocking=True)
                 idx_host[a:b].copy_(self.idx[a:b], non_blocking=True)
+                if out_host is not None:
+                    out_host[a:b].copy_(self.sae_out[a:b], non_blocking=True)
         tv = engine.total_variance(self.x_dev)
         fvu = (self.sq_err / tv).to(torch.float32)
         self.fvu_host.copy_(fvu, non_blocking=True)

@@ -27,6 +27,7 @@ def make_sae(d_in: int, num_latents: int, k: int, device, seed: int = 1234):
     sae.W_dec = torch.nn.Parameter(Wd)
     sae.b_dec = torch.nn.Parameter(torch.randn(d_in, device=device, generator=g) * 0.1)
     sae.encoder_planes = 3
+    sae.refine_values = "boundary"
     sae._packed = {}
     sae._overlap = None
     sae.overlap_chunk = 9472

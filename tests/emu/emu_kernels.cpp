@@ -122,18 +122,18 @@ void emu_refine_bf16(const void* x, long long T, long long ld_x, const float* W,
                      const float* xnorm, const float* xdnorm, float c_eps, const float* cand_vals,
                      const long long* cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
                      float* out_vals, long long* out_idx, int* status, int* flag_rows, const float* ext_lower,
-                     const void* lo, long long ld_w, int threads) {
+                     const void* lo, long long ld_w, int threads, int value_mode) {
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
   // fewer CTAs than tokens: the persistent token loop of the kernels is what runs beside the GEMM on the GPU
   emu::launch({(unsigned)((T + 1) / 2)}, {(unsigned)threads}, [&] {
     if (lo == nullptr)
       refine_kernel<__nv_bfloat16>(xb, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals,
                                    cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx, status, flag_rows,
-                                   ext_lower, T);
+                                   ext_lower, T, nullptr, value_mode);
     else
       refine_lo_kernel<__nv_bfloat16>(xb, ld_x, reinterpret_cast<const __half*>(lo), ld_w, d, N, bias, wnorm, dnorm,
                                       trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k, clamp_feature,
-                                      clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, T);
+                                      clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, T, nullptr, value_mode);
   });
 }
 
@@ -293,11 +293,11 @@ void emu_refine_f16(const void* x, long long T, long long ld_x, const float* W, 
   emu::launch({(unsigned)T}, {256}, [&] {
     if (lo == nullptr)
       refine_kernel<__half>(xh, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx,
-                            K2, k, -1, 0.f, out_vals, out_idx, status, flag_rows, nullptr, T);
+                            K2, k, -1, 0.f, out_vals, out_idx, status, flag_rows, nullptr, T, nullptr, 0);
     else
       refine_lo_kernel<__half>(xh, ld_x, reinterpret_cast<const __half*>(lo), ld_w, d, N, bias, wnorm, dnorm, trailer,
                                xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k, -1, 0.f, out_vals, out_idx, status,
-                               flag_rows, nullptr, T);
+                               flag_rows, nullptr, T, nullptr, 0);
   });
 }
 void emu_refine_f32(const float* x, long long T, long long ld_x, const float* W, long long d, long long N,
@@ -307,7 +307,7 @@ void emu_refine_f32(const float* x, long long T, long long ld_x, const float* W,
                     int* flag_rows) {
   emu::launch({(unsigned)T}, {256}, [&] {
     refine_kernel<float>(x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k,
-                         -1, 0.f, out_vals, out_idx, status, flag_rows, nullptr, T);
+                         -1, 0.f, out_vals, out_idx, status, flag_rows, nullptr, T, nullptr, 0);
   });
 }
 

@@ -19,6 +19,19 @@ REL = 1e-3  # tolerance stated by the north star for floating-point outputs
 TIE_REL = 2e-5  # rows whose fp64 k/(k+1) gap is below this (x value) may pick either boundary element
 
 
+VALUES = "boundary"
+
+
+@pytest.fixture(params=["boundary", "all"], autouse=True)
+def refine_values(request):
+    """every test of this file runs in both value modes of the refinement: "boundary" (the default: rigorous index set,
+    exact values only where they decide it) and "all" (every value exact)"""
+    global VALUES
+    VALUES = request.param
+    yield request.param
+    VALUES = "boundary"
+
+
 def _sae_from_params(p: O.SaeParams, planes: int = 3):
     from sae_auto_interp.sae import Sae, SaeConfig
 
@@ -29,6 +42,7 @@ def _sae_from_params(p: O.SaeParams, planes: int = 3):
         sae.W_dec.copy_(p.W_dec)
         sae.b_dec.copy_(p.b_dec)
     sae.encoder_planes = planes
+    sae.refine_values = VALUES
     return sae
 
 

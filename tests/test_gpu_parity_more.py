@@ -277,3 +277,37 @@ def test_decode_persistent_grid_equals_one_cta_per_token():
         o1 = engine.decode(idx, vals, W, b, x=x, sq_err=sq1, max_ctas=mc)
         assert torch.equal(o0, o1)
         assert abs(float(sq1) - float(sq0)) <= 1e-12 * abs(float(sq0))
+
+
+def test_boundary_values_mode_full_width():
+    """BASELINE config 2 shape, value mode "boundary" vs "all" on the same rows: identical index sets on every row,
+    re-evaluated members bit-equal to the exact mode, the others within 1e-3 relative of it (measured ~5e-5), and
+    far fewer rows gathered."""
+    import ctypes
+
+    from saeb200 import _capi, engine, synth
+
+    L = _capi.lib()
+    sae = synth.make_sae(4096, 131072, 64, DEV, seed=1234)
+    x = synth.make_activations(4096, 4096, DEV, seed=21)
+    enc = sae.packed_encoder()
+    rows = {}
+    res = {}
+    for name, vm in (("all", engine.VALUES_EXACT), ("boundary", engine.VALUES_BOUNDARY)):
+        _capi.check(L.saeb_set_option(b"stats", 1), "stats")
+        res[name] = engine.encode_topk(x, enc, 64, value_mode=vm)[:2]
+        torch.cuda.synchronize()
+        buf = (ctypes.c_ulonglong * 8)()
+        L.saeb_debug_stats(buf)
+        rows[name] = int(buf[7]) / x.shape[0]
+        _capi.check(L.saeb_set_option(b"stats", 0), "stats")
+        assert int(engine.encode_topk.last_status.item()) == 0
+    (va, ia), (vb, ib) = res["all"], res["boundary"]
+    sa, sb = torch.sort(ia, 1), torch.sort(ib, 1)
+    assert torch.equal(sa.values, sb.values), "value mode changed a TopK index set"
+    ga, gb = torch.gather(va, 1, sa.indices), torch.gather(vb, 1, sb.indices)
+    rel = ((ga - gb).abs() / ga.abs()).max().item()
+    assert rel < 1e-3, rel
+    assert float((ga == gb).float().mean()) > 0.02          # the boundary members were re-evaluated ...
+    assert rows["boundary"] < 0.35 * rows["all"], rows       # ... and only they
+    assert bool((vb[:, :-1] >= vb[:, 1:]).all())

@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "multimodal-sae_b200"))
 
 T, D, N, K = 65536, 4096, 131072, 64
+VALUE_MODE = int(os.environ.get("PROBE_VALUE_MODE", "0"))
 
 
 def _common(stages=0, planes=3):
@@ -98,7 +99,7 @@ def exp_parts(stages=0, max_ctas=0, chunk=9472):
             check(L.saeb_refine_candidates(x.data_ptr() + a * D * 2, code, D, prep.data_ptr(), T, a, b - a,
                                            enc.blob.data_ptr(), enc.W_enc.data_ptr(), D, N, K, 0, -1, 0.0, None, 0,
                                            acts[a:b].data_ptr(), idx[a:b].data_ptr(), status.data_ptr(), ws.data_ptr(),
-                                           ws.numel(), mc, st.cuda_stream), "refine")
+                                           ws.numel(), mc, VALUE_MODE, st.cuda_stream), "refine")
             engine.decode(idx[a:b], acts[a:b], sae.W_dec.data, sae.b_dec.data, x=x[a:b], sq_err=sq, out=out[a:b],
                           max_ctas=mc)
 
@@ -134,7 +135,87 @@ def exp_parts(stages=0, max_ctas=0, chunk=9472):
     return r
 
 
+def exp_power(seconds=3.0):
+    """board power (nvidia-smi, 100 ms samples) while looping the GEMM launches alone, the gathers alone and both: is
+    the step energy-bound under the power cap?"""
+    import threading
+    torch, _capi, engine, L, sae, enc, x = _common(0)
+    check = _capi.check
+    chunk = 9472
+    n_chunks = (T + chunk - 1) // chunk
+    prep = torch.empty(L.saeb_prep_bytes(T, D), dtype=torch.uint8, device="cuda")
+    wsb = L.saeb_candidates_workspace_bytes(chunk, D, N, K, 0)
+    ws = [torch.empty(wsb, dtype=torch.uint8, device="cuda") for _ in range(n_chunks)]
+    acts = torch.empty((T, K), dtype=torch.float32, device="cuda")
+    idx = torch.empty((T, K), dtype=torch.int64, device="cuda")
+    out = torch.empty((T, D), dtype=torch.float32, device="cuda")
+    status = torch.zeros(4, dtype=torch.int32, device="cuda")
+    code = engine._code(x)
+    st = torch.cuda.current_stream()
+    check(L.saeb_prep_activations(x.data_ptr(), code, T, D, D, prep.data_ptr(), st.cuda_stream), "prep")
+
+    def gemm():
+        for c in range(n_chunks):
+            a, b = c * chunk, min(T, (c + 1) * chunk)
+            check(L.saeb_encode_candidates(prep.data_ptr(), T, a, b - a, enc.blob.data_ptr(), D, N, K, 0, -1, 0.0,
+                                           ws[c].data_ptr(), ws[c].numel(), st.cuda_stream), "gemm")
+
+    def refine(vm):
+        for c in range(n_chunks):
+            a, b = c * chunk, min(T, (c + 1) * chunk)
+            check(L.saeb_refine_candidates(x.data_ptr() + a * D * 2, code, D, prep.data_ptr(), T, a, b - a,
+                                           enc.blob.data_ptr(), enc.W_enc.data_ptr(), D, N, K, 0, -1, 0.0, None, 0,
+                                           acts[a:b].data_ptr(), idx[a:b].data_ptr(), status.data_ptr(),
+                                           ws[c].data_ptr(), ws[c].numel(), 0, vm, st.cuda_stream), "refine")
+
+    def decode():
+        engine.decode(idx, acts, sae.W_dec.data, sae.b_dec.data, out=out)
+
+    gemm(); refine(0); decode(); torch.cuda.synchronize()
+    res = {}
+    for name, fn in (("idle", None), ("gemm", gemm), ("refine_exact", lambda: refine(0)),
+                     ("refine_boundary", lambda: refine(1)), ("decode", decode)):
+        samples, stop = [], threading.Event()
+
+        def pump():
+            import subprocess as sp
+            pr = sp.Popen(["nvidia-smi", "--query-gpu=power.draw,clocks.sm", "--format=csv,noheader,nounits", "-lms", "100"],
+                          stdout=sp.PIPE, text=True)
+            for line in pr.stdout:
+                if stop.is_set():
+                    break
+                try:
+                    pw, ck = line.split(",")
+                    samples.append((time.time(), float(pw), float(ck)))
+                except Exception:
+                    pass
+            pr.terminate()
+        th = threading.Thread(target=pump, daemon=True); th.start()
+        time.sleep(0.5)
+        t0 = time.time()
+        n = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        while time.time() - t0 < seconds:
+            if fn is None:
+                time.sleep(0.1)
+            else:
+                fn(); n += 1
+                if n % 4 == 0:
+                    torch.cuda.synchronize()
+        e1.record(); torch.cuda.synchronize()
+        t1 = time.time()
+        stop.set()
+        # nvidia-smi power.draw is a ~1 s moving average: use the second half of the window
+        tail = [(p_, c_) for ts, p_, c_ in samples if t0 + 0.6 * (t1 - t0) <= ts <= t1]
+        res[name] = dict(ms_per_pass=round(e0.elapsed_time(e1) / max(n, 1), 2), passes=n,
+                         power_w=round(sum(p_ for p_, _ in tail) / max(len(tail), 1), 1),
+                         sm_mhz=round(sum(c_ for _, c_ in tail) / max(len(tail), 1)))
+    return res
+
+
 EXPS = {
+    "power": lambda: exp_power(),
     "seq": lambda: exp_forward(overlap=False),
     "ov_r1": lambda: exp_forward(chunk=18944, ctas_per_sm=0, priority="mem"),
     "ov_c0_pgemm": lambda: exp_forward(chunk=18944, ctas_per_sm=0, priority="gemm"),
