@@ -48,20 +48,20 @@ def exp_forward(overlap=True, chunk=9472, ctas_per_sm=1, priority="gemm", stages
     out = torch.empty((T, D), dtype=torch.float32, device="cuda")
     sq = torch.zeros((), dtype=torch.float64, device="cuda")
     ov = OverlappedForward(enc, sae.W_dec.data, sae.b_dec.data, K, chunk=chunk, ctas_per_sm=ctas_per_sm,
-                           priority=priority) if overlap else None
+                           priority=priority, value_mode=VALUE_MODE) if overlap else None
 
     def step():
         sq.zero_()
         if ov is not None:
             ov.run(x, acts, idx, out, sq)
         else:
-            engine.encode_topk(x, enc, K, out_vals=acts, out_idx=idx)
+            engine.encode_topk(x, enc, K, out_vals=acts, out_idx=idx, value_mode=VALUE_MODE)
             engine.decode(idx, acts, sae.W_dec.data, sae.b_dec.data, x=x, sq_err=sq, out=out)
     ms = _time(torch, step)
     res = dict(ms=ms, tokens_per_s=round(T / (min(ms) * 1e-3)), path_tflops=round(T / (min(ms) * 1e-3) * 1.0743e9 / 1e12, 1))
     if check and ov is not None:
         n = 20000
-        a2, i2, _ = engine.encode_topk(x[:n], enc, K)
+        a2, i2, _ = engine.encode_topk(x[:n], enc, K, value_mode=VALUE_MODE)
         o2 = engine.decode(i2, a2, sae.W_dec.data, sae.b_dec.data)
         res["equals_sequential"] = bool(torch.equal(a2, acts[:n]) and torch.equal(i2, idx[:n]) and torch.equal(o2, out[:n]))
         res["flagged"] = int(ov.status.sum().item())
