@@ -176,6 +176,18 @@ int saeb_decode(const int64_t* idx, const float* vals, int64_t T, int k, const v
                 int64_t N, const float* b_dec, void* out, int out_dtype, int64_t ld_out, const void* x, int x_dtype,
                 int64_t ld_x, double* sq_err, int* err_flag, int max_ctas, void* stream);
 
+/* ---- probing queries -----------------------------------------------------------------------------------------
+ * Replaces the hook body of the reference's probing tool (tools/probe_activations.py:109-126):
+ *   latents = sae.pre_acts(hidden); top = latents.mean(0).topk(k).indices; maps = latents[:, top]
+ * saeb_column_sums ADDS the column sums of a dense latent chunk [T, ld] (as written by saeb_encode_topk's dense
+ * output) to colsum [N] (double; zero it first) -- chunks of tokens can be streamed through one scratch buffer.
+ * saeb_feature_maps evaluates out[j][t] = relu((x_t - b_dec) . W_enc[features[j]] + b_enc[features[j]]) exactly in
+ * fp32 for a few selected features (out [n_features, T]); err_flag is set to 1 on an out-of-range feature id. */
+int saeb_column_sums(const float* dense, int64_t T, int64_t ld, int64_t N, double* colsum, void* stream);
+int saeb_feature_maps(const void* x, int x_dtype, int64_t T, int64_t ld_x, const float* W_enc, const float* b_enc,
+                      const float* b_dec, int64_t d, int64_t N, const int64_t* features, int n_features, float* out,
+                      int* err_flag, void* stream);
+
 /* ---- backward of the sparse decode -------------------------------------------------------------------------
  * The decoder seam is a torch.autograd.Function in the reference (TritonDecoder, sae/kernels.py:403-429); these are
  * its two backward products, fp32:

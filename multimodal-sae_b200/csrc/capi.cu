@@ -37,6 +37,8 @@ int encode_merge_launch(long long T, long long N, int k, float* out_vals, long l
 int set_chunking(int v);
 int set_reserve_sms(int v);
 int set_gemm_stages(int v);
+int set_cluster4(int v);
+long long query_max_clusters4();
 int pack_weights_f16_launch(const float* W_enc, const float* b_enc, const float* b_dec, long long N, long long d,
                             long long d_pad, void* w_plane, float* bias, float* wnorm, float* dnorm, float* trailer,
                             cudaStream_t stream);
@@ -105,6 +107,11 @@ int scan_pool_launch(const float* vals, const long long* idx, long long T, int k
 int scan_merge_launch(void* bucket, int* bucket_cnt, int bucket_cap, long long F, int n_top, float base_thr,
                       float* top_vals, long long* top_win, float* feat_thr, cudaStream_t stream);
 
+int column_sums_launch(const float* dense, long long T, long long ld, long long N, double* colsum, cudaStream_t stream);
+int feature_maps_launch(const void* x, int x_dtype, long long T, long long ld_x, const float* W, const float* b_enc,
+                        const float* b_dec, long long d, long long N, const long long* sel, int n_sel, float* out,
+                        int* err_flag, cudaStream_t stream);
+
 int set_cta_pair(int v);
 int set_profile(int v);
 float last_encode_ms();
@@ -153,6 +160,7 @@ int saeb_set_option(const char* name, int value) {
   if (strcmp(name, "chunking") == 0) return set_chunking(value);
   if (strcmp(name, "reserve_sms") == 0) return set_reserve_sms(value);
   if (strcmp(name, "gemm_stages") == 0) return set_gemm_stages(value);
+  if (strcmp(name, "cluster4") == 0) return set_cluster4(value);
   if (strcmp(name, "kth_impl") == 0) return set_kth_impl(value);
   if (strcmp(name, "refine_threads") == 0) return set_refine_threads(value);
   if (strcmp(name, "refine_margin") == 0) {
@@ -186,6 +194,7 @@ long long saeb_query(const char* name) {
     return v;
   }
   if (strcmp(name, "persisting_l2_in_use_bytes") == 0) return persist_bytes();
+  if (strcmp(name, "max_clusters4") == 0) return query_max_clusters4();
   return -1;
 }
 
@@ -615,6 +624,26 @@ int saeb_kth_largest_gathered(const float* gathered, int R, int64_t T, int m, in
   if (T == 0) return 0;
   int rc = kth_gathered_launch(gathered, R, T, m, kth, tok_thr, (cudaStream_t)stream);
   if (rc == 0) g_launches += 1;
+  return rc;
+}
+
+int saeb_column_sums(const float* dense, int64_t T, int64_t ld, int64_t N, double* colsum, void* stream) {
+  g_err[0] = 0;
+  SAEB_REQUIRE(dense && colsum, "column_sums: null pointer");
+  int rc = column_sums_launch(dense, T, ld, N, colsum, (cudaStream_t)stream);
+  if (rc == 0 && T > 0) g_launches += 1;
+  return rc;
+}
+
+int saeb_feature_maps(const void* x, int x_dtype, int64_t T, int64_t ld_x, const float* W_enc, const float* b_enc,
+                      const float* b_dec, int64_t d, int64_t N, const int64_t* features, int n_features, float* out,
+                      int* err_flag, void* stream) {
+  g_err[0] = 0;
+  SAEB_REQUIRE(x && W_enc && b_enc && b_dec && features && out, "feature_maps: null pointer");
+  int rc = feature_maps_launch(x, x_dtype, T, ld_x, W_enc, b_enc, b_dec, d, N,
+                               reinterpret_cast<const long long*>(features), n_features, out, err_flag,
+                               (cudaStream_t)stream);
+  if (rc == 0 && T > 0 && n_features > 0) g_launches += 1;
   return rc;
 }
 

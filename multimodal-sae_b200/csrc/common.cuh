@@ -158,6 +158,18 @@ __device__ __forceinline__ void tma_load_3d_pair(void* dst, const void* desc, ui
       : "memory");
 }
 
+// CTA-pair + multicast variant (clusters of two CTA pairs): the box lands at the same CTA-relative offset in every CTA of
+// `cta_mask`; each destination's transaction bytes are signalled on the barrier of ITS pair's leader (peer bit cleared).
+__device__ __forceinline__ void tma_load_3d_pair_mc(void* dst, const void* desc, uint64_t* bar, int c0, int c1, int c2,
+                                                    uint16_t cta_mask, uint64_t hint) {
+  uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      ".L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6, %7;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask), "l"(hint)
+      : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, TMEM loads
 // ---------------------------------------------------------------------------------------------
@@ -228,15 +240,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 // tcgen05.commit: make the mbarrier track completion of all prior MMAs issued by this thread.
 // PAIR==2: multicast the arrive to the barrier at the same offset in both CTAs of the pair.
 template <int PAIR>
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit(uint64_t* bar, uint16_t cta_mask = 3) {
   if constexpr (PAIR == 1) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
   } else {
+    // the arrive is multicast to the barrier at the same offset in every CTA of `cta_mask` (cluster ranks)
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
             smem_u32(bar)),
-        "h"(static_cast<uint16_t>(3))
+        "h"(cta_mask)
         : "memory");
   }
 }

@@ -70,10 +70,18 @@ struct EncodeArgs {
 // ---------------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
-template <int AP, int BP, int PAIR, int SLOTS>
+// CL = CTA pairs per cluster.  CL == 2 (clusters of four CTAs, only with PAIR == 2 and S == 2): the two pairs of a
+// cluster work on the SAME token tile, pair p on feature-range split p, so they need the same activation tile in every
+// pipeline step.  Each of the four CTAs fetches one quarter of it (64 rows) and TMA-multicasts it to its counterpart in
+// the other pair: the activation tile is read from L2 once per cluster instead of once per pair (-25 % L2 -> SM
+// traffic; the kernel runs at the L2 slices' throughput limit, not at the tensor pipe's).  A stage of the ring is
+// written into both pairs, so it is recycled only when BOTH pairs' MMAs have consumed it (empty barriers count CL
+// commits, each multicast to all four CTAs); both pairs walk the same number of feature tiles.
+template <int AP, int BP, int PAIR, int SLOTS, int CL = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const EncodeArgs args) {
+  static_assert(CL == 1 || (CL == 2 && PAIR == 2), "clusters of two pairs need the CTA-pair MMA");
   using Cfg = EncCfg<AP, BP, PAIR>;
   const int STAGES = args.stages;   // run-time ring depth: a shallower ring leaves shared memory for co-resident gather CTAs
   constexpr int CAP = 32 * SLOTS;
@@ -92,8 +100,13 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
-  const uint32_t cta_rank = (PAIR == 2) ? cluster_ctarank() : 0;
+  const uint32_t crank = (PAIR == 2) ? cluster_ctarank() : 0;   // rank in the cluster: 0 .. PAIR * CL - 1
+  const uint32_t cta_rank = crank & (PAIR - 1);                   // position in the CTA pair
+  const uint32_t pair_id = (CL == 2) ? (crank >> 1) : 0;          // which pair of the cluster
+  const uint32_t leader_rank = pair_id * 2;                       // cluster rank of this pair's leader CTA
   const bool leader = cta_rank == 0;
+  const uint16_t pair_mask = (uint16_t)(3u << (2 * pair_id));     // the two CTAs of this pair
+  const uint16_t all_mask = (CL == 2) ? (uint16_t)0xF : (uint16_t)3;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -102,7 +115,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], PAIR);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CL);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -118,9 +131,10 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr;
 
   const bool timed = args.stats != nullptr;   // cycle accounting only when diagnostics are on
-  const int cluster_id = blockIdx.x / PAIR;
-  const int num_clusters = gridDim.x / PAIR;
-  const int num_units = args.num_m_tiles * args.S;
+  const int cluster_id = blockIdx.x / (PAIR * CL);
+  const int num_clusters = gridDim.x / (PAIR * CL);
+  // CL == 1: a unit is (token tile, split), one per pair; CL == 2: a unit is a token tile, pair p takes split p (S == 2)
+  const int num_units = (CL == 2) ? args.num_m_tiles : args.num_m_tiles * args.S;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -130,7 +144,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       long long w_prod = 0;
       const long long t_begin = timed ? clock64() : 0;
       for (int u = cluster_id; u < num_units; u += num_clusters) {
-        const int split = u % args.S, m_tile = u / args.S;
+        const int split = (CL == 2) ? (int)pair_id : u % args.S, m_tile = (CL == 2) ? u : u / args.S;
         const int nt0 = (int)((long long)split * args.num_n_tiles / args.S);
         const int nt1 = (int)((long long)(split + 1) * args.num_n_tiles / args.S);
         const int m0 = (((args.dbg & 1) ? 0 : m_tile) * PAIR + (int)cta_rank) * BM;
@@ -164,10 +178,19 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 tma_load_3d(sb + b * Cfg::B_PLANE, &tm_b, &full_bar[stage], kb * BK, n0, b, args.hint_b);
             } else {
               if (leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE * 2);
-              else mbar_arrive_cluster(&full_bar[stage], 0);
+              else mbar_arrive_cluster(&full_bar[stage], leader_rank);
+              if constexpr (CL == 2) {
+                // my quarter of the activation tile (64 rows), delivered to me and to my counterpart in the other pair
+                const uint16_t mask_a = (uint16_t)((1u << cta_rank) | (1u << (2 + cta_rank)));
 #pragma unroll
-              for (int a = 0; a < AP; ++a)
-                tma_load_3d_pair(sa + a * Cfg::A_PLANE, &tm_a, &full_bar[stage], kb * BK, m0, a, args.hint_a);
+                for (int a = 0; a < AP; ++a)
+                  tma_load_3d_pair_mc(sa + a * Cfg::A_PLANE + pair_id * (Cfg::A_PLANE / 2), &tm_a, &full_bar[stage],
+                                      kb * BK, m0 + (int)pair_id * (BM / 2), a, mask_a, args.hint_a);
+              } else {
+#pragma unroll
+                for (int a = 0; a < AP; ++a)
+                  tma_load_3d_pair(sa + a * Cfg::A_PLANE, &tm_a, &full_bar[stage], kb * BK, m0, a, args.hint_a);
+              }
 #pragma unroll
               for (int b = 0; b < BP; ++b)
                 tma_load_3d_pair(sb + b * Cfg::B_PLANE, &tm_b, &full_bar[stage], kb * BK, n0, b, args.hint_b);
@@ -191,7 +214,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       uint32_t tile_iter = 0;
       long long w_tempty = 0, w_full = 0;
       for (int u = cluster_id; u < num_units; u += num_clusters) {
-        const int split = u % args.S;
+        const int split = (CL == 2) ? (int)pair_id : u % args.S;
         const int nt0 = (int)((long long)split * args.num_n_tiles / args.S);
         const int nt1 = (int)((long long)(split + 1) * args.num_n_tiles / args.S);
         for (int nt = nt0; nt < nt1; ++nt, ++tile_iter) {
@@ -224,8 +247,8 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 }
               }
             }
-            umma_commit<PAIR>(&empty_bar[stage]);
-            if (kb == args.num_k_blocks - 1) umma_commit<PAIR>(&tfull_bar[acc_stage]);
+            umma_commit<PAIR>(&empty_bar[stage], all_mask);   // frees the stage in every CTA that writes into it
+            if (kb == args.num_k_blocks - 1) umma_commit<PAIR>(&tfull_bar[acc_stage], pair_mask);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -243,7 +266,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     uint32_t tile_iter = 0;
     long long w_tfull = 0, w_compact = 0;
     for (int u = cluster_id; u < num_units; u += num_clusters) {
-      const int split = u % args.S, m_tile = u / args.S;
+      const int split = (CL == 2) ? (int)pair_id : u % args.S, m_tile = (CL == 2) ? u : u / args.S;
       const int nt0 = (int)((long long)split * args.num_n_tiles / args.S);
       const int nt1 = (int)((long long)(split + 1) * args.num_n_tiles / args.S);
       const int row = (m_tile * PAIR + (int)cta_rank) * BM + (int)(q * 32 + lane);
@@ -281,7 +304,7 @@ encode_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             __syncwarp();
             if (lane == 0) {
               if constexpr (PAIR == 1) mbar_arrive(&tempty_bar[acc_stage]);
-              else mbar_arrive_cluster(&tempty_bar[acc_stage], 0);
+              else mbar_arrive_cluster(&tempty_bar[acc_stage], leader_rank);
             }
           }
           const int col0 = n_base + c * 32;
@@ -630,11 +653,11 @@ struct PersistWindow {
 };
 static thread_local PersistWindow g_window;   // set by the launching thread just before each launch
 
-template <int AP, int BP, int PAIR, int SLOTS>
+template <int AP, int BP, int PAIR, int SLOTS, int CL = 1>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const EncodeArgs& args, int grid,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, int* max_clusters_out = nullptr) {
   using Cfg = EncCfg<AP, BP, PAIR>;
-  auto kern = encode_topk_kernel<AP, BP, PAIR, SLOTS>;
+  auto kern = encode_topk_kernel<AP, BP, PAIR, SLOTS, CL>;
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   EncodeArgs largs = args;
   largs.stages = (g_gemm_stages >= 2 && g_gemm_stages < Cfg::STAGES) ? g_gemm_stages : Cfg::STAGES;
@@ -645,11 +668,21 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const Encode
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PAIR;
+  attr[0].val.clusterDim.x = PAIR * CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (max_clusters_out != nullptr) {   // occupancy query only: how many clusters of this shape can be resident at once
+    int n = 0;
+    cfg.gridDim = dim3(PAIR * CL * 1024);
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      n = 0;
+    }
+    *max_clusters_out = n;
+    return 0;
+  }
   if (g_persist_a && g_persist_bytes > 0 && g_window.bytes > 0) {
     // the activation tiles are re-read once per feature tile: keep them in the persisting set-aside of L2
     attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
@@ -690,6 +723,38 @@ static int launch_planes(int ap, int bp, const CUtensorMap& ta, const CUtensorMa
   return -1;
 }
 
+// clusters of two CTA pairs (single-pass modes only: one activation plane, one weight plane)
+static int g_cluster4 = 1;          // 0: never, 1: when every token tile of the launch gets a resident cluster, 2: always
+static int g_max_clusters4 = -1;    // resident clusters of 4 CTAs the device offers this kernel (queried once)
+int set_cluster4(int v) {
+  if (v < 0 || v > 2) {
+    set_error("cluster4 must be 0, 1 or 2");
+    return -1;
+  }
+  g_cluster4 = v;
+  return 0;
+}
+static int max_clusters4() {
+  if (g_max_clusters4 < 0) {
+    CUtensorMap dummy_a = {}, dummy_b = {};
+    EncodeArgs dummy = {};
+    int n = 0;
+    launch_cfg<1, 1, 2, 8, 2>(dummy_a, dummy_b, dummy, 4, nullptr, &n);
+    g_max_clusters4 = n;
+  }
+  return g_max_clusters4;
+}
+long long query_max_clusters4() { return max_clusters4(); }
+static int launch_cluster4(const CUtensorMap& ta, const CUtensorMap& tb, const EncodeArgs& args, int grid, int cap,
+                           cudaStream_t stream) {
+  switch (cap) {
+    case 256: return launch_cfg<1, 1, 2, 8, 2>(ta, tb, args, grid, stream);
+    case 512: return launch_cfg<1, 1, 2, 16, 2>(ta, tb, args, grid, stream);
+  }
+  set_error("unsupported candidate capacity %d for the 4-CTA cluster kernel", cap);
+  return -1;
+}
+
 // x_planes: [ap][T][ld_x] bf16 (ap==1: the caller's bf16 activations in place)
 // w_planes: [bp][N][d] bf16; bias: folded bias [N]
 // Phase 1: the fused GEMM launches (one per row chunk) -> candidate lists in the workspace (and/or dense output)
@@ -719,8 +784,12 @@ int encode_gemm_launch(const void* x_planes, int ap, long long T, long long ld_x
   for (int ci = 0; ci < plan.n_chunks; ++ci) {
     const ChunkPlan& c = plan.chunks[ci];
     const uint8_t* xa = reinterpret_cast<const uint8_t*>(x_planes) + (size_t)c.t0 * ld_x * 2;
+    // two CTA pairs per cluster sharing the activation tile: needs S == 2 splits of equal length and (unless forced)
+    // a resident cluster for every token tile of the launch
+    const bool cl2 = pair == 2 && ap == 1 && bp == 1 && c.S == 2 && plan.num_n_tiles % 2 == 0 && plan.cap <= 512 &&
+                     g_cluster4 > 0 && g_reserve_sms == 0 && (g_cluster4 == 2 || max_clusters4() >= c.num_m_tiles);
     CUtensorMap ta;
-    rc = make_map(&ta, xa, d, c.rows, ap, ld_x * 2, x_plane_stride * 2, BM);
+    rc = make_map(&ta, xa, d, c.rows, ap, ld_x * 2, x_plane_stride * 2, cl2 ? BM / 2 : BM);
     if (rc) return rc;
     EncodeArgs args;
     args.T = (int)c.rows; args.d = (int)d; args.N = (int)N; args.k = k;
@@ -748,8 +817,13 @@ int encode_gemm_launch(const void* x_planes, int ap, long long T, long long ld_x
     g_window.base = const_cast<uint8_t*>(xa);
     g_window.bytes = (plan.n_chunks > 1 || c.rows * ld_x * 2 <= (long long)g_persist_bytes + (8 << 20))
                          ? (size_t)c.rows * (size_t)ld_x * 2 : 0;   // plane 0 of this chunk
-    rc = (pair == 2) ? launch_planes<2>(ap, bp, ta, tb, args, c.grid, plan.cap, stream)
-                     : launch_planes<1>(ap, bp, ta, tb, args, c.grid, plan.cap, stream);
+    if (cl2) {
+      int clusters = max_clusters4() > 0 && max_clusters4() < c.num_m_tiles ? max_clusters4() : c.num_m_tiles;
+      rc = launch_cluster4(ta, tb, args, clusters * 4, plan.cap, stream);
+    } else {
+      rc = (pair == 2) ? launch_planes<2>(ap, bp, ta, tb, args, c.grid, plan.cap, stream)
+                       : launch_planes<1>(ap, bp, ta, tb, args, c.grid, plan.cap, stream);
+    }
     if (rc) return rc;
   }
   if (g_profile) {

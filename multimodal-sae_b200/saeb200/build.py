@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(LIB_DIR, "libsaeb200.so")
-SOURCES = ["capi.cu", "encode_topk.cu", "decode.cu", "pack.cu", "coo_scan.cu", "refine.cu", "exchange.cu", "decode_bwd.cu"]
+SOURCES = ["capi.cu", "encode_topk.cu", "decode.cu", "pack.cu", "coo_scan.cu", "refine.cu", "exchange.cu", "decode_bwd.cu", "probe.cu"]
 # every header a translation unit may include: common helpers, the device code (kernels_*.cuh) and the C ABI
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "saeb200.h")]
 

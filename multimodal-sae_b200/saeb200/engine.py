@@ -474,3 +474,48 @@ def kth_of_gathered(gathered: torch.Tensor, kth: Optional[int] = None) -> torch.
         check(L.saeb_kth_largest_gathered(g.data_ptr(), R, T, m, kth, out.data_ptr(), _stream()),
               "saeb_kth_largest_gathered")
     return out
+
+
+def mean_activations(x: torch.Tensor, enc_dense: PackedEncoder, *, chunk_tokens: int = 2048) -> torch.Tensor:
+    """mean over tokens of the dense latents relu(W_enc (x - b_dec) + b_enc), [N] fp32 -- `sae.pre_acts(x).mean(0)` of
+    the reference's probing tool (tools/probe_activations.py:109-121) without the [T, N] tensor: token chunks go through
+    the fused GEMM's dense store into one scratch buffer and are reduced by saeb_column_sums (fp64 accumulation)."""
+    _need_cuda(x, enc_dense.blob)
+    if enc_dense.planes != 2:
+        raise SaebError("mean_activations needs the bf16 hi+lo packed encoder (planes=2): it is the one with a dense store")
+    L = _capi.lib()
+    x2 = _as_2d(x, enc_dense.d_in)
+    T, N = x2.shape[0], enc_dense.num_latents
+    colsum = torch.zeros(N, dtype=torch.float64, device=x2.device)
+    with torch.cuda.device(x2.device):
+        for t0 in range(0, T, chunk_tokens):
+            xc = x2[t0:t0 + chunk_tokens]
+            _, _, dense = encode_topk(xc, enc_dense, 1, want_dense=True, want_topk=False)
+            check(L.saeb_column_sums(dense.data_ptr(), xc.shape[0], N, N, colsum.data_ptr(), _stream()),
+                  "saeb_column_sums")
+    return (colsum / max(T, 1)).to(torch.float32)
+
+
+def feature_maps(x: torch.Tensor, W_enc: torch.Tensor, b_enc: torch.Tensor, b_dec: torch.Tensor,
+                 features: torch.Tensor) -> torch.Tensor:
+    """maps[j, t] = relu((x_t - b_dec) . W_enc[features[j]] + b_enc[features[j]]), exact fp32: the columns
+    `latents[:, features]` of the dense latents (tools/probe_activations.py:122) for a few selected features."""
+    _need_cuda(x, W_enc, b_enc, b_dec, features)
+    L = _capi.lib()
+    N, d = W_enc.shape
+    x2 = _as_2d(x, d)
+    if x2.dtype not in _DT:
+        x2 = x2.to(torch.float32)
+    T = x2.shape[0]
+    W = W_enc.detach().to(torch.float32).contiguous()
+    sel = features.to(torch.int64).contiguous()
+    out = torch.empty((sel.numel(), T), dtype=torch.float32, device=x2.device)
+    err = torch.zeros(1, dtype=torch.int32, device=x2.device)
+    with torch.cuda.device(x2.device):
+        check(L.saeb_feature_maps(x2.data_ptr(), _code(x2), T, x2.stride(0) if T > 1 else d, W.data_ptr(),
+                                  b_enc.detach().to(torch.float32).contiguous().data_ptr(),
+                                  b_dec.detach().to(torch.float32).contiguous().data_ptr(), d, N, sel.data_ptr(),
+                                  sel.numel(), out.data_ptr(), err.data_ptr(), _stream()), "saeb_feature_maps")
+    if int(err.item()) != 0:
+        raise SaebError("feature_maps: feature id out of range")
+    return out

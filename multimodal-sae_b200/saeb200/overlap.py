@@ -52,8 +52,10 @@ class OverlappedForward:
         L = _capi.lib()
         with torch.cuda.device(dev):
             self.num_sms = int(L.saeb_query(b"num_sms"))
-        # gather CTAs per SM while a GEMM launch is resident (0: one CTA per token, the round-1 behaviour)
-        self.ctas_per_sm = _env_int("SAEB_OV_CTAS_PER_SM", 1) if ctas_per_sm is None else int(ctas_per_sm)
+        # gather CTAs per SM while a GEMM launch is resident; 0 (default) = one CTA per token.  Measured (round 2): every
+        # kernel of the step runs at the board's power cap on its own, so the step is energy-bound and bounded grids
+        # buy nothing here (they pay off where a latency chain, not energy, is the critical path)
+        self.ctas_per_sm = _env_int("SAEB_OV_CTAS_PER_SM", 0) if ctas_per_sm is None else int(ctas_per_sm)
         priority = os.environ.get("SAEB_OV_PRIORITY", "gemm") if priority is None else priority
         self.ws_bytes, self.ws = 0, [None] * self.N_WS
         self._reserve(chunk)

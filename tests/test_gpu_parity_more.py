@@ -311,3 +311,36 @@ def test_boundary_values_mode_full_width():
     assert float((ga == gb).float().mean()) > 0.02          # the boundary members were re-evaluated ...
     assert rows["boundary"] < 0.35 * rows["all"], rows       # ... and only they
     assert bool((vb[:, :-1] >= vb[:, 1:]).all())
+
+
+@pytest.mark.parametrize("T,d,N,k", [(1024, 1024, 16384, 64), (700, 4096, 8192, 32), (2500, 512, 4096 + 512, 16)])
+def test_cluster_of_two_pairs_multicast_equals_pair_kernel(T, d, N, k):
+    """The 4-CTA-cluster form of the fused GEMM (two CTA pairs share the activation tile through TMA multicast) must
+    give bit-identical TopK output to the CTA-pair form, and both must match the oracle.  `splits = 2` forces the
+    two-split decomposition the cluster kernel needs on these small shapes."""
+    from saeb200 import _capi, engine, synth
+
+    L = _capi.lib()
+    sae = synth.make_sae(d, N, k, DEV, seed=31)
+    enc = sae.packed_encoder()
+    x = synth.make_activations(T, d, DEV, seed=32)
+    res = {}
+    try:
+        _capi.check(L.saeb_set_option(b"splits", 2), "splits")
+        for mode in (0, 2):
+            _capi.check(L.saeb_set_option(b"cluster4", mode), "cluster4")
+            res[mode] = engine.encode_topk(x, enc, k, value_mode=engine.VALUES_EXACT)[:2]
+            torch.cuda.synchronize()
+            assert int(engine.encode_topk.last_status.item()) == 0
+    finally:
+        L.saeb_set_option(b"splits", 0)
+        L.saeb_set_option(b"cluster4", 1)
+    assert torch.equal(res[0][0], res[2][0]) and torch.equal(res[0][1], res[2][1])
+    p = O.SaeParams(sae.encoder.weight.data.cpu(), sae.encoder.bias.data.cpu(), sae.W_dec.data.cpu(),
+                    sae.b_dec.data.cpu(), k)
+    n = min(T, 300)
+    ref = O.encode(p, x[:n].float().cpu())
+    gi, gv = O.canonical_topk(res[2][0][:n].cpu(), res[2][1][:n].cpu())
+    ri, rv = O.canonical_topk(ref.top_acts, ref.top_indices)
+    assert np.array_equal(gi, ri)
+    np.testing.assert_allclose(gv, rv, rtol=1e-3, atol=1e-5)

@@ -214,7 +214,34 @@ def exp_power(seconds=3.0):
     return res
 
 
+def exp_gemm_only(cluster4=1, stages=0):
+    """the 7 GEMM launches of a 65 536-token step alone, CTA-pair kernel vs 4-CTA clusters with activation multicast"""
+    torch, _capi, engine, L, sae, enc, x = _common(stages)
+    check = _capi.check
+    check(L.saeb_set_option(b"cluster4", cluster4), "cluster4")
+    chunk = 9472
+    n_chunks = (T + chunk - 1) // chunk
+    prep = torch.empty(L.saeb_prep_bytes(T, D), dtype=torch.uint8, device="cuda")
+    wsb = L.saeb_candidates_workspace_bytes(chunk, D, N, K, 0)
+    ws = [torch.empty(wsb, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    st = torch.cuda.current_stream()
+    check(L.saeb_prep_activations(x.data_ptr(), engine._code(x), T, D, D, prep.data_ptr(), st.cuda_stream), "prep")
+
+    def gemm():
+        for c in range(n_chunks):
+            a, b = c * chunk, min(T, (c + 1) * chunk)
+            check(L.saeb_encode_candidates(prep.data_ptr(), T, a, b - a, enc.blob.data_ptr(), D, N, K, 0, -1, 0.0,
+                                           ws[c & 1].data_ptr(), ws[c & 1].numel(), st.cuda_stream), "gemm")
+    ms = _time(torch, gemm, iters=4)
+    return dict(ms=ms, tflops=round(2.0 * T * D * N / (min(ms) * 1e-3) / 1e12, 1),
+                max_clusters4=int(L.saeb_query(b"max_clusters4")))
+
+
 EXPS = {
+    "gemm_pair": lambda: exp_gemm_only(0),
+    "gemm_cl4": lambda: exp_gemm_only(2),
+    "gemm_cl4_auto": lambda: exp_gemm_only(1),
+    "gemm_cl4_s5": lambda: exp_gemm_only(2, 5),
     "power": lambda: exp_power(),
     "seq": lambda: exp_forward(overlap=False),
     "ov_r1": lambda: exp_forward(chunk=18944, ctas_per_sm=0, priority="mem"),
