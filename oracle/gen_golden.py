@@ -344,6 +344,32 @@ def gen_steering(ref):
                         clamp=np.float32(50.0), **res)
 
 
+def gen_probe(ref):
+    """tools/probe_activations.py:109-126 -- the hook body is inline in the script's __main__ (no importable
+    function), so the fixture executes exactly those statements on the reference's own `Sae` object."""
+    d, N, k = 64, 512, 8
+    p = O.init_params(d, N, k, seed=61)
+    sae = build_ref_sae(ref.sae, p)
+    g = torch.Generator().manual_seed(62)
+    res = {}
+    with torch.no_grad():
+        for tag, T, interval, drop in (("image", 41, [0, 12], True), ("text", 23, [3, 10], False)):
+            hidden = torch.randn(1, T, d, generator=g).to(torch.float16)
+            latents = sae.pre_acts(hidden)                                   # :112
+            if drop:
+                latents = latents[:, 1:, :]                                  # :115-116
+            topk_indices = (latents.squeeze(0).mean(dim=0).topk(k=interval[1]).indices.detach().cpu())[interval[0]:]
+            topk_acts = latents[:, :, topk_indices].squeeze(0).permute(1, 0).detach().cpu()   # :122
+            res[f"{tag}_hidden"] = hidden.numpy()
+            res[f"{tag}_interval"] = np.asarray(interval, np.int64)
+            res[f"{tag}_drop"] = np.int64(drop)
+            res[f"{tag}_indices"] = topk_indices.numpy()
+            res[f"{tag}_acts"] = topk_acts.numpy()
+            res[f"{tag}_mean"] = latents.squeeze(0).mean(dim=0).numpy()
+    np.savez_compressed(os.path.join(GOLD, "probe.npz"), W_enc=p.W_enc.numpy(), b_enc=p.b_enc.numpy(),
+                        W_dec=p.W_dec.numpy(), b_dec=p.b_dec.numpy(), k=np.int64(k), **res)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -354,7 +380,7 @@ def main():
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
     if only is not None:   # regenerate one fixture without touching the others
         {"decode_backward": gen_decode_backward, "attribution": gen_attribution, "image_constructor": gen_image_constructor, "decode_test": gen_decode_test, "cache_chain": gen_cache_chain,
-         "steering": gen_steering}[only](ref)
+         "steering": gen_steering, "probe": gen_probe}[only](ref)
         return
     gen_decode_backward(ref)
     gen_attribution(ref)
@@ -365,6 +391,7 @@ def main():
     gen_decode_test(ref)
     gen_cache_chain(ref)
     gen_steering(ref)
+    gen_probe(ref)
     print("golden fixtures written to", GOLD)
 
 

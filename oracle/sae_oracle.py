@@ -326,3 +326,20 @@ def steering_hook(p: SaeParams, hidden: torch.Tensor, feature: int, clamp_value:
         latents[:, :, feature] = clamp_value
     top_acts, top_indices = select_topk(latents, p.k)
     return decode(p, top_acts[0], top_indices[0]).unsqueeze(0).to(torch.float16)
+
+
+# ---------------------------------------------------------------------------
+# probing tool (reference tools/probe_activations.py:109-126)
+# ---------------------------------------------------------------------------
+def probe_mean_topk(p: SaeParams, hidden: torch.Tensor, interval: Sequence[int], drop_first: bool = False
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The tool's hook body: `latents = sae.pre_acts(hidden)` (:112); image-only llama inputs drop the BOS position
+    `latents[:, 1:, :]` (:115-116); `topk_indices = latents.squeeze(0).mean(dim=0).topk(k=interval[1]).indices
+    [interval[0]:]` (:119-121); `topk_acts = latents[:, :, topk_indices].squeeze(0).permute(1, 0)` (:122).
+    hidden [1, T, d] -> (indices [interval[1] - interval[0]], acts [n_features, T'])."""
+    latents = pre_acts(p, hidden)
+    if drop_first:
+        latents = latents[:, 1:, :]
+    topk_indices = latents.squeeze(0).mean(dim=0).topk(k=interval[1]).indices[interval[0]:]
+    topk_acts = latents[:, :, topk_indices].squeeze(0).permute(1, 0)
+    return topk_indices, topk_acts

@@ -32,6 +32,12 @@ def refine_values(request):
     VALUES = "boundary"
 
 
+def _vtol(tight: float) -> float:
+    """value tolerance: `tight` when every value is re-evaluated exactly, the 1e-3 bar in "boundary" mode (members of
+    the TopK that were not re-evaluated carry the fp16-weight tensor-core value)"""
+    return tight if VALUES == "all" else REL
+
+
 def _sae_from_params(p: O.SaeParams, planes: int = 3):
     from sae_auto_interp.sae import Sae, SaeConfig
 
@@ -236,7 +242,7 @@ def test_duplicated_latents_exact_ties():
     ref = O.encode(p, x.float())
     gv = enc.top_acts.cpu().sort(-1, descending=True).values
     rv = ref.top_acts.sort(-1, descending=True).values
-    np.testing.assert_allclose(gv.numpy(), rv.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(gv.numpy(), rv.numpy(), rtol=_vtol(1e-5), atol=1e-6)
     # ties broken towards the smaller feature id: of a duplicated pair (j, j + 1024) the copy j is taken first
     gi = enc.top_indices.cpu()
     hi_half = gi >= 1024
@@ -250,6 +256,8 @@ def test_duplicated_latents_exact_ties():
 def test_refine_values_are_fp32_exact():
     """In refine mode the returned activations are fp32 dot products against the fp32 weights: they agree with the
     oracle to fp32 summation noise (1e-5 relative), far inside the 1e-3 bar."""
+    if VALUES != "all":
+        pytest.skip("only the exact value mode promises fp32-exact values")
     p = O.init_params(1024, 8192, 32, seed=43)
     x = torch.randn(256, 1024, generator=torch.Generator().manual_seed(44)).to(torch.bfloat16)
     sae = _sae_from_params(p, 3)
@@ -507,7 +515,7 @@ def test_full_size_properties():
     dense = sae.pre_acts(x[rows])
     dv, di = dense.topk(64)
     assert torch.equal(torch.sort(di, 1).values, srt[rows])
-    torch.testing.assert_close(dv, v[rows], rtol=1e-4, atol=1e-6)   # two independent arithmetic paths
+    torch.testing.assert_close(dv, v[rows], rtol=_vtol(1e-4), atol=1e-6)   # two independent arithmetic paths
     # decode is linear in the activations and the bias is added once
     y1 = engine.decode(i[:512], v[:512], sae.W_dec.data, sae.b_dec.data)
     y2 = engine.decode(i[:512], 2 * v[:512], sae.W_dec.data, None)

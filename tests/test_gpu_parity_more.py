@@ -87,6 +87,7 @@ def test_mode4_residual_refine_vs_oracle(T, d, N, k, xdt):
     p = O.init_params(d, N, k, seed=300 + T)
     x = torch.randn(T, d, generator=torch.Generator().manual_seed(T + 1)).to(xdt)
     sae = _sae_from_params(p, 4)
+    sae.refine_values = "all"   # every value corrected: this test pins the grade of the corrected values
     enc = sae.encode(x.to(DEV))
     _assert_topk_parity(p, x.float(), enc.top_acts, enc.top_indices)
     # tighter than the 1e-3 bar: the corrected values are fp32-GEMM grade
@@ -334,7 +335,7 @@ def test_cluster_of_two_pairs_multicast_equals_pair_kernel(T, d, N, k):
             assert int(engine.encode_topk.last_status.item()) == 0
     finally:
         L.saeb_set_option(b"splits", 0)
-        L.saeb_set_option(b"cluster4", 1)
+        L.saeb_set_option(b"cluster4", 0)
     assert torch.equal(res[0][0], res[2][0]) and torch.equal(res[0][1], res[2][1])
     p = O.SaeParams(sae.encoder.weight.data.cpu(), sae.encoder.bias.data.cpu(), sae.W_dec.data.cpu(),
                     sae.b_dec.data.cpu(), k)
@@ -344,3 +345,51 @@ def test_cluster_of_two_pairs_multicast_equals_pair_kernel(T, d, N, k):
     ri, rv = O.canonical_topk(ref.top_acts, ref.top_indices)
     assert np.array_equal(gi, ri)
     np.testing.assert_allclose(gv, rv, rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("tag", ["image", "text"])
+def test_probe_activations_matches_reference_golden(tag):
+    """mean-over-tokens top features + their activation maps (tools/probe_activations.py:109-126) through the
+    engine (dense GEMM store reduced by saeb_column_sums, maps by saeb_feature_maps) vs the reference's tensors."""
+    from sae_auto_interp.probe_activations import make_hook, probe_hidden
+    from test_gpu_parity import _params, _sae_from_params
+
+    g = np.load(os.path.join(GOLDEN, "probe.npz"))
+    sae = _sae_from_params(_params(g))
+    hidden = torch.from_numpy(g[f"{tag}_hidden"]).to(DEV)
+    interval, drop = g[f"{tag}_interval"].tolist(), bool(g[f"{tag}_drop"])
+    idx, acts = probe_hidden(sae, hidden, interval, drop_first=drop)
+    assert idx.dtype == torch.int64 and acts.shape == tuple(g[f"{tag}_acts"].shape)
+    # the feature set and its order by mean activation (descending); means closer than 1e-5 relative may swap
+    ref_idx, ref_mean = g[f"{tag}_indices"], g[f"{tag}_mean"]
+    if not np.array_equal(idx.numpy(), ref_idx):
+        assert sorted(idx.tolist()) == sorted(ref_idx.tolist())
+        for a, b in zip(idx.tolist(), ref_idx.tolist()):
+            assert abs(ref_mean[a] - ref_mean[b]) <= 1e-5 * abs(ref_mean[b])
+    order = [idx.tolist().index(f) for f in ref_idx.tolist()]
+    np.testing.assert_allclose(acts.numpy()[order], g[f"{tag}_acts"], rtol=1e-3, atol=1e-5)
+    # the same through the forward hook the tool registers
+    sink = {}
+    make_hook(sae, interval, sink, drop_first=drop)(None, None, (hidden, None))
+    assert torch.equal(sink["topk_indices"], idx) and torch.equal(sink["topk_acts"], acts)
+
+
+def test_mean_activations_streams_token_chunks():
+    """column means are accumulated chunk by chunk: any chunking gives the same means (fp64 accumulation), equal to
+    the dense tensor's own mean"""
+    from saeb200 import engine, synth
+
+    sae = synth.make_sae(256, 2048, 16, DEV, seed=71)
+    x = synth.make_activations(1000, 256, DEV, seed=72)
+    enc2 = sae.packed_encoder(2)
+    m1 = engine.mean_activations(x, enc2, chunk_tokens=4096)
+    m2 = engine.mean_activations(x, enc2, chunk_tokens=333)
+    dense = sae.pre_acts(x)
+    torch.testing.assert_close(m1, m2, rtol=1e-6, atol=1e-9)
+    torch.testing.assert_close(m1, dense.double().mean(0).float(), rtol=1e-6, atol=1e-9)
+    maps = engine.feature_maps(x, sae.encoder.weight.data, sae.encoder.bias.data, sae.b_dec.data,
+                               torch.tensor([5, 77, 2047], device=DEV))
+    torch.testing.assert_close(maps, dense[:, [5, 77, 2047]].T.contiguous(), rtol=1e-3, atol=1e-5)
+    with pytest.raises(engine.SaebError):
+        engine.feature_maps(x, sae.encoder.weight.data, sae.encoder.bias.data, sae.b_dec.data,
+                            torch.tensor([2048], device=DEV))

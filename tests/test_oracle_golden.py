@@ -166,3 +166,15 @@ def test_scan_top_windows_agrees_with_constructor_semantics():
         np.testing.assert_allclose(scores[f, :n], pooled.numpy(), rtol=1e-6)
         # ties between equal pooled values may order differently; compare as sets of windows per value
         assert sorted(wins[f, :n].tolist()) == sorted(ids[:, 1].tolist())
+
+
+@pytest.mark.parametrize("tag", ["image", "text"])
+def test_probe_mean_topk_matches_reference(tag):
+    """tools/probe_activations.py:109-126 executed on the reference's own Sae (oracle/gen_golden.py::gen_probe)."""
+    g = np.load(os.path.join(GOLDEN, "probe.npz"))
+    p = O.SaeParams(torch.from_numpy(g["W_enc"]), torch.from_numpy(g["b_enc"]), torch.from_numpy(g["W_dec"]),
+                    torch.from_numpy(g["b_dec"]), int(g["k"]))
+    idx, acts = O.probe_mean_topk(p, torch.from_numpy(g[f"{tag}_hidden"]), g[f"{tag}_interval"].tolist(),
+                                  bool(g[f"{tag}_drop"]))
+    assert np.array_equal(idx.numpy(), g[f"{tag}_indices"])
+    np.testing.assert_allclose(acts.numpy(), g[f"{tag}_acts"], rtol=1e-6, atol=1e-7)
