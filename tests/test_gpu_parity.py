@@ -91,7 +91,12 @@ def test_forward_matches_reference_golden(name, planes):
     gi, gv = O.canonical_topk(out.latent_acts.cpu(), out.latent_indices.cpu())
     assert np.array_equal(gi, g["top_idx"]), "TopK index sets differ from the reference"
     np.testing.assert_allclose(gv, g["top_val"], rtol=REL, atol=1e-6)
-    np.testing.assert_allclose(out.sae_out.cpu().numpy(), g["sae_out"], rtol=REL, atol=1e-4)
+    got, want = out.sae_out.cpu().numpy(), g["sae_out"]
+    if VALUES == "all" or planes != 3:
+        np.testing.assert_allclose(got, want, rtol=REL, atol=1e-4)
+    # 1e-3 RELATIVE per reconstructed row in every mode (in "boundary" mode members that were not re-evaluated carry
+    # ~1e-4 relative noise, which an elementwise test would hold against the near-zero elements of a row)
+    assert float((np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)).max()) < REL
     np.testing.assert_allclose(float(out.fvu), float(g["fvu"]), rtol=REL)
     assert out.latent_indices.dtype == torch.int64 and out.latent_acts.dtype == torch.float32
     v = out.latent_acts
@@ -503,6 +508,7 @@ def test_full_size_properties():
     from saeb200 import engine, synth
 
     sae = synth.make_sae(4096, 131072, 64, DEV, seed=1234)
+    sae.refine_values = VALUES
     x = synth.make_activations(65536, 4096, DEV, seed=3)
     out = sae(x)
     v, i = out.latent_acts, out.latent_indices
