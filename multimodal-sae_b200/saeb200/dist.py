@@ -73,7 +73,7 @@ class EngineOps:
     pipelined = True
 
     def __init__(self, W_enc_shard, b_enc_shard, b_dec, feat_lo, feat_hi, n_top, ctx_len, device, planes=3,
-                 bucket_cap=256):
+                 bucket_cap=256, aux_priority=None):
         from . import _capi, engine
 
         self.engine, self._capi = engine, _capi
@@ -83,9 +83,15 @@ class EngineOps:
         self._x, self._k, self._prep, self._ws = [None, None], [0, 0], [None, None], [None, None]
         self._lb, self._cached = [None, None], [None, None]
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
-        self.stream_gemm = torch.cuda.Stream(device)
-        self.stream_aux = torch.cuda.Stream(device, priority=-1)   # exchange / refine / list update: first pick
-        # of whatever SM resources the GEMM grid leaves free
+        # SAEB_SCAN_AUX_PRIORITY = high (default: exchange / refine / list update get the first pick of whatever SM
+        # resources the GEMM grid leaves free) | low (GEMM CTAs are placed first at launch boundaries)
+        aux_priority = aux_priority or os.environ.get("SAEB_SCAN_AUX_PRIORITY", "high")
+        self.stream_gemm = torch.cuda.Stream(device, priority=0 if aux_priority == "high" else -1)
+        self.stream_aux = torch.cuda.Stream(device, priority=-1 if aux_priority == "high" else 0)
+        # > 0: the sharded refinement runs as a bounded persistent grid of that many CTAs and its helper launches use
+        # small blocks, so that nothing of the per-chunk chain has to wait for a GEMM launch boundary (saeb200.h,
+        # `max_ctas`); 0: one CTA per token
+        self.refine_max_ctas = int(os.environ.get("SAEB_SCAN_REFINE_CTAS", "0"))
         # SMs the GEMM grid leaves idle while a multi-rank scan is pipelined (see begin_pipeline).  Measured at 8 GPUs
         # (1 M tokens): 0 -> 4.85 M tokens/s, 4 (with NCCL_MAX_CTAS=4) -> 4.65-4.76 M: off by default
         self.reserve_sms = 0
@@ -198,7 +204,7 @@ class EngineOps:
                 x2.data_ptr(), eng._code(x2), x2.stride(0) if T > 1 else enc.d_in, self._prep[slot].data_ptr(), T, 0, T,
                 enc.blob.data_ptr(), enc.W_enc.data_ptr(), enc.d_in, enc.num_latents, k, 0, -1, 0.0,
                 None if ext_L is None else ext_L.data_ptr(), 1, vals.data_ptr(), idx.data_ptr(), self.status.data_ptr(),
-                self._ws[slot].data_ptr(), self._ws[slot].numel(), int(getattr(self, "refine_max_ctas", 0)), 0, st),
+                self._ws[slot].data_ptr(), self._ws[slot].numel(), int(self.refine_max_ctas), 0, st),
                 "saeb_refine_candidates")
         return vals, idx + self.feat_lo
 
