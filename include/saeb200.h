@@ -176,6 +176,16 @@ int saeb_decode(const int64_t* idx, const float* vals, int64_t T, int k, const v
                 int64_t N, const float* b_dec, void* out, int out_dtype, int64_t ld_out, const void* x, int x_dtype,
                 int64_t ld_x, double* sq_err, int* err_flag, int max_ctas, void* stream);
 
+/* ---- cache reader on the device ----------------------------------------------------------------------------
+ * Replaces the per-feature densify + pool of the example constructors (features/constructors.py:11-47 `_to_dense` +
+ * max_pool1d for text windows, :104-114 avg_pool1d over the base image tokens) for ALL features of a split file at
+ * once.  Input: the file's triples grouped by feature id (stable: file order kept inside a feature) as parallel arrays
+ * feature[nnz], window_key[nnz] (text: row * n_win + pos / ctx_len; image: row if pos < n_base; -1 = outside every
+ * window), activations[nnz].  For the first entry of every (feature, window) run: head = 1 and score = max of the run
+ * (mode 0) or (sequential fp32 sum of the run) * scale (mode 1, scale = 1 / n_base); other entries: head = 0. */
+int saeb_coo_window_scores(const int64_t* feature, const int64_t* window_key, const float* activations, int64_t nnz,
+                           int mode, float scale, float* score, int* head, void* stream);
+
 /* ---- probing queries -----------------------------------------------------------------------------------------
  * Replaces the hook body of the reference's probing tool (tools/probe_activations.py:109-126):
  *   latents = sae.pre_acts(hidden); top = latents.mean(0).topk(k).indices; maps = latents[:, top]
@@ -218,6 +228,15 @@ size_t saeb_coo_workspace_bytes(int64_t T);
 int saeb_coo_extract(const float* vals, const int64_t* idx, int64_t T, int k, float threshold,
                      const uint32_t* filter_bitmap, int64_t seq_len, int64_t row_offset, int64_t* locations,
                      float* activations, int64_t* nnz_out, void* workspace, size_t workspace_bytes, void* stream);
+/* Same extraction, but the triples are APPENDED behind *cursor (device int64, in/out) in a caller-owned arena of
+ * `capacity` entries (locations [capacity,3], activations [capacity]) and the cursor advances on the device: the cache
+ * of a whole run (reference Cache.add, features/cache.py:42-57, which moves every batch to the host) accumulates in HBM
+ * with no host round trip per batch; one device-to-host copy at Cache.save().  Entries that do not fit are dropped and
+ * *overflow_flag (device int, may be NULL) is set.  Workspace: saeb_coo_workspace_bytes(T) + 256 bytes. */
+int saeb_coo_append(const float* vals, const int64_t* idx, int64_t T, int k, float threshold,
+                    const uint32_t* filter_bitmap, int64_t seq_len, int64_t row_offset, int64_t* locations,
+                    float* activations, int64_t capacity, int64_t* cursor, int* overflow_flag, void* workspace,
+                    size_t workspace_bytes, void* stream);
 
 /* ---- per-feature top-activation scan ------------------------------------------------------------------------
  * Replaces, for all features at once, TensorBuffer.__getitem__ (features/loader.py:74-90) +

@@ -80,7 +80,8 @@ int total_variance_launch(const void* x, int x_dtype, long long T, long long d, 
 size_t coo_workspace_bytes(long long T);
 int coo_extract_launch(const float* vals, const long long* idx, long long T, int k, float threshold,
                        const uint32_t* filter, long long seq_len, long long row_offset, long long* locations,
-                       float* activations, long long* nnz_out, void* ws, size_t ws_bytes, cudaStream_t stream);
+                       float* activations, long long* nnz_out, void* ws, size_t ws_bytes, long long* cursor,
+                       long long capacity, int* overflow, cudaStream_t stream);
 int kth_gathered_launch(const float* gathered, int R, long long T, int m, int kth, float* tok_thr,
                         cudaStream_t stream);
 int set_kth_impl(int v);
@@ -112,6 +113,8 @@ int feature_maps_launch(const void* x, int x_dtype, long long T, long long ld_x,
                         const float* b_dec, long long d, long long N, const long long* sel, int n_sel, float* out,
                         int* err_flag, cudaStream_t stream);
 
+int coo_window_scores_launch(const long long* feat, const long long* key, const float* act, long long nnz, int mode,
+                             float scale, float* score, int* head, cudaStream_t stream);
 int set_cta_pair(int v);
 int set_profile(int v);
 float last_encode_ms();
@@ -570,8 +573,28 @@ int saeb_coo_extract(const float* vals, const int64_t* idx, int64_t T, int k, fl
   SAEB_REQUIRE(vals && idx && locations && activations && nnz_out && workspace, "coo_extract: null pointer");
   int rc = coo_extract_launch(vals, reinterpret_cast<const long long*>(idx), T, k, threshold, filter_bitmap, seq_len,
                               row_offset, reinterpret_cast<long long*>(locations), activations,
-                              reinterpret_cast<long long*>(nnz_out), workspace, workspace_bytes, (cudaStream_t)stream);
+                              reinterpret_cast<long long*>(nnz_out), workspace, workspace_bytes, nullptr, 0, nullptr,
+                              (cudaStream_t)stream);
   if (rc == 0) g_launches += 5;
+  return rc;
+}
+
+int saeb_coo_append(const float* vals, const int64_t* idx, int64_t T, int k, float threshold,
+                    const uint32_t* filter_bitmap, int64_t seq_len, int64_t row_offset, int64_t* locations,
+                    float* activations, int64_t capacity, int64_t* cursor, int* overflow_flag, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  g_err[0] = 0;
+  SAEB_REQUIRE(vals && idx && locations && activations && cursor && workspace, "coo_append: null pointer");
+  SAEB_REQUIRE(capacity >= 0, "coo_append: negative capacity");
+  SAEB_REQUIRE(workspace_bytes >= coo_workspace_bytes(T) + 256, "coo_append: workspace too small");
+  // the batch's own count lives in the last 256 bytes of the workspace
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  long long* batch_nnz = reinterpret_cast<long long*>(ws + ((workspace_bytes - 256) & ~(size_t)255));
+  int rc = coo_extract_launch(vals, reinterpret_cast<const long long*>(idx), T, k, threshold, filter_bitmap, seq_len,
+                              row_offset, reinterpret_cast<long long*>(locations), activations, batch_nnz, workspace,
+                              workspace_bytes - 256, reinterpret_cast<long long*>(cursor), capacity, overflow_flag,
+                              (cudaStream_t)stream);
+  if (rc == 0) g_launches += 6;
   return rc;
 }
 
@@ -624,6 +647,17 @@ int saeb_kth_largest_gathered(const float* gathered, int R, int64_t T, int m, in
   if (T == 0) return 0;
   int rc = kth_gathered_launch(gathered, R, T, m, kth, tok_thr, (cudaStream_t)stream);
   if (rc == 0) g_launches += 1;
+  return rc;
+}
+
+int saeb_coo_window_scores(const int64_t* feature, const int64_t* window_key, const float* activations, int64_t nnz,
+                           int mode, float scale, float* score, int* head, void* stream) {
+  g_err[0] = 0;
+  SAEB_REQUIRE(feature && window_key && activations && score && head, "coo_window_scores: null pointer");
+  int rc = coo_window_scores_launch(reinterpret_cast<const long long*>(feature),
+                                    reinterpret_cast<const long long*>(window_key), activations, nnz, mode, scale, score,
+                                    head, (cudaStream_t)stream);
+  if (rc == 0 && nnz > 0) g_launches += 1;
   return rc;
 }
 

@@ -20,9 +20,13 @@ size_t coo_workspace_bytes(long long T) {
          (size_t)(nchunks + 1) * sizeof(long long) + 256;
 }
 
+// cursor == nullptr: triples are written from entry 0 and *nnz_out = their number (saeb_coo_extract).
+// cursor != nullptr (device, in/out): they are appended behind *cursor in an arena of `capacity` entries and the cursor
+// advances -- no host round trip between batches (saeb_coo_append); nnz_out then is scratch for the batch's count.
 int coo_extract_launch(const float* vals, const long long* idx, long long T, int k, float threshold,
                        const uint32_t* filter, long long seq_len, long long row_offset, long long* locations,
-                       float* activations, long long* nnz_out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                       float* activations, long long* nnz_out, void* ws, size_t ws_bytes, long long* cursor,
+                       long long capacity, int* overflow, cudaStream_t stream) {
   SAEB_REQUIRE(T > 0 && k >= 1 && k <= 1024 && seq_len > 0, "coo: bad arguments T=%lld k=%d seq_len=%lld", T, k,
                seq_len);
   SAEB_REQUIRE(ws_bytes >= coo_workspace_bytes(T), "coo: workspace too small");
@@ -43,8 +47,13 @@ int coo_extract_launch(const float* vals, const long long* idx, long long T, int
   int kp2 = 2;
   while (kp2 < k) kp2 <<= 1;
   coo_emit_kernel<<<(unsigned)((T + wpb - 1) / wpb), wpb * 32, (size_t)wpb * kp2 * sizeof(uint2), stream>>>(
-      vals, idx, T, k, kp2, threshold, filter, offsets, seq_len, row_offset, locations, activations);
+      vals, idx, T, k, kp2, threshold, filter, offsets, seq_len, row_offset, locations, activations, cursor, capacity,
+      overflow);
   SAEB_CHECK_CUDA(cudaGetLastError());
+  if (cursor != nullptr) {
+    coo_advance_kernel<<<1, 32, 0, stream>>>(cursor, nnz_out, capacity);
+    SAEB_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -177,6 +186,15 @@ int image_pool_launch(const float* vals, const long long* idx, long long n_image
                                               reinterpret_cast<unsigned long long*>(b + p.sums_off),
                                               reinterpret_cast<int*>(b + p.list_off), p.slots,
                                               reinterpret_cast<uint2*>(bucket), bucket_cnt, bucket_cap, overflow);
+  SAEB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int coo_window_scores_launch(const long long* feat, const long long* key, const float* act, long long nnz, int mode,
+                             float scale, float* score, int* head, cudaStream_t stream) {
+  SAEB_REQUIRE(nnz >= 0 && (mode == 0 || mode == 1), "coo_window_scores: bad arguments");
+  if (nnz == 0) return 0;
+  coo_window_scores_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(feat, key, act, nnz, mode, scale, score, head);
   SAEB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -86,7 +86,10 @@ __global__ void scan_chunks_kernel(const int* __restrict__ in, long long n, cons
 __global__ void coo_emit_kernel(const float* __restrict__ vals, const long long* __restrict__ idx, long long T, int k,
                                 int kp2, float threshold, const uint32_t* __restrict__ filter,
                                 const long long* __restrict__ offsets, long long seq_len, long long row_offset,
-                                long long* __restrict__ locations, float* __restrict__ activations) {
+                                long long* __restrict__ locations, float* __restrict__ activations,
+                                const long long* __restrict__ base, long long capacity, int* __restrict__ overflow) {
+  // base (optional, device): entries are appended behind *base in an arena of `capacity` entries (saeb_coo_append);
+  // whatever does not fit is dropped and reported through *overflow
   extern __shared__ uint2 esm[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -118,14 +121,27 @@ __global__ void coo_emit_kernel(const float* __restrict__ vals, const long long*
       __syncwarp();
     }
   }
-  const long long off = offsets[t];
-  const int cnt = (int)(offsets[t + 1] - off);
+  const int cnt = (int)(offsets[t + 1] - offsets[t]);
+  const long long off = offsets[t] + (base != nullptr ? *base : 0);
   const long long r = row_offset + t / seq_len, pos = t % seq_len;
   for (int j = lane; j < cnt; j += 32) {
+    if (base != nullptr && off + j >= capacity) {
+      if (overflow != nullptr) atomicExch(overflow, 1);
+      continue;
+    }
     locations[(off + j) * 3 + 0] = r;
     locations[(off + j) * 3 + 1] = pos;
     locations[(off + j) * 3 + 2] = (long long)e[j].x;
     activations[off + j] = __uint_as_float(e[j].y);
+  }
+}
+
+// *cursor += *count (one thread): advances the arena cursor of saeb_coo_append after the emit kernel has read it
+__global__ void coo_advance_kernel(long long* __restrict__ cursor, const long long* __restrict__ count,
+                                   long long capacity) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const long long c = *cursor + *count;
+    *cursor = c < capacity ? c : capacity;
   }
 }
 
@@ -238,6 +254,33 @@ __global__ void scan_merge_kernel(uint2* __restrict__ bucket, int* __restrict__ 
     feat_thr[f] = (last.x != 0u) ? __uint_as_float(last.x) : base_thr;
     bucket_cnt[f] = 0;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cache reader on the device: pooled score of every (feature, window) of a split file
+// ---------------------------------------------------------------------------------------------
+// Input: the cached triples of a split file grouped by feature (stable, so a feature's entries keep the file's
+// (row, pos) order) with a window key per entry (text constructor: row * n_win + pos / ctx_len, reference
+// features/constructors.py:11-47; image constructor: the row, for positions below n_base, :109-114; -1 = entry outside
+// every window).  Entries of one (feature, window) are consecutive.  The thread that sits on the FIRST entry of a run
+// reduces the run in file order -- max for the text windows (max_pool1d), a sequential fp32 sum times `scale` for the
+// image mean (the same order as the reference's CPU index_add_ / avg_pool) -- and flags itself as the run's head.
+__global__ void __launch_bounds__(256)
+coo_window_scores_kernel(const long long* __restrict__ feat, const long long* __restrict__ key,
+                         const float* __restrict__ act, long long nnz, int mode, float scale,
+                         float* __restrict__ score, int* __restrict__ head) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnz) return;
+  const long long f = feat[i], k = key[i];
+  const bool is_head = k >= 0 && (i == 0 || feat[i - 1] != f || key[i - 1] != k);
+  head[i] = is_head ? 1 : 0;
+  if (!is_head) {
+    score[i] = 0.f;
+    return;
+  }
+  float acc = act[i];
+  for (long long j = i + 1; j < nnz && feat[j] == f && key[j] == k; ++j) acc = (mode == 0) ? fmaxf(acc, act[j]) : acc + act[j];
+  score[i] = (mode == 0) ? acc : acc * scale;
 }
 
 // ---------------------------------------------------------------------------------------------

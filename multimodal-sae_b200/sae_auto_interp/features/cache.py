@@ -30,11 +30,18 @@ except Exception:  # pragma: no cover
 
 
 class Cache:
-    """Accumulates per-module COO triples on the host (same fields as the reference's `Cache`)."""
+    """Accumulates per-module COO triples (same fields as the reference's `Cache`).
+
+    On the fused path (`add_topk` with CUDA tensors) the triples of a whole run accumulate in a device arena
+    (saeb200.engine.CooArena, saeb_coo_append): no `.cpu()` per batch like the reference (features/cache.py:52-53);
+    `save()` does the single device-to-host copy and leaves CPU tensors in `feature_locations` /
+    `feature_activations`, as the reference does.  `device_tensors(module)` hands the arena to `save_splits`, which
+    then sorts by split on the device."""
 
     def __init__(self, shard_size: int, filters: Optional[Dict[str, torch.Tensor]] = None, batch_size: int = 64):
         self.feature_locations = defaultdict(list)
         self.feature_activations = defaultdict(list)
+        self._arenas: Dict[str, "engine.CooArena"] = {}
         self.filters = filters
         self.batch_size = batch_size
         self.shard_size = shard_size  # global row offset of this rank's dataset shard
@@ -53,12 +60,24 @@ class Cache:
                  num_latents: int) -> None:
         """Fused path: TopK output [batch, seq, k] of one batch -> cached triples."""
         seq_len = top_acts.shape[-2]
-        loc, act = engine.coo_extract(
-            top_acts, top_indices, seq_len,
-            row_offset=batch_number * self.batch_size + self.shard_size,
-            filter_bitmap=self._bitmap(module_path, num_latents, top_acts.device))
+        row_offset = batch_number * self.batch_size + self.shard_size
+        bitmap = self._bitmap(module_path, num_latents, top_acts.device)
+        if top_acts.is_cuda:
+            arena = self._arenas.get(module_path)
+            if arena is None:
+                arena = self._arenas[module_path] = engine.CooArena(top_acts.device)
+                self.feature_locations[module_path]   # creates the keys the launchers iterate over
+                self.feature_activations[module_path]
+            arena.append(top_acts, top_indices, seq_len, row_offset=row_offset, filter_bitmap=bitmap)
+            return
+        loc, act = engine.coo_extract(top_acts, top_indices, seq_len, row_offset=row_offset, filter_bitmap=bitmap)
         self.feature_locations[module_path].append(loc.cpu())
         self.feature_activations[module_path].append(act.cpu())
+
+    def device_tensors(self, module_path: str):
+        """(locations, activations) still on the device, or None when this module was cached through the host path"""
+        arena = self._arenas.get(module_path)
+        return None if arena is None else arena.tensors()
 
     def get_nonzeros(self, latents: torch.Tensor, module_path: str):
         """Legacy entry for callers holding a dense (already TopK-masked) [batch, seq, feature] tensor: dense ->
@@ -76,6 +95,12 @@ class Cache:
         self.feature_activations[module_path].append(act.cpu())
 
     def save(self) -> None:
+        for module_path, arena in self._arenas.items():
+            loc, act = arena.tensors()
+            parts_l = self.feature_locations[module_path] if isinstance(self.feature_locations[module_path], list) else []
+            parts_a = self.feature_activations[module_path] if isinstance(self.feature_activations[module_path], list) else []
+            self.feature_locations[module_path] = parts_l + [loc.cpu()]     # the single device-to-host copy
+            self.feature_activations[module_path] = parts_a + [act.cpu()]
         for module_path in list(self.feature_locations.keys()):
             if isinstance(self.feature_locations[module_path], list):
                 self.feature_locations[module_path] = torch.cat(self.feature_locations[module_path], dim=0)
@@ -172,14 +197,20 @@ class FeatureCache:
         starts = torch.tensor([int(s) for s, _ in split_indices])
         ends = torch.tensor([int(e) for _, e in split_indices])
         for module_path in self.cache.feature_locations.keys():
-            loc = self.cache.feature_locations[module_path]
-            act = self.cache.feature_activations[module_path]
+            dev_pair = self.cache.device_tensors(module_path)
+            if dev_pair is not None:   # the arena is still in HBM: bucket + stable sort by split there, one copy back
+                loc, act = dev_pair
+                starts, ends = starts.to(loc.device), ends.to(loc.device)
+            else:
+                loc = self.cache.feature_locations[module_path]
+                act = self.cache.feature_activations[module_path]
+                starts, ends = starts.cpu(), ends.cpu()
             feat = loc[:, 2].contiguous()
             sid = torch.bucketize(feat, starts, right=True) - 1
             upper = ends[sid] + (1 if self.fix_split_bounds else 0)
             keep = feat < upper
             order = torch.sort(sid[keep], stable=True).indices
-            loc_k, act_k, sid_k = loc[keep][order], act[keep][order], sid[keep][order]
+            loc_k, act_k, sid_k = loc[keep][order].cpu(), act[keep][order].cpu(), sid[keep][order].cpu()
             cuts = torch.searchsorted(sid_k, torch.arange(n_splits + 1))
             module_dir = f"{save_dir}/{module_path}"
             os.makedirs(module_dir, exist_ok=True)

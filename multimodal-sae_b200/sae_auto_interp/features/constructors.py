@@ -27,11 +27,32 @@ def _feature_window_scores(locations: torch.Tensor, activations: torch.Tensor, s
 
 
 def pool_max_activation_windows(record: FeatureRecord, buffer_output: BufferOutput, tokens: torch.Tensor,
-                                cfg: FeatureConfig = None, *, ctx_len: int = None, max_examples: int = None):
-    """Top `max_examples` windows of `ctx_len` tokens by max activation, descending (reference :70-85)."""
+                                cfg: FeatureConfig = None, *, ctx_len: int = None, max_examples: int = None,
+                                ranked=None):
+    """Top `max_examples` windows of `ctx_len` tokens by max activation, descending (reference :70-85).
+
+    `ranked` (optional) = (scores, window ids) of this feature from the device ranking of the whole split file
+    (saeb200.engine.coo_top_windows, window id = row * n_win + w): the per-feature densify + max-pool + topk is then
+    skipped and only the selected windows are materialised."""
     ctx_len = ctx_len if ctx_len is not None else cfg.example_ctx_len
     max_examples = max_examples if max_examples is not None else cfg.max_examples
     seq_len = tokens.shape[1]
+    if ranked is not None:
+        n_win = seq_len // ctx_len
+        win = ranked[1][:max_examples].to(torch.long)
+        r, w = win // n_win, win % n_win
+        loc, act = buffer_output.locations, buffer_output.activations
+        ent_win = loc[:, 0] * n_win + loc[:, 1] // ctx_len
+        inside = loc[:, 1] < n_win * ctx_len
+        order = torch.argsort(win)
+        slot_sorted = torch.searchsorted(win[order], ent_win.clamp(max=int(win.max()) if win.numel() else 0))
+        slot_sorted = slot_sorted.clamp(max=max(win.numel() - 1, 0))
+        hit = inside & (win.numel() > 0) & (win[order][slot_sorted] == ent_win)
+        dense = torch.zeros((win.numel(), ctx_len), dtype=act.dtype)
+        dense.index_put_((order[slot_sorted[hit]], loc[hit, 1] % ctx_len), act[hit], accumulate=True)
+        cols = (w * ctx_len)[:, None] + torch.arange(ctx_len)[None, :]
+        record.examples = prepare_examples(tokens[r][torch.arange(win.numel())[:, None], cols], dense)
+        return
     rows, dense, pooled = _feature_window_scores(buffer_output.locations, buffer_output.activations, seq_len, ctx_len)
     n_win = pooled.shape[1]
     flat = pooled.flatten()
@@ -57,9 +78,9 @@ def random_activation_windows(record, tokens: torch.Tensor, buffer_output: Buffe
 
 
 def default_constructor(record: FeatureRecord, tokens: torch.Tensor, buffer_output: BufferOutput, n_random: int,
-                        ctx_len: int, max_examples: int):
+                        ctx_len: int, max_examples: int, ranked=None):
     pool_max_activation_windows(record, buffer_output=buffer_output, tokens=tokens, ctx_len=ctx_len,
-                                max_examples=max_examples)
+                                max_examples=max_examples, ranked=ranked)
     random_activation_windows(record, tokens=tokens, buffer_output=buffer_output, n_random=n_random, ctx_len=ctx_len)
 
 
@@ -101,14 +122,27 @@ def _dedup_ranked(ranked, ids, max_examples: int):
 
 
 def pool_max_activations_windows_image(record: FeatureRecord, buffer_output: BufferOutput, tokens, cfg: FeatureConfig,
-                                       processor=None):
+                                       processor=None, ranked=None):
     """Image variant (reference :88-148): rank images by the mean activation over the first `num_image_tokens` (576)
     positions, take the best `max_examples + 50`, drop repeated dataset ids, keep `max_examples`; `record.examples`
-    holds one ImageExample per kept image.  `tokens` is the image dataset (`len`, `.features`, `.select(indices=)`)."""
+    holds one ImageExample per kept image.  `tokens` is the image dataset (`len`, `.features`, `.select(indices=)`).
+
+    `ranked` (optional) = (scores, image ids) of this feature from the device ranking of the whole split file
+    (saeb200.engine.coo_top_windows(n_base=...), positive scores only, score desc / id asc): replaces the per-feature
+    score vector + topk; images that never fired fill the list in ascending id order when fewer than
+    `max_examples + 50` did (the reference's topk over the zero scores picks them in an unspecified order)."""
     n_base = getattr(processor, "num_image_tokens", 576)
     loc, act = buffer_output.locations, buffer_output.activations
-    score = image_scores(loc, act, len(tokens), n_base)
-    ranked = torch.topk(score, cfg.max_examples + 50).indices.tolist()
+    want = cfg.max_examples + 50
+    if ranked is not None:
+        ranked_ids = ranked[1][:want].tolist()
+        if len(ranked_ids) < want:
+            have = set(ranked_ids)
+            ranked_ids += [i for i in range(len(tokens)) if i not in have][: want - len(ranked_ids)]
+        ranked = ranked_ids
+    else:
+        score = image_scores(loc, act, len(tokens), n_base)
+        ranked = torch.topk(score, want).indices.tolist()
     if "id" in tokens.features:
         ranked = _dedup_ranked(ranked, tokens.select(indices=ranked)["id"], cfg.max_examples)
     else:

@@ -132,23 +132,96 @@ class FeatureDataset:
         return len(self.buffers)
 
     def load(self, collate: bool = False, constructor: Optional[Callable] = None, sampler: Optional[Callable] = None,
-             transform: Optional[Callable] = None):
+             transform: Optional[Callable] = None, device="auto"):
         """Per buffer, per feature: record -> `constructor(record=, buffer_output=)` -> `sampler(record)` ->
         `transform(record)` (the reference's callback protocol, features/loader.py:201-248).  `collate=True` returns
-        one flat list, otherwise a generator of per-buffer lists."""
+        one flat list, otherwise a generator of per-buffer lists.
 
-        def build(out: BufferOutput) -> FeatureRecord:
+        Device route: when `constructor` is a `functools.partial` of this package's `pool_max_activation_windows` /
+        `default_constructor` / `pool_max_activations_windows_image` and a CUDA device is available (`device="auto"`,
+        or an explicit device; `None` forces the host route), the RANKING step of the constructor -- the densify +
+        pool + topk the reference repeats for every feature -- runs once per split file on the device for all its
+        features (saeb200.engine.coo_top_windows) and each constructor call only materialises its selected examples.
+        This is what `launch/explain/explain_images.py:56-65` drives."""
+        plan = _device_plan(constructor, self.cfg) if device is not None else None
+        dev = None
+        if plan is not None:
+            if device == "auto":
+                dev = torch.device("cuda") if torch.cuda.is_available() else None
+            else:
+                dev = torch.device(device)
+
+        def build(out: BufferOutput, ranked=None) -> FeatureRecord:
             record = FeatureRecord(out.feature)
-            for step, kwargs in ((constructor, {"record": record, "buffer_output": out}), (sampler, None),
-                                 (transform, None)):
+            if constructor is not None:
+                kwargs = {"record": record, "buffer_output": out}
+                if ranked is not None:
+                    kwargs["ranked"] = ranked
+                constructor(**kwargs)
+            for step in (sampler, transform):
                 if step is not None:
-                    step(**kwargs) if kwargs else step(record)
+                    step(record)
             return record
 
         def records_of(buffer: TensorBuffer) -> List[FeatureRecord]:
             buffer._load()
-            return [build(buffer[i]["buffer"]) for i in range(len(buffer))]
+            ranking = _rank_split_on_device(buffer, plan, dev) if dev is not None else None
+            out = []
+            for i in range(len(buffer)):
+                bo = buffer[i]["buffer"]
+                out.append(build(bo, None if ranking is None else ranking(bo.feature.feature_index)))
+            return out
 
         if collate:
             return [rec for buffer in self.buffers for rec in records_of(buffer)]
         return (records_of(buffer) for buffer in self.buffers)
+
+
+def _device_plan(constructor, cfg):
+    """what the device has to rank for this constructor, or None if it is not one of the window constructors"""
+    import functools
+
+    from . import constructors as C
+
+    if not isinstance(constructor, functools.partial):
+        return None
+    kw = constructor.keywords
+    if constructor.func is C.pool_max_activations_windows_image:
+        c = kw.get("cfg", cfg)
+        return {"kind": "image", "n_base": getattr(kw.get("processor"), "num_image_tokens", 576),
+                "n_top": c.max_examples + 50}
+    if constructor.func in (C.pool_max_activation_windows, C.default_constructor):
+        c = kw.get("cfg", cfg)
+        tokens = kw.get("tokens")
+        if tokens is None or not hasattr(tokens, "shape"):
+            return None
+        ctx_len = kw.get("ctx_len") or (c.example_ctx_len if c is not None else None)
+        n_top = kw.get("max_examples") or (c.max_examples if c is not None else None)
+        if ctx_len is None or n_top is None:
+            return None
+        return {"kind": "text", "ctx_len": int(ctx_len), "seq_len": int(tokens.shape[1]), "n_top": int(n_top)}
+    return None
+
+
+def _rank_split_on_device(buffer: "TensorBuffer", plan, dev):
+    """one device pass over a split file -> lookup `feature id -> (scores, window ids)` (CPU tensors)"""
+    from saeb200 import engine
+
+    if plan["kind"] == "image":
+        feats, offs, scores, wins = engine.coo_top_windows(buffer.locations, buffer.activations, plan["n_top"],
+                                                           n_base=plan["n_base"], device=dev)
+    else:
+        feats, offs, scores, wins = engine.coo_top_windows(buffer.locations, buffer.activations, plan["n_top"],
+                                                           ctx_len=plan["ctx_len"], seq_len=plan["seq_len"], device=dev)
+    feats, offs, scores, wins = feats.cpu(), offs.cpu(), scores.cpu(), wins.cpu()   # one copy back per split file
+    index = {int(f): i for i, f in enumerate(feats.tolist())}
+    empty = (scores[:0], wins[:0])
+
+    def lookup(feature: int):
+        i = index.get(int(feature))
+        if i is None:
+            return empty
+        a, b = int(offs[i]), int(offs[i + 1])
+        return scores[a:b], wins[a:b]
+
+    return lookup

@@ -157,8 +157,17 @@ class Sae(nn.Module):
         """Fused encoder GEMM + TopK (reference sae/sae.py:183-185).  Rows come back ordered by
         (activation desc, index asc); the reference's order is unspecified (`sorted=False`).  `exact_values` overrides
         `self.refine_values` for this call (the activation cache asks for exact values: it ranks by them)."""
+        vm = self._value_mode(exact_values)
+        if torch.is_grad_enabled() and (x.requires_grad or self.encoder.weight.requires_grad
+                                        or self.encoder.bias.requires_grad or self.b_dec.requires_grad):
+            from .utils import SparseEncode   # differentiable like the reference's nn.Linear -> relu -> topk
+
+            acts, idx = SparseEncode.apply(x, self.encoder.weight, self.encoder.bias, self.b_dec,
+                                           self.packed_encoder(), self.cfg.k, int(clamp_feature), float(clamp_value),
+                                           vm)
+            return EncoderOutput(acts, idx)
         acts, idx, _ = engine.encode_topk(x, self.packed_encoder(), self.cfg.k, clamp_feature=clamp_feature,
-                                          clamp_value=clamp_value, value_mode=self._value_mode(exact_values))
+                                          clamp_value=clamp_value, value_mode=vm)
         return EncoderOutput(acts, idx)
 
     def _value_mode(self, exact_values: Optional[bool] = None) -> int:

@@ -59,6 +59,8 @@ SIGNATURES = {
                                           c_void_p, c_void_p, c_void_p]),
     "saeb_decode_backward_weight": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64,
                                             c_void_p, c_void_p, c_void_p]),
+    "saeb_coo_window_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p,
+                                       c_void_p]),
     "saeb_column_sums": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "saeb_feature_maps": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
@@ -66,6 +68,8 @@ SIGNATURES = {
     "saeb_coo_workspace_bytes": (c_size_t, [c_int64]),
     "saeb_coo_extract": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_int64, c_int64, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "saeb_coo_append": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_int64, c_int64, c_void_p,
+                                c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "saeb_scan_pool": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_int64, c_int64, c_int64,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "saeb_scan_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p,

@@ -519,3 +519,136 @@ def feature_maps(x: torch.Tensor, W_enc: torch.Tensor, b_enc: torch.Tensor, b_de
     if int(err.item()) != 0:
         raise SaebError("feature_maps: feature id out of range")
     return out
+
+
+def coo_top_windows(locations: torch.Tensor, activations: torch.Tensor, n_top: int, *, ctx_len: Optional[int] = None,
+                    seq_len: Optional[int] = None, n_base: Optional[int] = None, device=None
+                    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Ranking step of the example constructors for EVERY feature of a split file in one pass on the device.
+
+    locations [nnz, 3] int64 (row, pos, feature) / activations [nnz] f32 as stored in the cache's split files.
+      * text windows (`ctx_len`, `seq_len` given; reference pool_max_activation_windows, features/constructors.py:
+        11-85): score(feature, row, w) = max activation over positions [w * ctx_len, (w + 1) * ctx_len), windows beyond
+        seq_len // ctx_len are dropped like the reference's max_pool1d does; window id = row * n_win + w;
+      * images (`n_base` given; pool_max_activations_windows_image, :104-122): score(feature, row) = sum of the
+        activations at positions < n_base divided by n_base (avg_pool1d over the base image tokens); window id = row.
+    Returns (features [F'] sorted ascending, offsets [F' + 1], scores [M], window ids [M]): for features[i] the entries
+    offsets[i]:offsets[i+1] are its best <= n_top windows ordered (score desc, window id asc).  Tensors live on the
+    device.  The triples are grouped with one stable device sort, the pooled scores come from saeb_coo_window_scores
+    (file-order reduction, so image means equal the reference's sequential CPU sums bit for bit), the ranking is one
+    more device sort of (feature, score) keys."""
+    text = ctx_len is not None
+    if text == (n_base is not None):
+        raise SaebError("coo_top_windows: give either ctx_len + seq_len (text windows) or n_base (images)")
+    dev = torch.device(device) if device is not None else locations.device
+    if dev.type != "cuda":
+        raise SaebError("coo_top_windows needs a CUDA device: there is no CPU fallback")
+    L = _capi.lib()
+    loc = locations.to(dev, non_blocking=True)
+    act = activations.to(dev, torch.float32, non_blocking=True)
+    nnz = loc.shape[0]
+    empty = torch.zeros(0, dtype=torch.int64, device=dev)
+    if nnz == 0:
+        return empty, torch.zeros(1, dtype=torch.int64, device=dev), torch.zeros(0, device=dev), empty
+    row, pos, feat = loc[:, 0], loc[:, 1], loc[:, 2]
+    if text:
+        n_win = int(seq_len) // int(ctx_len)
+        key = row * n_win + pos // ctx_len
+        valid = pos < n_win * ctx_len
+        mode, scale = 0, 1.0
+    else:
+        key = row
+        valid = pos < n_base
+        mode, scale = 1, 1.0 / float(n_base)
+    feat, key, acts = feat[valid], key[valid], act[valid]
+    nnz = feat.numel()
+    if nnz == 0:
+        return empty, torch.zeros(1, dtype=torch.int64, device=dev), torch.zeros(0, device=dev), empty
+    # group by (feature, window) with ONE stable sort: file order is kept inside a window, so the sums below add in
+    # the order the reference's CPU ops do
+    span = int(key.max().item()) + 1
+    order = torch.sort(feat * span + key, stable=True).indices
+    feat, key, acts = feat[order].contiguous(), key[order].contiguous(), acts[order].contiguous()
+    score = torch.empty(nnz, dtype=torch.float32, device=dev)
+    head = torch.empty(nnz, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(L.saeb_coo_window_scores(feat.data_ptr(), key.data_ptr(), acts.data_ptr(), nnz, mode, scale,
+                                       score.data_ptr(), head.data_ptr(), _stream()), "saeb_coo_window_scores")
+    sel = head.nonzero().squeeze(1)
+    f_h, k_h, s_h = feat[sel], key[sel], score[sel]
+    keep = s_h > 0   # the constructors rank non-zero pooled values only (constructors.py:58-60)
+    f_h, k_h, s_h = f_h[keep], k_h[keep], s_h[keep]
+    # (feature asc, score desc) in one stable sort; window ids are already ascending inside a feature
+    comp = (f_h << 32) | (0xFFFFFFFF - s_h.view(torch.int32).to(torch.int64))
+    o2 = torch.sort(comp, stable=True).indices
+    f_s, k_s, s_s = f_h[o2], k_h[o2], s_h[o2]
+    feats, counts = torch.unique_consecutive(f_s, return_counts=True)
+    starts = torch.cumsum(counts, 0) - counts
+    rank = torch.arange(f_s.numel(), device=dev) - torch.repeat_interleave(starts, counts)
+    top = rank < n_top
+    kept = torch.clamp(counts, max=n_top)
+    offsets = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(kept, 0)])
+    return feats, offsets, s_s[top], k_s[top]
+
+
+class CooArena:
+    """Device-resident accumulation of the activation cache of one hooked module (reference Cache.add / Cache.save,
+    features/cache.py:42-71, which copies every batch to the host): `append` enqueues one extraction that writes behind
+    a device-side cursor, nothing comes back to the host until `tensors()`.
+
+    The host only tracks an upper bound of the fill (T * k per batch); when that bound reaches the capacity it reads
+    the true cursor once (the only synchronisation besides the final one) and grows the arena geometrically if the data
+    really do not fit."""
+
+    def __init__(self, device, capacity: int = 1 << 22):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise SaebError("CooArena needs a CUDA device: there is no CPU fallback")
+        self.capacity = int(capacity)
+        self.loc = torch.empty((self.capacity, 3), dtype=torch.int64, device=self.device)
+        self.act = torch.empty((self.capacity,), dtype=torch.float32, device=self.device)
+        self.cursor = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.upper = 0        # host-side upper bound of the cursor
+        self.syncs = 0        # host round trips so far (diagnostics / tests)
+
+    def _reserve(self, extra: int) -> None:
+        if self.upper + extra <= self.capacity:
+            return
+        n = int(self.cursor.item())
+        self.syncs += 1
+        self.upper = n
+        if n + extra > self.capacity:
+            cap = max(2 * self.capacity, n + extra)
+            loc = torch.empty((cap, 3), dtype=torch.int64, device=self.device)
+            act = torch.empty((cap,), dtype=torch.float32, device=self.device)
+            loc[:n].copy_(self.loc[:n])
+            act[:n].copy_(self.act[:n])
+            self.loc, self.act, self.capacity = loc, act, cap
+
+    def append(self, top_acts: torch.Tensor, top_indices: torch.Tensor, seq_len: int, *, row_offset: int = 0,
+               threshold: float = ACT_THRESHOLD, filter_bitmap: Optional[torch.Tensor] = None) -> None:
+        _need_cuda(top_acts, top_indices, filter_bitmap)
+        L = _capi.lib()
+        k = top_acts.shape[-1]
+        vals = top_acts.reshape(-1, k).to(torch.float32).contiguous()
+        idx = top_indices.reshape(-1, k).to(torch.int64).contiguous()
+        T = vals.shape[0]
+        if T == 0:
+            return
+        self._reserve(T * k)
+        with torch.cuda.device(self.device):
+            ws = _workspace(self.device, L.saeb_coo_workspace_bytes(T) + 256, "coo_append")
+            check(L.saeb_coo_append(vals.data_ptr(), idx.data_ptr(), T, k, float(threshold),
+                                    None if filter_bitmap is None else filter_bitmap.data_ptr(), seq_len, row_offset,
+                                    self.loc.data_ptr(), self.act.data_ptr(), self.capacity, self.cursor.data_ptr(),
+                                    self.overflow.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "saeb_coo_append")
+        self.upper += T * k
+
+    def tensors(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(locations [nnz, 3], activations [nnz]) views of the arena on the device (one synchronisation)"""
+        n = int(self.cursor.item())
+        self.syncs += 1
+        if int(self.overflow.item()) != 0:
+            raise SaebError("CooArena overflowed (internal error: the reserve logic must prevent this)")
+        return self.loc[:n], self.act[:n]

@@ -179,7 +179,7 @@ void emu_coo_extract(const float* vals, const long long* idx, long long T, int k
   int kp2 = 2;
   while (kp2 < k) kp2 <<= 1;
   emu::launch({g8}, {256}, [&] {
-    coo_emit_kernel(vals, idx, T, k, kp2, threshold, filter, offsets.data(), seq_len, row_offset, locations, activations);
+    coo_emit_kernel(vals, idx, T, k, kp2, threshold, filter, offsets.data(), seq_len, row_offset, locations, activations, nullptr, 0, nullptr);
   });
 }
 

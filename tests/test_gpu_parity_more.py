@@ -393,3 +393,143 @@ def test_mean_activations_streams_token_chunks():
     with pytest.raises(engine.SaebError):
         engine.feature_maps(x, sae.encoder.weight.data, sae.encoder.bias.data, sae.b_dec.data,
                             torch.tensor([2048], device=DEV))
+
+
+class _ToyLM(torch.nn.Module):
+    """the toy host model of the cache fixture (oracle/gen_golden.py::ToyLM): embedding -> one hooked linear layer"""
+
+    def __init__(self, emb, layer_w):
+        super().__init__()
+        self.emb = torch.nn.Embedding.from_pretrained(torch.from_numpy(emb), freeze=True)
+        self.layers = torch.nn.ModuleList([torch.nn.Linear(layer_w.shape[1], layer_w.shape[0], bias=False)])
+        with torch.no_grad():
+            self.layers[0].weight.copy_(torch.from_numpy(layer_w))
+
+    @property
+    def device(self):
+        return self.emb.weight.device
+
+    def forward(self, ids):
+        return self.layers[0](self.emb(ids))
+
+
+def _run_fixture_cache(tmp_path, n_splits=4):
+    from sae_auto_interp.features import FeatureCache
+    from test_gpu_parity import _params, _sae_from_params
+
+    g = np.load(os.path.join(GOLDEN, "cache_chain.npz"))
+    sae = _sae_from_params(_params(g))
+    model = _ToyLM(g["emb"], g["layer_w"]).to(DEV)
+    tokens = torch.from_numpy(g["tokens"])
+    fc = FeatureCache(model, None, {"layers.0": sae}, batch_size=2, shard_size=100)
+    fc.run(16, [{"input_ids": tokens[i]} for i in range(tokens.shape[0])])
+    return fc, g, tokens
+
+
+def test_device_cache_arena_writes_the_reference_split_files(tmp_path):
+    """FeatureCache on the device end to end: triples accumulate in the HBM arena (no host copy per batch), save_splits
+    buckets + sorts them on the device, and the files are byte-for-byte the ones the reference wrote for the same run
+    (fixture: FeatureCache.run -> save_splits -> concate_safetensors of the unmodified reference)."""
+    from safetensors.torch import load_file
+
+    fc, g, _ = _run_fixture_cache(tmp_path)
+    arena = fc.cache._arenas["layers.0"]
+    assert arena.syncs <= 2, "the arena must not synchronise per batch"      # save() only
+    assert fc.cache.feature_locations["layers.0"].device.type == "cpu"
+    assert np.array_equal(fc.cache.feature_locations["layers.0"].numpy(), g["nofilter_locations"])
+    assert fc.cache.device_tensors("layers.0")[0].is_cuda
+    fc.save_splits(4, str(tmp_path), rank=0)
+    fc.concate_safetensors(4, str(tmp_path))
+    files = sorted(os.listdir(tmp_path / "layers.0"))
+    assert files == sorted(g["split_files"].tolist())
+    for f in files:
+        data = load_file(str(tmp_path / "layers.0" / f))
+        assert np.array_equal(data["locations"].numpy(), g[f"split_{f}_locations"])
+        np.testing.assert_allclose(data["activations"].numpy(), g[f"split_{f}_activations"], rtol=1e-3)
+
+
+def test_coo_arena_grows_without_losing_entries():
+    from saeb200 import engine
+
+    gen = torch.Generator().manual_seed(3)
+    arena = engine.CooArena(DEV, capacity=64)
+    locs, acts = [], []
+    for b in range(5):
+        v = torch.rand(3, 16, 8, generator=gen).to(DEV)
+        v[v < 0.3] = 0.0
+        i = torch.stack([torch.randperm(500, generator=gen)[:8] for _ in range(48)]).view(3, 16, 8).to(DEV)
+        arena.append(v, i, 16, row_offset=10 * b)
+        l, a = engine.coo_extract(v, i, 16, row_offset=10 * b)
+        locs.append(l)
+        acts.append(a)
+    loc, act = arena.tensors()
+    assert torch.equal(loc, torch.cat(locs)) and torch.equal(act, torch.cat(acts))
+    assert arena.capacity >= loc.shape[0]
+
+
+def test_loader_device_route_equals_host_route(tmp_path):
+    """FeatureDataset.load with the window constructor bound through functools.partial (what the explain launchers
+    do): the device route (one ranking pass per split file for all its features) must build the same examples as the
+    per-feature host route, for every feature of the fixture's cache."""
+    from functools import partial
+
+    from sae_auto_interp.config import FeatureConfig
+    from sae_auto_interp.features import FeatureDataset, pool_max_activation_windows
+
+    fc, g, tokens = _run_fixture_cache(tmp_path)
+    fc.fix_split_bounds = True
+    fc.save_splits(4, str(tmp_path), rank=0)
+    fc.concate_safetensors(4, str(tmp_path))
+    cfg = FeatureConfig(width=64, example_ctx_len=4, min_examples=0, max_examples=5, n_splits=4)
+    big = torch.zeros(100 + tokens.shape[0], tokens.shape[1], dtype=torch.long)
+    big[100:] = tokens
+    ds = FeatureDataset(str(tmp_path), cfg, modules=["layers.0"])
+    ctor = partial(pool_max_activation_windows, tokens=big, cfg=cfg)
+    host = ds.load(collate=True, constructor=ctor, device=None)
+    ds2 = FeatureDataset(str(tmp_path), cfg, modules=["layers.0"])
+    dev = ds2.load(collate=True, constructor=ctor, device=DEV)
+    assert [r.feature.feature_index for r in host] == [r.feature.feature_index for r in dev] and len(host) > 20
+    n_checked = 0
+    for rh, rd in zip(host, dev):
+        assert len(rh.examples) == len(rd.examples)
+        # same windows in the same order unless two pooled scores tie exactly (torch.topk's tie order is unspecified)
+        key = lambda ex: (-float(ex.activations.max()), ex.tokens.tolist(), ex.activations.tolist())
+        for eh, ed in zip(sorted(rh.examples, key=key), sorted(rd.examples, key=key)):
+            assert torch.equal(eh.tokens, ed.tokens) and torch.equal(eh.activations, ed.activations)
+            n_checked += 1
+        sh = [float(e.activations.max()) for e in rh.examples]
+        sd = [float(e.activations.max()) for e in rd.examples]
+        assert sh == sd == sorted(sd, reverse=True)
+    assert n_checked > 50
+
+
+def test_image_loader_device_route_equals_host_route():
+    """image constructor: ranking by the mean over the base image tokens on the device (sequential file-order sums,
+    bit-equal to the host's) -> same images, same ImageExamples as the host route"""
+    from sae_auto_interp.config import FeatureConfig
+    from sae_auto_interp.features import pool_max_activations_windows_image
+    from sae_auto_interp.features.constructors import image_scores
+    from sae_auto_interp.features.features import Feature, FeatureRecord
+    from sae_auto_interp.features.loader import BufferOutput
+    from saeb200 import engine
+    from synth_images import synth_image_cache
+
+    ds, loc, act = synth_image_cache()
+    feats, offs, scores, wins = engine.coo_top_windows(
+        torch.cat([loc, torch.full((loc.shape[0], 1), 7)], 1) if loc.shape[1] == 2 else loc, act, 6 + 50, n_base=576,
+        device=DEV)
+    assert feats.tolist() == [7]
+    ref = image_scores(loc, act, len(ds), 576)
+    pos = ref > 0
+    order = torch.argsort(-ref[pos], stable=True)
+    want_ids = pos.nonzero().squeeze(1)[order][: 56]
+    assert torch.equal(wins.cpu(), want_ids) and torch.equal(scores.cpu(), ref[want_ids])
+    cfg = FeatureConfig(width=64, max_examples=6)
+    bo = BufferOutput(Feature("layers.0", 7), loc, act)
+    rec_h, rec_d = FeatureRecord(bo.feature), FeatureRecord(bo.feature)
+    pool_max_activations_windows_image(rec_h, bo, ds, cfg, None)
+    pool_max_activations_windows_image(rec_d, bo, ds, cfg, None, ranked=(scores.cpu(), wins.cpu()))
+    assert len(rec_h.examples) == len(rec_d.examples) == 6
+    for eh, ed in zip(rec_h.examples, rec_d.examples):
+        assert torch.equal(eh.activations, ed.activations)
+        assert np.array_equal(np.asarray(eh.image), np.asarray(ed.image))

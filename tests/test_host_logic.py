@@ -194,7 +194,7 @@ def _oracle_backend(monkeypatch):
     def pre_acts(self, x):
         return O.pre_acts(params(self), x.detach().float())
 
-    def encode(self, x, *, clamp_feature=-1, clamp_value=0.0):
+    def encode(self, x, *, clamp_feature=-1, clamp_value=0.0, exact_values=None):
         lat = pre_acts(self, x)
         if clamp_feature >= 0:
             lat[..., clamp_feature] = clamp_value

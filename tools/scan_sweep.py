@@ -14,8 +14,11 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "multimodal-sae_b200"))
 
-# name -> (exchange, waves, refine_max_ctas per SM, aux priority, schedule, gemm stages)
+# name -> (exchange, waves, refine_max_ctas per SM, aux priority, schedule, gemm stages[, packed mode])
 CONFIGS = {
+    "push_w4_m4": ("push", 4, 0, "high", "streams", 0, 4),
+    "nccl_w4_m4": ("nccl", 4, 0, "high", "streams", 0, 4),
+    "push_seq_phases_m4": ("push", 4, 0, "high", "sequential", 0, 4),
     "nccl_w4": ("nccl", 4, 0, "high", "streams", 0),
     "nccl_w8": ("nccl", 8, 0, "high", "streams", 0),
     "push_w4": ("push", 4, 0, "high", "streams", 0),
@@ -66,11 +69,12 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ref = None
     for name in args.configs.split(","):
-        exch, waves, ctas, prio, sched, stages = CONFIGS[name]
+        exch, waves, ctas, prio, sched, stages, *rest = CONFIGS[name]
+        planes = rest[0] if rest else 3
         os.environ["SAEB_SCAN_SCHEDULE"] = "streams" if sched == "sequential" else sched
         _capi.check(L.saeb_set_option(b"gemm_stages", stages), "gemm_stages")
         ops = sdist.EngineOps(sae.encoder.weight.data[lo:hi], sae.encoder.bias.data[lo:hi], sae.b_dec.data, lo, hi,
-                              args.top, ctx, dev, aux_priority=prio)
+                              args.top, ctx, dev, aux_priority=prio, planes=planes)
         ops.exchange = exch if world > 1 else "nccl"
         ops.refine_max_ctas = ctas * num_sms
         chunk = ops.chunk_tokens(world, waves)
@@ -80,7 +84,8 @@ def main():
                 yield xs[t0:min(args.tokens, limit, t0 + chunk)]
 
         out = {"config": name, "world": world, "tokens": args.tokens, "chunk_tokens": chunk, "exchange": exch,
-               "refine_max_ctas": ctas * num_sms, "aux_priority": prio, "schedule": sched, "gemm_stages": stages}
+               "refine_max_ctas": ctas * num_sms, "aux_priority": prio, "schedule": sched, "gemm_stages": stages,
+               "packed_mode": planes}
         try:
             sdist.sharded_scan(chunks(3 * chunk), ops, K, ctx, N)   # warm-up
             ops.scan = engine.TopActivationScan(lo, hi, args.top, ctx, dev)
@@ -122,6 +127,10 @@ def main():
                 if world > 1:
                     dist.all_reduce(same, op=dist.ReduceOp.MIN)
                 out["same_lists_as_first_config"] = bool(same.item() == 1.0)
+                if same.item() != 1.0:
+                    out["windows_equal_frac"] = float((res.top_win == ref.top_win).float().mean().item())
+                    out["max_rel_val_diff"] = float(((res.top_vals - ref.top_vals).abs()
+                                                     / ref.top_vals.abs().clamp_min(1e-30)).max().item())
         except Exception as exc:   # one broken configuration must not waste the multi-GPU call
             out["error"] = repr(exc)[:400]
         if rank == 0:
