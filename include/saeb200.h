@@ -182,9 +182,9 @@ int saeb_decode(const int64_t* idx, const float* vals, int64_t T, int k, const v
  * once.  Input: the file's triples grouped by feature id (stable: file order kept inside a feature) as parallel arrays
  * feature[nnz], window_key[nnz] (text: row * n_win + pos / ctx_len; image: row if pos < n_base; -1 = outside every
  * window), activations[nnz].  For the first entry of every (feature, window) run: head = 1 and score = max of the run
- * (mode 0) or (sequential fp32 sum of the run) * scale (mode 1, scale = 1 / n_base); other entries: head = 0. */
+ * (mode 0) or (sequential fp32 sum of the run) / divisor (mode 1, divisor = n_base); other entries: head = 0. */
 int saeb_coo_window_scores(const int64_t* feature, const int64_t* window_key, const float* activations, int64_t nnz,
-                           int mode, float scale, float* score, int* head, void* stream);
+                           int mode, float divisor, float* score, int* head, void* stream);
 
 /* ---- probing queries -----------------------------------------------------------------------------------------
  * Replaces the hook body of the reference's probing tool (tools/probe_activations.py:109-126):

@@ -114,7 +114,7 @@ int feature_maps_launch(const void* x, int x_dtype, long long T, long long ld_x,
                         int* err_flag, cudaStream_t stream);
 
 int coo_window_scores_launch(const long long* feat, const long long* key, const float* act, long long nnz, int mode,
-                             float scale, float* score, int* head, cudaStream_t stream);
+                             float divisor, float* score, int* head, cudaStream_t stream);
 int set_cta_pair(int v);
 int set_profile(int v);
 float last_encode_ms();
@@ -651,11 +651,11 @@ int saeb_kth_largest_gathered(const float* gathered, int R, int64_t T, int m, in
 }
 
 int saeb_coo_window_scores(const int64_t* feature, const int64_t* window_key, const float* activations, int64_t nnz,
-                           int mode, float scale, float* score, int* head, void* stream) {
+                           int mode, float divisor, float* score, int* head, void* stream) {
   g_err[0] = 0;
   SAEB_REQUIRE(feature && window_key && activations && score && head, "coo_window_scores: null pointer");
   int rc = coo_window_scores_launch(reinterpret_cast<const long long*>(feature),
-                                    reinterpret_cast<const long long*>(window_key), activations, nnz, mode, scale, score,
+                                    reinterpret_cast<const long long*>(window_key), activations, nnz, mode, divisor, score,
                                     head, (cudaStream_t)stream);
   if (rc == 0 && nnz > 0) g_launches += 1;
   return rc;

@@ -191,10 +191,10 @@ int image_pool_launch(const float* vals, const long long* idx, long long n_image
 }
 
 int coo_window_scores_launch(const long long* feat, const long long* key, const float* act, long long nnz, int mode,
-                             float scale, float* score, int* head, cudaStream_t stream) {
+                             float divisor, float* score, int* head, cudaStream_t stream) {
   SAEB_REQUIRE(nnz >= 0 && (mode == 0 || mode == 1), "coo_window_scores: bad arguments");
   if (nnz == 0) return 0;
-  coo_window_scores_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(feat, key, act, nnz, mode, scale, score, head);
+  coo_window_scores_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(feat, key, act, nnz, mode, divisor, score, head);
   SAEB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

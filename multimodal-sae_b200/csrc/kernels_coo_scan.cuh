@@ -263,11 +263,11 @@ __global__ void scan_merge_kernel(uint2* __restrict__ bucket, int* __restrict__ 
 // (row, pos) order) with a window key per entry (text constructor: row * n_win + pos / ctx_len, reference
 // features/constructors.py:11-47; image constructor: the row, for positions below n_base, :109-114; -1 = entry outside
 // every window).  Entries of one (feature, window) are consecutive.  The thread that sits on the FIRST entry of a run
-// reduces the run in file order -- max for the text windows (max_pool1d), a sequential fp32 sum times `scale` for the
-// image mean (the same order as the reference's CPU index_add_ / avg_pool) -- and flags itself as the run's head.
+// reduces the run in file order -- max for the text windows (max_pool1d), a sequential fp32 sum divided by `divisor` for
+// the image mean (the same order as the reference's CPU index_add_ / avg_pool) -- and flags itself as the run's head.
 __global__ void __launch_bounds__(256)
 coo_window_scores_kernel(const long long* __restrict__ feat, const long long* __restrict__ key,
-                         const float* __restrict__ act, long long nnz, int mode, float scale,
+                         const float* __restrict__ act, long long nnz, int mode, float divisor,
                          float* __restrict__ score, int* __restrict__ head) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nnz) return;
@@ -280,7 +280,7 @@ coo_window_scores_kernel(const long long* __restrict__ feat, const long long* __
   }
   float acc = act[i];
   for (long long j = i + 1; j < nnz && feat[j] == f && key[j] == k; ++j) acc = (mode == 0) ? fmaxf(acc, act[j]) : acc + act[j];
-  score[i] = (mode == 0) ? acc : acc * scale;
+  score[i] = (mode == 0) ? acc : acc / divisor;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -158,8 +158,9 @@ class Sae(nn.Module):
         (activation desc, index asc); the reference's order is unspecified (`sorted=False`).  `exact_values` overrides
         `self.refine_values` for this call (the activation cache asks for exact values: it ranks by them)."""
         vm = self._value_mode(exact_values)
-        if torch.is_grad_enabled() and (x.requires_grad or self.encoder.weight.requires_grad
-                                        or self.encoder.bias.requires_grad or self.b_dec.requires_grad):
+        # differentiable when the INPUT carries a gradient (attribution patching through several spliced SAEs); the
+        # encoder's own parameter gradients are a training matter: opt in with `self.train_encoder = True`
+        if torch.is_grad_enabled() and (x.requires_grad or getattr(self, "train_encoder", False)):
             from .utils import SparseEncode   # differentiable like the reference's nn.Linear -> relu -> topk
 
             acts, idx = SparseEncode.apply(x, self.encoder.weight, self.encoder.bias, self.b_dec,

@@ -555,11 +555,11 @@ def coo_top_windows(locations: torch.Tensor, activations: torch.Tensor, n_top: i
         n_win = int(seq_len) // int(ctx_len)
         key = row * n_win + pos // ctx_len
         valid = pos < n_win * ctx_len
-        mode, scale = 0, 1.0
+        mode, divisor = 0, 1.0
     else:
         key = row
         valid = pos < n_base
-        mode, scale = 1, 1.0 / float(n_base)
+        mode, divisor = 1, float(n_base)
     feat, key, acts = feat[valid], key[valid], act[valid]
     nnz = feat.numel()
     if nnz == 0:
@@ -572,7 +572,7 @@ def coo_top_windows(locations: torch.Tensor, activations: torch.Tensor, n_top: i
     score = torch.empty(nnz, dtype=torch.float32, device=dev)
     head = torch.empty(nnz, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        check(L.saeb_coo_window_scores(feat.data_ptr(), key.data_ptr(), acts.data_ptr(), nnz, mode, scale,
+        check(L.saeb_coo_window_scores(feat.data_ptr(), key.data_ptr(), acts.data_ptr(), nnz, mode, divisor,
                                        score.data_ptr(), head.data_ptr(), _stream()), "saeb_coo_window_scores")
     sel = head.nonzero().squeeze(1)
     f_h, k_h, s_h = feat[sel], key[sel], score[sel]

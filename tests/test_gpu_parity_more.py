@@ -492,14 +492,17 @@ def test_loader_device_route_equals_host_route(tmp_path):
     n_checked = 0
     for rh, rd in zip(host, dev):
         assert len(rh.examples) == len(rd.examples)
-        # same windows in the same order unless two pooled scores tie exactly (torch.topk's tie order is unspecified)
-        key = lambda ex: (-float(ex.activations.max()), ex.tokens.tolist(), ex.activations.tolist())
-        for eh, ed in zip(sorted(rh.examples, key=key), sorted(rd.examples, key=key)):
-            assert torch.equal(eh.tokens, ed.tokens) and torch.equal(eh.activations, ed.activations)
-            n_checked += 1
         sh = [float(e.activations.max()) for e in rh.examples]
         sd = [float(e.activations.max()) for e in rd.examples]
-        assert sh == sd == sorted(sd, reverse=True)
+        assert sh == sd == sorted(sd, reverse=True)      # same pooled scores, descending
+        # same windows, except among windows TIED at the cut-off score (repeated tokens give identical activations;
+        # torch.topk's choice among equal values is unspecified, the device route takes the smaller window id)
+        cut = sh[-1] if sh else 0.0
+        key = lambda ex: (ex.tokens.tolist(), ex.activations.tolist())
+        above_h = sorted(key(e) for e in rh.examples if float(e.activations.max()) > cut)
+        above_d = sorted(key(e) for e in rd.examples if float(e.activations.max()) > cut)
+        assert above_h == above_d
+        n_checked += len(above_h)
     assert n_checked > 50
 
 
@@ -533,3 +536,48 @@ def test_image_loader_device_route_equals_host_route():
     for eh, ed in zip(rec_h.examples, rec_d.examples):
         assert torch.equal(eh.activations, ed.activations)
         assert np.array_equal(np.asarray(eh.image), np.asarray(ed.image))
+
+
+def test_fused_encode_is_differentiable_like_the_reference_chain():
+    """Sae.encode under autograd (SparseEncode): gradients w.r.t. the input and the encoder parameters equal those of
+    the reference chain nn.Linear -> relu -> topk -> decode (sae/sae.py:172-191) evaluated with torch ops on the
+    device; two SAEs chained (the multi-layer attribution-patching situation): the gradient reaches the first one's
+    reconstruction through the second one's encoder."""
+    from saeb200 import synth
+
+    T, d, N, k = 96, 256, 2048, 16
+    sae1, sae2 = synth.make_sae(d, N, k, DEV, seed=81), synth.make_sae(d, N, k, DEV, seed=82)
+    for s in (sae1, sae2):
+        s.refine_values = "all"
+        s.requires_grad_(True)
+        s.train_encoder = True
+    x = synth.make_activations(T, d, DEV, seed=83, dtype=torch.float32).requires_grad_(True)
+    wsum = torch.randn(T, d, generator=torch.Generator().manual_seed(84)).to(DEV)
+
+    def fused(inp):
+        r1 = sae1.decode(*sae1.encode(inp))
+        r1.retain_grad()
+        r2 = sae2.decode(*sae2.encode(r1))
+        return r1, (r2 * wsum).sum()
+
+    def dense(sae, inp):
+        pre = torch.relu((inp - sae.b_dec) @ sae.encoder.weight.T + sae.encoder.bias)
+        v, i = pre.topk(k, dim=-1)
+        return (v.unsqueeze(-1) * sae.W_dec[i]).sum(1) + sae.b_dec
+
+    r1, loss = fused(x)
+    loss.backward()
+    got = {"x": x.grad.clone(), "r1": r1.grad.clone(), "W1": sae1.encoder.weight.grad.clone(),
+           "b1": sae1.encoder.bias.grad.clone(), "bd2": sae2.b_dec.grad.clone(), "Wd1": sae1.W_dec.grad.clone()}
+    for t in (x, sae1.encoder.weight, sae1.encoder.bias, sae2.b_dec, sae1.W_dec, sae1.b_dec, sae2.encoder.weight,
+              sae2.encoder.bias, sae2.W_dec):
+        t.grad = None
+    d1 = dense(sae1, x)
+    d1.retain_grad()
+    ((dense(sae2, d1)) * wsum).sum().backward()
+    want = {"x": x.grad, "r1": d1.grad, "W1": sae1.encoder.weight.grad, "b1": sae1.encoder.bias.grad,
+            "bd2": sae2.b_dec.grad, "Wd1": sae1.W_dec.grad}
+    assert got["r1"] is not None and float(got["r1"].abs().max()) > 0     # gradient crossed the second SAE's encoder
+    for name in got:
+        err = (got[name] - want[name]).norm() / want[name].norm()
+        assert float(err) < 1e-3, (name, float(err))
