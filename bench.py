@@ -356,8 +356,8 @@ def time_gathers(torch, L, _capi, engine, sae, enc, x, acts, idx, sae_out, peaks
 
     def refine(merged):
         check(L.saeb_refine_candidates(x.data_ptr(), _capi.BF16, D_IN, prep.data_ptr(), T, 0, T, enc.blob.data_ptr(),
-                                       enc.W_enc.data_ptr(), D_IN, WIDTH, K, 0, -1, 0.0, None, merged, a2.data_ptr(),
-                                       i2.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), 0, value_mode, st), "refine")
+                                       enc.W_enc.data_ptr(), D_IN, WIDTH, K, 0, -1, 0.0, None, None, None, merged,
+                                       a2.data_ptr(), None, i2.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), 0, value_mode, st), "refine")
 
     refine(0)   # merges the candidate lists once; the timed calls below reuse the merged lists
     check(L.saeb_set_option(b"stats", 1), "stats")

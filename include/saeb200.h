@@ -119,9 +119,10 @@ int saeb_encode_candidates(const void* prep, int64_t T_total, int64_t t0, int64_
                            size_t workspace_bytes, void* stream);
 int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total, int64_t t0,
                            int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N, int k, int margin,
-                           int64_t clamp_feature, float clamp_value, const float* ext_lower, int already_merged,
-                           float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
-                           size_t workspace_bytes, int max_ctas, int value_mode, void* stream);
+                           int64_t clamp_feature, float clamp_value, const float* ext_lower, const float* ext_upper,
+                           const float* feat_thr, int already_merged, float* out_vals, float* out_member,
+                           int64_t* out_idx, int32_t* status_out, void* workspace, size_t workspace_bytes,
+                           int max_ctas, int value_mode, void* stream);
 /* value_mode (saeb_encode_topk_refine, saeb_refine_candidates[_lo]): which outputs are re-evaluated exactly.
  *   0  every member of the TopK carries its exact fp32 value (reference grade, ~3e-7 relative);
  *   1  "boundary only": the index SET is still decided rigorously -- every candidate whose error interval
@@ -130,6 +131,16 @@ int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void*
  *      rigorously, ~5e-5 relative in practice at d = 4096; a member whose bound exceeds 2^-7 of its value is
  *      re-evaluated too).  About 10 instead of 70 gathered rows per token at k = 64, N = 131072.  Ignored (treated as
  *      0) for feature-sharded calls (ext_lower != NULL).
+ *   2  "scan": for the top-activation scan.  Membership is decided as in mode 1; a certain member is re-evaluated
+ *      EXACTLY only if it can still enter its feature's top-n list (a_j + eps_j >= feat_thr[feature], feat_thr [N]
+ *      = the scan's current n-th best per feature, may be NULL = always) and is reported with value 0 otherwise;
+ *      every boundary candidate is re-evaluated exactly.  Every value that reaches a list is an exact fp32 value.
+ *      Feature-sharded form: ext_lower [Tc] AND ext_upper [Tc] (an upper bound of the token's global (k+1)-th largest
+ *      upper bound, from the all-gathered ub lists of saeb_candidate_bounds) are given; the shard then also writes
+ *      out_member [Tc,k]: 3e38 for certain members, the exact value for boundary candidates, 0 for padding.  The
+ *      k-th largest of all shards' member values is the token's membership threshold (saeb_kth_largest_gathered);
+ *      pass it as tok_thr and out_member as `member` to saeb_scan_pool.
+ *   ext_upper / feat_thr / out_member are NULL outside mode 2.
  * max_ctas (saeb_refine_candidates[_lo], saeb_decode): 0 = one CTA per token.  > 0 = a persistent grid of at most that
  * many CTAs walks the tokens, and every helper launch of the call uses blocks small enough (<= 256 threads, <= 21 KB
  * of shared memory) to be scheduled on an SM that already hosts a CTA of the fused GEMM: with max_ctas = (1..2) x
@@ -146,16 +157,17 @@ int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void*
 int saeb_refine_candidates_lo(const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total, int64_t t0,
                               int64_t Tc, const void* packed4, const float* W_enc, int64_t d, int64_t N, int k,
                               int margin, int64_t clamp_feature, float clamp_value, const float* ext_lower,
-                              int already_merged, float* out_vals, int64_t* out_idx, int32_t* status_out,
-                              void* workspace, size_t workspace_bytes, int max_ctas, int value_mode, void* stream);
+                              const float* ext_upper, const float* feat_thr, int already_merged, float* out_vals,
+                              float* out_member, int64_t* out_idx, int32_t* status_out, void* workspace,
+                              size_t workspace_bytes, int max_ctas, int value_mode, void* stream);
 /* Feature-sharded use (every GPU holds N/R features, sees all tokens): after saeb_encode_candidates,
  * saeb_candidate_bounds merges this shard's candidates and writes, per token, its k largest LOWER bounds
  * a_j - eps_j (descending, lb_out [Tc,k]).  All-gather them, take the per-token k-th largest (saeb_kth_of_gathered):
  * that is a lower bound of the token's GLOBAL k-th activation; pass it as `ext_lower` (with already_merged = 1) and
  * the shard only re-evaluates candidates that can still be in the global TopK (about k/R + a few per token instead of
- * k + 25). */
+ * k + 25).  ub_out (optional, [Tc,k]): the k largest UPPER bounds a_j + eps_j as well, for value_mode 2. */
 int saeb_candidate_bounds(const void* prep, int64_t T_total, int64_t t0, int64_t Tc, const void* packed, int x_dtype,
-                          int64_t d, int64_t N, int k, int margin, int64_t clamp_feature, float* lb_out,
+                          int64_t d, int64_t N, int k, int margin, int64_t clamp_feature, float* lb_out, float* ub_out,
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* TopK of dense non-negative rows, (value desc, index asc): Sae.select_topk (sae/sae.py:179-181) for callers that hold
@@ -244,13 +256,14 @@ int saeb_coo_append(const float* vals, const int64_t* idx, int64_t T, int k, flo
  * windows of ctx_len tokens and the n_top best windows per feature, ordered (score desc, window asc).
  * saeb_scan_pool processes one chunk of tokens (at most bucket_cap windows): only features in [feat_lo, feat_hi)
  * (this GPU's shard) are kept, local index f - feat_lo.  tok_thr (NULL or [T]) is the per-token global k-th value
- * used under feature sharding.  saeb_scan_merge folds the buckets into the sorted per-feature lists
+ * used under feature sharding: an entry is dropped if its activation -- or, when `member` ([T,k], optional) is given,
+ * member[t][j] instead (value_mode 2 of the refinement) -- is below tok_thr[t].  saeb_scan_merge folds the buckets into the sorted per-feature lists
  * top_vals [F,n_top] f32 / top_win [F,n_top] i64 (-1 = empty), refreshes feat_thr and clears the bucket counters.
  * Initialise feat_thr to the activation threshold (1e-5), top_win to -1, bucket_cnt to 0. */
 int saeb_scan_pool(const float* vals, const int64_t* idx, int64_t T, int k, int ctx_len, float threshold,
                    int64_t feat_lo, int64_t feat_hi, int64_t window_base, const float* tok_thr,
-                   const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap, int* overflow_flag,
-                   void* stream);
+                   const float* member, const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap,
+                   int* overflow_flag, void* stream);
 int saeb_scan_merge(void* bucket, int* bucket_cnt, int bucket_cap, int64_t F, int n_top, float base_threshold,
                     float* top_vals, int64_t* top_win, float* feat_thr, void* stream);
 /* Image form of the scan (replaces, for all features at once, pool_max_activations_windows_image,

@@ -51,12 +51,13 @@ int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const
                   const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                   float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
                   float* dense_scratch, const float* ext_lower, const void* w_lo, long long ld_w, int max_ctas,
-                  int value_mode, cudaStream_t stream);
+                  int value_mode, const float* ext_upper, const float* feat_thr, float* out_member,
+                  cudaStream_t stream);
 int pack_weights_lo_launch(const float* W_enc, long long N, long long d, long long d_pad, const float* trailer,
                            void* lo_plane, cudaStream_t stream);
 int candidate_bounds_launch(const float* cand_vals, const long long* cand_idx, long long T, int K2, int k,
                             const float* wnorm, const float* dnorm, const float* xnorm, const float* xdnorm,
-                            float c_eps, long long clamp_feature, float* lb_out, cudaStream_t stream);
+                            float c_eps, long long clamp_feature, float* lb_out, float* ub_out, cudaStream_t stream);
 int dense_topk_launch(const float* dense, long long T, long long ld, long long N, int k, float* out_vals,
                       long long* out_idx, cudaStream_t stream);
 int set_splits(int v);
@@ -103,8 +104,8 @@ int push_gather_launch(const void* src, size_t bytes, void* const* peer_bases_de
                        int* counter, cudaStream_t stream);
 int scan_pool_launch(const float* vals, const long long* idx, long long T, int k, int ctx_len, float threshold,
                      long long feat_lo, long long feat_hi, long long window_base, const float* tok_thr,
-                     const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap, int* overflow,
-                     cudaStream_t stream);
+                     const float* member, const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap,
+                     int* overflow, cudaStream_t stream);
 int scan_merge_launch(void* bucket, int* bucket_cnt, int bucket_cap, long long F, int n_top, float base_thr,
                       float* top_vals, long long* top_win, float* feat_thr, cudaStream_t stream);
 
@@ -394,7 +395,7 @@ static inline float refine_c_eps(int /*x_dtype*/) {
 // already_merged = 1).
 int saeb_candidate_bounds(const void* prep, int64_t T_total, int64_t t0, int64_t Tc, const void* packed, int x_dtype,
                           int64_t d, int64_t N, int k, int margin, int64_t clamp_feature, float* lb_out,
-                          void* workspace, size_t workspace_bytes, void* stream) {
+                          float* ub_out, void* workspace, size_t workspace_bytes, void* stream) {
   g_err[0] = 0;
   SAEB_REQUIRE(prep && packed && lb_out && workspace, "candidate_bounds: null pointer");
   SAEB_REQUIRE(t0 >= 0 && Tc >= 0 && t0 + Tc <= T_total, "candidate_bounds: bad row range");
@@ -417,7 +418,7 @@ int saeb_candidate_bounds(const void* prep, int64_t T_total, int64_t t0, int64_t
   rc = candidate_bounds_launch(mvals, midx, Tc, K2, k < K2 ? k : K2, wnorm, dnorm,
                                reinterpret_cast<const float*>(pb + p.xnorm) + t0,
                                reinterpret_cast<const float*>(pb + p.xdnorm) + t0, refine_c_eps(x_dtype), clamp_feature,
-                               lb_out, st);
+                               lb_out, ub_out, st);
   if (rc == 0) g_launches += 2;
   return rc;
 }
@@ -425,13 +426,15 @@ int saeb_candidate_bounds(const void* prep, int64_t T_total, int64_t t0, int64_t
 static int refine_candidates_impl(bool lo, const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total,
                                   int64_t t0, int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N,
                                   int k, int margin, int64_t clamp_feature, float clamp_value, const float* ext_lower,
-                                  int already_merged, float* out_vals, int64_t* out_idx, int32_t* status_out,
-                                  void* workspace, size_t workspace_bytes, int max_ctas, int value_mode,
-                                  void* stream) {
+                                  const float* ext_upper, const float* feat_thr, int already_merged, float* out_vals,
+                                  float* out_member, int64_t* out_idx, int32_t* status_out, void* workspace,
+                                  size_t workspace_bytes, int max_ctas, int value_mode, void* stream) {
   g_err[0] = 0;
   SAEB_REQUIRE(x && prep && packed && W_enc && out_vals && out_idx && workspace, "refine_candidates: null pointer");
   SAEB_REQUIRE(max_ctas >= 0, "refine_candidates: max_ctas must be >= 0");
-  SAEB_REQUIRE(value_mode == 0 || value_mode == 1, "refine_candidates: value_mode must be 0 (exact values) or 1");
+  SAEB_REQUIRE(value_mode >= 0 && value_mode <= 2, "refine_candidates: value_mode must be 0, 1 or 2");
+  SAEB_REQUIRE(ext_upper == nullptr || (value_mode == 2 && ext_lower != nullptr && out_member != nullptr),
+               "refine_candidates: ext_upper needs value_mode 2, ext_lower and out_member");
   SAEB_REQUIRE(t0 >= 0 && Tc >= 0 && t0 + Tc <= T_total, "refine_candidates: bad row range");
   if (Tc == 0) return 0;
   const int K2raw = refine_k2(k, margin);
@@ -461,7 +464,8 @@ static int refine_candidates_impl(bool lo, const void* x, int x_dtype, int64_t l
                      reinterpret_cast<const float*>(pb + p.xdnorm) + t0, refine_c_eps(x_dtype), mvals, midx, K2,
                      k < K2 ? k : K2, clamp_feature, clamp_value, out_vals, reinterpret_cast<long long*>(out_idx), status,
                      reinterpret_cast<int*>(ws + w.flag_rows), reinterpret_cast<float*>(ws + w.dense), ext_lower,
-                     lo ? pk + mode3_bytes(N, d) : nullptr, pad8(d), max_ctas, value_mode, st);
+                     lo ? pk + mode3_bytes(N, d) : nullptr, pad8(d), max_ctas, value_mode, ext_upper, feat_thr,
+                     out_member, st);
   if (rc) return rc;
   if (status_out != nullptr)
     SAEB_CHECK_CUDA(cudaMemcpyAsync(status_out, status, sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -471,22 +475,26 @@ static int refine_candidates_impl(bool lo, const void* x, int x_dtype, int64_t l
 
 int saeb_refine_candidates(const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total, int64_t t0,
                            int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N, int k, int margin,
-                           int64_t clamp_feature, float clamp_value, const float* ext_lower, int already_merged,
-                           float* out_vals, int64_t* out_idx, int32_t* status_out, void* workspace,
-                           size_t workspace_bytes, int max_ctas, int value_mode, void* stream) {
+                           int64_t clamp_feature, float clamp_value, const float* ext_lower, const float* ext_upper,
+                           const float* feat_thr, int already_merged, float* out_vals, float* out_member,
+                           int64_t* out_idx, int32_t* status_out, void* workspace, size_t workspace_bytes,
+                           int max_ctas, int value_mode, void* stream) {
   return refine_candidates_impl(false, x, x_dtype, ld_x, prep, T_total, t0, Tc, packed, W_enc, d, N, k, margin,
-                                clamp_feature, clamp_value, ext_lower, already_merged, out_vals, out_idx, status_out,
-                                workspace, workspace_bytes, max_ctas, value_mode, stream);
+                                clamp_feature, clamp_value, ext_lower, ext_upper, feat_thr, already_merged, out_vals,
+                                out_member, out_idx, status_out, workspace, workspace_bytes, max_ctas, value_mode,
+                                stream);
 }
 
 int saeb_refine_candidates_lo(const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total, int64_t t0,
                               int64_t Tc, const void* packed4, const float* W_enc, int64_t d, int64_t N, int k,
                               int margin, int64_t clamp_feature, float clamp_value, const float* ext_lower,
-                              int already_merged, float* out_vals, int64_t* out_idx, int32_t* status_out,
-                              void* workspace, size_t workspace_bytes, int max_ctas, int value_mode, void* stream) {
+                              const float* ext_upper, const float* feat_thr, int already_merged, float* out_vals,
+                              float* out_member, int64_t* out_idx, int32_t* status_out, void* workspace,
+                              size_t workspace_bytes, int max_ctas, int value_mode, void* stream) {
   return refine_candidates_impl(true, x, x_dtype, ld_x, prep, T_total, t0, Tc, packed4, W_enc, d, N, k, margin,
-                                clamp_feature, clamp_value, ext_lower, already_merged, out_vals, out_idx, status_out,
-                                workspace, workspace_bytes, max_ctas, value_mode, stream);
+                                clamp_feature, clamp_value, ext_lower, ext_upper, feat_thr, already_merged, out_vals,
+                                out_member, out_idx, status_out, workspace, workspace_bytes, max_ctas, value_mode,
+                                stream);
 }
 
 size_t saeb_encode_topk_refine_workspace_bytes(int64_t T, int64_t d, int64_t N, int k, int margin) {
@@ -510,8 +518,8 @@ int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x,
                               workspace_bytes - prep_bytes, stream);
   if (rc) return rc;
   return saeb_refine_candidates(x, x_dtype, ld_x, ws, T, 0, T, packed, W_enc, d, N, k, margin, clamp_feature,
-                                clamp_value, nullptr, 0, out_vals, out_idx, status_out, ws + prep_bytes,
-                                workspace_bytes - prep_bytes, 0, value_mode, stream);
+                                clamp_value, nullptr, nullptr, nullptr, 0, out_vals, nullptr, out_idx, status_out,
+                                ws + prep_bytes, workspace_bytes - prep_bytes, 0, value_mode, stream);
 }
 
 int saeb_dense_topk(const float* dense, int64_t T, int64_t ld, int64_t N, int k, float* out_vals, int64_t* out_idx,
@@ -600,12 +608,12 @@ int saeb_coo_append(const float* vals, const int64_t* idx, int64_t T, int k, flo
 
 int saeb_scan_pool(const float* vals, const int64_t* idx, int64_t T, int k, int ctx_len, float threshold,
                    int64_t feat_lo, int64_t feat_hi, int64_t window_base, const float* tok_thr,
-                   const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap, int* overflow_flag,
-                   void* stream) {
+                   const float* member, const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap,
+                   int* overflow_flag, void* stream) {
   g_err[0] = 0;
   SAEB_REQUIRE(vals && idx && feat_thr && bucket && bucket_cnt, "scan_pool: null pointer");
   int rc = scan_pool_launch(vals, reinterpret_cast<const long long*>(idx), T, k, ctx_len, threshold, feat_lo, feat_hi,
-                            window_base, tok_thr, feat_thr, bucket, bucket_cnt, bucket_cap, overflow_flag,
+                            window_base, tok_thr, member, feat_thr, bucket, bucket_cnt, bucket_cap, overflow_flag,
                             (cudaStream_t)stream);
   if (rc == 0) g_launches += 1;
   return rc;

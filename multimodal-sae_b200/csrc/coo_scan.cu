@@ -96,8 +96,8 @@ int kth_gathered_launch(const float* gathered, int R, long long T, int m, int kt
 // ---------------------------------------------------------------------------------------------
 int scan_pool_launch(const float* vals, const long long* idx, long long T, int k, int ctx_len, float threshold,
                      long long feat_lo, long long feat_hi, long long window_base, const float* tok_thr,
-                     const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap, int* overflow,
-                     cudaStream_t stream) {
+                     const float* member, const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap,
+                     int* overflow, cudaStream_t stream) {
   SAEB_REQUIRE(T > 0 && k >= 1 && ctx_len >= 1, "scan_pool: bad arguments");
   const long long n_win = (T + ctx_len - 1) / ctx_len;
   SAEB_REQUIRE(n_win <= bucket_cap, "scan_pool: %lld windows per call exceed the bucket capacity %d", n_win,
@@ -109,7 +109,7 @@ int scan_pool_launch(const float* vals, const long long* idx, long long T, int k
   const size_t smem = (size_t)slots * 8;
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(scan_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   scan_pool_kernel<<<(unsigned)n_win, 256, smem, stream>>>(vals, idx, T, k, ctx_len, threshold, feat_lo, feat_hi,
-                                                          window_base, tok_thr, feat_thr,
+                                                          window_base, tok_thr, member, feat_thr,
                                                           reinterpret_cast<uint2*>(bucket), bucket_cnt, bucket_cap,
                                                           slots, overflow);
   SAEB_CHECK_CUDA(cudaGetLastError());

@@ -155,7 +155,8 @@ constexpr uint32_t HASH_EMPTY = 0xffffffffu;
 __global__ void scan_pool_kernel(const float* __restrict__ vals, const long long* __restrict__ idx, long long T, int k,
                                  int ctx_len, float threshold, long long feat_lo, long long feat_hi,
                                  long long window_base, const float* __restrict__ tok_thr,
-                                 const float* __restrict__ feat_thr, uint2* __restrict__ bucket,
+                                 const float* __restrict__ member, const float* __restrict__ feat_thr,
+                                 uint2* __restrict__ bucket,
                                  int* __restrict__ bucket_cnt, int bucket_cap, int slots, int* __restrict__ overflow) {
   extern __shared__ uint32_t hsm[];
   uint32_t* hkey = hsm;
@@ -175,7 +176,9 @@ __global__ void scan_pool_kernel(const float* __restrict__ vals, const long long
     const float v = vals[t * k + (e % k)];
     const long long f = idx[t * k + (e % k)];
     if (!(v > threshold) || f < feat_lo || f >= feat_hi) continue;
-    if (tok_thr != nullptr && v < tok_thr[t]) continue;   // not in the token's global top-k
+    // not in the token's global top-k?  `member` (optional, same layout as vals): the value that decides membership
+    // when it is not the activation itself (value_mode 2 of the sharded refinement: MEMBER_SURE for certain members)
+    if (tok_thr != nullptr && (member != nullptr ? member[t * k + (e % k)] : v) < tok_thr[t]) continue;
     const uint32_t key = (uint32_t)(f - feat_lo);
     uint32_t s = (key * 2654435761u) & mask;
     while (true) {

@@ -24,7 +24,8 @@ refine_body(const XT* __restrict__ x, long long ld_x, const float* __restrict__ 
             const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
             float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
             int* __restrict__ flag_rows, const float* __restrict__ ext_lower, const __half* __restrict__ Wlo,
-            long long ld_w, long long T, unsigned long long* __restrict__ stats, int value_mode) {
+            long long ld_w, long long T, unsigned long long* __restrict__ stats, int value_mode,
+            const float* __restrict__ ext_upper, const float* __restrict__ feat_thr, float* __restrict__ out_member) {
   extern __shared__ float rsm[];
   float* xs = rsm;                                   // [d4] activations of this row as fp32
   const int d4 = LO ? (int)((d + 7) & ~7ll) : (int)((d + 3) & ~3ll);   // LO: padded like the packed weight rows
@@ -172,29 +173,51 @@ refine_body(const XT* __restrict__ x, long long ld_x, const float* __restrict__ 
   //   candidates with a_j + eps_j < L are out; only the ones in between are gathered and re-evaluated, and the best
   //   (k - #certain) of them complete the set.  Certain members keep the tensor-core value a_j (|a_j - exact| <= eps_j
   //   rigorously; a member whose bound is looser than 2^-7 of its value is re-evaluated as well).
-  const bool boundary_only = value_mode == 1 && ext_lower == nullptr;
+  // value_mode 2 ("scan"): the caller only wants the members of the TopK that can still enter their feature's top-n
+  //   list (upper bound >= feat_thr[feature], the feature's current n-th best; lists only ever rise, so a stale
+  //   threshold is merely conservative).  Membership is decided as in mode 1; a certain member that cannot enter its
+  //   list is not gathered at all (reported with value 0), one that can is re-evaluated EXACTLY, and so is every
+  //   boundary candidate: every value that reaches a list is an exact fp32 value.
+  //   Feature-sharded form (ext_upper given = an upper bound of the token's GLOBAL (k+1)-th largest upper bound):
+  //   the shard cannot finish the membership decision alone, so it also writes `out_member`: MEMBER_SURE for certain
+  //   members, the exact value for boundary candidates -- the k-th largest of all shards' member values is then the
+  //   exact value of the weakest member among the boundary candidates (or MEMBER_SURE if there is none), and an entry
+  //   belongs to the token's TopK iff its member value reaches it.
+  constexpr float MEMBER_SURE = 3.0e38f;
+  const bool scan_mode = value_mode == 2;
+  const bool sharded_scan = scan_mode && ext_upper != nullptr;
+  const bool boundary_only = (value_mode == 1 && ext_lower == nullptr) || scan_mode;
   if (boundary_only) {
-    for (int j = tid; j < K2; j += nthr) {
-      if (a[j] > 0.f) {
-        int rank = 0;
-        const float u = ub[j];
-        for (int i = 0; i < K2; ++i) rank += (ub[i] > u || (ub[i] == u && i < j)) ? 1 : 0;
-        if (rank == k) s_U = u;
+    if (!sharded_scan) {
+      for (int j = tid; j < K2; j += nthr) {
+        if (a[j] > 0.f) {
+          int rank = 0;
+          const float u = ub[j];
+          for (int i = 0; i < K2; ++i) rank += (ub[i] > u || (ub[i] == u && i < j)) ? 1 : 0;
+          if (rank == k) s_U = u;
+        }
       }
+      __syncthreads();
     }
-    __syncthreads();
-    const float U = (nv > k) ? s_U : 0.f;
+    const float U = sharded_scan ? ext_upper[t] : ((nv > k) ? s_U : 0.f);
     int my_in = 0;
     for (int j = tid; j < K2; j += nthr) {
       int c = 0;
       if (a[j] > 0.f) {
         const float l = lb[j], eps = 0.5f * (ub[j] - l);
-        if (l > U && l > 0.f && eps <= a[j] * 0.0078125f) {
-          c = 1;
-          ex[j] = a[j];
+        if (l > U && l > 0.f && (scan_mode || eps <= a[j] * 0.0078125f)) {
           ++my_in;
+          if (!scan_mode) {
+            c = 1;             // certain member, keeps the tensor-core value
+            ex[j] = a[j];
+          } else if (feat_thr == nullptr || ub[j] >= feat_thr[f[j]]) {
+            c = 3;             // certain member that can enter its feature's list: exact value wanted
+          } else {
+            c = 1;             // certain member that cannot: not gathered
+            ex[j] = 0.f;
+          }
         } else if (ub[j] >= L) {
-          c = 2;
+          c = 2;               // membership undecided: exact value needed
         }
       }
       st[j] = c;
@@ -209,27 +232,69 @@ refine_body(const XT* __restrict__ x, long long ld_x, const float* __restrict__ 
     }
     __syncthreads();
     for (int j = warp; j < K2; j += nwarps)
-      if (st[j] == 2) evaluate(j);
+      if (st[j] >= 2) evaluate(j);
     __syncthreads();
-    // keep the best (k - #certain) evaluated candidates, drop the rest: afterwards exactly the members of the TopK are
-    // positive in ex[] and the common final pass only has to order them
-    const int need = k - s_cnt[3];
-    int* drop = reinterpret_cast<int*>(lb);   // the bounds are not needed any more
-    for (int j = tid; j < K2; j += nthr) {
-      int dr = 0;
-      if (st[j] == 2 && ex[j] > 0.f) {
-        const float v = ex[j];
-        const int fj = f[j];
-        int rank = 0;
-        for (int i = 0; i < K2; ++i) rank += (st[i] == 2 && (ex[i] > v || (ex[i] == v && f[i] < fj))) ? 1 : 0;
-        dr = rank >= need;
+    if (!sharded_scan) {
+      // keep the best (k - #certain) evaluated boundary candidates, drop the rest: afterwards exactly the members of
+      // the TopK (that are wanted) are positive in ex[] and the common final pass only has to order them
+      const int need = k - s_cnt[3];
+      int* drop = reinterpret_cast<int*>(lb);   // the bounds are not needed any more
+      for (int j = tid; j < K2; j += nthr) {
+        int dr = 0;
+        if (st[j] == 2 && ex[j] > 0.f) {
+          const float v = ex[j];
+          const int fj = f[j];
+          int rank = 0;
+          for (int i = 0; i < K2; ++i) rank += (st[i] == 2 && (ex[i] > v || (ex[i] == v && f[i] < fj))) ? 1 : 0;
+          dr = rank >= need;
+        }
+        drop[j] = dr;
       }
-      drop[j] = dr;
+      __syncthreads();
+      for (int j = tid; j < K2; j += nthr)
+        if (drop[j]) ex[j] = -1.f;
+      __syncthreads();
+    } else {
+      // sharded: hand every certain member and every positive boundary candidate to the caller, ordered by member value
+      float* mem = lb;   // the bounds are not needed any more
+      for (int j = tid; j < K2; j += nthr) {
+        float m = -1.f;
+        if (st[j] == 1 || st[j] == 3) m = MEMBER_SURE;
+        else if (st[j] == 2 && ex[j] > 0.f) m = ex[j];
+        mem[j] = m;
+      }
+      __syncthreads();
+      int my_out = 0;
+      for (int j = tid; j < K2; j += nthr) {
+        const float m = mem[j];
+        if (m > 0.f) {
+          ++my_out;
+          const int fj = f[j];
+          int rank = 0;
+          for (int i = 0; i < K2; ++i) rank += (mem[i] > m || (mem[i] == m && f[i] < fj)) ? 1 : 0;
+          if (rank < k) {
+            out_vals[t * k + rank] = fmaxf(ex[j], 0.f);
+            out_member[t * k + rank] = m;
+            out_idx[t * k + rank] = fj;
+          }
+        }
+      }
+      if (my_out) atomicAdd(&s_cnt[1], my_out);
+      __syncthreads();
+      const int nout = s_cnt[1];
+      if (nout > k && tid == 0) {   // more potential members on this shard than output slots: exact dense fallback
+        const int slot = atomicAdd(&status[0], 1);
+        flag_rows[slot] = (int)t;
+      }
+      for (int j = (nout < k ? nout : k) + tid; j < k; j += nthr) {
+        out_vals[t * k + j] = 0.f;
+        out_member[t * k + j] = 0.f;
+        out_idx[t * k + j] = 0;
+      }
+      __syncthreads();
+      if (stats != nullptr && tid == 0) atomicAdd(stats + 7, (unsigned long long)s_cnt[2]);
+      continue;   // next token of the persistent loop
     }
-    __syncthreads();
-    for (int j = tid; j < K2; j += nthr)
-      if (drop[j]) ex[j] = -1.f;
-    __syncthreads();
   } else {
   // stage A: the k best candidates by approximate value (the merged list is sorted by a, descending)
   for (int j = warp; j < k; j += nwarps)
@@ -314,10 +379,11 @@ refine_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict_
               const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
               float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
               int* __restrict__ flag_rows, const float* __restrict__ ext_lower, long long T,
-              unsigned long long* __restrict__ stats, int value_mode) {
+              unsigned long long* __restrict__ stats, int value_mode, const float* __restrict__ ext_upper,
+              const float* __restrict__ feat_thr, float* __restrict__ out_member) {
   refine_body<XT, false>(x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k,
                          clamp_feature, clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, nullptr, 0, T,
-                         stats, value_mode);
+                         stats, value_mode, ext_upper, feat_thr, out_member);
 }
 
 template <typename XT>
@@ -329,10 +395,11 @@ refine_lo_kernel(const XT* __restrict__ x, long long ld_x, const __half* __restr
                  const long long* __restrict__ cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
                  float* __restrict__ out_vals, long long* __restrict__ out_idx, int* __restrict__ status,
                  int* __restrict__ flag_rows, const float* __restrict__ ext_lower, long long T,
-                 unsigned long long* __restrict__ stats, int value_mode) {
+                 unsigned long long* __restrict__ stats, int value_mode, const float* __restrict__ ext_upper,
+                 const float* __restrict__ feat_thr, float* __restrict__ out_member) {
   refine_body<XT, true>(x, ld_x, nullptr, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx,
                         K2, k, clamp_feature, clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, Wlo, ld_w, T,
-                        stats, value_mode);
+                        stats, value_mode, ext_upper, feat_thr, out_member);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -344,8 +411,10 @@ __global__ void __launch_bounds__(128)
 candidate_bounds_kernel(const float* __restrict__ cand_vals, const long long* __restrict__ cand_idx, int K2, int k,
                         const float* __restrict__ wnorm, const float* __restrict__ dnorm,
                         const float* __restrict__ xnorm, const float* __restrict__ xdnorm, float c_eps,
-                        long long clamp_feature, float* __restrict__ lb_out) {
-  extern __shared__ float bsm[];   // [K2]
+                        long long clamp_feature, float* __restrict__ lb_out, float* __restrict__ ub_out) {
+  // ub_out (optional): the k largest UPPER bounds a_j + eps_j as well (descending): all-gathered, their (k+1)-th
+  // largest bounds the token's global (k+1)-th value from above (value_mode 2 of the refinement)
+  extern __shared__ float bsm[];   // [K2] lower bounds | [K2] upper bounds
   const long long t = blockIdx.x;
   const float xn = xnorm[t], xdn = xdnorm[t];
   for (int j = threadIdx.x; j < K2; j += blockDim.x) {
@@ -354,14 +423,24 @@ candidate_bounds_kernel(const float* __restrict__ cand_vals, const long long* __
     const float wn = wnorm[fj];
     const float eps = (fj == clamp_feature) ? 0.f : 1.001f * (xn * dnorm[fj] + xdn * wn) + c_eps * xn * wn;
     bsm[j] = (av > 0.f) ? fmaxf(av - eps, 0.f) : 0.f;
+    bsm[K2 + j] = (av > 0.f) ? av + eps : 0.f;
   }
-  for (int j = threadIdx.x; j < k; j += blockDim.x) lb_out[t * k + j] = 0.f;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    lb_out[t * k + j] = 0.f;
+    if (ub_out != nullptr) ub_out[t * k + j] = 0.f;
+  }
   __syncthreads();
   for (int j = threadIdx.x; j < K2; j += blockDim.x) {
     const float l = bsm[j];
     int rank = 0;
     for (int i = 0; i < K2; ++i) rank += (bsm[i] > l || (bsm[i] == l && i < j)) ? 1 : 0;
     if (rank < k) lb_out[t * k + rank] = l;
+    if (ub_out != nullptr) {
+      const float u = bsm[K2 + j];
+      rank = 0;
+      for (int i = 0; i < K2; ++i) rank += (bsm[K2 + i] > u || (bsm[K2 + i] == u && i < j)) ? 1 : 0;
+      if (rank < k) ub_out[t * k + rank] = u;
+    }
   }
 }
 
@@ -400,7 +479,8 @@ exact_rows_kernel(const XT* __restrict__ x, long long ld_x, const float* __restr
 
 // TopK of one dense non-negative row (value desc, index asc) by a whole block; `dsm` = kp2 uint2 of shared memory.
 __device__ __forceinline__ void dense_topk_block(const float* row, long long N, int k, uint2* dsm, long long orow,
-                                                 float* __restrict__ out_vals, long long* __restrict__ out_idx) {
+                                                 float* __restrict__ out_vals, long long* __restrict__ out_idx,
+                                                 float* __restrict__ out_member = nullptr) {
   __shared__ int s_red[32];
   __shared__ int s_count;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
@@ -476,6 +556,7 @@ __device__ __forceinline__ void dense_topk_block(const float* row, long long N, 
   for (int i = tid; i < k; i += blockDim.x) {
     out_vals[orow * k + i] = __uint_as_float(dsm[i].x);
     out_idx[orow * k + i] = (long long)dsm[i].y;
+    if (out_member != nullptr) out_member[orow * k + i] = __uint_as_float(dsm[i].x);   // exact values decide membership
   }
   __syncthreads();
 }
@@ -485,12 +566,12 @@ __device__ __forceinline__ void dense_topk_block(const float* row, long long N, 
 __global__ void __launch_bounds__(1024)
 dense_topk_kernel(const float* __restrict__ dense, long long ld, long long N, int k, const int* __restrict__ n_rows_dev,
                   int max_rows, const int* __restrict__ row_map, float* __restrict__ out_vals,
-                  long long* __restrict__ out_idx) {
+                  long long* __restrict__ out_idx, float* __restrict__ out_member) {
   extern __shared__ uint2 dsm[];   // [kp2] selected (value bits, index)
   const int slot = blockIdx.x;
   if (n_rows_dev != nullptr && slot >= min(*n_rows_dev, max_rows)) return;
   const long long orow = row_map ? row_map[slot] : slot;
-  dense_topk_block(dense + (long long)slot * ld, N, k, dsm, orow, out_vals, out_idx);
+  dense_topk_block(dense + (long long)slot * ld, N, k, dsm, orow, out_vals, out_idx, out_member);
 }
 
 // Flagged rows beyond the first RF_MAX_FLAG (degenerate inputs: massive ties, k close to N): block b walks the slots
@@ -501,7 +582,7 @@ __global__ void __launch_bounds__(1024)
 overflow_rows_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict__ W, long long d, long long N,
                      const float* __restrict__ bias, const int* __restrict__ status, const int* __restrict__ flag_rows,
                      long long clamp_feature, float clamp_value, float* dense, int k, float* __restrict__ out_vals,
-                     long long* __restrict__ out_idx) {
+                     long long* __restrict__ out_idx, float* __restrict__ out_member) {
   extern __shared__ uint2 osm[];   // [kp2] uint2 | [d] float
   const int nflag = status[0];
   if (nflag <= RF_MAX_FLAG) return;
@@ -527,7 +608,7 @@ overflow_rows_kernel(const XT* __restrict__ x, long long ld_x, const float* __re
       }
     }
     __syncthreads();
-    dense_topk_block(my, N, k, osm, t, out_vals, out_idx);
+    dense_topk_block(my, N, k, osm, t, out_vals, out_idx, out_member);
   }
 }
 

@@ -26,10 +26,10 @@ unsigned long long* stats_ptr();   // encode_topk.cu: device counters of option 
 
 int candidate_bounds_launch(const float* cand_vals, const long long* cand_idx, long long T, int K2, int k,
                             const float* wnorm, const float* dnorm, const float* xnorm, const float* xdnorm,
-                            float c_eps, long long clamp_feature, float* lb_out, cudaStream_t stream) {
+                            float c_eps, long long clamp_feature, float* lb_out, float* ub_out, cudaStream_t stream) {
   if (T == 0) return 0;
-  candidate_bounds_kernel<<<(unsigned)T, 128, (size_t)K2 * sizeof(float), stream>>>(
-      cand_vals, cand_idx, K2, k, wnorm, dnorm, xnorm, xdnorm, c_eps, clamp_feature, lb_out);
+  candidate_bounds_kernel<<<(unsigned)T, 128, (size_t)2 * K2 * sizeof(float), stream>>>(
+      cand_vals, cand_idx, K2, k, wnorm, dnorm, xnorm, xdnorm, c_eps, clamp_feature, lb_out, ub_out);
   SAEB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -59,7 +59,8 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
                            const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                            float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
                            float* dense_scratch, const float* ext_lower, const __half* w_lo, long long ld_w,
-                           int max_ctas, int value_mode, cudaStream_t stream) {
+                           int max_ctas, int value_mode, const float* ext_upper, const float* feat_thr,
+                           float* out_member, cudaStream_t stream) {
   // feature-sharded calls evaluate only a handful of candidates per token: smaller blocks, more tokens in flight
   const int threads = ext_lower != nullptr ? g_refine_threads_sharded : RF_THREADS;
   // max_ctas > 0: persistent grid (tokens walked with stride gridDim.x), sized by the caller so that a fixed number of
@@ -81,7 +82,8 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
     SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, threads, smem, stream>>>(x, ld_x, w_lo, ld_w, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps,
                                             cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx,
-                                            status, flag_rows, ext_lower, T, stats_ptr(), value_mode);
+                                            status, flag_rows, ext_lower, T, stats_ptr(), value_mode, ext_upper, feat_thr,
+                                            out_member);
   }
   if (!use_lo) {
     const int d4 = (int)((d + 3) & ~3ll);
@@ -91,7 +93,8 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
     SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, threads, smem, stream>>>(x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps,
                                             cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx,
-                                            status, flag_rows, ext_lower, T, stats_ptr(), value_mode);
+                                            status, flag_rows, ext_lower, T, stats_ptr(), value_mode, ext_upper, feat_thr,
+                                            out_member);
   }
   SAEB_CHECK_CUDA(cudaGetLastError());
   // exact dense fallback for the (normally zero) flagged rows; the grids exit at once when nothing is flagged
@@ -108,13 +111,13 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
   // when nothing is flagged, must never make the stream wait for a GEMM launch boundary
   const int fb_threads = max_ctas > 0 ? 256 : 1024;
   dense_topk_kernel<<<RF_MAX_FLAG, fb_threads, (size_t)kp2 * sizeof(uint2), stream>>>(
-      dense_scratch, N, N, k, status, RF_MAX_FLAG, flag_rows, out_vals, out_idx);
+      dense_scratch, N, N, k, status, RF_MAX_FLAG, flag_rows, out_vals, out_idx, out_member);
   SAEB_CHECK_CUDA(cudaGetLastError());
   auto ok = overflow_rows_kernel<XT>;
   const size_t osmem = (size_t)kp2 * sizeof(uint2) + (size_t)d * sizeof(float);
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(ok, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osmem));
   ok<<<RF_MAX_FLAG, fb_threads, osmem, stream>>>(x, ld_x, W, d, N, bias, status, flag_rows, clamp_feature, clamp_value,
-                                           dense_scratch, k, out_vals, out_idx);
+                                           dense_scratch, k, out_vals, out_idx, out_member);
   SAEB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -125,13 +128,14 @@ int refine_launch(const void* x, int x_dtype, long long T, long long ld_x, const
                   const float* cand_vals, const long long* cand_idx, int K2, int k, long long clamp_feature,
                   float clamp_value, float* out_vals, long long* out_idx, int* status, int* flag_rows,
                   float* dense_scratch, const float* ext_lower, const void* w_lo, long long ld_w, int max_ctas,
-                  int value_mode, cudaStream_t stream) {
+                  int value_mode, const float* ext_upper, const float* feat_thr, float* out_member,
+                  cudaStream_t stream) {
 #define SAEB_RF(XT)                                                                                                  \
   return refine_launch_t<XT>(reinterpret_cast<const XT*>(x), T, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm,   \
                              xdnorm, c_eps,                                                                          \
                              cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx, status,      \
                              flag_rows, dense_scratch, ext_lower, reinterpret_cast<const __half*>(w_lo), ld_w,       \
-                             max_ctas, value_mode, stream)
+                             max_ctas, value_mode, ext_upper, feat_thr, out_member, stream)
   if (x_dtype == DT_F32) SAEB_RF(float);
   if (x_dtype == DT_BF16) SAEB_RF(__nv_bfloat16);
   if (x_dtype == DT_F16) SAEB_RF(__half);
@@ -147,7 +151,7 @@ int dense_topk_launch(const float* dense, long long T, long long ld, long long N
   int kp2 = 2;
   while (kp2 < k) kp2 <<= 1;
   dense_topk_kernel<<<(unsigned)T, 1024, (size_t)kp2 * sizeof(uint2), stream>>>(dense, ld, N, k, nullptr, 0, nullptr,
-                                                                               out_vals, out_idx);
+                                                                               out_vals, out_idx, nullptr);
   SAEB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

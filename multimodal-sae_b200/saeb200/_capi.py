@@ -45,13 +45,15 @@ SIGNATURES = {
     "saeb_encode_candidates": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int,
                                        c_int64, c_float, c_void_p, c_size_t, c_void_p]),
     "saeb_refine_candidates": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p,
-                                       c_void_p, c_int64, c_int64, c_int, c_int, c_int64, c_float, c_void_p, c_int,
-                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+                                       c_void_p, c_int64, c_int64, c_int, c_int, c_int64, c_float, c_void_p, c_void_p,
+                                       c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                       c_int, c_int, c_void_p]),
     "saeb_refine_candidates_lo": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p,
-                                          c_void_p, c_int64, c_int64, c_int, c_int, c_int64, c_float, c_void_p, c_int,
-                                          c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+                                          c_void_p, c_int64, c_int64, c_int, c_int, c_int64, c_float, c_void_p,
+                                          c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_size_t, c_int, c_int, c_void_p]),
     "saeb_candidate_bounds": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int64, c_int64, c_int,
-                                      c_int, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                      c_int, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "saeb_dense_topk": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "saeb_decode": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p,
                             c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
@@ -71,7 +73,7 @@ SIGNATURES = {
     "saeb_coo_append": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_int64, c_int64, c_void_p,
                                 c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "saeb_scan_pool": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_int64, c_int64, c_int64,
-                               c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "saeb_scan_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
     "saeb_image_pool_workspace_bytes": (c_size_t, [c_int, c_int, c_int64]),

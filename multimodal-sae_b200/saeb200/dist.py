@@ -81,7 +81,7 @@ class EngineOps:
         self.feat_lo, self.feat_hi = feat_lo, feat_hi
         self.scan = engine.TopActivationScan(feat_lo, feat_hi, n_top, ctx_len, device, bucket_cap=bucket_cap)
         self._x, self._k, self._prep, self._ws = [None, None], [0, 0], [None, None], [None, None]
-        self._lb, self._cached = [None, None], [None, None]
+        self._lb, self._ub, self._cached = [None, None], [None, None], [None, None]
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         # SAEB_SCAN_AUX_PRIORITY = high (default: exchange / refine / list update get the first pick of whatever SM
         # resources the GEMM grid leaves free) | low (GEMM CTAs are placed first at launch boundaries)
@@ -92,6 +92,9 @@ class EngineOps:
         # small blocks, so that nothing of the per-chunk chain has to wait for a GEMM launch boundary (saeb200.h,
         # `max_ctas`); 0: one CTA per token
         self.refine_max_ctas = int(os.environ.get("SAEB_SCAN_REFINE_CTAS", "0"))
+        # 2 (default): the refinement only gathers latents that can still enter their feature's list ("scan" mode of
+        # the refinement, exact values, rigorous membership); 0: every member of every token's TopK is re-evaluated
+        self.scan_value_mode = int(os.environ.get("SAEB_SCAN_VALUE_MODE", "2"))
         # SMs the GEMM grid leaves idle while a multi-rank scan is pipelined (see begin_pipeline).  Measured at 8 GPUs
         # (1 M tokens): 0 -> 4.85 M tokens/s, 4 (with NCCL_MAX_CTAS=4) -> 4.65-4.76 M: off by default
         self.reserve_sms = 0
@@ -168,13 +171,14 @@ class EngineOps:
         if enc.planes < 3:
             vals, idx, _ = eng.encode_topk(x2, enc, k)
             self._cached[slot] = (vals, idx + self.feat_lo)
-            return vals
+            return vals, vals
         dev = x2.device
         with torch.cuda.device(dev):
             prep = self._scratch(self._prep, slot, L.saeb_prep_bytes(T, enc.d_in), dev)
             ws = self._scratch(self._ws, slot, L.saeb_candidates_workspace_bytes(T, enc.d_in, enc.num_latents, k, 0),
                                dev)
             lb = self._scratch(self._lb, slot, T * k * 4, dev)[: T * k * 4].view(torch.float32).view(T, k)
+            ub = self._scratch(self._ub, slot, T * k * 4, dev)[: T * k * 4].view(torch.float32).view(T, k)
             st = torch.cuda.current_stream().cuda_stream
             code = eng._code(x2)
             ldx = x2.stride(0) if T > 1 else enc.d_in
@@ -184,35 +188,49 @@ class EngineOps:
                                                       enc.num_latents, k, 0, -1, 0.0, ws.data_ptr(), ws.numel(), st),
                              "saeb_encode_candidates")
             self._capi.check(L.saeb_candidate_bounds(prep.data_ptr(), T, 0, T, enc.blob.data_ptr(), code, enc.d_in,
-                                                     enc.num_latents, k, 0, -1, lb.data_ptr(), ws.data_ptr(),
-                                                     ws.numel(), st), "saeb_candidate_bounds")
-        return lb
+                                                     enc.num_latents, k, 0, -1, lb.data_ptr(), ub.data_ptr(),
+                                                     ws.data_ptr(), ws.numel(), st), "saeb_candidate_bounds")
+        return lb, ub
 
-    def local_topk(self, ext_L=None, slot=0):
+    def local_topk(self, ext_L=None, ext_U=None, slot=0):
+        """exact local TopK entries of the chunk given to local_bounds -> (vals, member, global ids), all [Tc, k].
+        Refinement in "scan" mode (value_mode 2, include/saeb200.h): only latents that can still enter their feature's
+        top-n list (and every latent whose membership in the token's TopK is undecided) are gathered and re-evaluated,
+        exactly.  Unsharded call (ext_L = ext_U = None): membership is decided here, `member` is None.  Sharded call:
+        `member` carries what decides membership across shards (3e38 = certain, exact value = boundary candidate)."""
         eng, L = self.engine, self._capi.lib()
         enc, x2, k = self.enc, self._x[slot], self._k[slot]
         if enc.planes < 3:
-            return self._cached[slot]
+            vals, idx = self._cached[slot]
+            return vals, (vals if ext_L is not None else None), idx
         refine = L.saeb_refine_candidates_lo if enc.planes == 4 else L.saeb_refine_candidates
         T = x2.shape[0]
         dev = x2.device
         vals = torch.empty((T, k), dtype=torch.float32, device=dev)
         idx = torch.empty((T, k), dtype=torch.int64, device=dev)
+        sharded = ext_L is not None and ext_U is not None
+        member = torch.empty((T, k), dtype=torch.float32, device=dev) if sharded else None
+        mode = 2 if self.scan_value_mode == 2 and (sharded or ext_L is None) else 0
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream().cuda_stream
             self._capi.check(refine(
                 x2.data_ptr(), eng._code(x2), x2.stride(0) if T > 1 else enc.d_in, self._prep[slot].data_ptr(), T, 0, T,
                 enc.blob.data_ptr(), enc.W_enc.data_ptr(), enc.d_in, enc.num_latents, k, 0, -1, 0.0,
-                None if ext_L is None else ext_L.data_ptr(), 1, vals.data_ptr(), idx.data_ptr(), self.status.data_ptr(),
-                self._ws[slot].data_ptr(), self._ws[slot].numel(), int(self.refine_max_ctas), 0, st),
+                None if ext_L is None else ext_L.data_ptr(),
+                ext_U.data_ptr() if (sharded and mode == 2) else None,
+                self.scan.feat_thr.data_ptr() if mode == 2 else None, 1, vals.data_ptr(),
+                member.data_ptr() if (sharded and mode == 2) else None, idx.data_ptr(), self.status.data_ptr(),
+                self._ws[slot].data_ptr(), self._ws[slot].numel(), int(self.refine_max_ctas), mode, st),
                 "saeb_refine_candidates")
-        return vals, idx + self.feat_lo
+        if sharded and mode != 2:
+            member = vals
+        return vals, member, idx + self.feat_lo
 
     def kth_of_gathered(self, gathered, kth=None):
         return self.engine.kth_of_gathered(gathered, kth)
 
-    def scan_update(self, vals, idx, window_base, tok_thr):
-        self.scan.update(vals, idx, window_base, tok_thr)
+    def scan_update(self, vals, idx, window_base, tok_thr, member=None):
+        self.scan.update(vals, idx, window_base, tok_thr, None if member is vals else member)
 
     def scan_finalize(self):
         return self.scan.finalize()
@@ -281,6 +299,7 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
     world = dist.get_world_size(group) if distributed else 1
     k_local = min(k, ops.feat_hi - ops.feat_lo)
     m1 = bounds_width(k, k_local, world) if lb_width is None else max(1, min(k_local, int(lb_width)))
+    m1 = min(k_local, max(m1, -(-(k + 1) // max(world, 1))))   # the union of the shards' lists must hold k + 1 entries
     if pipelined is None:
         pipelined = bool(getattr(ops, "pipelined", False)) and phase_times is None
     tm = _PhaseTimer(phase_times is not None and torch.cuda.is_available())
@@ -288,21 +307,29 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
     exchange = exact and world > 1
 
     if exchange and hasattr(ops, "push_widths"):
-        ops.push_widths = (m1, k_local)
+        ops.push_widths = (2 * m1, k_local)
 
-    def finish(x, lb, slot, window_base):
-        """exchange 1 -> restricted exact local TopK -> exchange 2 -> per-feature list update, for one chunk"""
-        ext_L = tok_thr = None
+    def finish(x, bounds, slot, window_base):
+        """exchange 1 (bounds) -> restricted exact local TopK -> exchange 2 (member values) -> list update, one chunk"""
+        ext_L = ext_U = tok_thr = None
+        lb, ub = bounds
         if exchange:
-            ext_L = _kth(ops, _exchange(ops, _head(lb, m1), group, 0, slot), k)
+            # one all-gather carries both bound lists: [Tc, m1] lower | [Tc, m1] upper
+            g = _exchange(ops, torch.cat([_head(lb, m1), _head(ub, m1)], dim=-1), group, 0, slot)
+            ext_L = _kth(ops, g[:, :, :m1], k)
+            # upper bound of the token's (k+1)-th largest upper bound: the (k+1)-th largest of what was sent, or the
+            # smallest bound a shard sent if its list was cut off (whatever it did not send is no larger than that)
+            ext_U = torch.maximum(_kth(ops, g[:, :, m1:], k + 1), g[:, :, 2 * m1 - 1].amax(0))
             tm.mark("exchange1")
-        vals, idx = ops.local_topk(ext_L, slot) if slot is not None else ops.local_topk(ext_L)
+        args = (ext_L, ext_U, slot) if slot is not None else (ext_L, ext_U)
+        vals, member, idx = ops.local_topk(*args)
         tm.mark("refine")
         vals2 = vals.reshape(-1, k_local)
+        member2 = None if member is None else member.reshape(-1, k_local)
         if exchange:
-            tok_thr = _kth(ops, _exchange(ops, vals2, group, 1, slot), k)
+            tok_thr = _kth(ops, _exchange(ops, member2, group, 1, slot), k)
             tm.mark("exchange2")
-        ops.scan_update(vals2, idx.reshape(-1, k_local), window_base, tok_thr)
+        ops.scan_update(vals2, idx.reshape(-1, k_local), window_base, tok_thr, member2 if exchange else None)
         tm.mark("scan_update")
         return vals2.shape[0] // ctx_len
 
@@ -354,27 +381,30 @@ def _lookahead_loop(chunks, ops, k, k_local, ctx_len, exchange, group, m1) -> No
 
     def b1(item):
         slot, gathered, work, base = item
-        ext_L = None
+        ext_L = ext_U = None
         if exchange:
             work.wait()
-            ext_L = _kth(ops, gathered, k)
-        vals, idx = ops.local_topk(ext_L, slot)
+            ext_L = _kth(ops, gathered[:, :, :m1], k)
+            ext_U = torch.maximum(_kth(ops, gathered[:, :, m1:], k + 1), gathered[:, :, 2 * m1 - 1].amax(0))
+        vals, member, idx = ops.local_topk(ext_L, ext_U, slot)
         vals2, idx2 = vals.reshape(-1, k_local), idx.reshape(-1, k_local)
-        g2, w2 = _gather_stack(vals2, group, async_op=True) if exchange else (None, None)
-        return vals2, idx2, g2, w2, base
+        mem2 = None if member is None else member.reshape(-1, k_local)
+        g2, w2 = _gather_stack(mem2, group, async_op=True) if exchange else (None, None)
+        return vals2, idx2, mem2, g2, w2, base
 
     def b2(item):
-        vals2, idx2, gathered, work, base = item
+        vals2, idx2, mem2, gathered, work, base = item
         tok_thr = None
         if exchange:
             work.wait()
             tok_thr = _kth(ops, gathered, k)
-        ops.scan_update(vals2, idx2, base, tok_thr)
+        ops.scan_update(vals2, idx2, base, tok_thr, mem2 if exchange else None)
 
     for c, x in enumerate(chunks):
         slot = c & 1
-        lb = ops.local_bounds(x, k_local, slot)
-        g1, w1 = _gather_stack(_head(lb, m1), group, async_op=True) if exchange else (None, None)
+        lb, ub = ops.local_bounds(x, k_local, slot)
+        g1, w1 = (_gather_stack(torch.cat([_head(lb, m1), _head(ub, m1)], dim=-1), group, async_op=True)
+                  if exchange else (None, None))
         if stage1 is not None:
             nxt = b1(stage1)
             if stage2 is not None:
@@ -459,9 +489,13 @@ def _head(lb: torch.Tensor, m: int) -> torch.Tensor:
 
 
 def _kth(ops, gathered: torch.Tensor, k: int) -> torch.Tensor:
-    """per-token k-th largest of the R * m gathered values ([R, T, m]); with fewer than k values, the smallest"""
+    """per-token k-th largest of the R * m gathered values ([R, T, m]); 0 when there are fewer than k values (the
+    k-th largest of fewer than k bounds bounds nothing: 0 is the safe answer for lower AND upper bounds of
+    non-negative activations -- "no restriction" / "everything positive is a member")"""
     R, T, m = gathered.shape
-    return ops.kth_of_gathered(gathered, min(k, R * m))
+    if k > R * m:
+        return torch.zeros(T, dtype=gathered.dtype, device=gathered.device)
+    return ops.kth_of_gathered(gathered, k)
 
 
 def token_parallel_scan(chunks_local: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_latents: int,
@@ -480,7 +514,7 @@ def token_parallel_scan(chunks_local: Iterable[torch.Tensor], ops, k: int, ctx_l
     base = int(window_base)
     for x in chunks_local:
         ops.local_bounds(x, k)
-        vals, idx = ops.local_topk(None)
+        vals, _, idx = ops.local_topk(None, None)
         ops.scan_update(vals.reshape(-1, k), idx.reshape(-1, k), base, None)
         n_tok = x.shape[0] if x.dim() == 2 else x.numel() // x.shape[-1]
         base += n_tok // ctx_len

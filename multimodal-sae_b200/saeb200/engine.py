@@ -154,8 +154,8 @@ def encode_topk(x: torch.Tensor, enc: PackedEncoder, k: int, *, clamp_feature: i
                                            st), "saeb_encode_candidates")
             check(L.saeb_refine_candidates_lo(x2.data_ptr(), code, ldx, prep.data_ptr(), T, 0, T, enc.blob.data_ptr(),
                                               enc.W_enc.data_ptr(), enc.d_in, enc.num_latents, k, refine_margin,
-                                              clamp_feature, float(clamp_value), None, 0, vals.data_ptr(),
-                                              idx.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), 0,
+                                              clamp_feature, float(clamp_value), None, None, None, 0, vals.data_ptr(),
+                                              None, idx.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), 0,
                                               int(value_mode), st),
                   "saeb_refine_candidates_lo")
         encode_topk.last_status = status
@@ -367,13 +367,20 @@ class TopActivationScan:
         self._pending = 0
 
     def update(self, top_acts: torch.Tensor, top_indices: torch.Tensor, window_base: int,
-               tok_thr: Optional[torch.Tensor] = None) -> None:
+               tok_thr: Optional[torch.Tensor] = None, member: Optional[torch.Tensor] = None) -> None:
         """Feed TopK output of T tokens (T a multiple of ctx_len except for the very last chunk) whose first window
-        has global id `window_base`."""
+        has global id `window_base`.  tok_thr [T] / member [T, k] (optional): membership threshold per token and the
+        values it is compared with (feature-sharded scan, see saeb_scan_pool)."""
         L = _capi.lib()
         k = top_acts.shape[-1]
         vals = top_acts.reshape(-1, k)
         idx = top_indices.reshape(-1, k)
+        mem = None if member is None else member.reshape(-1, k)
+        for t_, dt_ in ((vals, torch.float32), (idx, torch.int64), (mem, torch.float32), (tok_thr, torch.float32)):
+            if t_ is not None and (t_.dtype != dt_ or not t_.is_contiguous() or t_.device != self.device):
+                raise SaebError("scan update needs contiguous float32 values / int64 indices on the scan's device")
+        if window_base < 0 or window_base + (vals.shape[0] + self.ctx_len - 1) // self.ctx_len >= 2 ** 32:
+            raise SaebError("scan update: window ids must fit 32 bits")
         T = vals.shape[0]
         max_tok = self.bucket_cap * self.ctx_len
         with torch.cuda.device(self.device):
@@ -386,6 +393,7 @@ class TopActivationScan:
                 check(L.saeb_scan_pool(v.data_ptr(), i.data_ptr(), t1 - t0, k, self.ctx_len, self.threshold,
                                        self.feat_lo, self.feat_hi, window_base + t0 // self.ctx_len,
                                        None if tok_thr is None else tok_thr[t0:t1].data_ptr(),
+                                       None if mem is None else mem[t0:t1].data_ptr(),
                                        self.feat_thr.data_ptr(), self.bucket.data_ptr(), self.bucket_cnt.data_ptr(),
                                        self.bucket_cap, self.overflow.data_ptr(), _stream()), "saeb_scan_pool")
                 self._pending += n_win
@@ -402,6 +410,9 @@ class TopActivationScan:
 
     def finalize(self) -> Tuple[torch.Tensor, torch.Tensor]:
         self.flush()
+        if int(self.overflow.item()) != 0:
+            raise SaebError("top-activation scan: a feature's bucket overflowed (more than bucket_cap windows between "
+                            "two flushes)")
         return self.top_vals, self.top_win
 
 

@@ -127,8 +127,8 @@ class OverlappedForward:
                     self.s_mem.wait_event(ev_a[c])
                     check(refine(x.data_ptr() + a * ldx * esz, code, ldx, prep.data_ptr(), T, a,
                                  b - a, enc.blob.data_ptr(), enc.W_enc.data_ptr(), enc.d_in,
-                                 enc.num_latents, k, 0, -1, 0.0, None, 0, acts[a:b].data_ptr(),
-                                 idx[a:b].data_ptr(), self.status[c % nws:].data_ptr(), ws.data_ptr(),
+                                 enc.num_latents, k, 0, -1, 0.0, None, None, None, 0, acts[a:b].data_ptr(),
+                                 None, idx[a:b].data_ptr(), self.status[c % nws:].data_ptr(), ws.data_ptr(),
                                  ws.numel(), max_ctas, self.value_mode, self.s_mem.cuda_stream),
                           "saeb_refine_candidates")
                     if sae_out is not None:

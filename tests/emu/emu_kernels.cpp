@@ -109,9 +109,9 @@ void emu_prep_x_f32(const float* x, long long T, long long d, long long ld_x, lo
 
 void emu_candidate_bounds(const float* cand_vals, const long long* cand_idx, long long T, int K2, int k,
                           const float* wnorm, const float* dnorm, const float* xnorm, const float* xdnorm, float c_eps,
-                          long long clamp_feature, float* lb_out) {
+                          long long clamp_feature, float* lb_out, float* ub_out) {
   emu::launch({(unsigned)T}, {128}, [&] {
-    candidate_bounds_kernel(cand_vals, cand_idx, K2, k, wnorm, dnorm, xnorm, xdnorm, c_eps, clamp_feature, lb_out);
+    candidate_bounds_kernel(cand_vals, cand_idx, K2, k, wnorm, dnorm, xnorm, xdnorm, c_eps, clamp_feature, lb_out, ub_out);
   });
 }
 
@@ -122,18 +122,19 @@ void emu_refine_bf16(const void* x, long long T, long long ld_x, const float* W,
                      const float* xnorm, const float* xdnorm, float c_eps, const float* cand_vals,
                      const long long* cand_idx, int K2, int k, long long clamp_feature, float clamp_value,
                      float* out_vals, long long* out_idx, int* status, int* flag_rows, const float* ext_lower,
-                     const void* lo, long long ld_w, int threads, int value_mode) {
+                     const void* lo, long long ld_w, int threads, int value_mode, const float* ext_upper,
+                     const float* feat_thr, float* out_member) {
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
   // fewer CTAs than tokens: the persistent token loop of the kernels is what runs beside the GEMM on the GPU
   emu::launch({(unsigned)((T + 1) / 2)}, {(unsigned)threads}, [&] {
     if (lo == nullptr)
       refine_kernel<__nv_bfloat16>(xb, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals,
                                    cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx, status, flag_rows,
-                                   ext_lower, T, nullptr, value_mode);
+                                   ext_lower, T, nullptr, value_mode, ext_upper, feat_thr, out_member);
     else
       refine_lo_kernel<__nv_bfloat16>(xb, ld_x, reinterpret_cast<const __half*>(lo), ld_w, d, N, bias, wnorm, dnorm,
                                       trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k, clamp_feature,
-                                      clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, T, nullptr, value_mode);
+                                      clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, T, nullptr, value_mode, ext_upper, feat_thr, out_member);
   });
 }
 
@@ -185,12 +186,13 @@ void emu_coo_extract(const float* vals, const long long* idx, long long T, int k
 
 void emu_scan_pool(const float* vals, const long long* idx, long long T, int k, int ctx_len, float threshold,
                    long long feat_lo, long long feat_hi, long long window_base, const float* tok_thr,
-                   const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap, int* overflow) {
+                   const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap, int* overflow,
+                   const float* member) {
   const long long n_win = (T + ctx_len - 1) / ctx_len;
   int slots = 64;
   while (slots < 2 * (long long)ctx_len * k) slots <<= 1;
   emu::launch({(unsigned)n_win}, {256}, [&] {
-    scan_pool_kernel(vals, idx, T, k, ctx_len, threshold, feat_lo, feat_hi, window_base, tok_thr, feat_thr,
+    scan_pool_kernel(vals, idx, T, k, ctx_len, threshold, feat_lo, feat_hi, window_base, tok_thr, member, feat_thr,
                      reinterpret_cast<uint2*>(bucket), bucket_cnt, bucket_cap, slots, overflow);
   });
 }
@@ -238,7 +240,7 @@ void emu_decode(const long long* idx, const float* vals, long long T, int k, con
 void emu_dense_topk(const float* dense, long long T, long long ld, long long N, int k, float* out_vals,
                     long long* out_idx, int threads) {
   emu::launch({(unsigned)T}, {(unsigned)threads},
-              [&] { dense_topk_kernel(dense, ld, N, k, nullptr, 0, nullptr, out_vals, out_idx); });
+              [&] { dense_topk_kernel(dense, ld, N, k, nullptr, 0, nullptr, out_vals, out_idx, nullptr); });
 }
 
 // the three fallback launches of refine_launch_t for flagged rows (bf16 activations): exact dense rows of the first
@@ -252,11 +254,11 @@ void emu_refine_fallback(const void* x, long long ld_x, const float* W, long lon
                                      dense_scratch);
   });
   emu::launch({(unsigned)RF_MAX_FLAG}, {(unsigned)threads}, [&] {
-    dense_topk_kernel(dense_scratch, N, N, k, status, RF_MAX_FLAG, flag_rows, out_vals, out_idx);
+    dense_topk_kernel(dense_scratch, N, N, k, status, RF_MAX_FLAG, flag_rows, out_vals, out_idx, nullptr);
   });
   emu::launch({3}, {(unsigned)threads}, [&] {
     overflow_rows_kernel<__nv_bfloat16>(xb, ld_x, W, d, N, bias, status, flag_rows, clamp_feature, clamp_value,
-                                        dense_scratch, k, out_vals, out_idx);
+                                        dense_scratch, k, out_vals, out_idx, nullptr);
   });
 }
 
@@ -293,11 +295,11 @@ void emu_refine_f16(const void* x, long long T, long long ld_x, const float* W, 
   emu::launch({(unsigned)T}, {256}, [&] {
     if (lo == nullptr)
       refine_kernel<__half>(xh, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx,
-                            K2, k, -1, 0.f, out_vals, out_idx, status, flag_rows, nullptr, T, nullptr, 0);
+                            K2, k, -1, 0.f, out_vals, out_idx, status, flag_rows, nullptr, T, nullptr, 0, nullptr, nullptr, nullptr);
     else
       refine_lo_kernel<__half>(xh, ld_x, reinterpret_cast<const __half*>(lo), ld_w, d, N, bias, wnorm, dnorm, trailer,
                                xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k, -1, 0.f, out_vals, out_idx, status,
-                               flag_rows, nullptr, T, nullptr, 0);
+                               flag_rows, nullptr, T, nullptr, 0, nullptr, nullptr, nullptr);
   });
 }
 void emu_refine_f32(const float* x, long long T, long long ld_x, const float* W, long long d, long long N,
@@ -307,7 +309,7 @@ void emu_refine_f32(const float* x, long long T, long long ld_x, const float* W,
                     int* flag_rows) {
   emu::launch({(unsigned)T}, {256}, [&] {
     refine_kernel<float>(x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k,
-                         -1, 0.f, out_vals, out_idx, status, flag_rows, nullptr, T, nullptr, 0);
+                         -1, 0.f, out_vals, out_idx, status, flag_rows, nullptr, T, nullptr, 0, nullptr, nullptr, nullptr);
   });
 }
 

@@ -27,22 +27,31 @@ class OracleOps:
     def local_bounds(self, x, k, slot=0):
         pa = O.pre_acts(self.sub, x.float())
         self._v[slot], self._i[slot] = pa.topk(k, sorted=True)
-        return self._v[slot] * (1 - 1e-3)   # a lower bound, like the engine's a_j - eps_j
-
-    def local_topk(self, ext_L=None, slot=0):
         v = self._v[slot]
-        if ext_L is not None:   # latents that cannot reach the global k-th value are not evaluated (reported as 0)
-            v = torch.where(v >= ext_L[:, None], v, torch.zeros_like(v))
-        return v, self._i[slot] + self.feat_lo
+        return v * (1 - 1e-3), v * (1 + 1e-3)   # lower / upper bounds, like the engine's a_j -/+ eps_j
+
+    def local_topk(self, ext_L=None, ext_U=None, slot=0):
+        """same contract as EngineOps.local_topk: sharded calls also return the member values (3e38 = certainly in the
+        token's global TopK, exact value = undecided, 0 = cannot be in it)"""
+        v = self._v[slot]
+        if ext_L is None:
+            return v, None, self._i[slot] + self.feat_lo
+        lb, ub = v * (1 - 1e-3), v * (1 + 1e-3)
+        sure = (lb > ext_U[:, None]) & (v > 0)
+        maybe = ~sure & (ub >= ext_L[:, None]) & (v > 0)
+        member = torch.where(sure, torch.full_like(v, 3.0e38), torch.where(maybe, v, torch.zeros_like(v)))
+        vals = torch.where(sure | maybe, v, torch.zeros_like(v))
+        return vals, member, self._i[slot] + self.feat_lo
 
     def kth_of_gathered(self, gathered, kth=None):
         R, T, m = gathered.shape
         kth = m if kth is None else kth
-        return gathered.permute(1, 0, 2).reshape(T, R * m).topk(kth).values[:, -1].contiguous()
+        return gathered.clamp_min(0).permute(1, 0, 2).reshape(T, R * m).topk(kth).values[:, -1].contiguous()
 
-    def scan_update(self, vals, idx, window_base, tok_thr):
+    def scan_update(self, vals, idx, window_base, tok_thr, member=None):
         if tok_thr is not None:
-            vals = torch.where(vals >= tok_thr[:, None], vals, torch.zeros_like(vals))
+            decide = vals if member is None else member
+            vals = torch.where(decide >= tok_thr[:, None], vals, torch.zeros_like(vals))
         if self.first_window is None:
             self.first_window = window_base   # chunks arrive in order: later ones continue this numbering
         self.acts.append(vals)

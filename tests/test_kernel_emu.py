@@ -160,19 +160,25 @@ def test_pack_and_prep_kernels(emu):
     assert np.array_equal(prep.astype(np.float32)[:, :100] * s["row_scale"][:, None], x)
 
 
-def _run_refine(emu, s, k, *, lo, ext_lower=None, threads=256, clamp=(-1, 0.0), value_mode=0, c_eps=2.0 ** -14):
+def _run_refine(emu, s, k, *, lo, ext_lower=None, threads=256, clamp=(-1, 0.0), value_mode=0, c_eps=2.0 ** -14,
+                ext_upper=None, feat_thr=None, want_member=False):
     T, K2 = s["cand_vals"].shape
     d, N = s["W"].shape[1], s["W"].shape[0]
     out_vals = np.full((T, k), np.nan, np.float32)
     out_idx = np.full((T, k), -7, np.int64)
     status = np.zeros(64, np.int32)
     flag_rows = np.full(max(T, 64), -1, np.int32)
+    out_member = np.full((T, k), np.nan, np.float32)
     emu.emu_refine_bf16(_p(s["xraw"]), c_longlong(T), c_longlong(d), _p(s["W"]), c_longlong(d), c_longlong(N),
                         _p(s["bias"]), _p(s["wnorm"]), _p(s["dnorm"]), _p(s["trailer"]), _p(s["xnorm"]), _p(s["xdnorm"]),
                         c_float(c_eps), _p(s["cand_vals"]), _p(s["cand_idx"]), c_int(K2), c_int(k),
                         c_longlong(clamp[0]), c_float(clamp[1]), _p(out_vals), _p(out_idx), _p(status), _p(flag_rows),
                         None if ext_lower is None else _p(ext_lower), _p(s["lo"]) if lo else None,
-                        c_longlong(s["d_pad"]), c_int(threads), c_int(value_mode))
+                        c_longlong(s["d_pad"]), c_int(threads), c_int(value_mode),
+                        None if ext_upper is None else _p(ext_upper), None if feat_thr is None else _p(feat_thr),
+                        _p(out_member) if want_member else None)
+    if want_member:
+        return out_vals, out_idx, int(status[0]), out_member
     return out_vals, out_idx, int(status[0])
 
 
@@ -324,7 +330,7 @@ def test_candidate_bounds_kernel(emu):
     T, K2 = s["cand_vals"].shape
     lb = np.full((T, k), np.nan, np.float32)
     emu.emu_candidate_bounds(_p(s["cand_vals"]), _p(s["cand_idx"]), c_longlong(T), c_int(K2), c_int(k), _p(s["wnorm"]),
-                             _p(s["dnorm"]), _p(s["xnorm"]), _p(s["xdnorm"]), c_float(2.0 ** -14), c_longlong(-1), _p(lb))
+                             _p(s["dnorm"]), _p(s["xnorm"]), _p(s["xdnorm"]), c_float(2.0 ** -14), c_longlong(-1), _p(lb), None)
     wn, dn = s["wnorm"][s["cand_idx"]], s["dnorm"][s["cand_idx"]]
     xn, xdn = s["xnorm"][:, None], s["xdnorm"][:, None]
     eps = np.float32(1.001) * (xn * dn + xdn * wn) + np.float32(2.0 ** -14) * xn * wn
@@ -460,7 +466,7 @@ def test_scan_pool_and_merge_kernels(emu):
         t0, t1 = w0 * ctx, min(T, (w0 + cap) * ctx)
         emu.emu_scan_pool(_p(vn[t0:t1]), _p(inn[t0:t1]), c_longlong(t1 - t0), c_int(k), c_int(ctx), c_float(1e-5),
                           c_longlong(lo), c_longlong(hi), c_longlong(w0), _p(tn[t0:t1]), _p(feat_thr), _p(bucket),
-                          _p(bucket_cnt), c_int(cap), _p(overflow))
+                          _p(bucket_cnt), c_int(cap), _p(overflow), None)
         emu.emu_scan_merge(_p(bucket), _p(bucket_cnt), c_int(cap), c_longlong(F), c_int(n_top), c_float(1e-5),
                            _p(top_vals), _p(top_win), _p(feat_thr))
     assert overflow[0] == 0
@@ -679,7 +685,7 @@ def test_feature_sharded_scan_chain_on_the_emulator(emu):
         lb = np.zeros((T, k), np.float32)
         emu.emu_candidate_bounds(_p(sh["cand_vals"]), _p(sh["cand_idx"]), c_longlong(T), c_int(sh["K2"]), c_int(k),
                                  _p(sh["wnorm"]), _p(sh["dnorm"]), _p(sh["xnorm"]), _p(sh["xdnorm"]),
-                                 c_float(2.0 ** -14), c_longlong(-1), _p(lb))
+                                 c_float(2.0 ** -14), c_longlong(-1), _p(lb), None)
         lbs.append(lb[:, :m1])
     g1 = np.ascontiguousarray(np.stack(lbs, 0))
     ext_L = np.zeros(T, np.float32)
@@ -712,7 +718,7 @@ def test_feature_sharded_scan_chain_on_the_emulator(emu):
         vc, ic = np.ascontiguousarray(v), np.ascontiguousarray(i)
         emu.emu_scan_pool(_p(vc), _p(ic), c_longlong(T), c_int(k), c_int(ctx), c_float(1e-5), c_longlong(sh["lo"]),
                           c_longlong(sh["hi"]), c_longlong(0), _p(tok_thr), _p(feat_thr), _p(bucket), _p(bucket_cnt),
-                          c_int(8), _p(overflow))
+                          c_int(8), _p(overflow), None)
         emu.emu_scan_merge(_p(bucket), _p(bucket_cnt), c_int(8), c_longlong(F), c_int(n_top), c_float(1e-5),
                            _p(top_vals), _p(top_win), _p(feat_thr))
         assert overflow[0] == 0
@@ -720,6 +726,96 @@ def test_feature_sharded_scan_chain_on_the_emulator(emu):
     ref_s, ref_w = O.scan_top_windows(ref.top_acts, ref.top_indices, N, ctx, n_top)
     np.testing.assert_allclose(np.concatenate([a for a, _ in parts]), ref_s, rtol=3e-6, atol=1e-7)
     assert np.array_equal(np.concatenate([b for _, b in parts]), ref_w)
+
+
+def test_refinement_scan_mode_unsharded(emu):
+    """value_mode 2 without sharding: only the members of the TopK whose feature can still take them (upper bound >=
+    feat_thr[feature]) come out, with EXACT values; the others are not gathered at all."""
+    d, N, k, margin, T = 100, 300, 8, 12, 8
+    s = _pipeline_inputs(emu, d=d, N=N, k=k, T=T, margin=margin, seed=131)
+    v0, i0, _ = _run_refine(emu, s, k, lo=False)                         # exact mode: the reference answer
+    feat_thr = np.where(np.arange(N) % 2 == 0, np.float32(1e-5), np.float32(1e30)).astype(np.float32)
+    v2, i2, flagged = _run_refine(emu, s, k, lo=False, value_mode=2, feat_thr=feat_thr, c_eps=2.0 ** -9)
+    assert flagged == 0
+    n_unwanted = 0
+    for r in range(T):
+        exact = {int(i): float(v) for i, v in zip(i0[r], v0[r])}
+        got = {int(i): float(v) for i, v in zip(i2[r], v2[r]) if v > 0}
+        assert all(got.get(i) == v for i, v in exact.items() if i % 2 == 0), r      # every wanted member, exact value
+        assert all(i in exact and exact[i] == v for i, v in got.items()), r        # nothing but members, exact values
+        n_unwanted += sum(1 for i in got if i % 2 == 1)   # only those whose membership had to be decided by value
+    assert n_unwanted < 0.25 * sum(1 for r in range(T) for i in i0[r] if int(i) % 2 == 1)
+    # without thresholds the mode is the exact mode (every member is re-evaluated)
+    v3, i3, _ = _run_refine(emu, s, k, lo=False, value_mode=2)
+    assert np.array_equal(v3, v0) and np.array_equal(i3, i0)
+
+
+def test_refinement_scan_mode_two_shards(emu):
+    """value_mode 2 under feature sharding (2 logical shards): bounds lists (lower AND upper) -> global L and U ->
+    per-shard refinement that writes member values -> k-th largest member value = membership threshold.  The entries
+    that pass it are exactly the oracle's global TopK, every value exact; with per-feature thresholds only the wanted
+    members are gathered."""
+    d, N, k, margin, R = 64, 512, 12, 12, 2
+    T = 24
+    p = O.init_params(d, N, k, seed=181)
+    x = torch.randn(T, d, generator=torch.Generator().manual_seed(182)).to(torch.bfloat16)
+    ref = O.encode(p, x.float())
+    ri, rv = O.canonical_topk(ref.top_acts, ref.top_indices)
+    shards = []
+    for r in range(R):
+        lo, hi = r * N // R, (r + 1) * N // R
+        sub = O.SaeParams(p.W_enc[lo:hi].contiguous(), p.b_enc[lo:hi].contiguous(), p.W_dec[lo:hi].contiguous(),
+                          p.b_dec, k)
+        sh = _pipeline_inputs(emu, d, hi - lo, k, T, margin, 0, p=sub, x=x)
+        sh["lo"], sh["hi"] = lo, hi
+        shards.append(sh)
+    c_eps = 2.0 ** -11      # wider intervals than the real ones: some candidates must be undecided on these toy shapes
+    lbs, ubs = [], []
+    for sh in shards:
+        lb, ub = np.zeros((T, k), np.float32), np.zeros((T, k), np.float32)
+        emu.emu_candidate_bounds(_p(sh["cand_vals"]), _p(sh["cand_idx"]), c_longlong(T), c_int(sh["K2"]), c_int(k),
+                                 _p(sh["wnorm"]), _p(sh["dnorm"]), _p(sh["xnorm"]), _p(sh["xdnorm"]),
+                                 c_float(c_eps), c_longlong(-1), _p(lb), _p(ub))
+        assert (ub >= lb).all() and (np.diff(ub, axis=1) <= 0).all()
+        lbs.append(lb)
+        ubs.append(ub)
+    all_lb, all_ub = np.concatenate(lbs, 1), np.concatenate(ubs, 1)
+    ext_L = np.ascontiguousarray(-np.sort(-all_lb, 1)[:, k - 1])
+    ext_U = np.ascontiguousarray(-np.sort(-all_ub, 1)[:, k])
+    for feat_thr_on in (False, True):
+        outs, n_gathered = [], 0
+        for sh in shards:
+            F = sh["hi"] - sh["lo"]
+            thr = (np.where(np.arange(F) % 2 == 0, np.float32(1e-5), np.float32(1e30)).astype(np.float32)
+                   if feat_thr_on else None)
+            v, i, flagged, mem = _run_refine(emu, sh, k, lo=False, ext_lower=ext_L, ext_upper=ext_U, value_mode=2,
+                                             threads=128, c_eps=c_eps, feat_thr=thr, want_member=True)
+            assert flagged == 0
+            assert ((mem == 0) | (mem >= 3e38) | (mem == v)).all()          # padding | certain | undecided (exact)
+            outs.append((v, i + sh["lo"], mem))
+            n_gathered += int((v > 0).sum())
+        allm = np.concatenate([m for _, _, m in outs], 1)
+        tok_thr = -np.sort(-allm, 1)[:, k - 1]
+        n_sure = sum(int((m >= 3e38).sum()) for _, _, m in outs)
+        n_maybe = sum(int(((m > 0) & (m < 3e38)).sum()) for _, _, m in outs)
+        assert n_sure > 0 and n_maybe > 0
+        for r in range(T):
+            members = {}
+            for v, i, m in outs:
+                for vv, ii, mm in zip(v[r], i[r], m[r]):
+                    if mm > 0 and mm >= tok_thr[r]:
+                        members[int(ii)] = float(vv)
+            assert sorted(members) == sorted(int(j) for j in ri[r]), r      # exactly the global TopK
+            exact = {int(j): float(w) for j, w in zip(ri[r], rv[r])}
+            for j, vv in members.items():
+                if feat_thr_on and (j - (0 if j < N // R else N // R)) % 2 == 1:
+                    # unwanted member: not gathered (0) unless its membership had to be decided by its exact value
+                    assert vv == 0.0 or abs(vv - exact[j]) <= 3e-6 * exact[j]
+                else:
+                    assert abs(vv - exact[j]) <= 3e-6 * exact[j]            # wanted member: exact value
+        if feat_thr_on:
+            assert n_gathered < 0.8 * n_all
+        n_all = n_gathered
 
 
 # ---------------------------------------------------------------------------------------------

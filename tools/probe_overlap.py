@@ -97,8 +97,8 @@ def exp_parts(stages=0, max_ctas=0, chunk=9472):
         a, b = c * chunk, min(T, (c + 1) * chunk)
         with torch.cuda.stream(st):
             check(L.saeb_refine_candidates(x.data_ptr() + a * D * 2, code, D, prep.data_ptr(), T, a, b - a,
-                                           enc.blob.data_ptr(), enc.W_enc.data_ptr(), D, N, K, 0, -1, 0.0, None, 0,
-                                           acts[a:b].data_ptr(), idx[a:b].data_ptr(), status.data_ptr(), ws.data_ptr(),
+                                           enc.blob.data_ptr(), enc.W_enc.data_ptr(), D, N, K, 0, -1, 0.0, None, None, None,
+                                           0, acts[a:b].data_ptr(), None, idx[a:b].data_ptr(), status.data_ptr(), ws.data_ptr(),
                                            ws.numel(), mc, VALUE_MODE, st.cuda_stream), "refine")
             engine.decode(idx[a:b], acts[a:b], sae.W_dec.data, sae.b_dec.data, x=x[a:b], sq_err=sq, out=out[a:b],
                           max_ctas=mc)
@@ -164,8 +164,8 @@ def exp_power(seconds=3.0):
         for c in range(n_chunks):
             a, b = c * chunk, min(T, (c + 1) * chunk)
             check(L.saeb_refine_candidates(x.data_ptr() + a * D * 2, code, D, prep.data_ptr(), T, a, b - a,
-                                           enc.blob.data_ptr(), enc.W_enc.data_ptr(), D, N, K, 0, -1, 0.0, None, 0,
-                                           acts[a:b].data_ptr(), idx[a:b].data_ptr(), status.data_ptr(),
+                                           enc.blob.data_ptr(), enc.W_enc.data_ptr(), D, N, K, 0, -1, 0.0, None, None, None,
+                                           0, acts[a:b].data_ptr(), None, idx[a:b].data_ptr(), status.data_ptr(),
                                            ws[c].data_ptr(), ws[c].numel(), 0, vm, st.cuda_stream), "refine")
 
     def decode():
