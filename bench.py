@@ -306,8 +306,11 @@ def run_scan(torch, sdist, engine, synth, sae, args, rank, world, dev, barrier, 
             # every GPU runs 1/world of the encoder GEMM for every token
             "tensor_frac_per_gpu": tps * ENC_FLOPS_PER_TOKEN / world / 1e12 / peaks["tflops_sustained"],
             "exchange": None if world == 1 else getattr(ops, "exchange", None),
-            "exchange1_columns": m1 if world > 1 else None,
-            "nvlink_bytes_per_chunk_per_rank_received": None if world == 1 else chunk * 4 * (m1 + K) * (world - 1),
+            "exchange1_columns": 2 * m1 if world > 1 else None,   # lower + upper bound lists
+            "exchange2_columns": K if world > 1 else None,         # member values
+            "nvlink_bytes_per_chunk_per_rank_received": None if world == 1 else chunk * 4 * (2 * m1 + K) * (world - 1),
+            "refine_mode": "scan (value_mode 2): only TopK members that can still enter their feature's list are "
+                           "gathered, exact values" if getattr(ops, "scan_value_mode", 0) == 2 else "every member exact",
             "final_allgather_bytes_per_rank": (hi - lo) * n_top * 12,
             "filled_features": int((res.top_win[:, 0] >= 0).sum().item()),
             "flagged_rows": int(ops.status.item()),

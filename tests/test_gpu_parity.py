@@ -445,9 +445,12 @@ def test_scan_matches_oracle():
     np.testing.assert_array_equal(torch.cat([b for _, b in parts]).cpu().numpy(), ref_w)
 
 
-def test_feature_sharded_scan_logical_shards():
-    """The multi-GPU choreography of saeb200.dist (bounds exchange -> restricted exact refinement -> value exchange ->
-    per-feature lists) with 4 logical shards on one device must reproduce the unsharded result exactly."""
+@pytest.mark.parametrize("scan_mode", [2, 0])
+def test_feature_sharded_scan_logical_shards(scan_mode):
+    """The multi-GPU choreography of saeb200.dist (bounds exchange -> restricted exact refinement -> member-value
+    exchange -> per-feature lists) with 4 logical shards on one device must reproduce the unsharded result exactly, in
+    the refinement's scan mode (2: only members that can still enter a list are gathered) and with every member
+    re-evaluated (0)."""
     from saeb200 import dist as sdist, engine
 
     N, d, k, ctx, n_top, R = 2048, 256, 16, 16, 4, 4
@@ -456,17 +459,22 @@ def test_feature_sharded_scan_logical_shards():
     shards = [sdist.shard_range(N, R, r) for r in range(R)]
     ops = [sdist.EngineOps(p.W_enc[lo:hi].to(DEV), p.b_enc[lo:hi].to(DEV), p.b_dec.to(DEV), lo, hi, n_top, ctx, DEV)
            for lo, hi in shards]
-    n_eval, m1 = 0, 8   # k / R = 4 is the narrowest legal width
+    for o in ops:
+        o.scan_value_mode = scan_mode
+    n_eval, m1 = 0, 8   # (k + 1) / R rounded up = 5 is the narrowest legal width
     for c0 in range(0, x.shape[0], ctx * 16):
         xc = x[c0:c0 + ctx * 16]
-        # exchange 1 carries only the first m1 columns of each shard's bound list (saeb200.dist.bounds_width)
-        lbs = torch.stack([o.local_bounds(xc, k)[:, :m1] for o in ops], 0)
+        # exchange 1 carries only the first m1 columns of each shard's bound lists (saeb200.dist.bounds_width)
+        bounds = [o.local_bounds(xc, k) for o in ops]
+        lbs = torch.stack([lb[:, :m1] for lb, _ in bounds], 0)
+        ubs = torch.stack([ub[:, :m1] for _, ub in bounds], 0)
         ext_L = engine.kth_of_gathered(lbs, k)
-        outs = [o.local_topk(ext_L) for o in ops]
-        n_eval += sum(int((v > 0).sum()) for v, _ in outs)
-        tok_thr = engine.kth_of_gathered(torch.stack([v for v, _ in outs], 0))
-        for o, (v, i) in zip(ops, outs):
-            o.scan_update(v, i, c0 // ctx, tok_thr)
+        ext_U = torch.maximum(engine.kth_of_gathered(ubs, k + 1), ubs[:, :, -1].amax(0))
+        outs = [o.local_topk(ext_L, ext_U) for o in ops]
+        n_eval += sum(int((v > 0).sum()) for v, _, _ in outs)
+        tok_thr = engine.kth_of_gathered(torch.stack([m for _, m, _ in outs], 0), k)
+        for o, (v, m, i) in zip(ops, outs):
+            o.scan_update(v, i, c0 // ctx, tok_thr, m)
     parts = [o.scan_finalize() for o in ops]
     vals = torch.cat([a for a, _ in parts]).cpu().numpy()
     wins = torch.cat([b for _, b in parts]).cpu().numpy()
