@@ -43,7 +43,12 @@ long long saeb_launch_count(void);
  * the collectives of the feature-sharded scan -- have somewhere to run while a GEMM launch is in flight.
  * "refine_threads": threads per refinement CTA in feature-sharded calls (default 128; 256 keeps more loads in flight
  * when the kernel runs beside a GEMM launch, where only one CTA fits per SM).  "kth_impl": see
- * saeb_kth_largest_gathered.  "l2_hints", "debug_tiles": diagnostics. */
+ * saeb_kth_largest_gathered.  "gemm_stages": depth of the GEMM's shared-memory ring (0 = as deep as fits: 6; 5 leaves
+ * ~54 KB per SM to gather CTAs running beside it).  "cluster4": 4-CTA clusters sharing the activation tile by TMA
+ * multicast (0 = off, default; 1 = when every token tile gets a resident cluster; 2 = always).  "stats": cycle /
+ * gather counters for saeb_debug_stats.  "l2_hints", "debug_tiles", "prefetch_b": diagnostics.
+ * Options are PER CALLING THREAD (thread-local state, like the error string): two threads driving two streams or two
+ * SAEs never see each other's settings, and the profiling events belong to the thread that set "profile". */
 int saeb_set_option(const char* name, int value);
 /* With option "profile" = 1 the library brackets the fused encode kernel (main kernel only) with CUDA events on the
  * launching stream; this returns the duration in ms of the most recent one (synchronises on it), < 0 if none. */

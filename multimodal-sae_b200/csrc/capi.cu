@@ -4,14 +4,24 @@
 #include <cstdio>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost nothing unless a tool (nsys / ncu --nvtx) is attached
+
 #include "../../include/saeb200.h"
 #include "common.cuh"
 
 namespace saeb {
 
 static thread_local char g_err[512] = {0};
-static int g_default_margin = 0;   // extra candidates per row in refine mode; 0: max(48, k/2)
+static thread_local int g_default_margin = 0;   // extra candidates per row in refine mode; 0: max(48, k/2)
 static std::atomic<long long> g_launches{0};
+
+// NVTX range around every compute entry point ("saeb:<phase>"): prep / gemm / bounds / refine / decode / coo / scan /
+// exchange show up as named ranges on the calling thread's timeline (tracing)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define SAEB_NVTX(name) saeb::NvtxRange _saeb_nvtx_range(name)
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -213,6 +223,7 @@ size_t saeb_packed_weights_bytes(int64_t N, int64_t d, int planes) {
 int saeb_pack_weights(const float* W_enc, const float* b_enc, const float* b_dec, int64_t N, int64_t d, int planes,
                       void* packed, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:pack_weights");
   SAEB_REQUIRE(W_enc && b_enc && b_dec && packed, "pack_weights: null pointer");
   SAEB_REQUIRE(planes >= 1 && planes <= 4, "pack_weights: planes must be 1, 2, 3 or 4");
   float* bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed) + planes_bytes(N, d, planes));
@@ -243,6 +254,7 @@ int saeb_encode_topk(const void* x, int x_dtype, int64_t T, int64_t ld_x, const 
                      int64_t N, int k, int64_t clamp_feature, float clamp_value, float* out_vals, int64_t* out_idx,
                      float* dense_out, int64_t ld_dense, void* workspace, size_t workspace_bytes, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:encode_topk");
   SAEB_REQUIRE(x && packed, "encode_topk: null pointer");
   SAEB_REQUIRE((out_vals != nullptr) == (out_idx != nullptr), "encode_topk: out_vals and out_idx go together");
   SAEB_REQUIRE(out_vals != nullptr || dense_out != nullptr, "encode_topk: nothing to compute");
@@ -336,6 +348,7 @@ size_t saeb_prep_bytes(int64_t T, int64_t d) { return prep_layout(T, d).total; }
 
 int saeb_prep_activations(const void* x, int x_dtype, int64_t T, int64_t ld_x, int64_t d, void* prep, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:prep");
   SAEB_REQUIRE(x && prep, "prep_activations: null pointer");
   SAEB_REQUIRE(x_dtype == DT_BF16 || x_dtype == DT_F16 || x_dtype == DT_F32, "prep_activations: bad x dtype %d", x_dtype);
   if (T == 0) return 0;
@@ -357,6 +370,7 @@ int saeb_encode_candidates(const void* prep, int64_t T_total, int64_t t0, int64_
                            int64_t N, int k, int margin, int64_t clamp_feature, float clamp_value, void* workspace,
                            size_t workspace_bytes, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:gemm");
   SAEB_REQUIRE(prep && packed && workspace, "encode_candidates: null pointer");
   SAEB_REQUIRE(t0 >= 0 && Tc >= 0 && t0 + Tc <= T_total, "encode_candidates: bad row range");
   SAEB_REQUIRE(clamp_feature < N, "encode_candidates: clamp_feature out of range");
@@ -397,6 +411,7 @@ int saeb_candidate_bounds(const void* prep, int64_t T_total, int64_t t0, int64_t
                           int64_t d, int64_t N, int k, int margin, int64_t clamp_feature, float* lb_out,
                           float* ub_out, void* workspace, size_t workspace_bytes, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:merge+bounds");
   SAEB_REQUIRE(prep && packed && lb_out && workspace, "candidate_bounds: null pointer");
   SAEB_REQUIRE(t0 >= 0 && Tc >= 0 && t0 + Tc <= T_total, "candidate_bounds: bad row range");
   if (Tc == 0) return 0;
@@ -430,6 +445,7 @@ static int refine_candidates_impl(bool lo, const void* x, int x_dtype, int64_t l
                                   float* out_member, int64_t* out_idx, int32_t* status_out, void* workspace,
                                   size_t workspace_bytes, int max_ctas, int value_mode, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:merge+refine");
   SAEB_REQUIRE(x && prep && packed && W_enc && out_vals && out_idx && workspace, "refine_candidates: null pointer");
   SAEB_REQUIRE(max_ctas >= 0, "refine_candidates: max_ctas must be >= 0");
   SAEB_REQUIRE(value_mode >= 0 && value_mode <= 2, "refine_candidates: value_mode must be 0, 1 or 2");
@@ -525,6 +541,7 @@ int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x,
 int saeb_dense_topk(const float* dense, int64_t T, int64_t ld, int64_t N, int k, float* out_vals, int64_t* out_idx,
                     void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:dense_topk");
   SAEB_REQUIRE(dense && out_vals && out_idx, "dense_topk: null pointer");
   int rc = dense_topk_launch(dense, T, ld, N, k, out_vals, reinterpret_cast<long long*>(out_idx), (cudaStream_t)stream);
   if (rc == 0 && T > 0) g_launches += 1;
@@ -535,6 +552,7 @@ int saeb_decode(const int64_t* idx, const float* vals, int64_t T, int k, const v
                 int64_t N, const float* b_dec, void* out, int out_dtype, int64_t ld_out, const void* x, int x_dtype,
                 int64_t ld_x, double* sq_err, int* err_flag, int max_ctas, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:decode");
   SAEB_REQUIRE(idx && vals && W_dec && out, "decode: null pointer");
   SAEB_REQUIRE(max_ctas >= 0, "decode: max_ctas must be >= 0");
   int rc = decode_launch(reinterpret_cast<const long long*>(idx), vals, T, k, W_dec, w_dtype, d, N, b_dec, out,
@@ -546,6 +564,7 @@ int saeb_decode(const int64_t* idx, const float* vals, int64_t T, int k, const v
 int saeb_decode_backward_acts(const float* grad_out, int64_t ld_g, const int64_t* idx, int64_t T, int k,
                               const float* W_dec, int64_t d, int64_t N, float* d_vals, int* err_flag, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:decode_bwd_acts");
   SAEB_REQUIRE(grad_out && idx && W_dec && d_vals, "decode_backward_acts: null pointer");
   int rc = decode_bwd_acts_launch(grad_out, ld_g, reinterpret_cast<const long long*>(idx), T, k, W_dec, d, N, d_vals,
                                   err_flag, (cudaStream_t)stream);
@@ -556,6 +575,7 @@ int saeb_decode_backward_acts(const float* grad_out, int64_t ld_g, const int64_t
 int saeb_decode_backward_weight(const float* grad_out, int64_t ld_g, const int64_t* idx, const float* vals, int64_t T,
                                 int k, int64_t d, int64_t N, float* dW_dec, int* err_flag, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:decode_bwd_weight");
   SAEB_REQUIRE(grad_out && idx && vals && dW_dec, "decode_backward_weight: null pointer");
   int rc = decode_bwd_weight_launch(grad_out, ld_g, reinterpret_cast<const long long*>(idx), vals, T, k, d, N, dW_dec,
                                     err_flag, (cudaStream_t)stream);
@@ -566,6 +586,7 @@ int saeb_decode_backward_weight(const float* grad_out, int64_t ld_g, const int64
 int saeb_total_variance(const void* x, int x_dtype, int64_t T, int64_t d, int64_t ld_x, double* scratch, double* out,
                         void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:total_variance");
   SAEB_REQUIRE(x && scratch && out, "total_variance: null pointer");
   int rc = total_variance_launch(x, x_dtype, T, d, ld_x, scratch, out, (cudaStream_t)stream);
   if (rc == 0) g_launches += 2;
@@ -578,6 +599,7 @@ int saeb_coo_extract(const float* vals, const int64_t* idx, int64_t T, int k, fl
                      const uint32_t* filter_bitmap, int64_t seq_len, int64_t row_offset, int64_t* locations,
                      float* activations, int64_t* nnz_out, void* workspace, size_t workspace_bytes, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:coo_extract");
   SAEB_REQUIRE(vals && idx && locations && activations && nnz_out && workspace, "coo_extract: null pointer");
   int rc = coo_extract_launch(vals, reinterpret_cast<const long long*>(idx), T, k, threshold, filter_bitmap, seq_len,
                               row_offset, reinterpret_cast<long long*>(locations), activations,
@@ -592,6 +614,7 @@ int saeb_coo_append(const float* vals, const int64_t* idx, int64_t T, int k, flo
                     float* activations, int64_t capacity, int64_t* cursor, int* overflow_flag, void* workspace,
                     size_t workspace_bytes, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:coo_append");
   SAEB_REQUIRE(vals && idx && locations && activations && cursor && workspace, "coo_append: null pointer");
   SAEB_REQUIRE(capacity >= 0, "coo_append: negative capacity");
   SAEB_REQUIRE(workspace_bytes >= coo_workspace_bytes(T) + 256, "coo_append: workspace too small");
@@ -611,6 +634,7 @@ int saeb_scan_pool(const float* vals, const int64_t* idx, int64_t T, int k, int 
                    const float* member, const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap,
                    int* overflow_flag, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:scan_pool");
   SAEB_REQUIRE(vals && idx && feat_thr && bucket && bucket_cnt, "scan_pool: null pointer");
   int rc = scan_pool_launch(vals, reinterpret_cast<const long long*>(idx), T, k, ctx_len, threshold, feat_lo, feat_hi,
                             window_base, tok_thr, member, feat_thr, bucket, bucket_cnt, bucket_cap, overflow_flag,
@@ -622,6 +646,7 @@ int saeb_scan_pool(const float* vals, const int64_t* idx, int64_t T, int k, int 
 int saeb_scan_merge(void* bucket, int* bucket_cnt, int bucket_cap, int64_t F, int n_top, float base_threshold,
                     float* top_vals, int64_t* top_win, float* feat_thr, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:scan_merge");
   SAEB_REQUIRE(bucket && bucket_cnt && top_vals && top_win && feat_thr, "scan_merge: null pointer");
   int rc = scan_merge_launch(bucket, bucket_cnt, bucket_cap, F, n_top, base_threshold, top_vals,
                              reinterpret_cast<long long*>(top_win), feat_thr, (cudaStream_t)stream);
@@ -641,6 +666,7 @@ int saeb_image_pool(const float* vals, const int64_t* idx, int64_t n_images, int
                     const float* tok_thr, const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap,
                     int* overflow_flag, void* workspace, size_t workspace_bytes, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:image_pool");
   SAEB_REQUIRE(vals && idx && feat_thr && bucket && bucket_cnt && workspace, "image_pool: null pointer");
   int rc = image_pool_launch(vals, reinterpret_cast<const long long*>(idx), n_images, tokens_per_image, k, n_base,
                              threshold, feat_lo, feat_hi, image_base, tok_thr, feat_thr, bucket, bucket_cnt, bucket_cap,
@@ -651,6 +677,7 @@ int saeb_image_pool(const float* vals, const int64_t* idx, int64_t n_images, int
 
 int saeb_kth_largest_gathered(const float* gathered, int R, int64_t T, int m, int kth, float* tok_thr, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:kth");
   SAEB_REQUIRE(gathered && tok_thr, "kth_largest_gathered: null pointer");
   if (T == 0) return 0;
   int rc = kth_gathered_launch(gathered, R, T, m, kth, tok_thr, (cudaStream_t)stream);
@@ -661,6 +688,7 @@ int saeb_kth_largest_gathered(const float* gathered, int R, int64_t T, int m, in
 int saeb_coo_window_scores(const int64_t* feature, const int64_t* window_key, const float* activations, int64_t nnz,
                            int mode, float divisor, float* score, int* head, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:coo_window_scores");
   SAEB_REQUIRE(feature && window_key && activations && score && head, "coo_window_scores: null pointer");
   int rc = coo_window_scores_launch(reinterpret_cast<const long long*>(feature),
                                     reinterpret_cast<const long long*>(window_key), activations, nnz, mode, divisor, score,
@@ -671,6 +699,7 @@ int saeb_coo_window_scores(const int64_t* feature, const int64_t* window_key, co
 
 int saeb_column_sums(const float* dense, int64_t T, int64_t ld, int64_t N, double* colsum, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:column_sums");
   SAEB_REQUIRE(dense && colsum, "column_sums: null pointer");
   int rc = column_sums_launch(dense, T, ld, N, colsum, (cudaStream_t)stream);
   if (rc == 0 && T > 0) g_launches += 1;
@@ -681,6 +710,7 @@ int saeb_feature_maps(const void* x, int x_dtype, int64_t T, int64_t ld_x, const
                       const float* b_dec, int64_t d, int64_t N, const int64_t* features, int n_features, float* out,
                       int* err_flag, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:feature_maps");
   SAEB_REQUIRE(x && W_enc && b_enc && b_dec && features && out, "feature_maps: null pointer");
   int rc = feature_maps_launch(x, x_dtype, T, ld_x, W_enc, b_enc, b_dec, d, N,
                                reinterpret_cast<const long long*>(features), n_features, out, err_flag,
@@ -697,6 +727,7 @@ int saeb_push_gather(const void* src, size_t bytes, void* const* peer_bases_dev,
                      size_t region_offset, void* multicast_base, size_t flags_offset, int channel, uint32_t seq,
                      int* counter, void* stream) {
   g_err[0] = 0;
+  SAEB_NVTX("saeb:exchange_push");
   SAEB_REQUIRE(src && peer_bases_dev && counter, "push_gather: null pointer");
   if (bytes == 0) return 0;
   int rc = push_gather_launch(src, bytes, peer_bases_dev, R, self_rank, region_offset, multicast_base, flags_offset,

@@ -65,7 +65,7 @@ int coo_extract_launch(const float* vals, const long long* idx, long long T, int
 // chunk between two collectives, so it sits on the critical path of the multi-GPU schedule (the first version re-read
 // the values from memory in every search step: ~0.8 ms per 37 888-token chunk at R*m = 512).
 // ---------------------------------------------------------------------------------------------
-static int g_kth_impl = 1;   // 1: register-resident search (default); 0: memory-resident (first version, diagnostics)
+static thread_local int g_kth_impl = 1;   // 1: register-resident search (default); 0: memory-resident (first version, diagnostics)
 int set_kth_impl(int v) {
   g_kth_impl = v ? 1 : 0;
   return 0;

@@ -426,12 +426,12 @@ static int num_sms() {
 
 int cap_for_k(int k) { return k <= 128 ? 256 : (k <= 256 ? 512 : 1024); }
 
-static int g_l2_hints = 1;   // 1: activation tiles evict_last (they are re-read once per feature tile), weights normal
+static thread_local int g_l2_hints = 1;   // 1: activation tiles evict_last (they are re-read once per feature tile), weights normal
 int set_l2_hints(int v) {
   g_l2_hints = v;
   return 0;
 }
-static int g_persist_a = 1;   // 1: pin the activation planes in the persisting part of L2 for the duration of the launch
+static thread_local int g_persist_a = 1;   // 1: pin the activation planes in the persisting part of L2 for the duration of the launch
 static size_t g_persist_bytes = 0;
 int set_persist_a(int v) {
   g_persist_a = v;
@@ -462,17 +462,17 @@ int read_stats(unsigned long long* out8) {
   if (!g_stats) return -1;
   return cudaMemcpy(out8, g_stats, 64, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }
-static int g_prefetch_b = 0;   // measured: no gain (7.07-7.12 ms per wave without, 7.03-7.19 with), kept as an option
+static thread_local int g_prefetch_b = 0;   // measured: no gain (7.07-7.12 ms per wave without, 7.03-7.19 with), kept as an option
 int set_prefetch_b(int v) {
   g_prefetch_b = v < 0 ? 0 : v;
   return 0;
 }
-static int g_dbg = 0;
+static thread_local int g_dbg = 0;
 int set_dbg(int v) {
   g_dbg = v;
   return 0;
 }
-static int g_splits = 0;     // 0 = automatic
+static thread_local int g_splits = 0;     // 0 = automatic
 int set_splits(int v) {
   if (v < 0 || v > 64) {
     set_error("splits must be in 0..64 (0 = automatic)");
@@ -536,12 +536,12 @@ struct EncodePlan {
   ChunkPlan chunks[512];
   size_t total_bytes;
 };
-static int g_chunking = 1;   // 0: one launch for the whole call
+static thread_local int g_chunking = 1;   // 0: one launch for the whole call
 // SMs left free by the persistent GEMM grid.  The feature-sharded scan runs its collectives, refinement and list
 // update on a second stream while the next chunk's GEMM is in flight; a grid that owns every SM would make those
 // kernels (NCCL's in particular: too many registers to co-reside) wait for a launch boundary and then displace GEMM
 // CTAs, which doubles that launch.
-static int g_reserve_sms = 0;
+static thread_local int g_reserve_sms = 0;
 int set_reserve_sms(int v) {
   g_reserve_sms = v < 0 ? 0 : v;
   return 0;
@@ -581,9 +581,9 @@ static bool make_plan(EncodePlan& p, long long T, long long N, int k, int pair) 
   return true;
 }
 
-static int g_profile = 0;
-static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
-static bool g_ev_valid = false;
+static thread_local int g_profile = 0;
+static thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;   // per calling thread, recorded on the call's stream
+static thread_local bool g_ev_valid = false;
 int set_profile(int v) {
   g_profile = v ? 1 : 0;
   if (g_profile && g_ev0 == nullptr) {
@@ -602,7 +602,7 @@ float last_encode_ms() {
   if (cudaEventElapsedTime(&ms, g_ev0, g_ev1) != cudaSuccess) return -1.f;
   return ms;
 }
-static int g_cta_pair = 0;   // 0 = not initialised (env SAEB_CTA_PAIR or default 2)
+static thread_local int g_cta_pair = 0;   // 0 = not initialised (env SAEB_CTA_PAIR or default 2)
 static int default_pair() {
   if (g_cta_pair == 0) {
     const char* e = getenv("SAEB_CTA_PAIR");
@@ -637,7 +637,7 @@ size_t encode_workspace_bytes(long long T, long long d, long long N, int k) {
 
 // depth of the smem ring (0 = as deep as fits: 6 stages of 32 KB in the single-pass pair mode).  5 leaves ~54 KB of
 // shared memory per SM to the gather CTAs that run beside the GEMM (saeb200.overlap).
-static int g_gemm_stages = 0;
+static thread_local int g_gemm_stages = 0;
 int set_gemm_stages(int v) {
   if (v != 0 && (v < 2 || v > 8)) {
     set_error("gemm_stages must be 0 (automatic) or 2..8");
@@ -728,7 +728,7 @@ static int launch_planes(int ap, int bp, const CUtensorMap& ta, const CUtensorMa
 // 33 resident clusters of four CTAs (132 of 148 SMs; GPC geometry) and the per-round time drops by < 2 % -- the L2
 // slices already merge the simultaneous unicast reads of up to ~4 CTAs, so multicast at cluster size 4 removes no L2
 // traffic (B300_MICROARCH: "at csz <= 4, MC ~ UC").  Kept as an option, off by default.
-static int g_cluster4 = 0;          // 0: never, 1: when every token tile of the launch gets a resident cluster, 2: always
+static thread_local int g_cluster4 = 0;          // 0: never, 1: when every token tile of the launch gets a resident cluster, 2: always
 static int g_max_clusters4 = -1;    // resident clusters of 4 CTAs the device offers this kernel (queried once)
 int set_cluster4(int v) {
   if (v < 0 || v > 2) {

@@ -40,7 +40,7 @@ int candidate_bounds_launch(const float* cand_vals, const long long* cand_idx, l
 // threads per refinement CTA in feature-sharded calls (ext_lower given): a shard evaluates only ~k/R + a few candidates
 // per token, so smaller blocks keep more tokens in flight when the kernel has the GPU to itself (128, the measured
 // default); beside a persistent GEMM grid only one CTA fits per SM and 256 threads keep more loads in flight
-static int g_refine_threads_sharded = 128;
+static thread_local int g_refine_threads_sharded = 128;
 int set_refine_threads(int v) {
   if (v < 32 || v > RF_THREADS || (v & 31)) {
     set_error("refine_threads must be a multiple of 32 in 32..%d", RF_THREADS);

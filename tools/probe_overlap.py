@@ -237,7 +237,59 @@ def exp_gemm_only(cluster4=1, stages=0):
                 max_clusters4=int(L.saeb_query(b"max_clusters4")))
 
 
+def exp_shard_phases(world=8, rank=3, tokens=1048576 // 4, waves=4):
+    """where does the GEMM stream of ONE rank of the feature-sharded scan spend its time?  prep / GEMM launches /
+    merge + bounds timed separately (CUDA events, summed over the chunks) for the shard N / world on one GPU"""
+    import torch
+    from saeb200 import _capi, dist as sdist, engine, synth
+    L = _capi.lib()
+    check = _capi.check
+    sae = synth.make_sae(D, N, K, "cuda", seed=1234)
+    lo, hi = sdist.shard_range(N, world, rank)
+    enc = engine.PackedEncoder.pack(sae.encoder.weight.data[lo:hi], sae.encoder.bias.data[lo:hi], sae.b_dec.data, 3)
+    Ns = hi - lo
+    chunk = waves * 9472
+    x = synth.make_activations(tokens, D, "cuda", seed=5)
+    prep = torch.empty(L.saeb_prep_bytes(chunk, D), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(L.saeb_candidates_workspace_bytes(chunk, D, Ns, K, 0), dtype=torch.uint8, device="cuda")
+    lb = torch.empty((chunk, K), dtype=torch.float32, device="cuda")
+    ub = torch.empty((chunk, K), dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    acc = {"prep": 0.0, "gemm": 0.0, "merge+bounds": 0.0}
+    n_chunks = 0
+    for rep in range(2):
+        evs = []
+        for t0 in range(0, tokens - chunk + 1, chunk):
+            xc = x[t0:t0 + chunk]
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            e[0].record()
+            check(L.saeb_prep_activations(xc.data_ptr(), _capi.BF16, chunk, D, D, prep.data_ptr(), st), "prep")
+            e[1].record()
+            check(L.saeb_encode_candidates(prep.data_ptr(), chunk, 0, chunk, enc.blob.data_ptr(), D, Ns, K, 0, -1, 0.0,
+                                           ws.data_ptr(), ws.numel(), st), "gemm")
+            e[2].record()
+            check(L.saeb_candidate_bounds(prep.data_ptr(), chunk, 0, chunk, enc.blob.data_ptr(), _capi.BF16, D, Ns, K, 0,
+                                          -1, lb.data_ptr(), ub.data_ptr(), ws.data_ptr(), ws.numel(), st), "bounds")
+            e[3].record()
+            evs.append(e)
+        torch.cuda.synchronize()
+        if rep == 1:
+            for e in evs:
+                acc["prep"] += e[0].elapsed_time(e[1])
+                acc["gemm"] += e[1].elapsed_time(e[2])
+                acc["merge+bounds"] += e[2].elapsed_time(e[3])
+            n_chunks = len(evs)
+    flops = 2.0 * n_chunks * chunk * D * Ns
+    return dict(world=world, features=Ns, chunk_tokens=chunk, chunks=n_chunks,
+                ms_per_chunk={k_: round(v_ / n_chunks, 3) for k_, v_ in acc.items()},
+                gemm_tflops=round(flops / (acc["gemm"] * 1e-3) / 1e12, 1),
+                per_1M_tokens_ms={k_: round(v_ / (n_chunks * chunk) * 1048576, 1) for k_, v_ in acc.items()})
+
+
 EXPS = {
+    "shard8": lambda: exp_shard_phases(8, 3),
+    "shard8_w8": lambda: exp_shard_phases(8, 3, waves=8),
+    "shard1": lambda: exp_shard_phases(1, 0),
     "gemm_pair": lambda: exp_gemm_only(0),
     "gemm_cl4": lambda: exp_gemm_only(2),
     "gemm_cl4_auto": lambda: exp_gemm_only(1),
