@@ -170,10 +170,12 @@ int saeb_refine_candidates_lo(const void* x, int x_dtype, int64_t ld_x, const vo
  * a_j - eps_j (descending, lb_out [Tc,k]).  All-gather them, take the per-token k-th largest (saeb_kth_of_gathered):
  * that is a lower bound of the token's GLOBAL k-th activation; pass it as `ext_lower` (with already_merged = 1) and
  * the shard only re-evaluates candidates that can still be in the global TopK (about k/R + a few per token instead of
- * k + 25).  ub_out (optional, [Tc,k]): the k largest UPPER bounds a_j + eps_j as well, for value_mode 2. */
+ * k + 25).  ub_out (optional, [Tc,k]): the k largest UPPER bounds a_j + eps_j as well, for value_mode 2.
+ * coresident != 0: launch shapes that fit beside a resident GEMM CTA (the call then can run on another stream INSIDE
+ * the next chunk's GEMM launches instead of between them). */
 int saeb_candidate_bounds(const void* prep, int64_t T_total, int64_t t0, int64_t Tc, const void* packed, int x_dtype,
                           int64_t d, int64_t N, int k, int margin, int64_t clamp_feature, float* lb_out, float* ub_out,
-                          void* workspace, size_t workspace_bytes, void* stream);
+                          void* workspace, size_t workspace_bytes, int coresident, void* stream);
 
 /* TopK of dense non-negative rows, (value desc, index asc): Sae.select_topk (sae/sae.py:179-181) for callers that hold
  * a dense [T, ld] latent tensor. */

@@ -409,7 +409,7 @@ static inline float refine_c_eps(int /*x_dtype*/) {
 // already_merged = 1).
 int saeb_candidate_bounds(const void* prep, int64_t T_total, int64_t t0, int64_t Tc, const void* packed, int x_dtype,
                           int64_t d, int64_t N, int k, int margin, int64_t clamp_feature, float* lb_out,
-                          float* ub_out, void* workspace, size_t workspace_bytes, void* stream) {
+                          float* ub_out, void* workspace, size_t workspace_bytes, int coresident, void* stream) {
   g_err[0] = 0;
   SAEB_NVTX("saeb:merge+bounds");
   SAEB_REQUIRE(prep && packed && lb_out && workspace, "candidate_bounds: null pointer");
@@ -428,7 +428,7 @@ int saeb_candidate_bounds(const void* prep, int64_t T_total, int64_t t0, int64_t
   const float* dnorm = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + 2 * bias_bytes(N));
   float* mvals = reinterpret_cast<float*>(ws + w.mvals);
   long long* midx = reinterpret_cast<long long*>(ws + w.midx);
-  int rc = encode_merge_launch(Tc, N, K2, mvals, midx, ws + w.enc, w.total - w.enc, 0, st);
+  int rc = encode_merge_launch(Tc, N, K2, mvals, midx, ws + w.enc, w.total - w.enc, coresident, st);
   if (rc) return rc;
   rc = candidate_bounds_launch(mvals, midx, Tc, K2, k < K2 ? k : K2, wnorm, dnorm,
                                reinterpret_cast<const float*>(pb + p.xnorm) + t0,

@@ -129,6 +129,18 @@ class Sae(nn.Module):
         return self.encoder.weight.dtype
 
     # ------------------------------------------------------------------ engine plumbing
+    def invalidate_packed(self) -> None:
+        """Drop the device-side repacks of the encoder.  They are rebuilt automatically when a parameter is replaced or
+        modified in place through autograd-visible ops (the cache key holds data_ptr and `_version`); writes through
+        `.data` (e.g. `sae.encoder.weight.data.mul_(2)`) bump neither -- call this after such edits.  Loading a state
+        dict does it for you."""
+        self._packed.clear()
+        self._overlap = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self.invalidate_packed()
+
     def packed_encoder(self, planes: Optional[int] = None) -> engine.PackedEncoder:
         planes = self.encoder_planes if planes is None else planes
         w, b, bd = self.encoder.weight, self.encoder.bias, self.b_dec
@@ -213,7 +225,9 @@ class Sae(nn.Module):
             sq_err = torch.zeros((), dtype=torch.float64, device=top_acts.device)
             sae_out = engine.decode(top_indices, top_acts, self.W_dec.data, self.b_dec.data, out_dtype=torch.float32,
                                     x=x, sq_err=sq_err)
-        total_variance = engine.total_variance(x)
+        # reference: (x - x.mean(0)).pow(2).sum() -- the mean is over the FIRST dimension only (sae/sae.py:204), so a
+        # [batch, seq, d] input is centred per (position, channel), i.e. as a [batch, seq * d] matrix
+        total_variance = engine.total_variance(x if x.dim() <= 2 else x.reshape(x.shape[0], -1))
         fvu = (sq_err / total_variance).to(torch.float32)
         zero = sae_out.new_tensor(0.0)
         return ForwardOutput(sae_out, top_acts, top_indices, fvu, zero, zero)

@@ -162,7 +162,9 @@ class EngineOps:
             store[slot] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         return store[slot]
 
-    def local_bounds(self, x, k, slot=0):
+    def local_gemm(self, x, k, slot=0):
+        """tensor-core half of a chunk: activation prep + the fused GEMM launches with candidate selection (enqueued on
+        the current stream).  `local_bounds_finish(slot)` completes it; `local_bounds` = both."""
         eng, L = self.engine, self._capi.lib()
         enc = self.enc
         x2 = eng._as_2d(x, enc.d_in)
@@ -171,14 +173,12 @@ class EngineOps:
         if enc.planes < 3:
             vals, idx, _ = eng.encode_topk(x2, enc, k)
             self._cached[slot] = (vals, idx + self.feat_lo)
-            return vals, vals
+            return
         dev = x2.device
         with torch.cuda.device(dev):
             prep = self._scratch(self._prep, slot, L.saeb_prep_bytes(T, enc.d_in), dev)
             ws = self._scratch(self._ws, slot, L.saeb_candidates_workspace_bytes(T, enc.d_in, enc.num_latents, k, 0),
                                dev)
-            lb = self._scratch(self._lb, slot, T * k * 4, dev)[: T * k * 4].view(torch.float32).view(T, k)
-            ub = self._scratch(self._ub, slot, T * k * 4, dev)[: T * k * 4].view(torch.float32).view(T, k)
             st = torch.cuda.current_stream().cuda_stream
             code = eng._code(x2)
             ldx = x2.stride(0) if T > 1 else enc.d_in
@@ -187,10 +187,32 @@ class EngineOps:
             self._capi.check(L.saeb_encode_candidates(prep.data_ptr(), T, 0, T, enc.blob.data_ptr(), enc.d_in,
                                                       enc.num_latents, k, 0, -1, 0.0, ws.data_ptr(), ws.numel(), st),
                              "saeb_encode_candidates")
-            self._capi.check(L.saeb_candidate_bounds(prep.data_ptr(), T, 0, T, enc.blob.data_ptr(), code, enc.d_in,
-                                                     enc.num_latents, k, 0, -1, lb.data_ptr(), ub.data_ptr(),
-                                                     ws.data_ptr(), ws.numel(), st), "saeb_candidate_bounds")
+
+    def local_bounds_finish(self, slot=0, coresident=False):
+        """candidate merge + per-token bound lists of the chunk given to `local_gemm` -> (lb, ub), both [Tc, k]
+        descending.  Small kernels: with `coresident` they are shaped to run on another stream INSIDE the next chunk's
+        GEMM launches."""
+        eng, L = self.engine, self._capi.lib()
+        enc, x2, k = self.enc, self._x[slot], self._k[slot]
+        if enc.planes < 3:
+            vals = self._cached[slot][0]
+            return vals, vals
+        T = x2.shape[0]
+        dev = x2.device
+        with torch.cuda.device(dev):
+            prep, ws = self._prep[slot], self._ws[slot]
+            lb = self._scratch(self._lb, slot, T * k * 4, dev)[: T * k * 4].view(torch.float32).view(T, k)
+            ub = self._scratch(self._ub, slot, T * k * 4, dev)[: T * k * 4].view(torch.float32).view(T, k)
+            st = torch.cuda.current_stream().cuda_stream
+            self._capi.check(L.saeb_candidate_bounds(prep.data_ptr(), T, 0, T, enc.blob.data_ptr(), eng._code(x2),
+                                                     enc.d_in, enc.num_latents, k, 0, -1, lb.data_ptr(), ub.data_ptr(),
+                                                     ws.data_ptr(), ws.numel(), 1 if coresident else 0, st),
+                             "saeb_candidate_bounds")
         return lb, ub
+
+    def local_bounds(self, x, k, slot=0):
+        self.local_gemm(x, k, slot)
+        return self.local_bounds_finish(slot)
 
     def local_topk(self, ext_L=None, ext_U=None, slot=0):
         """exact local TopK entries of the chunk given to local_bounds -> (vals, member, global ids), all [Tc, k].
@@ -429,11 +451,15 @@ def _pipelined_loop(chunks, ops, finish, k_local, ctx_len, sg, sa, cur) -> int:
     slot_free = [None, None]   # event: the chunk that last used this slot's scratch has left stream_aux
     prev = None
 
+    split = hasattr(ops, "local_gemm") and hasattr(ops, "local_bounds_finish")
+
     def drain(item):
-        x, lb, ready, slot, base = item
+        x, bounds, ready, slot, base = item
         with torch.cuda.stream(sa):
             sa.wait_event(ready)
-            finish(x, lb, slot, base)
+            if bounds is None:   # merge + bounds belong to the small-kernel chain, not to the tensor-core stream
+                bounds = ops.local_bounds_finish(slot, coresident=True)
+            finish(x, bounds, slot, base)
             slot_free[slot] = torch.cuda.Event()
             slot_free[slot].record(sa)
 
@@ -445,13 +471,17 @@ def _pipelined_loop(chunks, ops, finish, k_local, ctx_len, sg, sa, cur) -> int:
             sg.wait_stream(cur)   # whatever produced this chunk on the caller's stream
             if slot_free[slot] is not None:
                 sg.wait_event(slot_free[slot])
-            lb = ops.local_bounds(x, k_local, slot)
+            if split:
+                ops.local_gemm(x, k_local, slot)
+                bounds = None
+            else:
+                bounds = ops.local_bounds(x, k_local, slot)
             ready = torch.cuda.Event()
             ready.record(sg)
         n_tok = x.shape[0] if x.dim() == 2 else x.numel() // x.shape[-1]
         if prev is not None:
             drain(prev)
-        prev = (x, lb, ready, slot, window_base)
+        prev = (x, bounds, ready, slot, window_base)
         window_base += n_tok // ctx_len
     if prev is not None:
         drain(prev)

@@ -14,6 +14,9 @@ from ._capi import SaebError, check
 
 _DT = {torch.float32: _capi.F32, torch.bfloat16: _capi.BF16, torch.float16: _capi.F16}
 ACT_THRESHOLD = 1e-5  # reference features/cache.py:80-81
+# SAEB_DEBUG_CHECKS=1: read the kernels' device-side error flags after every call (synchronises) and raise on an
+# out-of-range index; off by default, the flags stay readable as `decode.last_err_flag` / `decode_backward.last_err_flag`
+DEBUG_CHECKS = __import__("os").environ.get("SAEB_DEBUG_CHECKS", "0") == "1"
 VALUES_EXACT, VALUES_BOUNDARY = 0, 1  # `value_mode` of the refinement (include/saeb200.h)
 
 
@@ -240,6 +243,8 @@ def decode(top_indices: torch.Tensor, top_acts: torch.Tensor, W_dec: torch.Tenso
                             None if (sq_err is None or x2 is None) else sq_err.data_ptr(), err_flag.data_ptr(),
                             int(max_ctas), _stream()), "saeb_decode")
     decode.last_err_flag = err_flag
+    if DEBUG_CHECKS and int(err_flag.item()) != 0:   # synchronises: debugging aid (SAEB_DEBUG_CHECKS=1)
+        raise SaebError("decode: a TopK index is outside [0, num_latents) (the reference's tl.device_assert)")
     return out.view(*lead, d)
 
 

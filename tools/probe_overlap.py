@@ -269,7 +269,7 @@ def exp_shard_phases(world=8, rank=3, tokens=1048576 // 4, waves=4):
                                            ws.data_ptr(), ws.numel(), st), "gemm")
             e[2].record()
             check(L.saeb_candidate_bounds(prep.data_ptr(), chunk, 0, chunk, enc.blob.data_ptr(), _capi.BF16, D, Ns, K, 0,
-                                          -1, lb.data_ptr(), ub.data_ptr(), ws.data_ptr(), ws.numel(), st), "bounds")
+                                          -1, lb.data_ptr(), ub.data_ptr(), ws.data_ptr(), ws.numel(), 0, st), "bounds")
             e[3].record()
             evs.append(e)
         torch.cuda.synchronize()
