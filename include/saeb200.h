@@ -45,7 +45,10 @@ long long saeb_launch_count(void);
  * when the kernel runs beside a GEMM launch, where only one CTA fits per SM).  "kth_impl": see
  * saeb_kth_largest_gathered.  "gemm_stages": depth of the GEMM's shared-memory ring (0 = as deep as fits: 6; 5 leaves
  * ~54 KB per SM to gather CTAs running beside it).  "cluster4": 4-CTA clusters sharing the activation tile by TMA
- * multicast (0 = off, default; 1 = when every token tile gets a resident cluster; 2 = always).  "stats": cycle /
+ * multicast (0 = off, default; 1 = when every token tile gets a resident cluster; 2 = always).  "scan_warp": 1
+ * (default) = feature-sharded scan calls of the refinement (value_mode 2 with ext_lower and ext_upper) run as the
+ * warp-per-token kernel without shared memory, which is scheduled beside a resident GEMM CTA; 0 = CTA per token.
+ * "stats": cycle /
  * gather counters for saeb_debug_stats.  "l2_hints", "debug_tiles", "prefetch_b": diagnostics.
  * Options are PER CALLING THREAD (thread-local state, like the error string): two threads driving two streams or two
  * SAEs never see each other's settings, and the profiling events belong to the thread that set "profile". */
@@ -273,6 +276,16 @@ int saeb_scan_pool(const float* vals, const int64_t* idx, int64_t T, int k, int 
                    int* overflow_flag, void* stream);
 int saeb_scan_merge(void* bucket, int* bucket_cnt, int bucket_cap, int64_t F, int n_top, float base_threshold,
                     float* top_vals, int64_t* top_win, float* feat_thr, void* stream);
+/* saeb_scan_pool with its hash tables in global scratch instead of shared memory (same appended entries): persistent
+ * 128-thread CTAs without shared memory, which are scheduled beside a resident CTA of the fused GEMM -- the form the
+ * pipelined scan uses, where the list update of chunk c runs inside the GEMM launches of chunk c+1.  The scratch
+ * (saeb_scan_pool_workspace_bytes) is initialised ONCE with saeb_scan_pool_init and left initialised by every call. */
+size_t saeb_scan_pool_workspace_bytes(int k, int ctx_len);
+int saeb_scan_pool_init(void* workspace, size_t workspace_bytes, int k, int ctx_len, void* stream);
+int saeb_scan_pool_ws(const float* vals, const int64_t* idx, int64_t T, int k, int ctx_len, float threshold,
+                      int64_t feat_lo, int64_t feat_hi, int64_t window_base, const float* tok_thr, const float* member,
+                      const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap, int* overflow_flag,
+                      void* workspace, size_t workspace_bytes, void* stream);
 /* Image form of the scan (replaces, for all features at once, pool_max_activations_windows_image,
  * features/constructors.py:88-148): the score of (feature, image) is the MEAN of the feature's TopK-masked activations
  * over the first n_base positions of the image's token row (avg_pool1d over the 576 base image tokens, :109-114).
@@ -297,6 +310,14 @@ int saeb_image_pool(const float* vals, const int64_t* idx, int64_t n_images, int
  * m = kth = k form.  Option "kth_impl" = 0 selects the first, memory-resident version of the kernel (diagnostics). */
 int saeb_kth_largest_gathered(const float* gathered, int R, int64_t T, int m, int kth, float* tok_thr, void* stream);
 int saeb_kth_of_gathered(const float* gathered, int R, int64_t T, int k, float* tok_thr, void* stream);
+/* Exchange 1 of the feature-sharded scan in one pass.  gathered [R][T][2*m1] f32: per shard and token the m1 largest
+ * lower bounds followed by the m1 largest upper bounds of saeb_candidate_bounds (both descending).  Writes
+ *   ext_lower[t] = k-th largest of the R*m1 lower bounds (0 if R*m1 < k)             -> `ext_lower` of the refinement
+ *   ext_upper[t] = max((k+1)-th largest of the R*m1 upper bounds (0 if R*m1 < k+1),
+ *                      the largest LAST column any shard sent)                       -> `ext_upper` (value_mode 2)
+ * (whatever a shard did not send is no larger than the last bound it sent).  R*m1 <= 2048. */
+int saeb_gathered_bounds(const float* gathered, int R, int64_t T, int m1, int k, float* ext_lower, float* ext_upper,
+                         void* stream);
 
 /* ---- peer-memory all-gather for the feature-sharded scan (optional replacement of the two per-chunk NCCL
  * all-gathers) -------------------------------------------------------------------------------------

@@ -96,6 +96,14 @@ int coo_extract_launch(const float* vals, const long long* idx, long long T, int
 int kth_gathered_launch(const float* gathered, int R, long long T, int m, int kth, float* tok_thr,
                         cudaStream_t stream);
 int set_kth_impl(int v);
+int gathered_bounds_launch(const float* gathered, int R, long long T, int m1, int k, float* ext_L, float* ext_U,
+                           cudaStream_t stream);
+size_t scan_pool_workspace_bytes(int k, int ctx_len);
+int scan_pool_init(void* ws, size_t ws_bytes, int k, int ctx_len, cudaStream_t stream);
+int scan_pool_ws_launch(const float* vals, const long long* idx, long long T, int k, int ctx_len, float threshold,
+                        long long feat_lo, long long feat_hi, long long window_base, const float* tok_thr,
+                        const float* member, const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap,
+                        int* overflow, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t image_pool_workspace_bytes(int k, int n_base, long long F);
 int image_pool_init(void* ws, size_t ws_bytes, int k, int n_base, long long F, cudaStream_t stream);
 int image_pool_launch(const float* vals, const long long* idx, long long n_images, long long tokens_per_image, int k,
@@ -103,6 +111,7 @@ int image_pool_launch(const float* vals, const long long* idx, long long n_image
                       const float* tok_thr, const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap,
                       int* overflow, void* ws, size_t ws_bytes, cudaStream_t stream);
 int set_refine_threads(int v);
+int set_scan_warp(int v);
 int decode_bwd_acts_launch(const float* grad_out, long long ld_g, const long long* idx, long long T, int k,
                            const float* W_dec, long long d, long long N, float* d_vals, int* err_flag,
                            cudaStream_t stream);
@@ -177,6 +186,7 @@ int saeb_set_option(const char* name, int value) {
   if (strcmp(name, "cluster4") == 0) return set_cluster4(value);
   if (strcmp(name, "kth_impl") == 0) return set_kth_impl(value);
   if (strcmp(name, "refine_threads") == 0) return set_refine_threads(value);
+  if (strcmp(name, "scan_warp") == 0) return set_scan_warp(value);
   if (strcmp(name, "refine_margin") == 0) {
     g_default_margin = value;
     return 0;
@@ -681,6 +691,38 @@ int saeb_kth_largest_gathered(const float* gathered, int R, int64_t T, int m, in
   SAEB_REQUIRE(gathered && tok_thr, "kth_largest_gathered: null pointer");
   if (T == 0) return 0;
   int rc = kth_gathered_launch(gathered, R, T, m, kth, tok_thr, (cudaStream_t)stream);
+  if (rc == 0) g_launches += 1;
+  return rc;
+}
+
+int saeb_gathered_bounds(const float* gathered, int R, int64_t T, int m1, int k, float* ext_lower, float* ext_upper,
+                         void* stream) {
+  g_err[0] = 0;
+  SAEB_NVTX("saeb:gathered_bounds");
+  SAEB_REQUIRE(gathered && ext_lower && ext_upper, "gathered_bounds: null pointer");
+  if (T == 0) return 0;
+  int rc = gathered_bounds_launch(gathered, R, T, m1, k, ext_lower, ext_upper, (cudaStream_t)stream);
+  if (rc == 0) g_launches += 1;
+  return rc;
+}
+
+size_t saeb_scan_pool_workspace_bytes(int k, int ctx_len) { return scan_pool_workspace_bytes(k, ctx_len); }
+
+int saeb_scan_pool_init(void* workspace, size_t workspace_bytes, int k, int ctx_len, void* stream) {
+  g_err[0] = 0;
+  return scan_pool_init(workspace, workspace_bytes, k, ctx_len, (cudaStream_t)stream);
+}
+
+int saeb_scan_pool_ws(const float* vals, const int64_t* idx, int64_t T, int k, int ctx_len, float threshold,
+                      int64_t feat_lo, int64_t feat_hi, int64_t window_base, const float* tok_thr, const float* member,
+                      const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap, int* overflow_flag,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  g_err[0] = 0;
+  SAEB_NVTX("saeb:scan_pool");
+  SAEB_REQUIRE(vals && idx && feat_thr && bucket && bucket_cnt && workspace, "scan_pool: null pointer");
+  int rc = scan_pool_ws_launch(vals, reinterpret_cast<const long long*>(idx), T, k, ctx_len, threshold, feat_lo, feat_hi,
+                               window_base, tok_thr, member, feat_thr, bucket, bucket_cnt, bucket_cap, overflow_flag,
+                               workspace, workspace_bytes, (cudaStream_t)stream);
   if (rc == 0) g_launches += 1;
   return rc;
 }

@@ -91,6 +91,25 @@ int kth_gathered_launch(const float* gathered, int R, long long T, int m, int kt
   return 0;
 }
 
+int gathered_bounds_launch(const float* gathered, int R, long long T, int m1, int k, float* ext_L, float* ext_U,
+                           cudaStream_t stream) {
+  SAEB_REQUIRE(R >= 1 && T > 0 && m1 >= 1 && k >= 1, "gathered_bounds: bad arguments R=%d T=%lld m1=%d k=%d", R, T, m1, k);
+  const int M = R * m1;
+  SAEB_REQUIRE(M <= 2048, "gathered_bounds: R*m1=%d too large (max 2048)", M);
+  const int wpb = 4;
+  const unsigned blocks = (unsigned)((T + wpb - 1) / wpb);
+  if (M <= 128)
+    gathered_bounds_kernel<4><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m1, k, ext_L, ext_U);
+  else if (M <= 256)
+    gathered_bounds_kernel<8><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m1, k, ext_L, ext_U);
+  else if (M <= 512)
+    gathered_bounds_kernel<16><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m1, k, ext_L, ext_U);
+  else
+    gathered_bounds_kernel<64><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m1, k, ext_L, ext_U);
+  SAEB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // top-activation scan
 // ---------------------------------------------------------------------------------------------
@@ -116,12 +135,66 @@ int scan_pool_launch(const float* vals, const long long* idx, long long T, int k
   return 0;
 }
 
+// ---- global-hash form of scan_pool (no shared memory: runs beside a resident GEMM CTA) ----
+struct ScanPoolPlan {
+  int grid, slots;
+  size_t keys_off, vals_off, list_off, total;
+};
+static ScanPoolPlan scan_pool_plan(int k, int ctx_len) {
+  ScanPoolPlan p;
+  const long long ent = (long long)ctx_len * k;
+  p.slots = 64;
+  while (p.slots < 2 * ent) p.slots <<= 1;
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  p.grid = 2 * (sms > 0 ? sms : 148);
+  const size_t tab = (size_t)p.grid * p.slots * 4;
+  p.vals_off = 0;
+  p.keys_off = tab;
+  p.list_off = 2 * tab;
+  p.total = 3 * tab;
+  return p;
+}
+size_t scan_pool_workspace_bytes(int k, int ctx_len) { return scan_pool_plan(k, ctx_len).total; }
+
+int scan_pool_init(void* ws, size_t ws_bytes, int k, int ctx_len, cudaStream_t stream) {
+  const ScanPoolPlan p = scan_pool_plan(k, ctx_len);
+  SAEB_REQUIRE(ws != nullptr && ws_bytes >= p.total, "scan_pool: workspace too small");
+  uint8_t* b = reinterpret_cast<uint8_t*>(ws);
+  SAEB_CHECK_CUDA(cudaMemsetAsync(b + p.vals_off, 0, p.keys_off - p.vals_off, stream));
+  SAEB_CHECK_CUDA(cudaMemsetAsync(b + p.keys_off, 0xff, p.list_off - p.keys_off, stream));   // HASH_EMPTY
+  return 0;
+}
+
+int scan_pool_ws_launch(const float* vals, const long long* idx, long long T, int k, int ctx_len, float threshold,
+                        long long feat_lo, long long feat_hi, long long window_base, const float* tok_thr,
+                        const float* member, const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap,
+                        int* overflow, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  SAEB_REQUIRE(T > 0 && k >= 1 && ctx_len >= 1, "scan_pool: bad arguments");
+  const long long n_win = (T + ctx_len - 1) / ctx_len;
+  SAEB_REQUIRE(n_win <= bucket_cap, "scan_pool: %lld windows per call exceed the bucket capacity %d", n_win,
+               bucket_cap);
+  const ScanPoolPlan p = scan_pool_plan(k, ctx_len);
+  SAEB_REQUIRE(ws != nullptr && ws_bytes >= p.total, "scan_pool: workspace too small");
+  uint8_t* b = reinterpret_cast<uint8_t*>(ws);
+  const int grid = n_win < p.grid ? (int)n_win : p.grid;
+  scan_pool_g_kernel<<<grid, 128, 0, stream>>>(vals, idx, T, k, ctx_len, threshold, feat_lo, feat_hi, window_base,
+                                               tok_thr, member, feat_thr, reinterpret_cast<uint2*>(bucket), bucket_cnt,
+                                               bucket_cap, p.slots, reinterpret_cast<uint32_t*>(b + p.keys_off),
+                                               reinterpret_cast<uint32_t*>(b + p.vals_off),
+                                               reinterpret_cast<int*>(b + p.list_off), n_win, overflow);
+  SAEB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int scan_merge_launch(void* bucket, int* bucket_cnt, int bucket_cap, long long F, int n_top, float base_thr,
                       float* top_vals, long long* top_win, float* feat_thr, cudaStream_t stream) {
   SAEB_REQUIRE(F > 0 && n_top >= 1 && n_top <= 1024, "scan_merge: bad arguments");
   int sort_n = 2;
   while (sort_n < n_top + bucket_cap) sort_n <<= 1;
-  const int wpb = 8;
+  // 4 warps per block: 16 KB at the default bucket capacity, small enough to be scheduled beside a resident GEMM CTA
+  const int wpb = ((size_t)8 * sort_n * sizeof(uint2) > 16 * 1024) ? 4 : 8;
   const size_t smem = (size_t)wpb * sort_n * sizeof(uint2);
   SAEB_REQUIRE(smem <= 200 * 1024, "scan_merge: n_top + bucket_cap too large");
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(scan_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -202,6 +202,70 @@ __global__ void scan_pool_kernel(const float* __restrict__ vals, const long long
   }
 }
 
+// Same result as scan_pool_kernel with the hash table in GLOBAL scratch instead of shared memory: persistent CTAs of 128
+// threads walk the windows (blockIdx.x, blockIdx.x + gridDim.x, ...), each with a private table that cleans itself
+// through the list of slots it occupied (like image_pool_kernel), so the launch needs no shared memory and is
+// scheduled beside a resident GEMM CTA -- the pipelined scan runs its list update inside the next chunk's GEMM
+// launches.  Entries that cannot beat their feature's current n-th best are dropped BEFORE they reach the table
+// (the pooled maximum is appended only if it beats that threshold, so the appended set is the same): late in a
+// scan almost nothing is inserted.  Scratch: keys [G][slots] (HASH_EMPTY), vals [G][slots] (0), list [G][slots];
+// initialised once, left initialised by every call.
+__global__ void __launch_bounds__(128)
+scan_pool_g_kernel(const float* __restrict__ vals, const long long* __restrict__ idx, long long T, int k, int ctx_len,
+                   float threshold, long long feat_lo, long long feat_hi, long long window_base,
+                   const float* __restrict__ tok_thr, const float* __restrict__ member,
+                   const float* __restrict__ feat_thr, uint2* __restrict__ bucket, int* __restrict__ bucket_cnt,
+                   int bucket_cap, int slots, uint32_t* hkeys, uint32_t* hvals, int* hlist, long long n_win,
+                   int* __restrict__ overflow) {
+  __shared__ int s_n;
+  uint32_t* keys = hkeys + (size_t)blockIdx.x * slots;
+  uint32_t* hval = hvals + (size_t)blockIdx.x * slots;
+  int* list = hlist + (size_t)blockIdx.x * slots;
+  const uint32_t mask = (uint32_t)slots - 1u;
+  const int n_ent = ctx_len * k;
+  for (long long w = blockIdx.x; w < n_win; w += gridDim.x) {
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const long long t0 = w * ctx_len;
+    for (int e = threadIdx.x; e < n_ent; e += blockDim.x) {
+      const long long t = t0 + e / k;
+      if (t >= T) continue;
+      const float v = vals[t * k + (e % k)];
+      const long long f = idx[t * k + (e % k)];
+      if (!(v > threshold) || f < feat_lo || f >= feat_hi) continue;
+      if (tok_thr != nullptr && (member != nullptr ? member[t * k + (e % k)] : v) < tok_thr[t]) continue;
+      const uint32_t key = (uint32_t)(f - feat_lo);
+      if (!(v > feat_thr[key])) continue;
+      uint32_t s = (key * 2654435761u) & mask;
+      while (true) {
+        const uint32_t old = atomicCAS(&keys[s], HASH_EMPTY, key);
+        if (old == HASH_EMPTY) list[atomicAdd(&s_n, 1)] = (int)s;
+        if (old == HASH_EMPTY || old == key) {
+          atomicMax(&hval[s], __float_as_uint(v));
+          break;
+        }
+        s = (s + 1) & mask;
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    const int n = s_n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int s = list[i];
+      // the table was written by atomics (L2): read it around L1
+      const uint32_t key = *reinterpret_cast<volatile uint32_t*>(&keys[s]);
+      const uint32_t vb = *reinterpret_cast<volatile uint32_t*>(&hval[s]);
+      keys[s] = HASH_EMPTY;
+      hval[s] = 0u;
+      const int pos = atomicAdd(&bucket_cnt[key], 1);
+      if (pos < bucket_cap) bucket[(size_t)key * bucket_cap + pos] = make_uint2(vb, (uint32_t)(window_base + w));
+      else if (overflow) atomicExch(overflow, 1);
+    }
+    __threadfence();
+    __syncthreads();
+  }
+}
+
 // one warp per feature: merge bucket into the feature's sorted top-n list; order (value desc, window asc)
 __global__ void scan_merge_kernel(uint2* __restrict__ bucket, int* __restrict__ bucket_cnt, int bucket_cap, long long F,
                                   int n_top, int sort_n, float base_thr, float* __restrict__ top_vals,

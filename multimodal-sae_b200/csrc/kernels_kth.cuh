@@ -36,6 +36,61 @@ kth_gathered_reg_kernel(const float* __restrict__ g, int R, long long T, int m, 
   if (lane == 0) tok_thr[t] = __uint_as_float(prefix);
 }
 
+// Exchange 1 of the feature-sharded scan in one pass: g [R][T][2*m1] holds, per shard and token, the m1 largest lower
+// bounds followed by the m1 largest upper bounds (both descending).  One warp per token:
+//   ext_L[t] = k-th largest of the R*m1 lower bounds                      (0 if there are fewer than k)
+//   ext_U[t] = max((k+1)-th largest of the R*m1 upper bounds (0 if fewer), the smallest bound any shard sent)
+// -- what a shard did not send is no larger than the last column it did send, so ext_U bounds the token's (k+1)-th
+// largest upper bound over ALL latents from above.  Replaces two strided copies, two kth launches, an amax and a
+// maximum of saeb200.dist; needs no shared memory, so it runs beside a resident GEMM CTA.
+template <int VPL>
+__global__ void __launch_bounds__(128)
+gathered_bounds_kernel(const float* __restrict__ g, int R, long long T, int m1, int k, float* __restrict__ ext_L,
+                       float* __restrict__ ext_U) {
+  const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= T) return;
+  const int M = R * m1;
+  uint32_t keyL[VPL], keyU[VPL];
+  uint32_t tail = 0;
+#pragma unroll
+  for (int s = 0; s < VPL; ++s) {
+    const int i = s * 32 + lane;
+    uint32_t bl = 0, bu = 0;
+    if (i < M) {
+      const int r = i / m1, j = i - r * m1;
+      const float* row = g + ((long long)r * T + t) * (2 * m1);
+      const float vl = __ldg(row + j), vu = __ldg(row + m1 + j);
+      if (vl > 0.f) bl = __float_as_uint(vl);
+      if (vu > 0.f) bu = __float_as_uint(vu);
+      if (j == m1 - 1 && bu > tail) tail = bu;
+    }
+    keyL[s] = bl;
+    keyU[s] = bu;
+  }
+  tail = __reduce_max_sync(0xffffffffu, tail);
+  uint32_t pl = 0, pu = 0;
+  for (int bit = 30; bit >= 0; --bit) {
+    const uint32_t tl = pl | (1u << bit), tu = pu | (1u << bit);
+    int cl = 0, cu = 0;
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) {
+      cl += (keyL[s] >= tl) ? 1 : 0;
+      cu += (keyU[s] >= tu) ? 1 : 0;
+    }
+    // one reduction for both counters (each is at most 32 * VPL <= 2048)
+    const int both = __reduce_add_sync(0xffffffffu, cl | (cu << 16));
+    if ((both & 0xffff) >= k) pl = tl;
+    if ((both >> 16) >= k + 1) pu = tu;
+  }
+  if (k > M) pl = 0;
+  if (k + 1 > M) pu = 0;
+  if (lane == 0) {
+    ext_L[t] = __uint_as_float(pl);
+    ext_U[t] = __uint_as_float(pu > tail ? pu : tail);
+  }
+}
+
 // any R*m: the values stay in memory (L1/L2) and are re-read in every search step
 __global__ void kth_gathered_mem_kernel(const float* __restrict__ g, int R, long long T, int m, int kth,
                                         float* __restrict__ tok_thr) {

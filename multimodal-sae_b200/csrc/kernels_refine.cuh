@@ -1,6 +1,8 @@
 // Device code only (no launch syntax): included by refine.cu for the GPU build and, with SAEB_CPU_EMU defined, by the CPU
 // emulation harness under tests/emu, which runs these kernels thread by thread on the host (tests/test_kernel_emu.py).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace saeb {
@@ -403,6 +405,217 @@ refine_lo_kernel(const XT* __restrict__ x, long long ld_x, const __half* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// Warp-per-token form of the refinement for the FEATURE-SHARDED SCAN (value_mode 2 with ext_lower / ext_upper).
+//
+// A shard of an R-way sharded scan evaluates only a handful of candidates per token exactly (the few members of the
+// token's global TopK it holds that can still enter their feature's list, plus the rare boundary candidate), so a
+// 256-thread CTA per token with the activation row staged in shared memory spends its time on set-up and barriers.
+// Here one WARP owns a token: the K2 <= 128 candidates live in registers (4 per lane), bounds / classification use
+// warp collectives only, the activation row is read straight from global memory (L2) during the dot product, and the
+// kernel needs no shared memory at all -- 128-thread CTAs that are scheduled BESIDE a resident GEMM CTA, which is
+// what the pipelined scan needs (the per-chunk chain runs inside the next chunk's GEMM launches).
+// Same classification rules, same bound formula and the same summation order of the exact dot product as
+// refine_body (values are bit-identical); the k output slots of a row are filled in candidate order instead of
+// (member value, id) order -- both consumers (the member-value exchange + kth, scan_pool) are order-independent.
+// ---------------------------------------------------------------------------------------------
+constexpr int RSW_THREADS = 128;
+constexpr int RSW_SLOTS = 4;   // candidates per lane
+
+template <typename XT>
+__device__ __forceinline__ float4 rsw_load_x4(const XT* __restrict__ xr, int c) {
+#if defined(SAEB_CPU_EMU)
+  return make_float4((float)xr[4 * c], (float)xr[4 * c + 1], (float)xr[4 * c + 2], (float)xr[4 * c + 3]);
+#else
+  if constexpr (sizeof(XT) == 4) {
+    return __ldg(reinterpret_cast<const float4*>(xr) + c);
+  } else {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(xr) + c);
+    if constexpr (std::is_same<XT, __nv_bfloat16>::value) {
+      return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                         __uint_as_float(u.y & 0xffff0000u));
+    } else {
+      const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+      const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      return make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+  }
+#endif
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(RSW_THREADS)
+refine_scan_warp_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict__ W, long long d, long long N,
+                        const float* __restrict__ bias, const float* __restrict__ wnorm,
+                        const float* __restrict__ dnorm, const float* __restrict__ trailer,
+                        const float* __restrict__ xnorm, const float* __restrict__ xdnorm, float c_eps,
+                        const float* __restrict__ cand_vals, const long long* __restrict__ cand_idx, int K2, int k,
+                        long long clamp_feature, float clamp_value, float* __restrict__ out_vals,
+                        long long* __restrict__ out_idx, int* __restrict__ status, int* __restrict__ flag_rows,
+                        const float* __restrict__ ext_lower, long long T, unsigned long long* __restrict__ stats,
+                        const float* __restrict__ ext_upper, const float* __restrict__ feat_thr,
+                        float* __restrict__ out_member, int vec_ok) {
+  constexpr float MEMBER_SURE = 3.0e38f;
+  const uint32_t full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const float wmax = trailer[1], dmax = trailer[3];
+  const bool vec = vec_ok != 0;
+  const int last_lane = (K2 - 1) & 31, last_slot = (K2 - 1) >> 5;
+  for (long long t = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); t < T; t += (long long)gridDim.x * wpb) {
+    const float xn = xnorm[t], xdn = xdnorm[t];
+    const XT* xr = x + t * ld_x;
+    float a[RSW_SLOTS], lb[RSW_SLOTS], ub[RSW_SLOTS], ex[RSW_SLOTS];
+    int f[RSW_SLOTS], st[RSW_SLOTS];
+    int nv = 0;
+#pragma unroll
+    for (int s = 0; s < RSW_SLOTS; ++s) {
+      const int j = lane + 32 * s;
+      float av = 0.f;
+      int fj = 0;
+      if (j < K2) {
+        av = cand_vals[t * K2 + j];
+        fj = (int)cand_idx[t * K2 + j];
+      }
+      const bool valid = av > 0.f;
+      const float wn = wnorm[fj];
+      const float eps = (fj == clamp_feature) ? 0.f : 1.001f * (xn * dnorm[fj] + xdn * wn) + c_eps * xn * wn;
+      a[s] = av;
+      f[s] = fj;
+      lb[s] = valid ? av - eps : -INFINITY;
+      ub[s] = valid ? av + eps : -INFINITY;
+      ex[s] = -1.f;
+      nv += __popc(__ballot_sync(full, valid));
+    }
+    // L = max(k-th largest local lower bound (0 if fewer than k positive candidates), external lower bound)
+    float L = 0.f;
+    if (nv >= k) {
+      uint32_t key[RSW_SLOTS];
+#pragma unroll
+      for (int s = 0; s < RSW_SLOTS; ++s) key[s] = lb[s] > 0.f ? __float_as_uint(lb[s]) : 0u;
+      uint32_t prefix = 0;
+      for (int bit = 30; bit >= 0; --bit) {
+        const uint32_t trial = prefix | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int s = 0; s < RSW_SLOTS; ++s) c += (key[s] >= trial) ? 1 : 0;
+        c = __reduce_add_sync(full, c);
+        if (c >= k) prefix = trial;
+      }
+      L = __uint_as_float(prefix);
+    }
+    L = fmaxf(L, ext_lower[t]);
+    const float U = ext_upper[t];
+    // list possibly too short?  (same test as refine_body)
+    float a_last = 0.f;
+#pragma unroll
+    for (int s = 0; s < RSW_SLOTS; ++s) {
+      const float v = __shfl_sync(full, a[s], last_lane);
+      if (s == last_slot) a_last = v;
+    }
+    if (lane == 0 && nv == K2 && a_last + 1.001f * (xn * dmax + xdn * wmax) + c_eps * xn * wmax >= L) {
+      const int slot = atomicAdd(&status[0], 1);
+      flag_rows[slot] = (int)t;
+    }
+    // classification: 1 = certain member that cannot enter its feature's list (not gathered), 3 = certain member that
+    // can (exact value wanted), 2 = membership undecided (exact value needed), 0 = out
+#pragma unroll
+    for (int s = 0; s < RSW_SLOTS; ++s) {
+      int c = 0;
+      if (a[s] > 0.f) {
+        const float l = lb[s];
+        if (l > U && l > 0.f) {
+          c = (feat_thr == nullptr || ub[s] >= feat_thr[f[s]]) ? 3 : 1;
+          if (c == 1) ex[s] = 0.f;
+        } else if (ub[s] >= L) {
+          c = 2;
+        }
+      }
+      st[s] = c;
+    }
+    // exact re-evaluation, one candidate at a time by the whole warp (same summation order as refine_body::evaluate)
+    int n_gathered = 0;
+#pragma unroll
+    for (int s = 0; s < RSW_SLOTS; ++s) {
+      uint32_t m = __ballot_sync(full, st[s] >= 2);
+      while (m) {
+        const int src = __ffs((int)m) - 1;
+        m &= m - 1;
+        const int fj = __shfl_sync(full, f[s], src);
+        float val;
+        if (fj == clamp_feature) {
+          val = clamp_value;
+        } else {
+          const float* wr = W + (long long)fj * d;
+          float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+          if (vec) {
+            const float4* w4 = reinterpret_cast<const float4*>(wr);
+            const int n4 = (int)(d >> 2);
+            int c = lane;
+            for (; c + 7 * 32 < n4; c += 8 * 32) {
+              float4 wv[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) wv[u] = ldg_nc_f4(w4 + c + u * 32);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const float4 xv = rsw_load_x4(xr, c + u * 32);
+                acc0 = fmaf(wv[u].x, xv.x, acc0);
+                acc1 = fmaf(wv[u].y, xv.y, acc1);
+                acc2 = fmaf(wv[u].z, xv.z, acc2);
+                acc3 = fmaf(wv[u].w, xv.w, acc3);
+              }
+            }
+            for (; c < n4; c += 32) {
+              const float4 wv = ldg_nc_f4(w4 + c);
+              const float4 xv = rsw_load_x4(xr, c);
+              acc0 = fmaf(wv.x, xv.x, acc0);
+              acc1 = fmaf(wv.y, xv.y, acc1);
+              acc2 = fmaf(wv.z, xv.z, acc2);
+              acc3 = fmaf(wv.w, xv.w, acc3);
+            }
+          } else {
+            for (long long i = lane; i < d; i += 32) acc0 = fmaf(wr[i], (float)xr[i], acc0);
+          }
+          float acc = (acc0 + acc1) + (acc2 + acc3);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(full, acc, o);
+          val = acc + bias[fj];
+        }
+        if (lane == src) ex[s] = (val > 0.f) ? val : -1.f;
+        ++n_gathered;
+      }
+    }
+    // hand every certain member and every positive boundary candidate to the caller (member value: MEMBER_SURE /
+    // the exact value); rows with more potential members than output slots take the exact dense fallback
+    int nout = 0;
+#pragma unroll
+    for (int s = 0; s < RSW_SLOTS; ++s) {
+      float m = -1.f;
+      if (st[s] == 1 || st[s] == 3) m = MEMBER_SURE;
+      else if (st[s] == 2 && ex[s] > 0.f) m = ex[s];
+      const bool o = m > 0.f;
+      const uint32_t mask = __ballot_sync(full, o);
+      const int pos = nout + __popc(mask & lt_mask);
+      if (o && pos < k) {
+        out_vals[t * k + pos] = fmaxf(ex[s], 0.f);
+        out_member[t * k + pos] = m;
+        out_idx[t * k + pos] = f[s];
+      }
+      nout += __popc(mask);
+    }
+    if (nout > k && lane == 0) {
+      const int slot = atomicAdd(&status[0], 1);
+      flag_rows[slot] = (int)t;
+    }
+    for (int j = (nout < k ? nout : k) + lane; j < k; j += 32) {
+      out_vals[t * k + j] = 0.f;
+      out_member[t * k + j] = 0.f;
+      out_idx[t * k + j] = 0;
+    }
+    if (stats != nullptr && lane == 0 && n_gathered) atomicAdd(stats + 7, (unsigned long long)n_gathered);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // per-row lower bounds of the k best candidates (feature-sharded scan): lb_out[t][0..k) = the k largest values of
 // a_j - eps_j, descending, floored at 0.  All-gathered across shards, their k-th largest is a lower bound of the
 // token's global k-th activation.
@@ -451,14 +664,18 @@ template <typename XT>
 __global__ void __launch_bounds__(256)
 exact_rows_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict__ W, long long d, long long N,
                   const float* __restrict__ bias, const int* __restrict__ status, const int* __restrict__ flag_rows,
-                  long long clamp_feature, float clamp_value, float* __restrict__ dense) {
+                  long long clamp_feature, float clamp_value, float* __restrict__ dense, int stage_x) {
+  // stage_x = 0: the activation row is read from global memory instead of a shared-memory copy, so that the (normally
+  // empty) grid needs no dynamic shared memory and is scheduled beside a resident GEMM CTA (same values either way)
   extern __shared__ float xsm[];
   const int slot = blockIdx.y;
   const int nflag = min(status[0], RF_MAX_FLAG);
   if (slot >= nflag) return;
   const long long t = flag_rows[slot];
-  for (long long i = threadIdx.x; i < d; i += blockDim.x) xsm[i] = (float)x[t * ld_x + i];
-  __syncthreads();
+  if (stage_x) {
+    for (long long i = threadIdx.x; i < d; i += blockDim.x) xsm[i] = (float)x[t * ld_x + i];
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const long long per_block = (N + gridDim.x - 1) / gridDim.x;
   const long long n0 = (long long)blockIdx.x * per_block;
@@ -466,7 +683,11 @@ exact_rows_kernel(const XT* __restrict__ x, long long ld_x, const float* __restr
   for (long long n = n0 + warp; n < n1; n += nw) {
     const float* wr = W + n * d;
     float acc = 0.f;
-    for (long long i = lane; i < d; i += 32) acc = fmaf(wr[i], xsm[i], acc);
+    if (stage_x) {
+      for (long long i = lane; i < d; i += 32) acc = fmaf(wr[i], xsm[i], acc);
+    } else {
+      for (long long i = lane; i < d; i += 32) acc = fmaf(wr[i], (float)x[t * ld_x + i], acc);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
@@ -582,8 +803,8 @@ __global__ void __launch_bounds__(1024)
 overflow_rows_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict__ W, long long d, long long N,
                      const float* __restrict__ bias, const int* __restrict__ status, const int* __restrict__ flag_rows,
                      long long clamp_feature, float clamp_value, float* dense, int k, float* __restrict__ out_vals,
-                     long long* __restrict__ out_idx, float* __restrict__ out_member) {
-  extern __shared__ uint2 osm[];   // [kp2] uint2 | [d] float
+                     long long* __restrict__ out_idx, float* __restrict__ out_member, int stage_x) {
+  extern __shared__ uint2 osm[];   // [kp2] uint2 | [d] float (stage_x != 0 only, see exact_rows_kernel)
   const int nflag = status[0];
   if (nflag <= RF_MAX_FLAG) return;
   int kp2 = 2;
@@ -593,12 +814,18 @@ overflow_rows_kernel(const XT* __restrict__ x, long long ld_x, const float* __re
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int slot = RF_MAX_FLAG + blockIdx.x; slot < nflag; slot += gridDim.x) {
     const long long t = flag_rows[slot];
-    for (long long i = threadIdx.x; i < d; i += blockDim.x) xs[i] = (float)x[t * ld_x + i];
+    if (stage_x) {
+      for (long long i = threadIdx.x; i < d; i += blockDim.x) xs[i] = (float)x[t * ld_x + i];
+    }
     __syncthreads();
     for (long long n = warp; n < N; n += nw) {
       const float* wr = W + n * d;
       float acc = 0.f;
-      for (long long i = lane; i < d; i += 32) acc = fmaf(wr[i], xs[i], acc);
+      if (stage_x) {
+        for (long long i = lane; i < d; i += 32) acc = fmaf(wr[i], xs[i], acc);
+      } else {
+        for (long long i = lane; i < d; i += 32) acc = fmaf(wr[i], (float)x[t * ld_x + i], acc);
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (lane == 0) {

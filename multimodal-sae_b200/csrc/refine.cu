@@ -50,6 +50,13 @@ int set_refine_threads(int v) {
   return 0;
 }
 
+// option "scan_warp" (default 1): feature-sharded scan calls of the refinement use the warp-per-token kernel
+static thread_local int g_scan_warp = 1;
+int set_scan_warp(int v) {
+  g_scan_warp = v != 0;
+  return 0;
+}
+
 size_t refine_fallback_bytes(long long N) { return (size_t)RF_MAX_FLAG * (size_t)N * sizeof(float) + 1024; }
 
 template <typename XT>
@@ -85,7 +92,22 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
                                             status, flag_rows, ext_lower, T, stats_ptr(), value_mode, ext_upper, feat_thr,
                                             out_member);
   }
-  if (!use_lo) {
+  // feature-sharded scan calls (value_mode 2 with both external bounds): warp-per-token kernel without shared
+  // memory, and fallback grids without dynamic shared memory -- every launch of the call fits beside a resident GEMM CTA
+  const bool scan_warp = !use_lo && g_scan_warp && value_mode == 2 && ext_lower != nullptr && ext_upper != nullptr &&
+                         out_member != nullptr && K2 <= 32 * RSW_SLOTS;
+  if (scan_warp) {
+    const int vec_ok = ((d & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(x) & (4 * sizeof(XT) - 1)) == 0) && ((ld_x & 3) == 0);
+    const int wpb = RSW_THREADS / 32;
+    long long blocks = (T + wpb - 1) / wpb;
+    if (max_ctas > 0 && max_ctas < blocks) blocks = max_ctas;
+    refine_scan_warp_kernel<XT><<<(unsigned)blocks, RSW_THREADS, 0, stream>>>(
+        x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k, clamp_feature,
+        clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, T, stats_ptr(), ext_upper, feat_thr, out_member,
+        vec_ok);
+  }
+  if (!use_lo && !scan_warp) {
     const int d4 = (int)((d + 3) & ~3ll);
     const size_t smem = (size_t)(d4 + 6 * K2) * sizeof(float);
     SAEB_REQUIRE(smem <= 200 * 1024, "refine: d=%lld too large for the shared-memory row buffer", d);
@@ -99,25 +121,26 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
   SAEB_CHECK_CUDA(cudaGetLastError());
   // exact dense fallback for the (normally zero) flagged rows; the grids exit at once when nothing is flagged
   auto ek = exact_rows_kernel<XT>;
-  const size_t esmem = (size_t)d * sizeof(float);
+  const int stage_x = scan_warp ? 0 : 1;
+  const size_t esmem = stage_x ? (size_t)d * sizeof(float) : 0;
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(ek, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
-  dim3 eg(128, RF_MAX_FLAG);
+  dim3 eg(scan_warp ? 16 : 128, RF_MAX_FLAG);
   ek<<<eg, 256, esmem, stream>>>(x, ld_x, W, d, N, bias, status, flag_rows, clamp_feature, clamp_value,
-                                 dense_scratch);
+                                 dense_scratch, stage_x);
   SAEB_CHECK_CUDA(cudaGetLastError());
   int kp2 = 2;
   while (kp2 < k) kp2 <<= 1;
   // beside a resident GEMM grid only small blocks can be scheduled (registers): the fallback grids, which exit at once
   // when nothing is flagged, must never make the stream wait for a GEMM launch boundary
-  const int fb_threads = max_ctas > 0 ? 256 : 1024;
+  const int fb_threads = (max_ctas > 0 || scan_warp) ? 256 : 1024;
   dense_topk_kernel<<<RF_MAX_FLAG, fb_threads, (size_t)kp2 * sizeof(uint2), stream>>>(
       dense_scratch, N, N, k, status, RF_MAX_FLAG, flag_rows, out_vals, out_idx, out_member);
   SAEB_CHECK_CUDA(cudaGetLastError());
   auto ok = overflow_rows_kernel<XT>;
-  const size_t osmem = (size_t)kp2 * sizeof(uint2) + (size_t)d * sizeof(float);
+  const size_t osmem = (size_t)kp2 * sizeof(uint2) + (stage_x ? (size_t)d * sizeof(float) : 0);
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(ok, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osmem));
   ok<<<RF_MAX_FLAG, fb_threads, osmem, stream>>>(x, ld_x, W, d, N, bias, status, flag_rows, clamp_feature, clamp_value,
-                                           dense_scratch, k, out_vals, out_idx, out_member);
+                                           dense_scratch, k, out_vals, out_idx, out_member, stage_x);
   SAEB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

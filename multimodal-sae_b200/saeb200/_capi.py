@@ -80,6 +80,12 @@ SIGNATURES = {
     "saeb_image_pool_init": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int64, c_void_p]),
     "saeb_image_pool": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_int64, c_int64, c_int64,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "saeb_scan_pool_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "saeb_scan_pool_init": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "saeb_scan_pool_ws": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_int64, c_int64, c_int64,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t,
+                                  c_void_p]),
+    "saeb_gathered_bounds": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "saeb_kth_of_gathered": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
     "saeb_kth_largest_gathered": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "saeb_push_gather": (c_int, [c_void_p, c_size_t, c_void_p, c_int, c_int, c_size_t, c_void_p, c_size_t, c_int,

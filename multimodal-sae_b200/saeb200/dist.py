@@ -104,6 +104,13 @@ class EngineOps:
         self.exchange = os.environ.get("SAEB_SCAN_EXCHANGE", "nccl")
         self.push_widths = None   # (exchange-1 width, exchange-2 width), set by sharded_scan
         self._push = None
+        # Pipelined scans run the per-chunk chain (merge, bounds, exchange, kth, refinement, list update) INSIDE the next
+        # chunk's GEMM launches.  That only works if every kernel of the chain fits beside a resident GEMM CTA: the
+        # GEMM's shared-memory ring is one stage shorter (5 x 32 KB: ~48 KB per SM left, < 1 % slower GEMM) and the
+        # chain uses its small-footprint launch shapes (`coresident`).  A kernel that does not fit waits for the next
+        # GEMM launch boundary (~1 ms each).  SAEB_SCAN_GEMM_STAGES=0 / SAEB_SCAN_CORESIDENT=0 restore the round-1 shapes.
+        self.gemm_stages = int(os.environ.get("SAEB_SCAN_GEMM_STAGES", "5"))
+        self.coresident = os.environ.get("SAEB_SCAN_CORESIDENT", "1") != "0"
 
     def push_gather(self, t, group, channel, slot):
         """[T, m] -> [R, T, m] through the peer-memory exchange, or None when it is not selected (caller uses NCCL).
@@ -139,6 +146,9 @@ class EngineOps:
         rt = os.environ.get("SAEB_REFINE_THREADS")   # tuning knob of the co-resident refinement (see saeb200.h)
         if rt:
             self._capi.check(self._capi.lib().saeb_set_option(b"refine_threads", int(rt)), "set_option")
+        if self.coresident:
+            self._capi.check(self._capi.lib().saeb_set_option(b"gemm_stages", self.gemm_stages), "set_option")
+            self.scan.coresident = True
 
     def chunk_tokens(self, world: int, waves: Optional[int] = None) -> int:
         """Tokens per scan chunk = `waves` full single-wave GEMM launches (256-row tiles on half of the CTA pairs the
@@ -153,6 +163,9 @@ class EngineOps:
 
     def end_pipeline(self):
         self._capi.check(self._capi.lib().saeb_set_option(b"reserve_sms", 0), "set_option")
+        if self.coresident:
+            self._capi.check(self._capi.lib().saeb_set_option(b"gemm_stages", 0), "set_option")
+            self.scan.coresident = False
 
     # ---- mode 3: GEMM -> bounds -> (exchange) -> refinement restricted by the global lower bound
     def _scratch(self, store, slot, nbytes, dev):
@@ -251,6 +264,9 @@ class EngineOps:
     def kth_of_gathered(self, gathered, kth=None):
         return self.engine.kth_of_gathered(gathered, kth)
 
+    def gathered_bounds(self, gathered, m1, k):
+        return self.engine.gathered_bounds(gathered, m1, k)
+
     def scan_update(self, vals, idx, window_base, tok_thr, member=None):
         self.scan.update(vals, idx, window_base, tok_thr, None if member is vals else member)
 
@@ -338,10 +354,7 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
         if exchange:
             # one all-gather carries both bound lists: [Tc, m1] lower | [Tc, m1] upper
             g = _exchange(ops, torch.cat([_head(lb, m1), _head(ub, m1)], dim=-1), group, 0, slot)
-            ext_L = _kth(ops, g[:, :, :m1], k)
-            # upper bound of the token's (k+1)-th largest upper bound: the (k+1)-th largest of what was sent, or the
-            # smallest bound a shard sent if its list was cut off (whatever it did not send is no larger than that)
-            ext_U = torch.maximum(_kth(ops, g[:, :, m1:], k + 1), g[:, :, 2 * m1 - 1].amax(0))
+            ext_L, ext_U = _bounds_of_gathered(ops, g, m1, k)
             tm.mark("exchange1")
         args = (ext_L, ext_U, slot) if slot is not None else (ext_L, ext_U)
         vals, member, idx = ops.local_topk(*args)
@@ -406,8 +419,7 @@ def _lookahead_loop(chunks, ops, k, k_local, ctx_len, exchange, group, m1) -> No
         ext_L = ext_U = None
         if exchange:
             work.wait()
-            ext_L = _kth(ops, gathered[:, :, :m1], k)
-            ext_U = torch.maximum(_kth(ops, gathered[:, :, m1:], k + 1), gathered[:, :, 2 * m1 - 1].amax(0))
+            ext_L, ext_U = _bounds_of_gathered(ops, gathered, m1, k)
         vals, member, idx = ops.local_topk(ext_L, ext_U, slot)
         vals2, idx2 = vals.reshape(-1, k_local), idx.reshape(-1, k_local)
         mem2 = None if member is None else member.reshape(-1, k_local)
@@ -516,6 +528,18 @@ def _gather_stack(t: torch.Tensor, group, async_op: bool = False):
 def _head(lb: torch.Tensor, m: int) -> torch.Tensor:
     """first m columns of the (descending) per-token bound lists"""
     return lb if m >= lb.shape[-1] else lb[..., :m]
+
+
+def _bounds_of_gathered(ops, g: torch.Tensor, m1: int, k: int):
+    """exchange 1 -> (ext_L, ext_U): the k-th largest gathered lower bound, and an upper bound of the token's (k+1)-th
+    largest upper bound: the (k+1)-th largest of what was sent, or the smallest bound a shard sent if its list was cut
+    off (whatever it did not send is no larger than that).  One fused kernel when the ops offer it."""
+    fused = getattr(ops, "gathered_bounds", None)
+    if fused is not None:
+        return fused(g, m1, k)
+    ext_L = _kth(ops, g[:, :, :m1], k)
+    ext_U = torch.maximum(_kth(ops, g[:, :, m1:], k + 1), g[:, :, 2 * m1 - 1].amax(0))
+    return ext_L, ext_U
 
 
 def _kth(ops, gathered: torch.Tensor, k: int) -> torch.Tensor:

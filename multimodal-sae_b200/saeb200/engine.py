@@ -370,6 +370,21 @@ class TopActivationScan:
         self.bucket_cnt = torch.zeros((self.F,), dtype=torch.int32, device=dev)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
         self._pending = 0
+        # True: the pooling kernel keeps its hash tables in global scratch (saeb_scan_pool_ws: no shared memory, runs
+        # beside a resident GEMM CTA) -- set by the pipelined scans, whose list update overlaps the next chunk's GEMM
+        self.coresident = False
+        self._pool_ws, self._pool_ws_k = None, None
+
+    def _pool_workspace(self, k: int) -> torch.Tensor:
+        if self._pool_ws is None or self._pool_ws_k != k:
+            L = _capi.lib()
+            with torch.cuda.device(self.device):
+                nbytes = L.saeb_scan_pool_workspace_bytes(k, self.ctx_len)
+                self._pool_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                check(L.saeb_scan_pool_init(self._pool_ws.data_ptr(), nbytes, k, self.ctx_len, _stream()),
+                      "saeb_scan_pool_init")
+            self._pool_ws_k = k
+        return self._pool_ws
 
     def update(self, top_acts: torch.Tensor, top_indices: torch.Tensor, window_base: int,
                tok_thr: Optional[torch.Tensor] = None, member: Optional[torch.Tensor] = None) -> None:
@@ -395,12 +410,17 @@ class TopActivationScan:
                 if self._pending + n_win > self.bucket_cap:
                     self.flush()
                 v, i = vals[t0:t1], idx[t0:t1]
-                check(L.saeb_scan_pool(v.data_ptr(), i.data_ptr(), t1 - t0, k, self.ctx_len, self.threshold,
-                                       self.feat_lo, self.feat_hi, window_base + t0 // self.ctx_len,
-                                       None if tok_thr is None else tok_thr[t0:t1].data_ptr(),
-                                       None if mem is None else mem[t0:t1].data_ptr(),
-                                       self.feat_thr.data_ptr(), self.bucket.data_ptr(), self.bucket_cnt.data_ptr(),
-                                       self.bucket_cap, self.overflow.data_ptr(), _stream()), "saeb_scan_pool")
+                args = (v.data_ptr(), i.data_ptr(), t1 - t0, k, self.ctx_len, self.threshold,
+                        self.feat_lo, self.feat_hi, window_base + t0 // self.ctx_len,
+                        None if tok_thr is None else tok_thr[t0:t1].data_ptr(),
+                        None if mem is None else mem[t0:t1].data_ptr(),
+                        self.feat_thr.data_ptr(), self.bucket.data_ptr(), self.bucket_cnt.data_ptr(),
+                        self.bucket_cap, self.overflow.data_ptr())
+                if self.coresident:
+                    ws = self._pool_workspace(k)
+                    check(L.saeb_scan_pool_ws(*args, ws.data_ptr(), ws.numel(), _stream()), "saeb_scan_pool_ws")
+                else:
+                    check(L.saeb_scan_pool(*args, _stream()), "saeb_scan_pool")
                 self._pending += n_win
 
     def flush(self) -> None:
@@ -490,6 +510,23 @@ def kth_of_gathered(gathered: torch.Tensor, kth: Optional[int] = None) -> torch.
         check(L.saeb_kth_largest_gathered(g.data_ptr(), R, T, m, kth, out.data_ptr(), _stream()),
               "saeb_kth_largest_gathered")
     return out
+
+
+def gathered_bounds(gathered: torch.Tensor, m1: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """gathered [R, T, 2*m1] f32 (exchange 1 of the feature-sharded scan: per shard and token the m1 largest lower
+    bounds | the m1 largest upper bounds) -> (ext_L [T], ext_U [T]): the k-th largest lower bound and an upper bound of
+    the (k+1)-th largest upper bound over all latents (saeb_gathered_bounds)."""
+    _need_cuda(gathered)
+    L = _capi.lib()
+    R, T, w = gathered.shape
+    if w != 2 * m1 or gathered.dtype != torch.float32 or not gathered.is_contiguous():
+        raise SaebError("gathered_bounds needs a contiguous float32 [R, T, 2*m1] tensor")
+    ext_L = torch.empty((T,), dtype=torch.float32, device=gathered.device)
+    ext_U = torch.empty((T,), dtype=torch.float32, device=gathered.device)
+    with torch.cuda.device(gathered.device):
+        check(L.saeb_gathered_bounds(gathered.data_ptr(), R, T, m1, int(k), ext_L.data_ptr(), ext_U.data_ptr(),
+                                     _stream()), "saeb_gathered_bounds")
+    return ext_L, ext_U
 
 
 def mean_activations(x: torch.Tensor, enc_dense: PackedEncoder, *, chunk_tokens: int = 2048) -> torch.Tensor:

@@ -125,6 +125,16 @@ void emu_refine_bf16(const void* x, long long T, long long ld_x, const float* W,
                      const void* lo, long long ld_w, int threads, int value_mode, const float* ext_upper,
                      const float* feat_thr, float* out_member) {
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  if (threads < 0) {
+    // warp-per-token kernel of the feature-sharded scan (refine_launch_t's `scan_warp` route); fewer warps than tokens
+    emu::launch({(unsigned)((T + 7) / 8)}, {(unsigned)RSW_THREADS}, [&] {
+      refine_scan_warp_kernel<__nv_bfloat16>(xb, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps,
+                                             cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx,
+                                             status, flag_rows, ext_lower, T, nullptr, ext_upper, feat_thr, out_member,
+                                             (d & 3) == 0);
+    });
+    return;
+  }
   // fewer CTAs than tokens: the persistent token loop of the kernels is what runs beside the GEMM on the GPU
   emu::launch({(unsigned)((T + 1) / 2)}, {(unsigned)threads}, [&] {
     if (lo == nullptr)
@@ -247,18 +257,19 @@ void emu_dense_topk(const float* dense, long long T, long long ld, long long N, 
 // RF_MAX_FLAG flagged tokens + their dense TopK, then the overflow kernel for the rest
 void emu_refine_fallback(const void* x, long long ld_x, const float* W, long long d, long long N, const float* bias,
                          const int* status, const int* flag_rows, long long clamp_feature, float clamp_value,
-                         float* dense_scratch, int k, float* out_vals, long long* out_idx, int gx, int threads) {
+                         float* dense_scratch, int k, float* out_vals, long long* out_idx, int gx, int threads,
+                         int stage_x) {
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
   emu::launch({(unsigned)gx, (unsigned)RF_MAX_FLAG}, {256}, [&] {
     exact_rows_kernel<__nv_bfloat16>(xb, ld_x, W, d, N, bias, status, flag_rows, clamp_feature, clamp_value,
-                                     dense_scratch);
+                                     dense_scratch, stage_x);
   });
   emu::launch({(unsigned)RF_MAX_FLAG}, {(unsigned)threads}, [&] {
     dense_topk_kernel(dense_scratch, N, N, k, status, RF_MAX_FLAG, flag_rows, out_vals, out_idx, nullptr);
   });
   emu::launch({3}, {(unsigned)threads}, [&] {
     overflow_rows_kernel<__nv_bfloat16>(xb, ld_x, W, d, N, bias, status, flag_rows, clamp_feature, clamp_value,
-                                        dense_scratch, k, out_vals, out_idx, nullptr);
+                                        dense_scratch, k, out_vals, out_idx, nullptr, stage_x);
   });
 }
 

@@ -445,13 +445,17 @@ def test_scan_matches_oracle():
     np.testing.assert_array_equal(torch.cat([b for _, b in parts]).cpu().numpy(), ref_w)
 
 
-@pytest.mark.parametrize("scan_mode", [2, 0])
-def test_feature_sharded_scan_logical_shards(scan_mode):
+@pytest.mark.parametrize("scan_mode,route", [(2, "coresident"), (2, "cta"), (0, "cta")])
+def test_feature_sharded_scan_logical_shards(scan_mode, route):
     """The multi-GPU choreography of saeb200.dist (bounds exchange -> restricted exact refinement -> member-value
     exchange -> per-feature lists) with 4 logical shards on one device must reproduce the unsharded result exactly, in
     the refinement's scan mode (2: only members that can still enter a list are gathered) and with every member
-    re-evaluated (0)."""
-    from saeb200 import dist as sdist, engine
+    re-evaluated (0).  route "coresident": the kernels the pipelined scan uses (warp-per-token refinement, fused
+    bounds-of-gathered kernel, global-hash list update); "cta": the CTA-per-token refinement, separate kth launches
+    and the shared-memory hash."""
+    from saeb200 import _capi, dist as sdist, engine
+
+    _capi.check(_capi.lib().saeb_set_option(b"scan_warp", 1 if route == "coresident" else 0), "set_option")
 
     N, d, k, ctx, n_top, R = 2048, 256, 16, 16, 4, 4
     p = O.init_params(d, N, k, seed=51)
@@ -470,6 +474,11 @@ def test_feature_sharded_scan_logical_shards(scan_mode):
         ubs = torch.stack([ub[:, :m1] for _, ub in bounds], 0)
         ext_L = engine.kth_of_gathered(lbs, k)
         ext_U = torch.maximum(engine.kth_of_gathered(ubs, k + 1), ubs[:, :, -1].amax(0))
+        if route == "coresident":
+            for o in ops:
+                o.scan.coresident = True
+            fl, fu = engine.gathered_bounds(torch.cat([lbs, ubs], -1).contiguous(), m1, k)
+            assert torch.equal(fl, ext_L) and torch.equal(fu, ext_U)
         outs = [o.local_topk(ext_L, ext_U) for o in ops]
         n_eval += sum(int((v > 0).sum()) for v, _, _ in outs)
         tok_thr = engine.kth_of_gathered(torch.stack([m for _, m, _ in outs], 0), k)
@@ -484,6 +493,56 @@ def test_feature_sharded_scan_logical_shards(scan_mode):
     np.testing.assert_array_equal(wins, ref_w)
     # the bounds exchange is what makes sharding pay: far fewer exact evaluations than R * k per token
     assert n_eval < 0.6 * R * k * x.shape[0]
+    _capi.check(_capi.lib().saeb_set_option(b"scan_warp", 1), "set_option")
+
+
+def test_gathered_bounds_kernel():
+    """saeb_gathered_bounds = k-th largest gathered lower bound / max((k+1)-th largest upper bound, largest last
+    column), every register tier, short unions (R * m1 < k: no restriction = 0)"""
+    from saeb200 import engine
+
+    gen = torch.Generator().manual_seed(77)
+    for R, T, m1, k in ((8, 500, 24, 64), (4, 33, 8, 16), (2, 9, 3, 7), (8, 40, 64, 64), (3, 17, 200, 100), (2, 5, 40, 64)):
+        g = torch.rand(R, T, 2 * m1, generator=gen)
+        g[:, ::4, m1 // 2:m1] = 0.0            # short lists are zero padded
+        g = g.to(DEV)
+        ext_L, ext_U = engine.gathered_bounds(g, m1, k)
+        lo = g[:, :, :m1].permute(1, 0, 2).reshape(T, R * m1)
+        up = g[:, :, m1:].permute(1, 0, 2).reshape(T, R * m1)
+        want_L = lo.topk(k).values[:, -1] if k <= R * m1 else torch.zeros(T, device=DEV)
+        want_U = up.topk(k + 1).values[:, -1] if k + 1 <= R * m1 else torch.zeros(T, device=DEV)
+        want_U = torch.maximum(want_U, g[:, :, 2 * m1 - 1].amax(0))
+        assert torch.equal(ext_L, want_L) and torch.equal(ext_U, want_U), (R, T, m1, k)
+
+
+def test_scan_pool_global_hash_equals_shared_hash():
+    """saeb_scan_pool_ws (hash tables in global scratch, persistent CTAs, entries pre-filtered by the feature's n-th
+    best) appends exactly what saeb_scan_pool does: identical lists after every chunk, with and without the per-token
+    membership threshold"""
+    from saeb200.engine import TopActivationScan
+
+    p = O.init_params(64, 1024, 8, seed=21)
+    x = torch.randn(64 * 60, 64, generator=torch.Generator().manual_seed(29)).to(torch.bfloat16)
+    enc = _sae_from_params(p).encode(x.to(DEV))
+    ctx, n_top = 16, 5
+    tok_thr = enc.top_acts[:, 5].contiguous()       # drops the three weakest latents of every token
+    for thr in (None, tok_thr):
+        a = TopActivationScan(100, 900, n_top, ctx, DEV, bucket_cap=32)
+        b = TopActivationScan(100, 900, n_top, ctx, DEV, bucket_cap=32)
+        b.coresident = True
+        step = ctx * 24
+        for t0 in range(0, x.shape[0], step):
+            for sc in (a, b):
+                sc.update(enc.top_acts[t0:t0 + step], enc.top_indices[t0:t0 + step], t0 // ctx,
+                          None if thr is None else thr[t0:t0 + step])
+                sc.flush()
+            assert torch.equal(a.top_vals, b.top_vals) and torch.equal(a.top_win, b.top_win)
+        sa_, sb_ = a.finalize(), b.finalize()
+        assert torch.equal(sa_[0], sb_[0]) and torch.equal(sa_[1], sb_[1])
+        if thr is None:
+            ref_s, ref_w = O.scan_top_windows(enc.top_acts.cpu(), enc.top_indices.cpu(), 1024, ctx, n_top)
+            np.testing.assert_array_equal(sb_[0].cpu().numpy(), ref_s[100:900])
+            np.testing.assert_array_equal(sb_[1].cpu().numpy(), ref_w[100:900])
 
 
 def test_kth_of_gathered():

@@ -573,7 +573,8 @@ def test_dense_topk_kernel(emu):
     assert np.array_equal(out_v, want_v) and np.array_equal(out_i, want_i)
 
 
-def test_refine_fallback_kernels(emu):
+@pytest.mark.parametrize("stage_x", [1, 0])
+def test_refine_fallback_kernels(emu, stage_x):
     """exact_rows_kernel + dense_topk_kernel (first 64 flagged rows, redirected through the row map) and
     overflow_rows_kernel (the rest): flagged tokens come out as the exact fp32 TopK, the others are left untouched"""
     d, N, k, T = 32, 96, 8, 80
@@ -590,7 +591,7 @@ def test_refine_fallback_kernels(emu):
     xraw, Wn = _bf16_raw(x), np.ascontiguousarray(p.W_enc.numpy())
     emu.emu_refine_fallback(_p(xraw), c_longlong(d), _p(Wn), c_longlong(d),
                             c_longlong(N), _p(folded), _p(status), _p(flag_rows), c_longlong(-1), c_float(0.0),
-                            _p(dense), c_int(k), _p(out_v), _p(out_i), c_int(2), c_int(128))
+                            _p(dense), c_int(k), _p(out_v), _p(out_i), c_int(2), c_int(128), c_int(stage_x))
     ref = O.encode(p, x.float())
     ri, rv = O.canonical_topk(ref.top_acts, ref.top_indices)
     gi, gv = O.canonical_topk(torch.from_numpy(out_v[flagged]), torch.from_numpy(out_i[flagged]))
@@ -750,11 +751,13 @@ def test_refinement_scan_mode_unsharded(emu):
     assert np.array_equal(v3, v0) and np.array_equal(i3, i0)
 
 
-def test_refinement_scan_mode_two_shards(emu):
+@pytest.mark.parametrize("threads", [128, -1])
+def test_refinement_scan_mode_two_shards(emu, threads):
     """value_mode 2 under feature sharding (2 logical shards): bounds lists (lower AND upper) -> global L and U ->
     per-shard refinement that writes member values -> k-th largest member value = membership threshold.  The entries
     that pass it are exactly the oracle's global TopK, every value exact; with per-feature thresholds only the wanted
-    members are gathered."""
+    members are gathered.  threads = -1: the warp-per-token kernel (refine_scan_warp_kernel) the launcher uses for
+    these calls -- same entries with bit-identical values as the CTA-per-token kernel, in candidate order."""
     d, N, k, margin, R = 64, 512, 12, 12, 2
     T = 24
     p = O.init_params(d, N, k, seed=181)
@@ -789,8 +792,16 @@ def test_refinement_scan_mode_two_shards(emu):
             thr = (np.where(np.arange(F) % 2 == 0, np.float32(1e-5), np.float32(1e30)).astype(np.float32)
                    if feat_thr_on else None)
             v, i, flagged, mem = _run_refine(emu, sh, k, lo=False, ext_lower=ext_L, ext_upper=ext_U, value_mode=2,
-                                             threads=128, c_eps=c_eps, feat_thr=thr, want_member=True)
+                                             threads=threads, c_eps=c_eps, feat_thr=thr, want_member=True)
             assert flagged == 0
+            if threads < 0:   # the same (id, value, member value) entries as the CTA-per-token kernel, row by row
+                v_c, i_c, _, m_c = _run_refine(emu, sh, k, lo=False, ext_lower=ext_L, ext_upper=ext_U, value_mode=2,
+                                               threads=128, c_eps=c_eps, feat_thr=thr, want_member=True)
+                for r in range(T):
+                    a_ = sorted((int(ii), float(vv), float(mm)) for vv, ii, mm in zip(v[r], i[r], mem[r]) if mm > 0)
+                    b_ = sorted((int(ii), float(vv), float(mm)) for vv, ii, mm in zip(v_c[r], i_c[r], m_c[r]) if mm > 0)
+                    assert a_ == b_, r
+                    assert ((v[r] == 0) & (i[r] == 0))[mem[r] == 0].all()
             assert ((mem == 0) | (mem >= 3e38) | (mem == v)).all()          # padding | certain | undecided (exact)
             outs.append((v, i + sh["lo"], mem))
             n_gathered += int((v > 0).sum())

@@ -68,6 +68,11 @@ def main():
     ap.add_argument("--prio", default="high", help="comma list of aux-stream priorities: high,low")
     ap.add_argument("--timeline-chunks", type=int, default=2)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--skip", default="", help="semicolon list of configurations, each a comma list of chain steps that "
+                    "are NOT launched (their recorded outputs are used instead): bounds,gbounds,topk,kth,update,exchange; "
+                    "'all' = GEMM stream only.  Marginal cost of each step on the GEMM")
+    ap.add_argument("--coresident", type=int, default=1, help="0: round-1 launch shapes of the chain")
+    ap.add_argument("--scan-warp", type=int, default=1, help="0: CTA-per-token refinement")
     args = ap.parse_args()
 
     import torch
@@ -95,7 +100,7 @@ def main():
     m1 = min(k_local, max(m1, -(-(K + 1) // R)))
 
     # ---- phase A: lockstep protocol over all logical shards, exchanges recorded
-    G1, G2 = [], []
+    G1, G2, REC = [], [], []
     for c in range(args.chunks):
         xc = xs[c * chunk:(c + 1) * chunk]
         bounds = [o.local_bounds(xc, k_local) for o in ops_all]
@@ -109,6 +114,8 @@ def main():
             o.scan_update(v, i, c * chunk // CTX, tok_thr, m)
         G1.append(g1)
         G2.append(g2)
+        REC.append(dict(ext=(ext_L.clone(), ext_U.clone()), topk=tuple(t_.clone() for t_ in outs[r]),
+                        tok_thr=tok_thr.clone()))
     ref_vals, ref_win = ops_all[r].scan_finalize()
     ref_vals, ref_win = ref_vals.clone(), ref_win.clone()
     del ops_all
@@ -126,9 +133,41 @@ def main():
             c = self.count[channel]
             self.count[channel] += 1
             g = (G1, G2)[channel][c]
-            with self.span(f"exchange{channel + 1}", c):
-                g[r].copy_(t)   # the live slab: keeps the data dependency of the real exchange
+            if "exchange" not in self.skip:
+                with self.span(f"exchange{channel + 1}", c):
+                    g[r].copy_(t)   # the live slab: keeps the data dependency of the real exchange
             return g
+
+        skip = frozenset()
+
+        def local_bounds_finish(self, slot=0, coresident=False):
+            if "bounds" in self.skip:   # views of the slot's (stale) bound lists: right shapes, nothing launched
+                T = self._x[slot].shape[0]
+                k = self._k[slot]
+                lb = self._scratch(self._lb, slot, T * k * 4, dev)[: T * k * 4].view(torch.float32).view(T, k)
+                ub = self._scratch(self._ub, slot, T * k * 4, dev)[: T * k * 4].view(torch.float32).view(T, k)
+                return lb, ub
+            return super().local_bounds_finish(slot, coresident)
+
+        def gathered_bounds(self, gathered, m1, k):
+            if "gbounds" in self.skip:
+                return REC[self.count[0] - 1]["ext"]
+            return super().gathered_bounds(gathered, m1, k)
+
+        def local_topk(self, ext_L=None, ext_U=None, slot=0):
+            if "topk" in self.skip:
+                return REC[self.count[0] - 1]["topk"]
+            return super().local_topk(ext_L, ext_U, slot)
+
+        def kth_of_gathered(self, gathered, kth=None):
+            if "kth" in self.skip:
+                return REC[self.count[1] - 1]["tok_thr"]
+            return super().kth_of_gathered(gathered, kth)
+
+        def scan_update(self, vals, idx, window_base, tok_thr, member=None):
+            if "update" in self.skip:
+                return
+            return super().scan_update(vals, idx, window_base, tok_thr, member)
 
         def span(self, name, c=None):
             ops = self
@@ -162,14 +201,19 @@ def main():
     fake = FakeDist(R, r)
     real_dist = sdist.dist
     results = []
-    for stages in [int(s) for s in args.stages.split(",")]:
+    ALL = "bounds,gbounds,topk,kth,update,exchange"
+    for skip in [frozenset((ALL if sk == "all" else sk).split(",")) - {""} for sk in args.skip.split(";")]:
+      for stages in [int(s) for s in args.stages.split(",")]:
         for ctas in [int(s) for s in args.refine_ctas.split(",")]:
             for prio in args.prio.split(","):
-                _capi.check(L.saeb_set_option(b"gemm_stages", stages), "gemm_stages")
                 lo, hi = shards[r]
                 ops = ReplayOps(sae.encoder.weight.data[lo:hi], sae.encoder.bias.data[lo:hi], sae.b_dec.data, lo, hi,
                                 args.top, CTX, dev, aux_priority=prio)
                 ops.refine_max_ctas = ctas * num_sms
+                ops.skip = skip
+                ops.gemm_stages = stages
+                ops.coresident = args.coresident != 0
+                _capi.check(L.saeb_set_option(b"scan_warp", args.scan_warp), "scan_warp")
                 sdist.dist = fake
                 try:
                     sdist.sharded_scan(chunks_iter(min(3, args.chunks)), ops, K, CTX, N)   # warm-up
@@ -177,7 +221,8 @@ def main():
                     ops.count = [0, 0]
                     ops.timeline = []
                     # kth_of_gathered is called 3x per chunk (ext_L, ext_U, tok_thr): one counter covers them
-                    for name in ("local_gemm", "local_bounds_finish", "local_topk", "scan_update", "kth_of_gathered"):
+                    for name in ("local_gemm", "local_bounds_finish", "local_topk", "scan_update", "kth_of_gathered",
+                                 "gathered_bounds"):
                         wrap(ops, name)
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     torch.cuda.synchronize()
@@ -189,6 +234,8 @@ def main():
                     sdist.dist = real_dist
                 ms = e0.elapsed_time(e1)
                 same = bool(torch.equal(res.top_win[lo:hi], ref_win) and torch.equal(res.top_vals[lo:hi], ref_vals))
+                if skip:
+                    same = None
                 # seconds per op class, and the timeline of the middle chunks (ms since the start of the timed run)
                 per = {}
                 for name, c, a, b in ops.timeline:
@@ -196,11 +243,11 @@ def main():
                 mid = args.chunks // 2
                 tl = [(name, c, round(e0.elapsed_time(a), 3), round(e0.elapsed_time(b), 3))
                       for name, c, a, b in ops.timeline
-                      if (name == "kth_of_gathered" and mid * 3 <= c < (mid + args.timeline_chunks) * 3)
-                      or (name != "kth_of_gathered" and c is not None and mid <= c < mid + args.timeline_chunks)]
+                      if c is not None and mid <= c < mid + args.timeline_chunks]
                 tl.sort(key=lambda t: t[2])
-                out = {"tag": args.tag, "world": R, "rank": r, "chunks": args.chunks, "chunk_tokens": chunk,
+                out = {"tag": args.tag, "skipped": sorted(skip), "world": R, "rank": r, "chunks": args.chunks, "chunk_tokens": chunk,
                        "gemm_stages": stages, "refine_ctas_per_sm": ctas, "aux_priority": prio,
+                       "coresident": args.coresident, "scan_warp": args.scan_warp,
                        "ms": round(ms, 2), "ms_per_chunk": round(ms / args.chunks, 3),
                        "ms_per_1M_tokens": round(ms / tokens * 1048576, 1),
                        "lists_equal_lockstep": same, "flagged_rows": int(ops.status.item()),
@@ -210,7 +257,7 @@ def main():
                 results.append(out)
                 del ops
                 torch.cuda.empty_cache()
-    _capi.check(L.saeb_set_option(b"gemm_stages", 0), "gemm_stages")
+    _capi.check(L.saeb_set_option(b"scan_warp", 1), "scan_warp")
 
 
 if __name__ == "__main__":

@@ -77,6 +77,8 @@ def main():
                               args.top, ctx, dev, aux_priority=prio, planes=planes)
         ops.exchange = exch if world > 1 else "nccl"
         ops.refine_max_ctas = ctas * num_sms
+        if stages:
+            ops.gemm_stages = stages
         chunk = ops.chunk_tokens(world, waves)
 
         def chunks(limit=args.tokens):
