@@ -180,6 +180,18 @@ int saeb_candidate_bounds(const void* prep, int64_t T_total, int64_t t0, int64_t
                           int64_t d, int64_t N, int k, int margin, int64_t clamp_feature, float* lb_out, float* ub_out,
                           void* workspace, size_t workspace_bytes, int coresident, void* stream);
 
+/* saeb_candidate_bounds as ONE register-resident kernel for the pipelined feature-sharded scan: selects the row's K2
+ * best candidates and writes bounds_out [Tc, 2*m1] = the m1 largest lower bounds | the m1 largest upper bounds of the
+ * row (zero padded, NOT sorted -- saeb_gathered_bounds does not need an order), the payload of exchange 1.  The merged
+ * candidates are left in the workspace UNSORTED: pass already_merged = 2 to saeb_refine_candidates, which then
+ * insists on the feature-sharded scan form (value_mode 2, ext_lower, ext_upper, out_member) whose warp-per-token
+ * kernel is order independent.  No passes over shared memory, 128-thread CTAs: runs beside a resident GEMM CTA.
+ * Returns 1 (nothing launched, no error) when the shape does not fit the kernel's registers (more than 512 list
+ * entries per row, or K2 > 128): use saeb_candidate_bounds then. */
+int saeb_candidate_bounds_packed(const void* prep, int64_t T_total, int64_t t0, int64_t Tc, const void* packed,
+                                 int x_dtype, int64_t d, int64_t N, int k, int margin, int64_t clamp_feature, int m1,
+                                 float* bounds_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* TopK of dense non-negative rows, (value desc, index asc): Sae.select_topk (sae/sae.py:179-181) for callers that hold
  * a dense [T, ld] latent tensor. */
 int saeb_dense_topk(const float* dense, int64_t T, int64_t ld, int64_t N, int k, float* out_vals, int64_t* out_idx,
@@ -314,8 +326,9 @@ int saeb_kth_of_gathered(const float* gathered, int R, int64_t T, int k, float* 
  * lower bounds followed by the m1 largest upper bounds of saeb_candidate_bounds (both descending).  Writes
  *   ext_lower[t] = k-th largest of the R*m1 lower bounds (0 if R*m1 < k)             -> `ext_lower` of the refinement
  *   ext_upper[t] = max((k+1)-th largest of the R*m1 upper bounds (0 if R*m1 < k+1),
- *                      the largest LAST column any shard sent)                       -> `ext_upper` (value_mode 2)
- * (whatever a shard did not send is no larger than the last bound it sent).  R*m1 <= 2048. */
+ *                      max over shards of the SMALLEST upper bound the shard sent)   -> `ext_upper` (value_mode 2)
+ * (whatever a shard did not send is no larger than the smallest bound it sent; a shard's lists need not be sorted).
+ * R*m1 <= 2048. */
 int saeb_gathered_bounds(const float* gathered, int R, int64_t T, int m1, int k, float* ext_lower, float* ext_upper,
                          void* stream);
 

@@ -111,7 +111,12 @@ int image_pool_launch(const float* vals, const long long* idx, long long n_image
                       const float* tok_thr, const float* feat_thr, void* bucket, int* bucket_cnt, int bucket_cap,
                       int* overflow, void* ws, size_t ws_bytes, cudaStream_t stream);
 int set_refine_threads(int v);
+int encode_select_bounds_launch(long long T, long long N, int K2, int m1, const float* wnorm, const float* dnorm,
+                                const float* xnorm, const float* xdnorm, float c_eps, long long clamp_feature,
+                                float* out_vals, long long* out_idx, float* exch, void* workspace,
+                                size_t workspace_bytes, cudaStream_t stream);
 int set_scan_warp(int v);
+int scan_warp_enabled();
 int decode_bwd_acts_launch(const float* grad_out, long long ld_g, const long long* idx, long long T, int k,
                            const float* W_dec, long long d, long long N, float* d_vals, int* err_flag,
                            cudaStream_t stream);
@@ -448,6 +453,35 @@ int saeb_candidate_bounds(const void* prep, int64_t T_total, int64_t t0, int64_t
   return rc;
 }
 
+// feature-sharded scan, step 1 as ONE kernel (see include/saeb200.h)
+int saeb_candidate_bounds_packed(const void* prep, int64_t T_total, int64_t t0, int64_t Tc, const void* packed,
+                                 int x_dtype, int64_t d, int64_t N, int k, int margin, int64_t clamp_feature, int m1,
+                                 float* bounds_out, void* workspace, size_t workspace_bytes, void* stream) {
+  g_err[0] = 0;
+  SAEB_NVTX("saeb:select+bounds");
+  SAEB_REQUIRE(prep && packed && bounds_out && workspace, "candidate_bounds_packed: null pointer");
+  SAEB_REQUIRE(t0 >= 0 && Tc >= 0 && t0 + Tc <= T_total, "candidate_bounds_packed: bad row range");
+  if (Tc == 0) return 0;
+  const int K2raw = refine_k2(k, margin);
+  const int K2 = K2raw < N ? K2raw : (int)N;
+  SAEB_REQUIRE(m1 >= 1 && m1 <= (k < K2 ? k : K2), "candidate_bounds_packed: need 1 <= m1 <= k");
+  const RefineWs w = refine_ws(Tc, d, N, k, margin);
+  SAEB_REQUIRE(workspace_bytes >= w.total, "candidate_bounds_packed: workspace too small");
+  const PrepLayout p = prep_layout(T_total, d);
+  const uint8_t* pb = reinterpret_cast<const uint8_t*>(prep);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
+  const float* wnorm = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + bias_bytes(N));
+  const float* dnorm = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + 2 * bias_bytes(N));
+  int rc = encode_select_bounds_launch(Tc, N, K2, m1, wnorm, dnorm, reinterpret_cast<const float*>(pb + p.xnorm) + t0,
+                                       reinterpret_cast<const float*>(pb + p.xdnorm) + t0, refine_c_eps(x_dtype),
+                                       clamp_feature, reinterpret_cast<float*>(ws + w.mvals),
+                                       reinterpret_cast<long long*>(ws + w.midx), bounds_out, ws + w.enc,
+                                       w.total - w.enc, (cudaStream_t)stream);
+  if (rc == 0) g_launches += 1;
+  return rc;
+}
+
 static int refine_candidates_impl(bool lo, const void* x, int x_dtype, int64_t ld_x, const void* prep, int64_t T_total,
                                   int64_t t0, int64_t Tc, const void* packed, const float* W_enc, int64_t d, int64_t N,
                                   int k, int margin, int64_t clamp_feature, float clamp_value, const float* ext_lower,
@@ -462,9 +496,15 @@ static int refine_candidates_impl(bool lo, const void* x, int x_dtype, int64_t l
   SAEB_REQUIRE(ext_upper == nullptr || (value_mode == 2 && ext_lower != nullptr && out_member != nullptr),
                "refine_candidates: ext_upper needs value_mode 2, ext_lower and out_member");
   SAEB_REQUIRE(t0 >= 0 && Tc >= 0 && t0 + Tc <= T_total, "refine_candidates: bad row range");
+  SAEB_REQUIRE(already_merged >= 0 && already_merged <= 2, "refine_candidates: already_merged must be 0, 1 or 2");
   if (Tc == 0) return 0;
   const int K2raw = refine_k2(k, margin);
   const int K2 = K2raw < N ? K2raw : (int)N;
+  // candidates left UNSORTED by saeb_candidate_bounds_packed: only the warp-per-token scan kernel may read them
+  SAEB_REQUIRE(already_merged != 2 || (!lo && value_mode == 2 && ext_lower && ext_upper && out_member && K2 <= 128 &&
+                                       scan_warp_enabled()),
+               "refine_candidates: already_merged = 2 needs the feature-sharded scan form (value_mode 2, ext_lower, "
+               "ext_upper, out_member) with option scan_warp = 1");
   const RefineWs w = refine_ws(Tc, d, N, k, margin);
   SAEB_REQUIRE(workspace_bytes >= w.total, "refine_candidates: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;

@@ -37,6 +37,16 @@ void set_error(const char* fmt, ...);
     }                                  \
   } while (0)
 
+// An SM's L1 / shared-memory split can only change while the SM is EMPTY.  The fused GEMM CTA needs ~180-211 KB; if the
+// driver sizes the split for it alone (196 KB for the 5-stage ring) a small kernel of another stream finds 16 KB left
+// instead of 48 KB, and a small CTA that lands on an empty SM first (at a GEMM launch boundary) sets a small split
+// that keeps the GEMM CTA out until it has left.  Every kernel that may run while a GEMM launch is in flight therefore
+// asks for the largest carve-out (measured: scan_merge_kernel, 17 KB, waited ~1 ms for a launch boundary per call
+// before this; profiles/r02m_scan_rank_emul_fine_timeline.log).
+#define SAEB_CARVEOUT(kernel)                                                                                     \
+  cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributePreferredSharedMemoryCarveout,    \
+                       (int)cudaSharedmemCarveoutMaxShared)
+
 // dtype codes of the C ABI (include/saeb200.h)
 enum : int { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
 

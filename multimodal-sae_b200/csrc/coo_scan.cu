@@ -80,13 +80,13 @@ int kth_gathered_launch(const float* gathered, int R, long long T, int m, int kt
   const unsigned blocks = (unsigned)((T + wpb - 1) / wpb);
   const int M = R * m;
   if (g_kth_impl == 1 && M <= 128)
-    kth_gathered_reg_kernel<4><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m, kth, tok_thr);
+    SAEB_CARVEOUT(kth_gathered_reg_kernel<4>), kth_gathered_reg_kernel<4><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m, kth, tok_thr);
   else if (g_kth_impl == 1 && M <= 512)
-    kth_gathered_reg_kernel<16><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m, kth, tok_thr);
+    SAEB_CARVEOUT(kth_gathered_reg_kernel<16>), kth_gathered_reg_kernel<16><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m, kth, tok_thr);
   else if (g_kth_impl == 1 && M <= 2048)
-    kth_gathered_reg_kernel<64><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m, kth, tok_thr);
+    SAEB_CARVEOUT(kth_gathered_reg_kernel<64>), kth_gathered_reg_kernel<64><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m, kth, tok_thr);
   else
-    kth_gathered_mem_kernel<<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m, kth, tok_thr);
+    SAEB_CARVEOUT(kth_gathered_mem_kernel), kth_gathered_mem_kernel<<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m, kth, tok_thr);
   SAEB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -99,13 +99,13 @@ int gathered_bounds_launch(const float* gathered, int R, long long T, int m1, in
   const int wpb = 4;
   const unsigned blocks = (unsigned)((T + wpb - 1) / wpb);
   if (M <= 128)
-    gathered_bounds_kernel<4><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m1, k, ext_L, ext_U);
+    SAEB_CARVEOUT(gathered_bounds_kernel<4>), gathered_bounds_kernel<4><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m1, k, ext_L, ext_U);
   else if (M <= 256)
-    gathered_bounds_kernel<8><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m1, k, ext_L, ext_U);
+    SAEB_CARVEOUT(gathered_bounds_kernel<8>), gathered_bounds_kernel<8><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m1, k, ext_L, ext_U);
   else if (M <= 512)
-    gathered_bounds_kernel<16><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m1, k, ext_L, ext_U);
+    SAEB_CARVEOUT(gathered_bounds_kernel<16>), gathered_bounds_kernel<16><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m1, k, ext_L, ext_U);
   else
-    gathered_bounds_kernel<64><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m1, k, ext_L, ext_U);
+    SAEB_CARVEOUT(gathered_bounds_kernel<64>), gathered_bounds_kernel<64><<<blocks, wpb * 32, 0, stream>>>(gathered, R, T, m1, k, ext_L, ext_U);
   SAEB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -127,6 +127,7 @@ int scan_pool_launch(const float* vals, const long long* idx, long long T, int k
   SAEB_REQUIRE(slots <= 16384 * 1, "scan_pool: ctx_len*k=%lld too large for the shared-memory hash (max 8192)", ent);
   const size_t smem = (size_t)slots * 8;
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(scan_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SAEB_CARVEOUT(scan_pool_kernel);
   scan_pool_kernel<<<(unsigned)n_win, 256, smem, stream>>>(vals, idx, T, k, ctx_len, threshold, feat_lo, feat_hi,
                                                           window_base, tok_thr, member, feat_thr,
                                                           reinterpret_cast<uint2*>(bucket), bucket_cnt, bucket_cap,
@@ -179,6 +180,7 @@ int scan_pool_ws_launch(const float* vals, const long long* idx, long long T, in
   SAEB_REQUIRE(ws != nullptr && ws_bytes >= p.total, "scan_pool: workspace too small");
   uint8_t* b = reinterpret_cast<uint8_t*>(ws);
   const int grid = n_win < p.grid ? (int)n_win : p.grid;
+  SAEB_CARVEOUT(scan_pool_g_kernel);
   scan_pool_g_kernel<<<grid, 128, 0, stream>>>(vals, idx, T, k, ctx_len, threshold, feat_lo, feat_hi, window_base,
                                                tok_thr, member, feat_thr, reinterpret_cast<uint2*>(bucket), bucket_cnt,
                                                bucket_cap, p.slots, reinterpret_cast<uint32_t*>(b + p.keys_off),
@@ -198,6 +200,7 @@ int scan_merge_launch(void* bucket, int* bucket_cnt, int bucket_cap, long long F
   const size_t smem = (size_t)wpb * sort_n * sizeof(uint2);
   SAEB_REQUIRE(smem <= 200 * 1024, "scan_merge: n_top + bucket_cap too large");
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(scan_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SAEB_CARVEOUT(scan_merge_kernel);
   scan_merge_kernel<<<(unsigned)((F + wpb - 1) / wpb), wpb * 32, smem, stream>>>(
       reinterpret_cast<uint2*>(bucket), bucket_cnt, bucket_cap, F, n_top, sort_n, base_thr, top_vals, top_win,
       feat_thr);
@@ -253,6 +256,7 @@ int image_pool_launch(const float* vals, const long long* idx, long long n_image
   SAEB_REQUIRE(ws != nullptr && ws_bytes >= p.total, "image_pool: workspace too small");
   uint8_t* b = reinterpret_cast<uint8_t*>(ws);
   const int grid = n_images < p.grid ? (int)n_images : p.grid;
+  SAEB_CARVEOUT(image_pool_kernel);
   image_pool_kernel<<<grid, 256, 0, stream>>>(vals, idx, n_images, tokens_per_image, k, n_base, threshold, feat_lo,
                                               feat_hi, image_base, tok_thr, feat_thr,
                                               reinterpret_cast<uint32_t*>(b + p.keys_off),

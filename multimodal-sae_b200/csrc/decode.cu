@@ -26,10 +26,11 @@ static int decode_dispatch_x(const long long* idx, const float* vals, long long 
                    (b_dec == nullptr || (reinterpret_cast<uintptr_t>(b_dec) & 15) == 0);
 #define SAEB_DEC_LAUNCH(XT, XP, LDX, SQ)                                                                            \
   do {                                                                                                              \
-    if (vec)                                                                                                        \
+    if (vec) {                                                                                                      \
+      SAEB_CARVEOUT((decode_kernel<WT, OT, XT>));                                                                    \
       decode_kernel<WT, OT, XT><<<grid, block, 0, stream>>>(idx, vals, k, W, d, N, b_dec, out, ld_out, XP, LDX, SQ,  \
                                                             err_flag, T);                                           \
-    else                                                                                                            \
+    } else                                                                                                          \
       decode_scalar_kernel<WT, OT, XT><<<grid, block, 0, stream>>>(idx, vals, k, W, d, N, b_dec, out, ld_out, XP,    \
                                                                    LDX, SQ, err_flag, T);                           \
   } while (0)

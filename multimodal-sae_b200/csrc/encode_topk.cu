@@ -659,6 +659,7 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const Encode
   using Cfg = EncCfg<AP, BP, PAIR>;
   auto kern = encode_topk_kernel<AP, BP, PAIR, SLOTS, CL>;
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  SAEB_CARVEOUT(kern);
   EncodeArgs largs = args;
   largs.stages = (g_gemm_stages >= 2 && g_gemm_stages < Cfg::STAGES) ? g_gemm_stages : Cfg::STAGES;
   cudaLaunchConfig_t cfg = {};
@@ -861,9 +862,40 @@ int encode_merge_launch(long long T, long long N, int k, float* out_vals, long l
     const size_t smem = per_warp * wpb;
     SAEB_CHECK_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = (int)((c.rows + wpb - 1) / wpb);
+    SAEB_CARVEOUT(topk_merge_kernel);
     topk_merge_kernel<<<blocks, wpb * 32, smem, stream>>>(
         reinterpret_cast<const uint2*>(ws + c.cand_off), reinterpret_cast<const int*>(ws + c.cnt_off), (int)c.rows, c.S,
         plan.cap, k, kp2, (int)N, max_entries, out_vals + (size_t)c.t0 * k, out_idx + (size_t)c.t0 * k);
+    SAEB_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// Feature-sharded scan: candidate selection + bound lists in one register-resident kernel (scan_select_bounds_kernel).
+// Returns 1 (nothing launched) when the row's lists do not fit its registers (S * CAP > 512 or K2 > 128): the caller
+// then takes the two-kernel route (encode_merge_launch + candidate_bounds_launch).
+int encode_select_bounds_launch(long long T, long long N, int K2, int m1, const float* wnorm, const float* dnorm,
+                                const float* xnorm, const float* xdnorm, float c_eps, long long clamp_feature,
+                                float* out_vals, long long* out_idx, float* exch, void* workspace,
+                                size_t workspace_bytes, cudaStream_t stream) {
+  const int pair = default_pair();
+  static thread_local EncodePlan plan;
+  SAEB_REQUIRE(make_plan(plan, T, N, K2, pair), "too many row chunks");
+  SAEB_REQUIRE(workspace != nullptr && workspace_bytes >= plan.total_bytes, "select_bounds: workspace too small");
+  SAEB_REQUIRE(m1 >= 1 && m1 <= K2, "select_bounds: need 1 <= m1 <= K2");
+  if (K2 > 128) return 1;
+  for (int ci = 0; ci < plan.n_chunks; ++ci)
+    if (plan.chunks[ci].S * plan.cap > 32 * SSB_VPL) return 1;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  const int wpb = SSB_THREADS / 32;
+  for (int ci = 0; ci < plan.n_chunks; ++ci) {
+    const ChunkPlan& c = plan.chunks[ci];
+    const int blocks = (int)((c.rows + wpb - 1) / wpb);
+    SAEB_CARVEOUT(scan_select_bounds_kernel);
+    scan_select_bounds_kernel<<<blocks, SSB_THREADS, 0, stream>>>(
+        reinterpret_cast<const uint2*>(ws + c.cand_off), reinterpret_cast<const int*>(ws + c.cnt_off), (int)c.rows, c.S,
+        plan.cap, K2, m1, wnorm, dnorm, xnorm + c.t0, xdnorm + c.t0, c_eps, clamp_feature,
+        out_vals + (size_t)c.t0 * K2, out_idx + (size_t)c.t0 * K2, exch + (size_t)c.t0 * 2 * m1);
     SAEB_CHECK_CUDA(cudaGetLastError());
   }
   return 0;

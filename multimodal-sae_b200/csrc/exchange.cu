@@ -34,6 +34,7 @@ int push_gather_launch(const void* src, size_t bytes, void* const* peer_bases_de
   size_t blocks = (n_vec + PUSH_THREADS * 4 - 1) / (PUSH_THREADS * 4);
   if (blocks < 1) blocks = 1;
   if (blocks > 64) blocks = 64;
+  SAEB_CARVEOUT(push_gather_kernel);
   push_gather_kernel<<<(unsigned)blocks, PUSH_THREADS, 0, stream>>>(reinterpret_cast<const uint4*>(src), n_vec,
                                                                     peer_bases_dev, R, self_rank, slab_off, mc,
                                                                     flags_offset, channel, seq, counter);

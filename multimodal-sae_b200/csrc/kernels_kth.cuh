@@ -39,7 +39,8 @@ kth_gathered_reg_kernel(const float* __restrict__ g, int R, long long T, int m, 
 // Exchange 1 of the feature-sharded scan in one pass: g [R][T][2*m1] holds, per shard and token, the m1 largest lower
 // bounds followed by the m1 largest upper bounds (both descending).  One warp per token:
 //   ext_L[t] = k-th largest of the R*m1 lower bounds                      (0 if there are fewer than k)
-//   ext_U[t] = max((k+1)-th largest of the R*m1 upper bounds (0 if fewer), the smallest bound any shard sent)
+//   ext_U[t] = max((k+1)-th largest of the R*m1 upper bounds (0 if fewer), max over shards of the SMALLEST upper
+//              bound the shard sent)
 // -- what a shard did not send is no larger than the last column it did send, so ext_U bounds the token's (k+1)-th
 // largest upper bound over ALL latents from above.  Replaces two strided copies, two kth launches, an amax and a
 // maximum of saeb200.dist; needs no shared memory, so it runs beside a resident GEMM CTA.
@@ -63,12 +64,23 @@ gathered_bounds_kernel(const float* __restrict__ g, int R, long long T, int m1, 
       const float vl = __ldg(row + j), vu = __ldg(row + m1 + j);
       if (vl > 0.f) bl = __float_as_uint(vl);
       if (vu > 0.f) bu = __float_as_uint(vu);
-      if (j == m1 - 1 && bu > tail) tail = bu;
     }
     keyL[s] = bl;
     keyU[s] = bu;
   }
-  tail = __reduce_max_sync(0xffffffffu, tail);
+  // per shard the SMALLEST upper bound it sent (0 if its list is not full: then nothing was cut off); lists need not
+  // be sorted
+  for (int r = 0; r < R; ++r) {
+    const float* row = g + ((long long)r * T + t) * (2 * m1) + m1;
+    uint32_t mn = 0xffffffffu;
+    for (int j = lane; j < m1; j += 32) {
+      const float vu = __ldg(row + j);
+      const uint32_t b = vu > 0.f ? __float_as_uint(vu) : 0u;
+      mn = b < mn ? b : mn;
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    tail = mn > tail ? mn : tail;
+  }
   uint32_t pl = 0, pu = 0;
   for (int bit = 30; bit >= 0; --bit) {
     const uint32_t tl = pl | (1u << bit), tu = pu | (1u << bit);

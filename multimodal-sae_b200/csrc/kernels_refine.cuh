@@ -460,7 +460,6 @@ refine_scan_warp_kernel(const XT* __restrict__ x, long long ld_x, const float* _
   const uint32_t lt_mask = (1u << lane) - 1u;
   const float wmax = trailer[1], dmax = trailer[3];
   const bool vec = vec_ok != 0;
-  const int last_lane = (K2 - 1) & 31, last_slot = (K2 - 1) >> 5;
   for (long long t = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); t < T; t += (long long)gridDim.x * wpb) {
     const float xn = xnorm[t], xdn = xdnorm[t];
     const XT* xr = x + t * ld_x;
@@ -505,13 +504,14 @@ refine_scan_warp_kernel(const XT* __restrict__ x, long long ld_x, const float* _
     }
     L = fmaxf(L, ext_lower[t]);
     const float U = ext_upper[t];
-    // list possibly too short?  (same test as refine_body)
-    float a_last = 0.f;
+    // list possibly too short?  (same test as refine_body; a_last = the smallest kept approximation -- the last entry
+    // of a sorted list, but the lists of saeb_candidate_bounds_packed are not sorted)
+    float a_last = INFINITY;
 #pragma unroll
-    for (int s = 0; s < RSW_SLOTS; ++s) {
-      const float v = __shfl_sync(full, a[s], last_lane);
-      if (s == last_slot) a_last = v;
-    }
+    for (int s = 0; s < RSW_SLOTS; ++s)
+      if (lane + 32 * s < K2) a_last = fminf(a_last, a[s]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a_last = fminf(a_last, __shfl_xor_sync(full, a_last, o));
     if (lane == 0 && nv == K2 && a_last + 1.001f * (xn * dmax + xdn * wmax) + c_eps * xn * wmax >= L) {
       const int slot = atomicAdd(&status[0], 1);
       flag_rows[slot] = (int)t;

@@ -129,13 +129,13 @@ int prep_x_f16_launch(const void* x, int x_dtype, long long T, long long d, long
   const unsigned blocks = (unsigned)((T + wpb - 1) / wpb);
   __half* o = reinterpret_cast<__half*>(out);
   if (x_dtype == DT_F32)
-    prep_x_f16_kernel<float><<<blocks, wpb * 32, 0, stream>>>(reinterpret_cast<const float*>(x), T, d, ld_x, d_pad, o,
+    SAEB_CARVEOUT(prep_x_f16_kernel<float>), prep_x_f16_kernel<float><<<blocks, wpb * 32, 0, stream>>>(reinterpret_cast<const float*>(x), T, d, ld_x, d_pad, o,
                                                              row_scale, xnorm, xdnorm);
   else if (x_dtype == DT_F16)
-    prep_x_f16_kernel<__half><<<blocks, wpb * 32, 0, stream>>>(reinterpret_cast<const __half*>(x), T, d, ld_x, d_pad, o,
+    SAEB_CARVEOUT(prep_x_f16_kernel<__half>), prep_x_f16_kernel<__half><<<blocks, wpb * 32, 0, stream>>>(reinterpret_cast<const __half*>(x), T, d, ld_x, d_pad, o,
                                                               row_scale, xnorm, xdnorm);
   else if (x_dtype == DT_BF16)
-    prep_x_f16_kernel<__nv_bfloat16><<<blocks, wpb * 32, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), T, d,
+    SAEB_CARVEOUT(prep_x_f16_kernel<__nv_bfloat16>), prep_x_f16_kernel<__nv_bfloat16><<<blocks, wpb * 32, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), T, d,
                                                                      ld_x, d_pad, o, row_scale, xnorm, xdnorm);
   else {
     set_error("prep_x: unsupported dtype %d", x_dtype);

@@ -28,6 +28,7 @@ int candidate_bounds_launch(const float* cand_vals, const long long* cand_idx, l
                             const float* wnorm, const float* dnorm, const float* xnorm, const float* xdnorm,
                             float c_eps, long long clamp_feature, float* lb_out, float* ub_out, cudaStream_t stream) {
   if (T == 0) return 0;
+  SAEB_CARVEOUT(candidate_bounds_kernel);
   candidate_bounds_kernel<<<(unsigned)T, 128, (size_t)2 * K2 * sizeof(float), stream>>>(
       cand_vals, cand_idx, K2, k, wnorm, dnorm, xnorm, xdnorm, c_eps, clamp_feature, lb_out, ub_out);
   SAEB_CHECK_CUDA(cudaGetLastError());
@@ -56,6 +57,7 @@ int set_scan_warp(int v) {
   g_scan_warp = v != 0;
   return 0;
 }
+int scan_warp_enabled() { return g_scan_warp; }
 
 size_t refine_fallback_bytes(long long N) { return (size_t)RF_MAX_FLAG * (size_t)N * sizeof(float) + 1024; }
 
@@ -87,6 +89,7 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
                  "refine: residual plane must be 16-byte aligned with rows padded to a multiple of 8");
     auto kern = refine_lo_kernel<XT>;
     SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SAEB_CARVEOUT(kern);
     kern<<<grid, threads, smem, stream>>>(x, ld_x, w_lo, ld_w, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps,
                                             cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx,
                                             status, flag_rows, ext_lower, T, stats_ptr(), value_mode, ext_upper, feat_thr,
@@ -102,6 +105,7 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
     const int wpb = RSW_THREADS / 32;
     long long blocks = (T + wpb - 1) / wpb;
     if (max_ctas > 0 && max_ctas < blocks) blocks = max_ctas;
+    SAEB_CARVEOUT(refine_scan_warp_kernel<XT>);
     refine_scan_warp_kernel<XT><<<(unsigned)blocks, RSW_THREADS, 0, stream>>>(
         x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps, cand_vals, cand_idx, K2, k, clamp_feature,
         clamp_value, out_vals, out_idx, status, flag_rows, ext_lower, T, stats_ptr(), ext_upper, feat_thr, out_member,
@@ -113,6 +117,7 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
     SAEB_REQUIRE(smem <= 200 * 1024, "refine: d=%lld too large for the shared-memory row buffer", d);
     auto kern = refine_kernel<XT>;
     SAEB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SAEB_CARVEOUT(kern);
     kern<<<grid, threads, smem, stream>>>(x, ld_x, W, d, N, bias, wnorm, dnorm, trailer, xnorm, xdnorm, c_eps,
                                             cand_vals, cand_idx, K2, k, clamp_feature, clamp_value, out_vals, out_idx,
                                             status, flag_rows, ext_lower, T, stats_ptr(), value_mode, ext_upper, feat_thr,
@@ -125,6 +130,7 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
   const size_t esmem = stage_x ? (size_t)d * sizeof(float) : 0;
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(ek, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
   dim3 eg(scan_warp ? 16 : 128, RF_MAX_FLAG);
+  SAEB_CARVEOUT(ek);
   ek<<<eg, 256, esmem, stream>>>(x, ld_x, W, d, N, bias, status, flag_rows, clamp_feature, clamp_value,
                                  dense_scratch, stage_x);
   SAEB_CHECK_CUDA(cudaGetLastError());
@@ -133,12 +139,14 @@ static int refine_launch_t(const XT* x, long long T, long long ld_x, const float
   // beside a resident GEMM grid only small blocks can be scheduled (registers): the fallback grids, which exit at once
   // when nothing is flagged, must never make the stream wait for a GEMM launch boundary
   const int fb_threads = (max_ctas > 0 || scan_warp) ? 256 : 1024;
+  SAEB_CARVEOUT(dense_topk_kernel);
   dense_topk_kernel<<<RF_MAX_FLAG, fb_threads, (size_t)kp2 * sizeof(uint2), stream>>>(
       dense_scratch, N, N, k, status, RF_MAX_FLAG, flag_rows, out_vals, out_idx, out_member);
   SAEB_CHECK_CUDA(cudaGetLastError());
   auto ok = overflow_rows_kernel<XT>;
   const size_t osmem = (size_t)kp2 * sizeof(uint2) + (stage_x ? (size_t)d * sizeof(float) : 0);
   SAEB_CHECK_CUDA(cudaFuncSetAttribute(ok, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osmem));
+  SAEB_CARVEOUT(ok);
   ok<<<RF_MAX_FLAG, fb_threads, osmem, stream>>>(x, ld_x, W, d, N, bias, status, flag_rows, clamp_feature, clamp_value,
                                            dense_scratch, k, out_vals, out_idx, out_member, stage_x);
   SAEB_CHECK_CUDA(cudaGetLastError());

@@ -82,6 +82,8 @@ class EngineOps:
         self.scan = engine.TopActivationScan(feat_lo, feat_hi, n_top, ctx_len, device, bucket_cap=bucket_cap)
         self._x, self._k, self._prep, self._ws = [None, None], [0, 0], [None, None], [None, None]
         self._lb, self._ub, self._cached = [None, None], [None, None], [None, None]
+        self._merged = [1, 1]   # how the slot's candidates were merged (already_merged of saeb_refine_candidates)
+        self.packed_bounds = os.environ.get("SAEB_SCAN_PACKED_BOUNDS", "1") != "0"
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         # SAEB_SCAN_AUX_PRIORITY = high (default: exchange / refine / list update get the first pick of whatever SM
         # resources the GEMM grid leaves free) | low (GEMM CTAs are placed first at launch boundaries)
@@ -185,7 +187,7 @@ class EngineOps:
         T = x2.shape[0]
         if enc.planes < 3:
             vals, idx, _ = eng.encode_topk(x2, enc, k)
-            self._cached[slot] = (vals, idx + self.feat_lo)
+            self._cached[slot] = (vals, idx)
             return
         dev = x2.device
         with torch.cuda.device(dev):
@@ -201,17 +203,33 @@ class EngineOps:
                                                       enc.num_latents, k, 0, -1, 0.0, ws.data_ptr(), ws.numel(), st),
                              "saeb_encode_candidates")
 
-    def local_bounds_finish(self, slot=0, coresident=False):
+    def local_bounds_finish(self, slot=0, coresident=False, pack_m1=None):
         """candidate merge + per-token bound lists of the chunk given to `local_gemm` -> (lb, ub), both [Tc, k]
         descending.  Small kernels: with `coresident` they are shaped to run on another stream INSIDE the next chunk's
-        GEMM launches."""
+        GEMM launches.  `pack_m1` (sharded scans): return the payload of exchange 1 instead, ONE tensor [Tc, 2*pack_m1]
+        (the m1 largest lower | upper bounds, unsorted) from the fused register-resident kernel
+        (saeb_candidate_bounds_packed); falls back to (lb, ub) when that kernel does not take the shape."""
         eng, L = self.engine, self._capi.lib()
         enc, x2, k = self.enc, self._x[slot], self._k[slot]
+        self._merged[slot] = 1
         if enc.planes < 3:
             vals = self._cached[slot][0]
             return vals, vals
         T = x2.shape[0]
         dev = x2.device
+        if pack_m1 is not None and enc.planes == 3 and self.scan_value_mode == 2 and self.packed_bounds:
+            with torch.cuda.device(dev):
+                out = self._scratch(self._lb, slot, T * k * 4, dev)[: T * 2 * pack_m1 * 4].view(torch.float32)
+                out = out.view(T, 2 * pack_m1)
+                rc = L.saeb_candidate_bounds_packed(self._prep[slot].data_ptr(), T, 0, T, enc.blob.data_ptr(),
+                                                    eng._code(x2), enc.d_in, enc.num_latents, k, 0, -1, int(pack_m1),
+                                                    out.data_ptr(), self._ws[slot].data_ptr(), self._ws[slot].numel(),
+                                                    torch.cuda.current_stream().cuda_stream)
+            if rc == 0:
+                self._merged[slot] = 2
+                return out
+            if rc != 1:   # 1 = shape not taken by the fused kernel: two-kernel route below
+                self._capi.check(rc, "saeb_candidate_bounds_packed")
         with torch.cuda.device(dev):
             prep, ws = self._prep[slot], self._ws[slot]
             lb = self._scratch(self._lb, slot, T * k * 4, dev)[: T * k * 4].view(torch.float32).view(T, k)
@@ -228,7 +246,8 @@ class EngineOps:
         return self.local_bounds_finish(slot)
 
     def local_topk(self, ext_L=None, ext_U=None, slot=0):
-        """exact local TopK entries of the chunk given to local_bounds -> (vals, member, global ids), all [Tc, k].
+        """exact local TopK entries of the chunk given to local_bounds -> (vals, member, ids), all [Tc, k]; the ids
+        are relative to this shard's first feature (`scan_update` knows).
         Refinement in "scan" mode (value_mode 2, include/saeb200.h): only latents that can still enter their feature's
         top-n list (and every latent whose membership in the token's TopK is undecided) are gathered and re-evaluated,
         exactly.  Unsharded call (ext_L = ext_U = None): membership is decided here, `member` is None.  Sharded call:
@@ -253,13 +272,13 @@ class EngineOps:
                 enc.blob.data_ptr(), enc.W_enc.data_ptr(), enc.d_in, enc.num_latents, k, 0, -1, 0.0,
                 None if ext_L is None else ext_L.data_ptr(),
                 ext_U.data_ptr() if (sharded and mode == 2) else None,
-                self.scan.feat_thr.data_ptr() if mode == 2 else None, 1, vals.data_ptr(),
+                self.scan.feat_thr.data_ptr() if mode == 2 else None, int(self._merged[slot]), vals.data_ptr(),
                 member.data_ptr() if (sharded and mode == 2) else None, idx.data_ptr(), self.status.data_ptr(),
                 self._ws[slot].data_ptr(), self._ws[slot].numel(), int(self.refine_max_ctas), mode, st),
                 "saeb_refine_candidates")
         if sharded and mode != 2:
             member = vals
-        return vals, member, idx + self.feat_lo
+        return vals, member, idx   # shard-LOCAL ids: scan_update passes the offset on (no kernel just to add it)
 
     def kth_of_gathered(self, gathered, kth=None):
         return self.engine.kth_of_gathered(gathered, kth)
@@ -268,7 +287,7 @@ class EngineOps:
         return self.engine.gathered_bounds(gathered, m1, k)
 
     def scan_update(self, vals, idx, window_base, tok_thr, member=None):
-        self.scan.update(vals, idx, window_base, tok_thr, None if member is vals else member)
+        self.scan.update(vals, idx, window_base, tok_thr, None if member is vals else member, idx_base=self.feat_lo)
 
     def scan_finalize(self):
         return self.scan.finalize()
@@ -350,10 +369,10 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
     def finish(x, bounds, slot, window_base):
         """exchange 1 (bounds) -> restricted exact local TopK -> exchange 2 (member values) -> list update, one chunk"""
         ext_L = ext_U = tok_thr = None
-        lb, ub = bounds
         if exchange:
             # one all-gather carries both bound lists: [Tc, m1] lower | [Tc, m1] upper
-            g = _exchange(ops, torch.cat([_head(lb, m1), _head(ub, m1)], dim=-1), group, 0, slot)
+            payload = bounds if torch.is_tensor(bounds) else torch.cat([_head(bounds[0], m1), _head(bounds[1], m1)], dim=-1)
+            g = _exchange(ops, payload, group, 0, slot)
             ext_L, ext_U = _bounds_of_gathered(ops, g, m1, k)
             tm.mark("exchange1")
         args = (ext_L, ext_U, slot) if slot is not None else (ext_L, ext_U)
@@ -386,7 +405,8 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
                 _lookahead_loop(chunks, ops, k, k_local, ctx_len, exchange, group, m1)
             else:
                 _pipelined_loop(chunks, ops, finish, k_local, ctx_len, ops.stream_gemm, ops.stream_aux,
-                                torch.cuda.current_stream())
+                                torch.cuda.current_stream(),
+                                pack_m1=m1 if (exchange and 2 * m1 <= k_local) else None)
         finally:
             if end is not None:
                 end()
@@ -456,7 +476,7 @@ def _lookahead_loop(chunks, ops, k, k_local, ctx_len, exchange, group, m1) -> No
         b2(stage2)
 
 
-def _pipelined_loop(chunks, ops, finish, k_local, ctx_len, sg, sa, cur) -> int:
+def _pipelined_loop(chunks, ops, finish, k_local, ctx_len, sg, sa, cur, pack_m1=None) -> int:
     """two-stream software pipeline of sharded_scan; returns the number of windows consumed"""
     sa.wait_stream(cur)
     window_base = 0
@@ -470,7 +490,10 @@ def _pipelined_loop(chunks, ops, finish, k_local, ctx_len, sg, sa, cur) -> int:
         with torch.cuda.stream(sa):
             sa.wait_event(ready)
             if bounds is None:   # merge + bounds belong to the small-kernel chain, not to the tensor-core stream
-                bounds = ops.local_bounds_finish(slot, coresident=True)
+                if pack_m1 is not None and getattr(ops, "packed_bounds", False):
+                    bounds = ops.local_bounds_finish(slot, coresident=True, pack_m1=pack_m1)
+                else:
+                    bounds = ops.local_bounds_finish(slot, coresident=True)
             finish(x, bounds, slot, base)
             slot_free[slot] = torch.cuda.Event()
             slot_free[slot].record(sa)
@@ -538,7 +561,7 @@ def _bounds_of_gathered(ops, g: torch.Tensor, m1: int, k: int):
     if fused is not None:
         return fused(g, m1, k)
     ext_L = _kth(ops, g[:, :, :m1], k)
-    ext_U = torch.maximum(_kth(ops, g[:, :, m1:], k + 1), g[:, :, 2 * m1 - 1].amax(0))
+    ext_U = torch.maximum(_kth(ops, g[:, :, m1:], k + 1), g[:, :, m1:].amin(-1).amax(0))
     return ext_L, ext_U
 
 

@@ -387,10 +387,11 @@ class TopActivationScan:
         return self._pool_ws
 
     def update(self, top_acts: torch.Tensor, top_indices: torch.Tensor, window_base: int,
-               tok_thr: Optional[torch.Tensor] = None, member: Optional[torch.Tensor] = None) -> None:
+               tok_thr: Optional[torch.Tensor] = None, member: Optional[torch.Tensor] = None, idx_base: int = 0) -> None:
         """Feed TopK output of T tokens (T a multiple of ctx_len except for the very last chunk) whose first window
         has global id `window_base`.  tok_thr [T] / member [T, k] (optional): membership threshold per token and the
-        values it is compared with (feature-sharded scan, see saeb_scan_pool)."""
+        values it is compared with (feature-sharded scan, see saeb_scan_pool).  `idx_base`: `top_indices` are relative
+        to that feature id (a shard's refinement emits shard-local ids; no kernel just to add the offset)."""
         L = _capi.lib()
         k = top_acts.shape[-1]
         vals = top_acts.reshape(-1, k)
@@ -411,7 +412,7 @@ class TopActivationScan:
                     self.flush()
                 v, i = vals[t0:t1], idx[t0:t1]
                 args = (v.data_ptr(), i.data_ptr(), t1 - t0, k, self.ctx_len, self.threshold,
-                        self.feat_lo, self.feat_hi, window_base + t0 // self.ctx_len,
+                        self.feat_lo - int(idx_base), self.feat_hi - int(idx_base), window_base + t0 // self.ctx_len,
                         None if tok_thr is None else tok_thr[t0:t1].data_ptr(),
                         None if mem is None else mem[t0:t1].data_ptr(),
                         self.feat_thr.data_ptr(), self.bucket.data_ptr(), self.bucket_cnt.data_ptr(),

@@ -115,6 +115,22 @@ void emu_candidate_bounds(const float* cand_vals, const long long* cand_idx, lon
   });
 }
 
+// fused candidate selection + bound lists of the feature-sharded scan (encode_select_bounds_launch's geometry)
+void emu_select_bounds(const void* cand, const int* cand_cnt, int T, int S, int CAP, int K2, int m1, const float* wnorm,
+                       const float* dnorm, const float* xnorm, const float* xdnorm, float c_eps,
+                       long long clamp_feature, float* out_vals, long long* out_idx, float* exch) {
+  const int wpb = SSB_THREADS / 32;
+  emu::launch({(unsigned)((T + wpb - 1) / wpb)}, {(unsigned)SSB_THREADS}, [&] {
+    scan_select_bounds_kernel(reinterpret_cast<const uint2*>(cand), cand_cnt, T, S, CAP, K2, m1, wnorm, dnorm, xnorm,
+                              xdnorm, c_eps, clamp_feature, out_vals, out_idx, exch);
+  });
+}
+
+// saeb_gathered_bounds for R * m1 <= 256
+void emu_gathered_bounds(const float* g, int R, long long T, int m1, int k, float* ext_L, float* ext_U) {
+  emu::launch({(unsigned)((T + 3) / 4)}, {128}, [&] { gathered_bounds_kernel<8>(g, R, T, m1, k, ext_L, ext_U); });
+}
+
 // the refinement kernel on bf16 activations: lo == nullptr -> exact fp32 re-evaluation (refine_kernel), else the
 // residual-plane correction (refine_lo_kernel)
 void emu_refine_bf16(const void* x, long long T, long long ld_x, const float* W, long long d, long long N,

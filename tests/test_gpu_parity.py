@@ -479,6 +479,19 @@ def test_feature_sharded_scan_logical_shards(scan_mode, route):
                 o.scan.coresident = True
             fl, fu = engine.gathered_bounds(torch.cat([lbs, ubs], -1).contiguous(), m1, k)
             assert torch.equal(fl, ext_L) and torch.equal(fu, ext_U)
+            # the fused register-resident kernel: the same m1 bounds per row in any order; it leaves the candidates
+            # unsorted for the warp-per-token refinement (already_merged = 2)
+            packed = []
+            for o in ops:
+                o.local_gemm(xc, k)
+                pb = o.local_bounds_finish(0, True, pack_m1=m1)
+                assert torch.is_tensor(pb) and o._merged[0] == 2
+                packed.append(pb.clone())
+            pk = torch.stack(packed, 0)
+            assert torch.equal(pk[:, :, :m1].sort(-1, descending=True).values, lbs)
+            assert torch.equal(pk[:, :, m1:].sort(-1, descending=True).values, ubs)
+            fl, fu = engine.gathered_bounds(pk, m1, k)
+            assert torch.equal(fl, ext_L) and torch.equal(fu, ext_U)
         outs = [o.local_topk(ext_L, ext_U) for o in ops]
         n_eval += sum(int((v > 0).sum()) for v, _, _ in outs)
         tok_thr = engine.kth_of_gathered(torch.stack([m for _, m, _ in outs], 0), k)
@@ -511,7 +524,7 @@ def test_gathered_bounds_kernel():
         up = g[:, :, m1:].permute(1, 0, 2).reshape(T, R * m1)
         want_L = lo.topk(k).values[:, -1] if k <= R * m1 else torch.zeros(T, device=DEV)
         want_U = up.topk(k + 1).values[:, -1] if k + 1 <= R * m1 else torch.zeros(T, device=DEV)
-        want_U = torch.maximum(want_U, g[:, :, 2 * m1 - 1].amax(0))
+        want_U = torch.maximum(want_U, g[:, :, m1:].amin(-1).amax(0))   # per shard the smallest bound it sent
         assert torch.equal(ext_L, want_L) and torch.equal(ext_U, want_U), (R, T, m1, k)
 
 

@@ -410,6 +410,56 @@ def test_topk_merge_kernel(emu, T, S, CAP, k, N):
     assert np.array_equal(out_v, want_v) and np.array_equal(out_i, want_i)
 
 
+@pytest.mark.parametrize("T,S,CAP,K2,m1,N", [(9, 2, 256, 112, 24, 5000), (6, 2, 128, 20, 5, 900), (5, 1, 512, 128, 40, 4000)])
+def test_select_bounds_kernel(emu, T, S, CAP, K2, m1, N):
+    """scan_select_bounds_kernel (one register-resident kernel) = topk_merge_kernel + candidate_bounds_kernel: the same
+    K2 selected candidates (ties at the K2-th value by smallest column; any order), and as bound lists the m1 largest
+    lower / upper bounds of the row (any order, zero padded); gathered_bounds_kernel on such unsorted lists gives the
+    k-th largest lower bound and max((k+1)-th largest upper bound, per shard the smallest bound sent)"""
+    rng = np.random.default_rng(T * S + K2)
+    cand = np.zeros((T, S, CAP, 2), np.uint32)
+    cnt = np.zeros((T, S), np.int32)
+    for t in range(T):
+        for s_ in range(S):
+            n = int(rng.integers(K2 // S + 1, CAP)) if t != 1 else 3      # row 1 is short: fewer than K2 candidates
+            cols = rng.choice(np.arange(s_ * (N // S), (s_ + 1) * (N // S)), size=n, replace=False)
+            v = np.round(rng.random(n).astype(np.float32) * 8, 1 if t == 2 else 6) + np.float32(0.5)   # row 2: many ties
+            cand[t, s_, :n, 0] = v.view(np.uint32)
+            cand[t, s_, :n, 1] = cols
+            cnt[t, s_] = n
+    wnorm = (rng.random(N).astype(np.float32) + 0.5)
+    dnorm = (wnorm * rng.random(N).astype(np.float32) * 2e-3).astype(np.float32)
+    xnorm = (rng.random(T).astype(np.float32) * 3 + 1)
+    xdnorm = np.zeros(T, np.float32)
+    c_eps = np.float32(2.0 ** -9)
+    # reference route: merge (sorted) -> bounds (sorted, k = K2 columns)
+    mv, mi = np.zeros((T, K2), np.float32), np.zeros((T, K2), np.int64)
+    emu.emu_topk_merge(_p(cand), _p(cnt), c_int(T), c_int(S), c_int(CAP), c_int(K2), c_int(N), _p(mv), _p(mi))
+    lb, ub = np.zeros((T, K2), np.float32), np.zeros((T, K2), np.float32)
+    emu.emu_candidate_bounds(_p(mv), _p(mi), c_longlong(T), c_int(K2), c_int(K2), _p(wnorm), _p(dnorm), _p(xnorm),
+                             _p(xdnorm), c_float(c_eps), c_longlong(-1), _p(lb), _p(ub))
+    ov, oi = np.full((T, K2), np.nan, np.float32), np.full((T, K2), -1, np.int64)
+    exch = np.full((T, 2 * m1), np.nan, np.float32)
+    emu.emu_select_bounds(_p(cand), _p(cnt), c_int(T), c_int(S), c_int(CAP), c_int(K2), c_int(m1), _p(wnorm), _p(dnorm),
+                          _p(xnorm), _p(xdnorm), c_float(c_eps), c_longlong(-1), _p(ov), _p(oi), _p(exch))
+    for t in range(T):
+        want = sorted((float(v), int(i)) for v, i in zip(mv[t], mi[t]) if v > 0)
+        got = sorted((float(v), int(i)) for v, i in zip(ov[t], oi[t]) if v > 0)
+        assert got == want, t
+        assert (ov[t] >= 0).all() and ((oi[t] == 0) | (ov[t] > 0)).all()
+        assert sorted(exch[t, :m1].tolist(), reverse=True) == lb[t, :m1].tolist(), t
+        assert sorted(exch[t, m1:].tolist(), reverse=True) == ub[t, :m1].tolist(), t
+    # gathered_bounds on R copies-with-noise of the unsorted payload vs numpy on the sorted lists
+    R, k = 3, min(2 * m1, 3 * m1 - 1)
+    g = np.stack([exch * np.float32(1.0 + 0.01 * r) for r in range(R)], 0).astype(np.float32)
+    ext_L, ext_U = np.zeros(T, np.float32), np.zeros(T, np.float32)
+    emu.emu_gathered_bounds(_p(np.ascontiguousarray(g)), c_int(R), c_longlong(T), c_int(m1), c_int(k), _p(ext_L), _p(ext_U))
+    lo_all = np.sort(g[:, :, :m1].transpose(1, 0, 2).reshape(T, -1), 1)[:, ::-1]
+    up_all = np.sort(g[:, :, m1:].transpose(1, 0, 2).reshape(T, -1), 1)[:, ::-1]
+    assert np.array_equal(ext_L, lo_all[:, k - 1])
+    assert np.array_equal(ext_U, np.maximum(up_all[:, k], g[:, :, m1:].min(-1).max(0)))
+
+
 @pytest.mark.parametrize("tag", ["nofilter", "filter"])
 def test_coo_extract_kernels(emu, tag):
     """coo_count / scan / emit: the reference's (row, pos, feature) triples in torch.nonzero order (features/cache.py:

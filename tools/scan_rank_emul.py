@@ -68,10 +68,12 @@ def main():
     ap.add_argument("--prio", default="high", help="comma list of aux-stream priorities: high,low")
     ap.add_argument("--timeline-chunks", type=int, default=2)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--fine", type=int, default=0, help="1: also time the individual library calls of update / refinement")
     ap.add_argument("--skip", default="", help="semicolon list of configurations, each a comma list of chain steps that "
                     "are NOT launched (their recorded outputs are used instead): bounds,gbounds,topk,kth,update,exchange; "
                     "'all' = GEMM stream only.  Marginal cost of each step on the GEMM")
     ap.add_argument("--coresident", type=int, default=1, help="0: round-1 launch shapes of the chain")
+    ap.add_argument("--packed-bounds", type=int, default=1, help="0: merge + candidate_bounds + cat instead of the fused kernel")
     ap.add_argument("--scan-warp", type=int, default=1, help="0: CTA-per-token refinement")
     args = ap.parse_args()
 
@@ -106,7 +108,7 @@ def main():
         bounds = [o.local_bounds(xc, k_local) for o in ops_all]
         g1 = torch.stack([torch.cat([lb[:, :m1], ub[:, :m1]], -1) for lb, ub in bounds], 0)
         ext_L = engine.kth_of_gathered(g1[:, :, :m1], K)
-        ext_U = torch.maximum(engine.kth_of_gathered(g1[:, :, m1:], K + 1), g1[:, :, 2 * m1 - 1].amax(0))
+        ext_U = torch.maximum(engine.kth_of_gathered(g1[:, :, m1:], K + 1), g1[:, :, m1:].amin(-1).amax(0))
         outs = [o.local_topk(ext_L, ext_U) for o in ops_all]
         g2 = torch.stack([m for _, m, _ in outs], 0)
         tok_thr = engine.kth_of_gathered(g2, K)
@@ -140,14 +142,14 @@ def main():
 
         skip = frozenset()
 
-        def local_bounds_finish(self, slot=0, coresident=False):
+        def local_bounds_finish(self, slot=0, coresident=False, pack_m1=None):
             if "bounds" in self.skip:   # views of the slot's (stale) bound lists: right shapes, nothing launched
                 T = self._x[slot].shape[0]
                 k = self._k[slot]
                 lb = self._scratch(self._lb, slot, T * k * 4, dev)[: T * k * 4].view(torch.float32).view(T, k)
                 ub = self._scratch(self._ub, slot, T * k * 4, dev)[: T * k * 4].view(torch.float32).view(T, k)
                 return lb, ub
-            return super().local_bounds_finish(slot, coresident)
+            return super().local_bounds_finish(slot, coresident, pack_m1)
 
         def gathered_bounds(self, gathered, m1, k):
             if "gbounds" in self.skip:
@@ -213,6 +215,7 @@ def main():
                 ops.skip = skip
                 ops.gemm_stages = stages
                 ops.coresident = args.coresident != 0
+                ops.packed_bounds = args.packed_bounds != 0
                 _capi.check(L.saeb_set_option(b"scan_warp", args.scan_warp), "scan_warp")
                 sdist.dist = fake
                 try:
@@ -224,6 +227,21 @@ def main():
                     for name in ("local_gemm", "local_bounds_finish", "local_topk", "scan_update", "kth_of_gathered",
                                  "gathered_bounds"):
                         wrap(ops, name)
+                    if args.fine:   # spans around the individual library calls of the list update / refinement
+                        wrap(ops.scan, "flush")
+                        ops.scan.span = ops.span
+                        for fname in ("saeb_scan_pool_ws", "saeb_scan_pool", "saeb_refine_candidates"):
+                            orig = getattr(L, fname)
+
+                            def make(orig=orig, fname=fname):
+                                cnt = [0]
+
+                                def f(*a):
+                                    cnt[0] += 1
+                                    with ops.span(fname, cnt[0] - 1):
+                                        return orig(*a)
+                                return f
+                            setattr(L, fname, make())
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     torch.cuda.synchronize()
                     e0.record()
@@ -242,12 +260,15 @@ def main():
                     per[name] = per.get(name, 0.0) + a.elapsed_time(b)
                 mid = args.chunks // 2
                 tl = [(name, c, round(e0.elapsed_time(a), 3), round(e0.elapsed_time(b), 3))
-                      for name, c, a, b in ops.timeline
-                      if c is not None and mid <= c < mid + args.timeline_chunks]
+                      for name, c, a, b in ops.timeline]
                 tl.sort(key=lambda t: t[2])
+                g0 = [t for t in tl if t[0] == "local_gemm" and t[1] == mid]
+                g1 = [t for t in tl if t[0] == "local_gemm" and t[1] == mid + args.timeline_chunks]
+                if g0 and g1:
+                    tl = [t for t in tl if g0[0][2] <= t[2] < g1[0][3]]
                 out = {"tag": args.tag, "skipped": sorted(skip), "world": R, "rank": r, "chunks": args.chunks, "chunk_tokens": chunk,
                        "gemm_stages": stages, "refine_ctas_per_sm": ctas, "aux_priority": prio,
-                       "coresident": args.coresident, "scan_warp": args.scan_warp,
+                       "coresident": args.coresident, "scan_warp": args.scan_warp, "packed_bounds": args.packed_bounds,
                        "ms": round(ms, 2), "ms_per_chunk": round(ms / args.chunks, 3),
                        "ms_per_1M_tokens": round(ms / tokens * 1048576, 1),
                        "lists_equal_lockstep": same, "flagged_rows": int(ops.status.item()),
