@@ -56,6 +56,11 @@ int saeb_set_option(const char* name, int value);
 /* With option "profile" = 1 the library brackets the fused encode kernel (main kernel only) with CUDA events on the
  * launching stream; this returns the duration in ms of the most recent one (synchronises on it), < 0 if none. */
 float saeb_profile_last_encode_ms(void);
+/* Diagnostics: a synthetic load of `ctas` 128-thread CTAs without shared memory (they are scheduled beside a resident
+ * GEMM CTA), `iters` iterations per thread: mode 0 = dependent FMA chains (issue slots only), 1 = streaming 16-byte
+ * reads of buf (DRAM traffic, L2 pollution), 2 = reads confined to the first 32 MB of buf (L2 bandwidth only).
+ * tools/probe_overlap.py uses it to separate what slows a GEMM launch that shares its SMs.  sink: one device float. */
+int saeb_debug_coload(int mode, int ctas, int64_t iters, const void* buf, size_t bytes, float* sink, void* stream);
 /* Diagnostics (option "stats" = 1 zeroes and enables device cycle counters of the fused encode kernel): host array of 8
  * counters summed over CTA pairs = {producer waiting for a free smem stage, MMA issuer waiting for a free TMEM stage,
  * MMA issuer waiting for TMA data, epilogue warp waiting for an accumulator, epilogue compaction time, kernel time,

@@ -116,6 +116,7 @@ int encode_select_bounds_launch(long long T, long long N, int K2, int m1, const 
                                 float* out_vals, long long* out_idx, float* exch, void* workspace,
                                 size_t workspace_bytes, cudaStream_t stream);
 int set_scan_warp(int v);
+int coload_launch(int mode, int ctas, long long iters, const void* buf, size_t bytes, float* sink, cudaStream_t stream);
 int scan_warp_enabled();
 int decode_bwd_acts_launch(const float* grad_out, long long ld_g, const long long* idx, long long T, int k,
                            const float* W_dec, long long d, long long N, float* d_vals, int* err_flag,
@@ -733,6 +734,11 @@ int saeb_kth_largest_gathered(const float* gathered, int R, int64_t T, int m, in
   int rc = kth_gathered_launch(gathered, R, T, m, kth, tok_thr, (cudaStream_t)stream);
   if (rc == 0) g_launches += 1;
   return rc;
+}
+
+int saeb_debug_coload(int mode, int ctas, int64_t iters, const void* buf, size_t bytes, float* sink, void* stream) {
+  g_err[0] = 0;
+  return coload_launch(mode, ctas, iters, buf, bytes, sink, (cudaStream_t)stream);
 }
 
 int saeb_gathered_bounds(const float* gathered, int R, int64_t T, int m1, int k, float* ext_lower, float* ext_upper,

@@ -24,14 +24,54 @@ kth_gathered_reg_kernel(const float* __restrict__ g, int R, long long T, int m, 
     }
     key[s] = b;
   }
-  uint32_t prefix = 0;
-  for (int bit = 30; bit >= 0; --bit) {
-    const uint32_t trial = prefix | (1u << bit);
-    int c = 0;
+  // Member values of the sharded refinement (value_mode 2) are 3e38 ("certainly in the TopK") for all but a handful of
+  // entries: with c of them, the kth largest is 3e38 if c >= kth, else the (kth - c)-th largest of the rest -- a few
+  // max-extractions instead of the 31-step search.  Generic inputs (no such values) fall through to the search.
+  const uint32_t SURE = __float_as_uint(3.0e38f);
+  int c_sure = 0, n_pos = 0;
 #pragma unroll
-    for (int s = 0; s < VPL; ++s) c += (key[s] >= trial) ? 1 : 0;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (c >= kth) prefix = trial;
+  for (int s = 0; s < VPL; ++s) {
+    c_sure += (key[s] == SURE) ? 1 : 0;
+    n_pos += (key[s] != 0u) ? 1 : 0;
+  }
+  const int both = __reduce_add_sync(0xffffffffu, c_sure | (n_pos << 16));
+  c_sure = both & 0xffff;
+  n_pos = both >> 16;
+  uint32_t prefix = 0;
+  if (c_sure >= kth) {
+    prefix = SURE;
+  } else if (n_pos < kth) {
+    prefix = 0;
+  } else if (c_sure > 0 && kth - c_sure <= 8) {
+    const int r = kth - c_sure;
+    for (int it = 0; it < r; ++it) {
+      uint32_t mx = 0;
+#pragma unroll
+      for (int s = 0; s < VPL; ++s) mx = (key[s] != SURE && key[s] > mx) ? key[s] : mx;
+      const uint32_t wm = __reduce_max_sync(0xffffffffu, mx);
+      prefix = wm;
+      // drop ONE instance of the maximum (equal values count separately)
+      const uint32_t holders = __ballot_sync(0xffffffffu, mx == wm);
+      if (lane == __ffs((int)holders) - 1) {
+        bool removed = false;
+#pragma unroll
+        for (int s = 0; s < VPL; ++s) {
+          if (!removed && key[s] == wm) {
+            key[s] = 0u;
+            removed = true;
+          }
+        }
+      }
+    }
+  } else {
+    for (int bit = 30; bit >= 0; --bit) {
+      const uint32_t trial = prefix | (1u << bit);
+      int c = 0;
+#pragma unroll
+      for (int s = 0; s < VPL; ++s) c += (key[s] >= trial) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c >= kth) prefix = trial;
+    }
   }
   if (lane == 0) tok_thr[t] = __uint_as_float(prefix);
 }

@@ -485,9 +485,12 @@ refine_scan_warp_kernel(const XT* __restrict__ x, long long ld_x, const float* _
       ex[s] = -1.f;
       nv += __popc(__ballot_sync(full, valid));
     }
-    // L = max(k-th largest local lower bound (0 if fewer than k positive candidates), external lower bound)
+    // L = max(k-th largest local lower bound (0 if fewer than k positive candidates), external lower bound).  The
+    // external bound (k-th largest lower bound over ALL shards) is the tight one; the local search (31 dependent
+    // warp-wide steps) only runs where it gave nothing.  A smaller L is still a valid lower bound: at worst a few more
+    // candidates are re-evaluated exactly.
     float L = 0.f;
-    if (nv >= k) {
+    if (nv >= k && !(ext_lower[t] > 0.f)) {
       uint32_t key[RSW_SLOTS];
 #pragma unroll
       for (int s = 0; s < RSW_SLOTS; ++s) key[s] = lb[s] > 0.f ? __float_as_uint(lb[s]) : 0u;

@@ -87,6 +87,7 @@ SIGNATURES = {
     "saeb_scan_pool_ws": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_int64, c_int64, c_int64,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t,
                                   c_void_p]),
+    "saeb_debug_coload": (c_int, [c_int, c_int, c_int64, c_void_p, c_size_t, c_void_p, c_void_p]),
     "saeb_gathered_bounds": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "saeb_kth_of_gathered": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
     "saeb_kth_largest_gathered": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p]),

@@ -100,10 +100,12 @@ class EngineOps:
         # SMs the GEMM grid leaves idle while a multi-rank scan is pipelined (see begin_pipeline).  Measured at 8 GPUs
         # (1 M tokens): 0 -> 4.85 M tokens/s, 4 (with NCCL_MAX_CTAS=4) -> 4.65-4.76 M: off by default
         self.reserve_sms = 0
-        # per-chunk exchanges: "nccl" (all_gather_into_tensor) or "push" (saeb_push_gather: this library's own
-        # peer-memory all-gather, small enough to run beside the GEMM CTAs; NOT yet measured -> opt-in,
-        # SAEB_SCAN_EXCHANGE=push or bench.py --scan-exchange push)
-        self.exchange = os.environ.get("SAEB_SCAN_EXCHANGE", "nccl")
+        # per-chunk exchanges: "push" (default: saeb_push_gather, this library's own peer-memory all-gather over NVLink
+        # / NVSwitch multicast, 31 registers and no shared memory, so it runs beside the GEMM CTAs; verified bit-exact
+        # against NCCL on 2 and 8 GPUs, profiles/r02d_push_gather_n2.json, r02e_scan_sweep_n8.log; every rank falls
+        # back to NCCL together when symmetric memory cannot be set up) or "nccl" (all_gather_into_tensor, whose
+        # kernels wait for a GEMM launch boundary); SAEB_SCAN_EXCHANGE / bench.py --scan-exchange
+        self.exchange = os.environ.get("SAEB_SCAN_EXCHANGE", "push")
         self.push_widths = None   # (exchange-1 width, exchange-2 width), set by sharded_scan
         self._push = None
         # Pipelined scans run the per-chunk chain (merge, bounds, exchange, kth, refinement, list update) INSIDE the next
@@ -389,10 +391,18 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
 
     window_base = 0
     if not pipelined:
+        fused = (exchange and 2 * m1 <= k_local and getattr(ops, "packed_bounds", False)
+                 and hasattr(ops, "local_gemm") and hasattr(ops, "local_bounds_finish"))
         for x in chunks:
-            lb = ops.local_bounds(x, k_local)
-            tm.mark("gemm+bounds")
-            window_base += finish(x, lb, None, window_base)
+            if fused:   # the same kernels as the pipelined schedules, one after the other
+                ops.local_gemm(x, k_local, 0)
+                tm.mark("gemm")
+                lb = ops.local_bounds_finish(0, False, pack_m1=m1)
+                tm.mark("select+bounds")
+            else:
+                lb = ops.local_bounds(x, k_local)
+                tm.mark("gemm+bounds")
+            window_base += finish(x, lb, 0 if fused else None, window_base)
     else:
         schedule = scan_schedule(world)
         if not hasattr(ops, "stream_gemm"):

@@ -52,10 +52,14 @@ class OverlappedForward:
         L = _capi.lib()
         with torch.cuda.device(dev):
             self.num_sms = int(L.saeb_query(b"num_sms"))
-        # gather CTAs per SM while a GEMM launch is resident; 0 (default) = one CTA per token.  Measured (round 2): every
-        # kernel of the step runs at the board's power cap on its own, so the step is energy-bound and bounded grids
-        # buy nothing here (they pay off where a latency chain, not energy, is the critical path)
-        self.ctas_per_sm = _env_int("SAEB_OV_CTAS_PER_SM", 0) if ctas_per_sm is None else int(ctas_per_sm)
+        # gather CTAs per SM while a GEMM launch is resident (0 = one CTA per token) and depth of the GEMM's shared-memory
+        # ring while the forward is pipelined.  Measured (round 2, profiles/r02o_forward_overlap_boundary_mode.log, ms per
+        # 65 536-token step): sequential 72.4-79.5, unbounded grids 72.2-74.0, 2 CTAs per SM beside a 5-stage ring
+        # 70.7-71.2 (3: 70.4-72.8).  Every kernel of the step runs at the board's power cap on its own (the step is
+        # energy-bound), so the gain is small; it only exists since every kernel asks for the largest shared-memory
+        # carve-out (common.cuh, SAEB_CARVEOUT).
+        self.ctas_per_sm = _env_int("SAEB_OV_CTAS_PER_SM", 2) if ctas_per_sm is None else int(ctas_per_sm)
+        self.gemm_stages = _env_int("SAEB_OV_GEMM_STAGES", 5 if self.ctas_per_sm > 0 else 0)
         priority = os.environ.get("SAEB_OV_PRIORITY", "gemm") if priority is None else priority
         self.ws_bytes, self.ws = 0, [None] * self.N_WS
         self._reserve(chunk)
@@ -102,6 +106,8 @@ class OverlappedForward:
         prep = self.prep
         nws = self.N_WS
         with torch.cuda.device(self.dev):
+            if self.gemm_stages:
+                check(L.saeb_set_option(b"gemm_stages", self.gemm_stages), "set_option")
             for c in range(n_chunks):
                 a, b = c * self.chunk, min(T, (c + 1) * self.chunk)
                 ws = self.ws[c % nws]
@@ -138,6 +144,8 @@ class OverlappedForward:
                     ev_b[c].record(self.s_mem)
                     if done_events is not None:
                         done_events[c].record(self.s_mem)
+            if self.gemm_stages:
+                check(L.saeb_set_option(b"gemm_stages", 0), "set_option")
         main.wait_stream(self.s_mem)
         main.wait_stream(self.s_gemm)
 

@@ -69,6 +69,27 @@ def test_kth_largest_kernels(emu, vpl):
         out = np.full(T, -1.0, np.float32)
         emu.emu_kth(c_int(vpl), _p(ga), c_int(R), c_longlong(T), c_int(m), c_int(kth), _p(out))
         assert np.array_equal(out, ref), (R, T, m, kth)
+        if vpl == 0 or kth < 4:
+            continue
+        # member values of the sharded refinement: 3e38 for most entries, a few exact values (with duplicates), zeros;
+        # rows with >= kth, kth - 1 ... kth - 9 and far fewer "certain" entries exercise every branch of the fast path
+        g2 = torch.zeros(R, T, m)
+        for t in range(T):
+            flat = torch.zeros(R * m)
+            n_sure = max(0, kth - (t % 11) + 1) if t % 5 else max(0, kth // 3)
+            n_sure = min(n_sure, R * m - 3)
+            perm = torch.randperm(R * m, generator=gen)
+            flat[perm[:n_sure]] = 3.0e38
+            n_oth = min(R * m - n_sure, 3 + t % 9)
+            vals_ = torch.rand(n_oth, generator=gen) * 5 + 0.1
+            if n_oth >= 2:
+                vals_[1] = vals_[0]                       # a tie
+            flat[perm[n_sure:n_sure + n_oth]] = vals_
+            g2[:, t, :] = flat.view(R, m)
+        ref2 = g2.permute(1, 0, 2).reshape(T, R * m).topk(kth).values[:, -1].numpy()
+        out2 = np.full(T, -1.0, np.float32)
+        emu.emu_kth(c_int(vpl), _p(np.ascontiguousarray(g2.numpy())), c_int(R), c_longlong(T), c_int(m), c_int(kth), _p(out2))
+        assert np.array_equal(out2, ref2), (R, T, m, kth, "member values")
 
 
 @pytest.mark.parametrize("T,d,N,k", [(5, 64, 40, 7), (3, 50, 30, 30), (2, 260, 64, 9)])
@@ -850,7 +871,10 @@ def test_refinement_scan_mode_two_shards(emu, threads):
                 for r in range(T):
                     a_ = sorted((int(ii), float(vv), float(mm)) for vv, ii, mm in zip(v[r], i[r], mem[r]) if mm > 0)
                     b_ = sorted((int(ii), float(vv), float(mm)) for vv, ii, mm in zip(v_c[r], i_c[r], m_c[r]) if mm > 0)
-                    assert a_ == b_, r
+                    # (the warp kernel takes the external lower bound alone when there is one: it may hand out a few
+                    # more boundary candidates than the CTA kernel, never fewer entries, and the same values)
+                    assert set(b_) <= set(a_), r
+                    assert all(m_ < 3e38 for _, _, m_ in set(a_) - set(b_)), r
                     assert ((v[r] == 0) & (i[r] == 0))[mem[r] == 0].all()
             assert ((mem == 0) | (mem >= 3e38) | (mem == v)).all()          # padding | certain | undecided (exact)
             outs.append((v, i + sh["lo"], mem))

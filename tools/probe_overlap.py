@@ -49,6 +49,8 @@ def exp_forward(overlap=True, chunk=9472, ctas_per_sm=1, priority="gemm", stages
     sq = torch.zeros((), dtype=torch.float64, device="cuda")
     ov = OverlappedForward(enc, sae.W_dec.data, sae.b_dec.data, K, chunk=chunk, ctas_per_sm=ctas_per_sm,
                            priority=priority, value_mode=VALUE_MODE) if overlap else None
+    if ov is not None:
+        ov.gemm_stages = stages
 
     def step():
         sq.zero_()
@@ -286,7 +288,90 @@ def exp_shard_phases(world=8, rank=3, tokens=1048576 // 4, waves=4):
                 per_1M_tokens_ms={k_: round(v_ / (n_chunks * chunk) * 1048576, 1) for k_, v_ in acc.items()})
 
 
+def exp_coload(world=8, rank=3, n_chunks=8, waves=4):
+    """the GEMM stream of one rank of the 8-way sharded scan (prep + 4 single-wave launches per 37 888-token chunk)
+    alone and with a synthetic co-resident load on a second stream: pure ALU, streaming reads, L2-resident reads, at two
+    intensities each.  Which resource does a co-resident chain take from the GEMM?"""
+    import torch
+    from saeb200 import _capi, dist as sdist, engine, synth
+    L = _capi.lib()
+    check = _capi.check
+    sae = synth.make_sae(D, N, K, "cuda", seed=1234)
+    lo, hi = sdist.shard_range(N, world, rank)
+    enc = engine.PackedEncoder.pack(sae.encoder.weight.data[lo:hi], sae.encoder.bias.data[lo:hi], sae.b_dec.data, 3)
+    Ns = hi - lo
+    chunk = waves * 9472
+    x = synth.make_activations(chunk * n_chunks, D, "cuda", seed=5)
+    prep = [torch.empty(L.saeb_prep_bytes(chunk, D), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    ws = [torch.empty(L.saeb_candidates_workspace_bytes(chunk, D, Ns, K, 0), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    buf = torch.empty(2 << 30, dtype=torch.uint8, device="cuda")
+    sink = torch.zeros(1, dtype=torch.float32, device="cuda")
+    sg, sa = torch.cuda.Stream(priority=0), torch.cuda.Stream(priority=-1)
+    check(L.saeb_set_option(b"gemm_stages", 5), "stages")
+
+    def run(load):
+        main = torch.cuda.current_stream()
+        sg.wait_stream(main); sa.wait_stream(main)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(sg)
+        for c in range(n_chunks):
+            xc = x[c * chunk:(c + 1) * chunk]
+            st = sg.cuda_stream
+            check(L.saeb_prep_activations(xc.data_ptr(), _capi.BF16, chunk, D, D, prep[c & 1].data_ptr(), st), "prep")
+            check(L.saeb_encode_candidates(prep[c & 1].data_ptr(), chunk, 0, chunk, enc.blob.data_ptr(), D, Ns, K, 0, -1, 0.0,
+                                           ws[c & 1].data_ptr(), ws[c & 1].numel(), st), "gemm")
+        e1.record(sg)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if load is not None:
+            mode, ctas, iters, reps = load
+            a0.record(sa)
+            for _ in range(reps):
+                check(L.saeb_debug_coload(mode, ctas, iters, buf.data_ptr(), buf.numel(), sink.data_ptr(), sa.cuda_stream), "coload")
+            a1.record(sa)
+        main.wait_stream(sg); main.wait_stream(sa)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n_chunks, (a0.elapsed_time(a1) if load is not None else 0.0)
+
+    res = {}
+    run(None)
+    base = min(run(None)[0] for _ in range(3))
+    res["gemm_alone_ms_per_chunk"] = round(base, 3)
+    # (mode, ctas, iters, launches): sized so that the load lasts about as long as the GEMM stream
+    loads = {"alu_2cta": (0, 296, 400000, 40), "alu_4cta": (0, 592, 400000, 40),
+             "stream_light": (1, 296, 2000, 40), "stream_heavy": (1, 592, 6000, 40),
+             "l2_light": (2, 296, 2000, 40), "l2_heavy": (2, 592, 6000, 40)}
+    if os.environ.get("PROBE_COLOAD_SMSP"):
+        # pure ALU load from ONE warp position of every 4-warp CTA (CTA-local warp id, then hardware warp slot):
+        # the GEMM's TMA producer is CTA warp 0, its MMA issuer warp 1, the epilogue warps 4-7
+        loads = {f"alu_2cta_warp{w}": (0 | ((1 << w) << 4), 296, 400000, 40) for w in range(4)}
+        loads.update({f"alu_2cta_hwslot{w}": (0 | ((1 << w) << 4) | 256, 296, 400000, 40) for w in range(4)})
+        loads["alu_2cta_warps23"] = (0 | (12 << 4), 296, 400000, 40)
+        loads["alu_4cta_warps23"] = (0 | (12 << 4), 592, 400000, 40)
+        loads["alu_2cta_warps01"] = (0 | (3 << 4), 296, 400000, 40)
+    for name, ld in loads.items():
+        alone = run_load_alone = None
+        # the load alone (duration, and bytes per second for the memory modes)
+        main = torch.cuda.current_stream()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(ld[3]):
+            check(L.saeb_debug_coload(ld[0], ld[1], ld[2], buf.data_ptr(), buf.numel(), sink.data_ptr(), main.cuda_stream), "coload")
+        a1.record(); torch.cuda.synchronize()
+        alone = a0.elapsed_time(a1)
+        g, a = run(ld)
+        gb = ld[1] * 128 * ld[2] * 16 * ld[3] / 1e9 if ld[0] else 0.0
+        res[name] = dict(gemm_ms_per_chunk=round(g, 3), slowdown=round(g / base - 1, 3), load_ms_beside=round(a, 1),
+                         load_ms_alone=round(alone, 1), load_gb=round(gb, 1),
+                         load_gbs_beside=round(gb / (a * 1e-3), 0) if a else None)
+    check(L.saeb_set_option(b"gemm_stages", 0), "stages")
+    return res
+
+
 EXPS = {
+    "coload": lambda: exp_coload(),
+    "ov0": lambda: exp_forward(ctas_per_sm=0),
+    "ov0_s5": lambda: exp_forward(ctas_per_sm=0, stages=5),
+    "ov4_s5": lambda: exp_forward(ctas_per_sm=4, stages=5),
     "shard8": lambda: exp_shard_phases(8, 3),
     "shard8_w8": lambda: exp_shard_phases(8, 3, waves=8),
     "shard1": lambda: exp_shard_phases(1, 0),

@@ -68,6 +68,8 @@ def main():
     ap.add_argument("--prio", default="high", help="comma list of aux-stream priorities: high,low")
     ap.add_argument("--timeline-chunks", type=int, default=2)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--sequential", type=int, default=0, help="1: one stream, phases back to back (every span = the "
+                    "kernel's time with the GPU to itself)")
     ap.add_argument("--fine", type=int, default=0, help="1: also time the individual library calls of update / refinement")
     ap.add_argument("--skip", default="", help="semicolon list of configurations, each a comma list of chain steps that "
                     "are NOT launched (their recorded outputs are used instead): bounds,gbounds,topk,kth,update,exchange; "
@@ -221,6 +223,8 @@ def main():
                 try:
                     sdist.sharded_scan(chunks_iter(min(3, args.chunks)), ops, K, CTX, N)   # warm-up
                     ops.scan = engine.TopActivationScan(lo, hi, args.top, CTX, dev)
+                    if args.sequential:
+                        ops.scan.coresident = ops.coresident
                     ops.count = [0, 0]
                     ops.timeline = []
                     # kth_of_gathered is called 3x per chunk (ext_L, ext_U, tok_thr): one counter covers them
@@ -245,7 +249,8 @@ def main():
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     torch.cuda.synchronize()
                     e0.record()
-                    res = sdist.sharded_scan(chunks_iter(args.chunks), ops, K, CTX, N)
+                    res = sdist.sharded_scan(chunks_iter(args.chunks), ops, K, CTX, N,
+                                             pipelined=False if args.sequential else None)
                     e1.record()
                     torch.cuda.synchronize()
                 finally:
@@ -268,7 +273,7 @@ def main():
                     tl = [t for t in tl if g0[0][2] <= t[2] < g1[0][3]]
                 out = {"tag": args.tag, "skipped": sorted(skip), "world": R, "rank": r, "chunks": args.chunks, "chunk_tokens": chunk,
                        "gemm_stages": stages, "refine_ctas_per_sm": ctas, "aux_priority": prio,
-                       "coresident": args.coresident, "scan_warp": args.scan_warp, "packed_bounds": args.packed_bounds,
+                       "sequential": args.sequential, "coresident": args.coresident, "scan_warp": args.scan_warp, "packed_bounds": args.packed_bounds,
                        "ms": round(ms, 2), "ms_per_chunk": round(ms / args.chunks, 3),
                        "ms_per_1M_tokens": round(ms / tokens * 1048576, 1),
                        "lists_equal_lockstep": same, "flagged_rows": int(ops.status.item()),

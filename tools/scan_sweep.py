@@ -23,6 +23,9 @@ CONFIGS = {
     "nccl_w8": ("nccl", 8, 0, "high", "streams", 0),
     "push_w4": ("push", 4, 0, "high", "streams", 0),
     "push_w8": ("push", 8, 0, "high", "streams", 0),
+    "push_w4_low": ("push", 4, 0, "low", "streams", 0),
+    "nccl_w4_low": ("nccl", 4, 0, "low", "streams", 0),
+    "push_w4_s6": ("push", 4, 0, "high", "streams", 6),
     "push_w4_small": ("push", 4, 4, "high", "streams", 0),
     "push_w8_small": ("push", 8, 4, "high", "streams", 0),
     "push_w4_small_low": ("push", 4, 4, "low", "streams", 0),
