@@ -85,9 +85,10 @@ class EngineOps:
         self._merged = [1, 1]   # how the slot's candidates were merged (already_merged of saeb_refine_candidates)
         self.packed_bounds = os.environ.get("SAEB_SCAN_PACKED_BOUNDS", "1") != "0"
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
-        # SAEB_SCAN_AUX_PRIORITY = high (default: exchange / refine / list update get the first pick of whatever SM
-        # resources the GEMM grid leaves free) | low (GEMM CTAs are placed first at launch boundaries)
-        aux_priority = aux_priority or os.environ.get("SAEB_SCAN_AUX_PRIORITY", "high")
+        # SAEB_SCAN_AUX_PRIORITY = low (default: GEMM CTAs are placed first at launch boundaries; measured 1 % faster
+        # at 8 GPUs, profiles/r02t_scan_sweep_n8_1M.log) | high (exchange / refine / list update get the first pick of
+        # whatever SM resources the GEMM grid leaves free)
+        aux_priority = aux_priority or os.environ.get("SAEB_SCAN_AUX_PRIORITY", "low")
         self.stream_gemm = torch.cuda.Stream(device, priority=0 if aux_priority == "high" else -1)
         self.stream_aux = torch.cuda.Stream(device, priority=-1 if aux_priority == "high" else 0)
         # > 0: the sharded refinement runs as a bounded persistent grid of that many CTAs and its helper launches use
@@ -114,6 +115,9 @@ class EngineOps:
         # chain uses its small-footprint launch shapes (`coresident`).  A kernel that does not fit waits for the next
         # GEMM launch boundary (~1 ms each).  SAEB_SCAN_GEMM_STAGES=0 / SAEB_SCAN_CORESIDENT=0 restore the round-1 shapes.
         self.gemm_stages = int(os.environ.get("SAEB_SCAN_GEMM_STAGES", "5"))
+        # activation prep of chunk c+1 on the small-kernel stream (see _pipelined_loop)
+        # (measured: no gain -- the step is energy-bound, moving work between streams does not remove it; opt-in)
+        self.prep_ahead = os.environ.get("SAEB_SCAN_PREP_AHEAD", "0") != "0"
         self.coresident = os.environ.get("SAEB_SCAN_CORESIDENT", "1") != "0"
 
     def push_gather(self, t, group, channel, slot):
@@ -179,13 +183,33 @@ class EngineOps:
             store[slot] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         return store[slot]
 
-    def local_gemm(self, x, k, slot=0):
-        """tensor-core half of a chunk: activation prep + the fused GEMM launches with candidate selection (enqueued on
-        the current stream).  `local_bounds_finish(slot)` completes it; `local_bounds` = both."""
+    def local_prep(self, x, k, slot=0):
+        """activation prep of a chunk (row scales, fp16 plane, row norms) into the slot's scratch, on the current stream.
+        The pipelined scan runs it on the SMALL-kernel stream one chunk ahead, so that the tensor-core stream holds
+        nothing but GEMM launches; `local_gemm(..., prepped=True)` then skips it."""
         eng, L = self.engine, self._capi.lib()
         enc = self.enc
         x2 = eng._as_2d(x, enc.d_in)
         self._x[slot], self._k[slot] = x2, k
+        if enc.planes < 3:
+            return
+        T = x2.shape[0]
+        dev = x2.device
+        with torch.cuda.device(dev):
+            prep = self._scratch(self._prep, slot, L.saeb_prep_bytes(T, enc.d_in), dev)
+            ldx = x2.stride(0) if T > 1 else enc.d_in
+            self._capi.check(L.saeb_prep_activations(x2.data_ptr(), eng._code(x2), T, ldx, enc.d_in, prep.data_ptr(),
+                                                     torch.cuda.current_stream().cuda_stream), "saeb_prep_activations")
+
+    def local_gemm(self, x, k, slot=0, prepped=False):
+        """tensor-core half of a chunk: activation prep (unless `local_prep` already did it) + the fused GEMM launches
+        with candidate selection (enqueued on the current stream).  `local_bounds_finish(slot)` completes it;
+        `local_bounds` = both."""
+        eng, L = self.engine, self._capi.lib()
+        enc = self.enc
+        if not prepped:
+            self.local_prep(x, k, slot)
+        x2 = self._x[slot]
         T = x2.shape[0]
         if enc.planes < 3:
             vals, idx, _ = eng.encode_topk(x2, enc, k)
@@ -193,14 +217,10 @@ class EngineOps:
             return
         dev = x2.device
         with torch.cuda.device(dev):
-            prep = self._scratch(self._prep, slot, L.saeb_prep_bytes(T, enc.d_in), dev)
+            prep = self._prep[slot]
             ws = self._scratch(self._ws, slot, L.saeb_candidates_workspace_bytes(T, enc.d_in, enc.num_latents, k, 0),
                                dev)
             st = torch.cuda.current_stream().cuda_stream
-            code = eng._code(x2)
-            ldx = x2.stride(0) if T > 1 else enc.d_in
-            self._capi.check(L.saeb_prep_activations(x2.data_ptr(), code, T, ldx, enc.d_in, prep.data_ptr(), st),
-                             "saeb_prep_activations")
             self._capi.check(L.saeb_encode_candidates(prep.data_ptr(), T, 0, T, enc.blob.data_ptr(), enc.d_in,
                                                       enc.num_latents, k, 0, -1, 0.0, ws.data_ptr(), ws.numel(), st),
                              "saeb_encode_candidates")
@@ -221,7 +241,7 @@ class EngineOps:
         dev = x2.device
         if pack_m1 is not None and enc.planes == 3 and self.scan_value_mode == 2 and self.packed_bounds:
             with torch.cuda.device(dev):
-                out = self._scratch(self._lb, slot, T * k * 4, dev)[: T * 2 * pack_m1 * 4].view(torch.float32)
+                out = self._scratch(self._lb, slot, T * max(k, 2 * pack_m1) * 4, dev)[: T * 2 * pack_m1 * 4].view(torch.float32)
                 out = out.view(T, 2 * pack_m1)
                 rc = L.saeb_candidate_bounds_packed(self._prep[slot].data_ptr(), T, 0, T, enc.blob.data_ptr(),
                                                     eng._code(x2), enc.d_in, enc.num_latents, k, 0, -1, int(pack_m1),
@@ -391,7 +411,7 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
 
     window_base = 0
     if not pipelined:
-        fused = (exchange and 2 * m1 <= k_local and getattr(ops, "packed_bounds", False)
+        fused = (exchange and getattr(ops, "packed_bounds", False)
                  and hasattr(ops, "local_gemm") and hasattr(ops, "local_bounds_finish"))
         for x in chunks:
             if fused:   # the same kernels as the pipelined schedules, one after the other
@@ -416,7 +436,7 @@ def sharded_scan(chunks: Iterable[torch.Tensor], ops, k: int, ctx_len: int, num_
             else:
                 _pipelined_loop(chunks, ops, finish, k_local, ctx_len, ops.stream_gemm, ops.stream_aux,
                                 torch.cuda.current_stream(),
-                                pack_m1=m1 if (exchange and 2 * m1 <= k_local) else None)
+                                pack_m1=m1 if exchange else None)
         finally:
             if end is not None:
                 end()
@@ -508,7 +528,26 @@ def _pipelined_loop(chunks, ops, finish, k_local, ctx_len, sg, sa, cur, pack_m1=
             slot_free[slot] = torch.cuda.Event()
             slot_free[slot].record(sa)
 
-    for c, x in enumerate(chunks):
+    # activation prep of chunk c+1 on the small-kernel stream, right behind the chain of chunk c-1 (which is the last
+    # reader of that slot's scratch): the tensor-core stream then holds nothing but GEMM launches
+    prefetch = split and hasattr(ops, "local_prep") and getattr(ops, "prep_ahead", False)
+    prep_done = [None, None]
+
+    def prep_ahead(x, slot):
+        x.record_stream(sa)
+        with torch.cuda.stream(sa):
+            sa.wait_stream(cur)
+            ops.local_prep(x, k_local, slot)
+            prep_done[slot] = torch.cuda.Event()
+            prep_done[slot].record(sa)
+
+    it = iter(chunks)
+    x_next = next(it, None)
+    if prefetch and x_next is not None:
+        prep_ahead(x_next, 0)
+    c = 0
+    while x_next is not None:
+        x, x_next = x_next, next(it, None)
         slot = c & 1
         x.record_stream(sg)
         x.record_stream(sa)
@@ -516,7 +555,11 @@ def _pipelined_loop(chunks, ops, finish, k_local, ctx_len, sg, sa, cur, pack_m1=
             sg.wait_stream(cur)   # whatever produced this chunk on the caller's stream
             if slot_free[slot] is not None:
                 sg.wait_event(slot_free[slot])
-            if split:
+            if prefetch:
+                sg.wait_event(prep_done[slot])
+                ops.local_gemm(x, k_local, slot, prepped=True)
+                bounds = None
+            elif split:
                 ops.local_gemm(x, k_local, slot)
                 bounds = None
             else:
@@ -526,8 +569,11 @@ def _pipelined_loop(chunks, ops, finish, k_local, ctx_len, sg, sa, cur, pack_m1=
         n_tok = x.shape[0] if x.dim() == 2 else x.numel() // x.shape[-1]
         if prev is not None:
             drain(prev)
+        if prefetch and x_next is not None:
+            prep_ahead(x_next, (c + 1) & 1)
         prev = (x, bounds, ready, slot, window_base)
         window_base += n_tok // ctx_len
+        c += 1
     if prev is not None:
         drain(prev)
     cur.wait_stream(sg)
