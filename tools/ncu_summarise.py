@@ -41,13 +41,13 @@ def rep(path, out):
         print(d["Kernel Name"][:80], t)
 
 
-def share(path, out):
+def share(path, out, last=0):
     lines = [l for l in open(path) if not l.startswith("==")]
-    rd = csv.DictReader(io.StringIO("".join(lines)))
+    rows = [r for r in csv.DictReader(io.StringIO("".join(lines))) if r.get("Metric Name") == "gpu__time_duration.sum"]
+    if last:   # only the last `last` launches of the run (e.g. the timed pass of a tool that warms up first)
+        rows = rows[-int(last):]
     per, total, n = {}, 0.0, 0
-    for r in rd:
-        if r.get("Metric Name") != "gpu__time_duration.sum":
-            continue
+    for r in rows:
         v = float(r["Metric Value"].replace(",", ""))
         unit = r["Metric Unit"]
         us = v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit, 1.0)
@@ -69,4 +69,4 @@ def share(path, out):
 
 
 if __name__ == "__main__":
-    {"rep": rep, "share": share}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"rep": rep, "share": share}[sys.argv[1]](*sys.argv[2:])
