@@ -316,6 +316,20 @@ def run_scan(torch, sdist, engine, synth, sae, args, rank, world, dev, barrier, 
             "flagged_rows": int(ops.status.item()),
             "schedule": "sequential (phase timing)" if args.scan_phases else sdist.scan_schedule(world),
             "phase_ms_rank0": {k_: round(v_, 2) for k_, v_ in phases.items()} or None}
+    if world > 1 and not args.scan_phases:
+        # where a chunk's time goes: one SEQUENTIAL pass (every kernel with the GPU to itself, CUDA events between the
+        # phases) over a bounded slice of the same tokens; the timed run above overlaps everything but the GEMM stream
+        n_ph = min(tokens, 8 * chunk)
+        ops.scan = engine.TopActivationScan(lo, hi, n_top, ctx_len, dev)
+        ph = {}
+        sdist.sharded_scan(chunks(n_ph), ops, K, ctx_len, WIDTH, phase_times=ph)
+        per_m = {k_: round(v_ / n_ph * 1048576, 2) for k_, v_ in ph.items()}
+        scan["phase_ms_per_1M_tokens_rank0"] = per_m
+        scan["phase_note"] = (f"sequential diagnostic pass over the first {n_ph} tokens (lists start empty: the refinement "
+                              f"gathers more than in steady state); pipelined, the chunk time is the GEMM stream plus what "
+                              f"the co-resident chain costs it")
+        scan["critical_phase"] = max(per_m, key=per_m.get) if per_m else None
+        scan["pipelined_over_gemm_alone"] = (sms / tokens * 1048576) / per_m["gemm"] if per_m.get("gemm") else None
     if world > 1 and crosscheck_tokens > 0:
         # the token-parallel form of the same scan (full SAE on every rank, tokens split, no per-chunk exchange, one
         # all-gather + merge at the end) must give the same lists -- checked on a bounded slice of the same tokens

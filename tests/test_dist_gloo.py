@@ -64,7 +64,25 @@ class OracleOps:
         return torch.from_numpy(s), torch.from_numpy(w)
 
 
-def _worker(rank, world, port, exact, pipelined, out_dir, lb_width=None):
+class PackedOracleOps(OracleOps):
+    """the ops of the pipelined CUDA path: GEMM and bounds are separate steps and the bounds arrive as ONE unsorted
+    payload [T, 2*m1] (saeb_candidate_bounds_packed); saeb200.dist must not rely on any order inside a shard's lists"""
+
+    packed_bounds = True
+
+    def local_gemm(self, x, k, slot=0, prepped=False):
+        self._lbub = super().local_bounds(x, k, slot)
+
+    def local_bounds_finish(self, slot=0, coresident=False, pack_m1=None):
+        lb, ub = self._lbub
+        if pack_m1 is None:
+            return lb, ub
+        g = torch.Generator().manual_seed(1000 + slot + lb.shape[0])
+        perm_l, perm_u = torch.randperm(pack_m1, generator=g), torch.randperm(pack_m1, generator=g)
+        return torch.cat([lb[:, :pack_m1][:, perm_l], ub[:, :pack_m1][:, perm_u]], -1).contiguous()
+
+
+def _worker(rank, world, port, exact, pipelined, out_dir, lb_width=None, packed=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, os.path.join(root, "multimodal-sae_b200"))
@@ -77,7 +95,7 @@ def _worker(rank, world, port, exact, pipelined, out_dir, lb_width=None):
         p = O.init_params(d, N, k, seed=77)
         x = torch.randn(ctx * 12, d, generator=torch.Generator().manual_seed(78)).to(torch.bfloat16)
         lo, hi = sdist.shard_range(N, world, rank)
-        ops = OracleOps(p, lo, hi, n_top, ctx)
+        ops = (PackedOracleOps if packed else OracleOps)(p, lo, hi, n_top, ctx)
         step = ctx * (2 if pipelined else 4)   # 6 / 3 chunks
         chunks = [x[i:i + step] for i in range(0, x.shape[0], step)]
         res = sdist.sharded_scan(chunks, ops, k, ctx, N, exact=exact, pipelined=pipelined, lb_width=lb_width)
@@ -136,13 +154,16 @@ def _free_port():
     return port
 
 
-@pytest.mark.parametrize("exact,pipelined,lb_width", [(True, False, None), (False, False, None), (True, True, None),
-                                                      (False, True, None), (True, False, 3), (True, True, 4)])
-def test_feature_sharded_scan_two_ranks(tmp_path, exact, pipelined, lb_width):
+@pytest.mark.parametrize("exact,pipelined,lb_width,packed", [
+    (True, False, None, False), (False, False, None, False), (True, True, None, False), (False, True, None, False),
+    (True, False, 3, False), (True, True, 4, False), (True, False, None, True), (True, False, 4, True)])
+def test_feature_sharded_scan_two_ranks(tmp_path, exact, pipelined, lb_width, packed):
     """sequential schedule and the one-chunk-lookahead schedule with asynchronous all-gathers; `lb_width` = columns of
-    the lower-bound lists in exchange 1 (3 = k / world, the narrowest legal width: the result must stay exact)"""
+    the lower-bound lists in exchange 1 (3 = k / world, the narrowest legal width: the result must stay exact);
+    `packed`: the bounds arrive as one UNSORTED payload per shard, as from the fused CUDA kernel"""
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), exact, pipelined, str(tmp_path), lb_width), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), exact, pipelined, str(tmp_path), lb_width, packed), nprocs=world,
+             join=True)
     r0, r1 = (np.load(tmp_path / f"rank{r}.npz") for r in range(world))
     assert np.array_equal(r0["vals"], r1["vals"]) and np.array_equal(r0["win"], r1["win"])  # all ranks agree
     assert r0["vals"].shape == (96, 3)
