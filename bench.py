@@ -316,6 +316,33 @@ def run_scan(torch, sdist, engine, synth, sae, args, rank, world, dev, barrier, 
             "flagged_rows": int(ops.status.item()),
             "schedule": "sequential (phase timing)" if args.scan_phases else sdist.scan_schedule(world),
             "phase_ms_rank0": {k_: round(v_, 2) for k_, v_ in phases.items()} or None}
+    if world > 1 and not args.no_scan_single:
+        # the SAME scan on one GPU in the same run (every rank holds the full SAE for the forward bench and runs it on
+        # its own GPU, max over ranks): the strong-scaling ratio can be formed from this record alone
+        ops1 = sdist.EngineOps(sae.encoder.weight.data, sae.encoder.bias.data, sae.b_dec.data, 0, WIDTH, n_top,
+                               ctx_len, dev, planes=args.planes)
+        chunk1 = ops1.chunk_tokens(1)
+
+        def chunks1(n=tokens):
+            for t0 in range(0, n, chunk1):
+                yield xs[t0:min(n, t0 + chunk1)]
+
+        sdist.sharded_scan(chunks1(min(tokens, 3 * chunk1)), ops1, K, ctx_len, WIDTH, local=True)
+        ops1.scan = engine.TopActivationScan(0, WIDTH, n_top, ctx_len, dev)
+        barrier()
+        e0.record()
+        res1 = sdist.sharded_scan(chunks1(), ops1, K, ctx_len, WIDTH, local=True)
+        e1.record()
+        barrier()
+        ms1 = max_over_ranks(e0.elapsed_time(e1))
+        same1 = torch.tensor([1.0 if (torch.equal(res1.top_win, res.top_win) and torch.equal(res1.top_vals, res.top_vals))
+                              else 0.0], device=dev)
+        torch.distributed.all_reduce(same1, op=torch.distributed.ReduceOp.MIN)
+        scan["single_gpu_same_run"] = {"ms": ms1, "tokens_per_s": tokens / (ms1 * 1e-3),
+                                       "lists_equal_sharded": bool(same1.item() == 1.0)}
+        scan["speedup_over_1_gpu_same_run"] = ms1 / sms
+        del ops1, res1
+        torch.cuda.empty_cache()
     if world > 1 and not args.scan_phases:
         # where a chunk's time goes: one SEQUENTIAL pass (every kernel with the GPU to itself, CUDA events between the
         # phases) over a bounded slice of the same tokens; the timed run above overlaps everything but the GEMM stream
@@ -709,6 +736,8 @@ def main():
     ap.add_argument("--scan-crosscheck-tokens", type=int, default=262144,
                     help="N > 1: tokens on which the feature-sharded lists are compared with the token-parallel form")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scan-single", action="store_true",
+                    help="N > 1: skip the one-GPU run of the same scan (the denominator of the strong-scaling ratio)")
     ap.add_argument("--no-c5", action="store_true")
     ap.add_argument("--no-alt-modes", action="store_true")
     ap.add_argument("--values", default="boundary", choices=["boundary", "exact"],

@@ -533,7 +533,8 @@ struct ChunkPlan {
 };
 struct EncodePlan {
   int pair, cap, num_n_tiles, n_chunks;
-  ChunkPlan chunks[512];
+  static constexpr int MAX_CHUNKS = 4096;   // 38.8 M tokens per call at one 9472-token wave per chunk
+  ChunkPlan chunks[MAX_CHUNKS];
   size_t total_bytes;
 };
 static thread_local int g_chunking = 1;   // 0: one launch for the whole call
@@ -564,7 +565,7 @@ static bool make_plan(EncodePlan& p, long long T, long long N, int k, int pair) 
   p.n_chunks = 0;
   size_t off = 0;
   for (long long t0 = 0; t0 < T; t0 += rows_full) {
-    if (p.n_chunks >= 512) return false;
+    if (p.n_chunks >= EncodePlan::MAX_CHUNKS) return false;
     ChunkPlan& c = p.chunks[p.n_chunks++];
     c.t0 = t0;
     c.rows = (T - t0 < rows_full) ? T - t0 : rows_full;
@@ -810,7 +811,8 @@ int encode_gemm_launch(const void* x_planes, int ap, long long T, long long ld_x
     args.stats = g_stats;
     args.hint_a = (g_l2_hints & 1) ? L2_EVICT_LAST : L2_EVICT_NORMAL;
     args.hint_b = (g_l2_hints & 2) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
-    args.idesc = make_idesc_f16(BM * pair, BN, operand_fmt, operand_fmt);   // 0 = fp16 operands, 1 = bf16
+    // 0 = fp16 operands, 1 = bf16, 2 = bf16 activations (A, in place) against the fp16 weight plane (B)
+    args.idesc = make_idesc_f16(BM * pair, BN, operand_fmt == 2 ? 1 : operand_fmt, operand_fmt == 2 ? 0 : operand_fmt);
     args.row_scale = row_scale ? row_scale + c.t0 : nullptr;
     args.w_unscale = w_unscale;
     args.bias = bias;
