@@ -185,18 +185,6 @@ int saeb_candidate_bounds(const void* prep, int64_t T_total, int64_t t0, int64_t
                           int64_t d, int64_t N, int k, int margin, int64_t clamp_feature, float* lb_out, float* ub_out,
                           void* workspace, size_t workspace_bytes, int coresident, void* stream);
 
-/* bf16 activations straight into the tensor cores: kind::f16 with A = the caller's bf16 rows IN PLACE (TMA reads them
- * where they lie) against B = the fp16 weight plane of the mode-3 blob.  saeb_prep_norms fills only the per-row part of
- * the `prep` buffer (||x||, row scale 1, rounding-error norm 0: bf16 reaches the tensor cores unrounded);
- * saeb_encode_candidates_bf16 is saeb_encode_candidates over x [T_total, ld_x] instead of the fp16 activation plane.  The
- * products are exact either way and a power-of-two row scale commutes with the fp32 accumulation, so the candidate
- * lists are bit-identical to the saeb_prep_activations route -- without writing and re-reading 8 KiB per token.
- * Needs d % 8 == 0, ld_x % 8 == 0 and 16-byte aligned x; refinement / bounds calls take the same `prep` buffer. */
-int saeb_prep_norms(const void* x, int x_dtype, int64_t T, int64_t ld_x, int64_t d, void* prep, void* stream);
-int saeb_encode_candidates_bf16(const void* x, int64_t ld_x, const void* prep, int64_t T_total, int64_t t0, int64_t Tc,
-                                const void* packed, int64_t d, int64_t N, int k, int margin, int64_t clamp_feature,
-                                float clamp_value, void* workspace, size_t workspace_bytes, void* stream);
-
 /* saeb_candidate_bounds as ONE register-resident kernel for the pipelined feature-sharded scan: selects the row's K2
  * best candidates and writes bounds_out [Tc, 2*m1] = the m1 largest lower bounds | the m1 largest upper bounds of the
  * row (zero padded, NOT sorted -- saeb_gathered_bounds does not need an order), the payload of exchange 1.  The merged

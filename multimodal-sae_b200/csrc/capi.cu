@@ -116,8 +116,6 @@ int encode_select_bounds_launch(long long T, long long N, int K2, int m1, const 
                                 float* out_vals, long long* out_idx, float* exch, void* workspace,
                                 size_t workspace_bytes, cudaStream_t stream);
 int set_scan_warp(int v);
-int prep_x_norms_launch(const void* x, long long T, long long d, long long ld_x, float* row_scale, float* xnorm,
-                        float* xdnorm, cudaStream_t stream);
 int coload_launch(int mode, int ctas, long long iters, const void* buf, size_t bytes, float* sink, cudaStream_t stream);
 int scan_warp_enabled();
 int decode_bwd_acts_launch(const float* grad_out, long long ld_g, const long long* idx, long long T, int k,
@@ -409,54 +407,6 @@ int saeb_encode_candidates(const void* prep, int64_t T_total, int64_t t0, int64_
   int rc = encode_gemm_launch(pb + p.x16 + (size_t)t0 * pad8(d) * 2, 1, Tc, pad8(d), (long long)Tc * pad8(d), packed, 1,
                               pad8(d), bias, d, N, K2, clamp_feature, clamp_value, true, nullptr, 0, ws + w.enc,
                               w.total - w.enc, 1, /*operand_fmt=fp16*/ 0,
-                              reinterpret_cast<const float*>(pb + p.row_scale) + t0, trailer, (cudaStream_t)stream);
-  if (rc == 0) g_launches += 1;
-  return rc;
-}
-
-// bf16 activations straight into the tensor cores (A = bf16 in place, B = the fp16 weight plane): row norms only, then
-// the same fused GEMM over the caller's rows.  No fp16 copy of the activations is written or read.
-int saeb_prep_norms(const void* x, int x_dtype, int64_t T, int64_t ld_x, int64_t d, void* prep, void* stream) {
-  g_err[0] = 0;
-  SAEB_NVTX("saeb:prep_norms");
-  SAEB_REQUIRE(x && prep, "prep_norms: null pointer");
-  SAEB_REQUIRE(x_dtype == DT_BF16, "prep_norms: bf16 activations only (other types need saeb_prep_activations)");
-  if (T == 0) return 0;
-  const PrepLayout p = prep_layout(T, d);
-  uint8_t* b = reinterpret_cast<uint8_t*>(prep);
-  int rc = prep_x_norms_launch(x, T, d, ld_x, reinterpret_cast<float*>(b + p.row_scale),
-                               reinterpret_cast<float*>(b + p.xnorm), reinterpret_cast<float*>(b + p.xdnorm),
-                               (cudaStream_t)stream);
-  if (rc == 0) g_launches += 1;
-  return rc;
-}
-
-int saeb_encode_candidates_bf16(const void* x, int64_t ld_x, const void* prep, int64_t T_total, int64_t t0, int64_t Tc,
-                                const void* packed, int64_t d, int64_t N, int k, int margin, int64_t clamp_feature,
-                                float clamp_value, void* workspace, size_t workspace_bytes, void* stream) {
-  g_err[0] = 0;
-  SAEB_NVTX("saeb:gemm");
-  SAEB_REQUIRE(x && prep && packed && workspace, "encode_candidates_bf16: null pointer");
-  SAEB_REQUIRE(t0 >= 0 && Tc >= 0 && t0 + Tc <= T_total, "encode_candidates_bf16: bad row range");
-  SAEB_REQUIRE(clamp_feature < N, "encode_candidates_bf16: clamp_feature out of range");
-  SAEB_REQUIRE(k >= 1 && k <= N && k <= 448, "encode_candidates_bf16: k=%d out of range", k);
-  SAEB_REQUIRE(d % 8 == 0 && ld_x % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
-               "encode_candidates_bf16: TMA reads the rows in place: d and ld_x must be multiples of 8, x 16-byte aligned");
-  if (Tc == 0) return 0;
-  const int K2raw = refine_k2(k, margin);
-  const int K2 = K2raw < N ? K2raw : (int)N;
-  const RefineWs w = refine_ws(Tc, d, N, k, margin);
-  SAEB_REQUIRE(workspace_bytes >= w.total, "encode_candidates_bf16: workspace too small: have %zu need %zu",
-               workspace_bytes, w.total);
-  const PrepLayout p = prep_layout(T_total, d);
-  const uint8_t* pb = reinterpret_cast<const uint8_t*>(prep);
-  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
-  const float* bias = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3));
-  const float* trailer = reinterpret_cast<const float*>(pk + planes_bytes(N, d, 3) + 3 * bias_bytes(N));
-  const uint8_t* xa = reinterpret_cast<const uint8_t*>(x) + (size_t)t0 * ld_x * 2;
-  int rc = encode_gemm_launch(xa, 1, Tc, ld_x, (long long)Tc * ld_x, packed, 1, pad8(d), bias, d, N, K2, clamp_feature,
-                              clamp_value, true, nullptr, 0, ws + w.enc, w.total - w.enc, 1, /*A bf16, B fp16*/ 2,
                               reinterpret_cast<const float*>(pb + p.row_scale) + t0, trailer, (cudaStream_t)stream);
   if (rc == 0) g_launches += 1;
   return rc;

@@ -811,8 +811,10 @@ int encode_gemm_launch(const void* x_planes, int ap, long long T, long long ld_x
     args.stats = g_stats;
     args.hint_a = (g_l2_hints & 1) ? L2_EVICT_LAST : L2_EVICT_NORMAL;
     args.hint_b = (g_l2_hints & 2) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
-    // 0 = fp16 operands, 1 = bf16, 2 = bf16 activations (A, in place) against the fp16 weight plane (B)
-    args.idesc = make_idesc_f16(BM * pair, BN, operand_fmt == 2 ? 1 : operand_fmt, operand_fmt == 2 ? 0 : operand_fmt);
+    // 0 = fp16 operands, 1 = bf16.  Mixed formats (A = bf16 rows in place against the fp16 weight plane, which would
+    // save the fp16 activation plane) are not an option: tcgen05.mma kind::f16 with a_format != b_format raises
+    // "illegal instruction" on sm_100a (tried in round 2, profiles/r02y_pytest_gpu.log).
+    args.idesc = make_idesc_f16(BM * pair, BN, operand_fmt, operand_fmt);
     args.row_scale = row_scale ? row_scale + c.t0 : nullptr;
     args.w_unscale = w_unscale;
     args.bias = bias;

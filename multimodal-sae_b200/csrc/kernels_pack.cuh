@@ -121,28 +121,4 @@ __global__ void prep_x_f16_kernel(const Tin* __restrict__ x, long long T, long l
   if (lane == 0) xdnorm[row] = sqrtf(dsq) * ldexpf(1.0f, e - 14) * (1.0f + 1e-5f);
 }
 
-// Row norms only, for bf16 activations that go into the tensor cores IN PLACE (kind::f16 with A = bf16, B = fp16: no
-// fp16 copy of the activations is written or read).  Same summation order as prep_x_f16_kernel, so ||x|| is bit-identical;
-// the row scale is 1 and the rounding-error norm 0 (bf16 reaches the tensor cores unrounded).
-__global__ void prep_x_norms_kernel(const __nv_bfloat16* __restrict__ x, long long T, long long d, long long ld_x,
-                                    float* __restrict__ row_scale, float* __restrict__ xnorm,
-                                    float* __restrict__ xdnorm) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= T) return;
-  const __nv_bfloat16* xr = x + row * ld_x;
-  float sq = 0.f;
-  for (long long i = lane; i < d; i += 32) {
-    const float v = (float)xr[i];
-    sq = fmaf(v, v, sq);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  if (lane == 0) {
-    row_scale[row] = 1.0f;
-    xnorm[row] = sqrtf(sq) * (1.0f + 1e-5f);
-    xdnorm[row] = 0.f;
-  }
-}
-
 }  // namespace saeb

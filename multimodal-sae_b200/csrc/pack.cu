@@ -145,15 +145,4 @@ int prep_x_f16_launch(const void* x, int x_dtype, long long T, long long d, long
   return 0;
 }
 
-int prep_x_norms_launch(const void* x, long long T, long long d, long long ld_x, float* row_scale, float* xnorm,
-                        float* xdnorm, cudaStream_t stream) {
-  const int wpb = 8;
-  const unsigned blocks = (unsigned)((T + wpb - 1) / wpb);
-  SAEB_CARVEOUT(prep_x_norms_kernel);
-  prep_x_norms_kernel<<<blocks, wpb * 32, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), T, d, ld_x, row_scale,
-                                                      xnorm, xdnorm);
-  SAEB_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
 }  // namespace saeb

@@ -54,9 +54,6 @@ SIGNATURES = {
                                           c_size_t, c_int, c_int, c_void_p]),
     "saeb_candidate_bounds": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int64, c_int64, c_int,
                                       c_int, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
-    "saeb_prep_norms": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
-    "saeb_encode_candidates_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
-                                            c_int64, c_int, c_int, c_int64, c_float, c_void_p, c_size_t, c_void_p]),
     "saeb_candidate_bounds_packed": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int64, c_int64,
                                              c_int, c_int, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "saeb_dense_topk": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),

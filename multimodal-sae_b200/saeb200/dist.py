@@ -83,9 +83,6 @@ class EngineOps:
         self._x, self._k, self._prep, self._ws = [None, None], [0, 0], [None, None], [None, None]
         self._lb, self._ub, self._cached = [None, None], [None, None], [None, None]
         self._merged = [1, 1]   # how the slot's candidates were merged (already_merged of saeb_refine_candidates)
-        self._in_place = [False, False]
-        # bf16 chunks go into the tensor cores in place (saeb_encode_candidates_bf16): no fp16 activation plane
-        self.bf16_in_place = os.environ.get("SAEB_SCAN_BF16_IN_PLACE", "0") != "0"
         self.packed_bounds = os.environ.get("SAEB_SCAN_PACKED_BOUNDS", "1") != "0"
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         # SAEB_SCAN_AUX_PRIORITY = low (default: GEMM CTAs are placed first at launch boundaries; measured 1 % faster
@@ -199,18 +196,10 @@ class EngineOps:
         T = x2.shape[0]
         dev = x2.device
         ldx = x2.stride(0) if T > 1 else enc.d_in
-        # bf16 rows go into the tensor cores in place (A = bf16, B = fp16 plane): only the row norms are prepared
-        self._in_place[slot] = bool(self.bf16_in_place and enc.planes == 3 and x2.dtype == torch.bfloat16
-                                    and enc.d_in % 8 == 0 and ldx % 8 == 0 and x2.data_ptr() % 16 == 0)
         with torch.cuda.device(dev):
             prep = self._scratch(self._prep, slot, L.saeb_prep_bytes(T, enc.d_in), dev)
-            st = torch.cuda.current_stream().cuda_stream
-            if self._in_place[slot]:
-                self._capi.check(L.saeb_prep_norms(x2.data_ptr(), eng._code(x2), T, ldx, enc.d_in, prep.data_ptr(), st),
-                                 "saeb_prep_norms")
-            else:
-                self._capi.check(L.saeb_prep_activations(x2.data_ptr(), eng._code(x2), T, ldx, enc.d_in,
-                                                         prep.data_ptr(), st), "saeb_prep_activations")
+            self._capi.check(L.saeb_prep_activations(x2.data_ptr(), eng._code(x2), T, ldx, enc.d_in, prep.data_ptr(),
+                                                     torch.cuda.current_stream().cuda_stream), "saeb_prep_activations")
 
     def local_gemm(self, x, k, slot=0, prepped=False):
         """tensor-core half of a chunk: activation prep (unless `local_prep` already did it) + the fused GEMM launches
@@ -232,16 +221,9 @@ class EngineOps:
             ws = self._scratch(self._ws, slot, L.saeb_candidates_workspace_bytes(T, enc.d_in, enc.num_latents, k, 0),
                                dev)
             st = torch.cuda.current_stream().cuda_stream
-            if self._in_place[slot]:
-                ldx = x2.stride(0) if T > 1 else enc.d_in
-                self._capi.check(L.saeb_encode_candidates_bf16(x2.data_ptr(), ldx, prep.data_ptr(), T, 0, T,
-                                                               enc.blob.data_ptr(), enc.d_in, enc.num_latents, k, 0, -1,
-                                                               0.0, ws.data_ptr(), ws.numel(), st),
-                                 "saeb_encode_candidates_bf16")
-            else:
-                self._capi.check(L.saeb_encode_candidates(prep.data_ptr(), T, 0, T, enc.blob.data_ptr(), enc.d_in,
-                                                          enc.num_latents, k, 0, -1, 0.0, ws.data_ptr(), ws.numel(), st),
-                                 "saeb_encode_candidates")
+            self._capi.check(L.saeb_encode_candidates(prep.data_ptr(), T, 0, T, enc.blob.data_ptr(), enc.d_in,
+                                                      enc.num_latents, k, 0, -1, 0.0, ws.data_ptr(), ws.numel(), st),
+                             "saeb_encode_candidates")
 
     def local_bounds_finish(self, slot=0, coresident=False, pack_m1=None):
         """candidate merge + per-token bound lists of the chunk given to `local_gemm` -> (lb, ub), both [Tc, k]

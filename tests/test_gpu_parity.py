@@ -509,32 +509,6 @@ def test_feature_sharded_scan_logical_shards(scan_mode, route):
     _capi.check(_capi.lib().saeb_set_option(b"scan_warp", 1), "set_option")
 
 
-@pytest.mark.parametrize("T,d,N,k", [(3000, 1024, 4096, 32), (700, 4096, 8192, 64)])
-def test_bf16_rows_in_place_equal_the_fp16_plane_route(T, d, N, k):
-    """saeb_prep_norms + saeb_encode_candidates_bf16 (kind::f16 with A = the bf16 rows in place, B = the fp16 weight
-    plane) must give the candidates of the saeb_prep_activations route bit for bit: the products are exact either way
-    and the power-of-two row scale commutes with the fp32 accumulation.  Checked on the sorted bound lists and on the
-    refined TopK (rows taken from a strided view: ld_x > d)."""
-    from saeb200 import dist as sdist
-
-    p = O.init_params(d, N, k, seed=61)
-    big = torch.randn(T, d + 64, generator=torch.Generator().manual_seed(62)).to(torch.bfloat16).to(DEV)
-    x = big[:, :d]                                          # row stride d + 64
-    outs = []
-    for in_place in (False, True):
-        ops = sdist.EngineOps(p.W_enc.to(DEV), p.b_enc.to(DEV), p.b_dec.to(DEV), 0, N, 4, 16, DEV)
-        ops.bf16_in_place = in_place
-        ops.local_gemm(x, k)
-        assert ops._in_place[0] == in_place
-        lb, ub = ops.local_bounds_finish(0)
-        vals, _, idx = ops.local_topk(None, None)
-        outs.append((lb.clone(), ub.clone(), vals.clone(), idx.clone()))
-        assert int(ops.status.item()) == 0
-    for a, b in zip(*outs):
-        assert torch.equal(a, b)
-    assert float(outs[1][2].max()) > 0
-
-
 def test_gathered_bounds_kernel():
     """saeb_gathered_bounds = k-th largest gathered lower bound / max((k+1)-th largest upper bound, largest last
     column), every register tier, short unions (R * m1 < k: no restriction = 0)"""

@@ -68,7 +68,6 @@ def main():
     ap.add_argument("--prio", default="high", help="comma list of aux-stream priorities: high,low")
     ap.add_argument("--timeline-chunks", type=int, default=2)
     ap.add_argument("--tag", default="")
-    ap.add_argument("--bf16-in-place", type=int, default=0, help="1: bf16 rows into the tensor cores in place (no fp16 plane)")
     ap.add_argument("--prep-ahead", type=int, default=1, help="0: activation prep on the GEMM stream")
     ap.add_argument("--sequential", type=int, default=0, help="1: one stream, phases back to back (every span = the "
                     "kernel's time with the GPU to itself)")
@@ -221,7 +220,6 @@ def main():
                 ops.coresident = args.coresident != 0
                 ops.packed_bounds = args.packed_bounds != 0
                 ops.prep_ahead = args.prep_ahead != 0
-                ops.bf16_in_place = args.bf16_in_place != 0
                 _capi.check(L.saeb_set_option(b"scan_warp", args.scan_warp), "scan_warp")
                 sdist.dist = fake
                 try:
@@ -277,7 +275,7 @@ def main():
                     tl = [t for t in tl if g0[0][2] <= t[2] < g1[0][3]]
                 out = {"tag": args.tag, "skipped": sorted(skip), "world": R, "rank": r, "chunks": args.chunks, "chunk_tokens": chunk,
                        "gemm_stages": stages, "refine_ctas_per_sm": ctas, "aux_priority": prio,
-                       "sequential": args.sequential, "bf16_in_place": args.bf16_in_place, "prep_ahead": args.prep_ahead, "coresident": args.coresident, "scan_warp": args.scan_warp, "packed_bounds": args.packed_bounds,
+                       "sequential": args.sequential, "prep_ahead": args.prep_ahead, "coresident": args.coresident, "scan_warp": args.scan_warp, "packed_bounds": args.packed_bounds,
                        "ms": round(ms, 2), "ms_per_chunk": round(ms / args.chunks, 3),
                        "ms_per_1M_tokens": round(ms / tokens * 1048576, 1),
                        "lists_equal_lockstep": same, "flagged_rows": int(ops.status.item()),

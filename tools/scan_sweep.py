@@ -25,7 +25,6 @@ CONFIGS = {
     "push_w8": ("push", 8, 0, "high", "streams", 0),
     "push_w4_low": ("push", 4, 0, "low", "streams", 0),
     "push_w4_low_prepahead": ("push", 4, 0, "low", "streams", 0),
-    "push_w4_low_inplace": ("push", 4, 0, "low", "streams", 0),
     "nccl_w4_low": ("nccl", 4, 0, "low", "streams", 0),
     "push_w4_s6": ("push", 4, 0, "high", "streams", 6),
     "push_w4_small": ("push", 4, 4, "high", "streams", 0),
@@ -85,7 +84,6 @@ def main():
         if stages:
             ops.gemm_stages = stages
         ops.prep_ahead = "prepahead" in name
-        ops.bf16_in_place = "inplace" in name
         chunk = ops.chunk_tokens(world, waves)
 
         def chunks(limit=args.tokens):
