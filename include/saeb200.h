@@ -122,7 +122,9 @@ int saeb_encode_topk_refine(const void* x, int x_dtype, int64_t T, int64_t ld_x,
  *   saeb_encode_candidates  rows [t0, t0+Tc): single-pass GEMM with fused candidate selection (tensor bound);
  *   saeb_refine_candidates  same rows: candidate merge + exact fp32 re-evaluation + dense fallback (HBM bound); `x`
  *                           points at row t0 of the original activations; ext_lower = NULL, already_merged = 0 unless
- *                           feature sharded (below).
+ *                           feature sharded (below).  already_merged: 0 = merge the GEMM's candidate lists first,
+ *                           1 = saeb_candidate_bounds already left sorted merged candidates in the workspace,
+ *                           2 = saeb_candidate_bounds_packed left UNSORTED ones (feature-sharded scan form only).
  * Both row-range calls share a scratch buffer of saeb_candidates_workspace_bytes(Tc, ...) bytes. */
 size_t saeb_prep_bytes(int64_t T, int64_t d);
 int saeb_prep_activations(const void* x, int x_dtype, int64_t T, int64_t ld_x, int64_t d, void* prep, void* stream);
