@@ -229,6 +229,8 @@ class Sae(nn.Module):
         # [batch, seq, d] input is centred per (position, channel), i.e. as a [batch, seq * d] matrix
         total_variance = engine.total_variance(x if x.dim() <= 2 else x.reshape(x.shape[0], -1))
         fvu = (sq_err / total_variance).to(torch.float32)
+        if sae_out.dtype != self.dtype:   # the reference computes in the SAE's dtype (sae/sae.py:172, :187-191)
+            sae_out = sae_out.to(self.dtype)
         zero = sae_out.new_tensor(0.0)
         return ForwardOutput(sae_out, top_acts, top_indices, fvu, zero, zero)
 
