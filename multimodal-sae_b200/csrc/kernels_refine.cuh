@@ -225,11 +225,13 @@ refine_body(const XT* __restrict__ x, long long ld_x, const float* __restrict__ 
       st[j] = c;
     }
     if (my_in) atomicAdd(&s_cnt[3], my_in);
+    bool flagged0 = false;   // thread 0: a row is flagged at most once (flag_rows holds one slot per row of the call)
     if (tid == 0 && nv == K2) {   // list possibly too short?  (same test as below)
       const float a_last = a[K2 - 1];
       if (a_last + 1.001f * (xn * dmax + xdn * wmax) + c_eps * xn * wmax >= L) {
         const int slot = atomicAdd(&status[0], 1);
         flag_rows[slot] = (int)t;
+        flagged0 = true;
       }
     }
     __syncthreads();
@@ -284,7 +286,7 @@ refine_body(const XT* __restrict__ x, long long ld_x, const float* __restrict__ 
       if (my_out) atomicAdd(&s_cnt[1], my_out);
       __syncthreads();
       const int nout = s_cnt[1];
-      if (nout > k && tid == 0) {   // more potential members on this shard than output slots: exact dense fallback
+      if (nout > k && tid == 0 && !flagged0) {   // more potential members than output slots: exact dense fallback
         const int slot = atomicAdd(&status[0], 1);
         flag_rows[slot] = (int)t;
       }
@@ -515,9 +517,11 @@ refine_scan_warp_kernel(const XT* __restrict__ x, long long ld_x, const float* _
       if (lane + 32 * s < K2) a_last = fminf(a_last, a[s]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a_last = fminf(a_last, __shfl_xor_sync(full, a_last, o));
+    bool flagged = false;   // lane 0: a row is flagged at most once (flag_rows holds one slot per row of the call)
     if (lane == 0 && nv == K2 && a_last + 1.001f * (xn * dmax + xdn * wmax) + c_eps * xn * wmax >= L) {
       const int slot = atomicAdd(&status[0], 1);
       flag_rows[slot] = (int)t;
+      flagged = true;
     }
     // classification: 1 = certain member that cannot enter its feature's list (not gathered), 3 = certain member that
     // can (exact value wanted), 2 = membership undecided (exact value needed), 0 = out
@@ -605,7 +609,7 @@ refine_scan_warp_kernel(const XT* __restrict__ x, long long ld_x, const float* _
       }
       nout += __popc(mask);
     }
-    if (nout > k && lane == 0) {
+    if (nout > k && lane == 0 && !flagged) {
       const int slot = atomicAdd(&status[0], 1);
       flag_rows[slot] = (int)t;
     }

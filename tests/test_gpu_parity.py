@@ -509,6 +509,43 @@ def test_feature_sharded_scan_logical_shards(scan_mode, route):
     _capi.check(_capi.lib().saeb_set_option(b"scan_warp", 1), "set_option")
 
 
+def test_sharded_refinement_flagged_rows_take_the_exact_dense_fallback():
+    """Feature-sharded scan form of the refinement with more potential members on the shard than output slots (external
+    bounds of 0 make every candidate a certain member, margin 1 gives K2 = k + 1 candidates): every row is flagged and
+    recomputed by the exact dense kernels -- the first 64 by the wide pair, the rest by the overflow kernel, both in
+    their co-resident launch shapes (activation row read from global memory) -- and comes out as the shard's exact
+    TopK with the values as member values."""
+    from saeb200 import _capi, dist as sdist
+
+    L = _capi.lib()
+    N, d, k, T = 512, 256, 16, 200
+    p = O.init_params(d, N, k, seed=71)
+    x = torch.randn(T, d, generator=torch.Generator().manual_seed(72)).to(torch.bfloat16)
+    _capi.check(L.saeb_set_option(b"refine_margin", 1), "set_option")
+    try:
+        for warp in (1, 0):
+            _capi.check(L.saeb_set_option(b"scan_warp", warp), "set_option")
+            ops = sdist.EngineOps(p.W_enc.to(DEV), p.b_enc.to(DEV), p.b_dec.to(DEV), 0, N, 4, 8, DEV)
+            ops.local_gemm(x.to(DEV), k)
+            pb = ops.local_bounds_finish(0, True, pack_m1=8) if warp else ops.local_bounds_finish(0)
+            assert torch.is_tensor(pb) == bool(warp)
+            zeros = torch.zeros(T, dtype=torch.float32, device=DEV)
+            vals, member, idx = ops.local_topk(zeros, zeros)
+            torch.cuda.synchronize()
+            assert int(ops.status.item()) == T            # every row flagged, exactly once
+            ref = O.encode(p, x.float())
+            ri, rv = O.canonical_topk(ref.top_acts, ref.top_indices)
+            gi, gv = O.canonical_topk(vals.cpu(), idx.cpu())
+            tie = O.tie_audit(p, x.float(), k, 2e-5)
+            ok = ~tie
+            assert np.array_equal(gi[ok], ri[ok])
+            np.testing.assert_allclose(gv[ok], rv[ok], rtol=3e-6, atol=1e-7)
+            assert torch.equal(member, vals)
+    finally:
+        _capi.check(L.saeb_set_option(b"refine_margin", 0), "set_option")
+        _capi.check(L.saeb_set_option(b"scan_warp", 1), "set_option")
+
+
 def test_gathered_bounds_kernel():
     """saeb_gathered_bounds = k-th largest gathered lower bound / max((k+1)-th largest upper bound, largest last
     column), every register tier, short unions (R * m1 < k: no restriction = 0)"""
