@@ -73,13 +73,21 @@ class EngineOps:
     pipelined = True
 
     def __init__(self, W_enc_shard, b_enc_shard, b_dec, feat_lo, feat_hi, n_top, ctx_len, device, planes=3,
-                 bucket_cap=256, aux_priority=None):
+                 bucket_cap=256, aux_priority=None, image_n_base=None):
+        """`image_n_base` (optional): the IMAGE form of the scan -- `ctx_len` is then the number of tokens per image row,
+        a feature's score for an image the mean of its TopK-masked activations over the first `image_n_base` positions
+        (engine.TopImageScan; reference pool_max_activations_windows_image, features/constructors.py:88-148).  A mean
+        needs every member's exact value, so the refinement runs with every member exact instead of the scan mode."""
         from . import _capi, engine
 
         self.engine, self._capi = engine, _capi
         self.enc = engine.PackedEncoder.pack(W_enc_shard, b_enc_shard, b_dec, planes)
         self.feat_lo, self.feat_hi = feat_lo, feat_hi
-        self.scan = engine.TopActivationScan(feat_lo, feat_hi, n_top, ctx_len, device, bucket_cap=bucket_cap)
+        if image_n_base is None:
+            self.scan = engine.TopActivationScan(feat_lo, feat_hi, n_top, ctx_len, device, bucket_cap=bucket_cap)
+        else:
+            self.scan = engine.TopImageScan(feat_lo, feat_hi, n_top, ctx_len, int(image_n_base), device,
+                                            bucket_cap=bucket_cap)
         self._x, self._k, self._prep, self._ws = [None, None], [0, 0], [None, None], [None, None]
         self._lb, self._ub, self._cached = [None, None], [None, None], [None, None]
         self._merged = [1, 1]   # how the slot's candidates were merged (already_merged of saeb_refine_candidates)
@@ -97,7 +105,7 @@ class EngineOps:
         self.refine_max_ctas = int(os.environ.get("SAEB_SCAN_REFINE_CTAS", "0"))
         # 2 (default): the refinement only gathers latents that can still enter their feature's list ("scan" mode of
         # the refinement, exact values, rigorous membership); 0: every member of every token's TopK is re-evaluated
-        self.scan_value_mode = int(os.environ.get("SAEB_SCAN_VALUE_MODE", "2"))
+        self.scan_value_mode = int(os.environ.get("SAEB_SCAN_VALUE_MODE", "2")) if image_n_base is None else 0
         # SMs the GEMM grid leaves idle while a multi-rank scan is pipelined (see begin_pipeline).  Measured at 8 GPUs
         # (1 M tokens): 0 -> 4.85 M tokens/s, 4 (with NCCL_MAX_CTAS=4) -> 4.65-4.76 M: off by default
         self.reserve_sms = 0
@@ -309,7 +317,8 @@ class EngineOps:
         return self.engine.gathered_bounds(gathered, m1, k)
 
     def scan_update(self, vals, idx, window_base, tok_thr, member=None):
-        self.scan.update(vals, idx, window_base, tok_thr, None if member is vals else member, idx_base=self.feat_lo)
+        same = member is None or member is vals or member.data_ptr() == vals.data_ptr()   # "every member exact" mode
+        self.scan.update(vals, idx, window_base, tok_thr, None if same else member, idx_base=self.feat_lo)
 
     def scan_finalize(self):
         return self.scan.finalize()

@@ -468,9 +468,14 @@ class TopImageScan(TopActivationScan):
         return self._ws
 
     def update(self, top_acts: torch.Tensor, top_indices: torch.Tensor, image_base: int,
-               tok_thr: Optional[torch.Tensor] = None) -> None:
+               tok_thr: Optional[torch.Tensor] = None, member: Optional[torch.Tensor] = None, idx_base: int = 0) -> None:
         """Feed the TopK output of whole image rows ([n_images * tokens_per_image, k]); the first row is image
-        `image_base`."""
+        `image_base`.  tok_thr [T] (feature-sharded scan): per-token membership threshold, compared with the activations
+        themselves -- a MEAN needs every member's exact value, so the shards must refine with every member exact
+        (`EngineOps.scan_value_mode = 0`); separate member values are refused.  `idx_base` as in TopActivationScan."""
+        if member is not None and member.data_ptr() != top_acts.data_ptr():
+            raise SaebError("TopImageScan averages activations: run the shards with every member exact "
+                            "(scan_value_mode = 0), not with the scan mode's member values")
         L = _capi.lib()
         k = top_acts.shape[-1]
         vals = top_acts.reshape(-1, k)
@@ -487,7 +492,7 @@ class TopImageScan(TopActivationScan):
                     self.flush()
                 v, i = vals[i0 * tpi:i1 * tpi], idx[i0 * tpi:i1 * tpi]
                 check(L.saeb_image_pool(v.data_ptr(), i.data_ptr(), i1 - i0, tpi, k, self.n_base, self.threshold,
-                                        self.feat_lo, self.feat_hi, image_base + i0,
+                                        self.feat_lo - int(idx_base), self.feat_hi - int(idx_base), image_base + i0,
                                         None if tok_thr is None else tok_thr[i0 * tpi:i1 * tpi].data_ptr(),
                                         self.feat_thr.data_ptr(), self.bucket.data_ptr(), self.bucket_cnt.data_ptr(),
                                         self.bucket_cap, self.overflow.data_ptr(), ws.data_ptr(), ws.numel(),

@@ -228,6 +228,44 @@ def test_image_scan_matches_the_per_feature_route():
         torch.testing.assert_close(s[f - lo, :len(order)], sc[order], rtol=1e-6, atol=1e-9)
 
 
+def test_feature_sharded_image_scan_logical_shards():
+    """The image form of the scan under feature sharding (EngineOps(image_n_base=...): TopImageScan per shard, every
+    member of the token's global TopK exact, membership threshold from the gathered values): 4 logical shards on one
+    device reproduce the unsharded TopImageScan over the SAE's own TopK output."""
+    from saeb200 import dist as sdist, engine
+    from saeb200.engine import TopImageScan
+    from test_gpu_parity import _sae_from_params
+
+    N, d, k, tpi, n_base, n_img, n_top, R = 2048, 256, 16, 24, 16, 40, 5, 4
+    p = O.init_params(d, N, k, seed=91)
+    x = torch.randn(n_img * tpi, d, generator=torch.Generator().manual_seed(92)).to(torch.bfloat16).to(DEV)
+    sae = _sae_from_params(p)
+    sae.refine_values = "all"
+    enc = sae.encode(x)
+    ref = TopImageScan(0, N, n_top, tpi, n_base, DEV)
+    ref.update(enc.top_acts, enc.top_indices, 0)
+    ref_s, ref_w = (t.cpu() for t in ref.finalize())
+    shards = [sdist.shard_range(N, R, r) for r in range(R)]
+    ops = [sdist.EngineOps(p.W_enc[lo:hi].to(DEV), p.b_enc[lo:hi].to(DEV), p.b_dec.to(DEV), lo, hi, n_top, tpi, DEV,
+                           image_n_base=n_base) for lo, hi in shards]
+    m1, step = 8, tpi * 10
+    for c0 in range(0, x.shape[0], step):
+        xc = x[c0:c0 + step]
+        bounds = [o.local_bounds(xc, k) for o in ops]
+        g = torch.cat([torch.stack([lb[:, :m1] for lb, _ in bounds], 0), torch.stack([ub[:, :m1] for _, ub in bounds], 0)], -1)
+        ext_L, ext_U = engine.gathered_bounds(g.contiguous(), m1, k)
+        outs = [o.local_topk(ext_L, ext_U) for o in ops]
+        tok_thr = engine.kth_of_gathered(torch.stack([m for _, m, _ in outs], 0), k)
+        for o, (v, m, i) in zip(ops, outs):
+            o.scan_update(v, i, c0 // tpi, tok_thr, m)
+    parts = [o.scan_finalize() for o in ops]
+    got_s = torch.cat([a for a, _ in parts]).cpu()
+    got_w = torch.cat([b for _, b in parts]).cpu()
+    assert torch.equal(got_w, ref_w)
+    torch.testing.assert_close(got_s, ref_s, rtol=1e-6, atol=1e-9)
+    assert int((ref_w >= 0).sum()) > N        # the comparison is not vacuous
+
+
 @pytest.mark.parametrize("planes", [3, 4])
 def test_overlapped_forward_with_bounded_gather_grids_equals_sequential(planes):
     """The two-stream forward (GEMM launches of chunk c+1 beside persistent, bounded gather grids of chunk c) must give
