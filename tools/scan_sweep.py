@@ -110,6 +110,12 @@ def main():
                        transport=(ops._push.transport if ops._push is not None else None))
             if phases:
                 out["phase_ms_rank0"] = {k_: round(v_, 2) for k_, v_ in phases.items()}
+                if world > 1:   # every rank's alone-times: a slow GPU sets the pace of the lockstep protocol
+                    keys = sorted(phases)
+                    mine = torch.tensor([phases[k_] for k_ in keys], dtype=torch.float32, device=dev)
+                    allp = [torch.empty_like(mine) for _ in range(world)]
+                    dist.all_gather(allp, mine)
+                    out["phase_ms_per_rank"] = {k_: [round(float(a[i]), 1) for a in allp] for i, k_ in enumerate(keys)}
             if ref is None:
                 ref = res
                 if world > 1 and args.crosscheck_tokens > 0:
