@@ -60,12 +60,17 @@ def token_slice(num_tokens: int, world: int, rank: int) -> Tuple[int, int]:
 class EngineOps:
     """CUDA implementation of the per-rank steps of the feature-sharded scan (thin calls into the C ABI).
 
-    Interface used by `sharded_scan` (the CPU gloo test injects an oracle-backed object with the same methods):
-      local_bounds(x, k)  -> [Tc, k] per-token lower bounds of this shard's k best latents (descending)
-      local_topk(ext_L)   -> (vals [Tc, k], global ids [Tc, k]) exact local TopK of the chunk given to local_bounds;
-                             `ext_L` [Tc] (optional) = lower bound of each token's GLOBAL k-th value, lets the shard skip
-                             the exact re-evaluation of latents that cannot be in the global TopK
+    Interface used by `sharded_scan` (the CPU gloo tests inject oracle-backed objects with the same methods):
+      local_bounds(x, k, slot)        -> (lb, ub), both [Tc, k] descending: lower / upper bounds a_j -/+ eps_j of the
+                                         shard's k best candidates of the chunk
+      local_topk(ext_L, ext_U, slot)  -> (vals, member, ids), all [Tc, k]: the shard's entries that can be in the token's
+                                         GLOBAL TopK given the bounds of the union (ext_L: lower bound of the global k-th
+                                         value, ext_U: upper bound of the (k+1)-th); member = 3e38 for certain members,
+                                         the exact value for undecided ones; ids as the ops like (scan_update takes them)
       kth_of_gathered, scan_update, scan_finalize
+      optional, used when present: local_gemm + local_bounds_finish(slot, coresident, pack_m1) (GEMM and bounds as
+      separate steps, bounds as one unsorted payload [Tc, 2*m1]), gathered_bounds (fused bounds of the union),
+      push_gather (own transport of the two exchanges), local_prep, begin_pipeline / end_pipeline
     `slot` (0/1) selects one of two private scratch sets, so that the GEMM of chunk c+1 can be in flight on
     `stream_gemm` while chunk c is exchanged / refined / scanned on `stream_aux` (`pipelined = True`).
     """
