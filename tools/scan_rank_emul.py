@@ -68,7 +68,7 @@ def main():
     ap.add_argument("--prio", default="high", help="comma list of aux-stream priorities: high,low")
     ap.add_argument("--timeline-chunks", type=int, default=2)
     ap.add_argument("--tag", default="")
-    ap.add_argument("--prep-ahead", type=int, default=1, help="0: activation prep on the GEMM stream")
+    ap.add_argument("--prep-ahead", type=int, default=0, help="0: activation prep on the GEMM stream")
     ap.add_argument("--sequential", type=int, default=0, help="1: one stream, phases back to back (every span = the "
                     "kernel's time with the GPU to itself)")
     ap.add_argument("--fine", type=int, default=0, help="1: also time the individual library calls of update / refinement")
