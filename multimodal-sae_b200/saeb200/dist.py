@@ -96,6 +96,14 @@ class EngineOps:
         self._x, self._k, self._prep, self._ws = [None, None], [0, 0], [None, None], [None, None]
         self._lb, self._ub, self._cached = [None, None], [None, None], [None, None]
         self._merged = [1, 1]   # how the slot's candidates were merged (already_merged of saeb_refine_candidates)
+        # Candidates kept per token and shard = k + margin (0 = the library default max(48, k/2)).  A shard of an R-way
+        # scan holds ~k/R of a token's TopK, so its list can be far shorter than the unsharded k + 48: k + 8 makes the
+        # GEMM's epilogue and the whole chain cheaper (one rank of 8, ms per chunk: 5.67 -> 5.24, GEMM stream alone
+        # 4.80 -> 4.52; profiles/r02ah_scan_rank_emul_margin.log).  Exactness does not depend on it: a list that could be
+        # too short is flagged and the row recomputed by the exact dense kernels.  Fixed per slot at local_prep time.
+        self.margin_sharded = int(os.environ.get("SAEB_SCAN_MARGIN", "8"))
+        self.margin = 0
+        self._margin = [0, 0]
         self.packed_bounds = os.environ.get("SAEB_SCAN_PACKED_BOUNDS", "1") != "0"
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         # SAEB_SCAN_AUX_PRIORITY = low (default: GEMM CTAs are placed first at launch boundaries; measured 1 % faster
@@ -170,6 +178,7 @@ class EngineOps:
         if self.coresident:
             self._capi.check(self._capi.lib().saeb_set_option(b"gemm_stages", self.gemm_stages), "set_option")
             self.scan.coresident = True
+        self.margin = self.margin_sharded if world > 1 else 0
 
     def chunk_tokens(self, world: int, waves: Optional[int] = None) -> int:
         """Tokens per scan chunk = `waves` full single-wave GEMM launches (256-row tiles on half of the CTA pairs the
@@ -183,6 +192,7 @@ class EngineOps:
         return waves * 256 * max(1, (sms // 2) // 2)
 
     def end_pipeline(self):
+        self.margin = 0
         self._capi.check(self._capi.lib().saeb_set_option(b"reserve_sms", 0), "set_option")
         if self.coresident:
             self._capi.check(self._capi.lib().saeb_set_option(b"gemm_stages", 0), "set_option")
@@ -203,7 +213,7 @@ class EngineOps:
         eng, L = self.engine, self._capi.lib()
         enc = self.enc
         x2 = eng._as_2d(x, enc.d_in)
-        self._x[slot], self._k[slot] = x2, k
+        self._x[slot], self._k[slot], self._margin[slot] = x2, k, int(self.margin)
         if enc.planes < 3:
             return
         T = x2.shape[0]
@@ -231,11 +241,11 @@ class EngineOps:
         dev = x2.device
         with torch.cuda.device(dev):
             prep = self._prep[slot]
-            ws = self._scratch(self._ws, slot, L.saeb_candidates_workspace_bytes(T, enc.d_in, enc.num_latents, k, 0),
+            ws = self._scratch(self._ws, slot, L.saeb_candidates_workspace_bytes(T, enc.d_in, enc.num_latents, k, self._margin[slot]),
                                dev)
             st = torch.cuda.current_stream().cuda_stream
             self._capi.check(L.saeb_encode_candidates(prep.data_ptr(), T, 0, T, enc.blob.data_ptr(), enc.d_in,
-                                                      enc.num_latents, k, 0, -1, 0.0, ws.data_ptr(), ws.numel(), st),
+                                                      enc.num_latents, k, self._margin[slot], -1, 0.0, ws.data_ptr(), ws.numel(), st),
                              "saeb_encode_candidates")
 
     def local_bounds_finish(self, slot=0, coresident=False, pack_m1=None):
@@ -257,7 +267,7 @@ class EngineOps:
                 out = self._scratch(self._lb, slot, T * max(k, 2 * pack_m1) * 4, dev)[: T * 2 * pack_m1 * 4].view(torch.float32)
                 out = out.view(T, 2 * pack_m1)
                 rc = L.saeb_candidate_bounds_packed(self._prep[slot].data_ptr(), T, 0, T, enc.blob.data_ptr(),
-                                                    eng._code(x2), enc.d_in, enc.num_latents, k, 0, -1, int(pack_m1),
+                                                    eng._code(x2), enc.d_in, enc.num_latents, k, self._margin[slot], -1, int(pack_m1),
                                                     out.data_ptr(), self._ws[slot].data_ptr(), self._ws[slot].numel(),
                                                     torch.cuda.current_stream().cuda_stream)
             if rc == 0:
@@ -271,7 +281,7 @@ class EngineOps:
             ub = self._scratch(self._ub, slot, T * k * 4, dev)[: T * k * 4].view(torch.float32).view(T, k)
             st = torch.cuda.current_stream().cuda_stream
             self._capi.check(L.saeb_candidate_bounds(prep.data_ptr(), T, 0, T, enc.blob.data_ptr(), eng._code(x2),
-                                                     enc.d_in, enc.num_latents, k, 0, -1, lb.data_ptr(), ub.data_ptr(),
+                                                     enc.d_in, enc.num_latents, k, self._margin[slot], -1, lb.data_ptr(), ub.data_ptr(),
                                                      ws.data_ptr(), ws.numel(), 1 if coresident else 0, st),
                              "saeb_candidate_bounds")
         return lb, ub
@@ -304,7 +314,7 @@ class EngineOps:
             st = torch.cuda.current_stream().cuda_stream
             self._capi.check(refine(
                 x2.data_ptr(), eng._code(x2), x2.stride(0) if T > 1 else enc.d_in, self._prep[slot].data_ptr(), T, 0, T,
-                enc.blob.data_ptr(), enc.W_enc.data_ptr(), enc.d_in, enc.num_latents, k, 0, -1, 0.0,
+                enc.blob.data_ptr(), enc.W_enc.data_ptr(), enc.d_in, enc.num_latents, k, self._margin[slot], -1, 0.0,
                 None if ext_L is None else ext_L.data_ptr(),
                 ext_U.data_ptr() if (sharded and mode == 2) else None,
                 self.scan.feat_thr.data_ptr() if mode == 2 else None, int(self._merged[slot]), vals.data_ptr(),

@@ -68,6 +68,9 @@ def main():
     ap.add_argument("--prio", default="high", help="comma list of aux-stream priorities: high,low")
     ap.add_argument("--timeline-chunks", type=int, default=2)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--shard-margin", type=int, default=-1, help="EngineOps.margin_sharded (-1 = its default)")
+    ap.add_argument("--margin", type=int, default=0, help="option refine_margin: candidates kept per row = k + margin "
+                    "(0 = default max(48, k/2)); smaller lists are safe (short lists are flagged and recomputed exactly)")
     ap.add_argument("--prep-ahead", type=int, default=0, help="0: activation prep on the GEMM stream")
     ap.add_argument("--sequential", type=int, default=0, help="1: one stream, phases back to back (every span = the "
                     "kernel's time with the GPU to itself)")
@@ -85,6 +88,7 @@ def main():
     from saeb200 import _capi, dist as sdist, engine, synth
 
     L = _capi.lib()
+    _capi.check(L.saeb_set_option(b"refine_margin", args.margin), "refine_margin")
     dev = torch.device("cuda", 0)
     R, r = args.world, args.rank
     sae = synth.make_sae(D, N, K, dev, seed=1234)
@@ -220,6 +224,8 @@ def main():
                 ops.coresident = args.coresident != 0
                 ops.packed_bounds = args.packed_bounds != 0
                 ops.prep_ahead = args.prep_ahead != 0
+                if args.shard_margin >= 0:
+                    ops.margin_sharded = args.shard_margin
                 _capi.check(L.saeb_set_option(b"scan_warp", args.scan_warp), "scan_warp")
                 sdist.dist = fake
                 try:
@@ -275,7 +281,7 @@ def main():
                     tl = [t for t in tl if g0[0][2] <= t[2] < g1[0][3]]
                 out = {"tag": args.tag, "skipped": sorted(skip), "world": R, "rank": r, "chunks": args.chunks, "chunk_tokens": chunk,
                        "gemm_stages": stages, "refine_ctas_per_sm": ctas, "aux_priority": prio,
-                       "sequential": args.sequential, "prep_ahead": args.prep_ahead, "coresident": args.coresident, "scan_warp": args.scan_warp, "packed_bounds": args.packed_bounds,
+                       "sequential": args.sequential, "margin": args.margin, "shard_margin": args.shard_margin, "prep_ahead": args.prep_ahead, "coresident": args.coresident, "scan_warp": args.scan_warp, "packed_bounds": args.packed_bounds,
                        "ms": round(ms, 2), "ms_per_chunk": round(ms / args.chunks, 3),
                        "ms_per_1M_tokens": round(ms / tokens * 1048576, 1),
                        "lists_equal_lockstep": same, "flagged_rows": int(ops.status.item()),

@@ -25,6 +25,9 @@ CONFIGS = {
     "push_w8": ("push", 8, 0, "high", "streams", 0),
     "push_w4_low": ("push", 4, 0, "low", "streams", 0),
     "push_w4_low_prepahead": ("push", 4, 0, "low", "streams", 0),
+    "push_w4_low_m48": ("push", 4, 0, "low", "streams", 0),
+    "push_w4_low_m16": ("push", 4, 0, "low", "streams", 0),
+    "push_w4_low_m4": ("push", 4, 0, "low", "streams", 0),
     "nccl_w4_low": ("nccl", 4, 0, "low", "streams", 0),
     "push_w4_s6": ("push", 4, 0, "high", "streams", 6),
     "push_w4_small": ("push", 4, 4, "high", "streams", 0),
@@ -84,6 +87,12 @@ def main():
         if stages:
             ops.gemm_stages = stages
         ops.prep_ahead = "prepahead" in name
+        if "_m48" in name:
+            ops.margin_sharded = 0
+        if "_m4" in name and "_m48" not in name:
+            ops.margin_sharded = 4
+        if "_m16" in name:
+            ops.margin_sharded = 16
         chunk = ops.chunk_tokens(world, waves)
 
         def chunks(limit=args.tokens):
