@@ -97,7 +97,7 @@ class EngineOps:
         self._lb, self._ub, self._cached = [None, None], [None, None], [None, None]
         self._merged = [1, 1]   # how the slot's candidates were merged (already_merged of saeb_refine_candidates)
         # Candidates kept per token and shard = k + margin (0 = the library default max(48, k/2)).  A shard of an R-way
-        # scan holds ~k/R of a token's TopK, so its list can be far shorter than the unsharded k + 48: k + 8 makes the
+        # scan (R >= 4) holds ~k/R of a token's TopK, so its list can be far shorter than the unsharded k + 48: k + 8 makes the
         # GEMM's epilogue and the whole chain cheaper (one rank of 8, ms per chunk: 5.67 -> 5.24, GEMM stream alone
         # 4.80 -> 4.52; profiles/r02ah_scan_rank_emul_margin.log).  Exactness does not depend on it: a list that could be
         # too short is flagged and the row recomputed by the exact dense kernels.  Fixed per slot at local_prep time.
@@ -178,7 +178,7 @@ class EngineOps:
         if self.coresident:
             self._capi.check(self._capi.lib().saeb_set_option(b"gemm_stages", self.gemm_stages), "set_option")
             self.scan.coresident = True
-        self.margin = self.margin_sharded if world > 1 else 0
+        self.margin = self.margin_sharded if world >= 4 else 0   # measured at 8 ranks; 2 ranks keep the default lists
 
     def chunk_tokens(self, world: int, waves: Optional[int] = None) -> int:
         """Tokens per scan chunk = `waves` full single-wave GEMM launches (256-row tiles on half of the CTA pairs the
